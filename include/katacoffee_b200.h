@@ -1,0 +1,203 @@
+/*
+ * katacoffee_b200.h -- C ABI of the B200-native KataCoffee leaf-evaluation hot path.
+ *
+ * This is the drop-in boundary: what a `USE_BACKEND=B200` build of the reference would link
+ * (cpp/neuralnet/b200backend.cpp implementing cpp/neuralnet/nninterface.h:31-171 forwards to
+ * these entry points; see INTEGRATION.md for the shim) plus the batched rules/features/hash
+ * entry points that have no counterpart in the reference (it runs them on the CPU one position
+ * at a time: cpp/game/board.cpp, cpp/game/boardhistory.cpp, cpp/neuralnet/nninputs.cpp).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; kc_last_error() returns the
+ *    thread-local message (the C++ shim rethrows it as StringError, the reference's convention,
+ *    cpp/neuralnet/nneval.cpp:327-330).
+ *  - no C++ or torch types cross the ABI: plain pointers and sizes only.
+ *  - pointers are HOST pointers unless the parameter name ends in `_dev`; the library owns all
+ *    device memory and frees it in the matching _destroy.
+ *  - kc_handle / kc_games own a CUDA stream and may be used by one thread at a time (mirrors
+ *    nninterface.h:18-20: a ComputeHandle is used by exactly one server thread); kc_model is
+ *    immutable and shareable (mirrors LoadedModel, nninterface.h:42-43).
+ *  - there is no CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef KATACOFFEE_B200_H_
+#define KATACOFFEE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_MAX_LEN 10                                        /* cpp/game/board.h:15  */
+#define KC_MAX_ARR_SIZE ((KC_MAX_LEN + 1) * (KC_MAX_LEN + 2) + 1) /* board.h:120-124 */
+#define KC_NUM_SPATIAL_V1 15                                 /* SURVEY.md 8.1-F      */
+#define KC_NUM_GLOBAL_V1 1
+#define KC_MAX_DEVICE_LEN 7  /* bitboard kernels: H*(W+1) <= 64 */
+
+typedef struct kc_ctx kc_ctx;
+typedef struct kc_model kc_model;
+typedef struct kc_handle kc_handle;
+typedef struct kc_games kc_games;
+
+const char* kc_last_error(void);
+int kc_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Context.  Replaces NeuralNet::globalInitialize + createComputeContext (nninterface.h:33,52-66)
+ * and Board::initHash (cpp/game/board.cpp:134-178: the Zobrist tables are generated on the host by
+ * the same MD5 -> SHA-256 -> xorshift1024* + PCG32 chain and uploaded to __constant__ memory).
+ * ------------------------------------------------------------------------------------------- */
+int kc_device_count(int* count);
+int kc_ctx_create(int device, kc_ctx** out);
+int kc_ctx_destroy(kc_ctx* ctx);
+/* Host-side Zobrist tables (uint64 pairs hash0,hash1): board [133][4][2] (colour index 0..3, empty
+ * and wall zero), player [4][2], size_x [11][2], size_y [11][2].  No GPU needed. */
+int kc_zobrist_tables(uint64_t* board, uint64_t* player, uint64_t* size_x, uint64_t* size_y);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model description: POD mirror of ModelDesc (cpp/neuralnet/desc.h:13-304).  Weight layouts are
+ * what desc.cpp produces: conv oc,ic,y,x (desc.cpp:131-152), matmul ic,oc (desc.cpp:284-299).
+ * Activations: 0 identity, 1 ReLU, 2 Mish (cpp/neuralnet/activations.h:4-6).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int32_t convYSize, convXSize, inChannels, outChannels; const float* weights; } kc_conv_desc;
+typedef struct { int32_t numChannels; float epsilon; int32_t hasScale, hasBias;
+                 const float *mean, *variance, *scale, *bias; } kc_bn_desc;
+typedef struct { int32_t inChannels, outChannels; const float* weights; } kc_matmul_desc;
+typedef struct { int32_t numChannels; int32_t pad_; const float* weights; } kc_matbias_desc;
+typedef struct {
+  int32_t kind; /* 0 ordinary, 2 global pooling (desc.h:173-175) */
+  int32_t preActivation, gpoolActivation, midActivation;
+  kc_bn_desc preBN;
+  kc_conv_desc regularConv;
+  kc_conv_desc gpoolConv;        /* kind 2 only */
+  kc_bn_desc gpoolBN;            /* kind 2 only */
+  kc_matmul_desc gpoolToBiasMul; /* kind 2 only */
+  kc_bn_desc midBN;
+  kc_conv_desc finalConv;
+} kc_block_desc;
+typedef struct {
+  int32_t version, numInputChannels, numInputGlobalChannels, numBlocks;
+  int32_t trunkNumChannels, midNumChannels, regularNumChannels, gpoolNumChannels;
+  int32_t trunkTipActivation, g1Activation, p1Activation, v1Activation, v2Activation, pad_;
+  kc_conv_desc initialConv;
+  kc_matmul_desc initialMatMul;
+  const kc_block_desc* blocks;
+  kc_bn_desc trunkTipBN;
+  kc_conv_desc p1Conv, g1Conv;   /* policy head (desc.h:216-240), Coffee shapes: p2Conv out = 4 */
+  kc_bn_desc g1BN;
+  kc_matmul_desc gpoolToBiasMul;
+  kc_bn_desc p1BN;
+  kc_conv_desc p2Conv;
+  kc_conv_desc v1Conv;           /* value head (desc.h:242-269): v3 out = 2, sv3 out = 2 */
+  kc_bn_desc v1BN;
+  kc_matmul_desc v2Mul;
+  kc_matbias_desc v2Bias;
+  kc_matmul_desc v3Mul;
+  kc_matbias_desc v3Bias;
+  kc_matmul_desc sv3Mul;
+  kc_matbias_desc sv3Bias;
+  kc_conv_desc vOwnershipConv;
+} kc_model_desc;
+
+/* Replaces NeuralNet::loadModelFile + the backend Model constructor (nninterface.h:42,
+ * eigenbackend.cpp:1380-1420): validates shapes, folds BN (scale/sqrt(var+eps), bias-mean*scale),
+ * re-tiles and converts the weights for both device paths. */
+int kc_model_create(kc_ctx* ctx, const kc_model_desc* desc, kc_model** out);
+int kc_model_destroy(kc_model* model);
+
+/* ---------------------------------------------------------------------------------------------
+ * Compute handle.  Replaces createComputeHandle / createInputBuffers / getOutput
+ * (nninterface.h:77-117).
+ * ------------------------------------------------------------------------------------------- */
+#define KC_FLAG_FP32_CHECK 1u       /* CUDA-core fp32 path (1e-4 gate); default is bf16 tcgen05 */
+#define KC_FLAG_INPUTS_NHWC 2u      /* kc_forward spatial rows are NHWC (inputsUseNHWC)          */
+#define KC_FLAG_SYM_PERMUTE_DIRS 4u /* play mode, SURVEY.md 8.1-K: also permute direction channels */
+
+int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLen, int nnYLen,
+                     unsigned flags, kc_handle** out);
+int kc_handle_destroy(kc_handle* h);
+int kc_handle_uses_bf16(const kc_handle* h); /* isUsingFP16 analogue, nninterface.h:88 */
+/* NeuralNet::getOutput (nninterface.h:112-117).  Inputs: spatial [n][15*H*W] fp32 (NCHW, or NHWC
+ * with KC_FLAG_INPUTS_NHWC), global [n][1], symmetry [n] in 0..7 (NULL = 0).  Outputs are raw
+ * logits, inverse-symmetrised, NNPos order (cpp/neuralnet/nninputs.cpp:6-14): policy [n][4*H*W],
+ * value [n][2] (win, loss), misc [n][2] (varTimeLeft, shorttermWinlossError pre-softplus),
+ * ownership [n][H*W] or NULL.  Synchronous: results are valid on return.  0 < n <= maxBatch. */
+int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, const int8_t* symmetry,
+               float* policy, float* value, float* misc, float* ownership);
+/* Copies the outputs of the last device-resident evaluation (kc_games_eval) to the host. */
+int kc_handle_read_outputs(kc_handle* h, int n, float* policy, float* value, float* misc, float* ownership);
+/* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
+int64_t kc_handle_launch_count(const kc_handle* h);
+/* Sum (ms) and count of the device durations of the trunk-kernel launches issued through this
+ * handle since the previous call (CUDA events recorded on the launching stream); synchronises. */
+int kc_handle_trunk_time(kc_handle* h, float* sumMs, int* count);
+/* Self-test of the tcgen05 descriptor conventions the trunk kernel relies on: D[128][N] =
+ * A[shift:shift+128][K] * B[N][K]^T on the tensor core (A, B bf16 bit patterns, D fp32). */
+int kc_selftest_umma(kc_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int rowsA, int N, int K, int shift);
+
+/* Layer-level hooks = NeuralNet::testEvaluateConv / BatchNorm / ResidualBlock /
+ * GlobalPoolingResidualBlock (nninterface.h:127-169), fp32 path; buffers NCHW or NHWC. */
+int kc_test_conv(kc_ctx* ctx, const kc_conv_desc* d, int n, int xLen, int yLen, int useNHWC,
+                 const float* in, float* out);
+int kc_test_batchnorm(kc_ctx* ctx, const kc_bn_desc* d, int activation, int n, int xLen, int yLen,
+                      int useNHWC, const float* in, const float* mask, float* out);
+int kc_test_resblock(kc_ctx* ctx, const kc_block_desc* d, int n, int xLen, int yLen, int useNHWC,
+                     const float* in, const float* mask, float* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched games: device-resident Board + BoardHistory for G concurrent games.
+ * Semantics per game are exactly the reference's (ledger 8.1):
+ * Board::isLegal (board.cpp:185-227), playMoveAssumeLegal (:427-435), checkGameEnd (:376-383),
+ * BoardHistory::makeBoardMoveAssumeLegal (boardhistory.cpp:157-176), getSitHash (board.cpp:288-292),
+ * NNInputs::fillRowV1 (nninputs.cpp:508-657), copyInputsWithSymmetry (nninputs.cpp:252-357).
+ * ------------------------------------------------------------------------------------------- */
+int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen, kc_games** out);
+int kc_games_destroy(kc_games* g);
+/* All games back to the empty board, black to move; game i gets id firstGameId + i.  `autoRefill`
+ * != 0 makes kc_games_step restart a finished game with a fresh id (ids continue after the last
+ * one handed out) instead of leaving it finished. */
+int kc_games_reset(kc_games* g, uint64_t seed, uint64_t firstGameId, int autoRefill);
+/* Overwrites games [g0, g0+n) with explicit positions (test hook): stones [n][H*W] (0 empty,
+ * 1 black, 2 white), nextPla [n], moves [n][5][2] = last five (pos, pla) pairs oldest first with
+ * pos = -1 for "none" (pos is a policy index dir*H*W + y*W + x), numTurns [n]. */
+int kc_games_load(kc_games* g, int g0, int n, const int8_t* stones, const int8_t* nextPla,
+                  const int16_t* moves, const int32_t* numTurns);
+/* One ply for every unfinished game.  movePos [G] (policy index, -1 = do nothing) or NULL for
+ * the counter-RNG random-legal move of SURVEY.md 8(d):
+ *   r = splitmix64(seed ^ gameId*0x9E3779B97F4A7C15 ^ ply), move = (r mod popcount)-th legal bit.
+ * Illegal movePos leaves the game unchanged and sets bit 15 of its status word.
+ * Outputs (any may be NULL), describing the position AFTER the move:
+ *   legal   [G][ceil(4*H*W/32)]  isLegal mask of the player to move, bit = policy index
+ *   status  [G]                  bits 0-7 numTurns, 8 finished, 9-10 winner, 11-12 next player
+ *   sitHash [G][2]               Board::getSitHash(next player)
+ *   played  [G]                  policy index played this ply (-1 if none)
+ *   gameIds [G]                  id of the game occupying each lane after the step */
+int kc_games_step(kc_games* g, const int16_t* movePos, uint32_t* legal, uint32_t* status,
+                  uint64_t* sitHash, int16_t* played, uint64_t* gameIds);
+/* NNInputs::fillRowV1 for every game's current position (+ optional per-game symmetry, exactly
+ * copyInputsWithSymmetry).  layout 0 = NCHW, 1 = NHWC; planes [G][15*H*W] fp32; global [G][1]. */
+int kc_games_features(kc_games* g, int layout, const int8_t* symmetry, float* planes, float* global);
+/* Device-resident evaluation of the current positions: V1 planes are generated in bf16 (or fp32
+ * for a KC_FLAG_FP32_CHECK handle) directly into the handle's input buffer and the net is run;
+ * nothing crosses PCIe.  Read the results with kc_handle_read_outputs. numGames <= maxBatch. */
+int kc_games_eval(kc_games* g, kc_handle* h, const int8_t* symmetry);
+/* Fused hot-path step used by bench.py: [random-legal step (+refill) -> planes -> forward] x plies,
+ * all on the device, no host synchronisation between plies.  h may be NULL (rules+features only:
+ * fp32 NCHW planes, legal masks, status words and sit-hashes are written to device buffers owned
+ * by the games object every ply). */
+typedef struct {
+  uint64_t steps;      /* game-steps executed (one per live game per ply) */
+  uint64_t evals;      /* positions sent through the net */
+  uint64_t gamesFinished, blackWins, whiteWins, draws;
+  uint64_t checksum;   /* XOR of sitHash0 of every position reached (cheap cross-check vs oracle) */
+} kc_stats;
+int kc_games_run(kc_games* g, kc_handle* h, int plies, kc_stats* statsAccum);
+int64_t kc_games_launch_count(const kc_games* g);
+/* Average device time in ms per ply of the rules+features kernel in the last kc_games_run. */
+float kc_games_last_kernel_ms(const kc_games* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

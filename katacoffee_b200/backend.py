@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's backend interface for this path.
+
+Function names and argument meaning follow cpp/neuralnet/nninterface.h (createComputeContext :52,
+createComputeHandle :77, getOutput :112, testEvaluate* :127-169) so the parity tests read like the
+reference's own tests/testnn.cpp; every call goes through the C ABI (capi) and raises KCError
+(the StringError analogue) on failure.  `Games` wraps the batched rules/features entry points.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib, ptr
+
+
+class ComputeContext:
+    def __init__(self, device=0):
+        self._p = C.c_void_p()
+        check(lib().kc_ctx_create(device, C.byref(self._p)))
+
+    def close(self):
+        if self._p:
+            lib().kc_ctx_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+def createComputeContext(gpuIdx=0):
+    return ComputeContext(gpuIdx)
+
+
+class LoadedModel:
+    def __init__(self, ctx, model):
+        """model: katacoffee_b200.modeldesc.Model (or anything with a .desc ModelDesc)."""
+        self.ctx, self.model = ctx, model
+        self._p = C.c_void_p()
+        check(lib().kc_model_create(ctx._p, C.byref(model.desc), C.byref(self._p)))
+
+    def close(self):
+        if self._p:
+            lib().kc_model_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+class ComputeHandle:
+    def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False):
+        self.ctx, self.loadedModel = ctx, loadedModel
+        self.maxBatch, self.nnXLen, self.nnYLen = maxBatchSize, nnXLen, nnYLen
+        self.inputsUseNHWC = inputsUseNHWC
+        flags = (capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_INPUTS_NHWC if inputsUseNHWC else 0)
+        self._p = C.c_void_p()
+        check(lib().kc_handle_create(ctx._p, loadedModel._p, maxBatchSize, nnXLen, nnYLen, flags, C.byref(self._p)))
+
+    def isUsingBF16(self):
+        return bool(lib().kc_handle_uses_bf16(self._p))
+
+    def launchCount(self):
+        return int(lib().kc_handle_launch_count(self._p))
+
+    def trunkTime(self):
+        s, n = C.c_float(), C.c_int()
+        check(lib().kc_handle_trunk_time(self._p, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def readOutputs(self, n, ownership=True):
+        hw = self.nnXLen * self.nnYLen
+        policy = np.empty((n, 4 * hw), np.float32)
+        value = np.empty((n, 2), np.float32)
+        misc = np.empty((n, 2), np.float32)
+        own = np.empty((n, hw), np.float32) if ownership else None
+        check(lib().kc_handle_read_outputs(self._p, n, ptr(policy), ptr(value), ptr(misc), ptr(own)))
+        return policy, value, misc, own
+
+    def close(self):
+        if self._p:
+            lib().kc_handle_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False):
+    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC)
+
+
+def getOutput(handle, rowSpatial, rowGlobal, symmetry=None, ownership=True, out=None):
+    """NeuralNet::getOutput: rowSpatial [n, 15*H*W] fp32, rowGlobal [n, 1], symmetry [n] int8.
+    Returns raw logits (policy [n,4HW], value [n,2], misc [n,2], ownership [n,HW])."""
+    n = rowSpatial.shape[0]
+    hw = handle.nnXLen * handle.nnYLen
+    rowSpatial = np.ascontiguousarray(rowSpatial, np.float32).reshape(n, 15 * hw)
+    rowGlobal = np.ascontiguousarray(rowGlobal, np.float32).reshape(n, 1)
+    sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8)
+    if out is None:
+        policy = np.empty((n, 4 * hw), np.float32)
+        value = np.empty((n, 2), np.float32)
+        misc = np.empty((n, 2), np.float32)
+        own = np.empty((n, hw), np.float32) if ownership else None
+    else:
+        policy, value, misc, own = out
+    check(lib().kc_forward(handle._p, n, ptr(rowSpatial), ptr(rowGlobal), ptr(sym), ptr(policy), ptr(value), ptr(misc), ptr(own)))
+    return policy, value, misc, own
+
+
+def _desc_conv(d):
+    w = np.ascontiguousarray(d["weights"], np.float32)
+    return capi.ConvDesc(d["convYSize"], d["convXSize"], d["inChannels"], d["outChannels"], w.ctypes.data_as(capi.c_float_p)), w
+
+
+def _desc_bn(d):
+    arrs = [np.ascontiguousarray(d[k], np.float32) for k in ("mean", "variance", "scale", "bias")]
+    return capi.BNDesc(d["numChannels"], d["epsilon"], int(d["hasScale"]), int(d["hasBias"]),
+                       *[a.ctypes.data_as(capi.c_float_p) for a in arrs]), arrs
+
+
+def _desc_matmul(d):
+    w = np.ascontiguousarray(d["weights"], np.float32)
+    return capi.MatMulDesc(d["inChannels"], d["outChannels"], w.ctypes.data_as(capi.c_float_p)), w
+
+
+def block_desc_from_dict(d):
+    """Builds a BlockDesc from a dict shaped like the reference's ResidualBlockDesc /
+    GlobalPoolingResidualBlockDesc (as extracted into tests/golden/nn_layers_golden.json)."""
+    keep = []
+    b = capi.BlockDesc()
+    b.kind = 2 if "gpoolConv" in d else 0
+    b.preActivation = b.gpoolActivation = b.midActivation = 1   # ActivationLayerDesc default = ReLU
+    for name, fn in (("preBN", _desc_bn), ("regularConv", _desc_conv), ("midBN", _desc_bn), ("finalConv", _desc_conv)):
+        s, k = fn(d[name]); setattr(b, name, s); keep.append(k)
+    if b.kind == 2:
+        for name, fn in (("gpoolConv", _desc_conv), ("gpoolBN", _desc_bn), ("gpoolToBiasMul", _desc_matmul)):
+            s, k = fn(d[name]); setattr(b, name, s); keep.append(k)
+    return b, keep
+
+
+def testEvaluateConv(ctx, desc, batchSize, nnXLen, nnYLen, useNHWC, inputBuffer):
+    d, keep = _desc_conv(desc)
+    inp = np.ascontiguousarray(inputBuffer, np.float32)
+    out = np.empty(batchSize * nnXLen * nnYLen * desc["outChannels"], np.float32)
+    check(lib().kc_test_conv(ctx._p, C.byref(d), batchSize, nnXLen, nnYLen, int(useNHWC), ptr(inp), ptr(out)))
+    return out
+
+
+def testEvaluateBatchNorm(ctx, desc, batchSize, nnXLen, nnYLen, useNHWC, inputBuffer, maskBuffer, activation=0):
+    d, keep = _desc_bn(desc)
+    inp = np.ascontiguousarray(inputBuffer, np.float32)
+    mask = np.ascontiguousarray(maskBuffer, np.float32)
+    out = np.empty_like(inp)
+    check(lib().kc_test_batchnorm(ctx._p, C.byref(d), activation, batchSize, nnXLen, nnYLen, int(useNHWC), ptr(inp), ptr(mask), ptr(out)))
+    return out
+
+
+def testEvaluateResidualBlock(ctx, desc, batchSize, nnXLen, nnYLen, useNHWC, inputBuffer, maskBuffer):
+    """Also serves testEvaluateGlobalPoolingResidualBlock (the desc decides)."""
+    b, keep = block_desc_from_dict(desc)
+    inp = np.ascontiguousarray(inputBuffer, np.float32)
+    mask = np.ascontiguousarray(maskBuffer, np.float32)
+    out = np.empty_like(inp)
+    check(lib().kc_test_resblock(ctx._p, C.byref(b), batchSize, nnXLen, nnYLen, int(useNHWC), ptr(inp), ptr(mask), ptr(out)))
+    return out
+
+
+class Games:
+    """G concurrent device-resident games (Board + BoardHistory of the reference, batched)."""
+
+    def __init__(self, ctx, numGames, xSize=5, ySize=5, winLen=4):
+        self.ctx, self.G, self.W, self.H, self.K = ctx, numGames, xSize, ySize, winLen
+        self.HW = xSize * ySize
+        self.LW = (4 * self.HW + 31) // 32
+        self._p = C.c_void_p()
+        check(lib().kc_games_create(ctx._p, numGames, xSize, ySize, winLen, C.byref(self._p)))
+
+    def reset(self, seed=0, firstGameId=0, autoRefill=False):
+        check(lib().kc_games_reset(self._p, seed, firstGameId, int(autoRefill)))
+
+    def load(self, g0, stones, nextPla, moves=None, numTurns=None):
+        stones = np.ascontiguousarray(stones, np.int8)
+        n = stones.shape[0]
+        nextPla = np.ascontiguousarray(nextPla, np.int8)
+        moves = None if moves is None else np.ascontiguousarray(moves, np.int16)
+        numTurns = None if numTurns is None else np.ascontiguousarray(numTurns, np.int32)
+        check(lib().kc_games_load(self._p, g0, n, ptr(stones), ptr(nextPla), ptr(moves), ptr(numTurns)))
+
+    def step(self, movePos=None):
+        G = self.G
+        mv = None if movePos is None else np.ascontiguousarray(movePos, np.int16)
+        legal = np.empty((G, self.LW), np.uint32)
+        status = np.empty(G, np.uint32)
+        sitHash = np.empty((G, 2), np.uint64)
+        played = np.empty(G, np.int16)
+        ids = np.empty(G, np.uint64)
+        check(lib().kc_games_step(self._p, ptr(mv), ptr(legal), ptr(status), ptr(sitHash), ptr(played), ptr(ids)))
+        return dict(legal=legal, status=status, sitHash=sitHash, played=played, gameIds=ids)
+
+    def features(self, nhwc=False, symmetry=None):
+        planes = np.empty((self.G, 15 * self.HW), np.float32)
+        glob = np.empty((self.G, 1), np.float32)
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8)
+        check(lib().kc_games_features(self._p, int(nhwc), ptr(sym), ptr(planes), ptr(glob)))
+        return planes, glob
+
+    def eval(self, handle, symmetry=None):
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8)
+        check(lib().kc_games_eval(self._p, handle._p, ptr(sym)))
+
+    def run(self, handle, plies, stats=None):
+        st = stats if stats is not None else capi.Stats()
+        check(lib().kc_games_run(self._p, handle._p if handle is not None else None, plies, C.byref(st)))
+        return st
+
+    def launchCount(self):
+        return int(lib().kc_games_launch_count(self._p))
+
+    def lastKernelMs(self):
+        return float(lib().kc_games_last_kernel_ms(self._p))
+
+    def close(self):
+        if self._p:
+            lib().kc_games_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+def zobristTables():
+    board = np.zeros((133, 4, 2), np.uint64)
+    player = np.zeros((4, 2), np.uint64)
+    sx = np.zeros((11, 2), np.uint64)
+    sy = np.zeros((11, 2), np.uint64)
+    check(lib().kc_zobrist_tables(ptr(board), ptr(player), ptr(sx), ptr(sy)))
+    return board, player, sx, sy
+
+
+def selftestUmma(ctx, A_bf16_bits, B_bf16_bits, shift):
+    rowsA, K = A_bf16_bits.shape
+    N = B_bf16_bits.shape[0]
+    D = np.zeros((128, N), np.float32)
+    A = np.ascontiguousarray(A_bf16_bits, np.uint16)
+    B = np.ascontiguousarray(B_bf16_bits, np.uint16)
+    check(lib().kc_selftest_umma(ctx._p, ptr(A), ptr(B), ptr(D), rowsA, N, K, shift))
+    return D

@@ -1,0 +1,131 @@
+"""ctypes bindings for include/katacoffee_b200.h (one prototype per exported symbol)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkatacoffee_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("convYSize", C.c_int32), ("convXSize", C.c_int32), ("inChannels", C.c_int32),
+                ("outChannels", C.c_int32), ("weights", c_float_p)]
+
+
+class BNDesc(C.Structure):
+    _fields_ = [("numChannels", C.c_int32), ("epsilon", C.c_float), ("hasScale", C.c_int32),
+                ("hasBias", C.c_int32), ("mean", c_float_p), ("variance", c_float_p),
+                ("scale", c_float_p), ("bias", c_float_p)]
+
+
+class MatMulDesc(C.Structure):
+    _fields_ = [("inChannels", C.c_int32), ("outChannels", C.c_int32), ("weights", c_float_p)]
+
+
+class MatBiasDesc(C.Structure):
+    _fields_ = [("numChannels", C.c_int32), ("pad_", C.c_int32), ("weights", c_float_p)]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("preActivation", C.c_int32), ("gpoolActivation", C.c_int32),
+                ("midActivation", C.c_int32), ("preBN", BNDesc), ("regularConv", ConvDesc),
+                ("gpoolConv", ConvDesc), ("gpoolBN", BNDesc), ("gpoolToBiasMul", MatMulDesc),
+                ("midBN", BNDesc), ("finalConv", ConvDesc)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("version", C.c_int32), ("numInputChannels", C.c_int32),
+                ("numInputGlobalChannels", C.c_int32), ("numBlocks", C.c_int32),
+                ("trunkNumChannels", C.c_int32), ("midNumChannels", C.c_int32),
+                ("regularNumChannels", C.c_int32), ("gpoolNumChannels", C.c_int32),
+                ("trunkTipActivation", C.c_int32), ("g1Activation", C.c_int32),
+                ("p1Activation", C.c_int32), ("v1Activation", C.c_int32), ("v2Activation", C.c_int32),
+                ("pad_", C.c_int32),
+                ("initialConv", ConvDesc), ("initialMatMul", MatMulDesc),
+                ("blocks", C.POINTER(BlockDesc)), ("trunkTipBN", BNDesc),
+                ("p1Conv", ConvDesc), ("g1Conv", ConvDesc), ("g1BN", BNDesc),
+                ("gpoolToBiasMul", MatMulDesc), ("p1BN", BNDesc), ("p2Conv", ConvDesc),
+                ("v1Conv", ConvDesc), ("v1BN", BNDesc), ("v2Mul", MatMulDesc), ("v2Bias", MatBiasDesc),
+                ("v3Mul", MatMulDesc), ("v3Bias", MatBiasDesc), ("sv3Mul", MatMulDesc),
+                ("sv3Bias", MatBiasDesc), ("vOwnershipConv", ConvDesc)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("evals", C.c_uint64), ("gamesFinished", C.c_uint64),
+                ("blackWins", C.c_uint64), ("whiteWins", C.c_uint64), ("draws", C.c_uint64),
+                ("checksum", C.c_uint64)]
+
+
+FLAG_FP32_CHECK = 1
+FLAG_INPUTS_NHWC = 2
+FLAG_SYM_PERMUTE_DIRS = 4
+
+vp = C.c_void_p
+# name -> (restype, argtypes); must list every symbol include/katacoffee_b200.h declares
+PROTOTYPES = {
+    "kc_last_error": (C.c_char_p, []),
+    "kc_abi_version": (C.c_int, []),
+    "kc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "kc_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "kc_ctx_destroy": (C.c_int, [vp]),
+    "kc_zobrist_tables": (C.c_int, [vp, vp, vp, vp]),
+    "kc_model_create": (C.c_int, [vp, C.POINTER(ModelDesc), C.POINTER(vp)]),
+    "kc_model_destroy": (C.c_int, [vp]),
+    "kc_handle_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
+    "kc_handle_destroy": (C.c_int, [vp]),
+    "kc_handle_uses_bf16": (C.c_int, [vp]),
+    "kc_forward": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "kc_handle_read_outputs": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+    "kc_handle_launch_count": (C.c_int64, [vp]),
+    "kc_handle_trunk_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "kc_selftest_umma": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "kc_test_conv": (C.c_int, [vp, C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "kc_test_batchnorm": (C.c_int, [vp, C.POINTER(BNDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "kc_test_resblock": (C.c_int, [vp, C.POINTER(BlockDesc), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "kc_games_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "kc_games_destroy": (C.c_int, [vp]),
+    "kc_games_reset": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int]),
+    "kc_games_load": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "kc_games_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "kc_games_features": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "kc_games_eval": (C.c_int, [vp, vp, vp]),
+    "kc_games_run": (C.c_int, [vp, vp, C.c_int, C.POINTER(Stats)]),
+    "kc_games_launch_count": (C.c_int64, [vp]),
+    "kc_games_last_kernel_ms": (C.c_float, [vp]),
+}
+
+_lib = None
+
+
+class KCError(RuntimeError):
+    """Raised for any non-zero status from the C ABI (the analogue of the reference's StringError)."""
+
+
+def lib():
+    """Loads the CUDA library. Fails loudly if it was not built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KCError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(katacoffee_b200 has no CPU or PyTorch fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise KCError(lib().kc_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,700 @@
+// Batched Coffee rules, history, sit-hash and NNInputs V1 feature planes on the device.
+//
+// One thread owns one game for the rule logic (pure 64-bit bitboard arithmetic, ~600 SASS
+// instructions per ply), then the whole CTA expands the 15 plane bitboards of its games into the
+// output tensor with 128-bit coalesced stores -- the plane write is the HBM-bound part (1500 B per
+// position in fp32), the logic is noise next to it.
+//
+// Semantics (reference file:line; canonical readings from SURVEY.md 8.1 quoted as "ledger X"):
+//   Board::isLegal                 cpp/game/board.cpp:185-227   (ledger B)
+//   Board::playMoveAssumeLegal     cpp/game/board.cpp:427-435
+//   Board::maxConsecutives/checkGameEnd  board.cpp:315-335,376-383 (ledger N: overlines win)
+//   BoardHistory::makeBoardMoveAssumeLegal  cpp/game/boardhistory.cpp:157-176 (ledger C draw, D history)
+//   Board::getSitHash              cpp/game/board.cpp:288-292   (ledger E: literal, no lastLoc)
+//   NNInputs::fillRowV1            cpp/neuralnet/nninputs.cpp:508-657 (ledger F, G)
+//   copyInputsWithSymmetry         cpp/neuralnet/nninputs.cpp:252-357 (ledger K parity mode)
+//   random-legal playout           cpp/program/playutils.cpp:10-32 with the counter RNG of SURVEY 8(d)
+//
+// Bitboard layout: bit = y*(W+1) + x, i.e. one always-zero pad column per row, so that the four
+// line directions are plain shifts (N-S: W+1, W-E: 1, NW-SE: W+2, NE-SW: W) that cannot wrap.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "kc_internal.h"
+#include "net.h"
+
+namespace kc {
+
+constexpr int GPB = 128;       // games per CTA in the fp32 feature modes
+constexpr int THREADS = 128;
+
+struct Geom {
+  int W, H, K, HW, stride;   // stride = W + 1
+  int LW;                    // legal mask words = ceil(4*HW/32)
+  int numGames;
+  uint64_t all;              // on-board cells (padded layout)
+  uint64_t rowMask;          // (1<<W)-1
+  uint64_t lines[4][13];     // [dir][line index]: N: x, W: y, NW: x-y+H-1, NE: x+y
+  uint64_t playerHash[4][2]; // ZOBRIST_PLAYER_HASH
+  uint64_t sizeHash[2];      // SIZE_X[W] ^ SIZE_Y[H]
+  uint64_t seed;
+  int autoRefill;
+  // bf16 tile layout for the trunk (see net.h): boards side by side, NB per 128-row tile
+  int NB, tileRowW;          // tileRowW = NB*(W+1)
+};
+
+struct State {   // SoA device arrays, one entry per game lane
+  uint64_t* black; uint64_t* white; uint64_t* hash0; uint64_t* hash1; uint64_t* gameId; uint64_t* misc;
+};
+// misc: bytes 0..4 = last five moves, most recent first: bits 0-5 dense cell, bits 6-7 player (0 = none)
+//       byte 5 = direction of the most recent move (4 = none), byte 6 = numTurns,
+//       byte 7 = bit0 finished, bits 1-2 winner, bits 3-4 next player
+
+struct StepOut {   // device pointers, any may be null
+  uint32_t* legal; uint32_t* status; uint64_t* sitHash; int16_t* played; unsigned long long* stats;
+};
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {  // cpp/core/hash.cpp:50-56
+  x += 0x9e3779b97f4a7c15ULL;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ int padOf(const Geom& g, int cell) { return cell + cell / g.W; }
+
+// Legal Locs of the player to move, one padded bitboard per direction (board.cpp:185-227).
+__device__ __forceinline__ void legalMasks(const Geom& g, uint64_t empty, int lastCell, int lastDir, uint64_t L[4]) {
+  uint64_t cand = empty;
+  if(lastDir < 4 && lastCell >= 0) {
+    int x = lastCell % g.W, y = lastCell / g.W;
+    int li = lastDir == 0 ? x : lastDir == 1 ? y : lastDir == 2 ? (x - y + g.H - 1) : (x + y);
+    cand &= g.lines[lastDir][li];
+  }
+#pragma unroll
+  for(int d = 0; d < 4; d++) {
+    int nl = (d == 0) ? g.W : (d == 1) ? g.H : (g.W + g.H - 1);
+    uint64_t ok = 0;
+    for(int i = 0; i < nl; i++) {
+      uint64_t e = empty & g.lines[d][i];
+      ok |= (__popcll(e) >= 2) ? e : 0ULL;   // another empty cell anywhere on the same line
+    }
+    L[d] = cand & ok;
+  }
+}
+
+__device__ __forceinline__ uint64_t toDense(const Geom& g, uint64_t m) {
+  uint64_t r = 0;
+  for(int y = 0; y < g.H; y++) r |= ((m >> (y * g.stride)) & g.rowMask) << (y * g.W);
+  return r;
+}
+
+// cells covered by a same-colour run of length >= n along shift s
+__device__ __forceinline__ uint64_t coverAtLeast(uint64_t m, int s, int n) {
+  uint64_t starts = m;
+  for(int i = 1; i < n; i++) starts &= (m >> (i * s));
+  uint64_t c = starts;
+  for(int i = 1; i < n; i++) c |= (starts << (i * s));
+  return c;
+}
+
+__device__ __forceinline__ int nthSetBit64(uint64_t m, int n) {  // n is 0-based
+  uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  int c = __popc(lo);
+  if(n < c) return __fns(lo, 0, n + 1);
+  return 32 + __fns(hi, 0, n - c + 1);
+}
+
+struct GameRegs {
+  uint64_t black, white, h0, h1, id, misc;
+};
+
+__device__ __forceinline__ int histCell(uint64_t misc, int i) { return (int)((misc >> (8 * i)) & 0x3f); }
+__device__ __forceinline__ int histPla(uint64_t misc, int i) { return (int)((misc >> (8 * i + 6)) & 0x3); }
+__device__ __forceinline__ int lastDirOf(uint64_t misc) { return (int)((misc >> 40) & 0xff); }
+__device__ __forceinline__ int numTurnsOf(uint64_t misc) { return (int)((misc >> 48) & 0xff); }
+__device__ __forceinline__ int flagsOf(uint64_t misc) { return (int)((misc >> 56) & 0xff); }
+
+__device__ __forceinline__ void resetGame(const Geom& g, GameRegs& s, uint64_t id) {
+  s.black = 0; s.white = 0;
+  s.h0 = g.sizeHash[0]; s.h1 = g.sizeHash[1];
+  s.id = id;
+  // no history, lastDir none, numTurns 0, not finished, winner 0, next player black (boardhistory.cpp:7-18)
+  s.misc = (4ULL << 40) | ((uint64_t)(1 << 3) << 56);
+}
+
+// The 15 V1 planes as padded bitboards (nninputs.cpp:508-657, ledger F/G).
+__device__ __forceinline__ void v1Planes(const Geom& g, const GameRegs& s, const uint64_t L[4], uint64_t* P /*[15], stride pstride*/, int pstride) {
+  int fl = flagsOf(s.misc);
+  int pla = (fl >> 3) & 3, opp = pla ^ 3;
+  uint64_t own = pla == 1 ? s.black : s.white, other = pla == 1 ? s.white : s.black;
+  int nt = numTurnsOf(s.misc);
+  P[0 * pstride] = g.all;
+  P[1 * pstride] = own;
+  P[2 * pstride] = other;
+  uint64_t lastBit = histPla(s.misc, 0) ? (1ULL << padOf(g, histCell(s.misc, 0))) : 0ULL;
+  int ld = lastDirOf(s.misc);
+#pragma unroll
+  for(int d = 0; d < 4; d++) P[(3 + d) * pstride] = (ld == d) ? lastBit : 0ULL;
+  // moves 2..5 plies ago: alternation chain own, opp, own, opp; breaks at the first failure
+  bool ok = true;
+#pragma unroll
+  for(int i = 1; i < 5; i++) {
+    int want = (i & 1) ? pla : opp;
+    ok = ok && nt >= i + 1 && histPla(s.misc, i) == want;
+    P[(6 + i) * pstride] = ok ? (1ULL << padOf(g, histCell(s.misc, i))) : 0ULL;
+  }
+  P[11 * pstride] = L[0] | L[1] | L[2] | L[3];
+  // stones in a maximal same-colour run of length exactly k-1, k-2, k-3 in some direction
+  uint64_t ex[3] = {0, 0, 0};
+  const int shifts[4] = {g.stride, 1, g.stride + 1, g.stride - 1};
+#pragma unroll
+  for(int c = 0; c < 2; c++) {
+    uint64_t m = c == 0 ? s.black : s.white;
+#pragma unroll
+    for(int d = 0; d < 4; d++) {
+      uint64_t hi = coverAtLeast(m, shifts[d], g.K);      // >= k
+#pragma unroll
+      for(int j = 0; j < 3; j++) {
+        int len = g.K - 1 - j;
+        uint64_t lo = len >= 1 ? coverAtLeast(m, shifts[d], len) : 0ULL;
+        ex[j] |= lo & ~hi;
+        hi = lo;
+      }
+    }
+  }
+  P[12 * pstride] = ex[0];
+  P[13 * pstride] = ex[1];
+  P[14 * pstride] = ex[2];
+}
+
+// One ply for one game. Returns the policy index played (-1 none).  Lnew = legal masks afterwards.
+__device__ __forceinline__ int stepGame(const Geom& g, GameRegs& s, int forcedMove, bool useForced,
+                                        const uint64_t* __restrict__ zob, uint64_t L[4], bool& illegal) {
+  illegal = false;
+  int fl = flagsOf(s.misc);
+  if((fl & 1) && g.autoRefill) {
+    resetGame(g, s, s.id + (uint64_t)g.numGames);
+    fl = flagsOf(s.misc);
+  }
+  int pla = (fl >> 3) & 3;
+  uint64_t empty = g.all & ~(s.black | s.white);
+  int lastCell = histPla(s.misc, 0) ? histCell(s.misc, 0) : -1;
+  legalMasks(g, empty, lastCell, lastDirOf(s.misc), L);
+  if(fl & 1) return -1;                         // finished, not refilled
+  int dir = -1, cellPad = 0;
+  if(useForced) {
+    if(forcedMove < 0) return -1;
+    if(forcedMove >= 4 * g.HW) { illegal = true; return -1; }
+    dir = forcedMove / g.HW;
+    int cell = forcedMove % g.HW;               // ledger I
+    cellPad = padOf(g, cell);
+    if(!((L[dir] >> cellPad) & 1ULL)) { illegal = true; return -1; }
+  } else {
+    int c0 = __popcll(L[0]), c1 = __popcll(L[1]), c2 = __popcll(L[2]), c3 = __popcll(L[3]);
+    int n = c0 + c1 + c2 + c3;
+    if(n == 0) return -1;
+    uint64_t r = splitmix64(g.seed ^ (s.id * 0x9E3779B97F4A7C15ULL) ^ (uint64_t)numTurnsOf(s.misc));
+    int k = (int)(r % (uint64_t)n);
+    if(k < c0) dir = 0;
+    else if(k < c0 + c1) { dir = 1; k -= c0; }
+    else if(k < c0 + c1 + c2) { dir = 2; k -= c0 + c1; }
+    else { dir = 3; k -= c0 + c1 + c2; }
+    cellPad = nthSetBit64(L[dir], k);
+  }
+  int y = cellPad / g.stride, x = cellPad - y * g.stride;
+  int cell = y * g.W + x;
+  // play (board.cpp:427-435) and history (boardhistory.cpp:157-176)
+  uint64_t bit = 1ULL << cellPad;
+  if(pla == 1) s.black |= bit; else s.white |= bit;
+  const uint64_t* z = zob + ((size_t)cell * 2 + (pla - 1)) * 2;
+  s.h0 ^= z[0]; s.h1 ^= z[1];
+  uint64_t hist = ((s.misc & 0xffffffffULL) << 8) | (uint64_t)(cell | (pla << 6));
+  int nt = numTurnsOf(s.misc) + 1;
+  // win through the last move (board.cpp:376-383), overlines count
+  uint64_t mine = pla == 1 ? s.black : s.white;
+  bool win = false;
+  const int shifts[4] = {g.stride, 1, g.stride + 1, g.stride - 1};
+#pragma unroll
+  for(int d = 0; d < 4; d++) win = win || ((coverAtLeast(mine, shifts[d], g.K) & bit) != 0);
+  int opp = pla ^ 3;
+  // legal masks of the player now to move (also decides the draw, ledger C)
+  uint64_t empty2 = empty & ~bit;
+  legalMasks(g, empty2, cell, dir, L);
+  bool none = (L[0] | L[1] | L[2] | L[3]) == 0;
+  int finished = (win || none) ? 1 : 0;
+  int winner = win ? pla : 0;
+  int nfl = finished | (winner << 1) | (opp << 3);
+  s.misc = (hist & 0xffffffffffULL) | ((uint64_t)dir << 40) | ((uint64_t)(nt & 0xff) << 48) | ((uint64_t)nfl << 56);
+  return dir * g.HW + cell;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel.  DO_STEP: play one ply first.  FEAT: 0 none, 1 fp32 NCHW, 2 fp32 NHWC, 3 bf16 trunk tiles.
+// ---------------------------------------------------------------------------------------------
+struct FeatOut {
+  float* planes;            // FEAT 1/2
+  float* global;            // FEAT 1/2
+  uint4* tiles;             // FEAT 3: [tile][2][128] 16-byte chunks
+  const int8_t* symmetry;   // per game or null
+  int gamesPerBlock;
+};
+
+template <bool DO_STEP, int FEAT>
+__global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
+                                                        int useMoves, const uint64_t* __restrict__ zob,
+                                                        StepOut so, FeatOut fo) {
+  __shared__ uint64_t sPlanes[15][GPB + 1];
+  __shared__ uint8_t sSrcPad[8][52];   // [symmetry][dst cell] -> padded bit index of the source cell
+  __shared__ int8_t sSym[GPB];
+  const int gpb = fo.gamesPerBlock;
+  const int gBase = blockIdx.x * gpb;
+  const int t = threadIdx.x;
+  const int gi = gBase + t;
+  const bool active = t < gpb && gi < g.numGames;
+
+  if(FEAT != 0) {
+    // symmetry tables: dst[sym(h,w)] = src[h,w] (nninputs.cpp:252-335), built per CTA (<= 8*49 entries)
+    for(int i = t; i < 8 * g.HW; i += THREADS) {
+      int sym = i / g.HW, cell = i % g.HW;
+      int h = cell / g.W, w = cell % g.W;
+      bool tr = (sym & 4) && g.H == g.W, fx = (sym & 2) != 0, fy = (sym & 1) != 0;
+      if(tr) { bool tmp = fx; fx = fy; fy = tmp; }
+      int rowStep = g.W, colStep = 1, base = 0;
+      if(fy) { base += (g.H - 1) * rowStep; rowStep = -rowStep; }
+      if(fx) { base += (g.W - 1) * colStep; colStep = -colStep; }
+      if(tr) { int tmp = rowStep; rowStep = colStep; colStep = tmp; }
+      int dst = base + h * rowStep + w * colStep;
+      sSrcPad[sym][dst] = (uint8_t)(cell + cell / g.W);
+    }
+    if(t < gpb) sSym[t] = (active && fo.symmetry) ? fo.symmetry[gi] : 0;
+  }
+
+  unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
+  if(active) {
+    GameRegs s;
+    s.black = st.black[gi]; s.white = st.white[gi]; s.h0 = st.hash0[gi]; s.h1 = st.hash1[gi];
+    s.id = st.gameId[gi]; s.misc = st.misc[gi];
+    uint64_t L[4];
+    int played = -1;
+    bool illegal = false;
+    if(DO_STEP) {
+      int mv = useMoves ? (int)moves[gi] : -1;
+      played = stepGame(g, s, mv, useMoves != 0, zob, L, illegal);
+      st.black[gi] = s.black; st.white[gi] = s.white; st.hash0[gi] = s.h0; st.hash1[gi] = s.h1;
+      st.gameId[gi] = s.id; st.misc[gi] = s.misc;
+    } else {
+      uint64_t empty = g.all & ~(s.black | s.white);
+      int lastCell = histPla(s.misc, 0) ? histCell(s.misc, 0) : -1;
+      legalMasks(g, empty, lastCell, lastDirOf(s.misc), L);
+    }
+    int fl = flagsOf(s.misc);
+    int nextPla = (fl >> 3) & 3;
+    uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
+    if(DO_STEP) {
+      if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) |
+                                    ((uint32_t)nextPla << 11) | (illegal ? (1u << 15) : 0u);
+      if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
+      if(so.played) so.played[gi] = (int16_t)played;
+      if(so.legal) {
+        // policy order: bit = dir*HW + y*W + x (nninputs.cpp:6-14)
+        uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for(int d = 0; d < 4; d++) {
+          uint64_t dm = toDense(g, L[d]);
+          int off = d * g.HW, w = off >> 6, sh = off & 63;
+#pragma unroll
+          for(int q = 0; q < 4; q++) {
+            if(q == w) acc[q] |= dm << sh;
+            if(q == w + 1 && sh) acc[q] |= dm >> (64 - sh);
+          }
+        }
+        for(int wd = 0; wd < g.LW; wd++)
+          so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
+      }
+      if(played >= 0) {
+        cSteps = 1;
+        cXor = sh0;
+        if(fl & 1) { cFin = 1; int wn = (fl >> 1) & 3; cB = wn == 1; cW = wn == 2; cD = wn == 0; }
+      }
+    }
+    if(FEAT != 0) v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
+  } else if(FEAT != 0 && t < GPB) {
+#pragma unroll
+    for(int c = 0; c < 15; c++) sPlanes[c][t] = 0;
+  }
+
+  if(DO_STEP && so.stats) {
+    // warp-reduce then one atomic per warp per counter
+    for(int o = 16; o > 0; o >>= 1) {
+      cSteps += __shfl_xor_sync(0xffffffffu, cSteps, o);
+      cFin += __shfl_xor_sync(0xffffffffu, cFin, o);
+      cB += __shfl_xor_sync(0xffffffffu, cB, o);
+      cW += __shfl_xor_sync(0xffffffffu, cW, o);
+      cD += __shfl_xor_sync(0xffffffffu, cD, o);
+      cXor ^= __shfl_xor_sync(0xffffffffu, cXor, o);
+    }
+    if((t & 31) == 0) {
+      if(cSteps) atomicAdd(&so.stats[0], cSteps);
+      if(cFin) atomicAdd(&so.stats[2], cFin);
+      if(cB) atomicAdd(&so.stats[3], cB);
+      if(cW) atomicAdd(&so.stats[4], cW);
+      if(cD) atomicAdd(&so.stats[5], cD);
+      if(cXor) atomicXor(&so.stats[6], cXor);
+    }
+  }
+  if(FEAT == 0) return;
+  __syncthreads();
+
+  const int ng = min(gpb, g.numGames - gBase);
+  if(ng <= 0) return;
+  if(FEAT == 1 || FEAT == 2) {
+    const int E = 15 * g.HW;
+    const uint32_t magicE = (uint32_t)((0x100000000ULL + E - 1) / E);
+    const int inner = FEAT == 1 ? g.HW : 15;
+    const uint32_t magicI = (uint32_t)((0x100000000ULL + inner - 1) / inner);
+    const int total = ng * E;
+    float* out = fo.planes + (size_t)gBase * E;
+    auto elem = [&](int e) -> float {
+      int gl = (int)__umulhi((uint32_t)e, magicE);
+      int r = e - gl * E;
+      int q = (int)__umulhi((uint32_t)r, magicI);
+      int rem = r - q * inner;
+      int c = FEAT == 1 ? q : rem;
+      int cell = FEAT == 1 ? rem : q;
+      int bit = sSrcPad[sSym[gl]][cell];
+      return (float)((sPlanes[c][gl] >> bit) & 1ULL);
+    };
+    const int nvec = total >> 2;
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for(int j = t; j < nvec; j += THREADS) {
+      int e = j << 2;
+      float4 v = make_float4(elem(e), elem(e + 1), elem(e + 2), elem(e + 3));
+      __stcs(&out4[j], v);
+    }
+    for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = elem(e);
+    if(fo.global && t < ng) fo.global[gBase + t] = (float)g.K;   // nninputs.cpp:656
+  } else if(FEAT == 3) {
+    // trunk input tiles: row = y*tileRowW + b*(W+1) + x, 16 bf16 channels per row as two 16 B chunks
+    // (channels 0..14 = V1 planes, channel 15 = the global feature win_len broadcast on board cells)
+    const int ntiles = (ng + g.NB - 1) / g.NB;
+    const int tileBase = gBase / g.NB;
+    const uint32_t ONE = 0x3f80u;
+    const uint32_t kval = (uint32_t)__bfloat16_as_ushort(__float2bfloat16((float)g.K));
+    for(int j = t; j < ntiles * 256; j += THREADS) {
+      int tile = j >> 8, chunk = (j >> 7) & 1, row = j & 127;
+      int y = row / g.tileRowW, rr = row - y * g.tileRowW;
+      int b = rr / g.stride, x = rr - b * g.stride;
+      int gl = tile * g.NB + b;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if(y < g.H && x < g.W && gl < ng) {
+        int bit = sSrcPad[sSym[gl]][y * g.W + x];
+        uint32_t w[4];
+#pragma unroll
+        for(int q = 0; q < 4; q++) {
+          int c0 = chunk * 8 + 2 * q, c1 = c0 + 1;
+          uint32_t lo = ((sPlanes[c0][gl] >> bit) & 1ULL) ? ONE : 0u;
+          uint32_t hi = (c1 < 15) ? (((sPlanes[c1][gl] >> bit) & 1ULL) ? ONE : 0u) : kval;
+          w[q] = lo | (hi << 16);
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fo.tiles[((size_t)(tileBase + tile) * 2 + chunk) * 128 + row] = v;
+    }
+  }
+}
+
+}  // namespace kc
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+struct kc_games {
+  kc_ctx* ctx = nullptr;
+  kc::Geom geom;
+  kc::State st;
+  uint64_t* d_zob = nullptr;          // [HW][2 colours][2]
+  int16_t* d_moves = nullptr;
+  uint32_t* d_legal = nullptr; uint32_t* d_status = nullptr; uint64_t* d_sitHash = nullptr; int16_t* d_played = nullptr;
+  unsigned long long* d_stats = nullptr;  // 8 counters
+  float* d_planes = nullptr; float* d_global = nullptr;  // fp32 feature outputs
+  int8_t* d_sym = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  float lastKernelMs = 0.f;
+  uint64_t nextId = 0;
+};
+
+namespace {
+using namespace kc;
+
+template <bool DO_STEP>
+void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
+  int gpb = feat == 3 ? G->geom.NB * 32 : GPB;
+  fo.gamesPerBlock = gpb;
+  int blocks = (G->geom.numGames + gpb - 1) / gpb;
+  switch(feat) {
+    case 0: games_kernel<DO_STEP, 0><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 1: games_kernel<DO_STEP, 1><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 2: games_kernel<DO_STEP, 2><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    default: games_kernel<DO_STEP, 3><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+  }
+  G->launches++;
+}
+
+StepOut stepOutOf(kc_games* G, bool all) {
+  StepOut so;
+  so.legal = all ? G->d_legal : nullptr; so.status = all ? G->d_status : nullptr;
+  so.sitHash = all ? G->d_sitHash : nullptr; so.played = all ? G->d_played : nullptr;
+  so.stats = G->d_stats;
+  return so;
+}
+}  // namespace
+
+extern "C" {
+
+int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen, kc_games** out) {
+  KC_CHECK(ctx && out, "kc_games_create: null argument");
+  KC_CHECK(numGames > 0, "kc_games_create: numGames must be positive");
+  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN,
+           "kc_games_create: board size must be within 2..7 (bitboard kernels need H*(W+1) <= 64)");
+  KC_CHECK(winLen >= 2 && winLen <= 7, "kc_games_create: winLen must be within 2..7");
+  KC_CUDA(cudaSetDevice(ctx->device));
+  kc_games* G = new kc_games();
+  G->ctx = ctx;
+  Geom& g = G->geom;
+  memset(&g, 0, sizeof(g));
+  g.W = xSize; g.H = ySize; g.K = winLen; g.HW = xSize * ySize; g.stride = xSize + 1;
+  g.LW = (4 * g.HW + 31) / 32;
+  g.numGames = numGames;
+  g.rowMask = (1ULL << g.W) - 1;
+  for(int y = 0; y < g.H; y++)
+    for(int x = 0; x < g.W; x++) {
+      uint64_t bit = 1ULL << (y * g.stride + x);
+      g.all |= bit;
+      g.lines[0][x] |= bit;
+      g.lines[1][y] |= bit;
+      g.lines[2][x - y + g.H - 1] |= bit;
+      g.lines[3][x + y] |= bit;
+    }
+  const ZobristTables& z = zobrist();
+  memcpy(g.playerHash, z.player, sizeof(g.playerHash));
+  g.sizeHash[0] = z.sizeX[g.W][0] ^ z.sizeY[g.H][0];
+  g.sizeHash[1] = z.sizeX[g.W][1] ^ z.sizeY[g.H][1];
+  g.NB = kc::boardsPerTile(g.W, g.H);
+  g.tileRowW = g.NB * g.stride;
+  std::vector<uint64_t> zob((size_t)g.HW * 4);
+  for(int y = 0; y < g.H; y++)
+    for(int x = 0; x < g.W; x++) {
+      int spot = (x + 1) + (y + 1) * (g.W + 1);   // board.h:74-75
+      for(int c = 0; c < 2; c++) {
+        zob[((size_t)(y * g.W + x) * 2 + c) * 2 + 0] = z.board[spot][c + 1][0];
+        zob[((size_t)(y * g.W + x) * 2 + c) * 2 + 1] = z.board[spot][c + 1][1];
+      }
+    }
+  size_t n = (size_t)numGames;
+  KC_CUDA(cudaMalloc(&G->d_zob, zob.size() * 8));
+  KC_CUDA(cudaMemcpy(G->d_zob, zob.data(), zob.size() * 8, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMalloc(&G->st.black, n * 8)); KC_CUDA(cudaMalloc(&G->st.white, n * 8));
+  KC_CUDA(cudaMalloc(&G->st.hash0, n * 8)); KC_CUDA(cudaMalloc(&G->st.hash1, n * 8));
+  KC_CUDA(cudaMalloc(&G->st.gameId, n * 8)); KC_CUDA(cudaMalloc(&G->st.misc, n * 8));
+  KC_CUDA(cudaMalloc(&G->d_moves, n * 2));
+  KC_CUDA(cudaMalloc(&G->d_legal, n * g.LW * 4)); KC_CUDA(cudaMalloc(&G->d_status, n * 4));
+  KC_CUDA(cudaMalloc(&G->d_sitHash, n * 16)); KC_CUDA(cudaMalloc(&G->d_played, n * 2));
+  KC_CUDA(cudaMalloc(&G->d_stats, 8 * 8));
+  KC_CUDA(cudaMemset(G->d_stats, 0, 64));
+  KC_CUDA(cudaMalloc(&G->d_planes, n * 15 * g.HW * 4)); KC_CUDA(cudaMalloc(&G->d_global, n * 4));
+  KC_CUDA(cudaMalloc(&G->d_sym, n));
+  KC_CUDA(cudaStreamCreateWithFlags(&G->stream, cudaStreamNonBlocking));
+  KC_CUDA(cudaEventCreate(&G->ev0)); KC_CUDA(cudaEventCreate(&G->ev1));
+  *out = G;
+  return kc_games_reset(G, 0, 0, 0);
+}
+
+int kc_games_destroy(kc_games* G) {
+  if(!G) return 0;
+  cudaSetDevice(G->ctx->device);
+  cudaStreamSynchronize(G->stream);
+  cudaFree(G->d_zob); cudaFree(G->st.black); cudaFree(G->st.white); cudaFree(G->st.hash0); cudaFree(G->st.hash1);
+  cudaFree(G->st.gameId); cudaFree(G->st.misc); cudaFree(G->d_moves); cudaFree(G->d_legal); cudaFree(G->d_status);
+  cudaFree(G->d_sitHash); cudaFree(G->d_played); cudaFree(G->d_stats); cudaFree(G->d_planes); cudaFree(G->d_global);
+  cudaFree(G->d_sym);
+  cudaEventDestroy(G->ev0); cudaEventDestroy(G->ev1);
+  cudaStreamDestroy(G->stream);
+  delete G;
+  return 0;
+}
+
+int kc_games_reset(kc_games* G, uint64_t seed, uint64_t firstGameId, int autoRefill) {
+  KC_CHECK(G, "kc_games_reset: null games");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  Geom& g = G->geom;
+  g.seed = seed;
+  g.autoRefill = autoRefill ? 1 : 0;
+  size_t n = (size_t)g.numGames;
+  std::vector<uint64_t> zero(n, 0), h0(n, g.sizeHash[0]), h1(n, g.sizeHash[1]), ids(n), misc(n, (4ULL << 40) | ((uint64_t)(1 << 3) << 56));
+  for(size_t i = 0; i < n; i++) ids[i] = firstGameId + i;
+  KC_CUDA(cudaMemcpyAsync(G->st.black, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemcpyAsync(G->st.white, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemcpyAsync(G->st.hash0, h0.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemcpyAsync(G->st.hash1, h1.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemcpyAsync(G->st.gameId, ids.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemcpyAsync(G->st.misc, misc.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  KC_CUDA(cudaMemsetAsync(G->d_stats, 0, 64, G->stream));
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  return 0;
+}
+
+int kc_games_load(kc_games* G, int g0, int n, const int8_t* stones, const int8_t* nextPla,
+                  const int16_t* moves, const int32_t* numTurns) {
+  KC_CHECK(G && stones && nextPla, "kc_games_load: null argument");
+  const Geom& g = G->geom;
+  KC_CHECK(g0 >= 0 && n > 0 && g0 + n <= g.numGames, "kc_games_load: range out of bounds");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const ZobristTables& z = zobrist();
+  std::vector<uint64_t> b(n), w(n), h0(n), h1(n), misc(n);
+  for(int i = 0; i < n; i++) {
+    uint64_t bb = 0, ww = 0, a0 = g.sizeHash[0], a1 = g.sizeHash[1];
+    for(int y = 0; y < g.H; y++)
+      for(int x = 0; x < g.W; x++) {
+        int c = stones[(size_t)i * g.HW + y * g.W + x];
+        KC_CHECK(c >= 0 && c <= 2, "kc_games_load: stone colour must be 0, 1 or 2");
+        if(c == 0) continue;
+        uint64_t bit = 1ULL << (y * g.stride + x);
+        if(c == 1) bb |= bit; else ww |= bit;
+        int spot = (x + 1) + (y + 1) * (g.W + 1);
+        a0 ^= z.board[spot][c][0]; a1 ^= z.board[spot][c][1];
+      }
+    KC_CHECK(nextPla[i] == 1 || nextPla[i] == 2, "kc_games_load: nextPla must be 1 or 2");
+    uint64_t m = 0;
+    int lastDir = 4;
+    if(moves) {
+      // moves are given oldest first; slot 0 of misc is the most recent
+      for(int k = 0; k < 5; k++) {
+        int pos = moves[((size_t)i * 5 + (4 - k)) * 2 + 0], pla = moves[((size_t)i * 5 + (4 - k)) * 2 + 1];
+        if(pos < 0) continue;
+        KC_CHECK(pos < 4 * g.HW && (pla == 1 || pla == 2), "kc_games_load: bad history entry");
+        m |= (uint64_t)((pos % g.HW) | (pla << 6)) << (8 * k);
+        if(k == 0) lastDir = pos / g.HW;
+      }
+    }
+    int nt = numTurns ? numTurns[i] : 0;
+    KC_CHECK(nt >= 0 && nt <= 255, "kc_games_load: numTurns out of range");
+    m |= ((uint64_t)lastDir << 40) | ((uint64_t)nt << 48) | ((uint64_t)(nextPla[i] << 3) << 56);
+    b[i] = bb; w[i] = ww; h0[i] = a0; h1[i] = a1; misc[i] = m;
+  }
+  KC_CUDA(cudaMemcpy(G->st.black + g0, b.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(G->st.white + g0, w.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(G->st.hash0 + g0, h0.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(G->st.hash1 + g0, h1.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(G->st.misc + g0, misc.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int kc_games_step(kc_games* G, const int16_t* movePos, uint32_t* legal, uint32_t* status,
+                  uint64_t* sitHash, int16_t* played, uint64_t* gameIds) {
+  KC_CHECK(G, "kc_games_step: null games");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  size_t n = (size_t)g.numGames;
+  if(movePos) KC_CUDA(cudaMemcpyAsync(G->d_moves, movePos, n * 2, cudaMemcpyHostToDevice, G->stream));
+  launchGames<true>(G, 0, movePos ? 1 : 0, stepOutOf(G, true), FeatOut{});
+  KC_CUDA(cudaGetLastError());
+  if(legal) KC_CUDA(cudaMemcpyAsync(legal, G->d_legal, n * g.LW * 4, cudaMemcpyDeviceToHost, G->stream));
+  if(status) KC_CUDA(cudaMemcpyAsync(status, G->d_status, n * 4, cudaMemcpyDeviceToHost, G->stream));
+  if(sitHash) KC_CUDA(cudaMemcpyAsync(sitHash, G->d_sitHash, n * 16, cudaMemcpyDeviceToHost, G->stream));
+  if(played) KC_CUDA(cudaMemcpyAsync(played, G->d_played, n * 2, cudaMemcpyDeviceToHost, G->stream));
+  if(gameIds) KC_CUDA(cudaMemcpyAsync(gameIds, G->st.gameId, n * 8, cudaMemcpyDeviceToHost, G->stream));
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  return 0;
+}
+
+int kc_games_features(kc_games* G, int layout, const int8_t* symmetry, float* planes, float* global) {
+  KC_CHECK(G && planes, "kc_games_features: null argument");
+  KC_CHECK(layout == 0 || layout == 1, "kc_games_features: layout must be 0 (NCHW) or 1 (NHWC)");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  size_t n = (size_t)g.numGames;
+  if(symmetry) {
+    for(size_t i = 0; i < n; i++) KC_CHECK(symmetry[i] >= 0 && symmetry[i] < 8, "kc_games_features: symmetry out of range");
+    KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
+  }
+  FeatOut fo{};
+  fo.planes = G->d_planes; fo.global = G->d_global; fo.symmetry = symmetry ? G->d_sym : nullptr;
+  StepOut so{};
+  launchGames<false>(G, layout == 0 ? 1 : 2, 0, so, fo);
+  KC_CUDA(cudaGetLastError());
+  KC_CUDA(cudaMemcpyAsync(planes, G->d_planes, n * 15 * g.HW * 4, cudaMemcpyDeviceToHost, G->stream));
+  if(global) KC_CUDA(cudaMemcpyAsync(global, G->d_global, n * 4, cudaMemcpyDeviceToHost, G->stream));
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  return 0;
+}
+
+int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) {
+  KC_CHECK(G && h, "kc_games_eval: null argument");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  size_t n = (size_t)g.numGames;
+  if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
+  if(symmetry) KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
+  FeatOut fo{};
+  fo.symmetry = symmetry ? G->d_sym : nullptr;
+  StepOut so{};
+  if(kc::handleIsBf16(h)) {
+    fo.tiles = (uint4*)kc::handleInputTiles(h);
+    launchGames<false>(G, 3, 0, so, fo);
+  } else {
+    fo.planes = kc::handleInputNHWC(h); fo.global = kc::handleInputGlobal(h);
+    launchGames<false>(G, 2, 0, so, fo);
+  }
+  KC_CUDA(cudaGetLastError());
+  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr);
+}
+
+int kc_games_run(kc_games* G, kc_handle* h, int plies, kc_stats* acc) {
+  KC_CHECK(G && plies > 0, "kc_games_run: bad argument");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  if(h && kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
+  KC_CUDA(cudaMemsetAsync(G->d_stats, 0, 64, G->stream));
+  float msSum = 0.f;
+  bool timeKernels = (h == nullptr);
+  if(timeKernels) KC_CUDA(cudaEventRecord(G->ev0, G->stream));
+  for(int p = 0; p < plies; p++) {
+    FeatOut fo{};
+    StepOut so = stepOutOf(G, true);
+    if(!h) {
+      fo.planes = G->d_planes; fo.global = G->d_global;
+      launchGames<true>(G, 1, 0, so, fo);
+    } else if(kc::handleIsBf16(h)) {
+      fo.tiles = (uint4*)kc::handleInputTiles(h);
+      launchGames<true>(G, 3, 0, so, fo);
+      if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
+    } else {
+      fo.planes = kc::handleInputNHWC(h); fo.global = kc::handleInputGlobal(h);
+      launchGames<true>(G, 2, 0, so, fo);
+      if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
+    }
+  }
+  if(timeKernels) KC_CUDA(cudaEventRecord(G->ev1, G->stream));
+  KC_CUDA(cudaGetLastError());
+  unsigned long long hs[8];
+  KC_CUDA(cudaMemcpyAsync(hs, G->d_stats, 64, cudaMemcpyDeviceToHost, G->stream));
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  if(timeKernels) { KC_CUDA(cudaEventElapsedTime(&msSum, G->ev0, G->ev1)); G->lastKernelMs = msSum / plies; }
+  if(acc) {
+    acc->steps += hs[0];
+    acc->evals += h ? hs[0] : 0;   // every stepped position is evaluated
+    acc->gamesFinished += hs[2]; acc->blackWins += hs[3]; acc->whiteWins += hs[4]; acc->draws += hs[5];
+    acc->checksum ^= hs[6];
+  }
+  return 0;
+}
+
+int64_t kc_games_launch_count(const kc_games* G) { return G ? G->launches : 0; }
+float kc_games_last_kernel_ms(const kc_games* G) { return G ? G->lastKernelMs : 0.f; }
+
+}  // extern "C"

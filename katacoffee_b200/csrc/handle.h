@@ -1,0 +1,47 @@
+// Compute handle shared by the fp32 check path (net_fp32.cu) and the bf16 tcgen05 path (net_bf16.cu).
+#pragma once
+#include "model.h"
+#include "net.h"
+
+namespace kc {
+struct Fp32Buffers {
+  float *in = nullptr, *global = nullptr, *mask = nullptr, *maskSum = nullptr;
+  float *trunk = nullptr, *tip = nullptr, *a = nullptr, *b = nullptr, *c = nullptr, *pool = nullptr, *bias = nullptr;
+};
+}  // namespace kc
+
+struct kc_handle {
+  kc_ctx* ctx = nullptr;
+  const kc_model* model = nullptr;
+  int maxBatch = 0, W = 0, H = 0;
+  unsigned flags = 0;
+  bool bf16 = true;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // staging of kc_forward's host rows
+  float* d_raw = nullptr; float* d_rawGlobal = nullptr; int8_t* d_sym = nullptr;
+  uint8_t* d_dstOfSrc = nullptr;     // [8][HW] copyInputsWithSymmetry map
+  uint8_t* d_dstOfSrcRev = nullptr;  // [8][HW] copyOutputsWithSymmetry map
+  // outputs (device): policy [n][4*HW], value [n][2], misc [n][2], ownership [n][HW]
+  float *d_policy = nullptr, *d_value = nullptr, *d_misc = nullptr, *d_own = nullptr;
+  kc::Fp32Buffers f32;
+  // bf16 path
+  void* d_tiles = nullptr;           // [numTiles][2][128] x 16 B input tiles
+  int numTilesAlloc = 0;
+  int* d_abort = nullptr;            // set by the trunk kernel if an mbarrier wait timed out
+  int64_t launches = 0;
+  float lastTrunkMs = 0.f;
+  // CUDA-event pairs around every trunk launch since the last kc_handle_trunk_time() call
+  std::vector<cudaEvent_t> evPool;
+  int evUsed = 0;
+  int lastN = 0;
+};
+
+namespace kc {
+// net_bf16.cu
+int allocTrunkBuffers(kc_handle* h);
+void freeTrunkBuffers(kc_handle* h);
+int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st);
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev);
+int checkTrunkAbort(kc_handle* h);   // after a synchronise: non-zero (and error set) if the kernel bailed out
+}  // namespace kc

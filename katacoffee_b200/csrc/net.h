@@ -1,0 +1,27 @@
+// Internal interface between the games kernels, the C ABI glue and the two net paths.
+#pragma once
+#include "kc_internal.h"
+
+namespace kc {
+
+// ---- trunk tile geometry (bf16 path) ----------------------------------------------------------
+// One MMA tile = 128 activation rows = NB boards laid side by side with one zero pad column each:
+//   row = y * (NB*(W+1)) + b*(W+1) + x        (x == W is the pad column, rows >= H*NB*(W+1) are dead)
+// so that a 3x3 tap (dy,dx) is the constant row shift (dy-1)*NB*(W+1) + (dx-1) and vertical
+// out-of-board taps fall into the zero halo above/below the tile.
+inline int boardsPerTile(int W, int H) { int nb = 128 / (H * (W + 1)); return nb > 4 ? 4 : nb; }
+constexpr int TILE_ROWS = 128;
+constexpr int HALO_ROWS = 32;                    // >= NB*(W+1)+1 for every supported size
+constexpr int ACT_ROWS = TILE_ROWS + 2 * HALO_ROWS;
+
+// ---- handle accessors used by games.cu ----------------------------------------------------------
+int handleCheckGeometry(kc_handle* h, int W, int H, int n);
+bool handleIsBf16(const kc_handle* h);
+void* handleInputTiles(kc_handle* h);      // bf16 path: [tiles][2][128] 16-byte chunks
+float* handleInputNHWC(kc_handle* h);      // fp32 path: [n][H*W][15]
+float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
+// Runs the net on the handle's (already symmetrised) input buffer on `stream`; symmetry_dev (device
+// pointer, may be null) is used for the inverse symmetry of the spatial outputs.
+int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev);
+
+}  // namespace kc

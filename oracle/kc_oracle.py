@@ -1,0 +1,268 @@
+"""ctypes binding of the CPU ORACLE (oracle/kc_oracle.h).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package katacoffee_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkc_oracle.so")
+REF_HASH_PATH = os.path.join(_HERE, "_ref", "libkc_ref_hash.so")
+
+
+def build(force=False):
+    """make -C oracle: the restatement always; oracle/_ref only where /root/reference exists."""
+    srcs = [os.path.join(_HERE, f) for f in ("ko_hash.cpp", "ko_game.cpp", "ko_net.cpp", "kc_oracle.h", "Makefile")]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.run(["make", "-C", _HERE, "libkc_oracle.so"], check=True, stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/cpp/core/sha2.cpp") and (force or not os.path.exists(REF_HASH_PATH)):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class StepRecord(C.Structure):
+    _fields_ = [("game", C.c_uint32), ("status", C.c_uint32), ("legal", C.c_uint32 * 5), ("movePos", C.c_int32),
+                ("sitHash", C.c_uint64 * 2), ("nnHash", C.c_uint64 * 2)]
+
+
+STEP_DTYPE = np.dtype([("game", "<u4"), ("status", "<u4"), ("legal", "<u4", (5,)), ("movePos", "<i4"),
+                       ("sitHash", "<u8", (2,)), ("nnHash", "<u8", (2,))], align=True)
+
+_lib = None
+vp = C.c_void_p
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        l = C.CDLL(LIB_PATH)
+        l.ko_splitmix64.restype = C.c_uint64
+        l.ko_splitmix64.argtypes = [C.c_uint64]
+        l.ko_rand_create.restype = vp
+        l.ko_rand_create.argtypes = [C.c_char_p]
+        l.ko_rand_destroy.argtypes = [vp]
+        l.ko_rand_next_uint.restype = C.c_uint32
+        l.ko_rand_next_uint.argtypes = [vp]
+        l.ko_rand_next_uint64.restype = C.c_uint64
+        l.ko_rand_next_uint64.argtypes = [vp]
+        l.ko_md5.argtypes = [C.c_char_p, C.c_size_t, vp]
+        l.ko_sha256.argtypes = [C.c_char_p, C.c_size_t, vp]
+        l.ko_sha256_u64.argtypes = [C.c_char_p, C.c_size_t, vp]
+        l.ko_xorshift1024_test.argtypes = [vp, C.c_int, vp]
+        l.ko_pcg32_test.argtypes = [C.c_uint64, C.c_int, vp]
+        l.ko_zobrist_tables.argtypes = [vp, vp, vp, vp]
+        l.ko_game_create.restype = vp
+        l.ko_game_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        for name in ("ko_game_destroy", "ko_game_reset"):
+            getattr(l, name).argtypes = [vp]
+        l.ko_game_set_stone.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        l.ko_game_set_last_loc.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        l.ko_game_set_history.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int]
+        l.ko_game_is_legal.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.ko_game_legal_mask.argtypes = [vp, C.c_int, vp]
+        l.ko_game_play.argtypes = [vp, C.c_int]
+        for name in ("ko_game_next_pla", "ko_game_num_turns", "ko_game_finished", "ko_game_winner"):
+            getattr(l, name).argtypes = [vp]
+        l.ko_game_status.restype = C.c_uint32
+        l.ko_game_status.argtypes = [vp]
+        l.ko_game_max_consecutives.argtypes = [vp, C.c_int, C.c_int]
+        l.ko_game_sit_hash.argtypes = [vp, C.c_int, vp]
+        l.ko_game_nn_hash.argtypes = [vp, C.c_int, C.c_double, C.c_float, C.c_double, vp]
+        l.ko_game_fill_row_v1.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+        l.ko_copy_inputs_with_symmetry.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.ko_copy_outputs_with_symmetry.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.ko_sym_dir.argtypes = [C.c_int, C.c_int]
+        l.ko_playout_choose.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+        l.ko_playout_run.restype = C.c_long
+        l.ko_playout_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, C.c_long,
+                                     vp, C.c_int, vp, C.c_int]
+        l.ko_model_create.restype = vp
+        l.ko_model_create.argtypes = [vp]
+        l.ko_model_destroy.argtypes = [vp]
+        l.ko_model_forward.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        l.ko_test_conv.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
+        l.ko_test_batchnorm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        l.ko_test_resblock.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+        l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
+        _lib = l
+    return _lib
+
+
+def ref_hash_lib():
+    """The REAL reference md5/sha2 (oracle/_ref), or None if it was not built/shipped."""
+    if not os.path.exists(REF_HASH_PATH):
+        return None
+    l = C.CDLL(REF_HASH_PATH)
+    l.kref_md5.argtypes = [C.c_char_p, C.c_size_t, vp]
+    l.kref_sha256_u64.argtypes = [C.c_char_p, C.c_size_t, vp]
+    l.kref_sha256_bytes.argtypes = [C.c_char_p, C.c_size_t, vp]
+    return l
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+class Game:
+    def __init__(self, x=5, y=5, k=4):
+        self.W, self.H, self.K = x, y, k
+        self.HW = x * y
+        self.LW = (4 * self.HW + 31) // 32
+        self._g = lib().ko_game_create(x, y, k)
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib().ko_game_destroy(self._g)
+            self._g = None
+
+    def reset(self):
+        lib().ko_game_reset(self._g)
+
+    def set_stone(self, x, y, color):
+        return lib().ko_game_set_stone(self._g, x, y, color)
+
+    def set_last_loc(self, x, y, d):
+        lib().ko_game_set_last_loc(self._g, x, y, d)
+
+    def set_history(self, moves, num_turns, next_pla):
+        """moves: list of (pos, pla) oldest first (pos = policy index)."""
+        n = len(moves)
+        pos = np.array([m[0] for m in moves], np.int32)
+        pla = np.array([m[1] for m in moves], np.int32)
+        lib().ko_game_set_history(self._g, n, _p(pos), _p(pla), num_turns, next_pla)
+
+    def is_legal(self, x, y, d, pla):
+        return bool(lib().ko_game_is_legal(self._g, x, y, d, pla))
+
+    def legal_mask(self, pla=None):
+        out = np.zeros(13, np.uint32)
+        n = lib().ko_game_legal_mask(self._g, self.next_pla() if pla is None else pla, _p(out))
+        return out[:self.LW].copy(), n
+
+    def play(self, pos):
+        return bool(lib().ko_game_play(self._g, pos))
+
+    def next_pla(self):
+        return lib().ko_game_next_pla(self._g)
+
+    def num_turns(self):
+        return lib().ko_game_num_turns(self._g)
+
+    def finished(self):
+        return bool(lib().ko_game_finished(self._g))
+
+    def winner(self):
+        return lib().ko_game_winner(self._g)
+
+    def status(self):
+        return int(lib().ko_game_status(self._g))
+
+    def sit_hash(self, pla=None):
+        out = np.zeros(2, np.uint64)
+        lib().ko_game_sit_hash(self._g, self.next_pla() if pla is None else pla, _p(out))
+        return out
+
+    def nn_hash(self, pla=None, pda=0.0, temp=1.0, optimism=0.0):
+        out = np.zeros(2, np.uint64)
+        lib().ko_game_nn_hash(self._g, self.next_pla() if pla is None else pla, pda, temp, optimism, _p(out))
+        return out
+
+    def fill_row_v1(self, nhwc=False, pla=None):
+        row = np.zeros(15 * self.HW, np.float32)
+        g = np.zeros(1, np.float32)
+        lib().ko_game_fill_row_v1(self._g, self.next_pla() if pla is None else pla, self.W, self.H, int(nhwc), _p(row), _p(g))
+        return row, g
+
+    def choose(self, seed, game_idx):
+        return lib().ko_playout_choose(self._g, seed, game_idx, None)
+
+
+def playout_run(x, y, k, seed, g0, n, max_plies=255, planes=True, nhwc=False, threads=1, max_records=None):
+    hw = x * y
+    if max_records is None:
+        max_records = n * (hw + 1)
+    recs = np.zeros(max_records, STEP_DTYPE)
+    assert STEP_DTYPE.itemsize == C.sizeof(StepRecord)
+    pl = np.zeros((max_records, 15 * hw), np.float32) if planes else None
+    gl = np.zeros(max_records, np.float32) if planes else None
+    total = lib().ko_playout_run(x, y, k, seed, g0, n, max_plies, _p(recs), max_records, _p(pl), int(nhwc), _p(gl), threads)
+    return recs[:total], (pl[:total] if planes else None), (gl[:total] if planes else None)
+
+
+def copy_inputs_with_symmetry(src, n, h, w, c, nhwc, sym):
+    src = np.ascontiguousarray(src, np.float32)
+    dst = np.zeros_like(src)
+    lib().ko_copy_inputs_with_symmetry(_p(src), _p(dst), n, h, w, c, int(nhwc), sym)
+    return dst
+
+
+def copy_outputs_with_symmetry(src, n, h, w, sym):
+    src = np.ascontiguousarray(src, np.float32)
+    dst = np.zeros_like(src)
+    lib().ko_copy_outputs_with_symmetry(_p(src), _p(dst), n, h, w, sym)
+    return dst
+
+
+class Model:
+    """Oracle copy of a katacoffee_b200.modeldesc.Model (same POD description)."""
+
+    def __init__(self, model):
+        self.model = model
+        self._m = lib().ko_model_create(C.byref(model.desc))
+
+    def __del__(self):
+        if getattr(self, "_m", None):
+            lib().ko_model_destroy(self._m)
+            self._m = None
+
+    def forward(self, rowSpatial, rowGlobal, x, y, symmetry=None, nhwc=False, mode=0, threads=1):
+        n = rowSpatial.shape[0]
+        hw = x * y
+        rs = np.ascontiguousarray(rowSpatial, np.float32)
+        rg = np.ascontiguousarray(rowGlobal, np.float32)
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8)
+        policy = np.zeros((n, 4 * hw), np.float32)
+        value = np.zeros((n, 2), np.float32)
+        misc = np.zeros((n, 2), np.float32)
+        own = np.zeros((n, hw), np.float32)
+        lib().ko_model_forward(self._m, n, x, y, int(nhwc), _p(rs), _p(rg), _p(sym), _p(policy), _p(value), _p(misc), _p(own), mode, threads)
+        return policy, value, misc, own
+
+
+def test_conv(desc_struct, n, xlen, ylen, nhwc, inp, out_channels, mode=0):
+    inp = np.ascontiguousarray(inp, np.float32)
+    out = np.zeros(n * xlen * ylen * out_channels, np.float32)
+    lib().ko_test_conv(C.byref(desc_struct), n, xlen, ylen, int(nhwc), _p(inp), _p(out), mode)
+    return out
+
+
+def test_batchnorm(desc_struct, activation, n, xlen, ylen, nhwc, inp, mask):
+    inp = np.ascontiguousarray(inp, np.float32)
+    mask = np.ascontiguousarray(mask, np.float32)
+    out = np.zeros_like(inp)
+    lib().ko_test_batchnorm(C.byref(desc_struct), activation, n, xlen, ylen, int(nhwc), _p(inp), _p(mask), _p(out))
+    return out
+
+
+def test_resblock(block_struct, n, xlen, ylen, nhwc, inp, mask, mode=0):
+    inp = np.ascontiguousarray(inp, np.float32)
+    mask = np.ascontiguousarray(mask, np.float32)
+    out = np.zeros_like(inp)
+    lib().ko_test_resblock(C.byref(block_struct), n, xlen, ylen, int(nhwc), _p(inp), _p(mask), _p(out), mode)
+    return out
+
+
+def postprocess(policy, legal_mask, value2, misc2, next_pla, temp=1.0):
+    p = np.ascontiguousarray(policy, np.float32).copy()
+    v = np.ascontiguousarray(value2, np.float32).copy()
+    m = np.ascontiguousarray(misc2, np.float32).copy()
+    lm = np.ascontiguousarray(legal_mask, np.uint32)
+    lib().ko_postprocess(_p(p), p.shape[0], _p(lm), temp, _p(v), _p(m), next_pla)
+    return p, v, m

@@ -1,0 +1,368 @@
+"""GPU parity tests proper: every call goes through the C ABI and is compared with the CPU oracle
+on the same seeded inputs.  Integer/byte results (legal masks, status, sit-hashes, planes) must be
+bit-exact; the net within 1e-4 (fp32 check mode) / 1e-2 (bf16 tcgen05) absolute, the tolerances
+BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_BF16 = 1e-2
+
+
+def bf16_bits(a):
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def bf16_round(a):
+    return (bf16_bits(a).astype(np.uint32) << 16).view(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K,shift,rowsA", [(128, 16, 0, 128), (128, 64, 0, 136), (128, 64, 3, 160), (96, 128, 25, 192),
+                                             (128, 128, 57, 192), (16, 32, 1, 130), (256, 32, 8, 144)])
+def test_umma_selftest(ctx, N, K, shift, rowsA):
+    """tcgen05.mma with the trunk's descriptor conventions (K-major, no swizzle, row-shifted A)."""
+    from katacoffee_b200 import backend
+    rng = np.random.default_rng(N * 1000 + K + shift)
+    A = bf16_round(rng.standard_normal((rowsA, K)).astype(np.float32))
+    B = bf16_round(rng.standard_normal((N, K)).astype(np.float32))
+    D = backend.selftestUmma(ctx, bf16_bits(A), bf16_bits(B), shift)
+    ref = A[shift:shift + 128].astype(np.float64) @ B.astype(np.float64).T
+    assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------------
+LAYER_CASES = golden("nn_layers_golden.json")
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=[c["label"] for c in LAYER_CASES])
+@pytest.mark.parametrize("nhwc", [0, 1])
+def test_layer_hooks_golden(ctx, case, nhwc):
+    """NeuralNet::testEvaluate* through the C ABI against the reference's literal vectors
+    (tests/testnn.cpp), reference tolerance."""
+    from katacoffee_b200 import backend
+    n, xl, yl = case["batchSize"], case["nnXLen"], case["nnYLen"]
+    d, kind = case["desc"], case["kind"]
+    if kind == "conv":
+        ic, oc = d["inChannels"], d["outChannels"]
+    elif kind == "batchnorm":
+        ic = oc = d["numChannels"]
+    else:
+        ic = oc = d["preBN"]["numChannels"]
+    inp = np.asarray(case["input"], np.float32)
+    exp = np.asarray(case["expected"], np.float32)
+    if nhwc:
+        inp = inp.reshape(n, ic, yl, xl).transpose(0, 2, 3, 1).reshape(-1)
+        exp = exp.reshape(n, oc, yl, xl).transpose(0, 2, 3, 1).reshape(-1)
+    if kind == "conv":
+        out = backend.testEvaluateConv(ctx, d, n, xl, yl, nhwc, inp)
+    elif kind == "batchnorm":
+        out = backend.testEvaluateBatchNorm(ctx, d, n, xl, yl, nhwc, inp, case["mask"])
+    else:
+        out = backend.testEvaluateResidualBlock(ctx, d, n, xl, yl, nhwc, inp, case["mask"])
+    tol = 1e-4 * np.maximum(np.maximum(np.abs(out[:exp.size]), np.abs(exp)), 1.0)
+    assert (np.abs(out[:exp.size] - exp) < tol).all()
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_trajectories(oracle, W, H, K, seed, G, planes=True, nhwc=False):
+    recs, pl, gl = oracle.playout_run(W, H, K, seed, 0, G, planes=planes, nhwc=nhwc, threads=8)
+    starts = np.flatnonzero(recs["movePos"] == -1)
+    ends = np.append(starts[1:], len(recs))
+    return recs, pl, gl, starts, ends
+
+
+@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 4096, 1), (6, 6, 4, 1500, 20261018), (5, 5, 4, 333, 7), (7, 7, 5, 200, 3), (4, 5, 3, 257, 9)])
+def test_games_step_bit_exact(ctx, oracle, W, H, K, G, seed):
+    """Random-legal playouts to terminal: legal masks, status words (ply/finished/winner/next
+    player), sit-hashes and the played move of every step equal the oracle's, bit for bit."""
+    from katacoffee_b200 import backend
+    recs, _, _, starts, ends = oracle_trajectories(oracle, W, H, K, seed, G, planes=False)
+    LW = (4 * W * H + 31) // 32
+    games = backend.Games(ctx, G, W, H, K)
+    games.reset(seed=seed)
+    lengths = ends - starts
+    checked = 0
+    for t in range(1, int(lengths.max()) + 1):
+        out = games.step()
+        live = lengths > t
+        idx = starts + np.minimum(t, lengths - 1)
+        r = recs[idx]
+        assert (out["status"] == r["status"]).all(), t
+        assert (out["sitHash"] == r["sitHash"]).all(), t
+        assert (out["legal"] == r["legal"][:, :LW]).all(), t
+        assert (out["played"][live] == r["movePos"][live]).all(), t
+        assert (out["played"][~live] == -1).all(), t
+        checked += int(live.sum())
+    assert checked == len(recs) - G
+    # one more step changes nothing: every game is finished
+    out2 = games.step()
+    assert (out2["status"] == out["status"]).all() and (out2["played"] == -1).all()
+    games.close()
+
+
+@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 2048, 1), (6, 6, 4, 700, 5)])
+def test_features_bit_exact(ctx, oracle, W, H, K, G, seed):
+    """NNInputs::fillRowV1 planes (NCHW and NHWC) + global feature at every ply, incl. terminal positions."""
+    from katacoffee_b200 import backend
+    recs, pl, gl, starts, ends = oracle_trajectories(oracle, W, H, K, seed, G)
+    lengths = ends - starts
+    games = backend.Games(ctx, G, W, H, K)
+    games.reset(seed=seed)
+    HW = W * H
+    for t in range(0, int(lengths.max())):
+        if t > 0:
+            games.step()
+        idx = starts + np.minimum(t, lengths - 1)
+        planes, glob = games.features(nhwc=False)
+        assert (planes == pl[idx]).all(), t
+        assert (glob[:, 0] == gl[idx]).all()
+        if t % 5 == 0:
+            p2, _ = games.features(nhwc=True)
+            assert (p2.reshape(G, HW, 15).transpose(0, 2, 1).reshape(G, -1) == pl[idx]).all(), t
+    games.close()
+
+
+def test_features_with_symmetry_bit_exact(ctx, oracle):
+    """copyInputsWithSymmetry fused into the feature kernel equals the oracle's copy of the plain planes."""
+    from katacoffee_b200 import backend
+    G, W, H = 1024, 5, 5
+    games = backend.Games(ctx, G, W, H, 4)
+    games.reset(seed=11)
+    for _ in range(6):
+        games.step()
+    base, _ = games.features(nhwc=False)
+    sym = (np.arange(G) % 8).astype(np.int8)
+    for nhwc in (False, True):
+        got, _ = games.features(nhwc=nhwc, symmetry=sym)
+        for s in range(8):
+            sel = np.flatnonzero(sym == s)
+            src = base[sel]
+            if nhwc:
+                src = src.reshape(-1, 15, 25).transpose(0, 2, 1).reshape(len(sel), -1)
+            exp = oracle.copy_inputs_with_symmetry(src, len(sel), H, W, 15, nhwc, s)
+            assert (got[sel] == exp).all(), (nhwc, s)
+    games.close()
+
+
+def test_forced_moves_illegal_and_load(ctx, oracle):
+    """kc_games_step with explicit moves (legal, illegal, skip) and kc_games_load of arbitrary positions."""
+    from katacoffee_b200 import backend
+    rng = np.random.default_rng(4)
+    G, W, H, K = 512, 5, 5, 4
+    HW = W * H
+    stones = np.zeros((G, HW), np.int8)
+    nextPla = np.zeros(G, np.int8)
+    moves = np.full((G, 5, 2), -1, np.int16)
+    numTurns = np.zeros(G, np.int32)
+    ogames = []
+    for g in range(G):
+        og = oracle.Game(W, H, K)
+        nst = int(rng.integers(0, 18))
+        cells = rng.permutation(HW)[:nst]
+        hist = []
+        for i, c in enumerate(cells):
+            col = 1 + int(rng.integers(0, 2))
+            stones[g, c] = col
+            og.set_stone(int(c % W), int(c // W), col)
+        # history: last up-to-5 stones as moves with random directions and (mostly) alternating players
+        pla = 1 + int(rng.integers(0, 2))
+        nextPla[g] = pla
+        nh = min(len(cells), int(rng.integers(0, 6)))
+        p = pla
+        for j in range(nh):
+            p = p ^ 3 if rng.random() < 0.85 else p
+            hist.append((int(rng.integers(0, 4)) * HW + int(cells[len(cells) - 1 - j]), p))
+        hist = hist[::-1]
+        for j, (ps, pl_) in enumerate(hist):
+            moves[g, 5 - len(hist) + j] = (ps, pl_)
+        numTurns[g] = int(rng.integers(len(hist), len(hist) + 3))
+        og.set_history(hist, int(numTurns[g]), pla)
+        ogames.append(og)
+    games = backend.Games(ctx, G, W, H, K)
+    games.load(0, stones, nextPla, moves, numTurns)
+    planes, glob = games.features()
+    for g in range(G):
+        assert (planes[g] == ogames[g].fill_row_v1()[0]).all(), g
+    # forced moves: a third legal, a third illegal/occupied, a third skipped
+    mv = np.full(G, -1, np.int16)
+    exp_ok = np.zeros(G, bool)
+    for g in range(G):
+        mode = g % 3
+        if mode == 0:
+            mask, n = ogames[g].legal_mask()
+            legal = [p for p in range(4 * HW) if (mask[p >> 5] >> (p & 31)) & 1]
+            if legal:
+                mv[g] = legal[int(rng.integers(0, len(legal)))]
+                exp_ok[g] = True
+        elif mode == 1:
+            mv[g] = int(rng.integers(0, 4 * HW))
+            exp_ok[g] = ogames[g].play(int(mv[g])) if False else False
+    # apply to oracle
+    illegal_expected = np.zeros(G, bool)
+    for g in range(G):
+        if mv[g] >= 0:
+            ok = ogames[g].play(int(mv[g]))
+            illegal_expected[g] = not ok
+    out = games.step(mv)
+    for g in range(G):
+        st = int(out["status"][g])
+        assert bool(st >> 15 & 1) == bool(illegal_expected[g]), g
+        assert (st & 0x7fff) == ogames[g].status(), g
+        assert (out["sitHash"][g] == ogames[g].sit_hash()).all(), g
+        assert (out["legal"][g] == ogames[g].legal_mask()[0]).all(), g
+    planes, _ = games.features()
+    for g in range(G):
+        assert (planes[g] == ogames[g].fill_row_v1()[0]).all(), g
+    games.close()
+
+
+# ------------------------------------------------------------------------------------------------
+def position_batch(oracle, W, H, K, seed, n):
+    recs, pl, gl = oracle.playout_run(W, H, K, seed, 0, max(8, n // 8), threads=8)
+    sel = np.random.default_rng(seed).permutation(len(recs))[:n]
+    return pl[sel], gl[sel].reshape(-1, 1)
+
+
+@pytest.mark.parametrize("net,W,H,n", [("b2c32", 5, 5, 37), ("b6c96", 5, 5, 200), ("b10c128", 5, 5, 64), ("b6c96", 6, 6, 50)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_forward_matches_oracle(ctx, oracle, net, W, H, n, mode):
+    """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward."""
+    from katacoffee_b200 import backend, modeldesc
+    model = modeldesc.Model(net, seed=5)
+    om = oracle.Model(model)
+    planes, glob = position_batch(oracle, W, H, 4, 3, n)
+    sym = (np.arange(n) % 8).astype(np.int8)
+    ep, ev, em, eo = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, maxBatchSize=max(n, 64), nnXLen=W, nnYLen=H, useFP32Check=(mode == "fp32"))
+    assert h.isUsingBF16() == (mode == "bf16")
+    p, v, m, o = backend.getOutput(h, planes, glob, sym)
+    tol = TOL_FP32 if mode == "fp32" else TOL_BF16
+    errs = [np.abs(p - ep).max(), np.abs(v - ev).max(), np.abs(m - em).max(), np.abs(o - eo).max()]
+    assert max(errs) < tol, errs
+    assert np.abs(ep).max() > 0.05 and np.abs(ev).max() > 0.01     # the comparison is not vacuous
+    # NHWC rows, no symmetry
+    h2 = backend.createComputeHandle(ctx, lm, max(n, 64), W, H, useFP32Check=(mode == "fp32"), inputsUseNHWC=True)
+    nhwc = planes.reshape(n, 15, W * H).transpose(0, 2, 1).reshape(n, -1)
+    p2, v2, m2, o2 = backend.getOutput(h2, nhwc, glob, None)
+    ep2, ev2, em2, eo2 = om.forward(planes, glob, W, H, mode=0, threads=8)
+    assert max(np.abs(p2 - ep2).max(), np.abs(v2 - ev2).max(), np.abs(m2 - em2).max(), np.abs(o2 - eo2).max()) < tol
+    for x in (h, h2, lm):
+        x.close()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
+    """kc_games_eval: planes generated on the device straight into the net input (no PCIe), with symmetry."""
+    from katacoffee_b200 import backend, modeldesc
+    G, W, H = 777, 5, 5
+    model = modeldesc.Model("b6c96", seed=2)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=(mode == "fp32"))
+    games = backend.Games(ctx, G, W, H, 4)
+    games.reset(seed=21)
+    for _ in range(9):
+        games.step()
+    planes, glob = games.features()
+    sym = ((np.arange(G) * 5) % 8).astype(np.int8)
+    games.eval(h, sym)
+    p, v, m, o = h.readOutputs(G)
+    ep, ev, em, eo = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    tol = TOL_FP32 if mode == "fp32" else TOL_BF16
+    assert max(np.abs(p - ep).max(), np.abs(v - ev).max(), np.abs(m - em).max(), np.abs(o - eo).max()) < tol
+    for x in (games, h, lm):
+        x.close()
+
+
+def test_run_counters_and_checksum(ctx, oracle):
+    """kc_games_run (the bench hot loop, rules+features only): counters and the XOR checksum of all
+    sit-hashes equal the oracle's over the same trajectories; with refill every lane steps every ply."""
+    from katacoffee_b200 import backend
+    G, W, H, K, seed = 4096, 5, 5, 4, 20261018
+    recs, _, _, starts, ends = oracle_trajectories(oracle, W, H, K, seed, G, planes=False)
+    moved = recs[recs["movePos"] >= 0]
+    games = backend.Games(ctx, G, W, H, K)
+    games.reset(seed=seed)
+    st = games.run(None, 30)
+    assert st.steps == len(moved)
+    assert st.checksum == int(np.bitwise_xor.reduce(moved["sitHash"][:, 0]))
+    fin = moved[(moved["status"] >> 8) & 1 == 1]
+    assert st.gamesFinished == G == len(fin)
+    w = (fin["status"] >> 9) & 3
+    assert (st.blackWins, st.whiteWins, st.draws) == (int((w == 1).sum()), int((w == 2).sum()), int((w == 0).sum()))
+    # refill: lane i plays games i, i+G, i+2G ...
+    games.reset(seed=seed, autoRefill=True)
+    plies = 40
+    st2 = games.run(None, plies)
+    assert st2.steps == G * plies
+    recs3, _, _ = oracle.playout_run(W, H, K, seed, 0, 3 * G, planes=False, threads=8)
+    starts3 = np.flatnonzero(recs3["movePos"] == -1)
+    len3 = np.append(starts3[1:], len(recs3)) - starts3 - 1     # moves per game
+    x = 0
+    for lane in range(G):
+        left, gidx = plies, lane
+        while left > 0:
+            k = min(left, int(len3[gidx]))
+            seg = recs3[starts3[gidx] + 1: starts3[gidx] + 1 + k]
+            x ^= int(np.bitwise_xor.reduce(seg["sitHash"][:, 0]))
+            left -= k
+            gidx += G
+    assert st2.checksum == x
+    games.close()
+
+
+def test_million_positions_full_size_parity(ctx, oracle):
+    """BASELINE config 2 at full size (65536 concurrent 5x5 games to terminal, ~1.3 M positions):
+    size-independent check = checksum-of-sit-hashes + outcome counters against the oracle, plus
+    bit-exact planes/legal/status on a random sample of lanes at every ply."""
+    from katacoffee_b200 import backend
+    G, W, H, K, seed = 65536, 5, 5, 4, 1
+    recs, _, _, starts, ends = oracle_trajectories(oracle, W, H, K, seed, G, planes=False)
+    moved = recs[recs["movePos"] >= 0]
+    assert len(moved) > 1_000_000
+    games = backend.Games(ctx, G, W, H, K)
+    games.reset(seed=seed)
+    st = games.run(None, 26)
+    assert st.steps == len(moved)
+    assert st.checksum == int(np.bitwise_xor.reduce(moved["sitHash"][:, 0]))
+    assert st.gamesFinished == G
+    # sampled lanes, every ply, all outputs
+    games.reset(seed=seed)
+    lanes = np.random.default_rng(0).permutation(G)[:512]
+    og = [oracle.Game(W, H, K) for _ in lanes]
+    for t in range(1, 26):
+        out = games.step()
+        planes, _ = games.features()
+        for j, lane in enumerate(lanes):
+            if not og[j].finished():
+                og[j].play(og[j].choose(seed, int(lane)))
+            assert og[j].status() == int(out["status"][lane])
+            assert (og[j].sit_hash() == out["sitHash"][lane]).all()
+            assert (og[j].legal_mask()[0] == out["legal"][lane]).all()
+            assert (og[j].fill_row_v1()[0] == planes[lane]).all()
+    games.close()
+
+
+def test_bf16_full_batch_and_odd_sizes(ctx, oracle):
+    """Tile/CTA boundary cases of the persistent trunk kernel: n = 1, NB-1, NB+1, odd tile counts, > one wave."""
+    from katacoffee_b200 import backend, modeldesc
+    model = modeldesc.Model("b2c32", seed=9)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    planes, glob = position_batch(oracle, 5, 5, 4, 17, 2500)
+    ep, ev, em, eo = om.forward(planes, glob, 5, 5, mode=0, threads=8)
+    h = backend.createComputeHandle(ctx, lm, 2500, 5, 5)
+    for n in (1, 3, 4, 5, 8, 9, 1185, 2500):
+        p, v, m, o = backend.getOutput(h, planes[:n], glob[:n], None)
+        err = max(np.abs(p - ep[:n]).max(), np.abs(v - ev[:n]).max(), np.abs(m - em[:n]).max(), np.abs(o - eo[:n]).max())
+        assert err < TOL_BF16, (n, err)
+    h.close(); lm.close()
