@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path's throughput on B200 (and the CPU reference arm beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json: "NN evals/s ... 5x5 k=4, b10c128"): every GPU owns G concurrent 5x5 k=4
+Coffee games.  One STEP = one ply of the fused leaf-evaluation hot path for all G games:
+  rules kernel (random-legal move, win/draw, sit-hash, legal mask, auto-refill of finished games)
+  -> V1 planes written in bf16 straight into the trunk's input tiles
+  -> b10c128 forward (one persistent tcgen05 kernel) -> policy / value / misc / ownership logits,
+so a step evaluates G positions.  `value` = positions evaluated per second, whole job, inputs
+resident in HBM, timed per step with CUDA events on the launching stream (max over ranks).
+`e2e` = the same metric through the reference-facing call (kc_forward == NeuralNet::getOutput)
+with HOST rows in pinned memory: H2D of the planes and D2H of the logits inside the timed region.
+`--impl reference` times the CPU restatement of the reference's own path (oracle: mailbox rules +
+fillRowV1 + Winograd/GEMM fp32 forward as the Eigen backend does) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NET = "b10c128"
+W = H = 5
+WINLEN = 4
+SEED = 20261018
+GAMES_PER_GPU = 148 * 128            # 18944: 8 boards per CTA work item -> 16 items per SM, no tail
+L2_FLUSH_BYTES = 256 << 20           # > 126 MB L2, written between timed steps
+BYTES_PER_STEP_FP32 = 1572           # rules+features algorithmic bytes per game-step (fp32 planes)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def cpu_reference_run(positions_per_step, steps, warmup, threads):
+    """The reference's own CPU path, restated (oracle): random-legal playouts with mailbox rules,
+    fillRowV1 (NHWC, as the Eigen backend wants) and the Winograd/GEMM fp32 forward in batches of 4
+    per thread (cpp/program/setup.cpp:299), over all host threads.  Returns evals/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import kc_oracle
+    from katacoffee_b200 import modeldesc
+    kc_oracle.build()
+    model = modeldesc.Model(NET, seed=1)
+    om = kc_oracle.Model(model)
+    games = max(8, positions_per_step // 16)
+    per_step = []
+    g0 = 0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        recs, planes, glob = kc_oracle.playout_run(W, H, WINLEN, SEED, g0, games, planes=True, nhwc=True, threads=threads,
+                                                   max_records=positions_per_step)
+        n = len(recs)
+        om.forward(planes, glob.reshape(-1, 1), W, H, symmetry=None, nhwc=True, mode=1, threads=threads)
+        dt = time.perf_counter() - t0
+        g0 += games
+        if s >= warmup:
+            per_step.append((n, dt))
+    tot_n = sum(n for n, _ in per_step)
+    tot_t = sum(t for _, t in per_step)
+    return tot_n / tot_t, tot_t / len(per_step) * 1e3, tot_n // len(per_step)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    positions = 768
+    evals_s, ms_step, n = cpu_reference_run(positions, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "nn_evals_per_s", "value": evals_s, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args.games), cpu_sample_positions_per_step=n),
+        "cpu_baseline": {"value": evals_s, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} positions per step: oracle mailbox rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward, batch 4 per thread"},
+        "e2e": {"value": evals_s, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(games_per_gpu):
+    return {"workload": f"5x5 k=4 Coffee leaf evaluation: rules step + V1 planes + {NET} forward per ply "
+                        "(BASELINE.json configs[2] net on configs[1]-style concurrent random-legal games)",
+            "net": NET, "board": "5x5", "win_len": WINLEN, "games_per_gpu": games_per_gpu, "seed": SEED,
+            "weights": "random-init (modeldesc rms-calibrated)", "l2": f"{L2_FLUSH_BYTES >> 20} MiB scratch overwritten between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    rank, world, local = dist_setup(args.gpus)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        torch.distributed.barrier()
+    from katacoffee_b200 import backend, modeldesc
+    G = args.games
+    peaks = load_peaks()
+    ctx = backend.createComputeContext(local)
+    model = modeldesc.Model(NET, seed=1)
+    lm = backend.LoadedModel(ctx, model)
+    handle = backend.createComputeHandle(ctx, lm, G, W, H)
+    games = backend.Games(ctx, G, W, H, WINLEN)
+    games.reset(seed=SEED, firstGameId=rank * (1 << 40), autoRefill=True)   # shard: disjoint game ids per rank
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (`value`) ----------------
+    games.runTimed(handle, args.warmup, L2_FLUSH_BYTES)
+    handle.trunkTime()
+    l0 = games.launchCount() + handle.launchCount()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    stats, ms_total = games.runTimed(handle, args.steps, L2_FLUSH_BYTES)
+    t1 = time.time()
+    barrier()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = games.launchCount() + handle.launchCount() - l0
+    trunk_ms, trunk_n = handle.trunkTime()
+    ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    counters = torch.tensor([stats.steps, stats.evals, stats.gamesFinished, stats.blackWins, stats.whiteWins, stats.draws],
+                            dtype=torch.int64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(ms_t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.reduce(counters, dst=0, op=torch.distributed.ReduceOp.SUM)   # the end-of-run NCCL reduce of statistics
+    ms_max = float(ms_t.item())
+    total_evals = G * args.steps * world
+    value = total_evals / (ms_max * 1e-3)
+
+    # rules+features alone (the HBM-bound kernel), fp32 NCHW planes + masks + hashes: secondary roofline
+    games_rf = backend.Games(ctx, 65536, W, H, WINLEN)
+    games_rf.reset(seed=SEED, autoRefill=True)
+    games_rf.runTimed(None, 3, L2_FLUSH_BYTES)
+    _, rf_ms = games_rf.runTimed(None, 20, L2_FLUSH_BYTES)
+    rf_steps_s = 65536 * 20 / (rf_ms * 1e-3)
+    games_rf.close()
+
+    # ---------------- host-buffer arm (`e2e`) ----------------
+    hw = W * H
+    nbuf = 4
+    pinned = [torch.empty((G, 15 * hw), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    glob_h = torch.full((G, 1), float(WINLEN)).pin_memory()
+    sym_h = np.zeros(G, np.int8)
+    for i in range(nbuf):
+        games.run(None, 2)
+        p, _ = games.features(nhwc=False)
+        pinned[i].numpy()[:] = p
+    outs = (torch.empty((G, 4 * hw)).pin_memory().numpy(), torch.empty((G, 2)).pin_memory().numpy(),
+            torch.empty((G, 2)).pin_memory().numpy(), torch.empty((G, hw)).pin_memory().numpy())
+    for i in range(args.warmup):
+        backend.getOutput(handle, pinned[i % nbuf].numpy(), glob_h.numpy(), sym_h, out=outs)
+    barrier()
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        backend.getOutput(handle, pinned[i % nbuf].numpy(), glob_h.numpy(), sym_h, out=outs)
+    te = time.perf_counter() - te0
+    barrier()
+    te_t = torch.tensor([te], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(te_t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = total_evals / float(te_t.item())
+    h2d = G * (15 * hw * 4 + 4 + 1)
+    d2h = G * (4 * hw * 4 + 8 + 8 + hw * 4)
+
+    if rank == 0:
+        flops = modeldesc.flops_per_eval(NET, hw)
+        trunk_avg_ms = trunk_ms / max(trunk_n, 1)
+        achieved = flops * G / (trunk_avg_ms * 1e-3) / 1e12
+        line = {
+            "metric": "nn_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(G),
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "kc_forward (NeuralNet::getOutput) with pinned host rows"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "trunk_kernel (tcgen05 whole-net forward)", "bound": "tensor", "achieved": achieved,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
+            "roofline_rules_features": {"kernel": "games_kernel<step, fp32 NCHW planes> at 65536 games", "bound": "hbm",
+                                        "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
+                                        "bytes_per_game_step": BYTES_PER_STEP_FP32},
+            "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
+                      "black_wins": int(counters[3]), "white_wins": int(counters[4]), "draws": int(counters[5])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            # bounded sample: calibrate on a small batch, then ~10 s of CPU work
+            r0, _, _ = cpu_reference_run(128, 1, 0, threads)
+            sample = int(min(8192, max(256, r0 * 10)))
+            r, _, n = cpu_reference_run(sample, 1, 0, threads)
+            line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} positions: oracle rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward (Eigen-algorithm restatement), batch 4 per thread"}
+        print(json.dumps(line), flush=True)
+    for o in (games, handle, lm, ctx):
+        o.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,6 +193,10 @@ typedef struct {
   uint64_t checksum;   /* XOR of sitHash0 of every position reached (cheap cross-check vs oracle) */
 } kc_stats;
 int kc_games_run(kc_games* g, kc_handle* h, int plies, kc_stats* statsAccum);
+/* Same, timed on the device: every ply is bracketed by a CUDA-event pair on the launching stream and
+ * *msTotal receives the sum of the per-ply durations; flushL2Bytes > 0 overwrites a scratch buffer of
+ * that size between plies (outside the timed windows) so no ply finds its inputs in L2 by accident. */
+int kc_games_run_timed(kc_games* g, kc_handle* h, int plies, size_t flushL2Bytes, kc_stats* statsAccum, float* msTotal);
 int64_t kc_games_launch_count(const kc_games* g);
 /* Average device time in ms per ply of the rules+features kernel in the last kc_games_run. */
 float kc_games_last_kernel_ms(const kc_games* g);

@@ -205,6 +205,13 @@ class Games:
         check(lib().kc_games_run(self._p, handle._p if handle is not None else None, plies, C.byref(st)))
         return st
 
+    def runTimed(self, handle, plies, flushL2Bytes=0, stats=None):
+        """Returns (stats, device milliseconds summed over the plies)."""
+        st = stats if stats is not None else capi.Stats()
+        ms = C.c_float()
+        check(lib().kc_games_run_timed(self._p, handle._p if handle is not None else None, plies, flushL2Bytes, C.byref(st), C.byref(ms)))
+        return st, ms.value
+
     def launchCount(self):
         return int(lib().kc_games_launch_count(self._p))
 

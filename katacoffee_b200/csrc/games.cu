@@ -425,7 +425,8 @@ struct kc_games {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   float lastKernelMs = 0.f;
-  uint64_t nextId = 0;
+  std::vector<cudaEvent_t> evPool;   // one (start, stop) pair per ply of kc_games_run_timed
+  void* d_flush = nullptr; size_t flushBytes = 0;
 };
 
 namespace {
@@ -521,7 +522,8 @@ int kc_games_destroy(kc_games* G) {
   cudaFree(G->d_zob); cudaFree(G->st.black); cudaFree(G->st.white); cudaFree(G->st.hash0); cudaFree(G->st.hash1);
   cudaFree(G->st.gameId); cudaFree(G->st.misc); cudaFree(G->d_moves); cudaFree(G->d_legal); cudaFree(G->d_status);
   cudaFree(G->d_sitHash); cudaFree(G->d_played); cudaFree(G->d_stats); cudaFree(G->d_planes); cudaFree(G->d_global);
-  cudaFree(G->d_sym);
+  cudaFree(G->d_sym); cudaFree(G->d_flush);
+  for(cudaEvent_t e : G->evPool) cudaEventDestroy(e);
   cudaEventDestroy(G->ev0); cudaEventDestroy(G->ev1);
   cudaStreamDestroy(G->stream);
   delete G;
@@ -654,16 +656,27 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) {
   return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr);
 }
 
-int kc_games_run(kc_games* G, kc_handle* h, int plies, kc_stats* acc) {
+int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes, kc_stats* acc, float* msTotal) {
   KC_CHECK(G && plies > 0, "kc_games_run: bad argument");
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const Geom& g = G->geom;
   if(h && kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
+  if(flushL2Bytes > G->flushBytes) {
+    cudaFree(G->d_flush);
+    G->d_flush = nullptr; G->flushBytes = 0;
+    KC_CUDA(cudaMalloc(&G->d_flush, flushL2Bytes));
+    G->flushBytes = flushL2Bytes;
+  }
+  while((int)G->evPool.size() < 2 * plies) {
+    cudaEvent_t e;
+    KC_CUDA(cudaEventCreate(&e));
+    G->evPool.push_back(e);
+  }
   KC_CUDA(cudaMemsetAsync(G->d_stats, 0, 64, G->stream));
-  float msSum = 0.f;
-  bool timeKernels = (h == nullptr);
-  if(timeKernels) KC_CUDA(cudaEventRecord(G->ev0, G->stream));
   for(int p = 0; p < plies; p++) {
+    // optional L2 flush between plies, outside the timed window of each ply
+    if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
+    KC_CUDA(cudaEventRecord(G->evPool[2 * p], G->stream));
     FeatOut fo{};
     StepOut so = stepOutOf(G, true);
     if(!h) {
@@ -678,20 +691,32 @@ int kc_games_run(kc_games* G, kc_handle* h, int plies, kc_stats* acc) {
       launchGames<true>(G, 2, 0, so, fo);
       if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
     }
+    KC_CUDA(cudaEventRecord(G->evPool[2 * p + 1], G->stream));
   }
-  if(timeKernels) KC_CUDA(cudaEventRecord(G->ev1, G->stream));
   KC_CUDA(cudaGetLastError());
   unsigned long long hs[8];
   KC_CUDA(cudaMemcpyAsync(hs, G->d_stats, 64, cudaMemcpyDeviceToHost, G->stream));
   KC_CUDA(cudaStreamSynchronize(G->stream));
-  if(timeKernels) { KC_CUDA(cudaEventElapsedTime(&msSum, G->ev0, G->ev1)); G->lastKernelMs = msSum / plies; }
+  float msSum = 0.f;
+  for(int p = 0; p < plies; p++) {
+    float ms = 0.f;
+    KC_CUDA(cudaEventElapsedTime(&ms, G->evPool[2 * p], G->evPool[2 * p + 1]));
+    msSum += ms;
+  }
+  if(!h) G->lastKernelMs = msSum / plies;
+  if(msTotal) *msTotal = msSum;
+  if(h && kc::handleCheckAbort(h)) return 1;
   if(acc) {
     acc->steps += hs[0];
-    acc->evals += h ? hs[0] : 0;   // every stepped position is evaluated
+    acc->evals += h ? (uint64_t)g.numGames * plies : 0;   // every lane's position goes through the net each ply
     acc->gamesFinished += hs[2]; acc->blackWins += hs[3]; acc->whiteWins += hs[4]; acc->draws += hs[5];
     acc->checksum ^= hs[6];
   }
   return 0;
+}
+
+int kc_games_run(kc_games* G, kc_handle* h, int plies, kc_stats* acc) {
+  return kc_games_run_timed(G, h, plies, 0, acc, nullptr);
 }
 
 int64_t kc_games_launch_count(const kc_games* G) { return G ? G->launches : 0; }

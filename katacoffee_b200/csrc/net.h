@@ -23,5 +23,6 @@ float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 // Runs the net on the handle's (already symmetrised) input buffer on `stream`; symmetry_dev (device
 // pointer, may be null) is used for the inverse symmetry of the spatial outputs.
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev);
+int handleCheckAbort(kc_handle* h);   // after a synchronise
 
 }  // namespace kc

@@ -309,6 +309,7 @@ bool handleIsBf16(const kc_handle* h) { return h->bf16; }
 void* handleInputTiles(kc_handle* h) { return h->d_tiles; }
 float* handleInputNHWC(kc_handle* h) { return h->f32.in; }
 float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
+int handleCheckAbort(kc_handle* h) { return checkTrunkAbort(h); }
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev) {
   h->lastN = n;
   if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev);

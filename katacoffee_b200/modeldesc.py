@@ -2,7 +2,11 @@
 
 Random-init weights follow SURVEY.md 8(d): He-style N(0, 2/fan_in) for layers followed by ReLU,
 N(0, 1/fan_in) for final linear layers, the second conv of each block scaled by 1/sqrt(numBlocks)
-so the trunk stays O(1), BN mean 0 / var 1 / eps 1e-4 / scale 1 / bias N(0, 0.1^2), ReLU everywhere.
+so the trunk stays O(1), BN mean 0 / eps 1e-4 / scale 1 / bias N(0, 0.1^2), ReLU everywhere.
+`calibrate` then fixes the BN running statistics on synthetic V1-like planes so that activations
+and logits are O(1) at every depth: "rms" (default) keeps mean 0 as SURVEY.md prescribes and sets
+variance = E[x^2]; "full" also sets the means (the numeric profile of a trained net, where the
+mean subtraction amplifies reduced-precision error); "none" leaves mean 0 / variance 1.
 Trunk shapes come from the reference's python/modelconfigs.py:129-247 (b6c96, b10c128, b15c192);
 head shapes are the Coffee ones: policy 4 channels, value 2, misc 2, ownership 1.
 Weight layouts are the ones desc.cpp produces: conv oc,ic,y,x; matmul ic,oc.
@@ -26,7 +30,7 @@ HEAD_C = 32
 class Model:
     """Owns the numpy weight arrays and the ctypes description pointing into them."""
 
-    def __init__(self, name, seed=0):
+    def __init__(self, name, seed=0, calibrate="rms"):
         if name not in CONFIGS:
             raise ValueError(f"unknown net {name}")
         self.name = name
@@ -34,6 +38,7 @@ class Model:
         self.trunk, self.num_blocks, self.v2 = C_, nb, v2
         rng = np.random.default_rng(seed)
         self._keep = []
+        self._np = {}      # ctypes struct address -> numpy arrays of that layer (for calibration)
         d = capi.ModelDesc()
         d.version = 1
         d.numInputChannels, d.numInputGlobalChannels, d.numBlocks = 15, 1, nb
@@ -80,6 +85,12 @@ class Model:
         d.sv3Bias = self._bias(rng, 2)
         d.vOwnershipConv = self._conv(rng, 1, HEAD_C, 1, relu=False)
         self.desc = d
+        self._blocks = blocks
+        self._gpool_blocks = gpool_blocks
+        if calibrate not in ("none", "rms", "full"):
+            raise ValueError("calibrate must be 'none', 'rms' or 'full'")
+        if calibrate != "none":
+            self._calibrate(np.random.default_rng(seed + 1000003), full=(calibrate == "full"))
 
     # -- helpers: every array is kept alive on self._keep --
     def _arr(self, a):
@@ -90,16 +101,84 @@ class Model:
     def _conv(self, rng, k, ic, oc, relu, mult=1.0):
         fan_in = k * k * ic
         std = np.sqrt((2.0 if relu else 1.0) / fan_in) * mult
-        w = rng.standard_normal((oc, ic, k, k)) * std
-        return capi.ConvDesc(k, k, ic, oc, self._arr(w))
+        w = np.ascontiguousarray(rng.standard_normal((oc, ic, k, k)) * std, np.float32)
+        d = capi.ConvDesc(k, k, ic, oc, self._arr(w))
+        self._np[C.addressof(d.weights.contents)] = w
+        return d
 
     def _bn(self, rng, c):
-        return capi.BNDesc(c, 1e-4, 1, 1, self._arr(np.zeros(c)), self._arr(np.ones(c)),
-                           self._arr(np.ones(c)), self._arr(rng.standard_normal(c) * 0.1))
+        arrs = [np.zeros(c, np.float32), np.ones(c, np.float32), np.ones(c, np.float32),
+                np.ascontiguousarray(rng.standard_normal(c) * 0.1, np.float32)]
+        d = capi.BNDesc(c, 1e-4, 1, 1, *[self._arr(a) for a in arrs])
+        self._np[C.addressof(d.mean.contents)] = arrs
+        return d
 
     def _matmul(self, rng, ic, oc, scale=1.0):
-        w = rng.standard_normal((ic, oc)) * np.sqrt(scale / ic)
-        return capi.MatMulDesc(ic, oc, self._arr(w))
+        w = np.ascontiguousarray(rng.standard_normal((ic, oc)) * np.sqrt(scale / ic), np.float32)
+        d = capi.MatMulDesc(ic, oc, self._arr(w))
+        self._np[C.addressof(d.weights.contents)] = w
+        return d
+
+    # -- calibration of the BN running statistics on synthetic planes (host-side, torch CPU) --
+    def _w(self, d):
+        return self._np[C.addressof(d.weights.contents)]
+
+    def _calibrate(self, rng, full, n=192, H=5, W=5):
+        import torch
+        import torch.nn.functional as F
+        x = np.zeros((n, 15, H, W), np.float32)
+        x[:, 0] = 1
+        stones = rng.random((n, H, W))
+        fill = rng.random((n, 1, 1)) * 0.8
+        x[:, 1] = stones < fill / 2
+        x[:, 2] = (stones >= fill / 2) & (stones < fill)
+        for c in range(3, 11):                      # one-hot move planes
+            idx = rng.integers(0, H * W, n)
+            on = rng.random(n) < (0.25 if c < 7 else 0.8)
+            x[np.arange(n)[on], c, idx[on] // W, idx[on] % W] = 1
+        x[:, 11] = (rng.random((n, H, W)) < 0.2) & (x[:, 1] + x[:, 2] == 0)
+        for c in (12, 13, 14):
+            x[:, c] = (rng.random((n, H, W)) < 0.3) & (x[:, 1] + x[:, 2] > 0)
+        x = torch.from_numpy(x)
+        g = torch.full((n, 1), 4.0)
+
+        def conv(t, d):
+            w = torch.from_numpy(self._w(d))
+            return F.conv2d(t, w, padding=d.convYSize // 2)
+
+        def bn_fit(t, d):
+            mean, var, scale, bias = self._np[C.addressof(d.mean.contents)]
+            dims = (0, 2, 3) if t.dim() == 4 else (0,)
+            if full:
+                mean[:] = t.mean(dims).numpy()
+                var[:] = t.var(dims, unbiased=False).numpy() + 1e-3
+            else:
+                var[:] = (t * t).mean(dims).numpy() + 1e-3
+            s = torch.from_numpy(scale / np.sqrt(var + d.epsilon))
+            b = torch.from_numpy(bias) - torch.from_numpy(mean) * s
+            shape = (1, -1, 1, 1) if t.dim() == 4 else (1, -1)
+            return torch.relu(t * s.view(shape) + b.view(shape))
+
+        def gpool(t):
+            mean = t.mean((2, 3))
+            sq = float(np.sqrt(H * W))
+            return torch.cat([mean, mean * ((sq - 14.0) * 0.1), t.amax((2, 3))], 1)
+
+        d = self.desc
+        trunk = conv(x, d.initialConv) + (g @ torch.from_numpy(self._w(d.initialMatMul)))[:, :, None, None]
+        for i in range(self.num_blocks):
+            b = self._blocks[i]
+            a = bn_fit(trunk, b.preBN)
+            reg = conv(a, b.regularConv)
+            if b.kind == 2:
+                gp = bn_fit(conv(a, b.gpoolConv), b.gpoolBN)
+                reg = reg + (gpool(gp) @ torch.from_numpy(self._w(b.gpoolToBiasMul)))[:, :, None, None]
+            trunk = trunk + conv(bn_fit(reg, b.midBN), b.finalConv)
+        tip = bn_fit(trunk, d.trunkTipBN)
+        g1 = bn_fit(conv(tip, d.g1Conv), d.g1BN)
+        p1 = conv(tip, d.p1Conv) + (gpool(g1) @ torch.from_numpy(self._w(d.gpoolToBiasMul)))[:, :, None, None]
+        bn_fit(p1, d.p1BN)
+        bn_fit(conv(tip, d.v1Conv), d.v1BN)
 
     def _bias(self, rng, c):
         return capi.MatBiasDesc(c, 0, self._arr(rng.standard_normal(c) * 0.1))

@@ -118,7 +118,7 @@ int ko_playout_choose(const ko_game* g, uint64_t seed, uint64_t gameIdx, uint64_
 typedef struct {
   uint32_t game;       /* game index */
   uint32_t status;     /* ko_game_status */
-  uint32_t legal[5];   /* isLegal mask of the player to move (raw, also when finished) */
+  uint32_t legal[7];   /* isLegal mask of the player to move (raw, also when finished); 7x7 needs 196 bits */
   int32_t  movePos;    /* move that led here, -1 for the initial position */
   uint64_t sitHash[2]; /* getSitHash(next player) */
   uint64_t nnHash[2];  /* NNInputs::getHash with default params */
@@ -183,7 +183,9 @@ void ko_model_destroy(ko_model* m);
  * (NHWC iff inputsNHWC) + rowGlobal [n][1] + symmetry [n]; outputs logits, inverse-symmetrised,
  * policy in NNPos order [n][4*H*W], value [n][2], misc [n][2], ownership [n][H*W] (may be NULL).
  * mode 0 = direct fp32 convolution (the checker), 1 = Winograd F(4x4,3x3) + GEMM as the Eigen
- * backend does (eigenbackend.cpp:417-667; used for the CPU baseline). */
+ * backend does (eigenbackend.cpp:417-667; used for the CPU baseline), 2 = mode 0 with every
+ * tensor-core convolution's weights and input activations rounded to bf16 (precision model of the
+ * tcgen05 path: separates rounding from kernel bugs in the parity tests). */
 void ko_model_forward(const ko_model* m, int n, int nnXLen, int nnYLen, int inputsNHWC,
                       const float* rowSpatial, const float* rowGlobal, const int8_t* symmetry,
                       float* policy, float* value, float* misc, float* ownership, int mode,

@@ -26,11 +26,11 @@ def build(force=False):
 
 
 class StepRecord(C.Structure):
-    _fields_ = [("game", C.c_uint32), ("status", C.c_uint32), ("legal", C.c_uint32 * 5), ("movePos", C.c_int32),
+    _fields_ = [("game", C.c_uint32), ("status", C.c_uint32), ("legal", C.c_uint32 * 7), ("movePos", C.c_int32),
                 ("sitHash", C.c_uint64 * 2), ("nnHash", C.c_uint64 * 2)]
 
 
-STEP_DTYPE = np.dtype([("game", "<u4"), ("status", "<u4"), ("legal", "<u4", (5,)), ("movePos", "<i4"),
+STEP_DTYPE = np.dtype([("game", "<u4"), ("status", "<u4"), ("legal", "<u4", (7,)), ("movePos", "<i4"),
                        ("sitHash", "<u8", (2,)), ("nnHash", "<u8", (2,))], align=True)
 
 _lib = None

@@ -271,8 +271,31 @@ void conv1x1Gemm(const Conv& cv, int n, int H, int W, const float* in, float* ou
   for(size_t i = 0; i < tmp.size(); i++) out[i] += tmp[i];
 }
 
+// round-to-nearest-even to bfloat16 precision (what the tensor-core path stores its operands in)
+inline float bf16r(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// mode 2 = "bf16 emulation": the same arithmetic as mode 0 with the convolution's weights and input
+// activations rounded to bf16 first (products are then exact in fp32, accumulation stays fp32) --
+// the precision model of the tcgen05 path, used to tell rounding apart from kernel bugs.
+void convApplyBf16(const Conv& cv, int n, int H, int W, const float* in, float* out, bool accumulate) {
+  Conv q = cv;
+  for(float& v : q.wTap) v = bf16r(v);
+  std::vector<float> a((size_t)n * H * W * cv.ic);
+  for(size_t i = 0; i < a.size(); i++) a[i] = bf16r(in[i]);
+  convDirect(q, n, H, W, a.data(), out, accumulate);
+}
+
 void convApply(const Conv& cv, int n, int H, int W, const float* in, float* out, bool accumulate, int mode) {
-  if(mode == 1 && cv.ky == 3 && cv.kx == 3) convWinograd3x3(cv, n, H, W, in, out, accumulate);
+  if(mode == 2) convApplyBf16(cv, n, H, W, in, out, accumulate);
+  else if(mode == 1 && cv.ky == 3 && cv.kx == 3) convWinograd3x3(cv, n, H, W, in, out, accumulate);
   else if(mode == 1 && cv.ky == 1 && cv.kx == 1) conv1x1Gemm(cv, n, H, W, in, out, accumulate);
   else convDirect(cv, n, H, W, in, out, accumulate);
 }
@@ -384,6 +407,11 @@ struct ko_model {
     // trunk (eigenbackend.cpp:1202-1226)
     std::vector<float> trunk((size_t)n * hw * trunkC), gb((size_t)n * trunkC);
     convApply(initialConv, n, H, W, in.data(), trunk.data(), false, mode);
+    if(mode == 2) {   // the tensor-core path folds this matmul into the initial conv as a 16th bf16 input channel
+      MatMul q = initialMatMul;
+      for(float& v : q.w) v = bf16r(v);
+      for(int b = 0; b < n; b++) q.apply(rowGlobal + (size_t)b * numInputGlobalChannels, &gb[(size_t)b * trunkC]);
+    } else
     for(int b = 0; b < n; b++) initialMatMul.apply(rowGlobal + (size_t)b * numInputGlobalChannels, &gb[(size_t)b * trunkC]);
     addNCBias(n, hw, trunkC, trunk.data(), gb.data());
     for(const Block& blk : blocks) blk.apply(n, H, W, trunk.data(), mask.data(), maskSum.data(), mode);
@@ -401,7 +429,7 @@ struct ko_model {
       for(int b = 0; b < n; b++) gpoolToBiasMul.apply(&cat[(size_t)b * 3 * gc], &bias[(size_t)b * pc]);
       addNCBias(n, hw, pc, p1.data(), bias.data());
       bnApply(p1BN, p1Act, n, hw, p1.data(), mask.data(), p12.data());
-      convApply(p2Conv, n, H, W, p12.data(), pol.data(), false, mode);
+      convApply(p2Conv, n, H, W, p12.data(), pol.data(), false, mode == 2 ? 0 : mode);   // fp32 on CUDA cores in the bf16 path
       // NHWC [hw][4] -> NNPos order dir*HW + y*W + x, inverse spatial symmetry per direction channel
       // (eigenbackend.cpp:1776: copyOutputsWithSymmetry; ledger H, K parity mode)
       int D = p2Conv.oc;
@@ -433,7 +461,7 @@ struct ko_model {
       }
       if(ownership) {
         std::vector<float> own((size_t)n * hw);
-        convApply(vOwnershipConv, n, H, W, v12.data(), own.data(), false, mode);
+        convApply(vOwnershipConv, n, H, W, v12.data(), own.data(), false, mode == 2 ? 0 : mode);
         for(int b = 0; b < n; b++)
           ko_copy_outputs_with_symmetry(&own[(size_t)b * hw], ownership + (size_t)b * hw, 1, H, W,
                                         symmetry ? symmetry[b] : 0);

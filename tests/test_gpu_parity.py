@@ -231,30 +231,89 @@ def position_batch(oracle, W, H, K, seed, n):
     return pl[sel], gl[sel].reshape(-1, 1)
 
 
-@pytest.mark.parametrize("net,W,H,n", [("b2c32", 5, 5, 37), ("b6c96", 5, 5, 200), ("b10c128", 5, 5, 64), ("b6c96", 6, 6, 50)])
+def legal_of(recs_sel, HW):
+    LW = (4 * HW + 31) // 32
+    return recs_sel["legal"][:, :LW], (recs_sel["status"] >> 11) & 3, (recs_sel["status"] >> 8) & 1
+
+
+def position_batch_full(oracle, W, H, K, seed, n):
+    recs, pl, gl = oracle.playout_run(W, H, K, seed, 0, max(8, n // 8), threads=8)
+    sel = np.random.default_rng(seed).permutation(len(recs))[:n]
+    return pl[sel], gl[sel].reshape(-1, 1), recs[sel]
+
+
+def postprocessed(oracle, outs, recs_sel, HW):
+    """NNEvaluator::evaluate post-processing (nneval.cpp:702-815) of raw outputs, skipping terminal rows."""
+    legal, nextpla, fin = legal_of(recs_sel, HW)
+    p, v, m, _ = outs
+    pols, vals = [], []
+    for i in range(len(p)):
+        if fin[i] or not legal[i].any():
+            continue
+        a = oracle.postprocess(p[i], legal[i], v[i], m[i], int(nextpla[i]))
+        pols.append(a[0]); vals.append(a[1])
+    return np.array(pols), np.array(vals)
+
+
+def check_bf16_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym, calibrate):
+    """The three bf16 bars (DESIGN.md 'precision'):
+    T1 kernel exactness vs the bf16-emulating oracle (mode 2) -- rounding is modelled, bugs are not;
+    T2 north-star bar vs the fp32 oracle on what NNOutput hands to search: value/misc logits and
+       post-processed policy / win-loss probabilities within 1e-2 absolute, raw policy/ownership
+       logits within the reference's own reduced-precision tolerance 0.03*max(|x|,|y|,3) (testnn.cpp:8-15);
+    T3 (trained-like 'full' calibration) the reference's fp16 acceptance thresholds
+       (testnnevalcanary.cpp:417-418: winrate max <= 5 %, policy max <= 6 %, 99th pct <= 2 % / 2.5 %)."""
+    HW = W * H
+    emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
+    ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    for a, b in zip(got, emu):
+        assert np.abs(a - b).max() < 3e-3, ("T1", np.abs(a - b).max())
+    gp, gv = postprocessed(oracle, got, recs_sel, HW)
+    rp, rv = postprocessed(oracle, ref, recs_sel, HW)
+    if calibrate == "full":
+        dp, dv = np.abs(gp - rp).max(1), np.abs(gv - rv).max(1)
+        assert dv.max() <= 0.05 and np.percentile(dv, 99) <= 0.02, ("T3 winrate", dv.max())
+        assert dp.max() <= 0.06 and np.percentile(dp, 99) <= 0.025, ("T3 policy", dp.max())
+        return
+    assert np.abs(got[1] - ref[1]).max() < TOL_BF16 and np.abs(got[2] - ref[2]).max() < TOL_BF16, "T2 value/misc logits"
+    assert np.abs(gp - rp).max() < TOL_BF16 and np.abs(gv - rv).max() < TOL_BF16, ("T2 post-processed", np.abs(gp - rp).max())
+    for a, b in ((got[0], ref[0]), (got[3], ref[3])):
+        tol = 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)
+        assert (np.abs(a - b) < tol).all(), ("T2 raw logits", np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("net,W,H,n,calibrate", [("b2c32", 5, 5, 37, "rms"), ("b6c96", 5, 5, 200, "rms"), ("b10c128", 5, 5, 300, "rms"),
+                                                 ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none")])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_forward_matches_oracle(ctx, oracle, net, W, H, n, mode):
+def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
     """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward."""
     from katacoffee_b200 import backend, modeldesc
-    model = modeldesc.Model(net, seed=5)
+    model = modeldesc.Model(net, seed=5, calibrate=calibrate)
     om = oracle.Model(model)
-    planes, glob = position_batch(oracle, W, H, 4, 3, n)
+    planes, glob, rsel = position_batch_full(oracle, W, H, 4, 3, n)
     sym = (np.arange(n) % 8).astype(np.int8)
-    ep, ev, em, eo = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
     lm = backend.LoadedModel(ctx, model)
     h = backend.createComputeHandle(ctx, lm, maxBatchSize=max(n, 64), nnXLen=W, nnYLen=H, useFP32Check=(mode == "fp32"))
     assert h.isUsingBF16() == (mode == "bf16")
-    p, v, m, o = backend.getOutput(h, planes, glob, sym)
-    tol = TOL_FP32 if mode == "fp32" else TOL_BF16
-    errs = [np.abs(p - ep).max(), np.abs(v - ev).max(), np.abs(m - em).max(), np.abs(o - eo).max()]
-    assert max(errs) < tol, errs
-    assert np.abs(ep).max() > 0.05 and np.abs(ev).max() > 0.01     # the comparison is not vacuous
+    got = backend.getOutput(h, planes, glob, sym)
+    ep = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    assert np.abs(ep[0]).max() > 0.05 and np.abs(ep[1]).max() > 0.01     # the comparison is not vacuous
+    if mode == "fp32":
+        errs = [np.abs(a - b).max() for a, b in zip(got, ep)]
+        assert max(errs) < TOL_FP32, errs
+    else:
+        # symmetry is applied to planes, not to legality: compare post-processed values without symmetry below
+        emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
+        for a, b in zip(got, emu):
+            assert np.abs(a - b).max() < 3e-3, np.abs(a - b).max()
+        got0 = backend.getOutput(h, planes, glob, None)
+        check_bf16_against_oracle(oracle, om, got0, planes, glob, rsel, W, H, None, calibrate)
     # NHWC rows, no symmetry
     h2 = backend.createComputeHandle(ctx, lm, max(n, 64), W, H, useFP32Check=(mode == "fp32"), inputsUseNHWC=True)
     nhwc = planes.reshape(n, 15, W * H).transpose(0, 2, 1).reshape(n, -1)
-    p2, v2, m2, o2 = backend.getOutput(h2, nhwc, glob, None)
-    ep2, ev2, em2, eo2 = om.forward(planes, glob, W, H, mode=0, threads=8)
-    assert max(np.abs(p2 - ep2).max(), np.abs(v2 - ev2).max(), np.abs(m2 - em2).max(), np.abs(o2 - eo2).max()) < tol
+    got2 = backend.getOutput(h2, nhwc, glob, None)
+    ref2 = om.forward(planes, glob, W, H, mode=0 if mode == "fp32" else 2, threads=8)
+    assert max(np.abs(a - b).max() for a, b in zip(got2, ref2)) < (TOL_FP32 if mode == "fp32" else 3e-3)
     for x in (h, h2, lm):
         x.close()
 
@@ -275,10 +334,10 @@ def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
     planes, glob = games.features()
     sym = ((np.arange(G) * 5) % 8).astype(np.int8)
     games.eval(h, sym)
-    p, v, m, o = h.readOutputs(G)
-    ep, ev, em, eo = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
-    tol = TOL_FP32 if mode == "fp32" else TOL_BF16
-    assert max(np.abs(p - ep).max(), np.abs(v - ev).max(), np.abs(m - em).max(), np.abs(o - eo).max()) < tol
+    got = h.readOutputs(G)
+    ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0 if mode == "fp32" else 2, threads=8)
+    tol = TOL_FP32 if mode == "fp32" else 3e-3
+    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < tol
     for x in (games, h, lm):
         x.close()
 
@@ -304,7 +363,7 @@ def test_run_counters_and_checksum(ctx, oracle):
     plies = 40
     st2 = games.run(None, plies)
     assert st2.steps == G * plies
-    recs3, _, _ = oracle.playout_run(W, H, K, seed, 0, 3 * G, planes=False, threads=8)
+    recs3, _, _ = oracle.playout_run(W, H, K, seed, 0, 8 * G, planes=False, threads=8)
     starts3 = np.flatnonzero(recs3["movePos"] == -1)
     len3 = np.append(starts3[1:], len(recs3)) - starts3 - 1     # moves per game
     x = 0
@@ -359,10 +418,10 @@ def test_bf16_full_batch_and_odd_sizes(ctx, oracle):
     om = oracle.Model(model)
     lm = backend.LoadedModel(ctx, model)
     planes, glob = position_batch(oracle, 5, 5, 4, 17, 2500)
-    ep, ev, em, eo = om.forward(planes, glob, 5, 5, mode=0, threads=8)
+    ep, ev, em, eo = om.forward(planes, glob, 5, 5, mode=2, threads=8)
     h = backend.createComputeHandle(ctx, lm, 2500, 5, 5)
     for n in (1, 3, 4, 5, 8, 9, 1185, 2500):
         p, v, m, o = backend.getOutput(h, planes[:n], glob[:n], None)
         err = max(np.abs(p - ep[:n]).max(), np.abs(v - ev[:n]).max(), np.abs(m - em[:n]).max(), np.abs(o - eo[:n]).max())
-        assert err < TOL_BF16, (n, err)
+        assert err < 3e-3, (n, err)
     h.close(); lm.close()
