@@ -16,8 +16,9 @@
 //  * Weights are pre-tiled on the host into the exact shared-memory image of each (16-channel,
 //    3-tap) stage and streamed L2 -> smem by the TMA engine (cp.async.bulk, UBLKCP) through a
 //    7-deep mbarrier ring, shared by both tiles (each stage feeds two MMAs).
-//  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-//    warps 2-5 / 6-9 = epilogue of tile 0 / 1 (thread = TMEM lane = activation row).
+//  * Warp roles: warp 0 = TMA producer, warps 1 / 2 = MMA issuer of tile 0 / 1 (one thread each;
+//    warp 1 also owns the TMEM allocation), warps 4-7 / 8-11 = epilogue of tile 0 / 1
+//    (thread = TMEM lane = activation row).
 //  * The epilogue (folded BN + ReLU + pad-row masking + bf16 pack) publishes the next layer's input
 //    16 channels at a time; the MMA warp starts the next layer on chunk c as soon as both tiles have
 //    published chunk c, so the tensor pipe only idles for the first chunk of every layer.
@@ -44,7 +45,7 @@ constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAX_C * 32;  // 12288
 constexpr int NSTAGES = 7;
 constexpr int SCR_STRIDE = 17;
 constexpr int MAX_NB = 4;
-constexpr int TRUNK_THREADS = 320;
+constexpr int TRUNK_THREADS = 384;   // warp 0 TMA producer, 1-2 MMA issuers (tile 0/1), 3 idle, 4-7 / 8-11 epilogue of tile 0 / 1
 constexpr int HEADC = 32;   // p1 = g1 = v1 = 32 channels
 constexpr int MAX_V2 = 128;
 
@@ -335,6 +336,83 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
 }
 
+// One thread issues every tcgen05.mma of one tile.  Descriptors are kept as (hi, lo) words: hi holds
+// SBO = 128 B and the sm_100 version bit, lo = start address >> 4 | LBO >> 4 << 16; a tap or a K-chunk is
+// a plain add on lo.  For 3x3 layers the K loop is chunk-major: 16 input channels x (3 stages x 3 taps),
+// each stage = one kernel row (dy), so the row shift is (dy-1)*tileRowW + (dx-1).
+__device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const uint32_t sbase, const uint32_t bars,
+                                       const uint32_t tmemBase, volatile int* abortFlag) {
+  uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
+  const uint32_t descHi = (128u >> 4) | (1u << 14);
+  const uint32_t aLo0 = (((sbase + OFF_ACT + t * ACT_BYTES + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+  const uint32_t ringLo0 = ((sbase + OFF_RING) & 0x3FFFFu) >> 4;
+  const uint32_t barFull = bars + BAR_FULL * 8, barEmpty = bars + BAR_EMPTY * 8, barChunk = bars + (BAR_CHUNK + t * 8) * 8;
+  auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
+  for(int item = blockIdx.x; item < P.numItems; item += gridDim.x, itemCount++) {
+    if(!mbar_wait(bars + (BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
+    if(itemCount > 0 && !mbar_wait(bars + (BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
+    tc_fence_after();
+    for(int l = 0; l < P.numLayers; l++) {
+      const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
+      const uint32_t idesc = idesc_bf16_f32(128, N);
+      const uint32_t d = tmemBase + t * 256 + (P.layers[l].outSel ? 128 : 0);
+      const uint32_t bStep = 2 * N;                    // one K-step of weights = N*32 bytes
+      const uint32_t bLbo = (uint32_t)N << 16;         // LBO = N*16 bytes
+      uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
+      if(ntaps == 9) {
+        const int nchunks = nk / 9;
+        for(int cc = 0; cc < nchunks; cc++) {
+          if(l > 0) {
+            const uint32_t bit = 1u << cc;
+            if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
+            chunkPhase ^= bit;
+            tc_fence_after();
+          }
+          const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
+#pragma unroll
+          for(int dy = 0; dy < 3; dy++) {
+            if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+            tc_fence_after();
+            const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+            const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
+#pragma unroll
+            for(int dx = 0; dx < 3; dx++) {
+              umma_bf16(d, desc(aLoR + dx), desc(bLo + dx * bStep), idesc, accum);
+              accum = 1u;
+            }
+            umma_commit(barEmpty + slot * 8);
+            if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        // 1x1 layers: K-step = one 16-channel chunk, stages of up to 3 K-steps
+        const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+        for(int s = 0; s < nst; s++) {
+          if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+          tc_fence_after();
+          const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+          const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
+          for(int kk = 0; kk < ks; kk++) {
+            const int cc = s * KSTEPS_PER_STAGE + kk;
+            if(l > 0) {
+              const uint32_t bit = 1u << cc;
+              if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
+              chunkPhase ^= bit;
+              tc_fence_after();
+            }
+            umma_bf16(d, desc(aLo0 + cc * (2 * CHUNK_BYTES >> 4)), desc(bLo + kk * bStep), idesc, accum);
+            accum = 1u;
+          }
+          umma_commit(barEmpty + slot * 8);
+          if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(bars + (BAR_ACC + t) * 8);
+      if(l == P.numLayers - 1) umma_commit(bars + (BAR_ACTFREE + t) * 8);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,7 +425,7 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
   for(int i = threadIdx.x; i < 2 * ACT_BYTES / 16; i += TRUNK_THREADS) reinterpret_cast<uint4*>(smem + OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
   for(int i = threadIdx.x; i < 8 * P.HW; i += TRUNK_THREADS) sSym[i] = P.dstOfSrcRev[i];
   if(threadIdx.x == 0) {
-    for(int i = 0; i < NSTAGES; i++) { mbar_init(bars + (BAR_FULL + i) * 8, 1); mbar_init(bars + (BAR_EMPTY + i) * 8, 1); }
+    for(int i = 0; i < NSTAGES; i++) { mbar_init(bars + (BAR_FULL + i) * 8, 1); mbar_init(bars + (BAR_EMPTY + i) * 8, 2); }   // both MMA issuers release a slot
     for(int t = 0; t < 2; t++) {
       mbar_init(bars + (BAR_ACC + t) * 8, 1); mbar_init(bars + (BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (BAR_IN + t) * 8, 1);
       mbar_init(bars + (BAR_HEAD + t) * 8, 128);
@@ -396,66 +474,15 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
         }
       }
     }
-  } else if(warp == 1) {
-    // =========================== MMA issuer ===========================
-    uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
-    bool alive = true;
-    for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x, itemCount++) {
-      for(int t = 0; t < 2 && alive; t++) {
-        alive = mbar_wait(bars + (BAR_IN + t) * 8, itemCount & 1, abortFlag, 21);
-        if(alive && itemCount > 0) alive = mbar_wait(bars + (BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22);
-      }
-      tc_fence_after();
-      for(int l = 0; l < P.numLayers && alive; l++) {
-        const LayerDesc L = P.layers[l];
-        const int nst = (L.nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
-        const uint32_t idesc = idesc_bf16_f32(128, L.N);
-        for(int s = 0; s < nst && alive; s++) {
-          alive = mbar_wait(bars + (BAR_FULL + slot) * 8, phase, abortFlag, 23);
-          if(!alive) break;
-          tc_fence_after();
-          int ks = min(KSTEPS_PER_STAGE, L.nk - s * KSTEPS_PER_STAGE);
-          for(int kk = 0; kk < ks && alive; kk++) {
-            int kidx = s * KSTEPS_PER_STAGE + kk;
-            int cc = kidx / L.ntaps, tap = kidx - cc * L.ntaps;
-            if(tap == 0 && l > 0) {
-              for(int t = 0; t < 2 && alive; t++) {
-                uint32_t bit = 1u << (t * 8 + cc);
-                alive = mbar_wait(bars + (BAR_CHUNK + t * 8 + cc) * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24);
-                chunkPhase ^= bit;
-              }
-              if(!alive) break;
-              tc_fence_after();
-            }
-            int shift = (L.ntaps == 9) ? ((tap / 3 - 1) * P.tileRowW + (tap % 3 - 1)) : 0;
-            if(lane == 0) {
-              uint64_t bdesc = smem_desc(sbase + OFF_RING + slot * STAGE_BYTES + kk * L.N * 32, (uint32_t)L.N * 16, 128);
-#pragma unroll
-              for(int t = 0; t < 2; t++) {
-                uint64_t adesc = smem_desc(sbase + OFF_ACT + t * ACT_BYTES + 2 * cc * CHUNK_BYTES + (HALO_ROWS + shift) * 16, CHUNK_BYTES, 128);
-                uint32_t d = tmemBase + t * 256 + (L.outSel ? 128 : 0);
-                umma_bf16(d, adesc, bdesc, idesc, (kidx > 0 || L.accumulate) ? 1u : 0u);
-              }
-            }
-            __syncwarp();
-          }
-          if(!alive) break;
-          if(lane == 0) umma_commit(bars + (BAR_EMPTY + slot) * 8);
-          __syncwarp();
-          if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
-        }
-        if(alive && lane == 0) {
-          umma_commit(bars + (BAR_ACC + 0) * 8);
-          umma_commit(bars + (BAR_ACC + 1) * 8);
-          if(l == P.numLayers - 1) { umma_commit(bars + (BAR_ACTFREE + 0) * 8); umma_commit(bars + (BAR_ACTFREE + 1) * 8); }
-        }
-        __syncwarp();
-      }
-    }
+  } else if(warp == 1 || warp == 2) {
+    // =========================== MMA issuers: one thread per tile ===========================
+    if(lane == 0) mmaIssuer(P, warp - 1, sbase, bars, tmemBase, abortFlag);
+  } else if(warp == 3) {
+    // idle (keeps the epilogue warps aligned to TMEM lane quadrants: warp % 4 == quadrant)
   } else {
     // =========================== epilogue warps ===========================
     EpiCtx c;
-    c.t = (warp - 2) >> 2;
+    c.t = (warp - 4) >> 2;
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     c.r = q * 32 + lane;
     c.e = c.r;

@@ -19,6 +19,9 @@ from . import capi
 
 CONFIGS = {
     # name: (trunk, mid, regular, gpool, numBlocks, gpool block indices, v2 size)
+    "b0c32": (32, 32, 16, 16, 0, (), 32),        # shallow nets: bf16 rounding has not decorrelated yet, so the
+    "b1c32": (32, 32, 16, 16, 1, (), 32),        #   tensor-core path can be compared POINTWISE with the bf16-emulating oracle
+    "b1c32g": (32, 32, 16, 16, 1, (0,), 32),
     "b2c32": (32, 32, 16, 16, 2, (1,), 32),      # tiny net for fast tests
     "b6c96": (96, 96, 64, 32, 6, (2, 4), 64),    # modelconfigs.py b6c96: gpool blocks 3 and 5 (1-based)
     "b10c128": (128, 128, 96, 32, 10, (4, 7), 80),
@@ -52,7 +55,7 @@ class Model:
             b = blocks[i]
             b.preActivation = b.gpoolActivation = b.midActivation = 1
             b.preBN = self._bn(rng, C_)
-            resid = 1.0 / np.sqrt(nb)
+            resid = 1.0 / np.sqrt(max(nb, 1))
             if i in gpool_blocks:
                 b.kind = 2
                 b.regularConv = self._conv(rng, 3, C_, reg, relu=True)
