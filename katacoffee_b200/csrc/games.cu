@@ -1,7 +1,7 @@
 // Batched Coffee rules, history, sit-hash and NNInputs V1 feature planes on the device.
 //
 // One thread owns one game for the rule logic (pure 64-bit bitboard arithmetic, ~600 SASS
-// instructions per ply), then the whole CTA expands the 15 plane bitboards of its games into the
+// instructions per ply; one warp = 32 games per CTA), then the whole CTA expands the 15 plane bitboards of its games into the
 // output tensor with 128-bit coalesced stores -- the plane write is the HBM-bound part (1500 B per
 // position in fp32), the logic is noise next to it.
 //
@@ -27,7 +27,7 @@
 
 namespace kc {
 
-constexpr int GPB = 128;       // games per CTA in the fp32 feature modes
+constexpr int GPB = 32;        // games per CTA: one warp runs the rules, all four warps expand the planes
 constexpr int THREADS = 128;
 
 struct Geom {
@@ -66,6 +66,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {  // cpp/core/hash.c
 __device__ __forceinline__ int padOf(const Geom& g, int cell) { return cell + cell / g.W; }
 
 // Legal Locs of the player to move, one padded bitboard per direction (board.cpp:185-227).
+// (loops are kept rolled on purpose: the kernel is instruction-cache sensitive)
 __device__ __forceinline__ void legalMasks(const Geom& g, uint64_t empty, int lastCell, int lastDir, uint64_t L[4]) {
   uint64_t cand = empty;
   if(lastDir < 4 && lastCell >= 0) {
@@ -73,10 +74,11 @@ __device__ __forceinline__ void legalMasks(const Geom& g, uint64_t empty, int la
     int li = lastDir == 0 ? x : lastDir == 1 ? y : lastDir == 2 ? (x - y + g.H - 1) : (x + y);
     cand &= g.lines[lastDir][li];
   }
-#pragma unroll
+#pragma unroll 1
   for(int d = 0; d < 4; d++) {
     int nl = (d == 0) ? g.W : (d == 1) ? g.H : (g.W + g.H - 1);
     uint64_t ok = 0;
+#pragma unroll 1
     for(int i = 0; i < nl; i++) {
       uint64_t e = empty & g.lines[d][i];
       ok |= (__popcll(e) >= 2) ? e : 0ULL;   // another empty cell anywhere on the same line
@@ -87,6 +89,7 @@ __device__ __forceinline__ void legalMasks(const Geom& g, uint64_t empty, int la
 
 __device__ __forceinline__ uint64_t toDense(const Geom& g, uint64_t m) {
   uint64_t r = 0;
+#pragma unroll 1
   for(int y = 0; y < g.H; y++) r |= ((m >> (y * g.stride)) & g.rowMask) << (y * g.W);
   return r;
 }
@@ -94,8 +97,10 @@ __device__ __forceinline__ uint64_t toDense(const Geom& g, uint64_t m) {
 // cells covered by a same-colour run of length >= n along shift s
 __device__ __forceinline__ uint64_t coverAtLeast(uint64_t m, int s, int n) {
   uint64_t starts = m;
+#pragma unroll 1
   for(int i = 1; i < n; i++) starts &= (m >> (i * s));
   uint64_t c = starts;
+#pragma unroll 1
   for(int i = 1; i < n; i++) c |= (starts << (i * s));
   return c;
 }
@@ -149,17 +154,17 @@ __device__ __forceinline__ void v1Planes(const Geom& g, const GameRegs& s, const
   P[11 * pstride] = L[0] | L[1] | L[2] | L[3];
   // stones in a maximal same-colour run of length exactly k-1, k-2, k-3 in some direction
   uint64_t ex[3] = {0, 0, 0};
-  const int shifts[4] = {g.stride, 1, g.stride + 1, g.stride - 1};
-#pragma unroll
-  for(int c = 0; c < 2; c++) {
-    uint64_t m = c == 0 ? s.black : s.white;
-#pragma unroll
-    for(int d = 0; d < 4; d++) {
-      uint64_t hi = coverAtLeast(m, shifts[d], g.K);      // >= k
+#pragma unroll 1
+  for(int cd = 0; cd < 8; cd++) {
+    {
+      const int d = cd & 3;
+      const uint64_t m = (cd & 4) ? s.white : s.black;
+      const int shift = d == 0 ? g.stride : d == 1 ? 1 : d == 2 ? g.stride + 1 : g.stride - 1;
+      uint64_t hi = coverAtLeast(m, shift, g.K);      // >= k
 #pragma unroll
       for(int j = 0; j < 3; j++) {
         int len = g.K - 1 - j;
-        uint64_t lo = len >= 1 ? coverAtLeast(m, shifts[d], len) : 0ULL;
+        uint64_t lo = len >= 1 ? coverAtLeast(m, shift, len) : 0ULL;
         ex[j] |= lo & ~hi;
         hi = lo;
       }
@@ -216,9 +221,11 @@ __device__ __forceinline__ int stepGame(const Geom& g, GameRegs& s, int forcedMo
   // win through the last move (board.cpp:376-383), overlines count
   uint64_t mine = pla == 1 ? s.black : s.white;
   bool win = false;
-  const int shifts[4] = {g.stride, 1, g.stride + 1, g.stride - 1};
-#pragma unroll
-  for(int d = 0; d < 4; d++) win = win || ((coverAtLeast(mine, shifts[d], g.K) & bit) != 0);
+#pragma unroll 1
+  for(int d = 0; d < 4; d++) {
+    const int shift = d == 0 ? g.stride : d == 1 ? 1 : d == 2 ? g.stride + 1 : g.stride - 1;
+    win = win || ((coverAtLeast(mine, shift, g.K) & bit) != 0);
+  }
   int opp = pla ^ 3;
   // legal masks of the player now to move (also decides the draw, ledger C)
   uint64_t empty2 = empty & ~bit;
@@ -249,6 +256,10 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
   __shared__ uint64_t sPlanes[15][GPB + 1];
   __shared__ uint8_t sSrcPad[8][52];   // [symmetry][dst cell] -> padded bit index of the source cell
   __shared__ int8_t sSym[GPB];
+  // FEAT 1 without symmetry: the CTA's whole output as one bit string (bit e = output float e), so the
+  // expansion is one shared load + one 128-bit store per four floats
+  __shared__ uint32_t sBits[GPB * 15 * 49 / 32 + 4];
+  const bool fastNCHW = (FEAT == 1) && fo.symmetry == nullptr;
   const int gpb = fo.gamesPerBlock;
   const int gBase = blockIdx.x * gpb;
   const int t = threadIdx.x;
@@ -270,6 +281,10 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
       sSrcPad[sym][dst] = (uint8_t)(cell + cell / g.W);
     }
     if(t < gpb) sSym[t] = (active && fo.symmetry) ? fo.symmetry[gi] : 0;
+    if(fastNCHW) {
+      for(int i = t; i < GPB * 15 * 49 / 32 + 4; i += THREADS) sBits[i] = 0;
+      __syncthreads();
+    }
   }
 
   unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
@@ -320,7 +335,29 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
         if(fl & 1) { cFin = 1; int wn = (fl >> 1) & 3; cB = wn == 1; cW = wn == 2; cD = wn == 0; }
       }
     }
-    if(FEAT != 0) v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
+    if(FEAT != 0) {
+      if(fastNCHW) {
+        v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
+        const int E = 15 * g.HW;
+        uint32_t bitPos = (uint32_t)t * E, wi = bitPos >> 5;
+        int fill = bitPos & 31;
+        uint64_t acc = 0;
+        auto append = [&](uint64_t bits, int n) {
+          acc |= bits << fill;
+          fill += n;
+          if(fill >= 32) { atomicOr(&sBits[wi++], (uint32_t)acc); acc >>= 32; fill -= 32; }
+        };
+#pragma unroll 1
+        for(int c = 0; c < 15; c++) {
+          uint64_t D = toDense(g, sPlanes[c][t]);
+          if(g.HW <= 25) append(D, g.HW);
+          else { append(D & 0x1FFFFFFULL, 25); append(D >> 25, g.HW - 25); }
+        }
+        if(fill) atomicOr(&sBits[wi], (uint32_t)acc);
+      } else {
+        v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
+      }
+    }
   } else if(FEAT != 0 && t < GPB) {
 #pragma unroll
     for(int c = 0; c < 15; c++) sPlanes[c][t] = 0;
@@ -350,7 +387,19 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
 
   const int ng = min(gpb, g.numGames - gBase);
   if(ng <= 0) return;
-  if(FEAT == 1 || FEAT == 2) {
+  if(fastNCHW) {
+    const int total = ng * 15 * g.HW;
+    float* out = fo.planes + (size_t)gBase * 15 * g.HW;
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const int nvec = total >> 2;
+    for(int j = t; j < nvec; j += THREADS) {
+      uint32_t b = sBits[j >> 3] >> ((j & 7) * 4);
+      float4 v = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+      __stcs(&out4[j], v);
+    }
+    for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = (float)((sBits[e >> 5] >> (e & 31)) & 1u);
+    if(fo.global && t < ng) fo.global[gBase + t] = (float)g.K;
+  } else if(FEAT == 1 || FEAT == 2) {
     const int E = 15 * g.HW;
     const uint32_t magicE = (uint32_t)((0x100000000ULL + E - 1) / E);
     const int inner = FEAT == 1 ? g.HW : 15;
@@ -434,7 +483,7 @@ using namespace kc;
 
 template <bool DO_STEP>
 void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
-  int gpb = feat == 3 ? G->geom.NB * 32 : GPB;
+  int gpb = feat == 3 ? G->geom.NB * 8 : GPB;   // FEAT 3: whole trunk tiles per CTA
   fo.gamesPerBlock = gpb;
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
   switch(feat) {
