@@ -177,7 +177,7 @@ def main():
         ge.build()
     if world > 1:
         torch.distributed.barrier()
-    from katacoffee_b200 import backend, modeldesc
+    from katacoffee_b200 import backend, modeldesc, shard
     G = args.games
     peaks = load_peaks()
     ctx = backend.createComputeContext(local)
@@ -185,7 +185,7 @@ def main():
     lm = backend.LoadedModel(ctx, model)
     handle = backend.createComputeHandle(ctx, lm, G, W, H)
     games = backend.Games(ctx, G, W, H, WINLEN)
-    games.reset(seed=SEED, firstGameId=rank * (1 << 40), autoRefill=True)   # shard: disjoint game ids per rank
+    games.reset(seed=SEED, firstGameId=shard.first_game_id(rank), autoRefill=True)   # shard: disjoint game ids per rank
 
     def barrier():
         if world > 1:
@@ -205,13 +205,9 @@ def main():
     clocks = sampler.stop(t0, t1) if sampler else None
     launches = games.launchCount() + handle.launchCount() - l0
     trunk_ms, trunk_n = handle.trunkTime()
-    ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    counters = torch.tensor([stats.steps, stats.evals, stats.gamesFinished, stats.blackWins, stats.whiteWins, stats.draws],
-                            dtype=torch.int64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(ms_t, op=torch.distributed.ReduceOp.MAX)
-        torch.distributed.reduce(counters, dst=0, op=torch.distributed.ReduceOp.SUM)   # the end-of-run NCCL reduce of statistics
-    ms_max = float(ms_t.item())
+    ms_max = shard.max_over_ranks(ms_total, "cuda")
+    # the end-of-run NCCL reduce of statistics -- the only collective of the whole job
+    counters = shard.reduce_stats([getattr(stats, f) for f in shard.STAT_FIELDS], "cuda")
     total_evals = G * args.steps * world
     value = total_evals / (ms_max * 1e-3)
 
@@ -243,10 +239,7 @@ def main():
         backend.getOutput(handle, pinned[i % nbuf].numpy(), glob_h.numpy(), sym_h, out=outs)
     te = time.perf_counter() - te0
     barrier()
-    te_t = torch.tensor([te], dtype=torch.float64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(te_t, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = total_evals / float(te_t.item())
+    e2e_value = total_evals / shard.max_over_ranks(te, "cuda")
     h2d = G * (15 * hw * 4 + 4 + 1)
     d2h = G * (4 * hw * 4 + 8 + 8 + hw * 4)
 

@@ -49,5 +49,23 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_host(force=False):
+    """The C++ nninterface backend (host/b200backend.cpp) as a shared library + its C++ test driver."""
+    host = os.path.join(HERE, "host")
+    lib = os.path.join(HERE, "libkc_b200backend.so")
+    exe = os.path.join(host, "test_b200backend")
+    src = os.path.join(host, "b200backend.cpp")
+    test = os.path.join(HERE, "..", "tests", "cpp", "test_b200backend.cpp")
+    newest = max(os.path.getmtime(p) for p in (src, test, os.path.join(host, "reftypes.h"), os.path.join(HERE, "..", "include", "katacoffee_b200.h")))
+    if not force and os.path.exists(lib) and os.path.exists(exe) and min(os.path.getmtime(lib), os.path.getmtime(exe)) >= newest:
+        return lib, exe
+    inc = ["-I" + os.path.join(HERE, "..", "include"), "-I" + host]
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall"] + inc + [src, "-o", lib, "-L" + HERE, "-lkatacoffee_b200",
+                    "-Wl,-rpath,$ORIGIN"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [test, "-o", exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
+                    "-Wl,-rpath," + HERE], check=True)
+    return lib, exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

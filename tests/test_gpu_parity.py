@@ -471,3 +471,13 @@ def test_bf16_full_batch_and_odd_sizes(ctx, oracle):
         assert max(np.abs(v - ev[:n]).max(), np.abs(m - em[:n]).max()) < TOL_BF16, n
         assert (np.abs(p - ep[:n]) < 0.03 * np.maximum(np.maximum(np.abs(p), np.abs(ep[:n])), 3.0)).all(), n
     h.close(); lm.close()
+
+
+def test_cpp_nninterface_backend(ctx):
+    """The C++ drop-in (host/b200backend.cpp: every NeuralNet:: function of nninterface.h) driven the way
+    NNEvaluator::serve drives a backend; its outputs equal direct C-ABI calls bit for bit."""
+    import subprocess
+    from katacoffee_b200 import build as kb
+    lib, exe = kb.build_host()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "b200backend ok" in r.stdout, r.stdout + r.stderr
