@@ -133,8 +133,10 @@ int64_t kc_handle_launch_count(const kc_handle* h);
  * handle since the previous call (CUDA events recorded on the launching stream); synchronises. */
 int kc_handle_trunk_time(kc_handle* h, float* sumMs, int* count);
 /* Self-test of the tcgen05 descriptor conventions the trunk kernel relies on: D[128][N] =
- * A[shift:shift+128][K] * B[N][K]^T on the tensor core (A, B bf16 bit patterns, D fp32). */
-int kc_selftest_umma(kc_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int rowsA, int N, int K, int shift);
+ * A[shift:shift+128][K] * B[N][K]^T on the tensor core (A, B bf16 bit patterns, D fp32).  ws != 0 uses the
+ * weight-stationary form: D gets two results [2][128][N], for row shifts `shift` and `shift+1`, the second MMA
+ * re-using the B operand latched by the first. */
+int kc_selftest_umma(kc_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int rowsA, int N, int K, int shift, int ws);
 
 /* Layer-level hooks = NeuralNet::testEvaluateConv / BatchNorm / ResidualBlock /
  * GlobalPoolingResidualBlock (nninterface.h:127-169), fp32 path; buffers NCHW or NHWC. */

@@ -233,11 +233,11 @@ def zobristTables():
     return board, player, sx, sy
 
 
-def selftestUmma(ctx, A_bf16_bits, B_bf16_bits, shift):
+def selftestUmma(ctx, A_bf16_bits, B_bf16_bits, shift, ws=False):
     rowsA, K = A_bf16_bits.shape
     N = B_bf16_bits.shape[0]
-    D = np.zeros((128, N), np.float32)
+    D = np.zeros((2, 128, N) if ws else (128, N), np.float32)
     A = np.ascontiguousarray(A_bf16_bits, np.uint16)
     B = np.ascontiguousarray(B_bf16_bits, np.uint16)
-    check(lib().kc_selftest_umma(ctx._p, ptr(A), ptr(B), ptr(D), rowsA, N, K, shift))
+    check(lib().kc_selftest_umma(ctx._p, ptr(A), ptr(B), ptr(D), rowsA, N, K, shift, int(ws)))
     return D

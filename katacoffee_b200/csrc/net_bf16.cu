@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -77,8 +78,9 @@ struct LayerDesc {
   int gpoolC;      // EPI_GPOOL: gpool channels (columns epiC .. epiC+gpoolC)
   unsigned wOffset; // byte offset of this layer's first stage in the weight stream
   int pOff;        // float offset of this layer's parameters
-  int pad0, pad1;
 };
+constexpr int MAX_LAYERS = 48;   // 1 + 2*blocks + 1; the table travels in the kernel parameter block (constant bank:
+                                 // warp-uniform loads, so the MMA issue loop stays on the uniform datapath)
 
 struct TrunkProgram {
   std::vector<LayerDesc> layers;
@@ -91,7 +93,8 @@ struct TrunkProgram {
 };
 
 struct TrunkParams {
-  const uint4* tiles; const uint8_t* wstream; const float* params; const LayerDesc* layers;
+  const uint4* tiles; const uint8_t* wstream; const float* params;
+  LayerDesc layers[MAX_LAYERS];
   int numLayers, numItems, n;
   int NB, W, H, HW, stride, tileRowW;
   const int8_t* sym; const uint8_t* dstOfSrcRev;
@@ -99,6 +102,7 @@ struct TrunkParams {
   int* abortFlag;
   float poolScale1, poolScale2, invHW;
   int v2C;
+  int useWs;   // 1: one issuer warp, weight-stationary MMA pairs (B latched once for both tiles)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -336,13 +340,22 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
 }
 
-// One thread issues every tcgen05.mma of one tile.  Descriptors are kept as (hi, lo) words: hi holds
-// SBO = 128 B and the sm_100 version bit, lo = start address >> 4 | LBO >> 4 << 16; a tap or a K-chunk is
-// a plain add on lo.  For 3x3 layers the K loop is chunk-major: 16 input channels x (3 stages x 3 taps),
-// each stage = one kernel row (dy), so the row shift is (dy-1)*tileRowW + (dx-1).
-__device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const uint32_t sbase, const uint32_t bars,
-                                       const uint32_t tmemBase, volatile int* abortFlag) {
+// The MMA issuer of one tile: a whole warp runs the (warp-uniform) control flow and waits on the
+// barriers; one elected lane issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are kept
+// as (hi, lo) words: hi holds SBO = 128 B and the sm_100 version bit, lo = start address >> 4 |
+// LBO >> 4 << 16; a tap or a K-chunk is a plain add on lo.  For 3x3 layers the K loop is chunk-major:
+// 16 input channels x (3 stages x 3 taps), each stage = one kernel row (dy), so the row shift is
+// (dy-1)*tileRowW + (dx-1).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, const uint32_t sbase, const uint32_t bars,
+                                          const uint32_t tmemBase, volatile int* abortFlag) {
   uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
+  const bool leader = elect_one();
   const uint32_t descHi = (128u >> 4) | (1u << 14);
   const uint32_t aLo0 = (((sbase + OFF_ACT + t * ACT_BYTES + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
   const uint32_t ringLo0 = ((sbase + OFF_RING) & 0x3FFFFu) >> 4;
@@ -366,7 +379,6 @@ __device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const 
             const uint32_t bit = 1u << cc;
             if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
             chunkPhase ^= bit;
-            tc_fence_after();
           }
           const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
 #pragma unroll
@@ -375,12 +387,14 @@ __device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const 
             tc_fence_after();
             const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
             const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
-#pragma unroll
-            for(int dx = 0; dx < 3; dx++) {
-              umma_bf16(d, desc(aLoR + dx), desc(bLo + dx * bStep), idesc, accum);
-              accum = 1u;
+            if(leader) {
+              umma_bf16(d, desc(aLoR), desc(bLo), idesc, accum);
+              umma_bf16(d, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
+              umma_bf16(d, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
+              umma_commit(barEmpty + slot * 8);
             }
-            umma_commit(barEmpty + slot * 8);
+            __syncwarp();
+            accum = 1u;
             if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
           }
         }
@@ -389,7 +403,6 @@ __device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const 
         const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
         for(int s = 0; s < nst; s++) {
           if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
-          tc_fence_after();
           const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
           const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
           for(int kk = 0; kk < ks; kk++) {
@@ -398,17 +411,127 @@ __device__ __noinline__ void mmaIssuer(const TrunkParams& P, const int t, const 
               const uint32_t bit = 1u << cc;
               if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
               chunkPhase ^= bit;
-              tc_fence_after();
             }
-            umma_bf16(d, desc(aLo0 + cc * (2 * CHUNK_BYTES >> 4)), desc(bLo + kk * bStep), idesc, accum);
+            tc_fence_after();
+            if(leader) umma_bf16(d, desc(aLo0 + cc * (2 * CHUNK_BYTES >> 4)), desc(bLo + kk * bStep), idesc, accum);
+            __syncwarp();
             accum = 1u;
           }
-          umma_commit(barEmpty + slot * 8);
+          if(leader) umma_commit(barEmpty + slot * 8);
+          __syncwarp();
           if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
         }
       }
-      umma_commit(bars + (BAR_ACC + t) * 8);
-      if(l == P.numLayers - 1) umma_commit(bars + (BAR_ACTFREE + t) * 8);
+      if(leader) {
+        umma_commit(bars + (BAR_ACC + t) * 8);
+        if(l == P.numLayers - 1) umma_commit(bars + (BAR_ACTFREE + t) * 8);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Weight-stationary issuer: ONE warp drives both tiles.  Every weight K-step is latched in a collector
+// buffer by the MMA of tile 0 (collector::bN::fill) and re-used by the MMA of tile 1 (::lastuse), so the B
+// operand is read from shared memory once per pair: operand traffic drops from 128 to 96 B/clk/SM, under the
+// 128 B/clk shared-memory limit that caps plain 128x128x16 SS MMAs.  Layers whose N is not 64/128 (the
+// 96-wide head conv) fall back to plain MMAs.
+__device__ __forceinline__ void mmaIssuerWs(const TrunkParams& P, const uint32_t sbase, const uint32_t bars, const uint32_t tmemBase,
+                                            volatile int* abortFlag) {
+  uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
+  const bool leader = elect_one();
+  const uint32_t descHi = (128u >> 4) | (1u << 14);
+  const uint32_t aLo0 = (((sbase + OFF_ACT + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+  const uint32_t aTile = ACT_BYTES >> 4;
+  const uint32_t ringLo0 = ((sbase + OFF_RING) & 0x3FFFFu) >> 4;
+  const uint32_t barFull = bars + BAR_FULL * 8, barEmpty = bars + BAR_EMPTY * 8, barChunk = bars + BAR_CHUNK * 8;
+  auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
+  for(int item = blockIdx.x; item < P.numItems; item += gridDim.x, itemCount++) {
+    for(int t = 0; t < 2; t++) {
+      if(!mbar_wait(bars + (BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
+      if(itemCount > 0 && !mbar_wait(bars + (BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
+    }
+    tc_fence_after();
+    for(int l = 0; l < P.numLayers; l++) {
+      const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
+      const uint32_t idesc = idesc_bf16_f32(128, N);
+      const uint32_t d0 = tmemBase + (P.layers[l].outSel ? 128 : 0), d1 = d0 + 256;
+      const uint32_t bStep = 2 * N, bLbo = (uint32_t)N << 16;
+      uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
+      const bool ws = (N == 128 || N == 64);
+      if(ntaps == 9) {
+        const int nchunks = nk / 9;
+        for(int cc = 0; cc < nchunks; cc++) {
+          if(l > 0) {
+            const uint32_t b0 = 1u << cc, b1 = 1u << (8 + cc);
+            if(!mbar_wait(barChunk + cc * 8, (chunkPhase & b0) ? 1 : 0, abortFlag, 24)) return;
+            if(!mbar_wait(barChunk + (8 + cc) * 8, (chunkPhase & b1) ? 1 : 0, abortFlag, 25)) return;
+            chunkPhase ^= (b0 | b1);
+          }
+          const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
+#pragma unroll
+          for(int dy = 0; dy < 3; dy++) {
+            if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+            tc_fence_after();
+            const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+            const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
+            if(leader) {
+              if(ws) {
+                umma_bf16_ws<0, 0>(d0, desc(aLoR), desc(bLo), idesc, accum);
+                umma_bf16_ws<0, 2>(d1, desc(aLoR + aTile), desc(bLo), idesc, accum);
+                umma_bf16_ws<1, 0>(d0, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
+                umma_bf16_ws<1, 2>(d1, desc(aLoR + 1 + aTile), desc(bLo + bStep), idesc, 1u);
+                umma_bf16_ws<2, 0>(d0, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
+                umma_bf16_ws<2, 2>(d1, desc(aLoR + 2 + aTile), desc(bLo + 2 * bStep), idesc, 1u);
+              } else {
+                umma_bf16(d0, desc(aLoR), desc(bLo), idesc, accum);
+                umma_bf16(d1, desc(aLoR + aTile), desc(bLo), idesc, accum);
+                umma_bf16(d0, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
+                umma_bf16(d1, desc(aLoR + 1 + aTile), desc(bLo + bStep), idesc, 1u);
+                umma_bf16(d0, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
+                umma_bf16(d1, desc(aLoR + 2 + aTile), desc(bLo + 2 * bStep), idesc, 1u);
+              }
+              umma_commit(barEmpty + slot * 8);
+            }
+            __syncwarp();
+            accum = 1u;
+            if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+        for(int s = 0; s < nst; s++) {
+          if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+          const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+          const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
+          for(int kk = 0; kk < ks; kk++) {
+            const int cc = s * KSTEPS_PER_STAGE + kk;
+            if(l > 0) {
+              const uint32_t b0 = 1u << cc, b1 = 1u << (8 + cc);
+              if(!mbar_wait(barChunk + cc * 8, (chunkPhase & b0) ? 1 : 0, abortFlag, 24)) return;
+              if(!mbar_wait(barChunk + (8 + cc) * 8, (chunkPhase & b1) ? 1 : 0, abortFlag, 25)) return;
+              chunkPhase ^= (b0 | b1);
+            }
+            tc_fence_after();
+            if(leader) {
+              const uint32_t aLo = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
+              umma_bf16(d0, desc(aLo), desc(bLo + kk * bStep), idesc, accum);
+              umma_bf16(d1, desc(aLo + aTile), desc(bLo + kk * bStep), idesc, accum);
+            }
+            __syncwarp();
+            accum = 1u;
+          }
+          if(leader) umma_commit(barEmpty + slot * 8);
+          __syncwarp();
+          if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+        }
+      }
+      if(leader) {
+        umma_commit(bars + (BAR_ACC + 0) * 8);
+        umma_commit(bars + (BAR_ACC + 1) * 8);
+        if(l == P.numLayers - 1) { umma_commit(bars + (BAR_ACTFREE + 0) * 8); umma_commit(bars + (BAR_ACTFREE + 1) * 8); }
+      }
+      __syncwarp();
     }
   }
 }
@@ -425,7 +548,7 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
   for(int i = threadIdx.x; i < 2 * ACT_BYTES / 16; i += TRUNK_THREADS) reinterpret_cast<uint4*>(smem + OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
   for(int i = threadIdx.x; i < 8 * P.HW; i += TRUNK_THREADS) sSym[i] = P.dstOfSrcRev[i];
   if(threadIdx.x == 0) {
-    for(int i = 0; i < NSTAGES; i++) { mbar_init(bars + (BAR_FULL + i) * 8, 1); mbar_init(bars + (BAR_EMPTY + i) * 8, 2); }   // both MMA issuers release a slot
+    for(int i = 0; i < NSTAGES; i++) { mbar_init(bars + (BAR_FULL + i) * 8, 1); mbar_init(bars + (BAR_EMPTY + i) * 8, P.useWs ? 1 : 2); }   // every MMA issuer releases a slot
     for(int t = 0; t < 2; t++) {
       mbar_init(bars + (BAR_ACC + t) * 8, 1); mbar_init(bars + (BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (BAR_IN + t) * 8, 1);
       mbar_init(bars + (BAR_HEAD + t) * 8, 128);
@@ -476,7 +599,8 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
     }
   } else if(warp == 1 || warp == 2) {
     // =========================== MMA issuers: one thread per tile ===========================
-    if(lane == 0) mmaIssuer(P, warp - 1, sbase, bars, tmemBase, abortFlag);
+    if(P.useWs) { if(warp == 1) mmaIssuerWs(P, sbase, bars, tmemBase, abortFlag); }
+    else mmaIssuer(P, warp - 1, sbase, bars, tmemBase, abortFlag);
   } else if(warp == 3) {
     // idle (keeps the epilogue warps aligned to TMEM lane quadrants: warp % 4 == quadrant)
   } else {
@@ -552,7 +676,7 @@ __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __re
 // UMMA self-test kernel: D[128][N] = A[shift .. shift+128][K] * B[N][K]^T with the same descriptor
 // construction as the trunk (row-shifted A operand), one CTA.
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
-                                                            float* __restrict__ D, int rowsA, int N, int K, int shift, int* abortFlag) {
+                                                            float* __restrict__ D, int rowsA, int N, int K, int shift, int ws, int* abortFlag) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t barStorage;
   __shared__ uint32_t tmemSlot;
@@ -575,24 +699,54 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(&tmemSlot);
-  if(threadIdx.x == 0) {
+  if(threadIdx.x == 0 && ws >= 10) {
+    // throughput probe: `ws` back-to-back MMAs over the same operands, two accumulators alternating like the
+    // trunk's two tiles; D[0] receives cycles per MMA
+    uint32_t idesc = idesc_bf16_f32(128, N);
+    uint64_t adesc = smem_desc(smem_u32(sA) + shift * 16, (uint32_t)rowsA * 16, 128);
+    uint64_t bdesc = smem_desc(smem_u32(sB), (uint32_t)N * 16, 128);
+    long long t0 = clock64();
+    const uint32_t dA = tmemBase, dB = tmemBase + N;
+    for(int i = 0; i < ws; i += 8) {
+      umma_bf16(dA, adesc, bdesc, idesc, 1u); umma_bf16(dB, adesc + 1, bdesc, idesc, 1u);
+      umma_bf16(dA, adesc + 2, bdesc, idesc, 1u); umma_bf16(dB, adesc, bdesc, idesc, 1u);
+      umma_bf16(dA, adesc + 1, bdesc, idesc, 1u); umma_bf16(dB, adesc + 2, bdesc, idesc, 1u);
+      umma_bf16(dA, adesc, bdesc, idesc, 1u); umma_bf16(dB, adesc + 1, bdesc, idesc, 1u);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0, abortFlag, 42);
+    long long t1 = clock64();
+    D[0] = (float)(t1 - t0) / (float)ws;
+  } else if(threadIdx.x == 0) {
     uint32_t idesc = idesc_bf16_f32(128, N);
     for(int kc = 0; kc < K / 16; kc++) {
       uint64_t adesc = smem_desc(smem_u32(sA) + (2 * kc) * rowsA * 16 + shift * 16, (uint32_t)rowsA * 16, 128);
       uint64_t bdesc = smem_desc(smem_u32(sB) + (2 * kc) * N * 16, (uint32_t)N * 16, 128);
-      umma_bf16(tmemBase, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
+      if(!ws) umma_bf16(tmemBase, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
+      else {
+        // weight-stationary pair: D0 = A[shift..] B^T (fills collector b0), D1 = A[shift+1..] B^T (re-uses it)
+        uint64_t adesc1 = smem_desc(smem_u32(sA) + (2 * kc) * rowsA * 16 + (shift + 1) * 16, (uint32_t)rowsA * 16, 128);
+        if(kc & 1) {
+          umma_bf16_ws<1, 0>(tmemBase, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
+          umma_bf16_ws<1, 2>(tmemBase + N, adesc1, bdesc, idesc, kc > 0 ? 1u : 0u);
+        } else {
+          umma_bf16_ws<0, 0>(tmemBase, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
+          umma_bf16_ws<0, 2>(tmemBase + N, adesc1, bdesc, idesc, kc > 0 ? 1u : 0u);
+        }
+      }
     }
     umma_commit(bar);
   }
   bool ok = mbar_wait(bar, 0, abortFlag, 41);
   tc_fence_after();
-  if(ok) {
+  if(ok && ws < 10) {
     int row = warp * 32 + lane;
-    for(int c0 = 0; c0 < N; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmemBase + ((uint32_t)(warp * 32) << 16) + c0, v);
-      for(int j = 0; j < 16; j++) D[(size_t)row * N + c0 + j] = v[j];
-    }
+    for(int half = 0; half < (ws ? 2 : 1); half++)
+      for(int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmemBase + ((uint32_t)(warp * 32) << 16) + half * N + c0, v);
+        for(int j = 0; j < 16; j++) D[((size_t)half * 128 + row) * N + c0 + j] = v[j];
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -664,6 +818,7 @@ int buildTrunkProgram(kc_model* m) {
       if(b.regularConv.oc % 16 != 0 || b.regularConv.oc > 96 || b.regularConv.oc + b.gpoolConv.oc > MAX_C) return unsupported("gpool block: regular channels must be a multiple of 16, <= 96");
     }
   }
+  if(2 * m->blocks.size() + 2 > (size_t)MAX_LAYERS) return unsupported("too many blocks for the tcgen05 kernel's layer table");
   TrunkProgram* T = new TrunkProgram();
   Packer pk;
   double macs = 0;
@@ -787,8 +942,9 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev) {
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
   TrunkParams P{};
-  P.tiles = (const uint4*)h->d_tiles; P.wstream = T->d_w; P.params = T->d_params; P.layers = T->d_layers;
+  P.tiles = (const uint4*)h->d_tiles; P.wstream = T->d_w; P.params = T->d_params;
   P.numLayers = (int)T->layers.size();
+  for(int i = 0; i < P.numLayers; i++) P.layers[i] = T->layers[i];
   P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride;
   int numTiles = (n + P.NB - 1) / P.NB;
   P.numItems = (numTiles + 1) / 2;
@@ -801,6 +957,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev) {
   P.poolScale2 = (sq - 14.0f) * (sq - 14.0f) * 0.01f - 0.1f;
   P.invHW = 1.0f / (float)P.HW;
   P.v2C = T->v2C;
+  { const char* e = getenv("KC_TRUNK_WS"); P.useWs = e ? atoi(e) : 0; }   // measured slower than plain MMAs (profiles/), kept as an option
   int grid = std::min(P.numItems, h->ctx->smCount);
   if((int)h->evPool.size() < h->evUsed + 2 && h->evPool.size() < 4096) {
     cudaEvent_t a, b;
@@ -822,26 +979,29 @@ extern "C" {
 // Self-test of the UMMA descriptor conventions the trunk kernel relies on (row-shifted K-major
 // no-swizzle A operand): computes D = A[shift:shift+128] * B^T on the tensor core and returns it.
 // A [rowsA][K], B [N][K] as bf16 bit patterns (uint16), D [128][N] fp32. K % 16 == 0, N % 16 == 0.
-int kc_selftest_umma(kc_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int rowsA, int N, int K, int shift) {
+int kc_selftest_umma(kc_ctx* ctx, const uint16_t* A, const uint16_t* B, float* D, int rowsA, int N, int K, int shift, int ws) {
   using namespace kc;
   KC_CHECK(ctx && A && B && D, "kc_selftest_umma: null argument");
-  KC_CHECK(K % 16 == 0 && N % 16 == 0 && N <= 256 && shift >= 0 && shift + 128 <= rowsA, "kc_selftest_umma: bad shape");
+  KC_CHECK(K % 16 == 0 && N % 16 == 0 && N <= 256 && shift >= 0 && shift + 128 + (ws ? 1 : 0) <= rowsA, "kc_selftest_umma: bad shape");
+  KC_CHECK(ws == 0 || ws >= 10 || N == 64 || N == 128, "kc_selftest_umma: the weight-stationary form needs N in {64, 128} here (two accumulators)");
+  KC_CHECK(ws < 10 || N <= 128, "kc_selftest_umma: throughput probe uses two accumulators");
+  const int nOut = ws ? 2 : 1;
   size_t smemBytes = (size_t)(K / 8) * (rowsA + N) * 16;
   KC_CHECK(smemBytes <= 200 * 1024, "kc_selftest_umma: operands do not fit shared memory");
   KC_CUDA(cudaSetDevice(ctx->device));
   __nv_bfloat16 *dA, *dB; float* dD; int* dAbort;
   KC_CUDA(cudaMalloc(&dA, (size_t)rowsA * K * 2)); KC_CUDA(cudaMalloc(&dB, (size_t)N * K * 2));
-  KC_CUDA(cudaMalloc(&dD, (size_t)128 * N * 4)); KC_CUDA(cudaMalloc(&dAbort, 4));
+  KC_CUDA(cudaMalloc(&dD, (size_t)nOut * 128 * N * 4)); KC_CUDA(cudaMalloc(&dAbort, 4));
   KC_CUDA(cudaMemcpy(dA, A, (size_t)rowsA * K * 2, cudaMemcpyHostToDevice));
   KC_CUDA(cudaMemcpy(dB, B, (size_t)N * K * 2, cudaMemcpyHostToDevice));
-  KC_CUDA(cudaMemset(dD, 0, (size_t)128 * N * 4)); KC_CUDA(cudaMemset(dAbort, 0, 4));
+  KC_CUDA(cudaMemset(dD, 0, (size_t)nOut * 128 * N * 4)); KC_CUDA(cudaMemset(dAbort, 0, 4));
   KC_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  umma_probe_kernel<<<1, 128, smemBytes>>>(dA, dB, dD, rowsA, N, K, shift, dAbort);
+  umma_probe_kernel<<<1, 128, smemBytes>>>(dA, dB, dD, rowsA, N, K, shift, ws, dAbort);
   KC_CUDA(cudaGetLastError());
   KC_CUDA(cudaDeviceSynchronize());
   int abortCode = 0;
   KC_CUDA(cudaMemcpy(&abortCode, dAbort, 4, cudaMemcpyDeviceToHost));
-  KC_CUDA(cudaMemcpy(D, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost));
+  KC_CUDA(cudaMemcpy(D, dD, (size_t)nOut * 128 * N * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dAbort);
   KC_CHECK(abortCode == 0, "kc_selftest_umma: kernel timed out waiting on an mbarrier (code " + std::to_string(abortCode) + ")");
   return 0;

@@ -90,6 +90,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t dTmem, uint64_t aDesc, uint64
     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
     ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Weight-stationary form: the B operand is latched in collector buffer b<BUF>; FILL loads it from shared
+// memory, a following USE/LASTUSE MMA re-uses the latched copy, so two MMAs that share B (the two
+// activation tiles of a CTA against one weight block) read B from shared memory once.
+// MODE: 0 = fill, 1 = use, 2 = lastuse, 3 = discard.  Shapes: M in {32,64,128}, N in {64,128,256}.
+template <int BUF, int MODE>
+__device__ __forceinline__ void umma_bf16_ws(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
+#define KC_WS_ASM(SUFFIX)                                                                                   \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                          \
+               "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" SUFFIX " [%0], %1, %2, %3, p;\n\t}"      \
+               ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate) : "memory")
+  if constexpr(BUF == 0 && MODE == 0) KC_WS_ASM("b0::fill");
+  else if constexpr(BUF == 0 && MODE == 1) KC_WS_ASM("b0::use");
+  else if constexpr(BUF == 0 && MODE == 2) KC_WS_ASM("b0::lastuse");
+  else if constexpr(BUF == 0 && MODE == 3) KC_WS_ASM("b0::discard");
+  else if constexpr(BUF == 1 && MODE == 0) KC_WS_ASM("b1::fill");
+  else if constexpr(BUF == 1 && MODE == 2) KC_WS_ASM("b1::lastuse");
+  else if constexpr(BUF == 2 && MODE == 0) KC_WS_ASM("b2::fill");
+  else if constexpr(BUF == 2 && MODE == 2) KC_WS_ASM("b2::lastuse");
+  else if constexpr(BUF == 3 && MODE == 0) KC_WS_ASM("b3::fill");
+  else if constexpr(BUF == 3 && MODE == 2) KC_WS_ASM("b3::lastuse");
+  else static_assert(BUF < 0, "unsupported collector combination");
+#undef KC_WS_ASM
+}
 // arrives on `bar` when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -38,6 +38,19 @@ def test_umma_selftest(ctx, N, K, shift, rowsA):
     assert np.abs(D - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("N,K,shift,rowsA", [(128, 32, 0, 136), (128, 128, 24, 192), (64, 64, 5, 150)])
+def test_umma_weight_stationary_pair(ctx, N, K, shift, rowsA):
+    """tcgen05.mma.ws with the B operand latched in a collector buffer and re-used by the next MMA."""
+    from katacoffee_b200 import backend
+    rng = np.random.default_rng(N + K + shift)
+    A = bf16_round(rng.standard_normal((rowsA, K)).astype(np.float32))
+    B = bf16_round(rng.standard_normal((N, K)).astype(np.float32))
+    D = backend.selftestUmma(ctx, bf16_bits(A), bf16_bits(B), shift, ws=True)
+    for i in range(2):
+        ref = A[shift + i:shift + i + 128].astype(np.float64) @ B.astype(np.float64).T
+        assert np.abs(D[i] - ref).max() < 1e-3 * max(1.0, np.abs(ref).max()), i
+
+
 # ------------------------------------------------------------------------------------------------
 LAYER_CASES = golden("nn_layers_golden.json")
 
