@@ -63,57 +63,101 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {  // cpp/core/hash.c
   return x ^ (x >> 31);
 }
 
-__device__ __forceinline__ int padOf(const Geom& g, int cell) { return cell + cell / g.W; }
+// Board dimensions: compile-time for the hot 5x5 k=4 configuration (30-bit bitboards in 32-bit registers,
+// every loop unrolls into straight-line code), run-time otherwise (64-bit bitboards, rolled loops: the
+// generic kernel is instruction-cache sensitive).
+template <int CW, int CH, int CK>
+struct StaticDims {
+  static_assert(CH * (CW + 1) <= 32, "static boards must fit a 32-bit bitboard");
+  static constexpr bool kStatic = true;
+  static constexpr int kUnroll = 16;
+  using BB = uint32_t;
+  __device__ __forceinline__ explicit StaticDims(const Geom&) {}
+  __device__ __forceinline__ constexpr int W() const { return CW; }
+  __device__ __forceinline__ constexpr int H() const { return CH; }
+  __device__ __forceinline__ constexpr int K() const { return CK; }
+  __device__ __forceinline__ constexpr int HW() const { return CW * CH; }
+  __device__ __forceinline__ constexpr int stride() const { return CW + 1; }
+};
+struct DynDims {
+  static constexpr bool kStatic = false;
+  static constexpr int kUnroll = 1;
+  using BB = uint64_t;
+  int w, h, k;
+  __device__ __forceinline__ explicit DynDims(const Geom& g) : w(g.W), h(g.H), k(g.K) {}
+  __device__ __forceinline__ int W() const { return w; }
+  __device__ __forceinline__ int H() const { return h; }
+  __device__ __forceinline__ int K() const { return k; }
+  __device__ __forceinline__ int HW() const { return w * h; }
+  __device__ __forceinline__ int stride() const { return w + 1; }
+};
 
-// Legal Locs of the player to move, one padded bitboard per direction (board.cpp:185-227).
-// (loops are kept rolled on purpose: the kernel is instruction-cache sensitive)
-__device__ __forceinline__ void legalMasks(const Geom& g, uint64_t empty, int lastCell, int lastDir, uint64_t L[4]) {
-  uint64_t cand = empty;
-  if(lastDir < 4 && lastCell >= 0) {
-    int x = lastCell % g.W, y = lastCell / g.W;
-    int li = lastDir == 0 ? x : lastDir == 1 ? y : lastDir == 2 ? (x - y + g.H - 1) : (x + y);
-    cand &= g.lines[lastDir][li];
-  }
-#pragma unroll 1
-  for(int d = 0; d < 4; d++) {
-    int nl = (d == 0) ? g.W : (d == 1) ? g.H : (g.W + g.H - 1);
-    uint64_t ok = 0;
-#pragma unroll 1
-    for(int i = 0; i < nl; i++) {
-      uint64_t e = empty & g.lines[d][i];
-      ok |= (__popcll(e) >= 2) ? e : 0ULL;   // another empty cell anywhere on the same line
-    }
-    L[d] = cand & ok;
-  }
-}
-
-__device__ __forceinline__ uint64_t toDense(const Geom& g, uint64_t m) {
-  uint64_t r = 0;
-#pragma unroll 1
-  for(int y = 0; y < g.H; y++) r |= ((m >> (y * g.stride)) & g.rowMask) << (y * g.W);
-  return r;
-}
-
-// cells covered by a same-colour run of length >= n along shift s
-__device__ __forceinline__ uint64_t coverAtLeast(uint64_t m, int s, int n) {
-  uint64_t starts = m;
-#pragma unroll 1
-  for(int i = 1; i < n; i++) starts &= (m >> (i * s));
-  uint64_t c = starts;
-#pragma unroll 1
-  for(int i = 1; i < n; i++) c |= (starts << (i * s));
-  return c;
-}
-
-__device__ __forceinline__ int nthSetBit64(uint64_t m, int n) {  // n is 0-based
+__device__ __forceinline__ int popcBB(uint32_t v) { return __popc(v); }
+__device__ __forceinline__ int popcBB(uint64_t v) { return __popcll(v); }
+__device__ __forceinline__ int nthSetBit(uint32_t m, int n) { return __fns(m, 0, n + 1); }   // n is 0-based
+__device__ __forceinline__ int nthSetBit(uint64_t m, int n) {
   uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
   int c = __popc(lo);
   if(n < c) return __fns(lo, 0, n + 1);
   return 32 + __fns(hi, 0, n - c + 1);
 }
 
+template <class D>
+__device__ __forceinline__ int padOf(const D& dm, int cell) { return cell + cell / dm.W(); }
+template <class D>
+__device__ __forceinline__ int shiftOf(const D& dm, int d) {
+  return d == 0 ? dm.stride() : d == 1 ? 1 : d == 2 ? dm.stride() + 1 : dm.stride() - 1;
+}
+
+// Legal Locs of the player to move, one padded bitboard per direction (board.cpp:185-227).
+template <class D>
+__device__ __forceinline__ void legalMasks(const D& dm, const Geom& g, typename D::BB empty, int lastCell, int lastDir, typename D::BB L[4]) {
+  using BB = typename D::BB;
+  BB cand = empty;
+  if(lastDir < 4 && lastCell >= 0) {
+    int x = lastCell % dm.W(), y = lastCell / dm.W();
+    int li = lastDir == 0 ? x : lastDir == 1 ? y : lastDir == 2 ? (x - y + dm.H() - 1) : (x + y);
+    cand &= (BB)g.lines[lastDir][li];
+  }
+#pragma unroll D::kUnroll
+  for(int d = 0; d < 4; d++) {
+    int nl = (d == 0) ? dm.W() : (d == 1) ? dm.H() : (dm.W() + dm.H() - 1);
+    BB ok = 0;
+#pragma unroll D::kUnroll
+    for(int i = 0; i < nl; i++) {
+      BB e = empty & (BB)g.lines[d][i];
+      ok |= (popcBB(e) >= 2) ? e : (BB)0;   // another empty cell anywhere on the same line
+    }
+    L[d] = cand & ok;
+  }
+}
+
+template <class D>
+__device__ __forceinline__ uint64_t toDense(const D& dm, typename D::BB m) {
+  using BB = typename D::BB;
+  const BB rowMask = ((BB)1 << dm.W()) - 1;
+  uint64_t r = 0;
+#pragma unroll D::kUnroll
+  for(int y = 0; y < dm.H(); y++) r |= (uint64_t)((m >> (y * dm.stride())) & rowMask) << (y * dm.W());
+  return r;
+}
+
+// cells covered by a same-colour run of length >= n along shift s
+template <class D>
+__device__ __forceinline__ typename D::BB coverAtLeast(typename D::BB m, int s, int n) {
+  typename D::BB starts = m;
+#pragma unroll D::kUnroll
+  for(int i = 1; i < n; i++) starts &= (m >> (i * s));
+  typename D::BB c = starts;
+#pragma unroll D::kUnroll
+  for(int i = 1; i < n; i++) c |= (starts << (i * s));
+  return c;
+}
+
+template <class BB>
 struct GameRegs {
-  uint64_t black, white, h0, h1, id, misc;
+  BB black, white;
+  uint64_t h0, h1, id, misc;
 };
 
 __device__ __forceinline__ int histCell(uint64_t misc, int i) { return (int)((misc >> (8 * i)) & 0x3f); }
@@ -122,7 +166,8 @@ __device__ __forceinline__ int lastDirOf(uint64_t misc) { return (int)((misc >> 
 __device__ __forceinline__ int numTurnsOf(uint64_t misc) { return (int)((misc >> 48) & 0xff); }
 __device__ __forceinline__ int flagsOf(uint64_t misc) { return (int)((misc >> 56) & 0xff); }
 
-__device__ __forceinline__ void resetGame(const Geom& g, GameRegs& s, uint64_t id) {
+template <class BB>
+__device__ __forceinline__ void resetGame(const Geom& g, GameRegs<BB>& s, uint64_t id) {
   s.black = 0; s.white = 0;
   s.h0 = g.sizeHash[0]; s.h1 = g.sizeHash[1];
   s.id = id;
@@ -131,15 +176,18 @@ __device__ __forceinline__ void resetGame(const Geom& g, GameRegs& s, uint64_t i
 }
 
 // The 15 V1 planes as padded bitboards (nninputs.cpp:508-657, ledger F/G).
-__device__ __forceinline__ void v1Planes(const Geom& g, const GameRegs& s, const uint64_t L[4], uint64_t* P /*[15], stride pstride*/, int pstride) {
+template <class D>
+__device__ __forceinline__ void v1Planes(const D& dm, const Geom& g, const GameRegs<typename D::BB>& s, const typename D::BB L[4],
+                                         uint64_t* P /*[15], stride pstride*/, int pstride) {
+  using BB = typename D::BB;
   int fl = flagsOf(s.misc);
   int pla = (fl >> 3) & 3, opp = pla ^ 3;
-  uint64_t own = pla == 1 ? s.black : s.white, other = pla == 1 ? s.white : s.black;
+  BB own = pla == 1 ? s.black : s.white, other = pla == 1 ? s.white : s.black;
   int nt = numTurnsOf(s.misc);
   P[0 * pstride] = g.all;
   P[1 * pstride] = own;
   P[2 * pstride] = other;
-  uint64_t lastBit = histPla(s.misc, 0) ? (1ULL << padOf(g, histCell(s.misc, 0))) : 0ULL;
+  uint64_t lastBit = histPla(s.misc, 0) ? (1ULL << padOf(dm, histCell(s.misc, 0))) : 0ULL;
   int ld = lastDirOf(s.misc);
 #pragma unroll
   for(int d = 0; d < 4; d++) P[(3 + d) * pstride] = (ld == d) ? lastBit : 0ULL;
@@ -149,25 +197,23 @@ __device__ __forceinline__ void v1Planes(const Geom& g, const GameRegs& s, const
   for(int i = 1; i < 5; i++) {
     int want = (i & 1) ? pla : opp;
     ok = ok && nt >= i + 1 && histPla(s.misc, i) == want;
-    P[(6 + i) * pstride] = ok ? (1ULL << padOf(g, histCell(s.misc, i))) : 0ULL;
+    P[(6 + i) * pstride] = ok ? (1ULL << padOf(dm, histCell(s.misc, i))) : 0ULL;
   }
   P[11 * pstride] = L[0] | L[1] | L[2] | L[3];
   // stones in a maximal same-colour run of length exactly k-1, k-2, k-3 in some direction
-  uint64_t ex[3] = {0, 0, 0};
-#pragma unroll 1
+  BB ex[3] = {0, 0, 0};
+#pragma unroll D::kUnroll
   for(int cd = 0; cd < 8; cd++) {
-    {
-      const int d = cd & 3;
-      const uint64_t m = (cd & 4) ? s.white : s.black;
-      const int shift = d == 0 ? g.stride : d == 1 ? 1 : d == 2 ? g.stride + 1 : g.stride - 1;
-      uint64_t hi = coverAtLeast(m, shift, g.K);      // >= k
+    const int d = cd & 3;
+    const BB m = (cd & 4) ? s.white : s.black;
+    const int shift = shiftOf(dm, d);
+    BB hi = coverAtLeast<D>(m, shift, dm.K());      // >= k
 #pragma unroll
-      for(int j = 0; j < 3; j++) {
-        int len = g.K - 1 - j;
-        uint64_t lo = len >= 1 ? coverAtLeast(m, shift, len) : 0ULL;
-        ex[j] |= lo & ~hi;
-        hi = lo;
-      }
+    for(int j = 0; j < 3; j++) {
+      int len = dm.K() - 1 - j;
+      BB lo = len >= 1 ? coverAtLeast<D>(m, shift, len) : (BB)0;
+      ex[j] |= lo & ~hi;
+      hi = lo;
     }
   }
   P[12 * pstride] = ex[0];
@@ -175,9 +221,11 @@ __device__ __forceinline__ void v1Planes(const Geom& g, const GameRegs& s, const
   P[14 * pstride] = ex[2];
 }
 
-// One ply for one game. Returns the policy index played (-1 none).  Lnew = legal masks afterwards.
-__device__ __forceinline__ int stepGame(const Geom& g, GameRegs& s, int forcedMove, bool useForced,
-                                        const uint64_t* __restrict__ zob, uint64_t L[4], bool& illegal) {
+// One ply for one game. Returns the policy index played (-1 none).  L = legal masks afterwards.
+template <class D>
+__device__ __forceinline__ int stepGame(const D& dm, const Geom& g, GameRegs<typename D::BB>& s, int forcedMove, bool useForced,
+                                        const uint64_t* __restrict__ zob, typename D::BB L[4], bool& illegal) {
+  using BB = typename D::BB;
   illegal = false;
   int fl = flagsOf(s.misc);
   if((fl & 1) && g.autoRefill) {
@@ -185,20 +233,20 @@ __device__ __forceinline__ int stepGame(const Geom& g, GameRegs& s, int forcedMo
     fl = flagsOf(s.misc);
   }
   int pla = (fl >> 3) & 3;
-  uint64_t empty = g.all & ~(s.black | s.white);
+  BB empty = (BB)g.all & ~(s.black | s.white);
   int lastCell = histPla(s.misc, 0) ? histCell(s.misc, 0) : -1;
-  legalMasks(g, empty, lastCell, lastDirOf(s.misc), L);
+  legalMasks(dm, g, empty, lastCell, lastDirOf(s.misc), L);
   if(fl & 1) return -1;                         // finished, not refilled
   int dir = -1, cellPad = 0;
   if(useForced) {
     if(forcedMove < 0) return -1;
-    if(forcedMove >= 4 * g.HW) { illegal = true; return -1; }
-    dir = forcedMove / g.HW;
-    int cell = forcedMove % g.HW;               // ledger I
-    cellPad = padOf(g, cell);
-    if(!((L[dir] >> cellPad) & 1ULL)) { illegal = true; return -1; }
+    if(forcedMove >= 4 * dm.HW()) { illegal = true; return -1; }
+    dir = forcedMove / dm.HW();
+    int cell = forcedMove % dm.HW();               // ledger I
+    cellPad = padOf(dm, cell);
+    if(!((L[dir] >> cellPad) & (BB)1)) { illegal = true; return -1; }
   } else {
-    int c0 = __popcll(L[0]), c1 = __popcll(L[1]), c2 = __popcll(L[2]), c3 = __popcll(L[3]);
+    int c0 = popcBB(L[0]), c1 = popcBB(L[1]), c2 = popcBB(L[2]), c3 = popcBB(L[3]);
     int n = c0 + c1 + c2 + c3;
     if(n == 0) return -1;
     uint64_t r = splitmix64(g.seed ^ (s.id * 0x9E3779B97F4A7C15ULL) ^ (uint64_t)numTurnsOf(s.misc));
@@ -207,35 +255,32 @@ __device__ __forceinline__ int stepGame(const Geom& g, GameRegs& s, int forcedMo
     else if(k < c0 + c1) { dir = 1; k -= c0; }
     else if(k < c0 + c1 + c2) { dir = 2; k -= c0 + c1; }
     else { dir = 3; k -= c0 + c1 + c2; }
-    cellPad = nthSetBit64(L[dir], k);
+    cellPad = nthSetBit(L[dir], k);
   }
-  int y = cellPad / g.stride, x = cellPad - y * g.stride;
-  int cell = y * g.W + x;
+  int y = cellPad / dm.stride(), x = cellPad - y * dm.stride();
+  int cell = y * dm.W() + x;
   // play (board.cpp:427-435) and history (boardhistory.cpp:157-176)
-  uint64_t bit = 1ULL << cellPad;
+  BB bit = (BB)1 << cellPad;
   if(pla == 1) s.black |= bit; else s.white |= bit;
   const uint64_t* z = zob + ((size_t)cell * 2 + (pla - 1)) * 2;
   s.h0 ^= z[0]; s.h1 ^= z[1];
   uint64_t hist = ((s.misc & 0xffffffffULL) << 8) | (uint64_t)(cell | (pla << 6));
   int nt = numTurnsOf(s.misc) + 1;
   // win through the last move (board.cpp:376-383), overlines count
-  uint64_t mine = pla == 1 ? s.black : s.white;
+  BB mine = pla == 1 ? s.black : s.white;
   bool win = false;
-#pragma unroll 1
-  for(int d = 0; d < 4; d++) {
-    const int shift = d == 0 ? g.stride : d == 1 ? 1 : d == 2 ? g.stride + 1 : g.stride - 1;
-    win = win || ((coverAtLeast(mine, shift, g.K) & bit) != 0);
-  }
+#pragma unroll D::kUnroll
+  for(int d = 0; d < 4; d++) win = win || ((coverAtLeast<D>(mine, shiftOf(dm, d), dm.K()) & bit) != 0);
   int opp = pla ^ 3;
   // legal masks of the player now to move (also decides the draw, ledger C)
-  uint64_t empty2 = empty & ~bit;
-  legalMasks(g, empty2, cell, dir, L);
+  BB empty2 = empty & ~bit;
+  legalMasks(dm, g, empty2, cell, dir, L);
   bool none = (L[0] | L[1] | L[2] | L[3]) == 0;
   int finished = (win || none) ? 1 : 0;
   int winner = win ? pla : 0;
   int nfl = finished | (winner << 1) | (opp << 3);
   s.misc = (hist & 0xffffffffffULL) | ((uint64_t)dir << 40) | ((uint64_t)(nt & 0xff) << 48) | ((uint64_t)nfl << 56);
-  return dir * g.HW + cell;
+  return dir * dm.HW() + cell;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,7 +294,7 @@ struct FeatOut {
   int gamesPerBlock;
 };
 
-template <bool DO_STEP, int FEAT>
+template <bool DO_STEP, int FEAT, class D>
 __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
                                                         int useMoves, const uint64_t* __restrict__ zob,
                                                         StepOut so, FeatOut fo) {
@@ -260,6 +305,8 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
   // expansion is one shared load + one 128-bit store per four floats
   __shared__ uint32_t sBits[GPB * 15 * 49 / 32 + 4];
   const bool fastNCHW = (FEAT == 1) && fo.symmetry == nullptr;
+  const D dm(g);
+  using BB = typename D::BB;
   const int gpb = fo.gamesPerBlock;
   const int gBase = blockIdx.x * gpb;
   const int t = threadIdx.x;
@@ -268,17 +315,17 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
 
   if(FEAT != 0) {
     // symmetry tables: dst[sym(h,w)] = src[h,w] (nninputs.cpp:252-335), built per CTA (<= 8*49 entries)
-    for(int i = t; i < 8 * g.HW; i += THREADS) {
-      int sym = i / g.HW, cell = i % g.HW;
-      int h = cell / g.W, w = cell % g.W;
-      bool tr = (sym & 4) && g.H == g.W, fx = (sym & 2) != 0, fy = (sym & 1) != 0;
+    for(int i = t; i < 8 * dm.HW(); i += THREADS) {
+      int sym = i / dm.HW(), cell = i % dm.HW();
+      int h = cell / dm.W(), w = cell % dm.W();
+      bool tr = (sym & 4) && dm.H() == dm.W(), fx = (sym & 2) != 0, fy = (sym & 1) != 0;
       if(tr) { bool tmp = fx; fx = fy; fy = tmp; }
-      int rowStep = g.W, colStep = 1, base = 0;
-      if(fy) { base += (g.H - 1) * rowStep; rowStep = -rowStep; }
-      if(fx) { base += (g.W - 1) * colStep; colStep = -colStep; }
+      int rowStep = dm.W(), colStep = 1, base = 0;
+      if(fy) { base += (dm.H() - 1) * rowStep; rowStep = -rowStep; }
+      if(fx) { base += (dm.W() - 1) * colStep; colStep = -colStep; }
       if(tr) { int tmp = rowStep; rowStep = colStep; colStep = tmp; }
       int dst = base + h * rowStep + w * colStep;
-      sSrcPad[sym][dst] = (uint8_t)(cell + cell / g.W);
+      sSrcPad[sym][dst] = (uint8_t)(cell + cell / dm.W());
     }
     if(t < gpb) sSym[t] = (active && fo.symmetry) ? fo.symmetry[gi] : 0;
     if(fastNCHW) {
@@ -289,21 +336,21 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
 
   unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
   if(active) {
-    GameRegs s;
-    s.black = st.black[gi]; s.white = st.white[gi]; s.h0 = st.hash0[gi]; s.h1 = st.hash1[gi];
+    GameRegs<BB> s;
+    s.black = (BB)st.black[gi]; s.white = (BB)st.white[gi]; s.h0 = st.hash0[gi]; s.h1 = st.hash1[gi];
     s.id = st.gameId[gi]; s.misc = st.misc[gi];
-    uint64_t L[4];
+    BB L[4];
     int played = -1;
     bool illegal = false;
     if(DO_STEP) {
       int mv = useMoves ? (int)moves[gi] : -1;
-      played = stepGame(g, s, mv, useMoves != 0, zob, L, illegal);
-      st.black[gi] = s.black; st.white[gi] = s.white; st.hash0[gi] = s.h0; st.hash1[gi] = s.h1;
+      played = stepGame(dm, g, s, mv, useMoves != 0, zob, L, illegal);
+      st.black[gi] = (uint64_t)s.black; st.white[gi] = (uint64_t)s.white; st.hash0[gi] = s.h0; st.hash1[gi] = s.h1;
       st.gameId[gi] = s.id; st.misc[gi] = s.misc;
     } else {
-      uint64_t empty = g.all & ~(s.black | s.white);
+      BB empty = (BB)g.all & ~(s.black | s.white);
       int lastCell = histPla(s.misc, 0) ? histCell(s.misc, 0) : -1;
-      legalMasks(g, empty, lastCell, lastDirOf(s.misc), L);
+      legalMasks(dm, g, empty, lastCell, lastDirOf(s.misc), L);
     }
     int fl = flagsOf(s.misc);
     int nextPla = (fl >> 3) & 3;
@@ -318,12 +365,12 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
         uint64_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
         for(int d = 0; d < 4; d++) {
-          uint64_t dm = toDense(g, L[d]);
-          int off = d * g.HW, w = off >> 6, sh = off & 63;
+          uint64_t dense = toDense(dm, L[d]);
+          int off = d * dm.HW(), w = off >> 6, sh = off & 63;
 #pragma unroll
           for(int q = 0; q < 4; q++) {
-            if(q == w) acc[q] |= dm << sh;
-            if(q == w + 1 && sh) acc[q] |= dm >> (64 - sh);
+            if(q == w) acc[q] |= dense << sh;
+            if(q == w + 1 && sh) acc[q] |= dense >> (64 - sh);
           }
         }
         for(int wd = 0; wd < g.LW; wd++)
@@ -337,8 +384,8 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
     }
     if(FEAT != 0) {
       if(fastNCHW) {
-        v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
-        const int E = 15 * g.HW;
+        v1Planes(dm, g, s, L, &sPlanes[0][t], GPB + 1);
+        const int E = 15 * dm.HW();
         uint32_t bitPos = (uint32_t)t * E, wi = bitPos >> 5;
         int fill = bitPos & 31;
         uint64_t acc = 0;
@@ -349,13 +396,13 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
         };
 #pragma unroll 1
         for(int c = 0; c < 15; c++) {
-          uint64_t D = toDense(g, sPlanes[c][t]);
-          if(g.HW <= 25) append(D, g.HW);
-          else { append(D & 0x1FFFFFFULL, 25); append(D >> 25, g.HW - 25); }
+          uint64_t D = toDense(dm, (BB)sPlanes[c][t]);
+          if(dm.HW() <= 25) append(D, dm.HW());
+          else { append(D & 0x1FFFFFFULL, 25); append(D >> 25, dm.HW() - 25); }
         }
         if(fill) atomicOr(&sBits[wi], (uint32_t)acc);
       } else {
-        v1Planes(g, s, L, &sPlanes[0][t], GPB + 1);
+        v1Planes(dm, g, s, L, &sPlanes[0][t], GPB + 1);
       }
     }
   } else if(FEAT != 0 && t < GPB) {
@@ -388,8 +435,8 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
   const int ng = min(gpb, g.numGames - gBase);
   if(ng <= 0) return;
   if(fastNCHW) {
-    const int total = ng * 15 * g.HW;
-    float* out = fo.planes + (size_t)gBase * 15 * g.HW;
+    const int total = ng * 15 * dm.HW();
+    float* out = fo.planes + (size_t)gBase * 15 * dm.HW();
     float4* out4 = reinterpret_cast<float4*>(out);
     const int nvec = total >> 2;
     for(int j = t; j < nvec; j += THREADS) {
@@ -398,11 +445,11 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
       __stcs(&out4[j], v);
     }
     for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = (float)((sBits[e >> 5] >> (e & 31)) & 1u);
-    if(fo.global && t < ng) fo.global[gBase + t] = (float)g.K;
+    if(fo.global && t < ng) fo.global[gBase + t] = (float)dm.K();
   } else if(FEAT == 1 || FEAT == 2) {
-    const int E = 15 * g.HW;
+    const int E = 15 * dm.HW();
     const uint32_t magicE = (uint32_t)((0x100000000ULL + E - 1) / E);
-    const int inner = FEAT == 1 ? g.HW : 15;
+    const int inner = FEAT == 1 ? dm.HW() : 15;
     const uint32_t magicI = (uint32_t)((0x100000000ULL + inner - 1) / inner);
     const int total = ng * E;
     float* out = fo.planes + (size_t)gBase * E;
@@ -424,22 +471,22 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
       __stcs(&out4[j], v);
     }
     for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = elem(e);
-    if(fo.global && t < ng) fo.global[gBase + t] = (float)g.K;   // nninputs.cpp:656
+    if(fo.global && t < ng) fo.global[gBase + t] = (float)dm.K();   // nninputs.cpp:656
   } else if(FEAT == 3) {
     // trunk input tiles: row = y*tileRowW + b*(W+1) + x, 16 bf16 channels per row as two 16 B chunks
     // (channels 0..14 = V1 planes, channel 15 = the global feature win_len broadcast on board cells)
     const int ntiles = (ng + g.NB - 1) / g.NB;
     const int tileBase = gBase / g.NB;
     const uint32_t ONE = 0x3f80u;
-    const uint32_t kval = (uint32_t)__bfloat16_as_ushort(__float2bfloat16((float)g.K));
+    const uint32_t kval = (uint32_t)__bfloat16_as_ushort(__float2bfloat16((float)dm.K()));
     for(int j = t; j < ntiles * 256; j += THREADS) {
       int tile = j >> 8, chunk = (j >> 7) & 1, row = j & 127;
       int y = row / g.tileRowW, rr = row - y * g.tileRowW;
-      int b = rr / g.stride, x = rr - b * g.stride;
+      int b = rr / dm.stride(), x = rr - b * dm.stride();
       int gl = tile * g.NB + b;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if(y < g.H && x < g.W && gl < ng) {
-        int bit = sSrcPad[sSym[gl]][y * g.W + x];
+      if(y < dm.H() && x < dm.W() && gl < ng) {
+        int bit = sSrcPad[sSym[gl]][y * dm.W() + x];
         uint32_t w[4];
 #pragma unroll
         for(int q = 0; q < 4; q++) {
@@ -481,17 +528,23 @@ struct kc_games {
 namespace {
 using namespace kc;
 
+template <bool DO_STEP, class D>
+void launchGamesD(kc_games* G, int feat, int useMoves, const StepOut& so, const FeatOut& fo, int blocks) {
+  switch(feat) {
+    case 0: games_kernel<DO_STEP, 0, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 1: games_kernel<DO_STEP, 1, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 2: games_kernel<DO_STEP, 2, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    default: games_kernel<DO_STEP, 3, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+  }
+}
 template <bool DO_STEP>
 void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
   int gpb = feat == 3 ? G->geom.NB * 8 : GPB;   // FEAT 3: whole trunk tiles per CTA
   fo.gamesPerBlock = gpb;
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
-  switch(feat) {
-    case 0: games_kernel<DO_STEP, 0><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    case 1: games_kernel<DO_STEP, 1><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    case 2: games_kernel<DO_STEP, 2><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    default: games_kernel<DO_STEP, 3><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-  }
+  const Geom& g = G->geom;
+  if(g.W == 5 && g.H == 5 && g.K == 4) launchGamesD<DO_STEP, StaticDims<5, 5, 4>>(G, feat, useMoves, so, fo, blocks);
+  else launchGamesD<DO_STEP, DynDims>(G, feat, useMoves, so, fo, blocks);
   G->launches++;
 }
 

@@ -17,7 +17,9 @@ struct kc_handle {
   unsigned flags = 0;
   bool bf16 = true;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2dStream = nullptr, d2hStream = nullptr;   // kc_forward pipelines copy / compute / copy over row chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> chunkEvents;
   // staging of kc_forward's host rows
   float* d_raw = nullptr; float* d_rawGlobal = nullptr; int8_t* d_sym = nullptr;
   uint8_t* d_dstOfSrc = nullptr;     // [8][HW] copyInputsWithSymmetry map
@@ -41,7 +43,8 @@ namespace kc {
 // net_bf16.cu
 int allocTrunkBuffers(kc_handle* h);
 void freeTrunkBuffers(kc_handle* h);
-int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st);
-int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev);
+// rowOffset (a multiple of 2*NB rows) selects a chunk of the batch: inputs, tiles and outputs are all offset by it
+int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st, int rowOffset = 0);
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset = 0);
 int checkTrunkAbort(kc_handle* h);   // after a synchronise: non-zero (and error set) if the kernel bailed out
 }  // namespace kc

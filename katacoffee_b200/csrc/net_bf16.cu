@@ -928,29 +928,33 @@ int checkTrunkAbort(kc_handle* h) {
   return 0;
 }
 
-int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st) {
-  const int NB = boardsPerTile(h->W, h->H);
+int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st, int rowOffset) {
+  const int NB = boardsPerTile(h->W, h->H), HW = h->W * h->H;
   int numTiles = ((n + NB - 1) / NB + 1) & ~1;
-  k_convert_tiles<<<(numTiles * 256 + 255) / 256, 256, 0, st>>>(h->d_raw, h->d_rawGlobal, sym_dev, h->d_dstOfSrc, (uint4*)h->d_tiles, n, numTiles,
+  uint4* tiles = (uint4*)h->d_tiles + (size_t)(rowOffset / NB) * 2 * TILE_ROWS;
+  k_convert_tiles<<<(numTiles * 256 + 255) / 256, 256, 0, st>>>(h->d_raw + (size_t)rowOffset * 15 * HW, h->d_rawGlobal + rowOffset,
+                                                               sym_dev ? sym_dev + rowOffset : nullptr, h->d_dstOfSrc, tiles, n, numTiles,
                                                                NB, h->W, h->H, rawNHWC);
   h->launches++;
   KC_CUDA(cudaGetLastError());
   return 0;
 }
 
-int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev) {
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset) {
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
   TrunkParams P{};
-  P.tiles = (const uint4*)h->d_tiles; P.wstream = T->d_w; P.params = T->d_params;
+  P.wstream = T->d_w; P.params = T->d_params;
   P.numLayers = (int)T->layers.size();
   for(int i = 0; i < P.numLayers; i++) P.layers[i] = T->layers[i];
   P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride;
   int numTiles = (n + P.NB - 1) / P.NB;
   P.numItems = (numTiles + 1) / 2;
   P.n = n;
-  P.sym = sym_dev; P.dstOfSrcRev = h->d_dstOfSrcRev;
-  P.policy = h->d_policy; P.value = h->d_value; P.misc = h->d_misc; P.own = h->d_own;
+  P.tiles = (const uint4*)h->d_tiles + (size_t)(rowOffset / P.NB) * 2 * TILE_ROWS;
+  P.sym = sym_dev ? sym_dev + rowOffset : nullptr; P.dstOfSrcRev = h->d_dstOfSrcRev;
+  P.policy = h->d_policy + (size_t)rowOffset * 4 * P.HW; P.value = h->d_value + (size_t)rowOffset * 2;
+  P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;
   float sq = sqrtf((float)P.HW);
   P.poolScale1 = (sq - 14.0f) * 0.1f;

@@ -5,6 +5,7 @@
 // getOutput) with direct convolutions, so that policy/value agree with the Eigen-algorithm oracle
 // within 1e-4; it also backs the layer-level hooks (nninterface.h:127-169).  The production path
 // is the bf16 tcgen05 trunk in net_bf16.cu; this file owns the handle and dispatches to it.
+#include <algorithm>
 #include <cstring>
 #include <cmath>
 
@@ -428,7 +429,9 @@ int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLe
       delete h; return kc::fail("kc_handle_create: bf16 path needs H*(W+1) <= 128");
     }
   }
-  if(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = kc::fail("kc_handle_create: cudaStreamCreate failed");
+  if(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+     cudaStreamCreateWithFlags(&h->h2dStream, cudaStreamNonBlocking) != cudaSuccess ||
+     cudaStreamCreateWithFlags(&h->d2hStream, cudaStreamNonBlocking) != cudaSuccess) rc = kc::fail("kc_handle_create: cudaStreamCreate failed");
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   alloc(&h->d_raw, nb * 15 * HW * 4); alloc(&h->d_rawGlobal, nb * 4); alloc(&h->d_sym, nb);
   alloc(&h->d_policy, nb * 4 * HW * 4); alloc(&h->d_value, nb * 2 * 4); alloc(&h->d_misc, nb * 2 * 4); alloc(&h->d_own, nb * HW * 4);
@@ -475,6 +478,9 @@ int kc_handle_destroy(kc_handle* h) {
   if(h->ev0) cudaEventDestroy(h->ev0);
   if(h->ev1) cudaEventDestroy(h->ev1);
   if(h->stream) cudaStreamDestroy(h->stream);
+  if(h->h2dStream) cudaStreamDestroy(h->h2dStream);
+  if(h->d2hStream) cudaStreamDestroy(h->d2hStream);
+  for(cudaEvent_t e : h->chunkEvents) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -518,25 +524,55 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
   cudaStream_t st = h->stream;
   if(symmetry)
     for(int i = 0; i < n; i++) KC_CHECK(symmetry[i] >= 0 && symmetry[i] < 8, "kc_forward: symmetry must be within 0..7");
+  int rawNHWC = (h->flags & KC_FLAG_INPUTS_NHWC) ? 1 : 0;
+  if(h->bf16) {
+    // Pipelined over row chunks: H2D of chunk i+1 and D2H of chunk i-1 overlap the trunk kernel of chunk i
+    // (three streams, one event pair per chunk).  A chunk is a whole number of CTA work items per SM.
+    const int NB = boardsPerTile(h->W, h->H);
+    const int wave = 2 * NB * h->ctx->smCount;                 // rows that give every SM one work item
+    int chunk = ((n + 3) / 4 + wave - 1) / wave * wave;        // aim at 4 chunks
+    if(chunk < 2 * wave) chunk = 2 * wave;
+    const int numChunks = (n + chunk - 1) / chunk;
+    while((int)h->chunkEvents.size() < 2 * numChunks) {
+      cudaEvent_t e;
+      KC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->chunkEvents.push_back(e);
+    }
+    for(int c = 0; c < numChunks; c++) {
+      const int r0 = c * chunk, rows = std::min(chunk, n - r0);
+      KC_CUDA(cudaMemcpyAsync(h->d_raw + (size_t)r0 * 15 * HW, spatial + (size_t)r0 * 15 * HW, (size_t)rows * 15 * HW * 4, cudaMemcpyHostToDevice, h->h2dStream));
+      KC_CUDA(cudaMemcpyAsync(h->d_rawGlobal + r0, global + r0, (size_t)rows * 4, cudaMemcpyHostToDevice, h->h2dStream));
+      if(symmetry) KC_CUDA(cudaMemcpyAsync(h->d_sym + r0, symmetry + r0, (size_t)rows, cudaMemcpyHostToDevice, h->h2dStream));
+      KC_CUDA(cudaEventRecord(h->chunkEvents[2 * c], h->h2dStream));
+      KC_CUDA(cudaStreamWaitEvent(st, h->chunkEvents[2 * c], 0));
+      if(convertInputToTiles(h, rows, rawNHWC, symmetry ? h->d_sym : nullptr, st, r0)) return 1;
+      if(runTrunkBf16(h, rows, st, symmetry ? h->d_sym : nullptr, r0)) return 1;
+      KC_CUDA(cudaEventRecord(h->chunkEvents[2 * c + 1], st));
+      KC_CUDA(cudaStreamWaitEvent(h->d2hStream, h->chunkEvents[2 * c + 1], 0));
+      KC_CUDA(cudaMemcpyAsync(policy + (size_t)r0 * 4 * HW, h->d_policy + (size_t)r0 * 4 * HW, (size_t)rows * 4 * HW * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+      KC_CUDA(cudaMemcpyAsync(value + (size_t)r0 * 2, h->d_value + (size_t)r0 * 2, (size_t)rows * 2 * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+      KC_CUDA(cudaMemcpyAsync(misc + (size_t)r0 * 2, h->d_misc + (size_t)r0 * 2, (size_t)rows * 2 * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+      if(ownership) KC_CUDA(cudaMemcpyAsync(ownership + (size_t)r0 * HW, h->d_own + (size_t)r0 * HW, (size_t)rows * HW * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+    }
+    h->lastN = n;
+    KC_CUDA(cudaStreamSynchronize(h->d2hStream));
+    KC_CUDA(cudaStreamSynchronize(st));
+    return checkTrunkAbort(h);
+  }
   KC_CUDA(cudaMemcpyAsync(h->d_raw, spatial, (size_t)n * 15 * HW * 4, cudaMemcpyHostToDevice, st));
   KC_CUDA(cudaMemcpyAsync(h->d_rawGlobal, global, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   if(symmetry) KC_CUDA(cudaMemcpyAsync(h->d_sym, symmetry, (size_t)n, cudaMemcpyHostToDevice, st));
   const int8_t* sym_dev = symmetry ? h->d_sym : nullptr;
-  int rawNHWC = (h->flags & KC_FLAG_INPUTS_NHWC) ? 1 : 0;
-  if(h->bf16) {
-    if(convertInputToTiles(h, n, rawNHWC, sym_dev, st)) return 1;
-  } else {
-    k_convert_input<<<blocksFor((long long)n * HW * 15), 256, 0, st>>>(h->d_raw, sym_dev, h->d_dstOfSrc, h->f32.in, n, HW, 15, rawNHWC);
-    KC_CUDA(cudaMemcpyAsync(h->f32.global, h->d_rawGlobal, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-    h->launches += 1;
-  }
+  k_convert_input<<<blocksFor((long long)n * HW * 15), 256, 0, st>>>(h->d_raw, sym_dev, h->d_dstOfSrc, h->f32.in, n, HW, 15, rawNHWC);
+  KC_CUDA(cudaMemcpyAsync(h->f32.global, h->d_rawGlobal, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  h->launches += 1;
   if(handleRunOnStream(h, n, st, sym_dev)) return 1;
   KC_CUDA(cudaMemcpyAsync(policy, h->d_policy, (size_t)n * 4 * HW * 4, cudaMemcpyDeviceToHost, st));
   KC_CUDA(cudaMemcpyAsync(value, h->d_value, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, st));
   KC_CUDA(cudaMemcpyAsync(misc, h->d_misc, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, st));
   if(ownership) KC_CUDA(cudaMemcpyAsync(ownership, h->d_own, (size_t)n * HW * 4, cudaMemcpyDeviceToHost, st));
   KC_CUDA(cudaStreamSynchronize(st));
-  return checkTrunkAbort(h);
+  return 0;
 }
 
 // ---- layer hooks (nninterface.h:127-169) ---------------------------------------------------------
