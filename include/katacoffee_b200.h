@@ -184,6 +184,13 @@ int kc_games_features(kc_games* g, int layout, const int8_t* symmetry, float* pl
  * for a KC_FLAG_FP32_CHECK handle) directly into the handle's input buffer and the net is run;
  * nothing crosses PCIe.  Read the results with kc_handle_read_outputs. numGames <= maxBatch. */
 int kc_games_eval(kc_games* g, kc_handle* h, const int8_t* symmetry);
+/* NNEvaluator::evaluate post-processing (cpp/neuralnet/nneval.cpp:702-815) of the last kc_games_eval, on the
+ * device: policyProbs [G][4*H*W] = legal-masked softmax with temperature (illegal = -1), whiteWinLoss [G][2] =
+ * (whiteWinProb, whiteLossProb), misc [G][2] = (varTimeLeft, shorttermWinlossError) after softplus and the
+ * model's multipliers, nnHash [G][2] = NNInputs::getHash with default parameters (nninputs.cpp:463-470).
+ * Any output may be NULL. */
+int kc_games_postprocess(kc_games* g, kc_handle* h, float policyTemperature, float* policyProbs, float* whiteWinLoss, float* misc,
+                         uint64_t* nnHash);
 /* Fused hot-path step used by bench.py: [random-legal step (+refill) -> planes -> forward] x plies,
  * all on the device, no host synchronisation between plies.  h may be NULL (rules+features only:
  * fp32 NCHW planes, legal masks, status words and sit-hashes are written to device buffers owned

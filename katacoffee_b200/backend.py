@@ -200,6 +200,15 @@ class Games:
         sym = None if symmetry is None else np.ascontiguousarray(symmetry, np.int8)
         check(lib().kc_games_eval(self._p, handle._p, ptr(sym)))
 
+    def postprocess(self, handle, policyTemperature=1.0):
+        """NNEvaluator::evaluate post-processing of the last eval(): (policyProbs, whiteWinLoss, misc, nnHash)."""
+        policy = np.empty((self.G, 4 * self.HW), np.float32)
+        wl = np.empty((self.G, 2), np.float32)
+        misc = np.empty((self.G, 2), np.float32)
+        nnh = np.empty((self.G, 2), np.uint64)
+        check(lib().kc_games_postprocess(self._p, handle._p, policyTemperature, ptr(policy), ptr(wl), ptr(misc), ptr(nnh)))
+        return policy, wl, misc, nnh
+
     def run(self, handle, plies, stats=None):
         st = stats if stats is not None else capi.Stats()
         check(lib().kc_games_run(self._p, handle._p if handle is not None else None, plies, C.byref(st)))

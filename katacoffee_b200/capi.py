@@ -90,6 +90,7 @@ PROTOTYPES = {
     "kc_games_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "kc_games_features": (C.c_int, [vp, C.c_int, vp, vp, vp]),
     "kc_games_eval": (C.c_int, [vp, vp, vp]),
+    "kc_games_postprocess": (C.c_int, [vp, vp, C.c_float, vp, vp, vp, vp]),
     "kc_games_run": (C.c_int, [vp, vp, C.c_int, C.POINTER(Stats)]),
     "kc_games_run_timed": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.POINTER(Stats), C.POINTER(C.c_float)]),
     "kc_games_launch_count": (C.c_int64, [vp]),

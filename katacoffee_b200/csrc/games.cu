@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
     int fl = flagsOf(s.misc);
     int nextPla = (fl >> 3) & 3;
     uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
-    if(DO_STEP) {
+    {
       if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) |
                                     ((uint32_t)nextPla << 11) | (illegal ? (1u << 15) : 0u);
       if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
         for(int wd = 0; wd < g.LW; wd++)
           so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
       }
-      if(played >= 0) {
+      if(DO_STEP && played >= 0) {
         cSteps = 1;
         cXor = sh0;
         if(fl & 1) { cFin = 1; int wn = (fl >> 1) & 3; cB = wn == 1; cW = wn == 2; cD = wn == 0; }
@@ -746,7 +746,8 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) {
   if(symmetry) KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
   FeatOut fo{};
   fo.symmetry = symmetry ? G->d_sym : nullptr;
-  StepOut so{};
+  StepOut so = stepOutOf(G, true);   // also refreshes legal masks / status / sit-hashes of the evaluated positions
+  so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {
     fo.tiles = (uint4*)kc::handleInputTiles(h);
     launchGames<false>(G, 3, 0, so, fo);
@@ -819,6 +820,27 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
 
 int kc_games_run(kc_games* G, kc_handle* h, int plies, kc_stats* acc) {
   return kc_games_run_timed(G, h, plies, 0, acc, nullptr);
+}
+
+int kc_games_postprocess(kc_games* G, kc_handle* h, float policyTemperature, float* policyProbs, float* whiteWinLoss, float* misc,
+                         uint64_t* nnHash) {
+  KC_CHECK(G && h && policyTemperature > 0.f, "kc_games_postprocess: bad argument");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
+  size_t n = (size_t)g.numGames;
+  float *dP, *dV, *dM; uint64_t* dH;
+  KC_CUDA(cudaMalloc(&dP, n * 4 * g.HW * 4)); KC_CUDA(cudaMalloc(&dV, n * 8)); KC_CUDA(cudaMalloc(&dM, n * 8)); KC_CUDA(cudaMalloc(&dH, n * 16));
+  kc::launchPostprocess(h, g.numGames, g.LW, G->d_legal, G->d_status, G->d_sitHash, policyTemperature, dP, dV, dM, dH, G->stream);
+  G->launches++;
+  KC_CUDA(cudaGetLastError());
+  if(policyProbs) KC_CUDA(cudaMemcpyAsync(policyProbs, dP, n * 4 * g.HW * 4, cudaMemcpyDeviceToHost, G->stream));
+  if(whiteWinLoss) KC_CUDA(cudaMemcpyAsync(whiteWinLoss, dV, n * 8, cudaMemcpyDeviceToHost, G->stream));
+  if(misc) KC_CUDA(cudaMemcpyAsync(misc, dM, n * 8, cudaMemcpyDeviceToHost, G->stream));
+  if(nnHash) KC_CUDA(cudaMemcpyAsync(nnHash, dH, n * 16, cudaMemcpyDeviceToHost, G->stream));
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  cudaFree(dP); cudaFree(dV); cudaFree(dM); cudaFree(dH);
+  return 0;
 }
 
 int64_t kc_games_launch_count(const kc_games* G) { return G ? G->launches : 0; }

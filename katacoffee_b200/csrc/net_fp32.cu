@@ -154,6 +154,59 @@ __global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__
   out[((size_t)b * c + k) * HW + p] = in[i];
 }
 
+// NNEvaluator::evaluate post-processing (nneval.cpp:702-815), one warp per row: legal-masked softmax of the
+// policy logits with temperature (illegal -> -1, all-underflow -> uniform), 2-way softmax of win/loss logits,
+// softplus heads (desc.cpp:956-963 multipliers), flip to white's view, NNInputs::getHash with default
+// parameters (nninputs.cpp:463-470: sit-hash ^ GAME_IS_OVER when finished).
+__global__ void k_postprocess(const float* __restrict__ policyLogits, const float* __restrict__ valueLogits, const float* __restrict__ miscLogits,
+                              const uint32_t* __restrict__ legal, const uint32_t* __restrict__ status, const uint64_t* __restrict__ sitHash,
+                              int n, int policySize, int LW, float invTemp, float* __restrict__ policy, float* __restrict__ winLoss,
+                              float* __restrict__ misc, uint64_t* __restrict__ nnHash) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(row >= n) return;
+  const float* p = policyLogits + (size_t)row * policySize;
+  float mx = -1e25f;
+  int cnt = 0;
+  for(int i = lane; i < policySize; i += 32) {
+    bool ok = (legal[(size_t)row * LW + (i >> 5)] >> (i & 31)) & 1u;
+    float v = ok ? p[i] * invTemp : -1e30f;
+    cnt += ok;
+    mx = fmaxf(mx, v);
+  }
+  for(int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  float sum = 0.f;
+  for(int i = lane; i < policySize; i += 32) {
+    bool ok = (legal[(size_t)row * LW + (i >> 5)] >> (i & 31)) & 1u;
+    sum += expf((ok ? p[i] * invTemp : -1e30f) - mx);
+  }
+  for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for(int i = lane; i < policySize; i += 32) {
+    bool ok = (legal[(size_t)row * LW + (i >> 5)] >> (i & 31)) & 1u;
+    float v;
+    if(!ok) v = -1.0f;
+    else if(sum <= 0.f) v = cnt > 0 ? 1.0f / cnt : 0.f;
+    else v = expf(p[i] * invTemp - mx) / sum;
+    policy[(size_t)row * policySize + i] = v;
+  }
+  if(lane == 0) {
+    uint32_t st = status[row];
+    int nextPla = (st >> 11) & 3;
+    double w = valueLogits[2 * (size_t)row], l = valueLogits[2 * (size_t)row + 1];
+    double m = fmax(w, l), ew = exp(w - m), el = exp(l - m), ps = ew + el;
+    double winProb = ew / ps, lossProb = el / ps;
+    auto softPlus = [](double x) { return x > 40.0 ? x : log(1.0 + exp(x)); };
+    double vtl = softPlus((double)miscLogits[2 * (size_t)row]) * 40.0;
+    double s = softPlus((double)miscLogits[2 * (size_t)row + 1] * 0.5);
+    winLoss[2 * (size_t)row] = (float)(nextPla == 2 ? winProb : lossProb);
+    winLoss[2 * (size_t)row + 1] = (float)(nextPla == 2 ? lossProb : winProb);
+    misc[2 * (size_t)row] = (float)vtl;
+    misc[2 * (size_t)row + 1] = (float)sqrt(s * s * 0.25);
+    bool fin = (st >> 8) & 1;
+    nnHash[2 * (size_t)row] = sitHash[2 * (size_t)row] ^ (fin ? ZOBRIST_GAME_IS_OVER0 : 0ULL);
+    nnHash[2 * (size_t)row + 1] = sitHash[2 * (size_t)row + 1] ^ (fin ? ZOBRIST_GAME_IS_OVER1 : 0ULL);
+  }
+}
+
 static inline int blocksFor(long long total, int threads = 256) { return (int)((total + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,6 +364,11 @@ void* handleInputTiles(kc_handle* h) { return h->d_tiles; }
 float* handleInputNHWC(kc_handle* h) { return h->f32.in; }
 float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
 int handleCheckAbort(kc_handle* h) { return checkTrunkAbort(h); }
+void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, const uint32_t* status_dev, const uint64_t* sitHash_dev,
+                       float policyTemperature, float* policy_dev, float* winLoss_dev, float* misc_dev, uint64_t* nnHash_dev, cudaStream_t stream) {
+  k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy, h->d_value, h->d_misc, legal_dev, status_dev, sitHash_dev, n,
+                                                                 4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
+}
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev) {
   h->lastN = n;
   if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev);

@@ -494,3 +494,62 @@ def test_cpp_nninterface_backend(ctx):
     lib, exe = kb.build_host()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "b200backend ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_postprocess_matches_oracle(ctx, oracle, mode):
+    """kc_games_postprocess == NNEvaluator::evaluate post-processing (nneval.cpp:702-815) applied to the same
+    logits, and NNInputs::getHash (sit-hash ^ GAME_IS_OVER on finished games)."""
+    from katacoffee_b200 import backend, modeldesc
+    G, W, H, seed = 600, 5, 5, 33
+    model = modeldesc.Model("b2c32", seed=4)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=(mode == "fp32"))
+    games = backend.Games(ctx, G, W, H, 4)
+    games.reset(seed=seed)
+    for t in range(17):
+        out = games.step()
+    games.eval(h)
+    logits = h.readOutputs(G)
+    for temp in (1.0, 0.7):
+        pol, wl, misc, nnh = games.postprocess(h, temp)
+        og = oracle.Game(W, H, 4)
+        nfin = 0
+        for g in range(G):
+            og.reset()
+            for t in range(17):
+                if og.finished():
+                    break
+                og.play(og.choose(seed, g))
+            assert (og.nn_hash() == nnh[g]).all()
+            nfin += og.finished()
+            legal, n = og.legal_mask()
+            ep, ev, em = oracle.postprocess(logits[0][g], legal, logits[1][g], logits[2][g], og.next_pla(), temp)
+            if n > 0:
+                assert np.abs(ep - pol[g]).max() < 2e-6, g
+            else:
+                assert (pol[g] == -1).all()
+            assert np.abs(ev - wl[g]).max() < 1e-6 and np.allclose(em, misc[g], rtol=1e-5, atol=1e-6)
+        assert 0 < nfin < G
+    for x in (games, h, lm):
+        x.close()
+
+
+def test_b15c192_6x6_check_path_and_bf16_rejection(ctx, oracle):
+    """BASELINE config 5 (6x6 k=4, b15c192): the fp32 check path matches the oracle; the tcgen05 path does not
+    support 192 trunk channels yet and must say so instead of falling back to anything."""
+    from katacoffee_b200 import backend, modeldesc, capi
+    W = H = 6
+    n = 24
+    model = modeldesc.Model("b15c192", seed=6)
+    om = oracle.Model(model)
+    planes, glob, _ = position_batch_full(oracle, W, H, 4, 9, n)
+    sym = (np.arange(n) % 8).astype(np.int8)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, n, W, H, useFP32Check=True)
+    got = backend.getOutput(h, planes, glob, sym)
+    ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_FP32
+    with pytest.raises(capi.KCError, match="trunk channels"):
+        backend.createComputeHandle(ctx, lm, n, W, H)
+    h.close(); lm.close()
