@@ -58,7 +58,8 @@ constexpr int OFF_POOLB = OFF_POOLA + 2 * MAX_NB * 96 * 4;
 constexpr int OFF_BIAS = OFF_POOLB + 2 * MAX_NB * 96 * 4;
 constexpr int OFF_V2 = OFF_BIAS + 2 * MAX_NB * 96 * 4;
 constexpr int OFF_SYM = OFF_V2 + 2 * MAX_NB * MAX_V2 * 4;
-constexpr int OFF_BAR = OFF_SYM + 448;
+constexpr int OFF_PAR = OFF_SYM + 448;                     // [tile][2 buffers][scale 128 | bias 128] fp32: the next layer's folded BN,
+constexpr int OFF_BAR = OFF_PAR + 2 * 2 * 2 * MAX_C * 4;   // staged while the tensor core is still busy with that layer
 // barriers (8 bytes each)
 constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + 2,
               BAR_IN = BAR_ACTFREE + 2, BAR_HEAD = BAR_IN + 2, BAR_CHUNK = BAR_HEAD + 2, NUM_BARS = BAR_CHUNK + 2 * 8;
@@ -123,6 +124,7 @@ struct EpiCtx {
   uint8_t* act;     // this tile's activation buffer
   uint32_t barChunk;  // smem address of actReady[t][0]
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
+  const float* par;  // staged folded BN of the layer being finished: scale[MAX_C] | bias[MAX_C]
 };
 
 // folded BN + ReLU + mask for 16 columns -> two 16-byte chunks of the activation tile
@@ -130,8 +132,8 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
   uint32_t pk[8];
 #pragma unroll
   for(int q = 0; q < 4; q++) {
-    float4 s = __ldg(reinterpret_cast<const float4*>(scale + cc * 16) + q);
-    float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cc * 16) + q);
+    float4 s = *(reinterpret_cast<const float4*>(scale + cc * 16) + q);     // shared memory (c.par), staged before the accumulator wait
+    float4 bb = *(reinterpret_cast<const float4*>(bias + cc * 16) + q);
     float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
     if(add) { x0 += add[cc * 16 + 4 * q]; x1 += add[cc * 16 + 4 * q + 1]; x2 += add[cc * 16 + 4 * q + 2]; x3 += add[cc * 16 + 4 * q + 3]; }
     float a0 = fmaxf(fmaf(x0, s.x, bb.x), 0.f), a1 = fmaxf(fmaf(x1, s.y, bb.y), 0.f);
@@ -169,13 +171,27 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
 }
 
 __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c) {
-  const float* scale = P.params + L.pOff;
-  const float* bias = scale + L.epiC;
+  const float* scale = c.par;
+  const float* bias = c.par + MAX_C;
   uint32_t src = c.tmemLane + (L.outSel ? 128 : 0);
-  for(int cc = 0; cc < L.epiC / 16; cc++) {
+  const int nch = L.epiC / 16;
+  // software pipeline: the TMEM load of chunk cc+1 is in flight while chunk cc is normalised, packed and published
+  uint32_t ra[16], rb[16];
+  tmem_ld16_issue(src, ra);
+  tmem_ld16_wait(ra);
+  for(int cc = 0; cc < nch; cc += 2) {
     float v[16];
-    tmem_ld16(src + cc * 16, v);
+    if(cc + 1 < nch) tmem_ld16_issue(src + (cc + 1) * 16, rb);
+#pragma unroll
+    for(int i = 0; i < 16; i++) v[i] = __uint_as_float(ra[i]);
     publish16(c, cc, v, scale, bias, nullptr);
+    if(cc + 1 >= nch) break;
+    tmem_ld16_wait(rb);
+    if(cc + 2 < nch) tmem_ld16_issue(src + (cc + 2) * 16, ra);
+#pragma unroll
+    for(int i = 0; i < 16; i++) v[i] = __uint_as_float(rb[i]);
+    publish16(c, cc + 1, v, scale, bias, nullptr);
+    if(cc + 2 < nch) tmem_ld16_wait(ra);
   }
 }
 
@@ -185,8 +201,8 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
   const float* gs = P.params + L.pOff;
   const float* gb = gs + G;
   const float* Wg = gb + G;
-  const float* ms = Wg + 3 * G * R;
-  const float* mb = ms + R;
+  const float* ms = c.par;            // midBN staged in shared memory
+  const float* mb = c.par + MAX_C;
   uint32_t src = c.tmemLane + 128;   // region S
   float* pooled = c.poolA;           // [NB][3G]
   __shared__ float sSum[2][MAX_NB * 16], sMax[2][MAX_NB * 16];
@@ -629,6 +645,17 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
     for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x) {
       for(int l = 0; l < P.numLayers && alive; l++, layerCount++) {
         const LayerDesc L = P.layers[l];
+        {
+          // stage this layer's folded BN (the one applied to its output) while its MMAs are still running
+          float* par = reinterpret_cast<float*>(smem + OFF_PAR) + (c.t * 2 + (layerCount & 1)) * 2 * MAX_C;
+          if(L.epi != EPI_HEAD && c.e < L.epiC) {
+            const float* sc = P.params + L.pOff + (L.epi == EPI_GPOOL ? 2 * L.gpoolC + 3 * L.gpoolC * L.epiC : 0);
+            par[c.e] = __ldg(sc + c.e);
+            par[MAX_C + c.e] = __ldg(sc + L.epiC + c.e);
+          }
+          c.par = par;
+          named_bar_sync(1 + c.t, 128);
+        }
         alive = mbar_wait(bars + (BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
         if(!alive) break;
         tc_fence_after();

@@ -588,7 +588,7 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
     // (three streams, one event pair per chunk).  A chunk is a whole number of CTA work items per SM.
     const int NB = boardsPerTile(h->W, h->H);
     const int wave = 2 * NB * h->ctx->smCount;                 // rows that give every SM one work item
-    int chunk = ((n + 3) / 4 + wave - 1) / wave * wave;        // aim at 4 chunks
+    int chunk = ((n + 7) / 8 + wave - 1) / wave * wave;        // aim at 8 chunks
     if(chunk < 2 * wave) chunk = 2 * wave;
     const int numChunks = (n + chunk - 1) / chunk;
     while((int)h->chunkEvents.size() < 2 * numChunks) {
