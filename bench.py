@@ -89,6 +89,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+    bench command (profiles/summarize.py writes the file); None if the capture is absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        t = json.load(f).get(name)
+    return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
+
+
 def dist_setup(n_gpus):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -257,12 +269,12 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "trunk_kernel (tcgen05 whole-net forward)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "traffic": load_traffic("prof_trunk"), "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
             "roofline_rules_features": {"kernel": "games_kernel<step, fp32 NCHW planes> at 65536 games", "bound": "hbm",
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
-                                        "bytes_per_game_step": BYTES_PER_STEP_FP32},
+                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games")},
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
                       "black_wins": int(counters[3]), "white_wins": int(counters[4]), "draws": int(counters[5])},
         }

@@ -38,33 +38,46 @@ namespace kc {
 
 using namespace ptx;
 
-constexpr int MAX_C = 128;
 constexpr int CHUNK_BYTES = ACT_ROWS * 16;             // one 8-channel chunk of an activation tile
-constexpr int ACT_BYTES = (MAX_C / 8) * CHUNK_BYTES;   // 49152
 constexpr int KSTEPS_PER_STAGE = 3;
-constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAX_C * 32;  // 12288
-constexpr int NSTAGES = 7;
 constexpr int SCR_STRIDE = 17;
 constexpr int MAX_NB = 4;
-constexpr int TRUNK_THREADS = 384;   // warp 0 TMA producer, 1-2 MMA issuers (tile 0/1), 3 idle, 4-7 / 8-11 epilogue of tile 0 / 1
 constexpr int HEADC = 32;   // p1 = g1 = v1 = 32 channels
 constexpr int MAX_V2 = 128;
 
-constexpr int OFF_ACT = 0;
-constexpr int OFF_RING = OFF_ACT + 2 * ACT_BYTES;
-constexpr int OFF_SCR = OFF_RING + NSTAGES * STAGE_BYTES;
-constexpr int OFF_POOLA = OFF_SCR + 2 * 128 * SCR_STRIDE * 4;
-constexpr int OFF_POOLB = OFF_POOLA + 2 * MAX_NB * 96 * 4;
-constexpr int OFF_BIAS = OFF_POOLB + 2 * MAX_NB * 96 * 4;
-constexpr int OFF_V2 = OFF_BIAS + 2 * MAX_NB * 96 * 4;
-constexpr int OFF_SYM = OFF_V2 + 2 * MAX_NB * MAX_V2 * 4;
-constexpr int OFF_PAR = OFF_SYM + 448;                     // [tile][2 buffers][scale 128 | bias 128] fp32: the next layer's folded BN,
-constexpr int OFF_BAR = OFF_PAR + 2 * 2 * 2 * MAX_C * 4;   // staged while the tensor core is still busy with that layer
-// barriers (8 bytes each)
-constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + 2,
-              BAR_IN = BAR_ACTFREE + 2, BAR_HEAD = BAR_IN + 2, BAR_CHUNK = BAR_HEAD + 2, NUM_BARS = BAR_CHUNK + 2 * 8;
-constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr int TRUNK_SMEM = OFF_TMEM + 16;
+// Compile-time shape of one trunk-kernel instantiation.  <128, 2, 7>: trunks up to 128 channels, two activation tiles
+// per CTA (TMEM: 2 x (T 128 + S 128) columns).  <192, 1, 6>: trunks up to 192 channels (b15c192), one tile per CTA
+// (TMEM: T 192 + S 192 columns of the 512 allocated).
+template <int MAXC_, int NT_, int NSTAGES_>
+struct TrunkCfg {
+  static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_;
+  static constexpr int NCH = MAXC / 16;                       // 16-channel chunks the epilogue publishes
+  static constexpr int MAXG = MAXC / 4 < 32 ? 32 : MAXC / 3;  // gpool channels: 32 (c128), 64 (c192)
+  static constexpr int POOLW = 3 * MAXG;                      // pooled vector per board (>= 96 for the heads)
+  static constexpr int THREADS = 128 + NT * 128;              // warp 0 TMA producer, 1..NT MMA issuers, 4.. epilogue (4 warps per tile)
+  static constexpr int ACT_BYTES = (MAXC / 8) * CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAXC * 32;
+  static constexpr int OFF_ACT = 0;
+  static constexpr int OFF_RING = OFF_ACT + NT * ACT_BYTES;
+  static constexpr int OFF_SCR = OFF_RING + NSTAGES * STAGE_BYTES;
+  static constexpr int OFF_POOLA = OFF_SCR + NT * 128 * SCR_STRIDE * 4;
+  static constexpr int OFF_POOLB = OFF_POOLA + NT * MAX_NB * POOLW * 4;
+  static constexpr int OFF_BIAS = OFF_POOLB + NT * MAX_NB * POOLW * 4;
+  static constexpr int OFF_V2 = OFF_BIAS + NT * MAX_NB * MAXC * 4;
+  static constexpr int OFF_SYM = OFF_V2 + NT * MAX_NB * MAX_V2 * 4;
+  static constexpr int OFF_PAR = OFF_SYM + 448;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
+  static constexpr int OFF_BAR = OFF_PAR + NT * 2 * 2 * MAXC * 4; // folded BN, staged while the tensor core is still busy with it
+  // barriers (8 bytes each)
+  static constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + NT,
+                       BAR_IN = BAR_ACTFREE + NT, BAR_HEAD = BAR_IN + NT, BAR_CHUNK = BAR_HEAD + NT, NUM_BARS = BAR_CHUNK + NT * NCH;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM = OFF_TMEM + 16;
+  static_assert(NT * 2 * MAXC <= 512, "TMEM: every tile needs a trunk region and a block-internal region");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(POOLW >= 96, "the heads pool 32 channels three ways");
+};
+using Cfg128 = TrunkCfg<128, 2, 7>;
+using Cfg192 = TrunkCfg<192, 1, 6>;
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
 
@@ -90,6 +103,7 @@ struct TrunkProgram {
   LayerDesc* d_layers = nullptr;
   size_t wBytes = 0;
   int v2C = 0;
+  int cfg = 0;     // 0: TrunkCfg<128, 2, 7>, 1: TrunkCfg<192, 1, 6>
   double flopsPerEval = 0;
 };
 
@@ -103,7 +117,6 @@ struct TrunkParams {
   int* abortFlag;
   float poolScale1, poolScale2, invHW;
   int v2C;
-  int useWs;   // 1: one issuer warp, weight-stationary MMA pairs (B latched once for both tiles)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -124,7 +137,7 @@ struct EpiCtx {
   uint8_t* act;     // this tile's activation buffer
   uint32_t barChunk;  // smem address of actReady[t][0]
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
-  const float* par;  // staged folded BN of the layer being finished: scale[MAX_C] | bias[MAX_C]
+  const float* par;  // staged folded BN of the layer being finished: scale[K::MAXC] | bias[K::MAXC]
 };
 
 // folded BN + ReLU + mask for 16 columns -> two 16-byte chunks of the activation tile
@@ -170,10 +183,11 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
   named_bar_sync(1 + c.t, 128);
 }
 
+template <class K>
 __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c) {
   const float* scale = c.par;
-  const float* bias = c.par + MAX_C;
-  uint32_t src = c.tmemLane + (L.outSel ? 128 : 0);
+  const float* bias = c.par + K::MAXC;
+  uint32_t src = c.tmemLane + (L.outSel ? K::MAXC : 0);
   const int nch = L.epiC / 16;
   // software pipeline: the TMEM load of chunk cc+1 is in flight while chunk cc is normalised, packed and published
   uint32_t ra[16], rb[16];
@@ -196,14 +210,15 @@ __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCt
 }
 
 // params: gpoolBN scale[G] bias[G] | Wg [3G][R] | midBN scale[R] bias[R]
+template <class K>
 __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c) {
   const int R = L.epiC, G = L.gpoolC;
   const float* gs = P.params + L.pOff;
   const float* gb = gs + G;
   const float* Wg = gb + G;
   const float* ms = c.par;            // midBN staged in shared memory
-  const float* mb = c.par + MAX_C;
-  uint32_t src = c.tmemLane + 128;   // region S
+  const float* mb = c.par + K::MAXC;
+  uint32_t src = c.tmemLane + K::MAXC;   // region S
   float* pooled = c.poolA;           // [NB][3G]
   __shared__ float sSum[2][MAX_NB * 16], sMax[2][MAX_NB * 16];
   for(int half = 0; half < G / 16; half++) {
@@ -228,10 +243,10 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
     int b = idx / R, oc = idx - b * R;
     float acc = 0.f;
     for(int k = 0; k < 3 * G; k++) acc = fmaf(pooled[b * 3 * G + k], __ldg(Wg + k * R + oc), acc);
-    c.biasBuf[b * 96 + oc] = acc;
+    c.biasBuf[b * K::MAXC + oc] = acc;
   }
   named_bar_sync(1 + c.t, 128);
-  const float* add = c.biasBuf + c.b * 96;
+  const float* add = c.biasBuf + c.b * K::MAXC;
   for(int cc = 0; cc < R / 16; cc++) {
     float v[16];
     tmem_ld16(src + cc * 16, v);
@@ -241,6 +256,7 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
 
 // params: g1BN s[32] b[32] | Wpb [96][32] | p1BN s[32] b[32] | W2 [32][4] | v1BN s[32] b[32] |
 //         Wv2 [96][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [32]
+template <class K>
 __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
                              const uint8_t* sSym) {
   const int V2 = P.v2C;
@@ -259,7 +275,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   const float* Wsv3 = b3 + 2;
   const float* bsv3 = Wsv3 + V2 * 2;
   const float* Wown = bsv3 + 2;
-  uint32_t src = c.tmemLane + 128;
+  uint32_t src = c.tmemLane + K::MAXC;
   __shared__ float sSum[2][MAX_NB * 16], sMax[2][MAX_NB * 16];
   float* pooledG = c.poolA;   // [NB][96]
   float* pooledV = c.poolB;   // [NB][96]
@@ -368,23 +384,24 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+template <class K>
 __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, const uint32_t sbase, const uint32_t bars,
                                           const uint32_t tmemBase, volatile int* abortFlag) {
   uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
   const bool leader = elect_one();
   const uint32_t descHi = (128u >> 4) | (1u << 14);
-  const uint32_t aLo0 = (((sbase + OFF_ACT + t * ACT_BYTES + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
-  const uint32_t ringLo0 = ((sbase + OFF_RING) & 0x3FFFFu) >> 4;
-  const uint32_t barFull = bars + BAR_FULL * 8, barEmpty = bars + BAR_EMPTY * 8, barChunk = bars + (BAR_CHUNK + t * 8) * 8;
+  const uint32_t aLo0 = (((sbase + K::OFF_ACT + t * K::ACT_BYTES + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+  const uint32_t ringLo0 = ((sbase + K::OFF_RING) & 0x3FFFFu) >> 4;
+  const uint32_t barFull = bars + K::BAR_FULL * 8, barEmpty = bars + K::BAR_EMPTY * 8, barChunk = bars + (K::BAR_CHUNK + t * K::NCH) * 8;
   auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
   for(int item = blockIdx.x; item < P.numItems; item += gridDim.x, itemCount++) {
-    if(!mbar_wait(bars + (BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
-    if(itemCount > 0 && !mbar_wait(bars + (BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
+    if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
+    if(itemCount > 0 && !mbar_wait(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
     tc_fence_after();
     for(int l = 0; l < P.numLayers; l++) {
       const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
       const uint32_t idesc = idesc_bf16_f32(128, N);
-      const uint32_t d = tmemBase + t * 256 + (P.layers[l].outSel ? 128 : 0);
+      const uint32_t d = tmemBase + t * (2 * K::MAXC) + (P.layers[l].outSel ? K::MAXC : 0);
       const uint32_t bStep = 2 * N;                    // one K-step of weights = N*32 bytes
       const uint32_t bLbo = (uint32_t)N << 16;         // LBO = N*16 bytes
       uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
@@ -401,7 +418,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
           for(int dy = 0; dy < 3; dy++) {
             if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
             tc_fence_after();
-            const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+            const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
             const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
             if(leader) {
               umma_bf16(d, desc(aLoR), desc(bLo), idesc, accum);
@@ -411,7 +428,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
             }
             __syncwarp();
             accum = 1u;
-            if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+            if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
           }
         }
       } else {
@@ -419,7 +436,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
         const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
         for(int s = 0; s < nst; s++) {
           if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
-          const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
+          const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
           const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
           for(int kk = 0; kk < ks; kk++) {
             const int cc = s * KSTEPS_PER_STAGE + kk;
@@ -435,149 +452,46 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
           }
           if(leader) umma_commit(barEmpty + slot * 8);
           __syncwarp();
-          if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+          if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
         }
       }
       if(leader) {
-        umma_commit(bars + (BAR_ACC + t) * 8);
-        if(l == P.numLayers - 1) umma_commit(bars + (BAR_ACTFREE + t) * 8);
+        umma_commit(bars + (K::BAR_ACC + t) * 8);
+        if(l == P.numLayers - 1) umma_commit(bars + (K::BAR_ACTFREE + t) * 8);
       }
       __syncwarp();
     }
   }
 }
 
-// Weight-stationary issuer: ONE warp drives both tiles.  Every weight K-step is latched in a collector
-// buffer by the MMA of tile 0 (collector::bN::fill) and re-used by the MMA of tile 1 (::lastuse), so the B
-// operand is read from shared memory once per pair: operand traffic drops from 128 to 96 B/clk/SM, under the
-// 128 B/clk shared-memory limit that caps plain 128x128x16 SS MMAs.  Layers whose N is not 64/128 (the
-// 96-wide head conv) fall back to plain MMAs.
-__device__ __forceinline__ void mmaIssuerWs(const TrunkParams& P, const uint32_t sbase, const uint32_t bars, const uint32_t tmemBase,
-                                            volatile int* abortFlag) {
-  uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
-  const bool leader = elect_one();
-  const uint32_t descHi = (128u >> 4) | (1u << 14);
-  const uint32_t aLo0 = (((sbase + OFF_ACT + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
-  const uint32_t aTile = ACT_BYTES >> 4;
-  const uint32_t ringLo0 = ((sbase + OFF_RING) & 0x3FFFFu) >> 4;
-  const uint32_t barFull = bars + BAR_FULL * 8, barEmpty = bars + BAR_EMPTY * 8, barChunk = bars + BAR_CHUNK * 8;
-  auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
-  for(int item = blockIdx.x; item < P.numItems; item += gridDim.x, itemCount++) {
-    for(int t = 0; t < 2; t++) {
-      if(!mbar_wait(bars + (BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
-      if(itemCount > 0 && !mbar_wait(bars + (BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
-    }
-    tc_fence_after();
-    for(int l = 0; l < P.numLayers; l++) {
-      const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
-      const uint32_t idesc = idesc_bf16_f32(128, N);
-      const uint32_t d0 = tmemBase + (P.layers[l].outSel ? 128 : 0), d1 = d0 + 256;
-      const uint32_t bStep = 2 * N, bLbo = (uint32_t)N << 16;
-      uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
-      const bool ws = (N == 128 || N == 64);
-      if(ntaps == 9) {
-        const int nchunks = nk / 9;
-        for(int cc = 0; cc < nchunks; cc++) {
-          if(l > 0) {
-            const uint32_t b0 = 1u << cc, b1 = 1u << (8 + cc);
-            if(!mbar_wait(barChunk + cc * 8, (chunkPhase & b0) ? 1 : 0, abortFlag, 24)) return;
-            if(!mbar_wait(barChunk + (8 + cc) * 8, (chunkPhase & b1) ? 1 : 0, abortFlag, 25)) return;
-            chunkPhase ^= (b0 | b1);
-          }
-          const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
-#pragma unroll
-          for(int dy = 0; dy < 3; dy++) {
-            if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
-            tc_fence_after();
-            const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
-            const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
-            if(leader) {
-              if(ws) {
-                umma_bf16_ws<0, 0>(d0, desc(aLoR), desc(bLo), idesc, accum);
-                umma_bf16_ws<0, 2>(d1, desc(aLoR + aTile), desc(bLo), idesc, accum);
-                umma_bf16_ws<1, 0>(d0, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
-                umma_bf16_ws<1, 2>(d1, desc(aLoR + 1 + aTile), desc(bLo + bStep), idesc, 1u);
-                umma_bf16_ws<2, 0>(d0, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
-                umma_bf16_ws<2, 2>(d1, desc(aLoR + 2 + aTile), desc(bLo + 2 * bStep), idesc, 1u);
-              } else {
-                umma_bf16(d0, desc(aLoR), desc(bLo), idesc, accum);
-                umma_bf16(d1, desc(aLoR + aTile), desc(bLo), idesc, accum);
-                umma_bf16(d0, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
-                umma_bf16(d1, desc(aLoR + 1 + aTile), desc(bLo + bStep), idesc, 1u);
-                umma_bf16(d0, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
-                umma_bf16(d1, desc(aLoR + 2 + aTile), desc(bLo + 2 * bStep), idesc, 1u);
-              }
-              umma_commit(barEmpty + slot * 8);
-            }
-            __syncwarp();
-            accum = 1u;
-            if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
-          }
-        }
-      } else {
-        const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
-        for(int s = 0; s < nst; s++) {
-          if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
-          const uint32_t bLo = (ringLo0 + slot * (STAGE_BYTES >> 4)) | bLbo;
-          const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
-          for(int kk = 0; kk < ks; kk++) {
-            const int cc = s * KSTEPS_PER_STAGE + kk;
-            if(l > 0) {
-              const uint32_t b0 = 1u << cc, b1 = 1u << (8 + cc);
-              if(!mbar_wait(barChunk + cc * 8, (chunkPhase & b0) ? 1 : 0, abortFlag, 24)) return;
-              if(!mbar_wait(barChunk + (8 + cc) * 8, (chunkPhase & b1) ? 1 : 0, abortFlag, 25)) return;
-              chunkPhase ^= (b0 | b1);
-            }
-            tc_fence_after();
-            if(leader) {
-              const uint32_t aLo = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
-              umma_bf16(d0, desc(aLo), desc(bLo + kk * bStep), idesc, accum);
-              umma_bf16(d1, desc(aLo + aTile), desc(bLo + kk * bStep), idesc, accum);
-            }
-            __syncwarp();
-            accum = 1u;
-          }
-          if(leader) umma_commit(barEmpty + slot * 8);
-          __syncwarp();
-          if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
-        }
-      }
-      if(leader) {
-        umma_commit(bars + (BAR_ACC + 0) * 8);
-        umma_commit(bars + (BAR_ACC + 1) * 8);
-        if(l == P.numLayers - 1) { umma_commit(bars + (BAR_ACTFREE + 0) * 8); umma_commit(bars + (BAR_ACTFREE + 1) * 8); }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-__global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkParams P) {
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams P) {
+  constexpr int NT = K::NT;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + OFF_BAR;
+  const uint32_t bars = sbase + K::OFF_BAR;
   volatile int* abortFlag = P.abortFlag;
-  uint8_t* sSym = smem + OFF_SYM;
+  uint8_t* sSym = smem + K::OFF_SYM;
 
   // ---- one-time setup ----
-  for(int i = threadIdx.x; i < 2 * ACT_BYTES / 16; i += TRUNK_THREADS) reinterpret_cast<uint4*>(smem + OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
-  for(int i = threadIdx.x; i < 8 * P.HW; i += TRUNK_THREADS) sSym[i] = P.dstOfSrcRev[i];
+  for(int i = threadIdx.x; i < NT * K::ACT_BYTES / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
+  for(int i = threadIdx.x; i < 8 * P.HW; i += K::THREADS) sSym[i] = P.dstOfSrcRev[i];
   if(threadIdx.x == 0) {
-    for(int i = 0; i < NSTAGES; i++) { mbar_init(bars + (BAR_FULL + i) * 8, 1); mbar_init(bars + (BAR_EMPTY + i) * 8, P.useWs ? 1 : 2); }   // every MMA issuer releases a slot
-    for(int t = 0; t < 2; t++) {
-      mbar_init(bars + (BAR_ACC + t) * 8, 1); mbar_init(bars + (BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (BAR_IN + t) * 8, 1);
-      mbar_init(bars + (BAR_HEAD + t) * 8, 128);
-      for(int c = 0; c < 8; c++) mbar_init(bars + (BAR_CHUNK + t * 8 + c) * 8, 128);
+    for(int i = 0; i < K::NSTAGES; i++) { mbar_init(bars + (K::BAR_FULL + i) * 8, 1); mbar_init(bars + (K::BAR_EMPTY + i) * 8, NT); }   // every MMA issuer releases a slot
+    for(int t = 0; t < NT; t++) {
+      mbar_init(bars + (K::BAR_ACC + t) * 8, 1); mbar_init(bars + (K::BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (K::BAR_IN + t) * 8, 1);
+      mbar_init(bars + (K::BAR_HEAD + t) * 8, 128);
+      for(int c = 0; c < K::NCH; c++) mbar_init(bars + (K::BAR_CHUNK + t * K::NCH + c) * 8, 128);
     }
     fence_mbar_init();
   }
   fence_proxy_async();
-  if(warp == 1) { tmem_alloc(sbase + OFF_TMEM, 512); tmem_relinquish(); }
+  if(warp == 1) { tmem_alloc(sbase + K::OFF_TMEM, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+  const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(smem + K::OFF_TMEM);
 
   if(warp == 0) {
     // =========================== TMA producer ===========================
@@ -585,13 +499,13 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
       uint32_t slot = 0, phase = 0, itemCount = 0;
       bool alive = true;
       for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x, itemCount++) {
-        for(int t = 0; t < 2 && alive; t++) {
-          if(itemCount > 0) alive = mbar_wait(bars + (BAR_ACTFREE + t) * 8, (itemCount - 1) & 1, abortFlag, 11);
+        for(int t = 0; t < NT && alive; t++) {
+          if(itemCount > 0) alive = mbar_wait(bars + (K::BAR_ACTFREE + t) * 8, (itemCount - 1) & 1, abortFlag, 11);
           if(!alive) break;
-          uint32_t bar = bars + (BAR_IN + t) * 8;
+          uint32_t bar = bars + (K::BAR_IN + t) * 8;
           mbar_arrive_expect_tx(bar, 2 * TILE_ROWS * 16);
-          const uint4* src = P.tiles + (size_t)(item * 2 + t) * 2 * TILE_ROWS;
-          uint32_t dst = sbase + OFF_ACT + t * ACT_BYTES + HALO_ROWS * 16;
+          const uint4* src = P.tiles + (size_t)(item * NT + t) * 2 * TILE_ROWS;
+          uint32_t dst = sbase + K::OFF_ACT + t * K::ACT_BYTES + HALO_ROWS * 16;
           bulk_g2s(dst, src, TILE_ROWS * 16, bar);
           bulk_g2s(dst + CHUNK_BYTES, src + TILE_ROWS, TILE_ROWS * 16, bar);
         }
@@ -602,22 +516,21 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
           for(int s = 0; s < nst; s++) {
             int ks = min(KSTEPS_PER_STAGE, L.nk - s * KSTEPS_PER_STAGE);
             uint32_t bytes = (uint32_t)ks * L.N * 32;
-            alive = mbar_wait(bars + (BAR_EMPTY + slot) * 8, phase ^ 1, abortFlag, 12);
+            alive = mbar_wait(bars + (K::BAR_EMPTY + slot) * 8, phase ^ 1, abortFlag, 12);
             if(!alive) break;
-            uint32_t bar = bars + (BAR_FULL + slot) * 8;
+            uint32_t bar = bars + (K::BAR_FULL + slot) * 8;
             mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(sbase + OFF_RING + slot * STAGE_BYTES, w, bytes, bar);
+            bulk_g2s(sbase + K::OFF_RING + slot * K::STAGE_BYTES, w, bytes, bar);
             w += bytes;
-            if(++slot == NSTAGES) { slot = 0; phase ^= 1; }
+            if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if(warp == 1 || warp == 2) {
+  } else if(warp >= 1 && warp <= NT) {
     // =========================== MMA issuers: one thread per tile ===========================
-    if(P.useWs) { if(warp == 1) mmaIssuerWs(P, sbase, bars, tmemBase, abortFlag); }
-    else mmaIssuer(P, warp - 1, sbase, bars, tmemBase, abortFlag);
-  } else if(warp == 3) {
+    mmaIssuer<K>(P, warp - 1, sbase, bars, tmemBase, abortFlag);
+  } else if(warp < 4) {
     // idle (keeps the epilogue warps aligned to TMEM lane quadrants: warp % 4 == quadrant)
   } else {
     // =========================== epilogue warps ===========================
@@ -632,14 +545,14 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
     c.valid = (y < P.H) && (x < P.W);
     c.cell = y * P.W + x;
     if(!c.valid) { c.b = 0; c.cell = 0; }
-    c.tmemLane = tmemBase + ((uint32_t)(q * 32) << 16) + c.t * 256;
-    c.act = smem + OFF_ACT + c.t * ACT_BYTES;
-    c.barChunk = bars + (BAR_CHUNK + c.t * 8) * 8;
-    c.scr = reinterpret_cast<float*>(smem + OFF_SCR) + c.t * 128 * SCR_STRIDE;
-    c.poolA = reinterpret_cast<float*>(smem + OFF_POOLA) + c.t * MAX_NB * 96;
-    c.poolB = reinterpret_cast<float*>(smem + OFF_POOLB) + c.t * MAX_NB * 96;
-    c.biasBuf = reinterpret_cast<float*>(smem + OFF_BIAS) + c.t * MAX_NB * 96;
-    c.v2buf = reinterpret_cast<float*>(smem + OFF_V2) + c.t * MAX_NB * MAX_V2;
+    c.tmemLane = tmemBase + ((uint32_t)(q * 32) << 16) + c.t * (2 * K::MAXC);
+    c.act = smem + K::OFF_ACT + c.t * K::ACT_BYTES;
+    c.barChunk = bars + (K::BAR_CHUNK + c.t * K::NCH) * 8;
+    c.scr = reinterpret_cast<float*>(smem + K::OFF_SCR) + c.t * 128 * SCR_STRIDE;
+    c.poolA = reinterpret_cast<float*>(smem + K::OFF_POOLA) + c.t * MAX_NB * K::POOLW;
+    c.poolB = reinterpret_cast<float*>(smem + K::OFF_POOLB) + c.t * MAX_NB * K::POOLW;
+    c.biasBuf = reinterpret_cast<float*>(smem + K::OFF_BIAS) + c.t * MAX_NB * K::MAXC;
+    c.v2buf = reinterpret_cast<float*>(smem + K::OFF_V2) + c.t * MAX_NB * MAX_V2;
     uint32_t layerCount = 0;
     bool alive = true;
     for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x) {
@@ -647,21 +560,23 @@ __global__ void __launch_bounds__(TRUNK_THREADS, 1) trunk_kernel(const TrunkPara
         const LayerDesc L = P.layers[l];
         {
           // stage this layer's folded BN (the one applied to its output) while its MMAs are still running
-          float* par = reinterpret_cast<float*>(smem + OFF_PAR) + (c.t * 2 + (layerCount & 1)) * 2 * MAX_C;
-          if(L.epi != EPI_HEAD && c.e < L.epiC) {
+          float* par = reinterpret_cast<float*>(smem + K::OFF_PAR) + (c.t * 2 + (layerCount & 1)) * 2 * K::MAXC;
+          if(L.epi != EPI_HEAD) {
             const float* sc = P.params + L.pOff + (L.epi == EPI_GPOOL ? 2 * L.gpoolC + 3 * L.gpoolC * L.epiC : 0);
-            par[c.e] = __ldg(sc + c.e);
-            par[MAX_C + c.e] = __ldg(sc + L.epiC + c.e);
+            for(int i = c.e; i < L.epiC; i += 128) {
+              par[i] = __ldg(sc + i);
+              par[K::MAXC + i] = __ldg(sc + L.epiC + i);
+            }
           }
           c.par = par;
           named_bar_sync(1 + c.t, 128);
         }
-        alive = mbar_wait(bars + (BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
+        alive = mbar_wait(bars + (K::BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
         if(!alive) break;
         tc_fence_after();
-        if(L.epi == EPI_BN) epilogueBN(P, L, c);
-        else if(L.epi == EPI_GPOOL) epilogueGPool(P, L, c);
-        else epilogueHead(P, L, c, item * 2 + c.t, bars + (BAR_HEAD + c.t) * 8, sSym);
+        if(L.epi == EPI_BN) epilogueBN<K>(P, L, c);
+        else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
+        else epilogueHead<K>(P, L, c, item * NT + c.t, bars + (K::BAR_HEAD + c.t) * 8, sSym);
       }
     }
   }
@@ -828,7 +743,10 @@ std::vector<float> cat(std::initializer_list<const std::vector<float>*> parts) {
 int buildTrunkProgram(kc_model* m) {
   auto unsupported = [&](const std::string& why) { m->trunk = nullptr; m->trunkUnsupportedWhy = why; return 0; };
   const int C = m->trunkC;
-  if(C % 16 != 0 || C > MAX_C) return unsupported("trunk channels must be a multiple of 16 and <= 128 for the tcgen05 kernel");
+  if(C % 16 != 0 || C > Cfg192::MAXC) return unsupported("trunk channels must be a multiple of 16 and <= 192 for the tcgen05 kernel");
+  // <= 128 channels: two activation tiles per CTA; up to 192 (b15c192): one tile per CTA (TMEM budget)
+  const int cfg = C <= Cfg128::MAXC ? 0 : 1;
+  const int maxC = cfg == 0 ? Cfg128::MAXC : Cfg192::MAXC, maxG = cfg == 0 ? Cfg128::MAXG : Cfg192::MAXG;
   if(m->initialConv.ky != 3 || m->initialConv.kx != 3) return unsupported("initial conv must be 3x3");
   if(m->p1Conv.oc != HEADC || m->g1Conv.oc != HEADC || m->v1Conv.oc != HEADC) return unsupported("head convs must have 32 channels");
   if(m->p1Conv.ky != 1 || m->g1Conv.ky != 1 || m->v1Conv.ky != 1 || m->p2Conv.ky != 1 || m->vOwnershipConv.ky != 1)
@@ -839,14 +757,15 @@ int buildTrunkProgram(kc_model* m) {
   for(const BlockW& b : m->blocks) {
     if(b.preBN.act != 1 || b.midBN.act != 1 || (b.kind == 2 && b.gpoolBN.act != 1)) return unsupported("only ReLU activations are implemented in the tcgen05 kernel");
     if(b.regularConv.ky != 3 || b.regularConv.kx != 3 || b.finalConv.ky != 3 || b.finalConv.kx != 3) return unsupported("block convs must be 3x3");
-    if(b.kind == 0 && (b.regularConv.oc % 16 != 0 || b.regularConv.oc > MAX_C)) return unsupported("mid channels must be a multiple of 16 and <= 128");
+    if(b.kind == 0 && (b.regularConv.oc % 16 != 0 || b.regularConv.oc > maxC)) return unsupported("mid channels must be a multiple of 16 and within the trunk width class");
     if(b.kind == 2) {
-      if(b.gpoolConv.ky != 3 || (b.gpoolConv.oc != 32 && b.gpoolConv.oc != 16)) return unsupported("gpool conv must be 3x3 with 16 or 32 channels");
-      if(b.regularConv.oc % 16 != 0 || b.regularConv.oc > 96 || b.regularConv.oc + b.gpoolConv.oc > MAX_C) return unsupported("gpool block: regular channels must be a multiple of 16, <= 96");
+      if(b.gpoolConv.ky != 3 || b.gpoolConv.oc % 16 != 0 || b.gpoolConv.oc > maxG) return unsupported("gpool conv must be 3x3 with a multiple of 16 channels, <= 32 (trunk <= 128) or <= 64 (trunk <= 192)");
+      if(b.regularConv.oc % 16 != 0 || b.regularConv.oc + b.gpoolConv.oc > maxC) return unsupported("gpool block: regular + gpool channels must fit the trunk width class");
     }
   }
   if(2 * m->blocks.size() + 2 > (size_t)MAX_LAYERS) return unsupported("too many blocks for the tcgen05 kernel's layer table");
   TrunkProgram* T = new TrunkProgram();
+  T->cfg = cfg;
   Packer pk;
   double macs = 0;
   auto bnOf = [&](size_t blockIdx) -> const BNW& { return blockIdx < m->blocks.size() ? m->blocks[blockIdx].preBN : m->trunkTipBN; };
@@ -939,7 +858,8 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaMemset(h->d_tiles, 0, bytes));
   KC_CUDA(cudaMalloc(&h->d_abort, 4));
   KC_CUDA(cudaMemset(h->d_abort, 0, 4));
-  KC_CUDA(cudaFuncSetAttribute(trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRUNK_SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
   return 0;
 }
 void freeTrunkBuffers(kc_handle* h) {
@@ -976,7 +896,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   for(int i = 0; i < P.numLayers; i++) P.layers[i] = T->layers[i];
   P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride;
   int numTiles = (n + P.NB - 1) / P.NB;
-  P.numItems = (numTiles + 1) / 2;
+  const int NT = T->cfg == 0 ? Cfg128::NT : Cfg192::NT;
+  P.numItems = (numTiles + NT - 1) / NT;
   P.n = n;
   P.tiles = (const uint4*)h->d_tiles + (size_t)(rowOffset / P.NB) * 2 * TILE_ROWS;
   P.sym = sym_dev ? sym_dev + rowOffset : nullptr; P.dstOfSrcRev = h->d_dstOfSrcRev;
@@ -988,7 +909,6 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.poolScale2 = (sq - 14.0f) * (sq - 14.0f) * 0.01f - 0.1f;
   P.invHW = 1.0f / (float)P.HW;
   P.v2C = T->v2C;
-  { const char* e = getenv("KC_TRUNK_WS"); P.useWs = e ? atoi(e) : 0; }   // measured slower than plain MMAs (profiles/), kept as an option
   int grid = std::min(P.numItems, h->ctx->smCount);
   if((int)h->evPool.size() < h->evUsed + 2 && h->evPool.size() < 4096) {
     cudaEvent_t a, b;
@@ -997,7 +917,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   }
   bool timed = (int)h->evPool.size() >= h->evUsed + 2;
   if(timed) cudaEventRecord(h->evPool[h->evUsed], st);
-  trunk_kernel<<<grid, TRUNK_THREADS, TRUNK_SMEM, st>>>(P);
+  if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
+  else trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);
   if(timed) { cudaEventRecord(h->evPool[h->evUsed + 1], st); h->evUsed += 2; }
   h->launches++;
   KC_CUDA(cudaGetLastError());

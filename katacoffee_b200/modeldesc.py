@@ -26,6 +26,8 @@ CONFIGS = {
     "b6c96": (96, 96, 64, 32, 6, (2, 4), 64),    # modelconfigs.py b6c96: gpool blocks 3 and 5 (1-based)
     "b10c128": (128, 128, 96, 32, 10, (4, 7), 80),
     "b15c192": (192, 192, 128, 64, 15, (6, 11), 96),
+    "b1c192g": (192, 192, 128, 64, 1, (0,), 96),   # shallow 192-wide net: pointwise check of the one-tile-per-CTA kernel
+    "b2c256": (256, 256, 192, 64, 2, (1,), 96),    # wider than the tensor-core kernel supports: must be rejected, not emulated
 }
 HEAD_C = 32
 

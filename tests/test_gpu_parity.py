@@ -303,7 +303,8 @@ def check_bf16_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym
 
 
 @pytest.mark.parametrize("net,W,H,n,calibrate", [("b2c32", 5, 5, 37, "rms"), ("b6c96", 5, 5, 200, "rms"), ("b10c128", 5, 5, 300, "rms"),
-                                                 ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none")])
+                                                 ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none"),
+                                                 ("b15c192", 6, 6, 61, "rms"), ("b15c192", 5, 5, 45, "rms")])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
     """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward."""
@@ -371,7 +372,7 @@ def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
         x.close()
 
 
-@pytest.mark.parametrize("net", ["b0c32", "b1c32", "b1c32g"])
+@pytest.mark.parametrize("net", ["b0c32", "b1c32", "b1c32g", "b1c192g"])
 @pytest.mark.parametrize("W,H", [(5, 5), (6, 6)])
 def test_bf16_shallow_pointwise(ctx, oracle, net, W, H):
     """Kernel exactness: on nets of depth 0-1 the tcgen05 path equals the bf16-emulating oracle
@@ -535,21 +536,37 @@ def test_postprocess_matches_oracle(ctx, oracle, mode):
         x.close()
 
 
-def test_b15c192_6x6_check_path_and_bf16_rejection(ctx, oracle):
-    """BASELINE config 5 (6x6 k=4, b15c192): the fp32 check path matches the oracle; the tcgen05 path does not
-    support 192 trunk channels yet and must say so instead of falling back to anything."""
+def test_b15c192_6x6_device_resident_and_unsupported_width_rejected(ctx, oracle):
+    """BASELINE config 5 (6x6 k=4, b15c192): games -> bf16 planes -> one-tile-per-CTA tcgen05 kernel, checked against the
+    fp32 oracle with the reduced-precision bars; a trunk wider than the tensor-core kernel supports must be refused on
+    the bf16 path (no emulation, no fallback) while the fp32 check path still runs it."""
     from katacoffee_b200 import backend, modeldesc, capi
     W = H = 6
-    n = 24
+    G = 64
     model = modeldesc.Model("b15c192", seed=6)
     om = oracle.Model(model)
-    planes, glob, _ = position_batch_full(oracle, W, H, 4, 9, n)
-    sym = (np.arange(n) % 8).astype(np.int8)
     lm = backend.LoadedModel(ctx, model)
-    h = backend.createComputeHandle(ctx, lm, n, W, H, useFP32Check=True)
-    got = backend.getOutput(h, planes, glob, sym)
-    ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
-    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_FP32
+    h = backend.createComputeHandle(ctx, lm, G, W, H)
+    assert h.isUsingBF16()
+    games = backend.Games(ctx, G, W, H, 4)
+    games.reset(seed=9)
+    for _ in range(6):
+        games.step()
+    planes, glob = games.features()
+    games.eval(h)
+    got = h.readOutputs(G)
+    ref = om.forward(planes, glob, W, H, mode=0, threads=8)
+    for a, b in zip(got, ref):
+        assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), np.abs(a - b).max()
+    assert np.abs(got[1] - ref[1]).max() < 2e-2
+    games.close(); h.close(); lm.close()
+    wide = modeldesc.Model("b2c256", seed=2)
+    lm2 = backend.LoadedModel(ctx, wide)
     with pytest.raises(capi.KCError, match="trunk channels"):
-        backend.createComputeHandle(ctx, lm, n, W, H)
-    h.close(); lm.close()
+        backend.createComputeHandle(ctx, lm2, 8, 5, 5)
+    h2 = backend.createComputeHandle(ctx, lm2, 8, 5, 5, useFP32Check=True)
+    planes5, glob5, _ = position_batch_full(oracle, 5, 5, 4, 9, 8)
+    got2 = backend.getOutput(h2, planes5, glob5, None)
+    ref2 = oracle.Model(wide).forward(planes5, glob5, 5, 5, mode=0, threads=8)
+    assert max(np.abs(a - b).max() for a, b in zip(got2, ref2)) < TOL_FP32
+    h2.close(); lm2.close()
