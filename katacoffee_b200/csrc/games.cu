@@ -27,8 +27,12 @@
 
 namespace kc {
 
-constexpr int GPB = 32;        // games per CTA: one warp runs the rules, all four warps expand the planes
-constexpr int THREADS = 128;
+// CTA shapes.  FEAT 0/1/2 (no planes, fp32 NCHW, fp32 NHWC): 64 threads = 64 games, every thread runs the rules of
+// its own game; the fp32 NCHW fast path is warp-autonomous (a warp expands the 32 games it stepped, no CTA barrier),
+// so warps drift apart and the plane stores of one overlap the bitboard arithmetic of another.
+// FEAT 3 (bf16 trunk tiles): 128 threads, NB*8 <= 32 games = whole trunk tiles per CTA.
+constexpr int TB_PLAIN = 64;
+constexpr int TB_TILES = 128;
 
 struct Geom {
   int W, H, K, HW, stride;   // stride = W + 1
@@ -295,15 +299,17 @@ struct FeatOut {
 };
 
 template <bool DO_STEP, int FEAT, class D>
-__global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
+__global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
                                                         int useMoves, const uint64_t* __restrict__ zob,
                                                         StepOut so, FeatOut fo) {
+  constexpr int THREADS = FEAT == 3 ? TB_TILES : TB_PLAIN;
+  constexpr int GPB = FEAT == 3 ? 32 : TB_PLAIN;       // most games a CTA can hold
   __shared__ uint64_t sPlanes[15][GPB + 1];
   __shared__ uint8_t sSrcPad[8][52];   // [symmetry][dst cell] -> padded bit index of the source cell
   __shared__ int8_t sSym[GPB];
-  // FEAT 1 without symmetry: the CTA's whole output as one bit string (bit e = output float e), so the
+  // FEAT 1 without symmetry: a warp's whole output as one bit string (bit e = output float e of its 32 games), so the
   // expansion is one shared load + one 128-bit store per four floats
-  __shared__ uint32_t sBits[GPB * 15 * 49 / 32 + 4];
+  __shared__ uint32_t sBits[FEAT == 1 ? GPB * 15 * 49 / 32 + 4 : 1];
   const bool fastNCHW = (FEAT == 1) && fo.symmetry == nullptr;
   const D dm(g);
   using BB = typename D::BB;
@@ -313,7 +319,12 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
   const int gi = gBase + t;
   const bool active = t < gpb && gi < g.numGames;
 
-  if(FEAT != 0) {
+  if(FEAT == 1 && fastNCHW) {
+    // each warp clears the bit string of its own 32 games (32*E bits = E words, word-aligned)
+    const int E = 15 * dm.HW();
+    for(int i = (t & 31); i < E; i += 32) sBits[(t >> 5) * E + i] = 0;
+    __syncwarp();
+  } else if(FEAT != 0) {
     // symmetry tables: dst[sym(h,w)] = src[h,w] (nninputs.cpp:252-335), built per CTA (<= 8*49 entries)
     for(int i = t; i < 8 * dm.HW(); i += THREADS) {
       int sym = i / dm.HW(), cell = i % dm.HW();
@@ -328,10 +339,6 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
       sSrcPad[sym][dst] = (uint8_t)(cell + cell / dm.W());
     }
     if(t < gpb) sSym[t] = (active && fo.symmetry) ? fo.symmetry[gi] : 0;
-    if(fastNCHW) {
-      for(int i = t; i < GPB * 15 * 49 / 32 + 4; i += THREADS) sBits[i] = 0;
-      __syncthreads();
-    }
   }
 
   unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
@@ -430,22 +437,32 @@ __global__ void __launch_bounds__(THREADS) games_kernel(const Geom g, State st, 
     }
   }
   if(FEAT == 0) return;
-  __syncthreads();
-
   const int ng = min(gpb, g.numGames - gBase);
-  if(ng <= 0) return;
-  if(fastNCHW) {
-    const int total = ng * 15 * dm.HW();
-    float* out = fo.planes + (size_t)gBase * 15 * dm.HW();
+  if(FEAT == 1 && fastNCHW) {
+    // warp-autonomous expansion: no CTA barrier, the warp's own 32 games only
+    __syncwarp();
+    const int w = t >> 5, lane = t & 31;
+    const int ngw = min(32, ng - w * 32);
+    if(ngw <= 0) return;
+    const int E = 15 * dm.HW();
+    const int total = ngw * E;
+    const uint32_t* bits = sBits + w * E;
+    float* out = fo.planes + ((size_t)gBase + w * 32) * E;
     float4* out4 = reinterpret_cast<float4*>(out);
     const int nvec = total >> 2;
-    for(int j = t; j < nvec; j += THREADS) {
-      uint32_t b = sBits[j >> 3] >> ((j & 7) * 4);
+#pragma unroll 4
+    for(int j = lane; j < nvec; j += 32) {
+      uint32_t b = bits[j >> 3] >> ((j & 7) * 4);
       float4 v = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
       __stcs(&out4[j], v);
     }
-    for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = (float)((sBits[e >> 5] >> (e & 31)) & 1u);
-    if(fo.global && t < ng) fo.global[gBase + t] = (float)dm.K();
+    for(int e = (nvec << 2) + lane; e < total; e += 32) out[e] = (float)((bits[e >> 5] >> (e & 31)) & 1u);
+    if(fo.global && lane < ngw) fo.global[gBase + w * 32 + lane] = (float)dm.K();
+    return;
+  }
+  __syncthreads();
+  if(ng <= 0) return;
+  if(false) {
   } else if(FEAT == 1 || FEAT == 2) {
     const int E = 15 * dm.HW();
     const uint32_t magicE = (uint32_t)((0x100000000ULL + E - 1) / E);
@@ -523,6 +540,9 @@ struct kc_games {
   float lastKernelMs = 0.f;
   std::vector<cudaEvent_t> evPool;   // one (start, stop) pair per ply of kc_games_run_timed
   void* d_flush = nullptr; size_t flushBytes = 0;
+  // rules+features-only timing: consecutive plies write their planes to different ring slots (4 x G x 15*HW fp32 > L2),
+  // so a ply never overwrites lines of the previous one that are still dirty in L2
+  float* d_planesRing[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -531,15 +551,15 @@ using namespace kc;
 template <bool DO_STEP, class D>
 void launchGamesD(kc_games* G, int feat, int useMoves, const StepOut& so, const FeatOut& fo, int blocks) {
   switch(feat) {
-    case 0: games_kernel<DO_STEP, 0, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    case 1: games_kernel<DO_STEP, 1, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    case 2: games_kernel<DO_STEP, 2, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    default: games_kernel<DO_STEP, 3, D><<<blocks, THREADS, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 0: games_kernel<DO_STEP, 0, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 1: games_kernel<DO_STEP, 1, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 2: games_kernel<DO_STEP, 2, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    default: games_kernel<DO_STEP, 3, D><<<blocks, TB_TILES, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
   }
 }
 template <bool DO_STEP>
 void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
-  int gpb = feat == 3 ? G->geom.NB * 8 : GPB;   // FEAT 3: whole trunk tiles per CTA
+  int gpb = feat == 3 ? G->geom.NB * 8 : TB_PLAIN;   // FEAT 3: whole trunk tiles per CTA
   fo.gamesPerBlock = gpb;
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
   const Geom& g = G->geom;
@@ -625,6 +645,7 @@ int kc_games_destroy(kc_games* G) {
   cudaFree(G->st.gameId); cudaFree(G->st.misc); cudaFree(G->d_moves); cudaFree(G->d_legal); cudaFree(G->d_status);
   cudaFree(G->d_sitHash); cudaFree(G->d_played); cudaFree(G->d_stats); cudaFree(G->d_planes); cudaFree(G->d_global);
   cudaFree(G->d_sym); cudaFree(G->d_flush);
+  for(float* p : G->d_planesRing) cudaFree(p);
   for(cudaEvent_t e : G->evPool) cudaEventDestroy(e);
   cudaEventDestroy(G->ev0); cudaEventDestroy(G->ev1);
   cudaStreamDestroy(G->stream);
@@ -776,14 +797,26 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     G->evPool.push_back(e);
   }
   KC_CUDA(cudaMemsetAsync(G->d_stats, 0, 64, G->stream));
+  // Rules+features only: plies are timed in groups of RING launches between one event pair (a ~25 us kernel is too short
+  // for a per-launch event pair: the pair itself costs a few us), each launch of a group writing its planes to a
+  // different ring slot.  With a net: one event pair per ply.
+  constexpr int RING = 4;
+  const int grp = h ? 1 : RING;
+  if(!h && flushL2Bytes)
+    for(int i = 0; i < RING - 1; i++)
+      if(!G->d_planesRing[i]) KC_CUDA(cudaMalloc(&G->d_planesRing[i], (size_t)g.numGames * 15 * g.HW * 4));
+  int nGroups = 0;
   for(int p = 0; p < plies; p++) {
-    // optional L2 flush between plies, outside the timed window of each ply
-    if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
-    KC_CUDA(cudaEventRecord(G->evPool[2 * p], G->stream));
+    // optional L2 flush between timed windows, outside them
+    if(p % grp == 0) {
+      if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
+      KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups], G->stream));
+    }
     FeatOut fo{};
     StepOut so = stepOutOf(G, true);
     if(!h) {
-      fo.planes = G->d_planes; fo.global = G->d_global;
+      const int slot = flushL2Bytes ? p % RING : 0;
+      fo.planes = slot == 0 ? G->d_planes : G->d_planesRing[slot - 1]; fo.global = G->d_global;
       launchGames<true>(G, 1, 0, so, fo);
     } else if(kc::handleIsBf16(h)) {
       fo.tiles = (uint4*)kc::handleInputTiles(h);
@@ -794,14 +827,14 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       launchGames<true>(G, 2, 0, so, fo);
       if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
     }
-    KC_CUDA(cudaEventRecord(G->evPool[2 * p + 1], G->stream));
+    if(p % grp == grp - 1 || p == plies - 1) { KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups + 1], G->stream)); nGroups++; }
   }
   KC_CUDA(cudaGetLastError());
   unsigned long long hs[8];
   KC_CUDA(cudaMemcpyAsync(hs, G->d_stats, 64, cudaMemcpyDeviceToHost, G->stream));
   KC_CUDA(cudaStreamSynchronize(G->stream));
   float msSum = 0.f;
-  for(int p = 0; p < plies; p++) {
+  for(int p = 0; p < nGroups; p++) {
     float ms = 0.f;
     KC_CUDA(cudaEventElapsedTime(&ms, G->evPool[2 * p], G->evPool[2 * p + 1]));
     msSum += ms;
