@@ -210,6 +210,49 @@ int64_t kc_games_launch_count(const kc_games* g);
 /* Average device time in ms per ply of the rules+features kernel in the last kc_games_run. */
 float kc_games_last_kernel_ms(const kc_games* g);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched tree search: the caller of the leaf-evaluation path.  G games, one PUCT tree each,
+ * advanced in lock step: per iteration every game descends to one leaf, the G leaves are evaluated as one batch
+ * (rules -> V1 planes -> net -> NNEvaluator post-processing, all on the device) and backed up.
+ * Reference: Search::playoutDescend (cpp/search/search.cpp:935-1160), selectBestChildToDescend and
+ * getExploreSelectionValue (cpp/search/searchexplorehelpers.cpp:9-45, 323-451), addLeafValue / recomputeNodeStats
+ * (cpp/search/searchupdatehelpers.cpp:12-76, 151-326), with SearchParams() defaults (cpp/search/searchparams.cpp:8-90)
+ * and valueWeightExponent 0 (see the header of csrc/search.cu for the exact canonical semantics).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kc_search kc_search;
+typedef struct {
+  int32_t maxVisits;            /* SearchParams::maxVisits: visits of the root per move (incl. its own evaluation) */
+  int32_t temperaturePlies;     /* plies played in proportion to visits (chosenMoveTemperature 1), afterwards the most visited move */
+  int32_t autoRefill;           /* restart finished games with fresh ids before the next search */
+  int32_t pad_;
+  double cpuctExploration;      /* SearchParams::cpuctExploration (1.0) */
+  double fpuReductionMax;       /* SearchParams::fpuReductionMax (0.2) */
+  double rootFpuReductionMax;   /* SearchParams::rootFpuReductionMax (0.2) */
+} kc_search_params;
+typedef struct {
+  uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;
+  uint64_t batchRows;           /* rows sent through the evaluator (numGames per iteration) */
+} kc_search_stats;
+/* handle == NULL selects the deterministic integer-hash evaluator (exact fp32 policy/value derived from the sit-hash),
+ * which exists so that the search logic can be compared bit for bit with the CPU oracle; with a handle the leaves go
+ * through kc_games_eval + kc_games_postprocess' kernels.  numGames <= the handle's maxBatch. */
+int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSize, int ySize, int winLen,
+                     const kc_search_params* params, kc_search** out);
+int kc_search_destroy(kc_search* s);
+/* The games being played (owned by the search): kc_games_load / kc_games_step work on it between searches. */
+kc_games* kc_search_games(kc_search* s);
+int kc_search_reset(kc_search* s, uint64_t seed, uint64_t firstGameId);
+/* One search (maxVisits iterations) from the current positions without playing a move. */
+int kc_search_run_visits(kc_search* s);
+/* Root statistics after kc_search_run_visits: rootVisits [G], rootUtilitySum [G] (white-positive), and per policy
+ * index [G][4*H*W]: edgeVisits, edgeUtilitySum, the root's policy (-1 illegal), creation order (255 = no child). */
+int kc_search_read_root(kc_search* s, int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits,
+                        double* edgeUtilitySum, float* policy, uint8_t* order);
+/* `moves` times: [refill] -> search -> choose and play the move.  chosenLast [G] receives the last moves played
+ * (policy index, -1 none); *msTotal the device time of the whole call. */
+int kc_search_play(kc_search* s, int moves, int16_t* chosenLast, kc_search_stats* statsAccum, float* msTotal);
+int64_t kc_search_launch_count(const kc_search* s);
+
 #ifdef __cplusplus
 }
 #endif

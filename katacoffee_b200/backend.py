@@ -233,6 +233,57 @@ class Games:
             self._p = C.c_void_p()
 
 
+class Search:
+    """G concurrent PUCT tree searches in lock step on the device (the reference's Search, batched over games).
+    handle=None selects the integer-hash evaluator used to test the search logic exactly against the oracle."""
+
+    def __init__(self, ctx, handle, numGames, xSize=5, ySize=5, winLen=4, maxVisits=800, temperaturePlies=0, autoRefill=False,
+                 cpuctExploration=1.0, fpuReductionMax=0.2, rootFpuReductionMax=0.2):
+        self.ctx, self.G, self.W, self.H = ctx, numGames, xSize, ySize
+        self.P = 4 * xSize * ySize
+        self.params = capi.SearchParams(maxVisits, temperaturePlies, int(autoRefill), 0, cpuctExploration, fpuReductionMax, rootFpuReductionMax)
+        self._p = C.c_void_p()
+        check(lib().kc_search_create(ctx._p, handle._p if handle is not None else None, numGames, xSize, ySize, winLen,
+                                     C.byref(self.params), C.byref(self._p)))
+        # a non-owning view of the games object inside the search
+        self.games = Games.__new__(Games)
+        self.games.ctx, self.games.G, self.games.W, self.games.H, self.games.K = ctx, numGames, xSize, ySize, winLen
+        self.games.HW = xSize * ySize
+        self.games.LW = (4 * self.games.HW + 31) // 32
+        self.games._p = C.c_void_p(lib().kc_search_games(self._p))
+        self.games.close = lambda: None
+
+    def reset(self, seed=0, firstGameId=0):
+        check(lib().kc_search_reset(self._p, seed, firstGameId))
+
+    def runVisits(self):
+        check(lib().kc_search_run_visits(self._p))
+
+    def readRoot(self):
+        G, P = self.G, self.P
+        out = dict(rootVisits=np.zeros(G, np.int32), rootUtilitySum=np.zeros(G, np.float64), edgeVisits=np.zeros((G, P), np.int32),
+                   edgeUtilitySum=np.zeros((G, P), np.float64), policy=np.zeros((G, P), np.float32), order=np.zeros((G, P), np.uint8))
+        check(lib().kc_search_read_root(self._p, ptr(out["rootVisits"]), ptr(out["rootUtilitySum"]), ptr(out["edgeVisits"]),
+                                        ptr(out["edgeUtilitySum"]), ptr(out["policy"]), ptr(out["order"])))
+        return out
+
+    def play(self, moves=1, stats=None):
+        """Returns (stats, last moves played [G], device ms)."""
+        st = stats if stats is not None else capi.SearchStats()
+        chosen = np.empty(self.G, np.int16)
+        ms = C.c_float()
+        check(lib().kc_search_play(self._p, moves, ptr(chosen), C.byref(st), C.byref(ms)))
+        return st, chosen, ms.value
+
+    def launchCount(self):
+        return int(lib().kc_search_launch_count(self._p))
+
+    def close(self):
+        if self._p:
+            lib().kc_search_destroy(self._p)
+            self._p = C.c_void_p()
+
+
 def zobristTables():
     board = np.zeros((133, 4, 2), np.uint64)
     player = np.zeros((4, 2), np.uint64)

@@ -57,6 +57,16 @@ class Stats(C.Structure):
                 ("checksum", C.c_uint64)]
 
 
+class SearchParams(C.Structure):
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("pad_", C.c_int32),
+                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("visits", "netEvals", "terminalVisits", "movesPlayed", "gamesFinished", "blackWins",
+                                          "whiteWins", "draws", "batchRows")]
+
+
 FLAG_FP32_CHECK = 1
 FLAG_INPUTS_NHWC = 2
 FLAG_SYM_PERMUTE_DIRS = 4
@@ -95,6 +105,14 @@ PROTOTYPES = {
     "kc_games_run_timed": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.POINTER(Stats), C.POINTER(C.c_float)]),
     "kc_games_launch_count": (C.c_int64, [vp]),
     "kc_games_last_kernel_ms": (C.c_float, [vp]),
+    "kc_search_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SearchParams), C.POINTER(vp)]),
+    "kc_search_destroy": (C.c_int, [vp]),
+    "kc_search_games": (vp, [vp]),
+    "kc_search_reset": (C.c_int, [vp, C.c_uint64, C.c_uint64]),
+    "kc_search_run_visits": (C.c_int, [vp]),
+    "kc_search_read_root": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "kc_search_play": (C.c_int, [vp, C.c_int, vp, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
+    "kc_search_launch_count": (C.c_int64, [vp]),
 }
 
 _lib = None

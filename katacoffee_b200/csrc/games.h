@@ -1,0 +1,32 @@
+// Host-side object behind kc_games (shared by games.cu and search.cu).
+#pragma once
+#include <vector>
+
+#include "games_device.cuh"
+#include "kc_internal.h"
+
+struct kc_games {
+  kc_ctx* ctx = nullptr;
+  kc::Geom geom;
+  kc::State st;
+  uint64_t* d_zob = nullptr;          // [HW][2 colours][2]
+  int16_t* d_moves = nullptr;
+  uint32_t* d_legal = nullptr; uint32_t* d_status = nullptr; uint64_t* d_sitHash = nullptr; int16_t* d_played = nullptr;
+  unsigned long long* d_stats = nullptr;  // 8 counters
+  float* d_planes = nullptr; float* d_global = nullptr;  // fp32 feature outputs
+  int8_t* d_sym = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  float lastKernelMs = 0.f;
+  std::vector<cudaEvent_t> evPool;   // one (start, stop) pair per ply of kc_games_run_timed
+  void* d_flush = nullptr; size_t flushBytes = 0;
+  // rules+features-only timing: consecutive plies write their planes to different ring slots (4 x G x 15*HW fp32 > L2),
+  // so a ply never overwrites lines of the previous one that are still dirty in L2
+  float* d_planesRing[3] = {nullptr, nullptr, nullptr};
+};
+
+
+namespace kc {
+int gamesRefreshOutputs(kc_games* G);   // games.cu: launches on G->stream, does not synchronise
+}

@@ -1,0 +1,507 @@
+// Batched Coffee tree search on the device: G games, one PUCT tree each, advanced in lock step -- every iteration each
+// game descends its tree to one leaf, the G leaves go through the hot path (V1 planes -> net forward -> post-processing)
+// as ONE batch, and the results are expanded into the trees and backed up.  This is the caller of the leaf-evaluation
+// path in the reference: Search::playoutDescend (cpp/search/search.cpp:935-1160),
+// selectBestChildToDescend / getExploreSelectionValue / getFpuValueForChildrenAssumeVisited
+// (cpp/search/searchexplorehelpers.cpp:9-45, 248-451), addLeafValue / recomputeNodeStats
+// (cpp/search/searchupdatehelpers.cpp:12-76, 151-326), restated for Coffee positions.
+//
+// Canonical semantics (what the CPU checker under tests and this file both implement, bit for bit):
+//  * SearchParams() defaults (cpp/search/searchparams.cpp:8-90) with valueWeightExponent = 0, i.e. no utility-based
+//    re-weighting of children (searchupdatehelpers.cpp:340-366): winLossUtilityFactor 1, cpuctExploration c,
+//    cpuctExplorationLog 0, cpuctUtilityStdevScale 0, fpuReductionMax f, rootFpuReductionMax f_root, fpuLossProp 0, no
+//    uncertainty weighting (every visit has weight 1), no graph search, no noise, no virtual losses (one descent per
+//    tree per iteration).  With unit weights recomputeNodeStats' weighted average over children plus the node's own
+//    evaluation equals the running mean of all leaf utilities below the node, which is what is accumulated (W, N).
+//  * selection value of a child (white-positive utilities, pla = player to move at the parent):
+//      exploreScaling = c * sqrt(totalChildWeight + 0.01)                     (searchexplorehelpers.cpp:17-25)
+//      value = exploreScaling * prior / (1 + childVisits) + (pla == WHITE ? Q : -Q)          (:27-45)
+//      unvisited: Q = fpu = parentUtility -/+ fpuReduction * sqrt(policy mass of visited children)   (:248-320)
+//    existing children are scanned in creation order and only a strictly larger value replaces the best; the single
+//    best unvisited move (largest prior, lowest policy index on ties) then competes, again strictly (:385-449).
+//  * a move that ends the game makes a terminal child without a net evaluation; each visit to it adds the result
+//    (white win +1, black win -1, draw 0; search.cpp:943-953 with ledger C for the draw).
+//  * the move played after the search is sampled in proportion to the root children's visits for the first
+//    `temperaturePlies` plies (chosenMoveTemperature 1) with the counter RNG of SURVEY.md 8(d), afterwards the most
+//    visited child (ties: earliest created).
+//  All search arithmetic is IEEE double without fused multiply-add (explicit round-to-nearest intrinsics here,
+//  -ffp-contract=off in the oracle), so trees agree exactly whenever the leaf evaluations agree exactly.
+#include <algorithm>
+#include <cstring>
+
+#include "games.h"
+#include "net.h"
+
+namespace kc {
+
+constexpr int MAX_PATH = 52;   // a 7x7 game has at most 49 plies
+constexpr uint64_t PHI = 0x9E3779B97F4A7C15ULL;
+constexpr uint64_t CHOOSE_SALT = 0xC0FFEE5EA4C4ULL;
+
+struct SearchCfg {
+  int P;             // policy size 4*H*W
+  int LW;            // legal words
+  int nodeStride;    // bytes
+  int maxNodes;
+  int maxVisits;
+  int temperaturePlies;
+  int numGames;
+  int autoRefill;
+  double cpuct, fpuRed, rootFpuRed;
+  uint64_t seed;
+};
+
+struct TreeMem {
+  uint8_t* nodes;         // [G][maxNodes][nodeStride]
+  int* nodeCount;         // [G]
+  int* pathNode;          // [G][MAX_PATH]
+  uint8_t* pathPos;       // [G][MAX_PATH]
+  int* pathLen;           // [G]
+  int* leafKind;          // [G] 0 idle, 1 new node (needs the net), 2 new terminal child, 3 revisit of a terminal child, 4 root evaluation
+  double* leafValue;      // [G] result of a terminal leaf (white-positive)
+  int* leafNextPla;       // [G] player to move at a new node
+  unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws
+};
+
+// node layout: header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 | policy[P] f32 |
+//              child[P] i32 | edgeN[P] i32 | order[P] u8
+struct NodeRef {
+  uint8_t* base; int P;
+  __device__ __forceinline__ int& N() const { return *reinterpret_cast<int*>(base); }
+  __device__ __forceinline__ int& numChildren() const { return *reinterpret_cast<int*>(base + 4); }
+  __device__ __forceinline__ int& nextPla() const { return *reinterpret_cast<int*>(base + 8); }
+  __device__ __forceinline__ double& W() const { return *reinterpret_cast<double*>(base + 16); }
+  __device__ __forceinline__ double* edgeW() const { return reinterpret_cast<double*>(base + 32); }
+  __device__ __forceinline__ float* policy() const { return reinterpret_cast<float*>(base + 32 + 8 * P); }
+  __device__ __forceinline__ int* child() const { return reinterpret_cast<int*>(base + 32 + 12 * P); }
+  __device__ __forceinline__ int* edgeN() const { return reinterpret_cast<int*>(base + 32 + 16 * P); }
+  __device__ __forceinline__ uint8_t* order() const { return base + 32 + 20 * P; }
+};
+// child codes: -1 none, >= 0 node index, -2 terminal draw, -3 terminal black win, -4 terminal white win
+__device__ __forceinline__ double terminalValue(int winner) { return winner == 2 ? 1.0 : winner == 1 ? -1.0 : 0.0; }
+
+template <class D>
+__device__ __forceinline__ void applyMoveLight(const D& dm, GameRegs<typename D::BB>& s, int pos, const uint64_t* __restrict__ zob) {
+  using BB = typename D::BB;
+  const int fl = flagsOf(s.misc), pla = (fl >> 3) & 3;
+  const int dir = pos / dm.HW(), cell = pos % dm.HW();
+  const BB bit = (BB)1 << padOf(dm, cell);
+  if(pla == 1) s.black |= bit; else s.white |= bit;
+  const uint64_t* z = zob + ((size_t)cell * 2 + (pla - 1)) * 2;
+  s.h0 ^= z[0]; s.h1 ^= z[1];
+  const uint64_t hist = ((s.misc & 0xffffffffULL) << 8) | (uint64_t)(cell | (pla << 6));
+  const int nt = numTurnsOf(s.misc) + 1;
+  s.misc = (hist & 0xffffffffffULL) | ((uint64_t)dir << 40) | ((uint64_t)(nt & 0xff) << 48) | ((uint64_t)((pla ^ 3) << 3) << 56);
+}
+
+__device__ __forceinline__ double warpSumD(double v) {   // butterfly: every lane ends with the same, order-defined sum
+  for(int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: one warp per game descends from the root to a leaf
+// ---------------------------------------------------------------------------------------------
+template <class D>
+__global__ void __launch_bounds__(128) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+  const D dm(g);
+  using BB = typename D::BB;
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  GameRegs<BB> s;
+  s.black = (BB)root.black[gi]; s.white = (BB)root.white[gi]; s.h0 = root.hash0[gi]; s.h1 = root.hash1[gi];
+  s.id = root.gameId[gi]; s.misc = root.misc[gi];
+  uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  const int count = t.nodeCount[gi];
+  int kind = 0, depth = 0;
+  double leafVal = 0.0;
+  const bool rootFinished = flagsOf(s.misc) & 1;
+  if(rootFinished) {
+    kind = 0;
+  } else if(count == 0) {
+    kind = 4;
+  } else if(NodeRef{treeBase, c.P}.N() >= c.maxVisits) {
+    kind = 0;
+  } else {
+    int node = 0;
+    while(true) {
+      NodeRef nd{treeBase + (size_t)node * c.nodeStride, c.P};
+      const int pla = nd.nextPla();
+      const double parentUtility = __ddiv_rn(nd.W(), (double)nd.N());
+      const double* eW = nd.edgeW(); const float* pol = nd.policy(); const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
+      double total = 0.0, mass = 0.0;
+      for(int pos = lane; pos < c.P; pos += 32)
+        if(ch[pos] != -1) { total = __dadd_rn(total, (double)eN[pos]); mass = __dadd_rn(mass, (double)pol[pos]); }
+      total = warpSumD(total);
+      mass = warpSumD(mass);
+      const double red = __dmul_rn(depth == 0 ? c.rootFpuRed : c.fpuRed, __dsqrt_rn(mass));
+      const double fpu = pla == 2 ? __dsub_rn(parentUtility, red) : __dadd_rn(parentUtility, red);
+      const double scale = __dmul_rn(c.cpuct, __dsqrt_rn(__dadd_rn(total, 0.01)));
+      // best existing child (value, then earliest created) and best unvisited move (prior, then lowest index)
+      double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
+      float newP = -1.0f; int newPos = -1;
+      for(int pos = lane; pos < c.P; pos += 32) {
+        const float p = pol[pos];
+        if(ch[pos] != -1) {
+          const double n = (double)eN[pos];
+          const double q = __ddiv_rn(eW[pos], n);
+          const double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, n)), pla == 2 ? q : -q);
+          const int o = ord[pos];
+          if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
+        } else if(p >= 0.0f) {
+          if(p > newP) { newP = p; newPos = pos; }   // ascending pos within a lane: ties keep the lowest index
+        }
+      }
+      for(int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, bestVal, o);
+        const int o2 = __shfl_xor_sync(0xffffffffu, bestOrd, o), p2 = __shfl_xor_sync(0xffffffffu, bestPos, o);
+        if(p2 >= 0 && (bestPos < 0 || v2 > bestVal || (v2 == bestVal && o2 < bestOrd))) { bestVal = v2; bestOrd = o2; bestPos = p2; }
+        const float np2 = __shfl_xor_sync(0xffffffffu, newP, o);
+        const int npos2 = __shfl_xor_sync(0xffffffffu, newPos, o);
+        if(npos2 >= 0 && (newPos < 0 || np2 > newP || (np2 == newP && npos2 < newPos))) { newP = np2; newPos = npos2; }
+      }
+      bool takeNew = false;
+      if(newPos >= 0) {
+        const double valNew = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)newP), 1.0), pla == 2 ? fpu : -fpu);
+        takeNew = bestPos < 0 || valNew > bestVal;
+      }
+      const int pos = takeNew ? newPos : bestPos;
+      if(pos < 0) { kind = 0; break; }   // no legal move recorded: cannot happen for a non-terminal node
+      if(lane == 0) { t.pathNode[(size_t)gi * MAX_PATH + depth] = node; t.pathPos[(size_t)gi * MAX_PATH + depth] = (uint8_t)pos; }
+      depth++;
+      if(!takeNew) {
+        const int cc = ch[pos];
+        if(cc <= -2) { kind = 3; leafVal = terminalValue(-2 - cc); break; }
+        applyMoveLight(dm, s, pos, zob);
+        node = cc;
+        continue;
+      }
+      BB L[4]; bool illegal;
+      stepGame(dm, g, s, pos, true, zob, L, illegal);
+      const int fl = flagsOf(s.misc);
+      if(fl & 1) { kind = 2; leafVal = terminalValue((fl >> 1) & 3); }
+      else kind = 1;
+      break;
+    }
+  }
+  if(lane == 0) {
+    t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
+    t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
+    // the position handed to the evaluator (also for idle lanes: the batch is dense, their result is ignored)
+    leaf.black[gi] = (uint64_t)s.black; leaf.white[gi] = (uint64_t)s.white; leaf.hash0[gi] = s.h0; leaf.hash1[gi] = s.h1;
+    leaf.gameId[gi] = s.id; leaf.misc[gi] = s.misc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic stand-in evaluator (integer hash of the situation -> exact fp32 policy / value), used to test the
+// search logic bit for bit against the oracle; the product path uses the net
+// ---------------------------------------------------------------------------------------------
+__global__ void k_hash_eval(int n, int P, int LW, const uint32_t* __restrict__ legal, const uint64_t* __restrict__ sitHash,
+                            float* __restrict__ policy, float* __restrict__ winLoss) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= n) return;
+  const uint64_t h0 = sitHash[2 * (size_t)gi], h1 = sitHash[2 * (size_t)gi + 1];
+  int sum = 0;
+  for(int pos = lane; pos < P; pos += 32) {
+    const bool ok = (legal[(size_t)gi * LW + (pos >> 5)] >> (pos & 31)) & 1u;
+    if(ok) sum += 1 + (int)((splitmix64(h0 ^ ((uint64_t)(pos + 1) * PHI)) >> 20) & 255);
+  }
+  for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for(int pos = lane; pos < P; pos += 32) {
+    const bool ok = (legal[(size_t)gi * LW + (pos >> 5)] >> (pos & 31)) & 1u;
+    const int w = 1 + (int)((splitmix64(h0 ^ ((uint64_t)(pos + 1) * PHI)) >> 20) & 255);
+    policy[(size_t)gi * P + pos] = ok ? __fdiv_rn((float)w, (float)sum) : -1.0f;
+  }
+  if(lane == 0) {
+    const uint64_t r = splitmix64(h1);
+    winLoss[2 * (size_t)gi] = (float)(r & 0xFFFF) * (1.0f / 131072.0f);
+    winLoss[2 * (size_t)gi + 1] = (float)((r >> 16) & 0xFFFF) * (1.0f / 131072.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// expand + backup: one warp per game
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  const int kind = t.leafKind[gi];
+  if(kind == 0) return;
+  uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  const int depth = t.pathLen[gi];
+  double v = t.leafValue[gi];
+  int newIdx = -1;
+  if(kind == 1 || kind == 4) {
+    v = __dsub_rn((double)winLoss[2 * (size_t)gi], (double)winLoss[2 * (size_t)gi + 1]);   // white-positive utility of the evaluation
+    newIdx = t.nodeCount[gi];
+    if(newIdx >= c.maxNodes) return;   // cannot happen: one new node per visit, maxNodes == maxVisits
+    NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P};
+    for(int pos = lane; pos < c.P; pos += 32) {
+      nd.edgeW()[pos] = 0.0; nd.policy()[pos] = policy[(size_t)gi * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
+    }
+    if(lane == 0) { nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi]; nd.W() = v; t.nodeCount[gi] = newIdx + 1; }
+  }
+  if(lane != 0) return;
+  for(int d = 0; d < depth; d++) {
+    NodeRef nd{treeBase + (size_t)t.pathNode[(size_t)gi * MAX_PATH + d] * c.nodeStride, c.P};
+    const int pos = t.pathPos[(size_t)gi * MAX_PATH + d];
+    if(d == depth - 1 && (kind == 1 || kind == 2)) {
+      nd.child()[pos] = kind == 1 ? newIdx : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
+      nd.order()[pos] = (uint8_t)nd.numChildren();
+      nd.numChildren() = nd.numChildren() + 1;
+    }
+    nd.N() = nd.N() + 1;
+    nd.W() = __dadd_rn(nd.W(), v);
+    nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
+    nd.edgeW()[pos] = __dadd_rn(nd.edgeW()[pos], v);
+  }
+  atomicAdd(&t.stats[0], 1ULL);
+  if(kind == 1 || kind == 4) atomicAdd(&t.stats[1], 1ULL); else atomicAdd(&t.stats[2], 1ULL);
+}
+
+// ---------------------------------------------------------------------------------------------
+// choose the move, play it on the root game, drop the tree; refill finished games
+// ---------------------------------------------------------------------------------------------
+template <class D>
+__global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeMem t, const uint64_t* __restrict__ zob, int16_t* __restrict__ chosen) {
+  const D dm(g);
+  using BB = typename D::BB;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if(gi >= c.numGames) return;
+  GameRegs<BB> s;
+  s.black = (BB)root.black[gi]; s.white = (BB)root.white[gi]; s.h0 = root.hash0[gi]; s.h1 = root.hash1[gi];
+  s.id = root.gameId[gi]; s.misc = root.misc[gi];
+  int move = -1;
+  if(!(flagsOf(s.misc) & 1) && t.nodeCount[gi] > 0) {
+    NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P};
+    const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
+    long long total = 0;
+    int bestN = -1, bestOrd = 1 << 20, bestPos = -1;
+    for(int pos = 0; pos < c.P; pos++)
+      if(ch[pos] != -1) {
+        total += eN[pos];
+        if(eN[pos] > bestN || (eN[pos] == bestN && ord[pos] < bestOrd)) { bestN = eN[pos]; bestOrd = ord[pos]; bestPos = pos; }
+      }
+    const int ply = numTurnsOf(s.misc);
+    if(ply < c.temperaturePlies && total > 0) {
+      const uint64_t r = splitmix64(c.seed ^ (s.id * PHI) ^ (uint64_t)ply ^ CHOOSE_SALT);
+      long long k = (long long)(r % (uint64_t)total);
+      for(int pos = 0; pos < c.P; pos++)
+        if(ch[pos] != -1) { if(k < eN[pos]) { move = pos; break; } k -= eN[pos]; }
+    } else move = bestPos;
+    if(move >= 0) {
+      BB L[4]; bool illegal;
+      Geom g2 = g; g2.autoRefill = 0;
+      stepGame(dm, g2, s, move, true, zob, L, illegal);
+      root.black[gi] = (uint64_t)s.black; root.white[gi] = (uint64_t)s.white; root.hash0[gi] = s.h0; root.hash1[gi] = s.h1; root.misc[gi] = s.misc;
+      atomicAdd(&t.stats[3], 1ULL);
+      const int fl = flagsOf(s.misc);
+      if(fl & 1) {
+        atomicAdd(&t.stats[4], 1ULL);
+        const int w = (fl >> 1) & 3;
+        atomicAdd(&t.stats[w == 1 ? 5 : w == 2 ? 6 : 7], 1ULL);
+      }
+    }
+  }
+  t.nodeCount[gi] = 0;
+  if(chosen) chosen[gi] = (int16_t)move;
+}
+
+template <class BB>
+__global__ void k_refill(const Geom g, const SearchCfg c, State root) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if(gi >= c.numGames) return;
+  const uint64_t misc = root.misc[gi];
+  if(!(flagsOf(misc) & 1)) return;
+  GameRegs<BB> s;
+  resetGame(g, s, root.gameId[gi] + (uint64_t)c.numGames);
+  root.black[gi] = 0; root.white[gi] = 0; root.hash0[gi] = s.h0; root.hash1[gi] = s.h1; root.gameId[gi] = s.id; root.misc[gi] = s.misc;
+}
+
+}  // namespace kc
+
+// =============================================================================================
+// host
+// =============================================================================================
+struct kc_search {
+  kc_ctx* ctx = nullptr;
+  kc_handle* handle = nullptr;   // null: hash evaluator
+  kc_games* root = nullptr;      // the games being played (owned)
+  kc_games* leaf = nullptr;      // the leaf positions of the current iteration (owned)
+  kc::SearchCfg cfg;
+  kc::TreeMem tree;
+  float* d_policy = nullptr; float* d_winLoss = nullptr; float* d_misc = nullptr; uint64_t* d_nnHash = nullptr;
+  int16_t* d_chosen = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+};
+
+using namespace kc;
+
+namespace {
+bool isStatic5(const Geom& g) { return g.W == 5 && g.H == 5 && g.K == 4; }
+
+int runVisits(kc_search* S) {
+  const SearchCfg& c = S->cfg;
+  kc_games* R = S->root; kc_games* Lf = S->leaf;
+  cudaStream_t st = Lf->stream;
+  const int warpBlocks = (c.numGames * 32 + 127) / 128;
+  for(int it = 0; it < c.maxVisits; it++) {
+    if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
+    else k_select<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
+    S->launches++;
+    if(S->handle) {
+      if(kc_games_eval(Lf, S->handle, nullptr)) return 1;
+      kc::launchPostprocess(S->handle, c.numGames, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, S->d_policy, S->d_winLoss, S->d_misc, S->d_nnHash, st);
+      S->launches += 3;
+    } else {
+      if(kc::gamesRefreshOutputs(Lf)) return 1;
+      k_hash_eval<<<warpBlocks, 128, 0, st>>>(c.numGames, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, S->d_policy, S->d_winLoss);
+      S->launches += 2;
+    }
+    k_expand_backup<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
+    S->launches++;
+  }
+  KC_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSize, int ySize, int winLen, const kc_search_params* p, kc_search** out) {
+  KC_CHECK(ctx && p && out, "kc_search_create: null argument");
+  KC_CHECK(p->maxVisits >= 1 && p->maxVisits <= 65536, "kc_search_create: maxVisits must be within 1..65536");
+  KC_CHECK(p->cpuctExploration > 0 && p->fpuReductionMax >= 0 && p->rootFpuReductionMax >= 0, "kc_search_create: bad exploration parameters");
+  KC_CUDA(cudaSetDevice(ctx->device));
+  kc_search* S = new kc_search();
+  S->ctx = ctx; S->handle = handleOrNull;
+  if(kc_games_create(ctx, numGames, xSize, ySize, winLen, &S->root) || kc_games_create(ctx, numGames, xSize, ySize, winLen, &S->leaf)) { delete S; return 1; }
+  if(handleOrNull && kc::handleCheckGeometry(handleOrNull, xSize, ySize, numGames)) { kc_games_destroy(S->root); kc_games_destroy(S->leaf); delete S; return 1; }
+  SearchCfg& c = S->cfg;
+  c.P = 4 * xSize * ySize; c.LW = (c.P + 31) / 32;
+  c.nodeStride = (32 + 21 * c.P + 15) / 16 * 16;
+  c.maxNodes = p->maxVisits; c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
+  c.numGames = numGames; c.autoRefill = p->autoRefill ? 1 : 0;
+  c.cpuct = p->cpuctExploration; c.fpuRed = p->fpuReductionMax; c.rootFpuRed = p->rootFpuReductionMax;
+  c.seed = 0;
+  const size_t n = (size_t)numGames;
+  const size_t treeBytes = n * c.maxNodes * c.nodeStride;
+  size_t freeB = 0, totalB = 0;
+  KC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  KC_CHECK(treeBytes + (1ULL << 30) < freeB, "kc_search_create: the trees (numGames x maxVisits x " + std::to_string(c.nodeStride) + " B) do not fit in free device memory");
+  KC_CUDA(cudaMalloc(&S->tree.nodes, treeBytes));
+  KC_CUDA(cudaMalloc(&S->tree.nodeCount, n * 4)); KC_CUDA(cudaMemset(S->tree.nodeCount, 0, n * 4));
+  KC_CUDA(cudaMalloc(&S->tree.pathNode, n * MAX_PATH * 4)); KC_CUDA(cudaMalloc(&S->tree.pathPos, n * MAX_PATH));
+  KC_CUDA(cudaMalloc(&S->tree.pathLen, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafKind, n * 4));
+  KC_CUDA(cudaMalloc(&S->tree.leafValue, n * 8)); KC_CUDA(cudaMalloc(&S->tree.leafNextPla, n * 4));
+  KC_CUDA(cudaMalloc(&S->tree.stats, 64)); KC_CUDA(cudaMemset(S->tree.stats, 0, 64));
+  KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
+  KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
+  KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
+  KC_CUDA(cudaEventCreate(&S->ev0)); KC_CUDA(cudaEventCreate(&S->ev1));
+  *out = S;
+  return 0;
+}
+
+int kc_search_destroy(kc_search* S) {
+  if(!S) return 0;
+  cudaSetDevice(S->ctx->device);
+  cudaStreamSynchronize(S->leaf->stream);
+  cudaFree(S->tree.nodes); cudaFree(S->tree.nodeCount); cudaFree(S->tree.pathNode); cudaFree(S->tree.pathPos); cudaFree(S->tree.pathLen);
+  cudaFree(S->tree.leafKind); cudaFree(S->tree.leafValue); cudaFree(S->tree.leafNextPla); cudaFree(S->tree.stats);
+  cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
+  cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
+  kc_games_destroy(S->root); kc_games_destroy(S->leaf);
+  delete S;
+  return 0;
+}
+
+kc_games* kc_search_games(kc_search* S) { return S ? S->root : nullptr; }
+
+int kc_search_reset(kc_search* S, uint64_t seed, uint64_t firstGameId) {
+  KC_CHECK(S, "kc_search_reset: null search");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  S->cfg.seed = seed;
+  if(kc_games_reset(S->root, seed, firstGameId, 0)) return 1;
+  KC_CUDA(cudaMemset(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4));
+  KC_CUDA(cudaMemset(S->tree.stats, 0, 64));
+  return 0;
+}
+
+int kc_search_run_visits(kc_search* S) {
+  KC_CHECK(S, "kc_search_run_visits: null search");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4, S->leaf->stream));
+  if(runVisits(S)) return 1;
+  KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
+  if(S->handle && kc::handleCheckAbort(S->handle)) return 1;
+  return 0;
+}
+
+int kc_search_read_root(kc_search* S, int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policy, uint8_t* order) {
+  KC_CHECK(S, "kc_search_read_root: null search");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  const SearchCfg& c = S->cfg;
+  std::vector<uint8_t> node(c.nodeStride);
+  std::vector<int> counts(c.numGames);
+  KC_CUDA(cudaMemcpy(counts.data(), S->tree.nodeCount, (size_t)c.numGames * 4, cudaMemcpyDeviceToHost));
+  for(int gi = 0; gi < c.numGames; gi++) {
+    const bool have = counts[gi] > 0;
+    if(have) KC_CUDA(cudaMemcpy(node.data(), S->tree.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.nodeStride, cudaMemcpyDeviceToHost));
+    else std::fill(node.begin(), node.end(), 0);
+    const uint8_t* b = node.data();
+    if(rootVisits) rootVisits[gi] = have ? *reinterpret_cast<const int*>(b) : 0;
+    if(rootUtilitySum) rootUtilitySum[gi] = have ? *reinterpret_cast<const double*>(b + 16) : 0.0;
+    for(int pos = 0; pos < c.P; pos++) {
+      const bool ex = have && reinterpret_cast<const int*>(b + 32 + 12 * c.P)[pos] != -1;
+      if(edgeVisits) edgeVisits[(size_t)gi * c.P + pos] = ex ? reinterpret_cast<const int*>(b + 32 + 16 * c.P)[pos] : 0;
+      if(edgeUtilitySum) edgeUtilitySum[(size_t)gi * c.P + pos] = ex ? reinterpret_cast<const double*>(b + 32)[pos] : 0.0;
+      if(policy) policy[(size_t)gi * c.P + pos] = have ? reinterpret_cast<const float*>(b + 32 + 8 * c.P)[pos] : 0.f;
+      if(order) order[(size_t)gi * c.P + pos] = ex ? (b + 32 + 20 * c.P)[pos] : 255;
+    }
+  }
+  return 0;
+}
+
+int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats* acc, float* msTotal) {
+  KC_CHECK(S && moves > 0, "kc_search_play: bad argument");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  const SearchCfg& c = S->cfg;
+  kc_games* R = S->root;
+  cudaStream_t st = S->leaf->stream;
+  const int blocks = (c.numGames + 127) / 128;
+  KC_CUDA(cudaMemsetAsync(S->tree.stats, 0, 64, st));
+  KC_CUDA(cudaEventRecord(S->ev0, st));
+  for(int m = 0; m < moves; m++) {
+    if(c.autoRefill) {
+      if(isStatic5(R->geom)) k_refill<uint32_t><<<blocks, 128, 0, st>>>(R->geom, c, R->st);
+      else k_refill<uint64_t><<<blocks, 128, 0, st>>>(R->geom, c, R->st);
+      S->launches++;
+    }
+    KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
+    if(runVisits(S)) return 1;
+    if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, R->d_zob, S->d_chosen);
+    else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, R->d_zob, S->d_chosen);
+    S->launches++;
+  }
+  KC_CUDA(cudaEventRecord(S->ev1, st));
+  KC_CUDA(cudaGetLastError());
+  unsigned long long hs[8];
+  KC_CUDA(cudaMemcpyAsync(hs, S->tree.stats, 64, cudaMemcpyDeviceToHost, st));
+  if(chosenLast) KC_CUDA(cudaMemcpyAsync(chosenLast, S->d_chosen, (size_t)c.numGames * 2, cudaMemcpyDeviceToHost, st));
+  KC_CUDA(cudaStreamSynchronize(st));
+  if(S->handle && kc::handleCheckAbort(S->handle)) return 1;
+  if(msTotal) KC_CUDA(cudaEventElapsedTime(msTotal, S->ev0, S->ev1));
+  if(acc) {
+    acc->visits += hs[0]; acc->netEvals += hs[1]; acc->terminalVisits += hs[2]; acc->movesPlayed += hs[3];
+    acc->gamesFinished += hs[4]; acc->blackWins += hs[5]; acc->whiteWins += hs[6]; acc->draws += hs[7];
+    acc->batchRows += (uint64_t)c.numGames * c.maxVisits * moves;
+  }
+  return 0;
+}
+
+int64_t kc_search_launch_count(const kc_search* S) { return S ? S->launches + kc_games_launch_count(S->leaf) : 0; }
+
+}  // extern "C"

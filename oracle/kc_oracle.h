@@ -202,6 +202,20 @@ void ko_postprocess(float* policy, int policySize, const uint32_t* legalMask, fl
                     float* value2 /* win,loss logits -> whiteWin, whiteLoss */, float* misc2,
                     int nextPla);
 
+/* ----------------------------------------------------------------------------------------------
+ * Tree search (ko_search.cpp): single-game restatement of the reference's playout loop under SearchParams()
+ * defaults with valueWeightExponent 0 (see the file header).  modelOrNull == NULL selects the integer-hash
+ * evaluator that the CUDA search also implements, so trees can be compared exactly.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t maxVisits, temperaturePlies, autoRefill, pad_;
+  double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
+} ko_search_params;   /* same layout as kc_search_params */
+void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                   int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                   uint8_t* orderOut, uint64_t counters[3] /* += visits, evaluations, terminal visits */);
+int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int ply, int temperaturePlies, uint64_t seed, uint64_t gameId);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ REF_HASH_PATH = os.path.join(_HERE, "_ref", "libkc_ref_hash.so")
 
 def build(force=False):
     """make -C oracle: the restatement always; oracle/_ref only where /root/reference exists."""
-    srcs = [os.path.join(_HERE, f) for f in ("ko_hash.cpp", "ko_game.cpp", "ko_net.cpp", "kc_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("ko_hash.cpp", "ko_game.cpp", "ko_net.cpp", "ko_search.cpp", "kc_oracle.h", "Makefile")]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.run(["make", "-C", _HERE, "libkc_oracle.so"], check=True, stdout=subprocess.DEVNULL)
@@ -91,6 +91,8 @@ def lib():
         l.ko_test_batchnorm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         l.ko_test_resblock.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]
         l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
+        l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
         _lib = l
     return _lib
 
@@ -266,3 +268,28 @@ def postprocess(policy, legal_mask, value2, misc2, next_pla, temp=1.0):
     lm = np.ascontiguousarray(legal_mask, np.uint32)
     lib().ko_postprocess(_p(p), p.shape[0], _p(lm), temp, _p(v), _p(m), next_pla)
     return p, v, m
+
+
+class SearchParams(C.Structure):
+    """Same layout as kc_search_params (include/katacoffee_b200.h)."""
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("pad_", C.c_int32),
+                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
+
+
+def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
+    """One oracle search from `game` (a Game); model=None uses the integer-hash evaluator.  Returns a dict with the
+    root statistics (arrays over the policy index) and the visit counters."""
+    P = 4 * game.HW
+    sp = SearchParams(max_visits, 0, 0, 0, cpuct, fpu, root_fpu)
+    rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
+    ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
+    cnt = np.zeros(3, np.uint64)
+    lib().ko_search_run(game._g, game.W, game.H, C.byref(sp), None if model is None else model._m, _p(rv), _p(rw), _p(ev), _p(ew), _p(pol),
+                        _p(order), _p(cnt))
+    return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
+            "counters": cnt}
+
+
+def search_choose(edge_visits, order, ply, temperature_plies, seed, game_id):
+    ev = np.ascontiguousarray(edge_visits, np.int32); od = np.ascontiguousarray(order, np.uint8)
+    return lib().ko_search_choose(_p(ev), _p(od), len(ev), ply, temperature_plies, seed, game_id)

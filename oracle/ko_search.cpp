@@ -1,0 +1,215 @@
+// CPU ORACLE (test infrastructure, see kc_oracle.h) of the Coffee tree search: a restatement of the reference's
+// single-threaded playout loop for one game,
+//   Search::playoutDescend                         cpp/search/search.cpp:935-1160
+//   Search::selectBestChildToDescend               cpp/search/searchexplorehelpers.cpp:323-451
+//   getExploreScaling / getExploreSelectionValue   cpp/search/searchexplorehelpers.cpp:9-45
+//   getFpuValueForChildrenAssumeVisited            cpp/search/searchexplorehelpers.cpp:248-320
+//   addLeafValue / recomputeNodeStats              cpp/search/searchupdatehelpers.cpp:12-76, 151-326
+// under SearchParams() defaults (cpp/search/searchparams.cpp:8-90) with valueWeightExponent = 0, cpuctExplorationLog = 0,
+// no graph search, no noise, one thread: every visit has weight 1, so a node's utilityAvg is the mean of the leaf
+// utilities below it (kept as a sum W and a count N), a child's weight is its visit count.  PARITY UNPINNED: the
+// reference's search does not compile against Coffee positions and has no Coffee test; this file is the
+// definition the CUDA search (katacoffee_b200/csrc/search.cu) is compared with, bit for bit.
+//
+// Compiled with -ffp-contract=off: all arithmetic is plain IEEE double, the same operations in the same order as the
+// device code (which uses explicit round-to-nearest intrinsics).  The only order-sensitive sum (the policy mass of the
+// visited children) is accumulated exactly as a 32-lane warp does it: lane = index mod 32, then an xor butterfly.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kc_oracle.h"
+
+namespace {
+
+constexpr uint64_t PHI = 0x9E3779B97F4A7C15ULL;
+constexpr uint64_t CHOOSE_SALT = 0xC0FFEE5EA4C4ULL;
+
+struct Node {
+  int N = 0, numChildren = 0, nextPla = 0;
+  double W = 0.0;
+  std::vector<double> edgeW;
+  std::vector<float> policy;
+  std::vector<int> child;     // -1 none, >= 0 node, -2 draw, -3 black win, -4 white win
+  std::vector<int> edgeN;
+  std::vector<uint8_t> order;
+  explicit Node(int P) : edgeW(P, 0.0), policy(P, -1.0f), child(P, -1), edgeN(P, 0), order(P, 0) {}
+};
+
+double terminalValue(int winner) { return winner == 2 ? 1.0 : winner == 1 ? -1.0 : 0.0; }
+
+double butterfly(double part[32]) {
+  double cur[32], nxt[32];
+  memcpy(cur, part, sizeof(cur));
+  for(int o = 16; o > 0; o >>= 1) {
+    for(int l = 0; l < 32; l++) nxt[l] = cur[l] + cur[l ^ o];
+    memcpy(cur, nxt, sizeof(cur));
+  }
+  return cur[0];
+}
+
+struct Evaluator {
+  const ko_model* model;   // null: integer-hash evaluator
+  int W, H, P, LW;
+  // fills policy [P] (-1 illegal) and (whiteWin, whiteLoss) for the position in g (player to move = next player)
+  void eval(const ko_game* g, float* policy, float winLoss[2]) const {
+    std::vector<uint32_t> legal(LW);
+    const int pla = ko_game_next_pla(g);
+    ko_game_legal_mask(g, pla, legal.data());
+    if(!model) {
+      uint64_t h[2];
+      ko_game_sit_hash(g, pla, h);
+      int sum = 0;
+      for(int pos = 0; pos < P; pos++)
+        if((legal[pos >> 5] >> (pos & 31)) & 1u) sum += 1 + (int)((ko_splitmix64(h[0] ^ ((uint64_t)(pos + 1) * PHI)) >> 20) & 255);
+      for(int pos = 0; pos < P; pos++) {
+        const bool ok = (legal[pos >> 5] >> (pos & 31)) & 1u;
+        const int w = 1 + (int)((ko_splitmix64(h[0] ^ ((uint64_t)(pos + 1) * PHI)) >> 20) & 255);
+        policy[pos] = ok ? (float)w / (float)sum : -1.0f;
+      }
+      const uint64_t r = ko_splitmix64(h[1]);
+      winLoss[0] = (float)(r & 0xFFFF) * (1.0f / 131072.0f);
+      winLoss[1] = (float)((r >> 16) & 0xFFFF) * (1.0f / 131072.0f);
+      return;
+    }
+    std::vector<float> planes((size_t)15 * W * H), own((size_t)W * H);
+    float glob = 0.f, value[2], misc[2];
+    ko_game_fill_row_v1(g, pla, W, H, 0, planes.data(), &glob);
+    ko_model_forward(model, 1, W, H, 0, planes.data(), &glob, nullptr, policy, value, misc, own.data(), 0, 1);
+    ko_postprocess(policy, P, legal.data(), 1.0f, value, misc, pla);
+    winLoss[0] = value[0]; winLoss[1] = value[1];
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                   int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                   uint8_t* orderOut, uint64_t counters[3]) {
+  const int P = 4 * x_size * y_size;
+  Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
+  std::vector<Node> nodes;
+  nodes.reserve(p->maxVisits);
+  uint64_t cVisits = 0, cEvals = 0, cTerminal = 0;
+  ko_game* g = ko_game_create(x_size, y_size, 4);
+  std::vector<float> pol(P);
+  float wl[2];
+  for(int it = 0; it < p->maxVisits && !ko_game_finished(rootGame); it++) {
+    ko_game_copy(g, rootGame);
+    std::vector<std::pair<int, int>> path;   // (node, pos)
+    int kind = 0;
+    double v = 0.0;
+    if(nodes.empty()) kind = 4;
+    else if(nodes[0].N >= p->maxVisits) break;
+    else {
+      int node = 0, depth = 0;
+      while(true) {
+        Node& nd = nodes[node];
+        const int pla = nd.nextPla;
+        const double parentUtility = nd.W / (double)nd.N;
+        double partT[32] = {0}, partM[32] = {0};
+        for(int pos = 0; pos < P; pos++)
+          if(nd.child[pos] != -1) { partT[pos & 31] = partT[pos & 31] + (double)nd.edgeN[pos]; partM[pos & 31] = partM[pos & 31] + (double)nd.policy[pos]; }
+        const double total = butterfly(partT), mass = butterfly(partM);
+        const double red = (depth == 0 ? p->rootFpuReductionMax : p->fpuReductionMax) * std::sqrt(mass);
+        const double fpu = pla == 2 ? parentUtility - red : parentUtility + red;
+        const double scale = p->cpuctExploration * std::sqrt(total + 0.01);
+        double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
+        float newP = -1.0f; int newPos = -1;
+        for(int pos = 0; pos < P; pos++) {
+          const float pr = nd.policy[pos];
+          if(nd.child[pos] != -1) {
+            const double n = (double)nd.edgeN[pos];
+            const double q = nd.edgeW[pos] / n;
+            const double val = (scale * (double)pr) / (1.0 + n) + (pla == 2 ? q : -q);
+            const int o = nd.order[pos];
+            if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
+          } else if(pr >= 0.0f) {
+            if(pr > newP) { newP = pr; newPos = pos; }
+          }
+        }
+        bool takeNew = false;
+        if(newPos >= 0) {
+          const double valNew = (scale * (double)newP) / 1.0 + (pla == 2 ? fpu : -fpu);
+          takeNew = bestPos < 0 || valNew > bestVal;
+        }
+        const int pos = takeNew ? newPos : bestPos;
+        if(pos < 0) { kind = 0; break; }
+        path.push_back({node, pos});
+        depth++;
+        if(!takeNew) {
+          const int cc = nd.child[pos];
+          if(cc <= -2) { kind = 3; v = terminalValue(-2 - cc); break; }
+          ko_game_play(g, pos);
+          node = cc;
+          continue;
+        }
+        ko_game_play(g, pos);
+        if(ko_game_finished(g)) { kind = 2; v = terminalValue(ko_game_winner(g)); }
+        else kind = 1;
+        break;
+      }
+    }
+    if(kind == 0) continue;
+    int newIdx = -1;
+    if(kind == 1 || kind == 4) {
+      ev.eval(g, pol.data(), wl);
+      v = (double)wl[0] - (double)wl[1];
+      newIdx = (int)nodes.size();
+      nodes.emplace_back(P);
+      Node& nn = nodes.back();
+      nn.N = 1; nn.W = v; nn.nextPla = ko_game_next_pla(g);
+      for(int pos = 0; pos < P; pos++) nn.policy[pos] = pol[pos];
+    }
+    for(size_t d = 0; d < path.size(); d++) {
+      Node& nd = nodes[path[d].first];
+      const int pos = path[d].second;
+      if(d + 1 == path.size() && (kind == 1 || kind == 2)) {
+        nd.child[pos] = kind == 1 ? newIdx : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
+        nd.order[pos] = (uint8_t)nd.numChildren;
+        nd.numChildren++;
+      }
+      nd.N += 1;
+      nd.W = nd.W + v;
+      nd.edgeN[pos] += 1;
+      nd.edgeW[pos] = nd.edgeW[pos] + v;
+    }
+    cVisits++;
+    if(kind == 1 || kind == 4) cEvals++; else cTerminal++;
+  }
+  ko_game_destroy(g);
+  const bool have = !nodes.empty();
+  if(rootVisits) *rootVisits = have ? nodes[0].N : 0;
+  if(rootUtilitySum) *rootUtilitySum = have ? nodes[0].W : 0.0;
+  for(int pos = 0; pos < P; pos++) {
+    const bool ex = have && nodes[0].child[pos] != -1;
+    if(edgeVisits) edgeVisits[pos] = ex ? nodes[0].edgeN[pos] : 0;
+    if(edgeUtilitySum) edgeUtilitySum[pos] = ex ? nodes[0].edgeW[pos] : 0.0;
+    if(policyOut) policyOut[pos] = have ? nodes[0].policy[pos] : 0.f;
+    if(orderOut) orderOut[pos] = ex ? nodes[0].order[pos] : 255;
+  }
+  if(counters) { counters[0] += cVisits; counters[1] += cEvals; counters[2] += cTerminal; }
+}
+
+// The move played after a search: proportional to the root children's visits for ply < temperaturePlies (counter RNG),
+// otherwise the most visited child, ties to the earliest created.  Returns -1 if the root has no child.
+int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int ply, int temperaturePlies, uint64_t seed, uint64_t gameId) {
+  long long total = 0;
+  int bestN = -1, bestOrd = 1 << 20, bestPos = -1;
+  for(int pos = 0; pos < P; pos++)
+    if(order[pos] != 255) {
+      total += edgeVisits[pos];
+      if(edgeVisits[pos] > bestN || (edgeVisits[pos] == bestN && order[pos] < bestOrd)) { bestN = edgeVisits[pos]; bestOrd = order[pos]; bestPos = pos; }
+    }
+  if(ply < temperaturePlies && total > 0) {
+    const uint64_t r = ko_splitmix64(seed ^ (gameId * PHI) ^ (uint64_t)ply ^ CHOOSE_SALT);
+    long long k = (long long)(r % (uint64_t)total);
+    for(int pos = 0; pos < P; pos++)
+      if(order[pos] != 255) { if(k < edgeVisits[pos]) return pos; k -= edgeVisits[pos]; }
+  }
+  return bestPos;
+}
+
+}  // extern "C"

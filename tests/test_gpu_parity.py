@@ -570,3 +570,131 @@ def test_b15c192_6x6_device_resident_and_unsupported_width_rejected(ctx, oracle)
     ref2 = oracle.Model(wide).forward(planes5, glob5, 5, 5, mode=0, threads=8)
     assert max(np.abs(a - b).max() for a, b in zip(got2, ref2)) < TOL_FP32
     h2.close(); lm2.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Batched tree search against the oracle's single-game restatement
+# ------------------------------------------------------------------------------------------------
+def _oracle_positions(oracle, W, H, K, seed, plies_of_game):
+    games = []
+    for gidx, plies in enumerate(plies_of_game):
+        og = oracle.Game(W, H, K)
+        for _ in range(plies):
+            if og.finished():
+                break
+            og.play(og.choose(seed, gidx))
+        games.append(og)
+    return games
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,K,G,V", [(5, 5, 4, 192, 160), (6, 6, 4, 48, 96), (4, 5, 3, 40, 64)])
+def test_search_hash_evaluator_bit_exact(ctx, oracle, W, H, K, G, V):
+    """Search logic (selection, FPU, expansion, terminal children, backup) with the integer-hash evaluator: root visit
+    counts, utility sums (IEEE double), priors and creation order equal the oracle's for every game, bit for bit."""
+    from katacoffee_b200 import backend
+    seed = 77
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V)
+    s.reset(seed=seed)
+    # spread the games over different depths: game g is advanced g % 9 random-legal plies
+    plies = np.array([g % 9 for g in range(G)])
+    ogames = _oracle_positions(oracle, W, H, K, seed, plies)
+    # replay the oracle's move lists on the device with forced moves
+    maxp = int(plies.max())
+    hist = [[] for _ in range(G)]
+    for g in range(G):
+        og = oracle.Game(W, H, K)
+        for _ in range(int(plies[g])):
+            if og.finished():
+                break
+            mv = og.choose(seed, g)
+            og.play(mv)
+            hist[g].append(mv)
+    for t in range(maxp):
+        mv = np.array([hist[g][t] if t < len(hist[g]) else -1 for g in range(G)], np.int16)
+        s.games.step(mv)
+    s.runVisits()
+    got = s.readRoot()
+    for g in range(G):
+        ref = oracle.search_run(ogames[g], V)
+        assert got["rootVisits"][g] == ref["rootVisits"], (g, got["rootVisits"][g], ref["rootVisits"])
+        assert (got["edgeVisits"][g] == ref["edgeVisits"]).all(), g
+        assert (got["order"][g] == ref["order"]).all(), g
+        assert (got["policy"][g] == ref["policy"]).all(), g
+        assert got["rootUtilitySum"][g] == ref["rootUtilitySum"], g
+        assert (got["edgeUtilitySum"][g] == ref["edgeUtilitySum"]).all(), g
+    assert got["rootVisits"].max() == V
+    s.close()
+
+
+@pytest.mark.gpu
+def test_search_selfplay_moves_match_oracle(ctx, oracle):
+    """search -> choose (visit-proportional for the first plies, then most visited) -> play, repeated to the end of the
+    games: the move sequences, results and counters equal the oracle's."""
+    from katacoffee_b200 import backend, capi
+    W = H = 5
+    G, V, seed, T = 96, 48, 5, 4
+    s = backend.Search(ctx, None, G, W, H, 4, maxVisits=V, temperaturePlies=T)
+    s.reset(seed=seed, firstGameId=1000)
+    ogames = [oracle.Game(W, H, 4) for _ in range(G)]
+    stats = capi.SearchStats()
+    ocnt = np.zeros(3, np.uint64)
+    ofinished = 0
+    for ply in range(26):
+        _, chosen, _ = s.play(1, stats)
+        for g in range(G):
+            og = ogames[g]
+            if og.finished():
+                assert chosen[g] == -1
+                continue
+            r = oracle.search_run(og, V)
+            ocnt += r["counters"]
+            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 1000 + g)
+            assert chosen[g] == mv, (ply, g, chosen[g], mv)
+            og.play(mv)
+            ofinished += og.finished()
+    assert all(og.finished() for og in ogames)
+    st = s.games.step(np.full(G, -1, np.int16))
+    assert all(int(st["status"][g]) == ogames[g].status() for g in range(G))
+    assert (stats.visits, stats.netEvals, stats.terminalVisits) == tuple(int(x) for x in ocnt)
+    assert stats.gamesFinished == ofinished == G and stats.blackWins + stats.whiteWins + stats.draws == G
+    s.close()
+
+
+@pytest.mark.gpu
+def test_search_with_net_close_to_oracle(ctx, oracle):
+    """The product configuration: leaves evaluated by the net (fp32 check path here, so that CPU and GPU evaluations
+    agree to 1e-4).  Trees may part on near-ties, so the bar is statistical: the root priors agree to 1e-4 everywhere
+    and the visit distributions are identical for most games and close for all."""
+    from katacoffee_b200 import backend, modeldesc
+    W = H = 5
+    G, V, seed = 48, 40, 3
+    model = modeldesc.Model("b2c32", seed=21)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=True)
+    s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V)
+    s.reset(seed=seed)
+    for _ in range(3):
+        s.games.step()
+    s.runVisits()
+    got = s.readRoot()
+    same = 0
+    for g in range(G):
+        og = oracle.Game(W, H, 4)
+        for _ in range(3):
+            og.play(og.choose(seed, g))
+        ref = oracle.search_run(og, V, model=om)
+        assert np.abs(got["policy"][g] - ref["policy"]).max() < 1e-4
+        assert got["rootVisits"][g] == ref["rootVisits"] == V
+        same += (got["edgeVisits"][g] == ref["edgeVisits"]).all()
+        assert np.abs(got["edgeVisits"][g] - ref["edgeVisits"]).sum() <= V // 2
+    assert same >= 0.8 * G, same
+    # and the bf16 tensor-core path runs the same search end to end
+    hb = backend.createComputeHandle(ctx, lm, G, W, H)
+    sb = backend.Search(ctx, hb, G, W, H, 4, maxVisits=V, temperaturePlies=30, autoRefill=True)
+    sb.reset(seed=seed)
+    st, chosen, ms = sb.play(3)
+    assert st.movesPlayed == 3 * G and st.visits == 3 * G * V and st.netEvals + st.terminalVisits == st.visits
+    for x in (s, sb, h, hb, lm):
+        x.close()
