@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
+    ap.add_argument("--selfplay-moves", type=int, default=1, help="moves per game timed in the self-play arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -255,6 +258,28 @@ def main():
     h2d = G * (15 * hw * 4 + 4 + 1)
     d2h = G * (4 * hw * 4 + 8 + 8 + hw * 4)
 
+    # ---------------- self-play arm (BASELINE.json: "selfplay moves/s", 800 visits/move) ----------------
+    # the same G games under the batched device tree search: per iteration every game descends to one leaf and the G
+    # leaves are one batch through the hot path; a move = SELFPLAY_VISITS iterations
+    selfplay = None
+    if not args.no_selfplay:
+        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True)
+        search.reset(seed=SEED, firstGameId=shard.first_game_id(rank))
+        handle.trunkTime()
+        barrier()
+        sp_stats, _, sp_ms = search.play(args.selfplay_moves)
+        barrier()
+        sp_ms_max = shard.max_over_ranks(sp_ms, "cuda")
+        sp = shard.reduce_stats([sp_stats.movesPlayed, sp_stats.visits, sp_stats.netEvals, sp_stats.terminalVisits, sp_stats.gamesFinished,
+                                 sp_stats.batchRows], "cuda")
+        selfplay = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
+                    "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
+                    "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
+                    "ms_per_iteration": sp_ms_max / (args.visits * args.selfplay_moves), "games_finished": int(sp[4]),
+                    "search": "lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), visit-proportional move choice",
+                    "kernel_launches": int(search.launchCount())}
+        search.close()
+
     if rank == 0:
         flops = modeldesc.flops_per_eval(NET, hw)
         trunk_avg_ms = trunk_ms / max(trunk_n, 1)
@@ -275,6 +300,7 @@ def main():
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
                                         "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games")},
+            "selfplay": selfplay,
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
                       "black_wins": int(counters[3]), "white_wins": int(counters[4]), "draws": int(counters[5])},
         }

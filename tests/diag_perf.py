@@ -23,3 +23,16 @@ for G in (4736, 18944):
     games.close(); h.close()
 g = backend.Games(ctx, 65536, 5, 5, 4); g.reset(seed=1, autoRefill=True); g.run(None, 5); g.run(None, 50)
 print(f"rules+features fp32 NCHW 65536 games: kernel {g.lastKernelMs():.4f} ms/ply -> {65536/g.lastKernelMs()*1e3/1e9:.3f} G steps/s, {65536*1572/g.lastKernelMs()*1e3/1e9:.0f} GB/s algorithmic")
+# batched tree search: per-iteration cost on top of the trunk
+if net == "b10c128" and W == 5:
+    for G, V in ((18944, 64),):
+        h = backend.createComputeHandle(ctx, lm, G, W, H)
+        s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, temperaturePlies=30, autoRefill=True)
+        s.reset(seed=1)
+        s.play(1)
+        h.trunkTime()
+        st, _, ms = s.play(2)
+        tms, tcnt = h.trunkTime()
+        print(f"search G={G} V={V}: {ms/2/V:.3f} ms per iteration (trunk {tms/tcnt:.3f} ms), {st.movesPlayed/(ms*1e-3):.0f} moves/s at {V} visits, "
+              f"{st.visits/(ms*1e-3)/1e6:.3f} M visits/s, net evals {st.netEvals/st.visits:.3f} of visits, games finished {st.gamesFinished}")
+        s.close(); h.close()
