@@ -33,6 +33,7 @@ WINLEN = 4
 SEED = 20261018
 GAMES_PER_GPU = 148 * 128            # 18944: 8 boards per CTA work item -> 16 items per SM, no tail
 L2_FLUSH_BYTES = 256 << 20           # > 126 MB L2, written between timed steps
+SELFPLAY_STAGGER = 20                # self-play arm: games start spread over plies 0..19 (a 5x5 game lasts 7..24 plies)
 BYTES_PER_STEP_FP32 = 1572           # rules+features algorithmic bytes per game-step (fp32 planes)
 
 
@@ -265,6 +266,11 @@ def main():
     if not args.no_selfplay:
         search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True)
         search.reset(seed=SEED, firstGameId=shard.first_game_id(rank))
+        # steady-state mix of a self-play run: game g starts the timed move after (g mod STAGGER) random-legal plies, as
+        # games that were refilled at different times do (movePos -2 = the counter-RNG move, -1 = stay)
+        lane = np.arange(G)
+        for t in range(SELFPLAY_STAGGER):
+            search.games.step(np.where(lane % SELFPLAY_STAGGER > t, -2, -1).astype(np.int16))
         handle.trunkTime()
         barrier()
         sp_stats, _, sp_ms = search.play(args.selfplay_moves)
@@ -273,7 +279,7 @@ def main():
         sp = shard.reduce_stats([sp_stats.movesPlayed, sp_stats.visits, sp_stats.netEvals, sp_stats.terminalVisits, sp_stats.gamesFinished,
                                  sp_stats.batchRows], "cuda")
         selfplay = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
-                    "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
+                    "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
                     "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
                     "ms_per_iteration": sp_ms_max / (args.visits * args.selfplay_moves), "games_finished": int(sp[4]),
                     "search": "lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), visit-proportional move choice",

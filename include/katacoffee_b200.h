@@ -166,7 +166,7 @@ int kc_games_reset(kc_games* g, uint64_t seed, uint64_t firstGameId, int autoRef
 int kc_games_load(kc_games* g, int g0, int n, const int8_t* stones, const int8_t* nextPla,
                   const int16_t* moves, const int32_t* numTurns);
 /* One ply for every unfinished game.  movePos [G] (policy index, -1 = do nothing) or NULL for
- * the counter-RNG random-legal move of SURVEY.md 8(d):
+ * the counter-RNG random-legal move of SURVEY.md 8(d) (also selected per game by movePos == -2):
  *   r = splitmix64(seed ^ gameId*0x9E3779B97F4A7C15 ^ ply), move = (r mod popcount)-th legal bit.
  * Illegal movePos leaves the game unchanged and sets bit 15 of its status word.
  * Outputs (any may be NULL), describing the position AFTER the move:
@@ -224,14 +224,15 @@ typedef struct {
   int32_t maxVisits;            /* SearchParams::maxVisits: visits of the root per move (incl. its own evaluation) */
   int32_t temperaturePlies;     /* plies played in proportion to visits (chosenMoveTemperature 1), afterwards the most visited move */
   int32_t autoRefill;           /* restart finished games with fresh ids before the next search */
-  int32_t pad_;
+  int32_t noCompaction;         /* 0 (default): on the bf16 path only the leaves that need the net are batched (terminal
+                                   visits take no row); 1: one row per game, idle rows evaluated and ignored */
   double cpuctExploration;      /* SearchParams::cpuctExploration (1.0) */
   double fpuReductionMax;       /* SearchParams::fpuReductionMax (0.2) */
   double rootFpuReductionMax;   /* SearchParams::rootFpuReductionMax (0.2) */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;
-  uint64_t batchRows;           /* rows sent through the evaluator (numGames per iteration) */
+  uint64_t batchRows;           /* rows sent through the evaluator */
 } kc_search_stats;
 /* handle == NULL selects the deterministic integer-hash evaluator (exact fp32 policy/value derived from the sit-hash),
  * which exists so that the search logic can be compared bit for bit with the CPU oracle; with a handle the leaves go

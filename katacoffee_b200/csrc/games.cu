@@ -499,7 +499,12 @@ int kc_games_features(kc_games* G, int layout, const int8_t* symmetry, float* pl
   return 0;
 }
 
-int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) {
+int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) { return kc::gamesEval(G, h, symmetry, nullptr); }
+
+}  // extern "C"
+
+namespace kc {
+int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev) {
   KC_CHECK(G && h, "kc_games_eval: null argument");
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const Geom& g = G->geom;
@@ -518,8 +523,11 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) {
     launchGames<false>(G, 2, 0, so, fo);
   }
   KC_CUDA(cudaGetLastError());
-  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr);
+  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr, nDev);
 }
+}  // namespace kc
+
+extern "C" {
 
 int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes, kc_stats* acc, float* msTotal) {
   KC_CHECK(G && plies > 0, "kc_games_run: bad argument");

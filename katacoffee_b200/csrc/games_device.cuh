@@ -215,7 +215,7 @@ __device__ __forceinline__ int stepGame(const D& dm, const Geom& g, GameRegs<typ
   legalMasks(dm, g, empty, lastCell, lastDirOf(s.misc), L);
   if(fl & 1) return -1;                         // finished, not refilled
   int dir = -1, cellPad = 0;
-  if(useForced) {
+  if(useForced && forcedMove != -2) {   // -2: "play the counter-RNG move" inside a forced-move batch
     if(forcedMove < 0) return -1;
     if(forcedMove >= 4 * dm.HW()) { illegal = true; return -1; }
     dir = forcedMove / dm.HW();

@@ -111,6 +111,7 @@ struct TrunkParams {
   const uint4* tiles; const uint8_t* wstream; const float* params;
   LayerDesc layers[MAX_LAYERS];
   int numLayers, numItems, n;
+  const int* nDev;   // if non-null: the number of rows is read from device memory (a batch compacted on the device)
   int NB, W, H, HW, stride, tileRowW;
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
@@ -258,7 +259,7 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
 //         Wv2 [96][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [32]
 template <class K>
 __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
-                             const uint8_t* sSym) {
+                             const uint8_t* sSym, const int nRows) {
   const int V2 = P.v2C;
   const float* g1s = P.params + L.pOff;
   const float* g1b = g1s + HEADC;
@@ -345,7 +346,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   if(c.e < P.NB * 4) {
     int b = c.e >> 2, o = c.e & 3;
     int game = gameBase + b;
-    if(game < P.n) {
+    if(game < nRows) {
       const float* Wm = (o < 2) ? Wv3 : Wsv3;
       int oo = o & 1;
       float acc = (o < 2) ? __ldg(b3 + oo) : __ldg(bsv3 + oo);
@@ -354,7 +355,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     }
   }
   int game = gameBase + c.b;
-  if(c.valid && game < P.n) {
+  if(c.valid && game < nRows) {
     const float* add = c.biasBuf + c.b * 96;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, own = 0.f;
 #pragma unroll
@@ -386,7 +387,7 @@ __device__ __forceinline__ bool elect_one() {
 
 template <class K>
 __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, const uint32_t sbase, const uint32_t bars,
-                                          const uint32_t tmemBase, volatile int* abortFlag) {
+                                          const uint32_t tmemBase, volatile int* abortFlag, const int numItems) {
   uint32_t slot = 0, phase = 0, itemCount = 0, chunkPhase = 0;
   const bool leader = elect_one();
   const uint32_t descHi = (128u >> 4) | (1u << 14);
@@ -394,7 +395,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
   const uint32_t ringLo0 = ((sbase + K::OFF_RING) & 0x3FFFFu) >> 4;
   const uint32_t barFull = bars + K::BAR_FULL * 8, barEmpty = bars + K::BAR_EMPTY * 8, barChunk = bars + (K::BAR_CHUNK + t * K::NCH) * 8;
   auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
-  for(int item = blockIdx.x; item < P.numItems; item += gridDim.x, itemCount++) {
+  for(int item = blockIdx.x; item < numItems; item += gridDim.x, itemCount++) {
     if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
     if(itemCount > 0 && !mbar_wait(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
     tc_fence_after();
@@ -473,6 +474,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
   const uint32_t bars = sbase + K::OFF_BAR;
   volatile int* abortFlag = P.abortFlag;
   uint8_t* sSym = smem + K::OFF_SYM;
+  const int nRows = P.nDev ? min(__ldg(P.nDev), P.n) : P.n;
+  const int numItems = P.nDev ? ((nRows + P.NB - 1) / P.NB + NT - 1) / NT : P.numItems;
 
   // ---- one-time setup ----
   for(int i = threadIdx.x; i < NT * K::ACT_BYTES / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     if(lane == 0) {
       uint32_t slot = 0, phase = 0, itemCount = 0;
       bool alive = true;
-      for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x, itemCount++) {
+      for(int item = blockIdx.x; item < numItems && alive; item += gridDim.x, itemCount++) {
         for(int t = 0; t < NT && alive; t++) {
           if(itemCount > 0) alive = mbar_wait(bars + (K::BAR_ACTFREE + t) * 8, (itemCount - 1) & 1, abortFlag, 11);
           if(!alive) break;
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     }
   } else if(warp >= 1 && warp <= NT) {
     // =========================== MMA issuers: one thread per tile ===========================
-    mmaIssuer<K>(P, warp - 1, sbase, bars, tmemBase, abortFlag);
+    mmaIssuer<K>(P, warp - 1, sbase, bars, tmemBase, abortFlag, numItems);
   } else if(warp < 4) {
     // idle (keeps the epilogue warps aligned to TMEM lane quadrants: warp % 4 == quadrant)
   } else {
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     c.v2buf = reinterpret_cast<float*>(smem + K::OFF_V2) + c.t * MAX_NB * MAX_V2;
     uint32_t layerCount = 0;
     bool alive = true;
-    for(int item = blockIdx.x; item < P.numItems && alive; item += gridDim.x) {
+    for(int item = blockIdx.x; item < numItems && alive; item += gridDim.x) {
       for(int l = 0; l < P.numLayers && alive; l++, layerCount++) {
         const LayerDesc L = P.layers[l];
         {
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
         tc_fence_after();
         if(L.epi == EPI_BN) epilogueBN<K>(P, L, c);
         else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
-        else epilogueHead<K>(P, L, c, item * NT + c.t, bars + (K::BAR_HEAD + c.t) * 8, sSym);
+        else epilogueHead<K>(P, L, c, item * NT + c.t, bars + (K::BAR_HEAD + c.t) * 8, sSym, nRows);
       }
     }
   }
@@ -887,7 +890,7 @@ int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev,
   return 0;
 }
 
-int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset) {
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset, const int* nDev) {
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
   TrunkParams P{};
@@ -899,6 +902,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   const int NT = T->cfg == 0 ? Cfg128::NT : Cfg192::NT;
   P.numItems = (numTiles + NT - 1) / NT;
   P.n = n;
+  P.nDev = nDev;
   P.tiles = (const uint4*)h->d_tiles + (size_t)(rowOffset / P.NB) * 2 * TILE_ROWS;
   P.sym = sym_dev ? sym_dev + rowOffset : nullptr; P.dstOfSrcRev = h->d_dstOfSrcRev;
   P.policy = h->d_policy + (size_t)rowOffset * 4 * P.HW; P.value = h->d_value + (size_t)rowOffset * 2;

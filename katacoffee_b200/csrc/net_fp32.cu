@@ -369,9 +369,9 @@ void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, c
   k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy, h->d_value, h->d_misc, legal_dev, status_dev, sitHash_dev, n,
                                                                  4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
 }
-int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev) {
+int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev) {
   h->lastN = n;
-  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev);
+  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, 0, nDev);
   return runFp32(h, n, stream, sym_dev);
 }
 

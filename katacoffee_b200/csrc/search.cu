@@ -47,6 +47,7 @@ struct SearchCfg {
   int temperaturePlies;
   int numGames;
   int autoRefill;
+  int compact;       // leaves that need the net are packed into a dense batch (slot = arrival order); 0: slot = game
   double cpuct, fpuRed, rootFpuRed;
   uint64_t seed;
 };
@@ -60,6 +61,8 @@ struct TreeMem {
   int* leafKind;          // [G] 0 idle, 1 new node (needs the net), 2 new terminal child, 3 revisit of a terminal child, 4 root evaluation
   double* leafValue;      // [G] result of a terminal leaf (white-positive)
   int* leafNextPla;       // [G] player to move at a new node
+  int* leafSlot;          // [G] row of the evaluation batch holding this game's leaf
+  int* evalCount;         // [1] rows of the current evaluation batch (compact mode)
   unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws
 };
 
@@ -187,9 +190,15 @@ __global__ void __launch_bounds__(128) k_select(const Geom g, const SearchCfg c,
   if(lane == 0) {
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
     t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
-    // the position handed to the evaluator (also for idle lanes: the batch is dense, their result is ignored)
-    leaf.black[gi] = (uint64_t)s.black; leaf.white[gi] = (uint64_t)s.white; leaf.hash0[gi] = s.h0; leaf.hash1[gi] = s.h1;
-    leaf.gameId[gi] = s.id; leaf.misc[gi] = s.misc;
+    const bool needsNet = kind == 1 || kind == 4;
+    // the position handed to the evaluator.  Compact mode: only leaves that need the net take a row, in arrival order
+    // (an evaluation does not depend on its row); otherwise row = game and idle rows are evaluated and ignored.
+    if(needsNet || !c.compact) {
+      const int slot = c.compact ? atomicAdd(t.evalCount, 1) : gi;
+      t.leafSlot[gi] = slot;
+      leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
+      leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
+    }
   }
 }
 
@@ -233,12 +242,13 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
   double v = t.leafValue[gi];
   int newIdx = -1;
   if(kind == 1 || kind == 4) {
-    v = __dsub_rn((double)winLoss[2 * (size_t)gi], (double)winLoss[2 * (size_t)gi + 1]);   // white-positive utility of the evaluation
+    const size_t row = (size_t)t.leafSlot[gi];
+    v = __dsub_rn((double)winLoss[2 * row], (double)winLoss[2 * row + 1]);   // white-positive utility of the evaluation
     newIdx = t.nodeCount[gi];
     if(newIdx >= c.maxNodes) return;   // cannot happen: one new node per visit, maxNodes == maxVisits
     NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P};
     for(int pos = lane; pos < c.P; pos += 32) {
-      nd.edgeW()[pos] = 0.0; nd.policy()[pos] = policy[(size_t)gi * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
+      nd.edgeW()[pos] = 0.0; nd.policy()[pos] = policy[row * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
     }
     if(lane == 0) { nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi]; nd.W() = v; t.nodeCount[gi] = newIdx + 1; }
   }
@@ -348,11 +358,12 @@ int runVisits(kc_search* S) {
   cudaStream_t st = Lf->stream;
   const int warpBlocks = (c.numGames * 32 + 127) / 128;
   for(int it = 0; it < c.maxVisits; it++) {
+    if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount, 0, 4, st));
     if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
     else k_select<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
     S->launches++;
     if(S->handle) {
-      if(kc_games_eval(Lf, S->handle, nullptr)) return 1;
+      if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount : nullptr)) return 1;
       kc::launchPostprocess(S->handle, c.numGames, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, S->d_policy, S->d_winLoss, S->d_misc, S->d_nnHash, st);
       S->launches += 3;
     } else {
@@ -384,6 +395,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.nodeStride = (32 + 21 * c.P + 15) / 16 * 16;
   c.maxNodes = p->maxVisits; c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
   c.numGames = numGames; c.autoRefill = p->autoRefill ? 1 : 0;
+  c.compact = (handleOrNull && kc::handleIsBf16(handleOrNull) && !p->noCompaction) ? 1 : 0;
   c.cpuct = p->cpuctExploration; c.fpuRed = p->fpuReductionMax; c.rootFpuRed = p->rootFpuReductionMax;
   c.seed = 0;
   const size_t n = (size_t)numGames;
@@ -396,6 +408,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CUDA(cudaMalloc(&S->tree.pathNode, n * MAX_PATH * 4)); KC_CUDA(cudaMalloc(&S->tree.pathPos, n * MAX_PATH));
   KC_CUDA(cudaMalloc(&S->tree.pathLen, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafKind, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.leafValue, n * 8)); KC_CUDA(cudaMalloc(&S->tree.leafNextPla, n * 4));
+  KC_CUDA(cudaMalloc(&S->tree.leafSlot, n * 4)); KC_CUDA(cudaMemset(S->tree.leafSlot, 0, n * 4));
+  KC_CUDA(cudaMalloc(&S->tree.evalCount, 4)); KC_CUDA(cudaMemset(S->tree.evalCount, 0, 4));
   KC_CUDA(cudaMalloc(&S->tree.stats, 64)); KC_CUDA(cudaMemset(S->tree.stats, 0, 64));
   KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
@@ -411,6 +425,7 @@ int kc_search_destroy(kc_search* S) {
   cudaStreamSynchronize(S->leaf->stream);
   cudaFree(S->tree.nodes); cudaFree(S->tree.nodeCount); cudaFree(S->tree.pathNode); cudaFree(S->tree.pathPos); cudaFree(S->tree.pathLen);
   cudaFree(S->tree.leafKind); cudaFree(S->tree.leafValue); cudaFree(S->tree.leafNextPla); cudaFree(S->tree.stats);
+  cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
   kc_games_destroy(S->root); kc_games_destroy(S->leaf);
@@ -497,7 +512,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
   if(acc) {
     acc->visits += hs[0]; acc->netEvals += hs[1]; acc->terminalVisits += hs[2]; acc->movesPlayed += hs[3];
     acc->gamesFinished += hs[4]; acc->blackWins += hs[5]; acc->whiteWins += hs[6]; acc->draws += hs[7];
-    acc->batchRows += (uint64_t)c.numGames * c.maxVisits * moves;
+    acc->batchRows += c.compact ? hs[1] : (uint64_t)c.numGames * c.maxVisits * moves;
   }
   return 0;
 }

@@ -208,7 +208,7 @@ void ko_postprocess(float* policy, int policySize, const uint32_t* legalMask, fl
  * evaluator that the CUDA search also implements, so trees can be compared exactly.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
-  int32_t maxVisits, temperaturePlies, autoRefill, pad_;
+  int32_t maxVisits, temperaturePlies, autoRefill, noCompaction;
   double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,

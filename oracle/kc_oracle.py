@@ -272,7 +272,7 @@ def postprocess(policy, legal_mask, value2, misc2, next_pla, temp=1.0):
 
 class SearchParams(C.Structure):
     """Same layout as kc_search_params (include/katacoffee_b200.h)."""
-    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("pad_", C.c_int32),
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32),
                 ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
 
 

@@ -696,5 +696,23 @@ def test_search_with_net_close_to_oracle(ctx, oracle):
     sb.reset(seed=seed)
     st, chosen, ms = sb.play(3)
     assert st.movesPlayed == 3 * G and st.visits == 3 * G * V and st.netEvals + st.terminalVisits == st.visits
+    # device-side batching: packing only the leaves that need the net into the batch changes nothing but the row an
+    # evaluation lands in -- trees and moves are identical to the one-row-per-game run, late in the game where many
+    # visits end in terminal children
+    res = []
+    for noc in (False, True):
+        sc = backend.Search(ctx, hb, G, W, H, 4, maxVisits=96, temperaturePlies=2, noCompaction=noc)
+        sc.reset(seed=11)
+        for _ in range(13):
+            sc.games.step()
+        sc.runVisits()
+        root = sc.readRoot()
+        stc, chosen, _ = sc.play(2)
+        res.append((root, chosen.copy(), (stc.visits, stc.netEvals, stc.terminalVisits, stc.batchRows)))
+        sc.close()
+    for k in ("rootVisits", "rootUtilitySum", "edgeVisits", "edgeUtilitySum", "policy", "order"):
+        assert (res[0][0][k] == res[1][0][k]).all(), k
+    assert (res[0][1] == res[1][1]).all() and res[0][2][:3] == res[1][2][:3]
+    assert res[0][2][2] > 0 and res[0][2][3] == res[0][2][1] < res[1][2][3]   # terminal visits took no batch row
     for x in (s, sb, h, hb, lm):
         x.close()
