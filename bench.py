@@ -143,6 +143,32 @@ def cpu_reference_run(positions_per_step, steps, warmup, threads):
     return tot_n / tot_t, tot_t / len(per_step) * 1e3, tot_n // len(per_step)
 
 
+def cpu_selfplay_run(threads, visits=24):
+    """The reference's own search loop restated (oracle/ko_search.cpp: one game, one thread, one position per net call)
+    with the fp32 direct-convolution forward, on all host threads at once.  Returns visits/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kc_oracle
+    from katacoffee_b200 import modeldesc
+    om = kc_oracle.Model(modeldesc.Model(NET, seed=1))
+    games = []
+    for i in range(threads):
+        g = kc_oracle.Game(W, H, WINLEN)
+        for _ in range(i % 8):
+            g.play(g.choose(SEED, i))
+        games.append(g)
+    done = [0] * threads
+
+    def work(i):
+        done[i] = int(kc_oracle.search_run(games[i], visits, model=om)["counters"][0])
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return sum(done) / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -316,7 +342,10 @@ def main():
             r0, _, _ = cpu_reference_run(128, 1, 0, threads)
             sample = int(min(8192, max(256, r0 * 10)))
             r, _, n = cpu_reference_run(sample, 1, 0, threads)
+            sp_visits_s = cpu_selfplay_run(threads)
             line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": threads, "kind": "port",
+                                    "selfplay_moves_per_s": sp_visits_s / args.visits, "selfplay_visits_per_s": sp_visits_s,
+                                    "selfplay_sample": f"{threads} games x 24 visits, oracle search + fp32 {NET} forward, one position per call",
                                     "sample": f"{n} positions: oracle rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward (Eigen-algorithm restatement), batch 4 per thread"}
         print(json.dumps(line), flush=True)
     for o in (games, handle, lm, ctx):
