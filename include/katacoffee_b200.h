@@ -132,6 +132,14 @@ int64_t kc_handle_launch_count(const kc_handle* h);
 /* Sum (ms) and count of the device durations of the trunk-kernel launches issued through this
  * handle since the previous call (CUDA events recorded on the launching stream); synchronises. */
 int kc_handle_trunk_time(kc_handle* h, float* sumMs, int* count);
+/* Diagnostic (handles created with KC_TRUNK_PROBE=1 in the environment): SM-clock timestamps of one layer boundary of
+ * the last trunk launch, CTA 0 / first work item / tile 0, out[32]: 0 last MMA of layer 5 issued, 1 epilogue saw the
+ * accumulator barrier, 2 first TMEM load done, 3 first 16 channels published, 7 last published, 6 issuer of layer 6
+ * starts waiting, 4 its wait is over, 5 its first MMAs are issued, 8..14 the MMAs of its input chunks 0..6 are issued,
+ * 15 its last MMA is issued; item boundary: 16 head conv issued, 17 head epilogue starts, 18 it has released TMEM,
+ * 19 it ends, 20 issuer starts the next item, 21 has issued its layer 0, 22 epilogue sees layer 0, 23 issuer has
+ * the first chunk of layer 1; 24..29 phases inside the head epilogue. */
+int kc_handle_trunk_probe(kc_handle* h, int64_t* out);
 /* Self-test of the tcgen05 descriptor conventions the trunk kernel relies on: D[128][N] =
  * A[shift:shift+128][K] * B[N][K]^T on the tensor core (A, B bf16 bit patterns, D fp32).  ws != 0 uses the
  * weight-stationary form: D gets two results [2][128][N], for row shifts `shift` and `shift+1`, the second MMA

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "kc_handle_read_outputs": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "kc_handle_launch_count": (C.c_int64, [vp]),
     "kc_handle_trunk_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "kc_handle_trunk_probe": (C.c_int, [vp, vp]),
     "kc_selftest_umma": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "kc_test_conv": (C.c_int, [vp, C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "kc_test_batchnorm": (C.c_int, [vp, C.POINTER(BNDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

@@ -30,6 +30,7 @@ struct kc_handle {
   // bf16 path
   void* d_tiles = nullptr;           // [numTiles][2][128] x 16 B input tiles
   int numTilesAlloc = 0;
+  long long* d_dbg = nullptr;        // KC_TRUNK_PROBE=1: timeline of one layer boundary (kc_handle_trunk_probe)
   int* d_abort = nullptr;            // set by the trunk kernel if an mbarrier wait timed out
   int64_t launches = 0;
   float lastTrunkMs = 0.f;

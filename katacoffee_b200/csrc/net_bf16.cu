@@ -48,15 +48,21 @@ constexpr int MAX_V2 = 128;
 // Compile-time shape of one trunk-kernel instantiation.  <128, 2, 7>: trunks up to 128 channels, two activation tiles
 // per CTA (TMEM: 2 x (T 128 + S 128) columns).  <192, 1, 6>: trunks up to 192 channels (b15c192), one tile per CTA
 // (TMEM: T 192 + S 192 columns of the 512 allocated).
-template <int MAXC_, int NT_, int NSTAGES_>
+// PAIR: the kernel runs as clusters of two CTAs on one TPC and every MMA is a tcgen05 cta_group::2 instruction (M = 256:
+// 128 activation rows from each CTA, the weight block split in halves between the two shared memories), so each SM reads
+// and stages only half of the weights: shared-memory operand traffic drops from 128 to 96 B/clk and the L2 -> SM weight
+// stream halves.
+template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false>
 struct TrunkCfg {
   static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_;
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int NCTA = PAIR ? 2 : 1;
   static constexpr int NCH = MAXC / 16;                       // 16-channel chunks the epilogue publishes
   static constexpr int MAXG = MAXC / 4 < 32 ? 32 : MAXC / 3;  // gpool channels: 32 (c128), 64 (c192)
   static constexpr int POOLW = 3 * MAXG;                      // pooled vector per board (>= 96 for the heads)
   static constexpr int THREADS = 128 + NT * 128;              // warp 0 TMA producer, 1..NT MMA issuers, 4.. epilogue (4 warps per tile)
   static constexpr int ACT_BYTES = (MAXC / 8) * CHUNK_BYTES;
-  static constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAXC * 32;
+  static constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAXC * 32 / NCTA;   // per CTA
   static constexpr int OFF_ACT = 0;
   static constexpr int OFF_RING = OFF_ACT + NT * ACT_BYTES;
   static constexpr int OFF_SCR = OFF_RING + NSTAGES * STAGE_BYTES;
@@ -69,7 +75,8 @@ struct TrunkCfg {
   static constexpr int OFF_BAR = OFF_PAR + NT * 2 * 2 * MAXC * 4; // folded BN, staged while the tensor core is still busy with it
   // barriers (8 bytes each)
   static constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + NT,
-                       BAR_IN = BAR_ACTFREE + NT, BAR_HEAD = BAR_IN + NT, BAR_CHUNK = BAR_HEAD + NT, NUM_BARS = BAR_CHUNK + NT * NCH;
+                       BAR_IN = BAR_ACTFREE + NT, BAR_HEAD = BAR_IN + NT, BAR_CHUNK = BAR_HEAD + NT, BAR_FULLP = BAR_CHUNK + NT * NCH,
+                       BAR_INP = BAR_FULLP + NSTAGES, NUM_BARS = BAR_INP + NT;   // FULLP / INP: the peer CTA's weights / input tile landed
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM = OFF_TMEM + 16;
   static_assert(NT * 2 * MAXC <= 512, "TMEM: every tile needs a trunk region and a block-internal region");
@@ -77,6 +84,7 @@ struct TrunkCfg {
   static_assert(POOLW >= 96, "the heads pool 32 channels three ways");
 };
 using Cfg128 = TrunkCfg<128, 2, 7>;
+using Cfg128P = TrunkCfg<128, 2, 14, true>;
 using Cfg192 = TrunkCfg<192, 1, 6>;
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
@@ -99,6 +107,7 @@ constexpr int MAX_LAYERS = 48;   // 1 + 2*blocks + 1; the table travels in the k
 struct TrunkProgram {
   std::vector<LayerDesc> layers;
   uint8_t* d_w = nullptr;
+  uint8_t* d_wPair = nullptr;   // the same stream with every stage split in halves of the output channels (pair mode)
   float* d_params = nullptr;
   LayerDesc* d_layers = nullptr;
   size_t wBytes = 0;
@@ -116,6 +125,7 @@ struct TrunkParams {
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
   int* abortFlag;
+  long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
   float poolScale1, poolScale2, invHW;
   int v2C;
 };
@@ -136,9 +146,11 @@ struct EpiCtx {
   int b, cell;      // board within tile, dense cell index
   uint32_t tmemLane;  // tmem base + lane offset + tile column offset
   uint8_t* act;     // this tile's activation buffer
-  uint32_t barChunk;  // smem address of actReady[t][0]
+  uint32_t barChunk;  // address of actReady[t][0] (pair mode: shared::cluster address in the leader CTA)
+  bool remote;        // pair mode, peer CTA: barriers the MMA issuer waits on live in the leader
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
-  const float* par;  // staged folded BN of the layer being finished: scale[K::MAXC] | bias[K::MAXC]
+  const float* par;  // staged folded BN of the layer being finished: scale[MAXC] | bias[MAXC]
+  long long* dbg;    // non-null for the one thread / layer whose timeline is recorded
 };
 
 // folded BN + ReLU + mask for 16 columns -> two 16-byte chunks of the activation tile
@@ -160,28 +172,66 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
   *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   *reinterpret_cast<uint4*>(dst + CHUNK_BYTES) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   fence_proxy_async();
-  mbar_arrive(c.barChunk + cc * 8);
+  __syncwarp();
+  if((c.r & 31) == 0) { if(c.remote) mbar_arrive_cluster(c.barChunk + cc * 8); else mbar_arrive(c.barChunk + cc * 8); }
 }
 
 // per-board pooling of 16 channels held one row per thread: writes sum and max per (board, channel)
 // into outSum/outMax[b*16 + j] (shared), using the tile's scratch.  All 128 threads of the tile call it.
-__device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float* sums, float* maxs) {
+// Two threads per (board, channel): even lane = upper rows, odd lane = lower rows, combined by one shuffle; the even lane
+// (c.e even, c.e >> 1 = board*16 + channel < NB*16) returns the board's sum and max.
+__device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float& sum, float& mx) {
+  named_bar_sync(1 + c.t, 128);   // the previous use of the scratch has been read
 #pragma unroll
   for(int j = 0; j < 16; j++) c.scr[c.r * SCR_STRIDE + j] = g[j];
   named_bar_sync(1 + c.t, 128);
-  if(c.e < P.NB * 16) {
-    int b = c.e >> 4, j = c.e & 15;
-    float s = 0.f, m = -1.0f;   // eigenbackend.cpp:145: max starts at -1
-    for(int y = 0; y < P.H; y++)
+  const int o = c.e >> 1, part = c.e & 1;
+  const int b = o >> 4, j = o & 15;
+  float s = 0.f, m = -1.0f;   // eigenbackend.cpp:145: max starts at -1
+  if(b < P.NB) {
+    const int yMid = (P.H + 1) >> 1;
+    const int y0 = part ? yMid : 0, y1 = part ? P.H : yMid;
+    for(int y = y0; y < y1; y++) {
+      const float* rowp = c.scr + (y * P.tileRowW + b * P.stride) * SCR_STRIDE + j;
       for(int x = 0; x < P.W; x++) {
-        float v = c.scr[(y * P.tileRowW + b * P.stride + x) * SCR_STRIDE + j];
+        float v = rowp[x * SCR_STRIDE];
         s += v;
         m = fmaxf(m, v);
       }
-    sums[c.e] = s;
-    maxs[c.e] = m;
+    }
   }
-  named_bar_sync(1 + c.t, 128);
+  const float s2 = __shfl_xor_sync(0xffffffffu, s, 1), m2 = __shfl_xor_sync(0xffffffffu, m, 1);
+  sum = s + s2;       // even lane: upper rows + lower rows
+  mx = fmaxf(m, m2);
+}
+
+// acc[b] = sum_k in[b*inStride + k] * W[k*OC + oc] for the NB boards of a tile, k ascending (same summation order as a plain
+// loop), with the weight loads issued 16 at a time: these tiny matmuls are pure L2 latency, not bandwidth.  Kdim % 16 == 0.
+__device__ __forceinline__ void pooledMatmul(const float* in, int inStride, const float* __restrict__ W, int Kdim, int OC, int oc, int NB,
+                                             float acc[MAX_NB]) {
+#pragma unroll
+  for(int b = 0; b < MAX_NB; b++) acc[b] = 0.f;
+  int k0 = 0;
+  for(; k0 + 32 <= Kdim; k0 += 32) {
+    float w[32];
+#pragma unroll
+    for(int j = 0; j < 32; j++) w[j] = __ldg(W + (size_t)(k0 + j) * OC + oc);
+#pragma unroll
+    for(int j = 0; j < 32; j++)
+#pragma unroll
+      for(int b = 0; b < MAX_NB; b++)
+        if(b < NB) acc[b] = fmaf(in[b * inStride + k0 + j], w[j], acc[b]);
+  }
+  for(; k0 < Kdim; k0 += 16) {
+    float w[16];
+#pragma unroll
+    for(int j = 0; j < 16; j++) w[j] = __ldg(W + (size_t)(k0 + j) * OC + oc);
+#pragma unroll
+    for(int j = 0; j < 16; j++)
+#pragma unroll
+      for(int b = 0; b < MAX_NB; b++)
+        if(b < NB) acc[b] = fmaf(in[b * inStride + k0 + j], w[j], acc[b]);
+  }
 }
 
 template <class K>
@@ -194,12 +244,14 @@ __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCt
   uint32_t ra[16], rb[16];
   tmem_ld16_issue(src, ra);
   tmem_ld16_wait(ra);
+  if(c.dbg) c.dbg[2] = clock64();
   for(int cc = 0; cc < nch; cc += 2) {
     float v[16];
     if(cc + 1 < nch) tmem_ld16_issue(src + (cc + 1) * 16, rb);
 #pragma unroll
     for(int i = 0; i < 16; i++) v[i] = __uint_as_float(ra[i]);
     publish16(c, cc, v, scale, bias, nullptr);
+    if(c.dbg && cc == 0) c.dbg[3] = clock64();
     if(cc + 1 >= nch) break;
     tmem_ld16_wait(rb);
     if(cc + 2 < nch) tmem_ld16_issue(src + (cc + 2) * 16, ra);
@@ -208,43 +260,44 @@ __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCt
     publish16(c, cc + 1, v, scale, bias, nullptr);
     if(cc + 2 < nch) tmem_ld16_wait(ra);
   }
+  if(c.dbg) c.dbg[7] = clock64();
 }
 
 // params: gpoolBN scale[G] bias[G] | Wg [3G][R] | midBN scale[R] bias[R]
 template <class K>
 __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c) {
   const int R = L.epiC, G = L.gpoolC;
-  const float* gs = P.params + L.pOff;
-  const float* gb = gs + G;
-  const float* Wg = gb + G;
-  const float* ms = c.par;            // midBN staged in shared memory
-  const float* mb = c.par + K::MAXC;
+  const float* Wg = P.params + L.pOff + 2 * G;
+  const float* ms = c.par;            // staged in shared memory before the accumulator wait: midBN scale[R], then gpoolBN scale[G]
+  const float* mb = c.par + K::MAXC;  //                                                       midBN bias[R],  then gpoolBN bias[G]
+  const float* gs = ms + R;
+  const float* gb = mb + R;
   uint32_t src = c.tmemLane + K::MAXC;   // region S
   float* pooled = c.poolA;           // [NB][3G]
-  __shared__ float sSum[2][MAX_NB * 16], sMax[2][MAX_NB * 16];
   for(int half = 0; half < G / 16; half++) {
     float v[16], g[16];
     tmem_ld16(src + R + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], __ldg(gs + half * 16 + j), __ldg(gb + half * 16 + j)), 0.f);
+      float a = fmaxf(fmaf(v[j], gs[half * 16 + j], gb[half * 16 + j]), 0.f);
       g[j] = c.valid ? a : 0.f;
     }
-    poolBoards16(P, c, g, sSum[c.t], sMax[c.t]);
-    if(c.e < P.NB * 16) {
-      int b = c.e >> 4, j = c.e & 15;
-      float mean = sSum[c.t][c.e] * P.invHW;
+    float sum, mx;
+    poolBoards16(P, c, g, sum, mx);
+    if(!(c.e & 1) && (c.e >> 1) < P.NB * 16) {
+      int b = c.e >> 5, j = (c.e >> 1) & 15;
+      float mean = sum * P.invHW;
       pooled[b * 3 * G + half * 16 + j] = mean;
       pooled[b * 3 * G + G + half * 16 + j] = mean * P.poolScale1;
-      pooled[b * 3 * G + 2 * G + half * 16 + j] = sMax[c.t][c.e];
+      pooled[b * 3 * G + 2 * G + half * 16 + j] = mx;
     }
   }
   named_bar_sync(1 + c.t, 128);
-  for(int idx = c.e; idx < P.NB * R; idx += 128) {
-    int b = idx / R, oc = idx - b * R;
-    float acc = 0.f;
-    for(int k = 0; k < 3 * G; k++) acc = fmaf(pooled[b * 3 * G + k], __ldg(Wg + k * R + oc), acc);
-    c.biasBuf[b * K::MAXC + oc] = acc;
+  for(int oc = c.e; oc < R; oc += 128) {
+    float acc[MAX_NB];
+    pooledMatmul(pooled, 3 * G, Wg, 3 * G, R, oc, P.NB, acc);
+#pragma unroll
+    for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[b * K::MAXC + oc] = acc[b];
   }
   named_bar_sync(1 + c.t, 128);
   const float* add = c.biasBuf + c.b * K::MAXC;
@@ -255,65 +308,91 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
   }
 }
 
-// params: g1BN s[32] b[32] | Wpb [96][32] | p1BN s[32] b[32] | W2 [32][4] | v1BN s[32] b[32] |
-//         Wv2 [96][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [32]
-template <class K>
-__device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
-                             const uint8_t* sSym, const int nRows) {
+__shared__ float sW3[2][4][MAX_V2 + 1];   // value / misc output matrices of the head, [tile][output][k], [V2] = bias
+__shared__ float sHeadPar[2][11 * HEADC + MAX_V2];   // small head parameters per tile (layout in epilogueHead), staged once per kernel
+
+__device__ __forceinline__ void stageHeadParams(const TrunkParams& P, const LayerDesc& L, int e, int t, float* par) {
   const int V2 = P.v2C;
-  const float* g1s = P.params + L.pOff;
-  const float* g1b = g1s + HEADC;
-  const float* Wpb = g1b + HEADC;
-  const float* p1s = Wpb + 96 * HEADC;
-  const float* p1b = p1s + HEADC;
-  const float* W2 = p1b + HEADC;
-  const float* v1s = W2 + HEADC * 4;
-  const float* v1b = v1s + HEADC;
-  const float* Wv2 = v1b + HEADC;
+  const float* base = P.params + L.pOff;
+  const float* p1s = base + 2 * HEADC + 96 * HEADC;              // p1BN s, b | W2 | v1BN s, b: 256 contiguous floats
+  const float* Wv2 = p1s + 8 * HEADC;
   const float* b2 = Wv2 + 96 * V2;
   const float* Wv3 = b2 + V2;
   const float* b3 = Wv3 + V2 * 2;
   const float* Wsv3 = b3 + 2;
   const float* bsv3 = Wsv3 + V2 * 2;
   const float* Wown = bsv3 + 2;
+  if(e < 2 * HEADC) par[e] = __ldg(base + e);
+  for(int i = e; i < 8 * HEADC; i += 128) par[2 * HEADC + i] = __ldg(p1s + i);
+  if(e < HEADC) par[10 * HEADC + e] = __ldg(Wown + e);
+  for(int i = e; i < V2; i += 128) par[11 * HEADC + i] = __ldg(b2 + i);
+  for(int i = e; i < 4 * V2; i += 128) {
+    const int o = i / V2, k = i - o * V2;
+    sW3[t][o][k] = __ldg(((o < 2) ? Wv3 : Wsv3) + k * 2 + (o & 1));
+  }
+  if(e < 4) sW3[t][e][V2] = __ldg(((e < 2) ? b3 : bsv3) + (e & 1));
+}
+
+// params: g1BN s[32] b[32] | Wpb [96][32] | p1BN s[32] b[32] | W2 [32][4] | v1BN s[32] b[32] |
+//         Wv2 [96][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [32]
+template <class K>
+__device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
+                             const uint8_t* sSym, const int nRows) {
+  const int V2 = P.v2C;
+  // small parameters were staged in shared memory before the accumulator wait (stageHeadParams): layout of c.par
+  //   [0,32) g1BN s | [32,64) g1BN b | [64,96) p1BN s | [96,128) p1BN b | [128,256) W2 [32][4] | [256,288) v1BN s | [288,320) v1BN b |
+  //   [320,352) Wown | [352,352+V2) b2 ;  sW3[tile][o][k] = value / misc output matrices, [o][V2] = their biases
+  const float* g1s = c.par;
+  const float* g1b = c.par + 32;
+  const float* p1s = c.par + 64;
+  const float* p1b = c.par + 96;
+  const float* W2 = c.par + 128;
+  const float* v1s = c.par + 256;
+  const float* v1b = c.par + 288;
+  const float* Wown = c.par + 320;
+  const float* b2 = c.par + 352;
+  const float* Wpb = P.params + L.pOff + 2 * HEADC;
+  const float* Wv2 = Wpb + 96 * HEADC + 2 * HEADC + 4 * HEADC + 2 * HEADC;
   uint32_t src = c.tmemLane + K::MAXC;
-  __shared__ float sSum[2][MAX_NB * 16], sMax[2][MAX_NB * 16];
   float* pooledG = c.poolA;   // [NB][96]
   float* pooledV = c.poolB;   // [NB][96]
   float v1a[HEADC];
+  const bool hp = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
+  if(hp) P.dbg[24] = clock64();
+  const bool poolOut = !(c.e & 1) && (c.e >> 1) < P.NB * 16;
+  const int pb = c.e >> 5, pj = (c.e >> 1) & 15;
   // g1 -> BN -> ReLU -> gpool (eigenbackend.cpp:1290-1291) ; v1 -> BN -> ReLU -> value pool (:1364-1366)
   for(int half = 0; half < 2; half++) {
-    float v[16], g[16];
+    float v[16], g[16], sum, mx;
     tmem_ld16(src + HEADC + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], __ldg(g1s + half * 16 + j), __ldg(g1b + half * 16 + j)), 0.f);
+      float a = fmaxf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), 0.f);
       g[j] = c.valid ? a : 0.f;
     }
-    poolBoards16(P, c, g, sSum[c.t], sMax[c.t]);
-    if(c.e < P.NB * 16) {
-      int b = c.e >> 4, j = c.e & 15;
-      float mean = sSum[c.t][c.e] * P.invHW;
-      pooledG[b * 96 + half * 16 + j] = mean;
-      pooledG[b * 96 + 32 + half * 16 + j] = mean * P.poolScale1;
-      pooledG[b * 96 + 64 + half * 16 + j] = sMax[c.t][c.e];
+    poolBoards16(P, c, g, sum, mx);
+    if(poolOut) {
+      float mean = sum * P.invHW;
+      pooledG[pb * 96 + half * 16 + pj] = mean;
+      pooledG[pb * 96 + 32 + half * 16 + pj] = mean * P.poolScale1;
+      pooledG[pb * 96 + 64 + half * 16 + pj] = mx;
     }
     tmem_ld16(src + 2 * HEADC + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], __ldg(v1s + half * 16 + j), __ldg(v1b + half * 16 + j)), 0.f);
+      float a = fmaxf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), 0.f);
       g[j] = c.valid ? a : 0.f;
       v1a[half * 16 + j] = g[j];
     }
-    poolBoards16(P, c, g, sSum[c.t], sMax[c.t]);
-    if(c.e < P.NB * 16) {
-      int b = c.e >> 4, j = c.e & 15;
-      float mean = sSum[c.t][c.e] * P.invHW;
-      pooledV[b * 96 + half * 16 + j] = mean;
-      pooledV[b * 96 + 32 + half * 16 + j] = mean * P.poolScale1;
-      pooledV[b * 96 + 64 + half * 16 + j] = mean * P.poolScale2;
+    poolBoards16(P, c, g, sum, mx);
+    if(poolOut) {
+      float mean = sum * P.invHW;
+      pooledV[pb * 96 + half * 16 + pj] = mean;
+      pooledV[pb * 96 + 32 + half * 16 + pj] = mean * P.poolScale1;
+      pooledV[pb * 96 + 64 + half * 16 + pj] = mean * P.poolScale2;
     }
   }
+  if(hp) P.dbg[25] = clock64();
   float p1[HEADC];
   {
     float v[16];
@@ -326,44 +405,60 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
   // all TMEM reads of this tile are done: the MMA warp may overwrite region S for the next item
   tc_fence_before();
-  mbar_arrive(barHead);
+  __syncwarp();
+  if((c.r & 31) == 0) { if(c.remote) mbar_arrive_cluster(barHead); else mbar_arrive(barHead); }
+  if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0) P.dbg[18] = clock64();
   named_bar_sync(1 + c.t, 128);
   // pooled matmuls: policy bias (NB*32 outputs) and v2 (NB*V2 outputs)
-  if(c.e < P.NB * HEADC) {
-    int b = c.e / HEADC, oc = c.e % HEADC;
-    float acc = 0.f;
-    for(int k = 0; k < 96; k++) acc = fmaf(pooledG[b * 96 + k], __ldg(Wpb + k * HEADC + oc), acc);
-    c.biasBuf[b * 96 + oc] = acc;
-  }
-  for(int idx = c.e; idx < P.NB * V2; idx += 128) {
-    int b = idx / V2, oc = idx - b * V2;
-    float acc = 0.f;
-    for(int k = 0; k < 96; k++) acc = fmaf(pooledV[b * 96 + k], __ldg(Wv2 + k * V2 + oc), acc);
-    c.v2buf[b * MAX_V2 + oc] = fmaxf(acc + __ldg(b2 + oc), 0.f);
-  }
-  named_bar_sync(1 + c.t, 128);
-  const int gameBase = tileIndex * P.NB;
-  if(c.e < P.NB * 4) {
-    int b = c.e >> 2, o = c.e & 3;
-    int game = gameBase + b;
-    if(game < nRows) {
-      const float* Wm = (o < 2) ? Wv3 : Wsv3;
-      int oo = o & 1;
-      float acc = (o < 2) ? __ldg(b3 + oo) : __ldg(bsv3 + oo);
-      for(int k = 0; k < V2; k++) acc = fmaf(c.v2buf[b * MAX_V2 + k], __ldg(Wm + k * 2 + oo), acc);
-      if(o < 2) P.value[(size_t)game * 2 + oo] = acc; else P.misc[(size_t)game * 2 + oo] = acc;
+  if(hp) P.dbg[26] = clock64();
+  // threads 0..31: policy bias column oc; threads 32..127: v2 columns -- both matmuls in flight at once
+  if(c.e < HEADC) {
+    float acc[MAX_NB];
+    pooledMatmul(pooledG, 96, Wpb, 96, HEADC, c.e, P.NB, acc);
+#pragma unroll
+    for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[b * 96 + c.e] = acc[b];
+  } else {
+    for(int oc = c.e - HEADC; oc < V2; oc += 128 - HEADC) {
+      float acc[MAX_NB];
+      pooledMatmul(pooledV, 96, Wv2, 96, V2, oc, P.NB, acc);
+      const float bias2 = b2[oc];
+#pragma unroll
+      for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = fmaxf(acc[b] + bias2, 0.f);
     }
   }
+  if(hp) P.dbg[27] = clock64();
+  named_bar_sync(1 + c.t, 128);
+  if(hp) P.dbg[28] = clock64();
+  const int gameBase = tileIndex * P.NB;
+  {
+    // value / misc outputs: 8 lanes per (board, output), each a slice of k, combined by an xor butterfly
+    const int q = c.e >> 3, seg = c.e & 7;
+    const int b = q >> 2, o = q & 3;
+    float acc = 0.f;
+    if(b < P.NB) {
+      const int kn = V2 >> 3;
+      for(int k = seg * kn; k < (seg + 1) * kn; k++) acc = fmaf(c.v2buf[b * MAX_V2 + k], sW3[c.t][o][k], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    const int game = gameBase + b;
+    if(seg == 0 && b < P.NB && game < nRows) {
+      acc += sW3[c.t][o][V2];
+      if(o < 2) P.value[(size_t)game * 2 + (o & 1)] = acc; else P.misc[(size_t)game * 2 + (o & 1)] = acc;
+    }
+  }
+  if(hp) P.dbg[29] = clock64();
   int game = gameBase + c.b;
   if(c.valid && game < nRows) {
     const float* add = c.biasBuf + c.b * 96;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, own = 0.f;
 #pragma unroll
     for(int k = 0; k < HEADC; k++) {
-      float a = fmaxf(fmaf(p1[k] + add[k], __ldg(p1s + k), __ldg(p1b + k)), 0.f);
-      float4 w = __ldg(reinterpret_cast<const float4*>(W2) + k);
+      float a = fmaxf(fmaf(p1[k] + add[k], p1s[k], p1b[k]), 0.f);
+      float4 w = *(reinterpret_cast<const float4*>(W2) + k);
       o0 = fmaf(a, w.x, o0); o1 = fmaf(a, w.y, o1); o2 = fmaf(a, w.z, o2); o3 = fmaf(a, w.w, o3);
-      own = fmaf(v1a[k], __ldg(Wown + k), own);
+      own = fmaf(v1a[k], Wown[k], own);
     }
     int s = P.sym ? P.sym[game] : 0;
     int dst = sSym[s * P.HW + c.cell];
@@ -394,38 +489,57 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
   const uint32_t aLo0 = (((sbase + K::OFF_ACT + t * K::ACT_BYTES + HALO_ROWS * 16) & 0x3FFFFu) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
   const uint32_t ringLo0 = ((sbase + K::OFF_RING) & 0x3FFFFu) >> 4;
   const uint32_t barFull = bars + K::BAR_FULL * 8, barEmpty = bars + K::BAR_EMPTY * 8, barChunk = bars + (K::BAR_CHUNK + t * K::NCH) * 8;
+  const uint32_t barFullP = bars + K::BAR_FULLP * 8;
   auto desc = [descHi](uint32_t lo) { return ((uint64_t)descHi << 32) | lo; };
-  for(int item = blockIdx.x; item < numItems; item += gridDim.x, itemCount++) {
+  // pair mode: this is the leader CTA; one MMA covers tile t of both CTAs, barriers carry both CTAs' arrivals
+  auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr(K::PAIR) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+  };
+  auto commit = [&](uint32_t bar) { if constexpr(K::PAIR) umma_commit_2cta(bar, 3); else umma_commit(bar); };
+  auto waitc = [&](uint32_t bar, uint32_t parity, int code) {   // barriers that guard data written by threads (of either CTA)
+    return mbar_wait(bar, parity, abortFlag, code);
+  };
+  const int itemStep = K::PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  for(int item = K::PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x; item < numItems; item += itemStep, itemCount++) {   // pair mode: item = item pair
     if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
-    if(itemCount > 0 && !mbar_wait(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, abortFlag, 22)) return;
+    if(K::PAIR && !waitc(bars + (K::BAR_INP + t) * 8, itemCount & 1, 26)) return;
+    if(itemCount > 0 && !waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
     tc_fence_after();
+    if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) P.dbg[20] = clock64();
     for(int l = 0; l < P.numLayers; l++) {
       const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
-      const uint32_t idesc = idesc_bf16_f32(128, N);
+      const uint32_t idesc = idesc_bf16_f32(128 * K::NCTA, N);
       const uint32_t d = tmemBase + t * (2 * K::MAXC) + (P.layers[l].outSel ? K::MAXC : 0);
-      const uint32_t bStep = 2 * N;                    // one K-step of weights = N*32 bytes
-      const uint32_t bLbo = (uint32_t)N << 16;         // LBO = N*16 bytes
+      const uint32_t bStep = 2 * N / K::NCTA;                    // one K-step of weights = N*32 bytes (per CTA: its half of the rows)
+      const uint32_t bLbo = (uint32_t)(N / K::NCTA) << 16;       // LBO = rows*16 bytes
       uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
       if(ntaps == 9) {
         const int nchunks = nk / 9;
         for(int cc = 0; cc < nchunks; cc++) {
+          const bool probe = P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && cc == 0 && leader;
+          if(probe) P.dbg[6] = clock64();
           if(l > 0) {
             const uint32_t bit = 1u << cc;
-            if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
+            if(!waitc(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, 24)) return;
             chunkPhase ^= bit;
           }
+          if(probe) P.dbg[4] = clock64();
+          if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 1 && cc == 0 && leader) P.dbg[23] = clock64();
           const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
 #pragma unroll
           for(int dy = 0; dy < 3; dy++) {
             if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+            if(K::PAIR && !mbar_wait(barFullP + slot * 8, phase, abortFlag, 27)) return;
             tc_fence_after();
             const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
             const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
             if(leader) {
-              umma_bf16(d, desc(aLoR), desc(bLo), idesc, accum);
-              umma_bf16(d, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
-              umma_bf16(d, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
-              umma_commit(barEmpty + slot * 8);
+              mma(d, desc(aLoR), desc(bLo), idesc, accum);
+              mma(d, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
+              mma(d, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
+              commit(barEmpty + slot * 8);
+              if(probe && dy == 0) P.dbg[5] = clock64();
+              if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && dy == 2 && cc < 7) P.dbg[8 + cc] = clock64();
             }
             __syncwarp();
             accum = 1u;
@@ -437,28 +551,33 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
         const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
         for(int s = 0; s < nst; s++) {
           if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
+          if(K::PAIR && !mbar_wait(barFullP + slot * 8, phase, abortFlag, 27)) return;
           const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
           const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
           for(int kk = 0; kk < ks; kk++) {
             const int cc = s * KSTEPS_PER_STAGE + kk;
             if(l > 0) {
               const uint32_t bit = 1u << cc;
-              if(!mbar_wait(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, abortFlag, 24)) return;
+              if(!waitc(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, 24)) return;
               chunkPhase ^= bit;
             }
             tc_fence_after();
-            if(leader) umma_bf16(d, desc(aLo0 + cc * (2 * CHUNK_BYTES >> 4)), desc(bLo + kk * bStep), idesc, accum);
+            if(leader) mma(d, desc(aLo0 + cc * (2 * CHUNK_BYTES >> 4)), desc(bLo + kk * bStep), idesc, accum);
             __syncwarp();
             accum = 1u;
           }
-          if(leader) umma_commit(barEmpty + slot * 8);
+          if(leader) commit(barEmpty + slot * 8);
           __syncwarp();
           if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
         }
       }
       if(leader) {
-        umma_commit(bars + (K::BAR_ACC + t) * 8);
-        if(l == P.numLayers - 1) umma_commit(bars + (K::BAR_ACTFREE + t) * 8);
+        commit(bars + (K::BAR_ACC + t) * 8);
+        if(l == P.numLayers - 1) commit(bars + (K::BAR_ACTFREE + t) * 8);
+        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 5) P.dbg[0] = clock64();
+        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6) P.dbg[15] = clock64();
+        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == P.numLayers - 1) P.dbg[16] = clock64();
+        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 0) P.dbg[21] = clock64();
       }
       __syncwarp();
     }
@@ -476,32 +595,47 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
   uint8_t* sSym = smem + K::OFF_SYM;
   const int nRows = P.nDev ? min(__ldg(P.nDev), P.n) : P.n;
   const int numItems = P.nDev ? ((nRows + P.NB - 1) / P.NB + NT - 1) / NT : P.numItems;
+  // work distribution: a "unit" is what one CTA (or one CTA pair) takes per round; in pair mode the two CTAs of a cluster
+  // take the two items of a unit and run the same number of rounds (the odd item out is a ghost: its tiles are read
+  // from the last real item, its outputs land beyond nRows and are dropped)
+  const uint32_t rank = K::PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = K::PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x, unitStep = K::PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int numUnits = K::PAIR ? (numItems + 1) / 2 : numItems;
+  auto itemOf = [&](int unit) { return K::PAIR ? 2 * unit + (int)rank : unit; };
 
   // ---- one-time setup ----
   for(int i = threadIdx.x; i < NT * K::ACT_BYTES / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
   for(int i = threadIdx.x; i < 8 * P.HW; i += K::THREADS) sSym[i] = P.dstOfSrcRev[i];
   if(threadIdx.x == 0) {
-    for(int i = 0; i < K::NSTAGES; i++) { mbar_init(bars + (K::BAR_FULL + i) * 8, 1); mbar_init(bars + (K::BAR_EMPTY + i) * 8, NT); }   // every MMA issuer releases a slot
+    for(int i = 0; i < K::NSTAGES; i++) {
+      mbar_init(bars + (K::BAR_FULL + i) * 8, 1); mbar_init(bars + (K::BAR_EMPTY + i) * 8, NT);   // every MMA issuer releases a slot
+      mbar_init(bars + (K::BAR_FULLP + i) * 8, 1);
+    }
     for(int t = 0; t < NT; t++) {
       mbar_init(bars + (K::BAR_ACC + t) * 8, 1); mbar_init(bars + (K::BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (K::BAR_IN + t) * 8, 1);
-      mbar_init(bars + (K::BAR_HEAD + t) * 8, 128);
-      for(int c = 0; c < K::NCH; c++) mbar_init(bars + (K::BAR_CHUNK + t * K::NCH + c) * 8, 128);
+      mbar_init(bars + (K::BAR_INP + t) * 8, 1);
+      mbar_init(bars + (K::BAR_HEAD + t) * 8, 4 * K::NCTA);   // one arrival per epilogue warp (of both CTAs in pair mode)
+      for(int c = 0; c < K::NCH; c++) mbar_init(bars + (K::BAR_CHUNK + t * K::NCH + c) * 8, 4 * K::NCTA);
     }
     fence_mbar_init();
   }
   fence_proxy_async();
-  if(warp == 1) { tmem_alloc(sbase + K::OFF_TMEM, 512); tmem_relinquish(); }
+  if(warp == 1) {
+    if constexpr(K::PAIR) { tmem_alloc2(sbase + K::OFF_TMEM, 512); tmem_relinquish2(); }
+    else { tmem_alloc(sbase + K::OFF_TMEM, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr(K::PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(smem + K::OFF_TMEM);
 
   if(warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (every CTA; pair mode: its half of each weight stage) ===========================
     if(lane == 0) {
       uint32_t slot = 0, phase = 0, itemCount = 0;
       bool alive = true;
-      for(int item = blockIdx.x; item < numItems && alive; item += gridDim.x, itemCount++) {
+      for(int unit = unit0; unit < numUnits && alive; unit += unitStep, itemCount++) {
+        const int item = min(itemOf(unit), numItems - 1);
         for(int t = 0; t < NT && alive; t++) {
           if(itemCount > 0) alive = mbar_wait(bars + (K::BAR_ACTFREE + t) * 8, (itemCount - 1) & 1, abortFlag, 11);
           if(!alive) break;
@@ -518,12 +652,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
           const uint8_t* w = P.wstream + L.wOffset;
           for(int s = 0; s < nst; s++) {
             int ks = min(KSTEPS_PER_STAGE, L.nk - s * KSTEPS_PER_STAGE);
-            uint32_t bytes = (uint32_t)ks * L.N * 32;
+            uint32_t bytes = (uint32_t)ks * L.N * 32;          // whole stage; the stream holds [rank 0 half][rank 1 half] per stage
             alive = mbar_wait(bars + (K::BAR_EMPTY + slot) * 8, phase ^ 1, abortFlag, 12);
             if(!alive) break;
             uint32_t bar = bars + (K::BAR_FULL + slot) * 8;
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(sbase + K::OFF_RING + slot * K::STAGE_BYTES, w, bytes, bar);
+            mbar_arrive_expect_tx(bar, bytes / K::NCTA);
+            bulk_g2s(sbase + K::OFF_RING + slot * K::STAGE_BYTES, w + rank * (bytes / K::NCTA), bytes / K::NCTA, bar);
             w += bytes;
             if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
           }
@@ -531,10 +665,29 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
       }
     }
   } else if(warp >= 1 && warp <= NT) {
-    // =========================== MMA issuers: one thread per tile ===========================
-    mmaIssuer<K>(P, warp - 1, sbase, bars, tmemBase, abortFlag, numItems);
+    // =========================== MMA issuers: one thread per tile (pair mode: in the leader CTA, for both CTAs) ===========================
+    if(rank == 0) mmaIssuer<K>(P, warp - 1, sbase, bars, tmemBase, abortFlag, numUnits);
   } else if(warp < 4) {
-    // idle (keeps the epilogue warps aligned to TMEM lane quadrants: warp % 4 == quadrant)
+    // warp 3.  Pair mode, peer CTA: relay -- tells the leader's issuers when this CTA's input tiles and weight halves have
+    // landed (a bulk copy can only signal a barrier of its own CTA).  Otherwise idle.
+    if(K::PAIR && rank == 1 && warp == 3 && lane == 0) {
+      uint32_t slot = 0, phase = 0, itemCount = 0;
+      bool alive = true;
+      for(int unit = unit0; unit < numUnits && alive; unit += unitStep, itemCount++) {
+        for(int t = 0; t < NT && alive; t++) {
+          alive = mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 13);
+          if(alive) mbar_arrive_cluster(mapa(bars + (K::BAR_INP + t) * 8, 0));
+        }
+        for(int l = 0; l < P.numLayers && alive; l++) {
+          const int nst = (P.layers[l].nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+          for(int s = 0; s < nst && alive; s++) {
+            alive = mbar_wait(bars + (K::BAR_FULL + slot) * 8, phase, abortFlag, 14);
+            if(alive) mbar_arrive_cluster(mapa(bars + (K::BAR_FULLP + slot) * 8, 0));
+            if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
   } else {
     // =========================== epilogue warps ===========================
     EpiCtx c;
@@ -550,7 +703,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     if(!c.valid) { c.b = 0; c.cell = 0; }
     c.tmemLane = tmemBase + ((uint32_t)(q * 32) << 16) + c.t * (2 * K::MAXC);
     c.act = smem + K::OFF_ACT + c.t * K::ACT_BYTES;
+    c.remote = K::PAIR && rank != 0;
     c.barChunk = bars + (K::BAR_CHUNK + c.t * K::NCH) * 8;
+    uint32_t barHead = bars + (K::BAR_HEAD + c.t) * 8;
+    if(c.remote) { c.barChunk = mapa(c.barChunk, 0); barHead = mapa(barHead, 0); }
     c.scr = reinterpret_cast<float*>(smem + K::OFF_SCR) + c.t * 128 * SCR_STRIDE;
     c.poolA = reinterpret_cast<float*>(smem + K::OFF_POOLA) + c.t * MAX_NB * K::POOLW;
     c.poolB = reinterpret_cast<float*>(smem + K::OFF_POOLB) + c.t * MAX_NB * K::POOLW;
@@ -558,7 +714,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     c.v2buf = reinterpret_cast<float*>(smem + K::OFF_V2) + c.t * MAX_NB * MAX_V2;
     uint32_t layerCount = 0;
     bool alive = true;
-    for(int item = blockIdx.x; item < numItems && alive; item += gridDim.x) {
+    stageHeadParams(P, P.layers[P.numLayers - 1], c.e, c.t, sHeadPar[c.t]);   // read after the first layer's named barrier at the earliest
+    for(int unit = unit0; unit < numUnits && alive; unit += unitStep) {
+      const int item = itemOf(unit);
       for(int l = 0; l < P.numLayers && alive; l++, layerCount++) {
         const LayerDesc L = P.layers[l];
         {
@@ -570,23 +728,38 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
               par[i] = __ldg(sc + i);
               par[K::MAXC + i] = __ldg(sc + L.epiC + i);
             }
+            if(L.epi == EPI_GPOOL && c.e < L.gpoolC) {   // gpoolBN behind midBN (epiC + gpoolC <= MAXC)
+              par[L.epiC + c.e] = __ldg(P.params + L.pOff + c.e);
+              par[K::MAXC + L.epiC + c.e] = __ldg(P.params + L.pOff + L.gpoolC + c.e);
+            }
+          } else {
+            par = sHeadPar[c.t];   // staged once, before the first item
           }
           c.par = par;
           named_bar_sync(1 + c.t, 128);
         }
         alive = mbar_wait(bars + (K::BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
         if(!alive) break;
+        c.dbg = (P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && layerCount == 5) ? P.dbg : nullptr;
+        if(c.dbg) c.dbg[1] = clock64();
+        const bool probeHead = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers - 1;
+        if(probeHead) P.dbg[17] = clock64();
+        if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers) P.dbg[22] = clock64();
         tc_fence_after();
         if(L.epi == EPI_BN) epilogueBN<K>(P, L, c);
         else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
-        else epilogueHead<K>(P, L, c, item * NT + c.t, bars + (K::BAR_HEAD + c.t) * 8, sSym, nRows);
+        else epilogueHead<K>(P, L, c, item * NT + c.t, barHead, sSym, nRows);
+        if(probeHead) P.dbg[19] = clock64();
       }
     }
   }
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
-  if(warp == 1) { tc_fence_after(); tmem_dealloc(tmemBase, 512); }
+  if constexpr(K::PAIR) cluster_sync(); else __syncthreads();
+  if(warp == 1) {
+    tc_fence_after();
+    if constexpr(K::PAIR) tmem_dealloc2(tmemBase, 512); else tmem_dealloc(tmemBase, 512);
+  }
 }
 
 // kc_forward input conversion: raw fp32 rows (NCHW/NHWC) + global -> symmetrised bf16 tiles
@@ -754,7 +927,7 @@ int buildTrunkProgram(kc_model* m) {
   if(m->p1Conv.oc != HEADC || m->g1Conv.oc != HEADC || m->v1Conv.oc != HEADC) return unsupported("head convs must have 32 channels");
   if(m->p1Conv.ky != 1 || m->g1Conv.ky != 1 || m->v1Conv.ky != 1 || m->p2Conv.ky != 1 || m->vOwnershipConv.ky != 1)
     return unsupported("head convs must be 1x1");
-  if(m->v2Mul.oc > MAX_V2) return unsupported("v2 size must be <= 128");
+  if(m->v2Mul.oc > MAX_V2 || m->v2Mul.oc % 16 != 0) return unsupported("v2 size must be a multiple of 16, <= 128");
   if(m->trunkTipBN.act != 1 || m->g1BN.act != 1 || m->p1BN.act != 1 || m->v1BN.act != 1 || m->v2Act != 1)
     return unsupported("only ReLU activations are implemented in the tcgen05 kernel");
   for(const BlockW& b : m->blocks) {
@@ -836,6 +1009,27 @@ int buildTrunkProgram(kc_model* m) {
     return kc::fail("buildTrunkProgram: out of device memory");
   }
   cudaMemcpy(T->d_w, pk.w.data(), pk.w.size(), cudaMemcpyHostToDevice);
+  if(cfg == 0) {
+    // pair-mode stream: per stage [rank 0: rows 0..N/2 of every K-step][rank 1: rows N/2..N], each K-step still [2][rows][8]
+    std::vector<uint8_t> w2(pk.w.size());
+    for(const LayerDesc& L : T->layers) {
+      const int N = L.N, half = N / 2;
+      const uint8_t* src = pk.w.data() + L.wOffset;
+      uint8_t* dst = w2.data() + L.wOffset;
+      for(int k0 = 0; k0 < L.nk; k0 += KSTEPS_PER_STAGE) {
+        const int ks = std::min(KSTEPS_PER_STAGE, L.nk - k0);
+        for(int h = 0; h < 2; h++)
+          for(int k = 0; k < ks; k++)
+            for(int kc = 0; kc < 2; kc++) {
+              memcpy(dst, src + (size_t)(k0 + k) * N * 32 + (size_t)kc * N * 16 + (size_t)h * half * 16, (size_t)half * 16);
+              dst += (size_t)half * 16;
+            }
+        src += 0;
+      }
+    }
+    if(cudaMalloc(&T->d_wPair, w2.size()) != cudaSuccess) { delete T; return kc::fail("buildTrunkProgram: out of device memory"); }
+    cudaMemcpy(T->d_wPair, w2.data(), w2.size(), cudaMemcpyHostToDevice);
+  }
   cudaMemcpy(T->d_params, pk.p.data(), pk.p.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(T->d_layers, T->layers.data(), T->layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice);
   m->trunk = T;
@@ -844,7 +1038,7 @@ int buildTrunkProgram(kc_model* m) {
 
 void freeTrunkProgram(kc_model* m) {
   if(!m->trunk) return;
-  cudaFree(m->trunk->d_w); cudaFree(m->trunk->d_params); cudaFree(m->trunk->d_layers);
+  cudaFree(m->trunk->d_w); cudaFree(m->trunk->d_wPair); cudaFree(m->trunk->d_params); cudaFree(m->trunk->d_layers);
   delete m->trunk;
   m->trunk = nullptr;
 }
@@ -861,12 +1055,14 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaMemset(h->d_tiles, 0, bytes));
   KC_CUDA(cudaMalloc(&h->d_abort, 4));
   KC_CUDA(cudaMemset(h->d_abort, 0, 4));
+  if(getenv("KC_TRUNK_PROBE")) { KC_CUDA(cudaMalloc(&h->d_dbg, 32 * 8)); KC_CUDA(cudaMemset(h->d_dbg, 0, 32 * 8)); }
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
   return 0;
 }
 void freeTrunkBuffers(kc_handle* h) {
-  cudaFree(h->d_abort);
+  cudaFree(h->d_abort); cudaFree(h->d_dbg);
   for(cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   h->evPool.clear();
 }
@@ -908,6 +1104,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.policy = h->d_policy + (size_t)rowOffset * 4 * P.HW; P.value = h->d_value + (size_t)rowOffset * 2;
   P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;
+  P.dbg = h->d_dbg;
   float sq = sqrtf((float)P.HW);
   P.poolScale1 = (sq - 14.0f) * 0.1f;
   P.poolScale2 = (sq - 14.0f) * (sq - 14.0f) * 0.01f - 0.1f;
@@ -921,7 +1118,22 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   }
   bool timed = (int)h->evPool.size() >= h->evUsed + 2;
   if(timed) cudaEventRecord(h->evPool[h->evUsed], st);
-  if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
+  // CTA pairs (cta_group::2) are the default for trunks up to 128 channels; KC_TRUNK_PAIR=0 selects the single-CTA kernel
+  static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }();
+  if(T->cfg == 0 && usePair) {
+    // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
+    P.wstream = T->d_wPair;
+    const int numUnits = nDev ? h->ctx->smCount / 2 : (P.numItems + 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(numUnits, h->ctx->smCount / 2)); cfg.blockDim = dim3(Cfg128P::THREADS);
+    cfg.dynamicSmemBytes = Cfg128P::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
+  }
+  else if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
   else trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);
   if(timed) { cudaEventRecord(h->evPool[h->evUsed + 1], st); h->evUsed += 2; }
   h->launches++;
@@ -932,6 +1144,14 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
 }  // namespace kc
 
 extern "C" {
+int kc_handle_trunk_probe(kc_handle* h, int64_t* out) {
+  KC_CHECK(h && out, "kc_handle_trunk_probe: null argument");
+  KC_CHECK(h->d_dbg, "kc_handle_trunk_probe: set KC_TRUNK_PROBE=1 before creating the handle");
+  KC_CUDA(cudaSetDevice(h->ctx->device));
+  KC_CUDA(cudaDeviceSynchronize());
+  KC_CUDA(cudaMemcpy(out, h->d_dbg, 32 * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 // Self-test of the UMMA descriptor conventions the trunk kernel relies on (row-shifted K-major
 // no-swizzle A operand): computes D = A[shift:shift+128] * B^T on the tensor core and returns it.
 // A [rowsA][K], B [N][K] as bf16 bit patterns (uint16), D [128][N] fp32. K % 16 == 0, N % 16 == 0.

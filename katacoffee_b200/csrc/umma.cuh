@@ -147,6 +147,63 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t r[16]) {
     :: "memory");
 }
 
+// ---- CTA pair (cluster of two CTAs on one TPC, tcgen05 cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+// arrive on an mbarrier of any CTA of the cluster (address from mapa).  Default (CTA-scope release) semantics on
+// purpose: what the arrival orders is this CTA's own shared-memory writes (already fenced to the async proxy) against
+// its OWN tensor core reading them for the pair's next MMA; a cluster-scope release costs microseconds per arrival.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t clusterAddr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+    "selp.u32 %0, 1, 0, p;\n\t}"
+    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, volatile int* abortFlag, int code) {
+  if(mbar_try_wait_cluster(bar, parity)) return true;
+  long long t0 = clock64();
+  for(uint32_t it = 1;; it++) {
+    if(mbar_try_wait_cluster(bar, parity)) return true;
+    if((it & 255u) == 0) {
+      if(*abortFlag != 0) return false;
+      if(clock64() - t0 > (1LL << 32)) { *abortFlag = code; return false; }
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dstSmem, uint32_t ncols) {  // whole warp, in each CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dstSmem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA's shared memory) * B^T (N/2 rows from each CTA's shared memory);
+// issued by one thread of the leader CTA (rank 0) for the pair
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+    ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in every CTA of `mask` once all prior MMAs of the pair completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
