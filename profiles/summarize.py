@@ -21,7 +21,7 @@ if os.path.exists(path):
         agg.setdefault(k, []).append(float(r["Metric Value"]))
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(out, f"{tag}_launches_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-selfplay\n")
         f.write("# kernel | grid | block | launches | mean us | share of profiled GPU time\n")
         for (name, grid, block), v in agg.items():
             f.write(f"{name} | {grid} | {block} | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {sum(v)/total*100:.1f}%\n")
