@@ -112,7 +112,10 @@ int kc_model_destroy(kc_model* model);
  * ------------------------------------------------------------------------------------------- */
 #define KC_FLAG_FP32_CHECK 1u       /* CUDA-core fp32 path (1e-4 gate); default is bf16 tcgen05 */
 #define KC_FLAG_INPUTS_NHWC 2u      /* kc_forward spatial rows are NHWC (inputsUseNHWC)          */
-#define KC_FLAG_SYM_PERMUTE_DIRS 4u /* play mode, SURVEY.md 8.1-K: also permute direction channels */
+#define KC_FLAG_SYM_PERMUTE_DIRS 4u /* play mode, SURVEY.md 8.1-K: a symmetry also permutes the direction channels (inputs 3..6 by
+                                       getSymDir, cpp/neuralnet/nninputs.cpp:409-433, the 4 policy channels by its inverse), which
+                                       makes it a true symmetry of the game; default is the reference backends' spatial-only copy.
+                                       Applies to kc_forward and kc_games_eval; kc_games_features is always spatial-only. */
 
 int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLen, int nnYLen,
                      unsigned flags, kc_handle** out);

@@ -42,11 +42,12 @@ class LoadedModel:
 
 
 class ComputeHandle:
-    def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False):
+    def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False):
         self.ctx, self.loadedModel = ctx, loadedModel
         self.maxBatch, self.nnXLen, self.nnYLen = maxBatchSize, nnXLen, nnYLen
         self.inputsUseNHWC = inputsUseNHWC
-        flags = (capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_INPUTS_NHWC if inputsUseNHWC else 0)
+        flags = ((capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_INPUTS_NHWC if inputsUseNHWC else 0) |
+                 (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0))
         self._p = C.c_void_p()
         check(lib().kc_handle_create(ctx._p, loadedModel._p, maxBatchSize, nnXLen, nnYLen, flags, C.byref(self._p)))
 
@@ -76,8 +77,8 @@ class ComputeHandle:
             self._p = C.c_void_p()
 
 
-def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False):
-    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC)
+def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False):
+    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC, playModeSymmetry)
 
 
 def getOutput(handle, rowSpatial, rowGlobal, symmetry=None, ownership=True, out=None):

@@ -44,6 +44,7 @@ struct FeatOut {
   float* global;            // FEAT 1/2
   uint4* tiles;             // FEAT 3: [tile][2][128] 16-byte chunks
   const int8_t* symmetry;   // per game or null
+  int permuteDirs;          // play mode (ledger K): with a symmetry, channels 3..6 follow symDir
   int gamesPerBlock;
 };
 
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(
       int c = FEAT == 1 ? q : rem;
       int cell = FEAT == 1 ? rem : q;
       int bit = sSrcPad[sSym[gl]][cell];
+      if(fo.permuteDirs) c = playModeChannel(c, sSym[gl]);
       return (float)((sPlanes[c][gl] >> bit) & 1ULL);
     };
     const int nvec = total >> 2;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(
 #pragma unroll
         for(int q = 0; q < 4; q++) {
           int c0 = chunk * 8 + 2 * q, c1 = c0 + 1;
+          if(fo.permuteDirs) { c0 = playModeChannel(c0, sSym[gl]); if(c1 < 15) c1 = playModeChannel(c1, sSym[gl]); }
           uint32_t lo = ((sPlanes[c0][gl] >> bit) & 1ULL) ? ONE : 0u;
           uint32_t hi = (c1 < 15) ? (((sPlanes[c1][gl] >> bit) & 1ULL) ? ONE : 0u) : kval;
           w[q] = lo | (hi << 16);
@@ -513,6 +516,7 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   if(symmetry) KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
   FeatOut fo{};
   fo.symmetry = symmetry ? G->d_sym : nullptr;
+  fo.permuteDirs = (symmetry && kc::handlePermutesDirs(h)) ? 1 : 0;
   StepOut so = stepOutOf(G, true);   // also refreshes legal masks / status / sit-hashes of the evaluated positions
   so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {

@@ -41,6 +41,16 @@ constexpr uint64_t ZOBRIST_GAME_IS_OVER1 = 0xf1d583d960a4ce7fULL;
 // (cpp/neuralnet/nninputs.cpp:252-357): dstPos[srcPos] for an H x W plane.
 void symmetryDstOfSrc(int H, int W, int symmetry, bool reverse, int* dstOfSrc);
 int symDir(int dir, int symmetry);  // nninputs.cpp:409-433 (ledger J)
+// The same map for device code, and the channel permutation of play mode (ledger K): V1 input channels 3..6 are the last
+// move's direction, so under symmetry s channel 3+d of the source is channel 3+symDir(d, s) of the symmetric position
+// (symDir is an involution and equal for s and its inverse, so the same function serves inputs and policy outputs).
+__host__ __device__ inline int symDirInline(int dir, int symmetry) {
+  const bool tr = (symmetry & 4) != 0, fx = (symmetry & 2) != 0, fy = (symmetry & 1) != 0;
+  if(fx != fy) dir = dir == 2 ? 3 : (dir == 3 ? 2 : dir);
+  if(tr) dir = dir == 0 ? 1 : (dir == 1 ? 0 : dir);
+  return dir;
+}
+__host__ __device__ inline int playModeChannel(int c, int symmetry) { return (c >= 3 && c <= 6) ? 3 + symDirInline(c - 3, symmetry) : c; }
 
 }  // namespace kc
 

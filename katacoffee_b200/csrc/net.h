@@ -17,6 +17,7 @@ constexpr int ACT_ROWS = TILE_ROWS + 2 * HALO_ROWS;
 // ---- handle accessors used by games.cu ----------------------------------------------------------
 int handleCheckGeometry(kc_handle* h, int W, int H, int n);
 bool handleIsBf16(const kc_handle* h);
+bool handlePermutesDirs(const kc_handle* h);   // KC_FLAG_SYM_PERMUTE_DIRS
 void* handleInputTiles(kc_handle* h);      // bf16 path: [tiles][2][128] 16-byte chunks
 float* handleInputNHWC(kc_handle* h);      // fp32 path: [n][H*W][15]
 float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]

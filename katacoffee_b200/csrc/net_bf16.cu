@@ -124,6 +124,7 @@ struct TrunkParams {
   int NB, W, H, HW, stride, tileRowW;
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
+  int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
   int* abortFlag;
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
   float poolScale1, poolScale2, invHW;
@@ -463,7 +464,12 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     int s = P.sym ? P.sym[game] : 0;
     int dst = sSym[s * P.HW + c.cell];
     float* pol = P.policy + (size_t)game * 4 * P.HW;
-    pol[dst] = o0; pol[P.HW + dst] = o1; pol[2 * P.HW + dst] = o2; pol[3 * P.HW + dst] = o3;
+    if(P.permuteDirs) {   // play mode: the net's direction channel d is direction symDir(d, s) of the original position
+      pol[symDirInline(0, s) * P.HW + dst] = o0; pol[symDirInline(1, s) * P.HW + dst] = o1;
+      pol[symDirInline(2, s) * P.HW + dst] = o2; pol[symDirInline(3, s) * P.HW + dst] = o3;
+    } else {
+      pol[dst] = o0; pol[P.HW + dst] = o1; pol[2 * P.HW + dst] = o2; pol[3 * P.HW + dst] = o3;
+    }
     P.own[(size_t)game * P.HW + dst] = own;
   }
 }
@@ -765,7 +771,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
 // kc_forward input conversion: raw fp32 rows (NCHW/NHWC) + global -> symmetrised bf16 tiles
 __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __restrict__ rawGlobal, const int8_t* __restrict__ sym,
                                 const uint8_t* __restrict__ dstOfSrc, uint4* __restrict__ tiles, int n, int numTiles,
-                                int NB, int W, int H, int rawNHWC) {
+                                int NB, int W, int H, int rawNHWC, int permuteDirs) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if(j >= numTiles * 256) return;
   const int HW = W * H, stride = W + 1, tileRowW = NB * stride;
@@ -783,6 +789,7 @@ __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __re
 #pragma unroll
     for(int q = 0; q < 8; q++) {
       int c = chunk * 8 + q;
+      if(permuteDirs) c = playModeChannel(c, s);   // destination channel c shows the source's channel playModeChannel(c)
       if(c < 15) f[q] = rawNHWC ? raw[((size_t)game * HW + srcCell) * 15 + c] : raw[((size_t)game * 15 + c) * HW + srcCell];
       else f[q] = rawGlobal[game];
     }
@@ -1080,7 +1087,7 @@ int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev,
   uint4* tiles = (uint4*)h->d_tiles + (size_t)(rowOffset / NB) * 2 * TILE_ROWS;
   k_convert_tiles<<<(numTiles * 256 + 255) / 256, 256, 0, st>>>(h->d_raw + (size_t)rowOffset * 15 * HW, h->d_rawGlobal + rowOffset,
                                                                sym_dev ? sym_dev + rowOffset : nullptr, h->d_dstOfSrc, tiles, n, numTiles,
-                                                               NB, h->W, h->H, rawNHWC);
+                                                               NB, h->W, h->H, rawNHWC, (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0);
   h->launches++;
   KC_CUDA(cudaGetLastError());
   return 0;
@@ -1104,6 +1111,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.policy = h->d_policy + (size_t)rowOffset * 4 * P.HW; P.value = h->d_value + (size_t)rowOffset * 2;
   P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;
+  P.permuteDirs = (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0;
   P.dbg = h->d_dbg;
   float sq = sqrtf((float)P.HW);
   P.poolScale1 = (sq - 14.0f) * 0.1f;

@@ -24,13 +24,14 @@ __device__ __forceinline__ float activate(float x, int act) {
 
 // raw rows (NCHW or NHWC, as the caller filled them) -> symmetrised NHWC fp32 (copyInputsWithSymmetry)
 __global__ void k_convert_input(const float* __restrict__ raw, const int8_t* __restrict__ sym, const uint8_t* __restrict__ dstOfSrc,
-                                float* __restrict__ out, int n, int HW, int C, int rawNHWC) {
+                                float* __restrict__ out, int n, int HW, int C, int rawNHWC, int permuteDirs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n * HW * C) return;
   int c = i % C, p = (i / C) % HW, b = i / (C * HW);
   int s = sym ? sym[b] : 0;
   float v = rawNHWC ? raw[((size_t)b * HW + p) * C + c] : raw[((size_t)b * C + c) * HW + p];
-  out[((size_t)b * HW + dstOfSrc[s * HW + p]) * C + c] = v;
+  const int cd = permuteDirs ? playModeChannel(c, s) : c;   // play mode (ledger K): direction channels follow the symmetry
+  out[((size_t)b * HW + dstOfSrc[s * HW + p]) * C + cd] = v;
 }
 
 __global__ void k_mask_from_input(const float* __restrict__ in, float* __restrict__ mask, float* __restrict__ maskSum, int n, int HW, int C) {
@@ -134,12 +135,13 @@ __global__ void k_add_nc_bias(float* __restrict__ x, const float* __restrict__ b
 }
 // NHWC [n][HW][D] -> [n][d*HW + dst(p)] with the inverse spatial symmetry (copyOutputsWithSymmetry)
 __global__ void k_spatial_out(const float* __restrict__ in, const int8_t* __restrict__ sym, const uint8_t* __restrict__ dstOfSrcRev,
-                              float* __restrict__ out, int n, int HW, int D) {
+                              float* __restrict__ out, int n, int HW, int D, int permuteDirs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n * HW * D) return;
   int d = i % D, p = (i / D) % HW, b = i / (D * HW);
   int s = sym ? sym[b] : 0;
-  out[((size_t)b * D + d) * HW + dstOfSrcRev[s * HW + p]] = in[i];
+  const int dd = (permuteDirs && D == 4) ? symDirInline(d, s) : d;
+  out[((size_t)b * D + dd) * HW + dstOfSrcRev[s * HW + p]] = in[i];
 }
 __global__ void k_nchw_to_nhwc(const float* __restrict__ in, float* __restrict__ out, int n, int c, int HW) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +339,7 @@ static int runFp32(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev) 
   k_add_nc_bias<<<blocksFor(rows * pc), 256, 0, st>>>(f.a, f.bias, n, HW, pc);
   k_bn<<<blocksFor(rows * pc), 256, 0, st>>>(f.a, m->p1BN.d_scale, m->p1BN.d_bias, f.mask, f.a, rows, pc, m->p1BN.act);
   k_conv<<<blocksFor(rows * D), 256, 0, st>>>(f.a, m->p2Conv.d_tap, f.c, n, H, W, pc, D, m->p2Conv.ky, m->p2Conv.kx, 0);
-  k_spatial_out<<<blocksFor(rows * D), 256, 0, st>>>(f.c, sym_dev, h->d_dstOfSrcRev, h->d_policy, n, HW, D);
+  k_spatial_out<<<blocksFor(rows * D), 256, 0, st>>>(f.c, sym_dev, h->d_dstOfSrcRev, h->d_policy, n, HW, D, (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0);
   // value head
   int vc = m->v1Conv.oc, v2c = m->v2Mul.oc;
   k_conv<<<blocksFor(rows * vc), 256, 0, st>>>(f.tip, m->v1Conv.d_tap, f.a, n, H, W, C, vc, m->v1Conv.ky, m->v1Conv.kx, 0);
@@ -347,7 +349,7 @@ static int runFp32(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev) 
   k_matmul<<<blocksFor((long long)n * m->v3Mul.oc), 256, 0, st>>>(f.bias, m->v3Mul.d, m->v3Bias.d, h->d_value, n, v2c, m->v3Mul.oc, 0);
   k_matmul<<<blocksFor((long long)n * m->sv3Mul.oc), 256, 0, st>>>(f.bias, m->sv3Mul.d, m->sv3Bias.d, h->d_misc, n, v2c, m->sv3Mul.oc, 0);
   k_conv<<<blocksFor(rows), 256, 0, st>>>(f.a, m->vOwnershipConv.d_tap, f.c, n, H, W, vc, 1, m->vOwnershipConv.ky, m->vOwnershipConv.kx, 0);
-  k_spatial_out<<<blocksFor(rows), 256, 0, st>>>(f.c, sym_dev, h->d_dstOfSrcRev, h->d_own, n, HW, 1);
+  k_spatial_out<<<blocksFor(rows), 256, 0, st>>>(f.c, sym_dev, h->d_dstOfSrcRev, h->d_own, n, HW, 1, 0);
   h->launches += 18;
   KC_CUDA(cudaGetLastError());
   return 0;
@@ -360,6 +362,7 @@ int handleCheckGeometry(kc_handle* h, int W, int H, int n) {
   return 0;
 }
 bool handleIsBf16(const kc_handle* h) { return h->bf16; }
+bool handlePermutesDirs(const kc_handle* h) { return (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) != 0; }
 void* handleInputTiles(kc_handle* h) { return h->d_tiles; }
 float* handleInputNHWC(kc_handle* h) { return h->f32.in; }
 float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
@@ -472,7 +475,6 @@ int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLe
   KC_CHECK(ctx && model && out, "kc_handle_create: null argument");
   KC_CHECK(maxBatch > 0, "kc_handle_create: maxBatch must be positive");
   KC_CHECK(nnXLen >= 2 && nnYLen >= 2 && nnXLen <= KC_MAX_LEN && nnYLen <= KC_MAX_LEN, "kc_handle_create: nnXLen/nnYLen out of range");
-  KC_CHECK(!(flags & KC_FLAG_SYM_PERMUTE_DIRS), "kc_handle_create: KC_FLAG_SYM_PERMUTE_DIRS (play mode) is not implemented yet; parity mode only");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_handle* h = new kc_handle();
   h->ctx = ctx; h->model = model; h->maxBatch = maxBatch; h->W = nnXLen; h->H = nnYLen; h->flags = flags;
@@ -621,7 +623,7 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
   KC_CUDA(cudaMemcpyAsync(h->d_rawGlobal, global, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   if(symmetry) KC_CUDA(cudaMemcpyAsync(h->d_sym, symmetry, (size_t)n, cudaMemcpyHostToDevice, st));
   const int8_t* sym_dev = symmetry ? h->d_sym : nullptr;
-  k_convert_input<<<blocksFor((long long)n * HW * 15), 256, 0, st>>>(h->d_raw, sym_dev, h->d_dstOfSrc, h->f32.in, n, HW, 15, rawNHWC);
+  k_convert_input<<<blocksFor((long long)n * HW * 15), 256, 0, st>>>(h->d_raw, sym_dev, h->d_dstOfSrc, h->f32.in, n, HW, 15, rawNHWC, (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0);
   KC_CUDA(cudaMemcpyAsync(h->f32.global, h->d_rawGlobal, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   h->launches += 1;
   if(handleRunOnStream(h, n, st, sym_dev)) return 1;
