@@ -263,6 +263,24 @@ int kc_search_read_root(kc_search* s, int32_t* rootVisits, double* rootUtilitySu
 /* `moves` times: [refill] -> search -> choose and play the move.  chosenLast [G] receives the last moves played
  * (policy index, -1 none); *msTotal the device time of the whole call. */
 int kc_search_play(kc_search* s, int moves, int16_t* chosenLast, kc_search_stats* statsAccum, float* msTotal);
+/* Training rows (TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566).  After
+ * kc_search_enable_training_rows every move played by kc_search_play is recorded and, when its game ends, written out
+ * as one row of the reference's npz arrays (rows of one game are consecutive, games in completion order):
+ *   binaryInputNCHWPacked [N][15][ceil(H*W/8)] u8   fillRowV1 planes, bits big-endian in each byte (packBits :218-233)
+ *   globalInputNC         [N][1] f32                win_len
+ *   policyTargetsNCMove   [N][2][4*H*W] i16         visits of this turn's search; of the next turn's (all ones on the last turn)
+ *   globalTargetsNC       [N][64] f32               the reference's literal indices: 0..9 win/loss td-targets from the player to move's
+ *        view for nowFactor 0, 1/(1+A*0.176), 1/(1+A*0.056), 1/(1+A*0.016), 1 (fillValueTDTargets :286-314; the turn targets are the
+ *        search's root estimate (1 +- utility)/2, the last one the result, draw = 0.5/0.5), 25 row weight 1, 26 policy weight 1,
+ *        27 ownership weight 1, 28 next-policy weight, 33 future-position weight 1, 36..40 history masks 1 (the reference randomises
+ *        them), 41..46 game hash in 22/22/20-bit chunks (splitmix64 of the game id), 51 turn index, 60 root visits, 63 version 1;
+ *        every other entry 0 (Go-only or not produced by this search: score, lead, surprise / entropy statistics, net ages)
+ *   valueTargetsNCHW      [N][5][H][W] i8           0 final stones (+1 own, -1 opponent's), 1 zero, 2 / 3 the stones 2 / 6 plies later
+ *        (clipped to the end), 4 the longest same-colour run through each final stone (recordMaxConsecutives, stones only)
+ * maxRows bounds the device buffer; rows of games that do not fit are counted in *numDropped. */
+int kc_search_enable_training_rows(kc_search* s, int maxRows);
+int kc_search_read_training_rows(kc_search* s, int* numRows, int* numDropped, uint8_t* binaryInputNCHWPacked, float* globalInputNC,
+                                 int16_t* policyTargetsNCMove, float* globalTargetsNC, int8_t* valueTargetsNCHW, int clear);
 int64_t kc_search_launch_count(const kc_search* s);
 
 #ifdef __cplusplus

@@ -276,6 +276,28 @@ class Search:
         check(lib().kc_search_play(self._p, moves, ptr(chosen), C.byref(st), C.byref(ms)))
         return st, chosen, ms.value
 
+    def enableTrainingRows(self, maxRows):
+        self._maxRows = maxRows
+        check(lib().kc_search_enable_training_rows(self._p, maxRows))
+
+    def readTrainingRows(self, clear=True):
+        """The finished games' rows as the reference's npz arrays (dict name -> array) + the number of dropped rows."""
+        HW = self.W * self.H
+        n = self._maxRows
+        out = dict(binaryInputNCHWPacked=np.zeros((n, 15, (HW + 7) // 8), np.uint8), globalInputNC=np.zeros((n, 1), np.float32),
+                   policyTargetsNCMove=np.zeros((n, 2, self.P), np.int16), globalTargetsNC=np.zeros((n, 64), np.float32),
+                   valueTargetsNCHW=np.zeros((n, 5, self.H, self.W), np.int8))
+        rows, dropped = C.c_int(), C.c_int()
+        check(lib().kc_search_read_training_rows(self._p, C.byref(rows), C.byref(dropped), ptr(out["binaryInputNCHWPacked"]), ptr(out["globalInputNC"]),
+                                                 ptr(out["policyTargetsNCMove"]), ptr(out["globalTargetsNC"]), ptr(out["valueTargetsNCHW"]), int(clear)))
+        return {k: v[:rows.value] for k, v in out.items()}, dropped.value
+
+    def writeTrainingNpz(self, path, clear=True):
+        """numpy .npz with the reference's array names (TrainingWriteBuffers::writeToZipFile, trainingwrite.cpp:566-587)."""
+        rows, dropped = self.readTrainingRows(clear)
+        np.savez_compressed(path, **rows)
+        return len(rows["globalInputNC"]), dropped
+
     def launchCount(self):
         return int(lib().kc_search_launch_count(self._p))
 

@@ -113,6 +113,8 @@ PROTOTYPES = {
     "kc_search_run_visits": (C.c_int, [vp]),
     "kc_search_read_root": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "kc_search_play": (C.c_int, [vp, C.c_int, vp, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
+    "kc_search_enable_training_rows": (C.c_int, [vp, C.c_int]),
+    "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
     "kc_search_launch_count": (C.c_int64, [vp]),
 }
 

@@ -66,6 +66,23 @@ struct TreeMem {
   unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws
 };
 
+// Training-row capture (reference cpp/dataio/trainingwrite.cpp:316-566 TrainingWriteBuffers::addRow,
+// cpp/program/play.cpp:1428-1460).  Every move played by kc_search_play is recorded per game (position before the move,
+// root visits / utility, visit counts); when the game ends the rows are finished (result-dependent targets) and appended to
+// an output buffer.  Canonical row (the reference's literal 64-channel layout, entries it derives from Go-only or
+// random state fixed): see the comment of kc_search_read_training_rows in the header.
+struct TrainMem {
+  int enabled, maxPlies, maxRows, pad_;
+  uint64_t* recBlack; uint64_t* recWhite; uint64_t* recMisc;   // [G][maxPlies] position before the move
+  int* recN; double* recW;                                     // [G][maxPlies] root visits, root utility sum (white-positive)
+  int16_t* recVisits;                                          // [G][maxPlies][P]
+  int* recCount;                                               // [G]
+  uint64_t* recGameId;                                         // [G] id of the game being recorded
+  int* rowCount;                                               // [2]: rows written, rows dropped (buffer full)
+  uint8_t* outBin; float* outGlobalIn; int16_t* outPolicy; float* outGlobalT; int8_t* outValue;
+  double nowFactor[5];                                         // fillValueTDTargets factors (trainingwrite.cpp:403-414)
+};
+
 // node layout: header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 | policy[P] f32 |
 //              child[P] i32 | edgeN[P] i32 | order[P] u8
 struct NodeRef {
@@ -274,7 +291,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
 // choose the move, play it on the root game, drop the tree; refill finished games
 // ---------------------------------------------------------------------------------------------
 template <class D>
-__global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeMem t, const uint64_t* __restrict__ zob, int16_t* __restrict__ chosen) {
+__global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeMem t, TrainMem tr, const uint64_t* __restrict__ zob, int16_t* __restrict__ chosen) {
   const D dm(g);
   using BB = typename D::BB;
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,6 +318,17 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
         if(ch[pos] != -1) { if(k < eN[pos]) { move = pos; break; } k -= eN[pos]; }
     } else move = bestPos;
     if(move >= 0) {
+      if(tr.enabled) {
+        const int k = tr.recCount[gi];
+        if(k < tr.maxPlies) {
+          const size_t r = (size_t)gi * tr.maxPlies + k;
+          if(k == 0) tr.recGameId[gi] = s.id;
+          tr.recBlack[r] = (uint64_t)s.black; tr.recWhite[r] = (uint64_t)s.white; tr.recMisc[r] = s.misc;
+          tr.recN[r] = nd.N(); tr.recW[r] = nd.W();
+          for(int pos = 0; pos < c.P; pos++) tr.recVisits[r * c.P + pos] = (int16_t)(ch[pos] != -1 ? min(eN[pos], 32767) : 0);
+          tr.recCount[gi] = k + 1;
+        }
+      }
       BB L[4]; bool illegal;
       Geom g2 = g; g2.autoRefill = 0;
       stepGame(dm, g2, s, move, true, zob, L, illegal);
@@ -316,6 +344,130 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
   }
   t.nodeCount[gi] = 0;
   if(chosen) chosen[gi] = (int16_t)move;
+}
+
+// One warp per finished game: turn its records into training rows.
+template <class D>
+__global__ void __launch_bounds__(128) k_emit_rows(const Geom g, const SearchCfg c, State root, TrainMem tr) {
+  const D dm(g);
+  using BB = typename D::BB;
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  const uint64_t fmisc = root.misc[gi];
+  const int R = tr.recCount[gi];
+  if(!(flagsOf(fmisc) & 1) || R == 0) return;
+  const int HW = dm.HW(), P = c.P, PB = (HW + 7) / 8;
+  int base = 0;
+  if(lane == 0) {
+    base = atomicAdd(&tr.rowCount[0], R);
+    if(base + R > tr.maxRows) { atomicAdd(&tr.rowCount[0], -R); atomicAdd(&tr.rowCount[1], R); base = -1; }
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  if(base >= 0) {
+    const int winner = (flagsOf(fmisc) >> 1) & 3;
+    const double finalWin = winner == 2 ? 1.0 : winner == 1 ? 0.0 : 0.5;   // ScoreValue::whiteWinsOfWinner, draw = 0.5 (ledger C)
+    const BB finalB = (BB)root.black[gi], finalW = (BB)root.white[gi];
+    // longest same-colour run through every stone at the end (recordMaxConsecutives, canonical: stones only, 4 line directions)
+    BB runAtLeast[2][8];   // [colour][len-1] cells of that colour lying in a run of length >= len (len 1..8)
+    const int maxLen = max(dm.W(), dm.H());   // no run is longer (also keeps every shift inside the bitboard width)
+    for(int col = 0; col < 2; col++) {
+      const BB m = col ? finalW : finalB;
+      for(int len = 1; len <= 8; len++) {
+        BB acc = 0;
+        if(len <= maxLen)
+          for(int d = 0; d < 4; d++) acc |= coverAtLeast<D>(m, shiftOf(dm, d), len);
+        runAtLeast[col][len - 1] = len == 1 ? m : acc;
+      }
+    }
+    const uint64_t gid = tr.recGameId[gi];
+    const uint64_t gh0 = splitmix64(gid), gh1 = splitmix64(gid ^ PHI);
+    for(int i = 0; i < R; i++) {
+      const size_t r = (size_t)gi * tr.maxPlies + i;
+      const size_t row = (size_t)base + i;
+      GameRegs<BB> s;
+      s.black = (BB)tr.recBlack[r]; s.white = (BB)tr.recWhite[r]; s.misc = tr.recMisc[r]; s.h0 = s.h1 = 0; s.id = gid;
+      const int pla = (flagsOf(s.misc) >> 3) & 3;
+      // binaryInputNCHWPacked: the V1 planes of the position, bits big-endian within each byte (packBits, trainingwrite.cpp:218-233)
+      BB empty = (BB)g.all & ~(s.black | s.white);
+      int lastCell = histPla(s.misc, 0) ? histCell(s.misc, 0) : -1;
+      BB L[4];
+      legalMasks(dm, g, empty, lastCell, lastDirOf(s.misc), L);
+      uint64_t planes[15];
+      v1Planes(dm, g, s, L, planes, 1);
+      for(int j = lane; j < 15 * PB; j += 32) {
+        const int ch = j / PB, byte = j - ch * PB;
+        const uint64_t dense = toDense(dm, (BB)planes[ch]);
+        tr.outBin[row * 15 * PB + j] = (uint8_t)(__brev((uint32_t)((dense >> (8 * byte)) & 0xff)) >> 24);
+      }
+      // policy targets: this turn's visits, next turn's visits (uniform ones with weight 0 on the last turn)
+      for(int pos = lane; pos < P; pos += 32) {
+        tr.outPolicy[(row * 2 + 0) * P + pos] = tr.recVisits[r * P + pos];
+        tr.outPolicy[(row * 2 + 1) * P + pos] = (i + 1 < R) ? tr.recVisits[(r + 1) * P + pos] : (int16_t)1;
+      }
+      // spatial value targets [5][HW]: final ownership, 0, board 2 plies ahead, board 6 plies ahead, final longest run
+      auto boardAt = [&](int k, BB& b, BB& w) {   // position before move k; k == R: the final position
+        if(k >= R) { b = finalB; w = finalW; } else { b = (BB)tr.recBlack[(size_t)gi * tr.maxPlies + k]; w = (BB)tr.recWhite[(size_t)gi * tr.maxPlies + k]; }
+      };
+      BB b2, w2, b3, w3;
+      boardAt(min(i + 2, R), b2, w2);
+      boardAt(min(i + 6, R), b3, w3);
+      for(int cell = lane; cell < HW; cell += 32) {
+        const int bit = padOf(dm, cell);
+        auto rel = [&](BB b, BB w) -> int8_t {
+          const int col = ((b >> bit) & 1) ? 1 : ((w >> bit) & 1) ? 2 : 0;
+          return (int8_t)(col == 0 ? 0 : (col == pla ? 1 : -1));
+        };
+        int8_t* v = tr.outValue + row * 5 * HW;
+        v[cell] = rel(finalB, finalW);
+        v[HW + cell] = 0;
+        v[2 * HW + cell] = rel(b2, w2);
+        v[3 * HW + cell] = rel(b3, w3);
+        int len = 0;
+        for(int col = 0; col < 2; col++)
+          for(int l = 1; l <= 8; l++) if((runAtLeast[col][l - 1] >> bit) & 1) len = max(len, l);
+        v[4 * HW + cell] = (int8_t)len;
+      }
+      if(lane == 0) {
+        tr.outGlobalIn[row] = (float)dm.K();
+        float* gt = tr.outGlobalT + row * 64;
+        for(int k = 0; k < 64; k++) gt[k] = 0.f;
+        // td-like value targets from the player to move's view (fillValueTDTargets, trainingwrite.cpp:286-314): white win/loss
+        // targets of turn j are the search's root estimate ((1 +- utility)/2), of the end the game result
+        for(int f = 0; f < 5; f++) {
+          const double nowFactor = tr.nowFactor[f];
+          double winV = 0.0, lossV = 0.0, weightLeft = 1.0;
+          for(int j = i; j <= R; j++) {
+            double weightNow;
+            if(j == R) { weightNow = weightLeft; weightLeft = 0.0; }
+            else { weightNow = __dmul_rn(weightLeft, nowFactor); weightLeft = __dmul_rn(weightLeft, __dsub_rn(1.0, nowFactor)); }
+            double tw, tl;
+            if(j == R) { tw = finalWin; tl = __dsub_rn(1.0, finalWin); }
+            else {
+              const double u = __ddiv_rn(tr.recW[(size_t)gi * tr.maxPlies + j], (double)tr.recN[(size_t)gi * tr.maxPlies + j]);
+              tw = __dmul_rn(__dadd_rn(1.0, u), 0.5); tl = __dmul_rn(__dsub_rn(1.0, u), 0.5);
+            }
+            winV = __dadd_rn(winV, __dmul_rn(weightNow, pla == 2 ? tw : tl));
+            lossV = __dadd_rn(lossV, __dmul_rn(weightNow, pla == 2 ? tl : tw));
+          }
+          gt[2 * f] = (float)winV; gt[2 * f + 1] = (float)lossV;
+        }
+        gt[25] = 1.0f;                          // row weight
+        gt[26] = 1.0f;                          // policy target weight
+        gt[27] = 1.0f;                          // final ownership weight
+        gt[28] = (i + 1 < R) ? 1.0f : 0.0f;     // next-turn policy target weight
+        gt[33] = 1.0f;                          // future position weight
+        for(int k = 36; k <= 40; k++) gt[k] = 1.0f;   // history masks (the reference draws them at random with p = 0.98 each)
+        gt[41] = (float)(gh0 & 0x3FFFFF); gt[42] = (float)((gh0 >> 22) & 0x3FFFFF); gt[43] = (float)((gh0 >> 44) & 0xFFFFF);
+        gt[44] = (float)(gh1 & 0x3FFFFF); gt[45] = (float)((gh1 >> 22) & 0x3FFFFF); gt[46] = (float)((gh1 >> 44) & 0xFFFFF);
+        gt[51] = (float)numTurnsOf(s.misc);     // turn idx
+        gt[60] = (float)tr.recN[r];             // visits of the search behind the row
+        gt[63] = 1.0f;                          // data format version
+      }
+    }
+  }
+  __syncwarp();
+  if(lane == 0) tr.recCount[gi] = 0;
 }
 
 template <class BB>
@@ -343,6 +495,7 @@ struct kc_search {
   kc::TreeMem tree;
   float* d_policy = nullptr; float* d_winLoss = nullptr; float* d_misc = nullptr; uint64_t* d_nnHash = nullptr;
   int16_t* d_chosen = nullptr;
+  kc::TrainMem train = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
 };
@@ -426,6 +579,9 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.nodes); cudaFree(S->tree.nodeCount); cudaFree(S->tree.pathNode); cudaFree(S->tree.pathPos); cudaFree(S->tree.pathLen);
   cudaFree(S->tree.leafKind); cudaFree(S->tree.leafValue); cudaFree(S->tree.leafNextPla); cudaFree(S->tree.stats);
   cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
+  { kc::TrainMem& t = S->train;
+    cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);
+    cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
   kc_games_destroy(S->root); kc_games_destroy(S->leaf);
@@ -497,9 +653,15 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     }
     KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
     if(runVisits(S)) return 1;
-    if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, R->d_zob, S->d_chosen);
-    else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, R->d_zob, S->d_chosen);
+    if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
+    else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     S->launches++;
+    if(S->train.enabled) {
+      const int wb = (c.numGames * 32 + 127) / 128;
+      if(isStatic5(R->geom)) k_emit_rows<StaticDims<5, 5, 4>><<<wb, 128, 0, st>>>(R->geom, c, R->st, S->train);
+      else k_emit_rows<DynDims><<<wb, 128, 0, st>>>(R->geom, c, R->st, S->train);
+      S->launches++;
+    }
   }
   KC_CUDA(cudaEventRecord(S->ev1, st));
   KC_CUDA(cudaGetLastError());
@@ -514,6 +676,56 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     acc->gamesFinished += hs[4]; acc->blackWins += hs[5]; acc->whiteWins += hs[6]; acc->draws += hs[7];
     acc->batchRows += c.compact ? hs[1] : (uint64_t)c.numGames * c.maxVisits * moves;
   }
+  return 0;
+}
+
+int kc_search_enable_training_rows(kc_search* S, int maxRows) {
+  KC_CHECK(S && maxRows > 0, "kc_search_enable_training_rows: bad argument");
+  KC_CHECK(!S->train.enabled, "kc_search_enable_training_rows: already enabled");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  const SearchCfg& c = S->cfg;
+  const Geom& g = S->root->geom;
+  TrainMem& t = S->train;
+  const size_t n = (size_t)c.numGames, mp = (size_t)g.HW, PB = (size_t)(g.HW + 7) / 8;
+  t.maxPlies = g.HW; t.maxRows = maxRows;
+  KC_CUDA(cudaMalloc(&t.recBlack, n * mp * 8)); KC_CUDA(cudaMalloc(&t.recWhite, n * mp * 8)); KC_CUDA(cudaMalloc(&t.recMisc, n * mp * 8));
+  KC_CUDA(cudaMalloc(&t.recN, n * mp * 4)); KC_CUDA(cudaMalloc(&t.recW, n * mp * 8));
+  KC_CUDA(cudaMalloc(&t.recVisits, n * mp * c.P * 2));
+  KC_CUDA(cudaMalloc(&t.recCount, n * 4)); KC_CUDA(cudaMemset(t.recCount, 0, n * 4));
+  KC_CUDA(cudaMalloc(&t.recGameId, n * 8));
+  KC_CUDA(cudaMalloc(&t.rowCount, 8)); KC_CUDA(cudaMemset(t.rowCount, 0, 8));
+  KC_CUDA(cudaMalloc(&t.outBin, (size_t)maxRows * 15 * PB)); KC_CUDA(cudaMalloc(&t.outGlobalIn, (size_t)maxRows * 4));
+  KC_CUDA(cudaMalloc(&t.outPolicy, (size_t)maxRows * 2 * c.P * 2)); KC_CUDA(cudaMalloc(&t.outGlobalT, (size_t)maxRows * 64 * 4));
+  KC_CUDA(cudaMalloc(&t.outValue, (size_t)maxRows * 5 * g.HW));
+  const double area = (double)g.HW;
+  t.nowFactor[0] = 0.0; t.nowFactor[1] = 1.0 / (1.0 + area * 0.176); t.nowFactor[2] = 1.0 / (1.0 + area * 0.056);
+  t.nowFactor[3] = 1.0 / (1.0 + area * 0.016); t.nowFactor[4] = 1.0;
+  t.enabled = 1;
+  return 0;
+}
+
+int kc_search_read_training_rows(kc_search* S, int* numRows, int* numDropped, uint8_t* binaryInputNCHWPacked, float* globalInputNC,
+                                 int16_t* policyTargetsNCMove, float* globalTargetsNC, int8_t* valueTargetsNCHW, int clear) {
+  KC_CHECK(S && numRows, "kc_search_read_training_rows: null argument");
+  KC_CHECK(S->train.enabled, "kc_search_read_training_rows: call kc_search_enable_training_rows first");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
+  const SearchCfg& c = S->cfg;
+  const Geom& g = S->root->geom;
+  const TrainMem& t = S->train;
+  int cnt[2];
+  KC_CUDA(cudaMemcpy(cnt, t.rowCount, 8, cudaMemcpyDeviceToHost));
+  const size_t rows = (size_t)cnt[0], PB = (size_t)(g.HW + 7) / 8;
+  *numRows = cnt[0];
+  if(numDropped) *numDropped = cnt[1];
+  if(rows) {
+    if(binaryInputNCHWPacked) KC_CUDA(cudaMemcpy(binaryInputNCHWPacked, t.outBin, rows * 15 * PB, cudaMemcpyDeviceToHost));
+    if(globalInputNC) KC_CUDA(cudaMemcpy(globalInputNC, t.outGlobalIn, rows * 4, cudaMemcpyDeviceToHost));
+    if(policyTargetsNCMove) KC_CUDA(cudaMemcpy(policyTargetsNCMove, t.outPolicy, rows * 2 * c.P * 2, cudaMemcpyDeviceToHost));
+    if(globalTargetsNC) KC_CUDA(cudaMemcpy(globalTargetsNC, t.outGlobalT, rows * 64 * 4, cudaMemcpyDeviceToHost));
+    if(valueTargetsNCHW) KC_CUDA(cudaMemcpy(valueTargetsNCHW, t.outValue, rows * 5 * g.HW, cudaMemcpyDeviceToHost));
+  }
+  if(clear) KC_CUDA(cudaMemset(t.rowCount, 0, 8));
   return 0;
 }
 

@@ -215,6 +215,10 @@ void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_sea
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                    uint8_t* orderOut, uint64_t counters[3] /* += visits, evaluations, terminal visits */);
 int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int ply, int temperaturePlies, uint64_t seed, uint64_t gameId);
+/* Training rows of one finished game (restatement of TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566, with the
+ * canonical choices documented at kc_search_read_training_rows); arrays as in the reference's npz, R rows. */
+void ko_training_rows(int x_size, int y_size, int win_len, int R, const int32_t* movePos, const int32_t* rootN, const double* rootW,
+                      const int16_t* visits, uint64_t gameId, uint8_t* bin, float* globalIn, int16_t* policy, float* globalT, int8_t* value);
 
 #ifdef __cplusplus
 }

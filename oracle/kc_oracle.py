@@ -93,6 +93,8 @@ def lib():
         l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
         l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        l.ko_training_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp, vp]
+        l.ko_game_color_at.argtypes = [vp, C.c_int, C.c_int]
         _lib = l
     return _lib
 
@@ -293,3 +295,17 @@ def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
 def search_choose(edge_visits, order, ply, temperature_plies, seed, game_id):
     ev = np.ascontiguousarray(edge_visits, np.int32); od = np.ascontiguousarray(order, np.uint8)
     return lib().ko_search_choose(_p(ev), _p(od), len(ev), ply, temperature_plies, seed, game_id)
+
+
+def training_rows(x, y, k, moves, root_n, root_w, visits, game_id):
+    """Oracle training rows of one finished game (dict of the reference's npz arrays, R rows)."""
+    R, HW = len(moves), x * y
+    P = 4 * HW
+    mv = np.ascontiguousarray(moves, np.int32); rn = np.ascontiguousarray(root_n, np.int32); rw = np.ascontiguousarray(root_w, np.float64)
+    vs = np.ascontiguousarray(visits, np.int16).reshape(R, P)
+    out = dict(binaryInputNCHWPacked=np.zeros((R, 15, (HW + 7) // 8), np.uint8), globalInputNC=np.zeros((R, 1), np.float32),
+               policyTargetsNCMove=np.zeros((R, 2, P), np.int16), globalTargetsNC=np.zeros((R, 64), np.float32),
+               valueTargetsNCHW=np.zeros((R, 5, y, x), np.int8))
+    lib().ko_training_rows(x, y, k, R, _p(mv), _p(rn), _p(rw), _p(vs), game_id, _p(out["binaryInputNCHWPacked"]), _p(out["globalInputNC"]),
+                           _p(out["policyTargetsNCMove"]), _p(out["globalTargetsNC"]), _p(out["valueTargetsNCHW"]))
+    return out

@@ -212,4 +212,102 @@ int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int
   return bestPos;
 }
 
+// Training rows of one finished game (TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566, restated with the
+// canonical choices listed at kc_search_read_training_rows in include/katacoffee_b200.h): the game is replayed from the
+// empty board with `movePos`, turn i carries the root visits / utility sum / visit counts of the search that chose move i.
+void ko_training_rows(int x_size, int y_size, int win_len, int R, const int32_t* movePos, const int32_t* rootN, const double* rootW,
+                      const int16_t* visits, uint64_t gameId, uint8_t* bin, float* globalIn, int16_t* policy, float* globalT, int8_t* value) {
+  const int HW = x_size * y_size, P = 4 * HW, PB = (HW + 7) / 8;
+  std::vector<ko_game*> pos(R + 1);
+  pos[0] = ko_game_create(x_size, y_size, win_len);
+  for(int i = 0; i < R; i++) {
+    pos[i + 1] = ko_game_create(x_size, y_size, win_len);
+    ko_game_copy(pos[i + 1], pos[i]);
+    ko_game_play(pos[i + 1], movePos[i]);
+  }
+  const ko_game* fin = pos[R];
+  const int winner = ko_game_winner(fin);
+  const double finalWin = winner == 2 ? 1.0 : winner == 1 ? 0.0 : 0.5;
+  const double area = (double)HW;
+  const double nowFactors[5] = {0.0, 1.0 / (1.0 + area * 0.176), 1.0 / (1.0 + area * 0.056), 1.0 / (1.0 + area * 0.016), 1.0};
+  const uint64_t gh0 = ko_splitmix64(gameId), gh1 = ko_splitmix64(gameId ^ PHI);
+  // longest same-colour run through each final stone, over the four line directions
+  std::vector<int> maxRun(HW, 0);
+  const int DX[4] = {0, -1, -1, 1}, DY[4] = {-1, 0, -1, -1};
+  for(int y = 0; y < y_size; y++)
+    for(int x = 0; x < x_size; x++) {
+      const int col = ko_game_color_at(fin, x, y);
+      if(col == 0) continue;
+      for(int d = 0; d < 4; d++) {
+        int len = 1;
+        for(int sgn = -1; sgn <= 1; sgn += 2)
+          for(int k = 1;; k++) {
+            const int xx = x + sgn * k * DX[d], yy = y + sgn * k * DY[d];
+            if(xx < 0 || yy < 0 || xx >= x_size || yy >= y_size || ko_game_color_at(fin, xx, yy) != col) break;
+            len++;
+          }
+        if(len > maxRun[y * x_size + x]) maxRun[y * x_size + x] = len;
+      }
+    }
+  std::vector<float> planes((size_t)15 * HW);
+  for(int i = 0; i < R; i++) {
+    const ko_game* g = pos[i];
+    const int pla = ko_game_next_pla(g);
+    float glob = 0.f;
+    ko_game_fill_row_v1(g, pla, x_size, y_size, 0, planes.data(), &glob);
+    for(int c = 0; c < 15; c++)
+      for(int byte = 0; byte < PB; byte++) {
+        uint8_t b = 0;
+        for(int k = 0; k < 8 && byte * 8 + k < HW; k++) b |= (uint8_t)((uint8_t)planes[(size_t)c * HW + byte * 8 + k] << (7 - k));
+        bin[((size_t)i * 15 + c) * PB + byte] = b;
+      }
+    globalIn[i] = glob;
+    for(int p = 0; p < P; p++) {
+      policy[((size_t)i * 2 + 0) * P + p] = visits[(size_t)i * P + p];
+      policy[((size_t)i * 2 + 1) * P + p] = (i + 1 < R) ? visits[(size_t)(i + 1) * P + p] : (int16_t)1;
+    }
+    const ko_game* g2 = pos[std::min(i + 2, R)];
+    const ko_game* g3 = pos[std::min(i + 6, R)];
+    auto rel = [&](const ko_game* gg, int x, int y) -> int8_t {
+      const int col = ko_game_color_at(gg, x, y);
+      return (int8_t)(col == 0 ? 0 : (col == pla ? 1 : -1));
+    };
+    int8_t* v = value + (size_t)i * 5 * HW;
+    for(int y = 0; y < y_size; y++)
+      for(int x = 0; x < x_size; x++) {
+        const int cell = y * x_size + x;
+        v[cell] = rel(fin, x, y);
+        v[HW + cell] = 0;
+        v[2 * HW + cell] = rel(g2, x, y);
+        v[3 * HW + cell] = rel(g3, x, y);
+        v[4 * HW + cell] = (int8_t)maxRun[cell];
+      }
+    float* gt = globalT + (size_t)i * 64;
+    for(int k = 0; k < 64; k++) gt[k] = 0.f;
+    for(int f = 0; f < 5; f++) {
+      const double nowFactor = nowFactors[f];
+      double winV = 0.0, lossV = 0.0, weightLeft = 1.0;
+      for(int j = i; j <= R; j++) {
+        double weightNow;
+        if(j == R) { weightNow = weightLeft; weightLeft = 0.0; }
+        else { weightNow = weightLeft * nowFactor; weightLeft = weightLeft * (1.0 - nowFactor); }
+        double tw, tl;
+        if(j == R) { tw = finalWin; tl = 1.0 - finalWin; }
+        else { const double u = rootW[j] / (double)rootN[j]; tw = (1.0 + u) * 0.5; tl = (1.0 - u) * 0.5; }
+        winV = winV + weightNow * (pla == 2 ? tw : tl);
+        lossV = lossV + weightNow * (pla == 2 ? tl : tw);
+      }
+      gt[2 * f] = (float)winV; gt[2 * f + 1] = (float)lossV;
+    }
+    gt[25] = 1.0f; gt[26] = 1.0f; gt[27] = 1.0f; gt[28] = (i + 1 < R) ? 1.0f : 0.0f; gt[33] = 1.0f;
+    for(int k = 36; k <= 40; k++) gt[k] = 1.0f;
+    gt[41] = (float)(gh0 & 0x3FFFFF); gt[42] = (float)((gh0 >> 22) & 0x3FFFFF); gt[43] = (float)((gh0 >> 44) & 0xFFFFF);
+    gt[44] = (float)(gh1 & 0x3FFFFF); gt[45] = (float)((gh1 >> 22) & 0x3FFFFF); gt[46] = (float)((gh1 >> 44) & 0xFFFFF);
+    gt[51] = (float)ko_game_num_turns(g);
+    gt[60] = (float)rootN[i];
+    gt[63] = 1.0f;
+  }
+  for(ko_game* g : pos) ko_game_destroy(g);
+}
+
 }  // extern "C"
