@@ -290,13 +290,16 @@ def main():
     # leaves are one batch through the hot path; a move = SELFPLAY_VISITS iterations
     selfplay = None
     if not args.no_selfplay:
-        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True)
+        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True, reuseTree=True)
         search.reset(seed=SEED, firstGameId=shard.first_game_id(rank))
         # steady-state mix of a self-play run: game g starts the timed move after (g mod STAGGER) random-legal plies, as
         # games that were refilled at different times do (movePos -2 = the counter-RNG move, -1 = stay)
         lane = np.arange(G)
         for t in range(SELFPLAY_STAGGER):
             search.games.step(np.where(lane % SELFPLAY_STAGGER > t, -2, -1).astype(np.int16))
+        # one untimed move first: it builds the trees whose chosen subtrees the timed move re-uses, as every move of a
+        # running self-play does (Search::makeMove)
+        search.play(1)
         handle.trunkTime()
         barrier()
         sp_stats, _, sp_ms = search.play(args.selfplay_moves)
@@ -307,8 +310,8 @@ def main():
         selfplay = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
                     "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
                     "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
-                    "ms_per_iteration": sp_ms_max / (args.visits * args.selfplay_moves), "games_finished": int(sp[4]),
-                    "search": "lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), visit-proportional move choice",
+                    "ms_per_move_batch": sp_ms_max / args.selfplay_moves, "games_finished": int(sp[4]),
+                    "search": "lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
                     "kernel_launches": int(search.launchCount())}
         search.close()
 

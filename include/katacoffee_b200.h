@@ -237,6 +237,9 @@ typedef struct {
   int32_t autoRefill;           /* restart finished games with fresh ids before the next search */
   int32_t noCompaction;         /* 0 (default): on the bf16 path only the leaves that need the net are batched (terminal
                                    visits take no row); 1: one row per game, idle rows evaluated and ignored */
+  int32_t reuseTree;            /* keep the subtree of the move played for the next search (Search::makeMove); its visits count
+                                   towards maxVisits, so later searches need fewer evaluations */
+  int32_t pad_;
   double cpuctExploration;      /* SearchParams::cpuctExploration (1.0) */
   double fpuReductionMax;       /* SearchParams::fpuReductionMax (0.2) */
   double rootFpuReductionMax;   /* SearchParams::rootFpuReductionMax (0.2) */

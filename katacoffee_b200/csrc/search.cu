@@ -48,6 +48,7 @@ struct SearchCfg {
   int numGames;
   int autoRefill;
   int compact;       // leaves that need the net are packed into a dense batch (slot = arrival order); 0: slot = game
+  int reuseTree;     // keep the chosen child's subtree for the next search (Search::makeMove)
   double cpuct, fpuRed, rootFpuRed;
   uint64_t seed;
 };
@@ -63,6 +64,9 @@ struct TreeMem {
   int* leafNextPla;       // [G] player to move at a new node
   int* leafSlot;          // [G] row of the evaluation batch holding this game's leaf
   int* evalCount;         // [1] rows of the current evaluation batch (compact mode)
+  uint8_t* nodesAlt;      // second tree buffer: re-rooting copies the kept subtree there, then the two swap
+  int* rerootQueue;       // [G][maxNodes] breadth-first order of the kept subtree (old node indices)
+  int* active;            // [1] set by k_select when any game still had a visit to make
   unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws
 };
 
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(128) k_select(const Geom g, const SearchCfg c,
     }
   }
   if(lane == 0) {
+    if(kind != 0) *t.active = 1;
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
     t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
     const bool needsNet = kind == 1 || kind == 4;
@@ -342,8 +347,51 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
       }
     }
   }
-  t.nodeCount[gi] = 0;
+  if(!c.reuseTree) t.nodeCount[gi] = 0;   // with tree re-use k_reroot decides what survives
   if(chosen) chosen[gi] = (int16_t)move;
+}
+
+// Tree re-use (Search::makeMove): one warp per game copies the subtree under the move just played, breadth first, into the
+// other tree buffer (new root = node 0) and remaps the child indices; no subtree (unexpanded or terminal child, finished
+// game, no move) leaves an empty tree.
+__global__ void __launch_bounds__(128) k_reroot(const SearchCfg c, TreeMem t, State root, const int16_t* __restrict__ chosen) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  const uint8_t* src = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  uint8_t* dst = t.nodesAlt + (size_t)gi * c.maxNodes * c.nodeStride;
+  int* queue = t.rerootQueue + (size_t)gi * c.maxNodes;
+  const int move = chosen[gi];
+  int count = 0;
+  if(move >= 0 && t.nodeCount[gi] > 0 && !(flagsOf(root.misc[gi]) & 1)) {
+    const int first = NodeRef{const_cast<uint8_t*>(src), c.P}.child()[move];
+    if(first >= 0) {
+      if(lane == 0) queue[0] = first;
+      count = 1;
+      __syncwarp();
+      for(int i = 0; i < count; i++) {
+        const int old = queue[i];
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)old * c.nodeStride);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)i * c.nodeStride);
+        for(int k = lane; k < c.nodeStride / 16; k += 32) d4[k] = s4[k];
+        __syncwarp();
+        // children in policy-index order get the next free indices
+        int* dch = NodeRef{dst + (size_t)i * c.nodeStride, c.P}.child();
+        for(int p0 = 0; p0 < c.P; p0 += 32) {
+          const int pos = p0 + lane;
+          const int ch = pos < c.P ? dch[pos] : -1;
+          const unsigned m = __ballot_sync(0xffffffffu, ch >= 0);
+          if(ch >= 0) {
+            const int ni = count + __popc(m & ((1u << lane) - 1));
+            queue[ni] = ch;
+            dch[pos] = ni;
+          }
+          count += __popc(m);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if(lane == 0) t.nodeCount[gi] = count;
 }
 
 // One warp per finished game: turn its records into training rows.
@@ -511,6 +559,14 @@ int runVisits(kc_search* S) {
   cudaStream_t st = Lf->stream;
   const int warpBlocks = (c.numGames * 32 + 127) / 128;
   for(int it = 0; it < c.maxVisits; it++) {
+    if(c.reuseTree && it > 0 && (it & 31) == 0) {
+      // games that kept a subtree finish their visit budget early: stop once no game had a visit left to make
+      int active = 0;
+      KC_CUDA(cudaMemcpyAsync(&active, S->tree.active, 4, cudaMemcpyDeviceToHost, st));
+      KC_CUDA(cudaStreamSynchronize(st));
+      if(!active) break;
+      KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
+    }
     if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount, 0, 4, st));
     if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
     else k_select<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
@@ -549,14 +605,20 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.maxNodes = p->maxVisits; c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
   c.numGames = numGames; c.autoRefill = p->autoRefill ? 1 : 0;
   c.compact = (handleOrNull && kc::handleIsBf16(handleOrNull) && !p->noCompaction) ? 1 : 0;
+  c.reuseTree = p->reuseTree ? 1 : 0;
   c.cpuct = p->cpuctExploration; c.fpuRed = p->fpuReductionMax; c.rootFpuRed = p->rootFpuReductionMax;
   c.seed = 0;
   const size_t n = (size_t)numGames;
-  const size_t treeBytes = n * c.maxNodes * c.nodeStride;
+  const size_t treeBytes = n * c.maxNodes * c.nodeStride * (c.reuseTree ? 2 : 1);
   size_t freeB = 0, totalB = 0;
   KC_CUDA(cudaMemGetInfo(&freeB, &totalB));
   KC_CHECK(treeBytes + (1ULL << 30) < freeB, "kc_search_create: the trees (numGames x maxVisits x " + std::to_string(c.nodeStride) + " B) do not fit in free device memory");
-  KC_CUDA(cudaMalloc(&S->tree.nodes, treeBytes));
+  KC_CUDA(cudaMalloc(&S->tree.nodes, treeBytes / (c.reuseTree ? 2 : 1)));
+  if(c.reuseTree) {
+    KC_CUDA(cudaMalloc(&S->tree.nodesAlt, treeBytes / 2));
+    KC_CUDA(cudaMalloc(&S->tree.rerootQueue, n * c.maxNodes * 4));
+  }
+  KC_CUDA(cudaMalloc(&S->tree.active, 4)); KC_CUDA(cudaMemset(S->tree.active, 0, 4));
   KC_CUDA(cudaMalloc(&S->tree.nodeCount, n * 4)); KC_CUDA(cudaMemset(S->tree.nodeCount, 0, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.pathNode, n * MAX_PATH * 4)); KC_CUDA(cudaMalloc(&S->tree.pathPos, n * MAX_PATH));
   KC_CUDA(cudaMalloc(&S->tree.pathLen, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafKind, n * 4));
@@ -579,6 +641,7 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.nodes); cudaFree(S->tree.nodeCount); cudaFree(S->tree.pathNode); cudaFree(S->tree.pathPos); cudaFree(S->tree.pathLen);
   cudaFree(S->tree.leafKind); cudaFree(S->tree.leafValue); cudaFree(S->tree.leafNextPla); cudaFree(S->tree.stats);
   cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
+  cudaFree(S->tree.nodesAlt); cudaFree(S->tree.rerootQueue); cudaFree(S->tree.active);
   { kc::TrainMem& t = S->train;
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
@@ -651,11 +714,17 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
       else k_refill<uint64_t><<<blocks, 128, 0, st>>>(R->geom, c, R->st);
       S->launches++;
     }
-    KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
+    if(!c.reuseTree) KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
+    KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
     if(runVisits(S)) return 1;
     if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     S->launches++;
+    if(c.reuseTree) {
+      k_reroot<<<(c.numGames * 32 + 127) / 128, 128, 0, st>>>(c, S->tree, R->st, S->d_chosen);
+      std::swap(S->tree.nodes, S->tree.nodesAlt);
+      S->launches++;
+    }
     if(S->train.enabled) {
       const int wb = (c.numGames * 32 + 127) / 128;
       if(isStatic5(R->geom)) k_emit_rows<StaticDims<5, 5, 4>><<<wb, 128, 0, st>>>(R->geom, c, R->st, S->train);

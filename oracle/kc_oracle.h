@@ -208,12 +208,20 @@ void ko_postprocess(float* policy, int policySize, const uint32_t* legalMask, fl
  * evaluator that the CUDA search also implements, so trees can be compared exactly.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
-  int32_t maxVisits, temperaturePlies, autoRefill, noCompaction;
+  int32_t maxVisits, temperaturePlies, autoRefill, noCompaction, reuseTree, pad_;
   double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                    uint8_t* orderOut, uint64_t counters[3] /* += visits, evaluations, terminal visits */);
+typedef struct ko_search ko_search;   /* persistent tree: continue() searches on, advance() re-roots at the move played */
+ko_search* ko_search_create(void);
+void ko_search_destroy(ko_search* s);
+void ko_search_clear(ko_search* s);
+void ko_search_continue(ko_search* s, const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                        int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                        uint8_t* orderOut, uint64_t counters[3]);
+void ko_search_advance(ko_search* s, int movePos);
 int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int ply, int temperaturePlies, uint64_t seed, uint64_t gameId);
 /* Training rows of one finished game (restatement of TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566, with the
  * canonical choices documented at kc_search_read_training_rows); arrays as in the reference's npz, R rows. */

@@ -93,6 +93,11 @@ def lib():
         l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
         l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        l.ko_search_create.restype = vp
+        l.ko_search_destroy.argtypes = [vp]
+        l.ko_search_clear.argtypes = [vp]
+        l.ko_search_continue.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        l.ko_search_advance.argtypes = [vp, C.c_int]
         l.ko_training_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp, vp]
         l.ko_game_color_at.argtypes = [vp, C.c_int, C.c_int]
         _lib = l
@@ -274,7 +279,7 @@ def postprocess(policy, legal_mask, value2, misc2, next_pla, temp=1.0):
 
 class SearchParams(C.Structure):
     """Same layout as kc_search_params (include/katacoffee_b200.h)."""
-    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32),
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("pad_", C.c_int32),
                 ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
 
 
@@ -282,7 +287,7 @@ def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
     """One oracle search from `game` (a Game); model=None uses the integer-hash evaluator.  Returns a dict with the
     root statistics (arrays over the policy index) and the visit counters."""
     P = 4 * game.HW
-    sp = SearchParams(max_visits, 0, 0, 0, cpuct, fpu, root_fpu)
+    sp = SearchParams(max_visits, 0, 0, 0, 0, 0, cpuct, fpu, root_fpu)
     rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
     ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
     cnt = np.zeros(3, np.uint64)
@@ -290,6 +295,32 @@ def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
                         _p(order), _p(cnt))
     return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
             "counters": cnt}
+
+
+class PersistentSearch:
+    """Oracle search that keeps the chosen child's subtree between moves (tree re-use)."""
+
+    def __init__(self):
+        self._s = lib().ko_search_create()
+
+    def __del__(self):
+        if getattr(self, "_s", None):
+            lib().ko_search_destroy(self._s)
+            self._s = None
+
+    def run(self, game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
+        P = 4 * game.HW
+        sp = SearchParams(max_visits, 0, 0, 0, 1, 0, cpuct, fpu, root_fpu)
+        rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
+        ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
+        cnt = np.zeros(3, np.uint64)
+        lib().ko_search_continue(self._s, game._g, game.W, game.H, C.byref(sp), None if model is None else model._m, _p(rv), _p(rw), _p(ev),
+                                 _p(ew), _p(pol), _p(order), _p(cnt))
+        return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
+                "counters": cnt}
+
+    def advance(self, move_pos):
+        lib().ko_search_advance(self._s, int(move_pos))
 
 
 def search_choose(edge_visits, order, ply, temperature_plies, seed, game_id):

@@ -85,12 +85,11 @@ struct Evaluator {
 
 extern "C" {
 
-void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
-                   int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
-                   uint8_t* orderOut, uint64_t counters[3]) {
+static void searchRunOnTree(std::vector<Node>& nodes, const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p,
+                            const ko_model* modelOrNull, int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits,
+                            double* edgeUtilitySum, float* policyOut, uint8_t* orderOut, uint64_t counters[3]) {
   const int P = 4 * x_size * y_size;
   Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
-  std::vector<Node> nodes;
   nodes.reserve(p->maxVisits);
   uint64_t cVisits = 0, cEvals = 0, cTerminal = 0;
   ko_game* g = ko_game_create(x_size, y_size, 4);
@@ -191,6 +190,41 @@ void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_sea
     if(orderOut) orderOut[pos] = ex ? nodes[0].order[pos] : 255;
   }
   if(counters) { counters[0] += cVisits; counters[1] += cEvals; counters[2] += cTerminal; }
+}
+
+void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                   int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                   uint8_t* orderOut, uint64_t counters[3]) {
+  std::vector<Node> nodes;
+  searchRunOnTree(nodes, rootGame, x_size, y_size, p, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters);
+}
+
+// Persistent tree with re-use between moves (Search::makeMove keeps the chosen child's subtree): run() continues the
+// search of the current tree until the root has maxVisits visits, advance() re-roots at the child reached by movePos
+// (an unexpanded or terminal child drops the tree).
+struct ko_search { std::vector<Node> nodes; };
+ko_search* ko_search_create(void) { return new ko_search(); }
+void ko_search_destroy(ko_search* s) { delete s; }
+void ko_search_clear(ko_search* s) { s->nodes.clear(); }
+void ko_search_continue(ko_search* s, const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                        int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                        uint8_t* orderOut, uint64_t counters[3]) {
+  searchRunOnTree(s->nodes, rootGame, x_size, y_size, p, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters);
+}
+void ko_search_advance(ko_search* s, int movePos) {
+  if(s->nodes.empty() || movePos < 0) { s->nodes.clear(); return; }
+  const int c = s->nodes[0].child[movePos];
+  if(c < 0) { s->nodes.clear(); return; }
+  // breadth-first copy of the subtree (the device re-roots in the same order, although node indices carry no meaning)
+  std::vector<Node> out;
+  std::vector<int> queue{c};
+  for(size_t i = 0; i < queue.size(); i++) {
+    Node n = s->nodes[queue[i]];
+    for(size_t pos = 0; pos < n.child.size(); pos++)
+      if(n.child[pos] >= 0) { queue.push_back(n.child[pos]); n.child[pos] = (int)queue.size() - 1; }
+    out.push_back(std::move(n));
+  }
+  s->nodes.swap(out);
 }
 
 // The move played after a search: proportional to the root children's visits for ply < temperaturePlies (counter RNG),

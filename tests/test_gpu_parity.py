@@ -822,3 +822,36 @@ def test_training_rows_match_oracle(ctx, oracle, tmp_path, W, H, K):
     z = np.load(str(tmp_path / "rows.npz"))
     assert nrows == n and set(z.files) == {"binaryInputNCHWPacked", "globalInputNC", "policyTargetsNCMove", "globalTargetsNC", "valueTargetsNCHW"}
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,K", [(5, 5, 4), (6, 6, 4)])
+def test_search_tree_reuse_matches_oracle(ctx, oracle, W, H, K):
+    """Tree re-use (Search::makeMove keeps the chosen child's subtree, its visits count towards maxVisits): move
+    sequences, per-move root statistics and the visit / evaluation counters equal the oracle's persistent search."""
+    from katacoffee_b200 import backend, capi
+    G, V, seed, T = 64, 56, 21, 5
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, temperaturePlies=T, reuseTree=True)
+    s.reset(seed=seed, firstGameId=77)
+    ogames = [oracle.Game(W, H, K) for _ in range(G)]
+    osearch = [oracle.PersistentSearch() for _ in range(G)]
+    stats = capi.SearchStats()
+    ocnt = np.zeros(3, np.uint64)
+    for ply in range(W * H):
+        _, chosen, _ = s.play(1, stats)
+        for g in range(G):
+            og = ogames[g]
+            if og.finished():
+                assert chosen[g] == -1
+                continue
+            r = osearch[g].run(og, V)
+            assert r["rootVisits"] == V
+            ocnt += r["counters"]
+            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 77 + g)
+            assert chosen[g] == mv, (ply, g, chosen[g], mv)
+            og.play(mv)
+            osearch[g].advance(mv)
+    assert all(og.finished() for og in ogames)
+    assert (stats.visits, stats.netEvals, stats.terminalVisits) == tuple(int(x) for x in ocnt)
+    assert stats.visits < 0.9 * stats.movesPlayed * V          # re-use really saved visits
+    s.close()
