@@ -590,16 +590,27 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
     // (three streams, one event pair per chunk).  A chunk is a whole number of CTA work items per SM.
     const int NB = boardsPerTile(h->W, h->H);
     const int wave = 2 * NB * h->ctx->smCount;                 // rows that give every SM one work item
-    int chunk = ((n + 7) / 8 + wave - 1) / wave * wave;        // aim at 8 chunks
-    if(chunk < 2 * wave) chunk = 2 * wave;
-    const int numChunks = (n + chunk - 1) / chunk;
+    // Tapered schedule (in waves): a small first chunk so that compute starts after a short copy, a small last chunk so
+    // that little is left to copy back when the last kernel ends, at most 4 waves in between: 16 waves -> 1,2,4,4,4,1.
+    const int totalWaves = (n + wave - 1) / wave;
+    std::vector<int> sizes;
+    if(totalWaves >= 8) {
+      sizes.push_back(1); sizes.push_back(2);
+      int mid = totalWaves - 4;
+      while(mid > 0) { int s = std::min(4, mid); sizes.push_back(s); mid -= s; }
+      sizes.push_back(1);
+    } else {
+      for(int w = 0; w < totalWaves; w += 2) sizes.push_back(std::min(2, totalWaves - w));
+    }
+    const int numChunks = (int)sizes.size();
     while((int)h->chunkEvents.size() < 2 * numChunks) {
       cudaEvent_t e;
       KC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->chunkEvents.push_back(e);
     }
-    for(int c = 0; c < numChunks; c++) {
-      const int r0 = c * chunk, rows = std::min(chunk, n - r0);
+    int r0 = 0;
+    for(int c = 0; c < numChunks; r0 += sizes[c] * wave, c++) {
+      const int rows = std::min(sizes[c] * wave, n - r0);
       KC_CUDA(cudaMemcpyAsync(h->d_raw + (size_t)r0 * 15 * HW, spatial + (size_t)r0 * 15 * HW, (size_t)rows * 15 * HW * 4, cudaMemcpyHostToDevice, h->h2dStream));
       KC_CUDA(cudaMemcpyAsync(h->d_rawGlobal + r0, global + r0, (size_t)rows * 4, cudaMemcpyHostToDevice, h->h2dStream));
       if(symmetry) KC_CUDA(cudaMemcpyAsync(h->d_sym + r0, symmetry + r0, (size_t)rows, cudaMemcpyHostToDevice, h->h2dStream));
