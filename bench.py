@@ -256,9 +256,9 @@ def main():
     # rules+features alone (the HBM-bound kernel), fp32 NCHW planes + masks + hashes: secondary roofline
     games_rf = backend.Games(ctx, 65536, W, H, WINLEN)
     games_rf.reset(seed=SEED, autoRefill=True)
-    games_rf.runTimed(None, 3, L2_FLUSH_BYTES)
-    _, rf_ms = games_rf.runTimed(None, 20, L2_FLUSH_BYTES)
-    rf_steps_s = 65536 * 20 / (rf_ms * 1e-3)
+    games_rf.runTimed(None, 8, L2_FLUSH_BYTES)
+    _, rf_ms = games_rf.runTimed(None, 24, L2_FLUSH_BYTES)
+    rf_steps_s = 65536 * 24 / (rf_ms * 1e-3)
     games_rf.close()
 
     # ---------------- host-buffer arm (`e2e`) ----------------
@@ -331,7 +331,8 @@ def main():
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                          "traffic": load_traffic("prof_trunk"), "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
-            "roofline_rules_features": {"kernel": "games_kernel<step, fp32 NCHW planes> at 65536 games", "bound": "hbm",
+            "roofline_rules_features": {"kernel": "games_multi_kernel (rules step + fp32 NCHW planes, 8 plies per launch, 4-slot plane ring) at 65536 games",
+                                        "bound": "hbm", "plies_per_launch": 8,
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
                                         "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games")},

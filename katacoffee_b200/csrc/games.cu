@@ -271,6 +271,126 @@ __global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Several plies in one launch (rules + fp32 NCHW planes, random-legal moves, no symmetry): the state of a game stays
+// in registers between plies, and because every warp is autonomous the bitboard arithmetic of one warp's next ply
+// overlaps the plane stores of the others -- the single-ply kernel pays a store-free rules phase on every launch.
+// Ply p writes its planes to ring slot (firstSlot + p) % 4; masks, status words, hashes and moves are overwritten per
+// ply.  Semantically identical to `plies` launches of games_kernel<true, 1>.
+// ---------------------------------------------------------------------------------------------
+struct PlaneRing { float* slot[4]; };
+
+template <class D>
+__global__ void __launch_bounds__(TB_PLAIN) games_multi_kernel(const Geom g, State st, const uint64_t* __restrict__ zob, StepOut so,
+                                                               PlaneRing ring, float* __restrict__ global, int plies, int firstSlot) {
+  constexpr int GPB = TB_PLAIN;
+  __shared__ uint64_t sPlanes[15][GPB + 1];
+  __shared__ uint32_t sBits[GPB * 15 * 49 / 32 + 4];
+  const D dm(g);
+  using BB = typename D::BB;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int gBase = blockIdx.x * GPB;
+  const int gi = gBase + t;
+  const bool active = gi < g.numGames;
+  const int E = 15 * dm.HW();
+  const int ngw = min(32, g.numGames - gBase - w * 32);
+  if(ngw <= 0) return;
+  GameRegs<BB> s;
+  s.black = 0; s.white = 0; s.h0 = s.h1 = s.id = s.misc = 0;
+  if(active) {
+    s.black = (BB)st.black[gi]; s.white = (BB)st.white[gi]; s.h0 = st.hash0[gi]; s.h1 = st.hash1[gi];
+    s.id = st.gameId[gi]; s.misc = st.misc[gi];
+  }
+  unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
+  uint32_t* bits = sBits + w * E;
+  for(int p = 0; p < plies; p++) {
+    for(int i = lane; i < E; i += 32) bits[i] = 0;
+    __syncwarp();
+    if(active) {
+      BB L[4];
+      bool illegal = false;
+      const int played = stepGame(dm, g, s, -1, false, zob, L, illegal);
+      const int fl = flagsOf(s.misc);
+      const int nextPla = (fl >> 3) & 3;
+      const uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
+      if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
+      if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
+      if(so.played) so.played[gi] = (int16_t)played;
+      if(so.legal) {
+        uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for(int d = 0; d < 4; d++) {
+          uint64_t dense = toDense(dm, L[d]);
+          int off = d * dm.HW(), wq = off >> 6, sh = off & 63;
+#pragma unroll
+          for(int q = 0; q < 4; q++) {
+            if(q == wq) acc[q] |= dense << sh;
+            if(q == wq + 1 && sh) acc[q] |= dense >> (64 - sh);
+          }
+        }
+        for(int wd = 0; wd < g.LW; wd++) so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
+      }
+      if(played >= 0) {
+        cSteps += 1;
+        cXor ^= sh0;
+        if(fl & 1) { cFin += 1; int wn = (fl >> 1) & 3; cB += wn == 1; cW += wn == 2; cD += wn == 0; }
+      }
+      v1Planes(dm, g, s, L, &sPlanes[0][t], GPB + 1);
+      uint32_t bitPos = (uint32_t)t * E, wi = bitPos >> 5;
+      int fill = bitPos & 31;
+      uint64_t acc = 0;
+      auto append = [&](uint64_t b, int n) {
+        acc |= b << fill;
+        fill += n;
+        if(fill >= 32) { atomicOr(&sBits[wi++], (uint32_t)acc); acc >>= 32; fill -= 32; }
+      };
+#pragma unroll 1
+      for(int c = 0; c < 15; c++) {
+        uint64_t Dn = toDense(dm, (BB)sPlanes[c][t]);
+        if(dm.HW() <= 25) append(Dn, dm.HW());
+        else { append(Dn & 0x1FFFFFFULL, 25); append(Dn >> 25, dm.HW() - 25); }
+      }
+      if(fill) atomicOr(&sBits[wi], (uint32_t)acc);
+    }
+    __syncwarp();
+    const int total = ngw * E;
+    float* out = ring.slot[(firstSlot + p) & 3] + ((size_t)gBase + w * 32) * E;
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const int nvec = total >> 2;
+#pragma unroll 4
+    for(int j = lane; j < nvec; j += 32) {
+      uint32_t b = bits[j >> 3] >> ((j & 7) * 4);
+      float4 v = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+      __stcs(&out4[j], v);
+    }
+    for(int e = (nvec << 2) + lane; e < total; e += 32) out[e] = (float)((bits[e >> 5] >> (e & 31)) & 1u);
+    __syncwarp();
+  }
+  if(global && lane < ngw) global[gBase + w * 32 + lane] = (float)dm.K();
+  if(active) {
+    st.black[gi] = (uint64_t)s.black; st.white[gi] = (uint64_t)s.white; st.hash0[gi] = s.h0; st.hash1[gi] = s.h1;
+    st.gameId[gi] = s.id; st.misc[gi] = s.misc;
+  }
+  if(so.stats) {
+    for(int o = 16; o > 0; o >>= 1) {
+      cSteps += __shfl_xor_sync(0xffffffffu, cSteps, o);
+      cFin += __shfl_xor_sync(0xffffffffu, cFin, o);
+      cB += __shfl_xor_sync(0xffffffffu, cB, o);
+      cW += __shfl_xor_sync(0xffffffffu, cW, o);
+      cD += __shfl_xor_sync(0xffffffffu, cD, o);
+      cXor ^= __shfl_xor_sync(0xffffffffu, cXor, o);
+    }
+    if(lane == 0) {
+      if(cSteps) atomicAdd(&so.stats[0], cSteps);
+      if(cFin) atomicAdd(&so.stats[2], cFin);
+      if(cB) atomicAdd(&so.stats[3], cB);
+      if(cW) atomicAdd(&so.stats[4], cW);
+      if(cD) atomicAdd(&so.stats[5], cD);
+      if(cXor) atomicXor(&so.stats[6], cXor);
+    }
+  }
+}
+
 }  // namespace kc
 
 // =============================================================================================
@@ -559,7 +679,27 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     for(int i = 0; i < RING - 1; i++)
       if(!G->d_planesRing[i]) KC_CUDA(cudaMalloc(&G->d_planesRing[i], (size_t)g.numGames * 15 * g.HW * 4));
   int nGroups = 0;
-  for(int p = 0; p < plies; p++) {
+  if(!h) {
+    // rules + features only: one multi-ply launch per group of RING plies, one event pair per launch
+    PlaneRing ring;
+    for(int i = 0; i < RING; i++) ring.slot[i] = (flushL2Bytes && i > 0) ? G->d_planesRing[i - 1] : G->d_planes;
+    const int blocks = (g.numGames + TB_PLAIN - 1) / TB_PLAIN;
+    constexpr int PLIES_PER_LAUNCH = 8;   // two turns of the 4-slot ring (412 MB > L2 between two writes of a slot)
+    for(int p = 0; p < plies; p += PLIES_PER_LAUNCH) {
+      const int np = std::min(PLIES_PER_LAUNCH, plies - p);
+      if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
+      KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups], G->stream));
+      StepOut so = stepOutOf(G, true);
+      if(g.W == 5 && g.H == 5 && g.K == 4)
+        games_multi_kernel<StaticDims<5, 5, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+      else
+        games_multi_kernel<DynDims><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+      G->launches++;
+      KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups + 1], G->stream));
+      nGroups++;
+    }
+  }
+  for(int p = 0; h && p < plies; p++) {
     // optional L2 flush between timed windows, outside them
     if(p % grp == 0) {
       if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
