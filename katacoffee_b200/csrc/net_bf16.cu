@@ -98,6 +98,8 @@ struct LayerDesc {
   int epi;         // epilogue kind
   int epiC;        // channels published to the activation tile (multiple of 16)
   int gpoolC;      // EPI_GPOOL: gpool channels (columns epiC .. epiC+gpoolC)
+  int act;         // activation after the folded BN this layer's epilogue applies (0 identity, 1 ReLU, 2 Mish)
+  int gpoolAct;    // EPI_GPOOL: activation of the gpool branch
   unsigned wOffset; // byte offset of this layer's first stage in the weight stream
   int pOff;        // float offset of this layer's parameters
 };
@@ -125,6 +127,7 @@ struct TrunkParams {
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
   int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
+  int g1Act, p1Act, v1Act, v2Act;   // head activations
   int* abortFlag;
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
   float poolScale1, poolScale2, invHW;
@@ -134,6 +137,18 @@ struct TrunkParams {
 // ------------------------------------------------------------------------------------------------
 // device code
 // ------------------------------------------------------------------------------------------------
+// Activations (cpp/neuralnet/activations.h:4-6): 0 identity, 1 ReLU, 2 Mish = x*tanh(softplus(x)) (eigenbackend.cpp:729, linear
+// above 20).  With n = e^x, tanh(log(1+n)) = n(n+2) / (n(n+2) + 2): one exponential and one division.  `act` is warp-uniform.
+__device__ __forceinline__ float actf(float x, int act) {
+  if(act == 1) return fmaxf(x, 0.f);
+  if(act == 2) {
+    const float n = __expf(fminf(x, 20.f));
+    const float t = n * (n + 2.f);
+    return x > 20.f ? x : x * __fdividef(t, t + 2.f);
+  }
+  return x;
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -155,7 +170,8 @@ struct EpiCtx {
 };
 
 // folded BN + ReLU + mask for 16 columns -> two 16-byte chunks of the activation tile
-__device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v[16], const float* scale, const float* bias, const float* add) {
+template <bool RELU>
+__device__ __forceinline__ void publish16T(const EpiCtx& c, int cc, const float v[16], const float* scale, const float* bias, const float* add, int act) {
   uint32_t pk[8];
 #pragma unroll
   for(int q = 0; q < 4; q++) {
@@ -163,8 +179,14 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
     float4 bb = *(reinterpret_cast<const float4*>(bias + cc * 16) + q);
     float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
     if(add) { x0 += add[cc * 16 + 4 * q]; x1 += add[cc * 16 + 4 * q + 1]; x2 += add[cc * 16 + 4 * q + 2]; x3 += add[cc * 16 + 4 * q + 3]; }
-    float a0 = fmaxf(fmaf(x0, s.x, bb.x), 0.f), a1 = fmaxf(fmaf(x1, s.y, bb.y), 0.f);
-    float a2 = fmaxf(fmaf(x2, s.z, bb.z), 0.f), a3 = fmaxf(fmaf(x3, s.w, bb.w), 0.f);
+    float a0, a1, a2, a3;
+    if(RELU) {
+      a0 = fmaxf(fmaf(x0, s.x, bb.x), 0.f); a1 = fmaxf(fmaf(x1, s.y, bb.y), 0.f);
+      a2 = fmaxf(fmaf(x2, s.z, bb.z), 0.f); a3 = fmaxf(fmaf(x3, s.w, bb.w), 0.f);
+    } else {
+      a0 = actf(fmaf(x0, s.x, bb.x), act); a1 = actf(fmaf(x1, s.y, bb.y), act);
+      a2 = actf(fmaf(x2, s.z, bb.z), act); a3 = actf(fmaf(x3, s.w, bb.w), act);
+    }
     if(!c.valid) { a0 = a1 = a2 = a3 = 0.f; }
     pk[2 * q] = pack2(a0, a1);
     pk[2 * q + 1] = pack2(a2, a3);
@@ -179,6 +201,12 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
 
 // per-board pooling of 16 channels held one row per thread: writes sum and max per (board, channel)
 // into outSum/outMax[b*16 + j] (shared), using the tile's scratch.  All 128 threads of the tile call it.
+// the ReLU instantiation is the hot one: keeping the other activations out of it keeps its code as it was
+__device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v[16], const float* scale, const float* bias, const float* add, int act) {
+  if(act == 1) publish16T<true>(c, cc, v, scale, bias, add, act);
+  else publish16T<false>(c, cc, v, scale, bias, add, act);
+}
+
 // Two threads per (board, channel): even lane = upper rows, odd lane = lower rows, combined by one shuffle; the even lane
 // (c.e even, c.e >> 1 = board*16 + channel < NB*16) returns the board's sum and max.
 __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float& sum, float& mx) {
@@ -251,14 +279,14 @@ __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCt
     if(cc + 1 < nch) tmem_ld16_issue(src + (cc + 1) * 16, rb);
 #pragma unroll
     for(int i = 0; i < 16; i++) v[i] = __uint_as_float(ra[i]);
-    publish16(c, cc, v, scale, bias, nullptr);
+    publish16(c, cc, v, scale, bias, nullptr, L.act);
     if(c.dbg && cc == 0) c.dbg[3] = clock64();
     if(cc + 1 >= nch) break;
     tmem_ld16_wait(rb);
     if(cc + 2 < nch) tmem_ld16_issue(src + (cc + 2) * 16, ra);
 #pragma unroll
     for(int i = 0; i < 16; i++) v[i] = __uint_as_float(rb[i]);
-    publish16(c, cc + 1, v, scale, bias, nullptr);
+    publish16(c, cc + 1, v, scale, bias, nullptr, L.act);
     if(cc + 2 < nch) tmem_ld16_wait(ra);
   }
   if(c.dbg) c.dbg[7] = clock64();
@@ -280,7 +308,7 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
     tmem_ld16(src + R + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], gs[half * 16 + j], gb[half * 16 + j]), 0.f);
+      float a = actf(fmaf(v[j], gs[half * 16 + j], gb[half * 16 + j]), L.gpoolAct);
       g[j] = c.valid ? a : 0.f;
     }
     float sum, mx;
@@ -305,7 +333,7 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
   for(int cc = 0; cc < R / 16; cc++) {
     float v[16];
     tmem_ld16(src + cc * 16, v);
-    publish16(c, cc, v, ms, mb, add);
+    publish16(c, cc, v, ms, mb, add, L.act);
   }
 }
 
@@ -368,7 +396,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     tmem_ld16(src + HEADC + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), 0.f);
+      float a = actf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), P.g1Act);
       g[j] = c.valid ? a : 0.f;
     }
     poolBoards16(P, c, g, sum, mx);
@@ -381,7 +409,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     tmem_ld16(src + 2 * HEADC + half * 16, v);
 #pragma unroll
     for(int j = 0; j < 16; j++) {
-      float a = fmaxf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), 0.f);
+      float a = actf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), P.v1Act);
       g[j] = c.valid ? a : 0.f;
       v1a[half * 16 + j] = g[j];
     }
@@ -424,7 +452,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       pooledMatmul(pooledV, 96, Wv2, 96, V2, oc, P.NB, acc);
       const float bias2 = b2[oc];
 #pragma unroll
-      for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = fmaxf(acc[b] + bias2, 0.f);
+      for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = actf(acc[b] + bias2, P.v2Act);
     }
   }
   if(hp) P.dbg[27] = clock64();
@@ -456,7 +484,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, own = 0.f;
 #pragma unroll
     for(int k = 0; k < HEADC; k++) {
-      float a = fmaxf(fmaf(p1[k] + add[k], p1s[k], p1b[k]), 0.f);
+      float a = actf(fmaf(p1[k] + add[k], p1s[k], p1b[k]), P.p1Act);
       float4 w = *(reinterpret_cast<const float4*>(W2) + k);
       o0 = fmaf(a, w.x, o0); o1 = fmaf(a, w.y, o1); o2 = fmaf(a, w.z, o2); o3 = fmaf(a, w.w, o3);
       own = fmaf(v1a[k], Wown[k], own);
@@ -935,10 +963,7 @@ int buildTrunkProgram(kc_model* m) {
   if(m->p1Conv.ky != 1 || m->g1Conv.ky != 1 || m->v1Conv.ky != 1 || m->p2Conv.ky != 1 || m->vOwnershipConv.ky != 1)
     return unsupported("head convs must be 1x1");
   if(m->v2Mul.oc > MAX_V2 || m->v2Mul.oc % 16 != 0) return unsupported("v2 size must be a multiple of 16, <= 128");
-  if(m->trunkTipBN.act != 1 || m->g1BN.act != 1 || m->p1BN.act != 1 || m->v1BN.act != 1 || m->v2Act != 1)
-    return unsupported("only ReLU activations are implemented in the tcgen05 kernel");
   for(const BlockW& b : m->blocks) {
-    if(b.preBN.act != 1 || b.midBN.act != 1 || (b.kind == 2 && b.gpoolBN.act != 1)) return unsupported("only ReLU activations are implemented in the tcgen05 kernel");
     if(b.regularConv.ky != 3 || b.regularConv.kx != 3 || b.finalConv.ky != 3 || b.finalConv.kx != 3) return unsupported("block convs must be 3x3");
     if(b.kind == 0 && (b.regularConv.oc % 16 != 0 || b.regularConv.oc > maxC)) return unsupported("mid channels must be a multiple of 16 and within the trunk width class");
     if(b.kind == 2) {
@@ -962,6 +987,7 @@ int buildTrunkProgram(kc_model* m) {
       return tap == 4 ? m->initialMatMul.h[n] : 0.f;
     });
     const BNW& bn = bnOf(0);
+    L.act = bn.act;
     L.pOff = pk.addParams(cat({&bn.scale, &bn.bias}));
     T->layers.push_back(L);
     macs += 9.0 * 15 * C + C;
@@ -975,6 +1001,7 @@ int buildTrunkProgram(kc_model* m) {
     L1.wOffset = pk.addConv(R + G, C, 9, [&](int n, int ic, int tap) {
       return n < R ? convW(b.regularConv, n, ic, tap) : convW(b.gpoolConv, n - R, ic, tap);
     });
+    L1.act = b.midBN.act; L1.gpoolAct = b.kind == 2 ? b.gpoolBN.act : 0;
     if(b.kind == 2) L1.pOff = pk.addParams(cat({&b.gpoolBN.scale, &b.gpoolBN.bias, &b.gpoolToBias.h, &b.midBN.scale, &b.midBN.bias}));
     else L1.pOff = pk.addParams(cat({&b.midBN.scale, &b.midBN.bias}));
     T->layers.push_back(L1);
@@ -982,6 +1009,7 @@ int buildTrunkProgram(kc_model* m) {
     L2.nk = 9 * (R / 16); L2.ntaps = 9; L2.N = C; L2.outSel = 0; L2.accumulate = 1; L2.epi = EPI_BN; L2.epiC = C;
     L2.wOffset = pk.addConv(C, R, 9, [&](int n, int ic, int tap) { return convW(b.finalConv, n, ic, tap); });
     const BNW& bn = bnOf(bi + 1);
+    L2.act = bn.act;
     L2.pOff = pk.addParams(cat({&bn.scale, &bn.bias}));
     T->layers.push_back(L2);
     macs += 9.0 * C * (R + G) + 9.0 * R * C + 3.0 * G * R;
@@ -1112,6 +1140,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;
   P.permuteDirs = (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0;
+  P.g1Act = m->g1BN.act; P.p1Act = m->p1BN.act; P.v1Act = m->v1BN.act; P.v2Act = m->v2Act;
   P.dbg = h->d_dbg;
   float sq = sqrtf((float)P.HW);
   P.poolScale1 = (sq - 14.0f) * 0.1f;

@@ -35,10 +35,13 @@ HEAD_C = 32
 class Model:
     """Owns the numpy weight arrays and the ctypes description pointing into them."""
 
-    def __init__(self, name, seed=0, calibrate="rms"):
+    def __init__(self, name, seed=0, calibrate="rms", activation="relu"):
         if name not in CONFIGS:
             raise ValueError(f"unknown net {name}")
+        if activation not in ("relu", "mish"):
+            raise ValueError("activation must be 'relu' or 'mish' (cpp/neuralnet/activations.h:4-6)")
         self.name = name
+        self.act = act = 1 if activation == "relu" else 2
         C_, mid, reg, gp, nb, gpool_blocks, v2 = CONFIGS[name]
         self.trunk, self.num_blocks, self.v2 = C_, nb, v2
         rng = np.random.default_rng(seed)
@@ -48,14 +51,14 @@ class Model:
         d.version = 1
         d.numInputChannels, d.numInputGlobalChannels, d.numBlocks = 15, 1, nb
         d.trunkNumChannels, d.midNumChannels, d.regularNumChannels, d.gpoolNumChannels = C_, mid, reg, gp
-        d.trunkTipActivation = d.g1Activation = d.p1Activation = d.v1Activation = d.v2Activation = 1
+        d.trunkTipActivation = d.g1Activation = d.p1Activation = d.v1Activation = d.v2Activation = act
         d.initialConv = self._conv(rng, 3, 15, C_, relu=True)
         d.initialMatMul = self._matmul(rng, 1, C_, scale=0.3)
         blocks = (capi.BlockDesc * nb)()
         self.flops_per_eval_cell = 2.0 * (9 * 15 * C_ + C_)
         for i in range(nb):
             b = blocks[i]
-            b.preActivation = b.gpoolActivation = b.midActivation = 1
+            b.preActivation = b.gpoolActivation = b.midActivation = act
             b.preBN = self._bn(rng, C_)
             resid = 1.0 / np.sqrt(max(nb, 1))
             if i in gpool_blocks:
@@ -162,7 +165,8 @@ class Model:
             s = torch.from_numpy(scale / np.sqrt(var + d.epsilon))
             b = torch.from_numpy(bias) - torch.from_numpy(mean) * s
             shape = (1, -1, 1, 1) if t.dim() == 4 else (1, -1)
-            return torch.relu(t * s.view(shape) + b.view(shape))
+            y = t * s.view(shape) + b.view(shape)
+            return torch.relu(y) if self.act == 1 else F.mish(y)
 
         def gpool(t):
             mean = t.mean((2, 3))

@@ -855,3 +855,32 @@ def test_search_tree_reuse_matches_oracle(ctx, oracle, W, H, K):
     assert (stats.visits, stats.netEvals, stats.terminalVisits) == tuple(int(x) for x in ocnt)
     assert stats.visits < 0.9 * stats.movesPlayed * V          # re-use really saved visits
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("net,W,H,n", [("b1c32g", 5, 5, 120), ("b6c96", 5, 5, 150), ("b2c32", 6, 6, 60)])
+def test_mish_activation_both_paths(ctx, oracle, net, W, H, n):
+    """Mish nets (activations.h:4-6, eigenbackend.cpp:729): fp32 check path within 1e-4 of the oracle, tensor-core path
+    within the reduced-precision bars (its Mish is n(n+2)/(n(n+2)+2) with n = e^x, exact up to fp32 rounding)."""
+    from katacoffee_b200 import backend, modeldesc
+    model = modeldesc.Model(net, seed=8, activation="mish")
+    om = oracle.Model(model)
+    planes, glob, rsel = position_batch_full(oracle, W, H, 4, 11, n)
+    sym = (np.arange(n) % 8).astype(np.int8)
+    ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
+    lm = backend.LoadedModel(ctx, model)
+    hf = backend.createComputeHandle(ctx, lm, n, W, H, useFP32Check=True)
+    got = backend.getOutput(hf, planes, glob, sym)
+    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_FP32
+    hb = backend.createComputeHandle(ctx, lm, n, W, H)
+    assert hb.isUsingBF16()
+    gb = backend.getOutput(hb, planes, glob, sym)
+    for a, b in zip(gb, ref):
+        assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), np.abs(a - b).max()
+    if net == "b1c32g":      # shallow: pointwise against the bf16-emulating oracle
+        emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
+        assert max(np.abs(a - b).max() for a, b in zip(gb, emu)) < 1e-2
+    relu = backend.getOutput(backend.createComputeHandle(ctx, backend.LoadedModel(ctx, modeldesc.Model(net, seed=8)), n, W, H), planes, glob, sym)
+    assert np.abs(relu[0] - gb[0]).max() > 1e-2        # the activation really differs from the ReLU net's
+    for x in (hf, hb, lm):
+        x.close()
