@@ -335,7 +335,7 @@ def main():
                                         "bound": "hbm", "plies_per_launch": 8,
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
-                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games")},
+                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games_multi") or load_traffic("prof_games")},
             "selfplay": selfplay,
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
                       "black_wins": int(counters[3]), "white_wins": int(counters[4]), "draws": int(counters[5])},

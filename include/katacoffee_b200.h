@@ -239,14 +239,19 @@ typedef struct {
                                    visits take no row); 1: one row per game, idle rows evaluated and ignored */
   int32_t reuseTree;            /* keep the subtree of the move played for the next search (Search::makeMove); its visits count
                                    towards maxVisits, so later searches need fewer evaluations */
-  int32_t pad_;
+  int32_t useGraphSearch;       /* SearchParams::useGraphSearch: positions with equal stones, player to move and last move share one
+                                   node (cpp/search/search.cpp:704-757); not together with reuseTree */
   double cpuctExploration;      /* SearchParams::cpuctExploration (1.0) */
   double fpuReductionMax;       /* SearchParams::fpuReductionMax (0.2) */
   double rootFpuReductionMax;   /* SearchParams::rootFpuReductionMax (0.2) */
+  double subtreeValueBiasFactor;          /* SearchParams::subtreeValueBiasFactor (0 = off; selfplay1.cfg:180 uses 0.30) */
+  double subtreeValueBiasWeightExponent;  /* SearchParams::subtreeValueBiasWeightExponent (0.5 default, selfplay1.cfg:181 0.8) */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;
   uint64_t batchRows;           /* rows sent through the evaluator */
+  uint64_t transpositionHits;   /* graph search: new edges that found their position already in the graph (no evaluation) */
+  uint64_t catchUpVisits;       /* graph search: visits absorbed by an edge lagging behind its node (maybeCatchUpEdgeVisits) */
 } kc_search_stats;
 /* handle == NULL selects the deterministic integer-hash evaluator (exact fp32 policy/value derived from the sit-hash),
  * which exists so that the search logic can be compared bit for bit with the CPU oracle; with a handle the leaves go
@@ -284,6 +289,10 @@ int kc_search_play(kc_search* s, int moves, int16_t* chosenLast, kc_search_stats
 int kc_search_enable_training_rows(kc_search* s, int maxRows);
 int kc_search_read_training_rows(kc_search* s, int* numRows, int* numDropped, uint8_t* binaryInputNCHWPacked, float* globalInputNC,
                                  int16_t* policyTargetsNCMove, float* globalTargetsNC, int8_t* valueTargetsNCHW, int clear);
+/* Graph-mode searches (useGraphSearch or subtreeValueBiasFactor != 0): digest [G] = order-independent hash over every node of
+ * each game's graph (visits, weightSum and utilityAvg bit patterns, edges with their visit counts and creation order), the
+ * quantity the oracle's ko_search_run_graph reports, for whole-graph comparisons. */
+int kc_search_tree_digest(kc_search* s, uint64_t* digest);
 int64_t kc_search_launch_count(const kc_search* s);
 
 #ifdef __cplusplus

@@ -239,10 +239,12 @@ class Search:
     handle=None selects the integer-hash evaluator used to test the search logic exactly against the oracle."""
 
     def __init__(self, ctx, handle, numGames, xSize=5, ySize=5, winLen=4, maxVisits=800, temperaturePlies=0, autoRefill=False,
-                 cpuctExploration=1.0, fpuReductionMax=0.2, rootFpuReductionMax=0.2, noCompaction=False, reuseTree=False):
+                 cpuctExploration=1.0, fpuReductionMax=0.2, rootFpuReductionMax=0.2, noCompaction=False, reuseTree=False,
+                 useGraphSearch=False, subtreeValueBiasFactor=0.0, subtreeValueBiasWeightExponent=0.5):
         self.ctx, self.G, self.W, self.H = ctx, numGames, xSize, ySize
         self.P = 4 * xSize * ySize
-        self.params = capi.SearchParams(maxVisits, temperaturePlies, int(autoRefill), int(noCompaction), int(reuseTree), 0, cpuctExploration, fpuReductionMax, rootFpuReductionMax)
+        self.params = capi.SearchParams(maxVisits, temperaturePlies, int(autoRefill), int(noCompaction), int(reuseTree), int(useGraphSearch), cpuctExploration, fpuReductionMax, rootFpuReductionMax,
+                                        subtreeValueBiasFactor, subtreeValueBiasWeightExponent)
         self._p = C.c_void_p()
         check(lib().kc_search_create(ctx._p, handle._p if handle is not None else None, numGames, xSize, ySize, winLen,
                                      C.byref(self.params), C.byref(self._p)))
@@ -266,6 +268,12 @@ class Search:
                    edgeUtilitySum=np.zeros((G, P), np.float64), policy=np.zeros((G, P), np.float32), order=np.zeros((G, P), np.uint8))
         check(lib().kc_search_read_root(self._p, ptr(out["rootVisits"]), ptr(out["rootUtilitySum"]), ptr(out["edgeVisits"]),
                                         ptr(out["edgeUtilitySum"]), ptr(out["policy"]), ptr(out["order"])))
+        return out
+
+    def treeDigest(self):
+        """Graph-mode searches: hash over every node of each game's graph (see kc_search_tree_digest)."""
+        out = np.zeros(self.G, np.uint64)
+        check(lib().kc_search_tree_digest(self._p, ptr(out)))
         return out
 
     def play(self, moves=1, stats=None):

@@ -58,13 +58,14 @@ class Stats(C.Structure):
 
 
 class SearchParams(C.Structure):
-    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("pad_", C.c_int32),
-                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("useGraphSearch", C.c_int32),
+                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double),
+                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double)]
 
 
 class SearchStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("visits", "netEvals", "terminalVisits", "movesPlayed", "gamesFinished", "blackWins",
-                                          "whiteWins", "draws", "batchRows")]
+                                          "whiteWins", "draws", "batchRows", "transpositionHits", "catchUpVisits")]
 
 
 FLAG_FP32_CHECK = 1
@@ -115,6 +116,7 @@ PROTOTYPES = {
     "kc_search_play": (C.c_int, [vp, C.c_int, vp, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
     "kc_search_enable_training_rows": (C.c_int, [vp, C.c_int]),
     "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
+    "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
 }
 

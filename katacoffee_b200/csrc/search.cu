@@ -49,7 +49,12 @@ struct SearchCfg {
   int autoRefill;
   int compact;       // leaves that need the net are packed into a dense batch (slot = arrival order); 0: slot = game
   int reuseTree;     // keep the chosen child's subtree for the next search (Search::makeMove)
+  int graph;         // node-centric statistics (graph search and / or subtree value bias), see "graph mode" below
+  int useTable;      // graph mode: look new positions up in the transposition table (SearchParams::useGraphSearch)
+  int polOff;        // byte offset of the per-move arrays inside a node
+  int tableCap;      // graph mode: slots of the per-game transposition and bias tables (power of two, >= 2 * maxNodes)
   double cpuct, fpuRed, rootFpuRed;
+  double biasFactor, biasExp;   // SearchParams::subtreeValueBiasFactor / subtreeValueBiasWeightExponent
   uint64_t seed;
 };
 
@@ -67,8 +72,18 @@ struct TreeMem {
   uint8_t* nodesAlt;      // second tree buffer: re-rooting copies the kept subtree there, then the two swap
   int* rerootQueue;       // [G][maxNodes] breadth-first order of the kept subtree (old node indices)
   int* active;            // [1] set by k_select when any game still had a visit to make
-  unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws
+  unsigned long long* stats;  // 0 visits, 1 net evaluations, 2 terminal visits, 3 moves played, 4 games finished, 5 black, 6 white, 7 draws,
+                              // 8 transposition hits, 9 catch-up visits (graph mode)
+  // graph mode
+  uint64_t* tblKeys;      // [G][tableCap][2] transposition keys
+  int* tblVals;           // [G][tableCap] node index + 1 (0 = empty slot)
+  uint64_t* biasKeys;     // [G][tableCap][2] subtree-value-bias keys (key0 == 0: empty slot)
+  double* biasVals;       // [G][tableCap][2] deltaUtilitySum, weightSum
+  uint64_t* leafKey;      // [G][2] transposition key of a new node
+  uint64_t* leafBiasKey;  // [G][2] bias key of a new node (key0 == 0: none)
+  int* leafTarget;        // [G] existing node a new edge transposes to
 };
+constexpr int NUM_STATS = 16;
 
 // Training-row capture (reference cpp/dataio/trainingwrite.cpp:316-566 TrainingWriteBuffers::addRow,
 // cpp/program/play.cpp:1428-1460).  Every move played by kc_search_play is recorded per game (position before the move,
@@ -87,19 +102,28 @@ struct TrainMem {
   double nowFactor[5];                                         // fillValueTDTargets factors (trainingwrite.cpp:403-414)
 };
 
-// node layout: header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 | policy[P] f32 |
-//              child[P] i32 | edgeN[P] i32 | order[P] u8
+// node layout, tree mode:  header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 |
+//                           policy[P] f32 | child[P] i32 | edgeN[P] i32 | order[P] u8            (polOff = 32 + 8 P)
+//              graph mode: header { int visits; int numChildren; int nextPla; int biasEntry; double weightSum, utilityAvg,
+//                           nnUtility, lastBiasDeltaSum, lastBiasWeight, pad } | policy | child | edgeN | order   (polOff = 64)
 struct NodeRef {
-  uint8_t* base; int P;
+  uint8_t* base; int P; int polOff;
   __device__ __forceinline__ int& N() const { return *reinterpret_cast<int*>(base); }
   __device__ __forceinline__ int& numChildren() const { return *reinterpret_cast<int*>(base + 4); }
   __device__ __forceinline__ int& nextPla() const { return *reinterpret_cast<int*>(base + 8); }
   __device__ __forceinline__ double& W() const { return *reinterpret_cast<double*>(base + 16); }
   __device__ __forceinline__ double* edgeW() const { return reinterpret_cast<double*>(base + 32); }
-  __device__ __forceinline__ float* policy() const { return reinterpret_cast<float*>(base + 32 + 8 * P); }
-  __device__ __forceinline__ int* child() const { return reinterpret_cast<int*>(base + 32 + 12 * P); }
-  __device__ __forceinline__ int* edgeN() const { return reinterpret_cast<int*>(base + 32 + 16 * P); }
-  __device__ __forceinline__ uint8_t* order() const { return base + 32 + 20 * P; }
+  __device__ __forceinline__ float* policy() const { return reinterpret_cast<float*>(base + polOff); }
+  __device__ __forceinline__ int* child() const { return reinterpret_cast<int*>(base + polOff + 4 * P); }
+  __device__ __forceinline__ int* edgeN() const { return reinterpret_cast<int*>(base + polOff + 8 * P); }
+  __device__ __forceinline__ uint8_t* order() const { return base + polOff + 12 * P; }
+  // graph mode header
+  __device__ __forceinline__ int& biasEntry() const { return *reinterpret_cast<int*>(base + 12); }
+  __device__ __forceinline__ double& weightSum() const { return *reinterpret_cast<double*>(base + 16); }
+  __device__ __forceinline__ double& utilityAvg() const { return *reinterpret_cast<double*>(base + 24); }
+  __device__ __forceinline__ double& nnUtility() const { return *reinterpret_cast<double*>(base + 32); }
+  __device__ __forceinline__ double& lastDelta() const { return *reinterpret_cast<double*>(base + 40); }
+  __device__ __forceinline__ double& lastWeight() const { return *reinterpret_cast<double*>(base + 48); }
 };
 // child codes: -1 none, >= 0 node index, -2 terminal draw, -3 terminal black win, -4 terminal white win
 __device__ __forceinline__ double terminalValue(int winner) { return winner == 2 ? 1.0 : winner == 1 ? -1.0 : 0.0; }
@@ -144,12 +168,12 @@ __global__ void __launch_bounds__(128) k_select(const Geom g, const SearchCfg c,
     kind = 0;
   } else if(count == 0) {
     kind = 4;
-  } else if(NodeRef{treeBase, c.P}.N() >= c.maxVisits) {
+  } else if(NodeRef{treeBase, c.P, c.polOff}.N() >= c.maxVisits) {
     kind = 0;
   } else {
     int node = 0;
     while(true) {
-      NodeRef nd{treeBase + (size_t)node * c.nodeStride, c.P};
+      NodeRef nd{treeBase + (size_t)node * c.nodeStride, c.P, c.polOff};
       const int pla = nd.nextPla();
       const double parentUtility = __ddiv_rn(nd.W(), (double)nd.N());
       const double* eW = nd.edgeW(); const float* pol = nd.policy(); const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
     v = __dsub_rn((double)winLoss[2 * row], (double)winLoss[2 * row + 1]);   // white-positive utility of the evaluation
     newIdx = t.nodeCount[gi];
     if(newIdx >= c.maxNodes) return;   // cannot happen: one new node per visit, maxNodes == maxVisits
-    NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P};
+    NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P, c.polOff};
     for(int pos = lane; pos < c.P; pos += 32) {
       nd.edgeW()[pos] = 0.0; nd.policy()[pos] = policy[row * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
     }
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
   }
   if(lane != 0) return;
   for(int d = 0; d < depth; d++) {
-    NodeRef nd{treeBase + (size_t)t.pathNode[(size_t)gi * MAX_PATH + d] * c.nodeStride, c.P};
+    NodeRef nd{treeBase + (size_t)t.pathNode[(size_t)gi * MAX_PATH + d] * c.nodeStride, c.P, c.polOff};
     const int pos = t.pathPos[(size_t)gi * MAX_PATH + d];
     if(d == depth - 1 && (kind == 1 || kind == 2)) {
       nd.child()[pos] = kind == 1 ? newIdx : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
@@ -290,6 +314,344 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
   }
   atomicAdd(&t.stats[0], 1ULL);
   if(kind == 1 || kind == 4) atomicAdd(&t.stats[1], 1ULL); else atomicAdd(&t.stats[2], 1ULL);
+}
+
+// =============================================================================================
+// graph mode: graph search (transpositions) and subtree value bias -- BASELINE config 4
+// =============================================================================================
+// Reference: Search::allocateOrFindNode (cpp/search/search.cpp:704-757), playoutDescend / maybeCatchUpEdgeVisits (:935-1207),
+// selection on the children's NODE statistics with getChildWeight (cpp/search/searchexplorehelpers.cpp:92-127, 323-451,
+// cpp/search/searchnode.h:59-65), addLeafValue / recomputeNodeStats with the bias table (cpp/search/searchupdatehelpers.cpp:12-76,
+// 151-326), SubtreeValueBiasTable::get (cpp/search/subtreevaluebiastable.cpp:61-78).  Canonical semantics on top of the tree
+// mode's (DESIGN.md ledger rows L, M):
+//  * a node keeps (visits, weightSum, utilityAvg, its own evaluation nnUtility); an edge keeps its visit count; the weight of
+//    a child seen from a parent is weightSum * (edgeVisits / max(visits, 1)); a visit re-computes every node on the path,
+//    bottom up, from its children: utilityAvg = (sum_i w_i u_i + own) / (sum_i w_i + 1) (valueWeightExponent 0, unit weights).
+//  * transposition key = getSitHash(next player) ^ mix(last move): the state that decides legality (the literal GraphHash
+//    chains the previous hash after every non-pass move, graphhash.cpp:14-29, and would never transpose in a game without
+//    passes).  Finished positions are not shared: terminal children stay per edge (equivalent, their statistics are constants).
+//  * choosing a child whose edge has fewer visits than the node behind it adds the edge visit without descending
+//    (maybeCatchUpEdgeVisits); a new edge that transposes to an existing node does exactly that on its first visit.
+//  * bias entry of a node = per-search table keyed by (player who moved, previous move, move, colours of the 5x5 window
+//    around the move on the board before it); on every re-computation the node moves its contribution
+//    (childrenUtility - nnUtility) * W^exponent to the entry and adds factor * deltaSum / weightSum to its own evaluation.
+//    The root has no entry.  W^exponent: sqrt for 0.5, identity for 1, otherwise detPow (IEEE basic operations only, the
+//    oracle computes the same bits).
+
+__device__ __forceinline__ double detLog(double x) {
+  long long b = __double_as_longlong(x);
+  int k = (int)((b >> 52) & 0x7ff) - 1022;
+  b = (b & 0x800fffffffffffffLL) | 0x3fe0000000000000LL;
+  double m = __longlong_as_double(b);
+  if(m < 0.70710678118654752) { m = __dmul_rn(m, 2.0); k -= 1; }
+  const double z = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0)), z2 = __dmul_rn(z, z);
+  double s = __ddiv_rn(1.0, 27.0);
+  for(int n = 25; n >= 1; n -= 2) s = __dadd_rn(__dmul_rn(s, z2), __ddiv_rn(1.0, (double)n));
+  return __dadd_rn(__dmul_rn((double)k, 0.69314718055994531), __dmul_rn(__dmul_rn(2.0, z), s));
+}
+__device__ __forceinline__ double detExp(double y) {
+  const double n = rint(__dmul_rn(y, 1.4426950408889634));
+  const double r = __dsub_rn(__dsub_rn(y, __dmul_rn(n, 0.693147180369123816490)), __dmul_rn(n, 1.90821492927058770002e-10));
+  double s = __ddiv_rn(1.0, 6227020800.0);
+  const double inv[13] = {1.0, 1.0, __ddiv_rn(1.0, 2.0), __ddiv_rn(1.0, 6.0), __ddiv_rn(1.0, 24.0), __ddiv_rn(1.0, 120.0), __ddiv_rn(1.0, 720.0),
+                          __ddiv_rn(1.0, 5040.0), __ddiv_rn(1.0, 40320.0), __ddiv_rn(1.0, 362880.0), __ddiv_rn(1.0, 3628800.0),
+                          __ddiv_rn(1.0, 39916800.0), __ddiv_rn(1.0, 479001600.0)};
+#pragma unroll
+  for(int i = 12; i >= 0; i--) s = __dadd_rn(__dmul_rn(s, r), inv[i]);
+  const double sc = __longlong_as_double((long long)((int)n + 1023) << 52);
+  return __dmul_rn(s, sc);
+}
+__device__ __forceinline__ double biasPow(double x, double e) {
+  if(e == 0.5) return __dsqrt_rn(x);
+  if(e == 1.0) return x;
+  return detExp(__dmul_rn(e, detLog(x)));
+}
+
+// statistics of the child behind edge `pos` of `nd`: (visits, weightSum, utilityAvg); terminal children are constants
+__device__ __forceinline__ void childStats(const SearchCfg& c, uint8_t* treeBase, int cc, int e, int& cv, double& cw, double& cu) {
+  if(cc >= 0) {
+    NodeRef ch{treeBase + (size_t)cc * c.nodeStride, c.P, c.polOff};
+    cv = ch.N(); cw = ch.weightSum(); cu = ch.utilityAvg();
+  } else { cv = e; cw = (double)e; cu = terminalValue(-2 - cc); }
+}
+__device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
+
+template <class D>
+__global__ void __launch_bounds__(128) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+  const D dm(g);
+  using BB = typename D::BB;
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  GameRegs<BB> s;
+  s.black = (BB)root.black[gi]; s.white = (BB)root.white[gi]; s.h0 = root.hash0[gi]; s.h1 = root.hash1[gi];
+  s.id = root.gameId[gi]; s.misc = root.misc[gi];
+  uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  const int count = t.nodeCount[gi];
+  int kind = 0, depth = 0, target = -1;
+  double leafVal = 0.0;
+  uint64_t key0 = 0, key1 = 0, bk0 = 0, bk1 = 0;
+  if(flagsOf(s.misc) & 1) kind = 0;
+  else if(count == 0) kind = 4;
+  else if(NodeRef{treeBase, c.P, c.polOff}.N() >= c.maxVisits) kind = 0;
+  else {
+    int node = 0;
+    while(true) {
+      NodeRef nd{treeBase + (size_t)node * c.nodeStride, c.P, c.polOff};
+      const int pla = nd.nextPla();
+      const double parentUtility = nd.utilityAvg();
+      const float* pol = nd.policy(); const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
+      double total = 0.0, mass = 0.0;
+      for(int pos = lane; pos < c.P; pos += 32) {
+        const int cc = ch[pos];
+        if(cc != -1) {
+          int cv; double cw, cu;
+          childStats(c, treeBase, cc, eN[pos], cv, cw, cu);
+          total = __dadd_rn(total, childWeightOf(cw, eN[pos], cv));
+          mass = __dadd_rn(mass, (double)pol[pos]);
+        }
+      }
+      total = warpSumD(total);
+      mass = warpSumD(mass);
+      const double red = __dmul_rn(depth == 0 ? c.rootFpuRed : c.fpuRed, __dsqrt_rn(mass));
+      const double fpu = pla == 2 ? __dsub_rn(parentUtility, red) : __dadd_rn(parentUtility, red);
+      const double scale = __dmul_rn(c.cpuct, __dsqrt_rn(__dadd_rn(total, 0.01)));
+      double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
+      float newP = -1.0f; int newPos = -1;
+      for(int pos = lane; pos < c.P; pos += 32) {
+        const float p = pol[pos];
+        const int cc = ch[pos];
+        if(cc != -1) {
+          int cv; double cw, cu;
+          childStats(c, treeBase, cc, eN[pos], cv, cw, cu);
+          const double w = childWeightOf(cw, eN[pos], cv);
+          const double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, w)), pla == 2 ? cu : -cu);
+          const int o = ord[pos];
+          if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
+        } else if(p >= 0.0f) {
+          if(p > newP) { newP = p; newPos = pos; }
+        }
+      }
+      for(int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, bestVal, o);
+        const int o2 = __shfl_xor_sync(0xffffffffu, bestOrd, o), p2 = __shfl_xor_sync(0xffffffffu, bestPos, o);
+        if(p2 >= 0 && (bestPos < 0 || v2 > bestVal || (v2 == bestVal && o2 < bestOrd))) { bestVal = v2; bestOrd = o2; bestPos = p2; }
+        const float np2 = __shfl_xor_sync(0xffffffffu, newP, o);
+        const int npos2 = __shfl_xor_sync(0xffffffffu, newPos, o);
+        if(npos2 >= 0 && (newPos < 0 || np2 > newP || (np2 == newP && npos2 < newPos))) { newP = np2; newPos = npos2; }
+      }
+      bool takeNew = false;
+      if(newPos >= 0) {
+        const double valNew = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)newP), 1.0), pla == 2 ? fpu : -fpu);
+        takeNew = bestPos < 0 || valNew > bestVal;
+      }
+      const int pos = takeNew ? newPos : bestPos;
+      if(pos < 0) { kind = 0; break; }
+      if(lane == 0) { t.pathNode[(size_t)gi * MAX_PATH + depth] = node; t.pathPos[(size_t)gi * MAX_PATH + depth] = (uint8_t)pos; }
+      depth++;
+      if(!takeNew) {
+        const int cc = ch[pos];
+        if(cc <= -2) { kind = 3; leafVal = terminalValue(-2 - cc); break; }
+        if(eN[pos] < NodeRef{treeBase + (size_t)cc * c.nodeStride, c.P, c.polOff}.N()) { kind = 5; break; }   // catch up, no descent
+        applyMoveLight(dm, s, pos, zob);
+        node = cc;
+        continue;
+      }
+      const BB beforeB = s.black, beforeW = s.white;
+      const uint64_t beforeMisc = s.misc;
+      BB L[4]; bool illegal;
+      stepGame(dm, g, s, pos, true, zob, L, illegal);
+      const int fl = flagsOf(s.misc);
+      if(fl & 1) { kind = 2; leafVal = terminalValue((fl >> 1) & 3); break; }
+      const int nextPla = (fl >> 3) & 3;
+      const uint64_t lm = (uint64_t)(pos + 1);
+      key0 = s.h0 ^ g.playerHash[nextPla][0] ^ splitmix64(lm);
+      key1 = s.h1 ^ g.playerHash[nextPla][1] ^ splitmix64(lm * PHI);
+      if(c.useTable) {
+        int found = -1;
+        if(lane == 0) {
+          const uint64_t* keys = t.tblKeys + (size_t)gi * c.tableCap * 2;
+          const int* vals = t.tblVals + (size_t)gi * c.tableCap;
+          int slot = (int)(key0 & (uint64_t)(c.tableCap - 1));
+          while(true) {
+            const int v = vals[slot];
+            if(v == 0) break;
+            if(keys[2 * slot] == key0 && keys[2 * slot + 1] == key1) { found = v - 1; break; }
+            slot = (slot + 1) & (c.tableCap - 1);
+          }
+        }
+        found = __shfl_sync(0xffffffffu, found, 0);
+        if(found >= 0) { kind = 6; target = found; break; }
+      }
+      kind = 1;
+      if(c.biasFactor != 0.0 && histPla(beforeMisc, 0) != 0) {
+        const int HW = dm.HW(), cell = pos % HW, cx = cell % dm.W(), cy = cell / dm.W();
+        uint64_t win = 0;
+        for(int dy = -2; dy <= 2; dy++)
+          for(int dx = -2; dx <= 2; dx++) {
+            const int x = cx + dx, y = cy + dy;
+            uint64_t code = 3;
+            if(x >= 0 && y >= 0 && x < dm.W() && y < dm.H()) {
+              const int bit = y * dm.stride() + x;
+              code = ((beforeB >> bit) & 1) ? 1 : ((beforeW >> bit) & 1) ? 2 : 0;
+            }
+            win |= code << (2 * ((dy + 2) * 5 + (dx + 2)));
+          }
+        const uint64_t mover = (uint64_t)((flagsOf(beforeMisc) >> 3) & 3);
+        bk0 = win | (mover << 50) | ((uint64_t)pos << 52);
+        bk1 = (uint64_t)(lastDirOf(beforeMisc) * HW + histCell(beforeMisc, 0) + 1);
+      }
+      break;
+    }
+  }
+  if(lane == 0) {
+    if(kind != 0) *t.active = 1;
+    t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
+    t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
+    t.leafKey[2 * (size_t)gi] = key0; t.leafKey[2 * (size_t)gi + 1] = key1;
+    t.leafBiasKey[2 * (size_t)gi] = bk0; t.leafBiasKey[2 * (size_t)gi + 1] = bk1;
+    t.leafTarget[gi] = target;
+    const bool needsNet = kind == 1 || kind == 4;
+    if(needsNet || !c.compact) {
+      const int slot = c.compact ? atomicAdd(t.evalCount, 1) : gi;
+      t.leafSlot[gi] = slot;
+      leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
+      leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
+    }
+  }
+}
+
+// recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
+__device__ __forceinline__ void recomputeNode(const SearchCfg& c, const TreeMem& t, int gi, uint8_t* treeBase, NodeRef nd, int lane) {
+  const int* ch = nd.child(); const int* eN = nd.edgeN();
+  double sumW = 0.0, sumWU = 0.0;
+  for(int pos = lane; pos < c.P; pos += 32) {
+    const int cc = ch[pos];
+    if(cc != -1) {
+      int cv; double cw, cu;
+      const int e = eN[pos];
+      childStats(c, treeBase, cc, e, cv, cw, cu);
+      if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
+      const double w = childWeightOf(cw, e, cv);
+      sumW = __dadd_rn(sumW, w);
+      sumWU = __dadd_rn(sumWU, __dmul_rn(w, cu));
+    }
+  }
+  sumW = warpSumD(sumW);
+  sumWU = warpSumD(sumWU);
+  if(lane == 0) {
+    double utility = nd.nnUtility();
+    const int be = nd.biasEntry();
+    if(c.biasFactor != 0.0 && be >= 0) {
+      double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
+      double ed = E[0], ew = E[1];
+      if(sumW > 1e-10) {
+        const double uc = __ddiv_rn(sumWU, sumW);
+        const double bw = biasPow(sumW, c.biasExp);
+        const double ds = __dmul_rn(__dsub_rn(uc, nd.nnUtility()), bw);
+        ed = __dadd_rn(ed, __dsub_rn(ds, nd.lastDelta()));
+        ew = __dadd_rn(ew, __dsub_rn(bw, nd.lastWeight()));
+        E[0] = ed; E[1] = ew;
+        nd.lastDelta() = ds; nd.lastWeight() = bw;
+      }
+      if(ew > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, ed), ew));
+    }
+    nd.utilityAvg() = __ddiv_rn(__dadd_rn(sumWU, utility), __dadd_rn(sumW, 1.0));
+    nd.weightSum() = __dadd_rn(sumW, 1.0);
+    nd.N() = nd.N() + 1;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  const int kind = t.leafKind[gi];
+  if(kind == 0) return;
+  uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  const int depth = t.pathLen[gi];
+  double v = t.leafValue[gi];
+  int newIdx = -1;
+  if(kind == 1 || kind == 4) {
+    const size_t row = (size_t)t.leafSlot[gi];
+    v = __dsub_rn((double)winLoss[2 * row], (double)winLoss[2 * row + 1]);
+    newIdx = t.nodeCount[gi];
+    if(newIdx >= c.maxNodes) return;   // cannot happen: at most one new node per visit
+    NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P, c.polOff};
+    for(int pos = lane; pos < c.P; pos += 32) {
+      nd.policy()[pos] = policy[row * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
+    }
+    if(lane == 0) {
+      int be = -1;
+      double utility = v;
+      const uint64_t bk0 = t.leafBiasKey[2 * (size_t)gi], bk1 = t.leafBiasKey[2 * (size_t)gi + 1];
+      if(kind == 1 && bk0 != 0) {   // SubtreeValueBiasTable::get: find or create the entry
+        uint64_t* keys = t.biasKeys + (size_t)gi * c.tableCap * 2;
+        int slot = (int)(splitmix64(bk0 ^ splitmix64(bk1)) & (uint64_t)(c.tableCap - 1));
+        while(true) {
+          if(keys[2 * slot] == 0) { keys[2 * slot] = bk0; keys[2 * slot + 1] = bk1; break; }
+          if(keys[2 * slot] == bk0 && keys[2 * slot + 1] == bk1) break;
+          slot = (slot + 1) & (c.tableCap - 1);
+        }
+        be = slot;
+        const double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
+        if(E[1] > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, E[0]), E[1]));   // addLeafValue :27-37
+      }
+      nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi]; nd.biasEntry() = be;
+      nd.weightSum() = 1.0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
+      t.nodeCount[gi] = newIdx + 1;
+      if(kind == 1 && c.useTable) {
+        uint64_t* keys = t.tblKeys + (size_t)gi * c.tableCap * 2;
+        int* vals = t.tblVals + (size_t)gi * c.tableCap;
+        const uint64_t key0 = t.leafKey[2 * (size_t)gi], key1 = t.leafKey[2 * (size_t)gi + 1];
+        int slot = (int)(key0 & (uint64_t)(c.tableCap - 1));
+        while(vals[slot] != 0) slot = (slot + 1) & (c.tableCap - 1);
+        keys[2 * slot] = key0; keys[2 * slot + 1] = key1; vals[slot] = newIdx + 1;
+      }
+    }
+  }
+  __syncwarp();
+  for(int d = depth - 1; d >= 0; d--) {
+    NodeRef nd{treeBase + (size_t)t.pathNode[(size_t)gi * MAX_PATH + d] * c.nodeStride, c.P, c.polOff};
+    const int pos = t.pathPos[(size_t)gi * MAX_PATH + d];
+    if(lane == 0) {
+      if(d == depth - 1 && (kind == 1 || kind == 2 || kind == 6)) {
+        nd.child()[pos] = kind == 1 ? newIdx : kind == 6 ? t.leafTarget[gi] : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
+        nd.order()[pos] = (uint8_t)nd.numChildren();
+        nd.numChildren() = nd.numChildren() + 1;
+      }
+      nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
+    }
+    __syncwarp();
+    recomputeNode(c, t, gi, treeBase, nd, lane);
+  }
+  if(lane != 0) return;
+  atomicAdd(&t.stats[0], 1ULL);
+  if(kind == 1 || kind == 4) atomicAdd(&t.stats[1], 1ULL);
+  else if(kind == 2 || kind == 3) atomicAdd(&t.stats[2], 1ULL);
+  else if(kind == 6) atomicAdd(&t.stats[8], 1ULL);
+  else atomicAdd(&t.stats[9], 1ULL);
+}
+
+// hash over every node of every game's graph (creation order = node index), compared with the oracle's
+__global__ void __launch_bounds__(128) k_tree_digest(const SearchCfg c, TreeMem t, uint64_t* __restrict__ out) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  const int count = t.nodeCount[gi];
+  uint64_t h = 0;
+  for(int i = lane; i < count; i += 32) {
+    NodeRef nd{treeBase + (size_t)i * c.nodeStride, c.P, c.polOff};
+    const uint64_t wb = (uint64_t)__double_as_longlong(nd.weightSum()), ub = (uint64_t)__double_as_longlong(nd.utilityAvg());
+    uint64_t nh = splitmix64((uint64_t)nd.N() ^ ((uint64_t)nd.numChildren() << 32)) ^ splitmix64(wb ^ PHI) ^ splitmix64(ub + PHI);
+    for(int pos = 0; pos < c.P; pos++) {
+      const int cc = nd.child()[pos];
+      if(cc != -1)
+        nh ^= splitmix64((((uint64_t)(uint32_t)cc << 32) | (uint64_t)(uint32_t)nd.edgeN()[pos]) + (uint64_t)(pos + 1) * PHI + nd.order()[pos]);
+    }
+    h ^= splitmix64(nh + (uint64_t)(i + 1) * PHI);
+  }
+  for(int o = 16; o > 0; o >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, o);
+  if(lane == 0) out[gi] = h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -306,7 +668,7 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
   s.id = root.gameId[gi]; s.misc = root.misc[gi];
   int move = -1;
   if(!(flagsOf(s.misc) & 1) && t.nodeCount[gi] > 0) {
-    NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P};
+    NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P, c.polOff};
     const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
     long long total = 0;
     int bestN = -1, bestOrd = 1 << 20, bestPos = -1;
@@ -329,7 +691,7 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
           const size_t r = (size_t)gi * tr.maxPlies + k;
           if(k == 0) tr.recGameId[gi] = s.id;
           tr.recBlack[r] = (uint64_t)s.black; tr.recWhite[r] = (uint64_t)s.white; tr.recMisc[r] = s.misc;
-          tr.recN[r] = nd.N(); tr.recW[r] = nd.W();
+          tr.recN[r] = nd.N(); tr.recW[r] = c.graph ? __dmul_rn(nd.utilityAvg(), (double)nd.N()) : nd.W();
           for(int pos = 0; pos < c.P; pos++) tr.recVisits[r * c.P + pos] = (int16_t)(ch[pos] != -1 ? min(eN[pos], 32767) : 0);
           tr.recCount[gi] = k + 1;
         }
@@ -363,7 +725,7 @@ __global__ void __launch_bounds__(128) k_reroot(const SearchCfg c, TreeMem t, St
   const int move = chosen[gi];
   int count = 0;
   if(move >= 0 && t.nodeCount[gi] > 0 && !(flagsOf(root.misc[gi]) & 1)) {
-    const int first = NodeRef{const_cast<uint8_t*>(src), c.P}.child()[move];
+    const int first = NodeRef{const_cast<uint8_t*>(src), c.P, c.polOff}.child()[move];
     if(first >= 0) {
       if(lane == 0) queue[0] = first;
       count = 1;
@@ -375,7 +737,7 @@ __global__ void __launch_bounds__(128) k_reroot(const SearchCfg c, TreeMem t, St
         for(int k = lane; k < c.nodeStride / 16; k += 32) d4[k] = s4[k];
         __syncwarp();
         // children in policy-index order get the next free indices
-        int* dch = NodeRef{dst + (size_t)i * c.nodeStride, c.P}.child();
+        int* dch = NodeRef{dst + (size_t)i * c.nodeStride, c.P, c.polOff}.child();
         for(int p0 = 0; p0 < c.P; p0 += 32) {
           const int pos = p0 + lane;
           const int ch = pos < c.P ? dch[pos] : -1;
@@ -553,6 +915,18 @@ using namespace kc;
 namespace {
 bool isStatic5(const Geom& g) { return g.W == 5 && g.H == 5 && g.K == 4; }
 
+// graph mode: a search starts with empty transposition and bias tables (no tree re-use: every node of the previous search is
+// gone, so every bias entry is unreferenced -- SubtreeValueBiasTable::clearUnusedSynchronous, search.cpp:689-690)
+int clearTables(kc_search* S, cudaStream_t st) {
+  const SearchCfg& c = S->cfg;
+  if(!c.graph) return 0;
+  const size_t slots = (size_t)c.numGames * c.tableCap;
+  KC_CUDA(cudaMemsetAsync(S->tree.tblVals, 0, slots * 4, st));
+  KC_CUDA(cudaMemsetAsync(S->tree.biasKeys, 0, slots * 16, st));
+  KC_CUDA(cudaMemsetAsync(S->tree.biasVals, 0, slots * 16, st));
+  return 0;
+}
+
 int runVisits(kc_search* S) {
   const SearchCfg& c = S->cfg;
   kc_games* R = S->root; kc_games* Lf = S->leaf;
@@ -568,7 +942,10 @@ int runVisits(kc_search* S) {
       KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
     }
     if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount, 0, 4, st));
-    if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
+    if(c.graph) {
+      if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
+      else k_select_graph<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
+    } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
     else k_select<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
     S->launches++;
     if(S->handle) {
@@ -580,7 +957,8 @@ int runVisits(kc_search* S) {
       k_hash_eval<<<warpBlocks, 128, 0, st>>>(c.numGames, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, S->d_policy, S->d_winLoss);
       S->launches += 2;
     }
-    k_expand_backup<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
+    if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
+    else k_expand_backup<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
     S->launches++;
   }
   KC_CUDA(cudaGetLastError());
@@ -594,6 +972,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(ctx && p && out, "kc_search_create: null argument");
   KC_CHECK(p->maxVisits >= 1 && p->maxVisits <= 65536, "kc_search_create: maxVisits must be within 1..65536");
   KC_CHECK(p->cpuctExploration > 0 && p->fpuReductionMax >= 0 && p->rootFpuReductionMax >= 0, "kc_search_create: bad exploration parameters");
+  KC_CHECK(!(p->useGraphSearch || p->subtreeValueBiasFactor != 0.0) || !p->reuseTree, "kc_search_create: graph search / subtree value bias with reuseTree is not supported");
+  KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
   S->ctx = ctx; S->handle = handleOrNull;
@@ -601,7 +981,13 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   if(handleOrNull && kc::handleCheckGeometry(handleOrNull, xSize, ySize, numGames)) { kc_games_destroy(S->root); kc_games_destroy(S->leaf); delete S; return 1; }
   SearchCfg& c = S->cfg;
   c.P = 4 * xSize * ySize; c.LW = (c.P + 31) / 32;
-  c.nodeStride = (32 + 21 * c.P + 15) / 16 * 16;
+  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0) ? 1 : 0;
+  c.useTable = p->useGraphSearch ? 1 : 0;
+  c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent;
+  c.polOff = c.graph ? 64 : 32 + 8 * c.P;
+  c.nodeStride = (c.polOff + 13 * c.P + 15) / 16 * 16;
+  c.tableCap = 16;
+  while(c.tableCap < 2 * p->maxVisits) c.tableCap *= 2;
   c.maxNodes = p->maxVisits; c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
   c.numGames = numGames; c.autoRefill = p->autoRefill ? 1 : 0;
   c.compact = (handleOrNull && kc::handleIsBf16(handleOrNull) && !p->noCompaction) ? 1 : 0;
@@ -625,7 +1011,14 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CUDA(cudaMalloc(&S->tree.leafValue, n * 8)); KC_CUDA(cudaMalloc(&S->tree.leafNextPla, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.leafSlot, n * 4)); KC_CUDA(cudaMemset(S->tree.leafSlot, 0, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.evalCount, 4)); KC_CUDA(cudaMemset(S->tree.evalCount, 0, 4));
-  KC_CUDA(cudaMalloc(&S->tree.stats, 64)); KC_CUDA(cudaMemset(S->tree.stats, 0, 64));
+  KC_CUDA(cudaMalloc(&S->tree.stats, NUM_STATS * 8)); KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
+  if(c.graph) {
+    const size_t slots = n * c.tableCap;
+    KC_CUDA(cudaMalloc(&S->tree.tblKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.tblVals, slots * 4));
+    KC_CUDA(cudaMalloc(&S->tree.biasKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.biasVals, slots * 16));
+    KC_CUDA(cudaMalloc(&S->tree.leafKey, n * 16)); KC_CUDA(cudaMalloc(&S->tree.leafBiasKey, n * 16)); KC_CUDA(cudaMalloc(&S->tree.leafTarget, n * 4));
+    KC_CUDA(cudaMemset(S->tree.tblVals, 0, slots * 4)); KC_CUDA(cudaMemset(S->tree.biasKeys, 0, slots * 16)); KC_CUDA(cudaMemset(S->tree.biasVals, 0, slots * 16));
+  }
   KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
   KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
@@ -642,6 +1035,8 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.leafKind); cudaFree(S->tree.leafValue); cudaFree(S->tree.leafNextPla); cudaFree(S->tree.stats);
   cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
   cudaFree(S->tree.nodesAlt); cudaFree(S->tree.rerootQueue); cudaFree(S->tree.active);
+  cudaFree(S->tree.tblKeys); cudaFree(S->tree.tblVals); cudaFree(S->tree.biasKeys); cudaFree(S->tree.biasVals);
+  cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget);
   { kc::TrainMem& t = S->train;
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
@@ -660,7 +1055,7 @@ int kc_search_reset(kc_search* S, uint64_t seed, uint64_t firstGameId) {
   S->cfg.seed = seed;
   if(kc_games_reset(S->root, seed, firstGameId, 0)) return 1;
   KC_CUDA(cudaMemset(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4));
-  KC_CUDA(cudaMemset(S->tree.stats, 0, 64));
+  KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
   return 0;
 }
 
@@ -668,6 +1063,7 @@ int kc_search_run_visits(kc_search* S) {
   KC_CHECK(S, "kc_search_run_visits: null search");
   KC_CUDA(cudaSetDevice(S->ctx->device));
   KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4, S->leaf->stream));
+  if(clearTables(S, S->leaf->stream)) return 1;
   if(runVisits(S)) return 1;
   KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
   if(S->handle && kc::handleCheckAbort(S->handle)) return 1;
@@ -686,14 +1082,28 @@ int kc_search_read_root(kc_search* S, int32_t* rootVisits, double* rootUtilitySu
     if(have) KC_CUDA(cudaMemcpy(node.data(), S->tree.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.nodeStride, cudaMemcpyDeviceToHost));
     else std::fill(node.begin(), node.end(), 0);
     const uint8_t* b = node.data();
-    if(rootVisits) rootVisits[gi] = have ? *reinterpret_cast<const int*>(b) : 0;
-    if(rootUtilitySum) rootUtilitySum[gi] = have ? *reinterpret_cast<const double*>(b + 16) : 0.0;
+    const int* child = reinterpret_cast<const int*>(b + c.polOff + 4 * c.P);
+    const int* edgeN = reinterpret_cast<const int*>(b + c.polOff + 8 * c.P);
+    const int visits = have ? *reinterpret_cast<const int*>(b) : 0;
+    if(rootVisits) rootVisits[gi] = visits;
+    // graph mode reports utilityAvg * visits (and per edge the child's utilityAvg * edgeVisits): one rounding, as the oracle does
+    if(rootUtilitySum) rootUtilitySum[gi] = !have ? 0.0 : c.graph ? *reinterpret_cast<const double*>(b + 24) * (double)visits : *reinterpret_cast<const double*>(b + 16);
     for(int pos = 0; pos < c.P; pos++) {
-      const bool ex = have && reinterpret_cast<const int*>(b + 32 + 12 * c.P)[pos] != -1;
-      if(edgeVisits) edgeVisits[(size_t)gi * c.P + pos] = ex ? reinterpret_cast<const int*>(b + 32 + 16 * c.P)[pos] : 0;
-      if(edgeUtilitySum) edgeUtilitySum[(size_t)gi * c.P + pos] = ex ? reinterpret_cast<const double*>(b + 32)[pos] : 0.0;
-      if(policy) policy[(size_t)gi * c.P + pos] = have ? reinterpret_cast<const float*>(b + 32 + 8 * c.P)[pos] : 0.f;
-      if(order) order[(size_t)gi * c.P + pos] = ex ? (b + 32 + 20 * c.P)[pos] : 255;
+      const bool ex = have && child[pos] != -1;
+      if(edgeVisits) edgeVisits[(size_t)gi * c.P + pos] = ex ? edgeN[pos] : 0;
+      if(edgeUtilitySum) {
+        double v = 0.0;
+        if(ex && !c.graph) v = reinterpret_cast<const double*>(b + 32)[pos];
+        else if(ex) {
+          double cu = child[pos] == -4 ? 1.0 : child[pos] == -3 ? -1.0 : 0.0;
+          if(child[pos] >= 0)
+            KC_CUDA(cudaMemcpy(&cu, S->tree.nodes + ((size_t)gi * c.maxNodes + child[pos]) * c.nodeStride + 24, 8, cudaMemcpyDeviceToHost));
+          v = cu * (double)edgeN[pos];
+        }
+        edgeUtilitySum[(size_t)gi * c.P + pos] = v;
+      }
+      if(policy) policy[(size_t)gi * c.P + pos] = have ? reinterpret_cast<const float*>(b + c.polOff)[pos] : 0.f;
+      if(order) order[(size_t)gi * c.P + pos] = ex ? (b + c.polOff + 12 * c.P)[pos] : 255;
     }
   }
   return 0;
@@ -706,7 +1116,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
   kc_games* R = S->root;
   cudaStream_t st = S->leaf->stream;
   const int blocks = (c.numGames + 127) / 128;
-  KC_CUDA(cudaMemsetAsync(S->tree.stats, 0, 64, st));
+  KC_CUDA(cudaMemsetAsync(S->tree.stats, 0, NUM_STATS * 8, st));
   KC_CUDA(cudaEventRecord(S->ev0, st));
   for(int m = 0; m < moves; m++) {
     if(c.autoRefill) {
@@ -716,6 +1126,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     }
     if(!c.reuseTree) KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
     KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
+    if(clearTables(S, st)) return 1;
     if(runVisits(S)) return 1;
     if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
@@ -734,8 +1145,8 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
   }
   KC_CUDA(cudaEventRecord(S->ev1, st));
   KC_CUDA(cudaGetLastError());
-  unsigned long long hs[8];
-  KC_CUDA(cudaMemcpyAsync(hs, S->tree.stats, 64, cudaMemcpyDeviceToHost, st));
+  unsigned long long hs[NUM_STATS];
+  KC_CUDA(cudaMemcpyAsync(hs, S->tree.stats, NUM_STATS * 8, cudaMemcpyDeviceToHost, st));
   if(chosenLast) KC_CUDA(cudaMemcpyAsync(chosenLast, S->d_chosen, (size_t)c.numGames * 2, cudaMemcpyDeviceToHost, st));
   KC_CUDA(cudaStreamSynchronize(st));
   if(S->handle && kc::handleCheckAbort(S->handle)) return 1;
@@ -744,6 +1155,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     acc->visits += hs[0]; acc->netEvals += hs[1]; acc->terminalVisits += hs[2]; acc->movesPlayed += hs[3];
     acc->gamesFinished += hs[4]; acc->blackWins += hs[5]; acc->whiteWins += hs[6]; acc->draws += hs[7];
     acc->batchRows += c.compact ? hs[1] : (uint64_t)c.numGames * c.maxVisits * moves;
+    acc->transpositionHits += hs[8]; acc->catchUpVisits += hs[9];
   }
   return 0;
 }
@@ -795,6 +1207,22 @@ int kc_search_read_training_rows(kc_search* S, int* numRows, int* numDropped, ui
     if(valueTargetsNCHW) KC_CUDA(cudaMemcpy(valueTargetsNCHW, t.outValue, rows * 5 * g.HW, cudaMemcpyDeviceToHost));
   }
   if(clear) KC_CUDA(cudaMemset(t.rowCount, 0, 8));
+  return 0;
+}
+
+int kc_search_tree_digest(kc_search* S, uint64_t* digest) {
+  KC_CHECK(S && digest, "kc_search_tree_digest: null argument");
+  KC_CHECK(S->cfg.graph, "kc_search_tree_digest: only for searches created with useGraphSearch or a subtree value bias");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  const SearchCfg& c = S->cfg;
+  uint64_t* d = nullptr;
+  KC_CUDA(cudaMalloc(&d, (size_t)c.numGames * 8));
+  k_tree_digest<<<(c.numGames * 32 + 127) / 128, 128, 0, S->leaf->stream>>>(c, S->tree, d);
+  const cudaError_t e = cudaMemcpyAsync(digest, d, (size_t)c.numGames * 8, cudaMemcpyDeviceToHost, S->leaf->stream);
+  cudaStreamSynchronize(S->leaf->stream);
+  cudaFree(d);
+  KC_CUDA(e);
+  KC_CUDA(cudaGetLastError());
   return 0;
 }
 

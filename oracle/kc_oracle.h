@@ -96,6 +96,12 @@ void ko_game_nn_hash(const ko_game* g, int pla, double playoutDoublingAdvantage,
 void ko_game_fill_row_v1(const ko_game* g, int pla, int nnXLen, int nnYLen, int useNHWC,
                          float* rowBin, float* rowGlobal);
 int ko_game_color_at(const ko_game* g, int x, int y);
+/* policy index of the k-th most recent move (0 = last), -1 if there is none */
+int ko_game_recent_move_pos(const ko_game* g, int k);
+/* GraphHash::getGraphHash (cpp/game/graphhash.cpp:3-28), literal.  Because Coffee has no pass move the reference chains the
+ * previous hash in after EVERY move, so the literal hash is path-dependent and never transposes (SURVEY ledger row L in
+ * DESIGN.md); the search's transposition key is ko_search's canonical state key instead. */
+void ko_graph_hash(const uint64_t prev[2], const ko_game* g, int nextPla, uint64_t out[2]);
 
 /* SymmetryHelpers (nninputs.cpp:252-433) */
 void ko_copy_inputs_with_symmetry(const float* src, float* dst, int n, int h, int w, int c,
@@ -208,12 +214,18 @@ void ko_postprocess(float* policy, int policySize, const uint32_t* legalMask, fl
  * evaluator that the CUDA search also implements, so trees can be compared exactly.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
-  int32_t maxVisits, temperaturePlies, autoRefill, noCompaction, reuseTree, pad_;
+  int32_t maxVisits, temperaturePlies, autoRefill, noCompaction, reuseTree, useGraphSearch;
   double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
+  double subtreeValueBiasFactor, subtreeValueBiasWeightExponent;
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                    uint8_t* orderOut, uint64_t counters[3] /* += visits, evaluations, terminal visits */);
+/* Graph search (transpositions) and subtree value bias: see the block comment in ko_search.cpp.  counters[5] += visits,
+ * evaluations, terminal visits, transposition hits, catch-up visits. */
+void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                         int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                         uint8_t* orderOut, uint64_t counters[5], uint64_t* digest);
 typedef struct ko_search ko_search;   /* persistent tree: continue() searches on, advance() re-roots at the move played */
 ko_search* ko_search_create(void);
 void ko_search_destroy(ko_search* s);

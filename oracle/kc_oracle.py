@@ -93,6 +93,9 @@ def lib():
         l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
         l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        l.ko_search_run_graph.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        l.ko_graph_hash.argtypes = [vp, vp, C.c_int, vp]
+        l.ko_game_recent_move_pos.argtypes = [vp, C.c_int]
         l.ko_search_create.restype = vp
         l.ko_search_destroy.argtypes = [vp]
         l.ko_search_clear.argtypes = [vp]
@@ -279,8 +282,9 @@ def postprocess(policy, legal_mask, value2, misc2, next_pla, temp=1.0):
 
 class SearchParams(C.Structure):
     """Same layout as kc_search_params (include/katacoffee_b200.h)."""
-    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("pad_", C.c_int32),
-                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double)]
+    _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("useGraphSearch", C.c_int32),
+                ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double),
+                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double)]
 
 
 def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
@@ -295,6 +299,20 @@ def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
                         _p(order), _p(cnt))
     return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
             "counters": cnt}
+
+
+def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5):
+    """One oracle graph search (transpositions + subtree value bias) from `game`; see ko_search.cpp.  counters = visits,
+    evaluations, terminal visits, transposition hits, catch-up visits; digest = hash over the whole graph."""
+    P = 4 * game.HW
+    sp = SearchParams(max_visits, 0, 0, 0, 0, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent)
+    rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
+    ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
+    cnt = np.zeros(5, np.uint64); dg = np.zeros(1, np.uint64)
+    lib().ko_search_run_graph(game._g, game.W, game.H, C.byref(sp), None if model is None else model._m, _p(rv), _p(rw), _p(ev), _p(ew),
+                              _p(pol), _p(order), _p(cnt), _p(dg))
+    return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
+            "counters": cnt, "digest": int(dg[0])}
 
 
 class PersistentSearch:

@@ -331,6 +331,34 @@ int ko_game_finished(const ko_game* g) { return g->isGameFinished ? 1 : 0; }
 int ko_game_winner(const ko_game* g) { return g->winner; }
 int ko_game_max_consecutives(const ko_game* g, int x, int y) { return g->maxConsecutives(g->spotOf(x, y)); }
 int ko_game_color_at(const ko_game* g, int x, int y) { return g->colors[g->spotOf(x, y)]; }
+// policy index (dir*H*W + y*W + x) of the k-th most recent move (0 = the last one), -1 if the history is shorter
+int ko_game_recent_move_pos(const ko_game* g, int k) {
+  const int n = (int)g->moveHistory.size();
+  if(k < 0 || k >= n) return -1;
+  const Move& m = g->moveHistory[n - 1 - k];
+  return (int)m.dir * g->x_size * g->y_size + g->getY(m.spot) * g->x_size + g->getX(m.spot);
+}
+// GraphHash::getGraphHash (cpp/game/graphhash.cpp:3-28), literal: state hash = getSitHash(nextPla) ^ GAME_IS_OVER when finished;
+// after any move the previous graph hash is chained in (hash0 = splitMix64(h0 ^ h1), hash1 = nasam(h1) + hash0, then += state hash).
+static uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+static uint64_t nasam(uint64_t x) {   // cpp/core/hash.cpp:72-80
+  x ^= rotr64(x, 25) ^ rotr64(x, 47);
+  x *= 0x9e6c63d0676a9a99ULL;
+  x ^= (x >> 23) ^ (x >> 51);
+  x *= 0x9e6d62d06f6a9a9bULL;
+  x ^= (x >> 23) ^ (x >> 51);
+  return x;
+}
+void ko_graph_hash(const uint64_t prev[2], const ko_game* g, int nextPla, uint64_t out[2]) {
+  uint64_t st[2];
+  ko_game_sit_hash(g, nextPla, st);
+  if(g->isGameFinished) { st[0] ^= GAME_IS_OVER0; st[1] ^= GAME_IS_OVER1; }
+  if(g->moveHistory.empty()) { out[0] = st[0]; out[1] = st[1]; return; }
+  uint64_t h0 = ko_splitmix64(prev[0] ^ prev[1]);
+  uint64_t h1 = nasam(prev[1]) + h0;
+  out[0] = h0 + st[0];
+  out[1] = h1 + st[1];
+}
 uint32_t ko_game_status(const ko_game* g) {
   return (uint32_t)(g->numTurns & 0xff) | ((g->isGameFinished ? 1u : 0u) << 8) |
          ((uint32_t)g->winner << 9) | ((uint32_t)g->presumedNextMovePla << 11);

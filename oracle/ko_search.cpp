@@ -199,6 +199,302 @@ void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_sea
   searchRunOnTree(nodes, rootGame, x_size, y_size, p, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Graph search + subtree value bias (BASELINE config 4: useGraphSearch, subtreeValueBiasFactor).
+// Restates, for one game and one thread:
+//   Search::allocateOrFindNode (transposition lookup)        cpp/search/search.cpp:704-757
+//   Search::playoutDescend / maybeCatchUpEdgeVisits          cpp/search/search.cpp:935-1207
+//   selection on child NODE statistics, getChildWeight       cpp/search/searchexplorehelpers.cpp:92-127, 323-451, searchnode.h:59-65
+//   addLeafValue / recomputeNodeStats incl. the bias table   cpp/search/searchupdatehelpers.cpp:12-76, 151-326
+//   SubtreeValueBiasTable::get                               cpp/search/subtreevaluebiastable.cpp:61-78
+// Canonical choices (ledger rows L and M):
+//  * transposition key = getSitHash(next player) mixed with the last move (cell + direction): the state that decides
+//    legality.  The literal GraphHash chains the previous hash after every non-pass move (graphhash.cpp:14-29) and would
+//    never transpose in a game without passes.  Finished positions are not shared (terminal children stay per edge;
+//    equivalent, their statistics are constants).
+//  * a node keeps (visits, weightSum, utilityAvg); an edge keeps its visit count; a child's weight seen from a parent is
+//    weightSum * edgeVisits / max(visits, 1).  valueWeightExponent 0, no noise pruning, unit evaluation weights.
+//  * bias entry key = (player who moved, previous move, move, colours of the 5x5 window around the move on the board
+//    before it); Go's atari and ko terms do not exist.  The root has no entry; the table is per search.
+//  * origTotalChildWeight^exponent: sqrt for 0.5, identity for 1, otherwise detPow (below) -- a pow built from IEEE
+//    basic operations only, so that the device computes the same bits.
+//  * sums over children are accumulated per lane (policy index mod 32) and combined by an xor butterfly, like the warp does.
+// PARITY UNPINNED, like the rest of the search.
+#include <map>
+namespace {
+
+double detLog(double x) {
+  uint64_t b; memcpy(&b, &x, 8);
+  int k = (int)((b >> 52) & 0x7ff) - 1022;                       // x = m * 2^k, m in [0.5, 1)
+  b = (b & 0x800fffffffffffffULL) | 0x3fe0000000000000ULL;
+  double m; memcpy(&m, &b, 8);
+  if(m < 0.70710678118654752) { m = m * 2.0; k -= 1; }
+  const double z = (m - 1.0) / (m + 1.0), z2 = z * z;
+  double s = 1.0 / 27.0;
+  for(int n = 25; n >= 1; n -= 2) s = s * z2 + 1.0 / (double)n;
+  return (double)k * 0.69314718055994531 + (2.0 * z) * s;
+}
+double detExp(double y) {
+  const double n = std::nearbyint(y * 1.4426950408889634);
+  const double r = (y - n * 0.693147180369123816490) - n * 1.90821492927058770002e-10;
+  double s = 1.0 / 6227020800.0;                                 // 1/13!
+  static const double inv[13] = {1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,
+                                 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0};
+  for(int i = 12; i >= 0; i--) s = s * r + inv[i];
+  const uint64_t eb = (uint64_t)((int)n + 1023) << 52;           // 2^n, n well inside the normal range here
+  double sc; memcpy(&sc, &eb, 8);
+  return s * sc;
+}
+double biasPow(double x, double e) {
+  if(e == 0.5) return std::sqrt(x);
+  if(e == 1.0) return x;
+  return detExp(e * detLog(x));
+}
+
+struct GNode {
+  int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1;
+  double weightSum = 0.0, utilityAvg = 0.0, nnUtility = 0.0, lastDelta = 0.0, lastWeight = 0.0;
+  std::vector<float> policy;
+  std::vector<int> child, edgeN;
+  std::vector<uint8_t> order;
+  explicit GNode(int P) : policy(P, -1.0f), child(P, -1), edgeN(P, 0), order(P, 0) {}
+};
+struct BiasEntry { double deltaSum = 0.0, weightSum = 0.0; };
+typedef std::pair<uint64_t, uint64_t> Key;
+
+struct GraphSearch {
+  int W, H, P;
+  const ko_search_params* p;
+  std::vector<GNode> nodes;
+  std::map<Key, int> table;       // transposition key -> node
+  std::map<Key, int> biasIndex;   // bias key -> entry
+  std::vector<BiasEntry> bias;
+
+  static Key stateKey(const ko_game* g) {
+    uint64_t h[2];
+    ko_game_sit_hash(g, ko_game_next_pla(g), h);
+    const uint64_t lm = (uint64_t)(ko_game_recent_move_pos(g, 0) + 1);
+    return Key(h[0] ^ ko_splitmix64(lm), h[1] ^ ko_splitmix64(lm * PHI));
+  }
+  // key of the bias entry of the node reached by `movePos` from `before` (the position before the move)
+  Key biasKey(const ko_game* before, int movePos) const {
+    const int HW = W * H, cell = movePos % HW, cx = cell % W, cy = cell / W;
+    uint64_t win = 0;
+    for(int dy = -2; dy <= 2; dy++)
+      for(int dx = -2; dx <= 2; dx++) {
+        const int x = cx + dx, y = cy + dy;
+        const uint64_t code = (x < 0 || y < 0 || x >= W || y >= H) ? 3 : (uint64_t)ko_game_color_at(before, x, y);
+        win |= code << (2 * ((dy + 2) * 5 + (dx + 2)));
+      }
+    const uint64_t mover = (uint64_t)ko_game_next_pla(before);
+    return Key(win | (mover << 50) | ((uint64_t)movePos << 52), (uint64_t)(ko_game_recent_move_pos(before, 0) + 1));
+  }
+  void childStats(const GNode& nd, int pos, int& cv, double& cw, double& cu) const {
+    const int c = nd.child[pos];
+    if(c >= 0) { cv = nodes[c].visits; cw = nodes[c].weightSum; cu = nodes[c].utilityAvg; }
+    else { cv = nd.edgeN[pos]; cw = (double)nd.edgeN[pos]; cu = terminalValue(-2 - c); }
+  }
+  static double childWeight(double cw, int e, int cv) { return cw * ((double)e / (double)std::max(cv, 1)); }
+
+  void recompute(GNode& nd) {
+    double partW[32] = {0}, partWU[32] = {0};
+    for(int pos = 0; pos < P; pos++)
+      if(nd.child[pos] != -1) {
+        int cv; double cw, cu;
+        childStats(nd, pos, cv, cw, cu);
+        const int e = nd.edgeN[pos];
+        if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
+        const double w = childWeight(cw, e, cv);
+        partW[pos & 31] = partW[pos & 31] + w;
+        partWU[pos & 31] = partWU[pos & 31] + w * cu;
+      }
+    const double sumW = butterfly(partW), sumWU = butterfly(partWU);
+    double utility = nd.nnUtility;
+    if(p->subtreeValueBiasFactor != 0.0 && nd.biasEntry >= 0) {
+      BiasEntry& E = bias[nd.biasEntry];
+      if(sumW > 1e-10) {
+        const double uc = sumWU / sumW;
+        const double bw = biasPow(sumW, p->subtreeValueBiasWeightExponent);
+        const double ds = (uc - nd.nnUtility) * bw;
+        E.deltaSum = E.deltaSum + (ds - nd.lastDelta);
+        E.weightSum = E.weightSum + (bw - nd.lastWeight);
+        nd.lastDelta = ds; nd.lastWeight = bw;
+      }
+      if(E.weightSum > 0.001) utility = utility + (p->subtreeValueBiasFactor * E.deltaSum) / E.weightSum;
+    }
+    nd.utilityAvg = (sumWU + utility) / (sumW + 1.0);
+    nd.weightSum = sumW + 1.0;
+    nd.visits += 1;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// One graph search from rootGame (no tree re-use).  Outputs as ko_search_run, with rootUtilitySum = utilityAvg * visits and
+// edgeUtilitySum[pos] = child's utilityAvg * edgeVisits (one rounding each); counters += visits, evaluations, terminal visits,
+// transposition hits (new edge to an existing node), catch-up visits (edge behind its child: no descent); digest (may be NULL)
+// receives a hash over every node of the graph in creation order.
+void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                         int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                         uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
+  const int P = 4 * x_size * y_size;
+  Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
+  GraphSearch S{x_size, y_size, P, p, {}, {}, {}, {}};
+  S.nodes.reserve(p->maxVisits);
+  uint64_t cnt[5] = {0, 0, 0, 0, 0};
+  ko_game* g = ko_game_create(x_size, y_size, 4);
+  ko_game* before = ko_game_create(x_size, y_size, 4);
+  std::vector<float> pol(P);
+  float wl[2];
+  for(int it = 0; it < p->maxVisits && !ko_game_finished(rootGame); it++) {
+    ko_game_copy(g, rootGame);
+    std::vector<std::pair<int, int>> path;
+    int kind = 0, target = -1;   // 1 new node, 2 new terminal child, 3 terminal revisit, 4 root evaluation, 5 catch-up, 6 transposition
+    double v = 0.0;
+    Key leafKey(0, 0), leafBias(0, 0);
+    bool haveBias = false;
+    if(S.nodes.empty()) kind = 4;
+    else if(S.nodes[0].visits >= p->maxVisits) break;
+    else {
+      int node = 0, depth = 0;
+      while(true) {
+        GNode& nd = S.nodes[node];
+        const int pla = nd.nextPla;
+        double partT[32] = {0}, partM[32] = {0};
+        for(int pos = 0; pos < P; pos++)
+          if(nd.child[pos] != -1) {
+            int cv; double cw, cu;
+            S.childStats(nd, pos, cv, cw, cu);
+            partT[pos & 31] = partT[pos & 31] + GraphSearch::childWeight(cw, nd.edgeN[pos], cv);
+            partM[pos & 31] = partM[pos & 31] + (double)nd.policy[pos];
+          }
+        const double total = butterfly(partT), mass = butterfly(partM);
+        const double parentUtility = nd.utilityAvg;
+        const double red = (depth == 0 ? p->rootFpuReductionMax : p->fpuReductionMax) * std::sqrt(mass);
+        const double fpu = pla == 2 ? parentUtility - red : parentUtility + red;
+        const double scale = p->cpuctExploration * std::sqrt(total + 0.01);
+        double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
+        float newP = -1.0f; int newPos = -1;
+        for(int pos = 0; pos < P; pos++) {
+          const float pr = nd.policy[pos];
+          if(nd.child[pos] != -1) {
+            int cv; double cw, cu;
+            S.childStats(nd, pos, cv, cw, cu);
+            const double w = GraphSearch::childWeight(cw, nd.edgeN[pos], cv);
+            const double val = (scale * (double)pr) / (1.0 + w) + (pla == 2 ? cu : -cu);
+            const int o = nd.order[pos];
+            if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
+          } else if(pr >= 0.0f) {
+            if(pr > newP) { newP = pr; newPos = pos; }
+          }
+        }
+        bool takeNew = false;
+        if(newPos >= 0) {
+          const double valNew = (scale * (double)newP) / 1.0 + (pla == 2 ? fpu : -fpu);
+          takeNew = bestPos < 0 || valNew > bestVal;
+        }
+        const int pos = takeNew ? newPos : bestPos;
+        if(pos < 0) { kind = 0; break; }
+        path.push_back({node, pos});
+        depth++;
+        if(!takeNew) {
+          const int cc = nd.child[pos];
+          if(cc <= -2) { kind = 3; v = terminalValue(-2 - cc); break; }
+          if(nd.edgeN[pos] < S.nodes[cc].visits) { kind = 5; break; }   // maybeCatchUpEdgeVisits: no descent
+          ko_game_play(g, pos);
+          node = cc;
+          continue;
+        }
+        ko_game_copy(before, g);
+        ko_game_play(g, pos);
+        if(ko_game_finished(g)) { kind = 2; v = terminalValue(ko_game_winner(g)); break; }
+        leafKey = GraphSearch::stateKey(g);
+        if(p->useGraphSearch) {
+          auto f = S.table.find(leafKey);
+          if(f != S.table.end()) { kind = 6; target = f->second; break; }
+        }
+        kind = 1;
+        // moveHistory.size() >= 2 after the move (search.cpp:740): the position before it has a last move
+        if(p->subtreeValueBiasFactor != 0.0 && ko_game_recent_move_pos(before, 0) >= 0) { haveBias = true; leafBias = S.biasKey(before, pos); }
+        break;
+      }
+    }
+    if(kind == 0) continue;
+    int newIdx = -1;
+    if(kind == 1 || kind == 4) {
+      ev.eval(g, pol.data(), wl);
+      v = (double)wl[0] - (double)wl[1];
+      newIdx = (int)S.nodes.size();
+      S.nodes.emplace_back(P);
+      GNode& nn = S.nodes.back();
+      nn.visits = 1; nn.weightSum = 1.0; nn.nnUtility = v; nn.nextPla = ko_game_next_pla(g);
+      for(int pos = 0; pos < P; pos++) nn.policy[pos] = pol[pos];
+      double utility = v;
+      if(haveBias) {
+        auto f = S.biasIndex.find(leafBias);
+        if(f == S.biasIndex.end()) { f = S.biasIndex.insert({leafBias, (int)S.bias.size()}).first; S.bias.emplace_back(); }
+        nn.biasEntry = f->second;
+        const BiasEntry& E = S.bias[nn.biasEntry];
+        if(E.weightSum > 0.001) utility = utility + (p->subtreeValueBiasFactor * E.deltaSum) / E.weightSum;   // addLeafValue :27-37
+      }
+      nn.utilityAvg = utility;
+      if(kind == 1 && p->useGraphSearch) S.table[leafKey] = newIdx;
+    }
+    for(int d = (int)path.size() - 1; d >= 0; d--) {
+      GNode& nd = S.nodes[path[d].first];
+      const int pos = path[d].second;
+      if(d + 1 == (int)path.size() && (kind == 1 || kind == 2 || kind == 6)) {
+        nd.child[pos] = kind == 1 ? newIdx : kind == 6 ? target : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
+        nd.order[pos] = (uint8_t)nd.numChildren;
+        nd.numChildren++;
+      }
+      nd.edgeN[pos] += 1;
+      S.recompute(nd);
+    }
+    cnt[0]++;
+    if(kind == 1 || kind == 4) cnt[1]++;
+    else if(kind == 2 || kind == 3) cnt[2]++;
+    else if(kind == 6) cnt[3]++;
+    else cnt[4]++;
+  }
+  ko_game_destroy(g); ko_game_destroy(before);
+  const bool have = !S.nodes.empty();
+  if(rootVisits) *rootVisits = have ? S.nodes[0].visits : 0;
+  if(rootUtilitySum) *rootUtilitySum = have ? S.nodes[0].utilityAvg * (double)S.nodes[0].visits : 0.0;
+  for(int pos = 0; pos < P; pos++) {
+    const bool ex = have && S.nodes[0].child[pos] != -1;
+    int cv = 0; double cw = 0.0, cu = 0.0;
+    if(ex) S.childStats(S.nodes[0], pos, cv, cw, cu);
+    if(edgeVisits) edgeVisits[pos] = ex ? S.nodes[0].edgeN[pos] : 0;
+    if(edgeUtilitySum) edgeUtilitySum[pos] = ex ? cu * (double)S.nodes[0].edgeN[pos] : 0.0;
+    if(policyOut) policyOut[pos] = have ? S.nodes[0].policy[pos] : 0.f;
+    if(orderOut) orderOut[pos] = ex ? S.nodes[0].order[pos] : 255;
+  }
+  if(counters) for(int i = 0; i < 5; i++) counters[i] += cnt[i];
+  if(digest) {
+    uint64_t h = 0;
+    for(size_t i = 0; i < S.nodes.size(); i++) {
+      const GNode& nd = S.nodes[i];
+      uint64_t wb, ub;
+      memcpy(&wb, &nd.weightSum, 8); memcpy(&ub, &nd.utilityAvg, 8);
+      uint64_t nh = ko_splitmix64((uint64_t)nd.visits ^ ((uint64_t)nd.numChildren << 32)) ^ ko_splitmix64(wb ^ PHI) ^ ko_splitmix64(ub + PHI);
+      for(int pos = 0; pos < P; pos++)
+        if(nd.child[pos] != -1)
+          nh ^= ko_splitmix64(((uint64_t)(uint32_t)nd.child[pos] << 32 | (uint64_t)(uint32_t)nd.edgeN[pos]) + (uint64_t)(pos + 1) * PHI + nd.order[pos]);
+      h ^= ko_splitmix64(nh + (uint64_t)(i + 1) * PHI);
+    }
+    *digest = h;
+  }
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // Persistent tree with re-use between moves (Search::makeMove keeps the chosen child's subtree): run() continues the
 // search of the current tree until the root has maxVisits visits, advance() re-roots at the child reached by movePos
 // (an unexpanded or terminal child drops the tree).

@@ -627,6 +627,93 @@ def test_search_hash_evaluator_bit_exact(ctx, oracle, W, H, K, G, V):
     s.close()
 
 
+def _advance_device_like_oracle(oracle, s, W, H, K, seed, plies):
+    """Plays game g `plies[g]` counter-RNG plies on the oracle and replays the same moves on the device search's games."""
+    G = len(plies)
+    hist = [[] for _ in range(G)]
+    ogames = []
+    for g in range(G):
+        og = oracle.Game(W, H, K)
+        for _ in range(int(plies[g])):
+            if og.finished():
+                break
+            mv = og.choose(seed, g)
+            og.play(mv)
+            hist[g].append(mv)
+        ogames.append(og)
+    for t in range(int(max(plies))):
+        s.games.step(np.array([hist[g][t] if t < len(hist[g]) else -1 for g in range(G)], np.int16))
+    return ogames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,K,G,V,graph,factor,exponent", [
+    (5, 5, 4, 160, 200, True, 0.0, 0.5),     # graph search alone
+    (5, 5, 4, 160, 200, True, 0.30, 0.8),    # selfplay1.cfg:180-183: graph search + subtree value bias, exponent via detPow
+    (5, 5, 4, 96, 160, False, 0.45, 0.5),    # bias without transpositions, sqrt weight (SearchParams() exponent)
+    (6, 6, 4, 48, 120, True, 0.30, 1.0),
+    (4, 5, 3, 40, 96, True, 0.30, 0.8)])
+def test_search_graph_and_value_bias_bit_exact(ctx, oracle, W, H, K, G, V, graph, factor, exponent):
+    """Graph search (transposition table, edge visits, catch-up) and subtree value bias with the integer-hash evaluator:
+    every node of every game's graph (visits, weightSum, utilityAvg bit patterns, edges) equals the oracle's -- compared
+    through the whole-graph digest and, at the root, field by field."""
+    from katacoffee_b200 import backend, capi
+    seed = 91
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, useGraphSearch=graph, subtreeValueBiasFactor=factor,
+                       subtreeValueBiasWeightExponent=exponent)
+    s.reset(seed=seed)
+    plies = np.array([4 + g % 12 for g in range(G)])   # mid-game positions: transpositions need a few stones on the board
+    ogames = _advance_device_like_oracle(oracle, s, W, H, K, seed, plies)
+    s.runVisits()
+    got = s.readRoot()
+    dig = s.treeDigest()
+    cnt = np.zeros(5, np.uint64)
+    for g in range(G):
+        ref = oracle.search_run_graph(ogames[g], V, graph=graph, bias_factor=factor, bias_exponent=exponent)
+        cnt += ref["counters"]
+        assert got["rootVisits"][g] == ref["rootVisits"], (g, got["rootVisits"][g], ref["rootVisits"])
+        assert (got["edgeVisits"][g] == ref["edgeVisits"]).all(), g
+        assert (got["order"][g] == ref["order"]).all(), g
+        assert (got["policy"][g] == ref["policy"]).all(), g
+        assert got["rootUtilitySum"][g] == ref["rootUtilitySum"], g
+        assert (got["edgeUtilitySum"][g] == ref["edgeUtilitySum"]).all(), g
+        assert int(dig[g]) == ref["digest"], g
+    if graph and (W, H) == (5, 5):
+        assert cnt[3] > 0 and cnt[4] > 0, cnt    # the 5x5 cases do exercise transpositions and catch-up visits
+    s.close()
+
+
+@pytest.mark.gpu
+def test_search_graph_selfplay_counters_match_oracle(ctx, oracle):
+    """Self-play with graph search + subtree value bias: moves, results and the visit / evaluation / transposition /
+    catch-up counters equal the oracle's, move after move to the end of the games."""
+    from katacoffee_b200 import backend, capi
+    W = H = 5
+    G, V, seed, T = 64, 64, 13, 4
+    s = backend.Search(ctx, None, G, W, H, 4, maxVisits=V, temperaturePlies=T, useGraphSearch=True, subtreeValueBiasFactor=0.3,
+                       subtreeValueBiasWeightExponent=0.8)
+    s.reset(seed=seed, firstGameId=500)
+    ogames = [oracle.Game(W, H, 4) for _ in range(G)]
+    stats = capi.SearchStats()
+    ocnt = np.zeros(5, np.uint64)
+    for ply in range(26):
+        _, chosen, _ = s.play(1, stats)
+        for g in range(G):
+            og = ogames[g]
+            if og.finished():
+                assert chosen[g] == -1
+                continue
+            r = oracle.search_run_graph(og, V, graph=True, bias_factor=0.3, bias_exponent=0.8)
+            ocnt += r["counters"]
+            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 500 + g)
+            assert chosen[g] == mv, (ply, g, chosen[g], mv)
+            og.play(mv)
+    assert all(og.finished() for og in ogames)
+    assert (stats.visits, stats.netEvals, stats.terminalVisits, stats.transpositionHits, stats.catchUpVisits) == tuple(int(x) for x in ocnt)
+    assert stats.netEvals + stats.terminalVisits + stats.transpositionHits + stats.catchUpVisits == stats.visits
+    s.close()
+
+
 @pytest.mark.gpu
 def test_search_selfplay_moves_match_oracle(ctx, oracle):
     """search -> choose (visit-proportional for the first plies, then most visited) -> play, repeated to the end of the

@@ -51,3 +51,69 @@ def test_oracle_search_and_training_rows(oracle, W, H, K):
         assert rows["valueTargetsNCHW"][0, 4].max() >= K
     else:
         assert rows["valueTargetsNCHW"][0, 4].max() < K
+
+
+def _midgame(oracle, W, H, K, seed, gid, plies):
+    og = oracle.Game(W, H, K)
+    for _ in range(plies):
+        if og.finished():
+            break
+        og.play(og.choose(seed, gid))
+    return og
+
+
+def test_oracle_graph_search_invariants(oracle):
+    """Graph mode of the oracle search: without transposition table and bias it visits exactly what the tree search visits
+    (same selection rule on the same statistics, utilities of the hash evaluator are dyadic so even the sums agree);
+    with the table, every visit is an evaluation, a terminal visit, a transposition hit or a catch-up visit."""
+    V = 300
+    hits = 0
+    for gid in range(12):
+        og = _midgame(oracle, 5, 5, 4, 17, gid, 5 + gid % 8)
+        if og.finished():
+            continue
+        a = oracle.search_run(og, V)
+        b = oracle.search_run_graph(og, V, graph=False)
+        assert (a["edgeVisits"] == b["edgeVisits"]).all() and (a["order"] == b["order"]).all()
+        assert abs(a["rootUtilitySum"] - b["rootUtilitySum"]) < 1e-9
+        c = oracle.search_run_graph(og, V, graph=True)
+        assert c["rootVisits"] == V and int(c["counters"][0]) == V == int(c["counters"][1:].sum())
+        assert c["edgeVisits"].sum() == V - 1
+        hits += int(c["counters"][3])
+        d = oracle.search_run_graph(og, V, graph=True, bias_factor=0.3, bias_exponent=0.8)
+        assert d["rootVisits"] == V and abs(d["rootUtilitySum"]) <= V
+        assert d["digest"] != c["digest"]
+    assert hits > 0
+
+
+def test_oracle_det_pow_close_to_libm(oracle):
+    """The bias weight W^exponent uses a pow built from IEEE basic operations (so the device can reproduce its bits);
+    indirectly: exponent 0.5 through sqrt and through exp(0.5 log) give searches that agree to rounding noise."""
+    og = _midgame(oracle, 5, 5, 4, 3, 1, 6)
+    a = oracle.search_run_graph(og, 200, graph=True, bias_factor=0.3, bias_exponent=0.5)
+    b = oracle.search_run_graph(og, 200, graph=True, bias_factor=0.3, bias_exponent=0.5000000001)
+    assert abs(a["rootUtilitySum"] - b["rootUtilitySum"]) < 1e-6 * 200
+
+
+def test_literal_graph_hash_is_path_dependent(oracle):
+    """GraphHash::getGraphHash as written (graphhash.cpp:14-29) chains the previous hash after every move, so two move orders
+    reaching the same stones / player / last move get different hashes -- why the search keys on the state instead."""
+    import ctypes as C
+    def chain(moves):
+        og = oracle.Game(5, 5, 4)
+        h = np.zeros(2, np.uint64)
+        for mv in moves:
+            nh = np.zeros(2, np.uint64)
+            oracle.lib().ko_graph_hash(h.ctypes.data_as(C.c_void_p), og._g, og.next_pla(), nh.ctypes.data_as(C.c_void_p))
+            h = nh
+            assert og.play(mv)
+        nh = np.zeros(2, np.uint64)
+        oracle.lib().ko_graph_hash(h.ctypes.data_as(C.c_void_p), og._g, og.next_pla(), nh.ctypes.data_as(C.c_void_p))
+        return og, nh
+    HW = 25
+    # black a, white b, black c, white d  vs  black c, white b, black a, white d: all on row 0 with direction W-E (dir 1)
+    p = lambda x, y, d: d * HW + y * 5 + x
+    g1, h1 = chain([p(0, 0, 1), p(1, 0, 1), p(2, 0, 1), p(4, 0, 1)])
+    g2, h2 = chain([p(2, 0, 1), p(1, 0, 1), p(0, 0, 1), p(4, 0, 1)])
+    assert tuple(g1.sit_hash()) == tuple(g2.sit_hash())
+    assert tuple(h1) != tuple(h2)
