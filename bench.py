@@ -288,17 +288,16 @@ def main():
     # ---------------- self-play arm (BASELINE.json: "selfplay moves/s", 800 visits/move) ----------------
     # the same G games under the batched device tree search: per iteration every game descends to one leaf and the G
     # leaves are one batch through the hot path; a move = SELFPLAY_VISITS iterations
-    selfplay = None
-    if not args.no_selfplay:
-        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True, reuseTree=True)
+    def selfplay_arm(label, **search_kw):
+        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True, **search_kw)
         search.reset(seed=SEED, firstGameId=shard.first_game_id(rank))
         # steady-state mix of a self-play run: game g starts the timed move after (g mod STAGGER) random-legal plies, as
         # games that were refilled at different times do (movePos -2 = the counter-RNG move, -1 = stay)
         lane = np.arange(G)
         for t in range(SELFPLAY_STAGGER):
             search.games.step(np.where(lane % SELFPLAY_STAGGER > t, -2, -1).astype(np.int16))
-        # one untimed move first: it builds the trees whose chosen subtrees the timed move re-uses, as every move of a
-        # running self-play does (Search::makeMove)
+        # one untimed move first: with tree re-use it builds the trees whose chosen subtrees the timed move re-uses, as
+        # every move of a running self-play does (Search::makeMove)
         search.play(1)
         handle.trunkTime()
         barrier()
@@ -306,14 +305,24 @@ def main():
         barrier()
         sp_ms_max = shard.max_over_ranks(sp_ms, "cuda")
         sp = shard.reduce_stats([sp_stats.movesPlayed, sp_stats.visits, sp_stats.netEvals, sp_stats.terminalVisits, sp_stats.gamesFinished,
-                                 sp_stats.batchRows], "cuda")
-        selfplay = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
-                    "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
-                    "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
-                    "ms_per_move_batch": sp_ms_max / args.selfplay_moves, "games_finished": int(sp[4]),
-                    "search": "lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
-                    "kernel_launches": int(search.launchCount())}
+                                 sp_stats.batchRows, sp_stats.transpositionHits, sp_stats.catchUpVisits], "cuda")
+        out = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
+               "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
+               "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
+               "transposition_fraction_of_visits": (sp[6] + sp[7]) / max(sp[1], 1),
+               "ms_per_move_batch": sp_ms_max / args.selfplay_moves, "games_finished": int(sp[4]),
+               "search": label, "kernel_launches": int(search.launchCount())}
         search.close()
+        return out
+
+    selfplay = selfplay_graph = None
+    if not args.no_selfplay:
+        # BASELINE.json configs[3]: graph search + subtree value bias (cpp/configs/training/selfplay1.cfg:180-183)
+        selfplay_graph = selfplay_arm("lock-step PUCT per game, useGraphSearch + subtreeValueBiasFactor 0.30 / WeightExponent 0.8 (selfplay1.cfg:180-183), "
+                                      "valueWeightExponent 0, visit-proportional move choice, no tree re-use",
+                                      useGraphSearch=True, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightExponent=0.8)
+        selfplay = selfplay_arm("lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
+                                reuseTree=True)
 
     if rank == 0:
         flops = modeldesc.flops_per_eval(NET, hw)
@@ -337,6 +346,7 @@ def main():
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
                                         "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games_multi") or load_traffic("prof_games")},
             "selfplay": selfplay,
+            "selfplay_graph": selfplay_graph,
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
                       "black_wins": int(counters[3]), "white_wins": int(counters[4]), "draws": int(counters[5])},
         }

@@ -151,7 +151,7 @@ __device__ __forceinline__ double warpSumD(double v) {   // butterfly: every lan
 // select: one warp per game descends from the root to a leaf
 // ---------------------------------------------------------------------------------------------
 template <class D>
-__global__ void __launch_bounds__(128) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+__global__ void __launch_bounds__(128, 8) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
   const D dm(g);
   using BB = typename D::BB;
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -377,7 +377,7 @@ __device__ __forceinline__ void childStats(const SearchCfg& c, uint8_t* treeBase
 __device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
 
 template <class D>
-__global__ void __launch_bounds__(128) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+__global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
   const D dm(g);
   using BB = typename D::BB;
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -562,7 +562,7 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, const TreeMem&
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
+__global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(gi >= c.numGames) return;
   const int kind = t.leafKind[gi];

@@ -8,7 +8,9 @@ ctx = backend.createComputeContext(0)
 G, V = 18944, int(sys.argv[1]) if len(sys.argv) > 1 else 24
 lm = backend.LoadedModel(ctx, modeldesc.Model("b10c128", seed=1))
 h = backend.createComputeHandle(ctx, lm, G, 5, 5)
-s = backend.Search(ctx, h, G, 5, 5, 4, maxVisits=V, temperaturePlies=30, autoRefill=True)
+graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
+kw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8) if graph else {}
+s = backend.Search(ctx, h, G, 5, 5, 4, maxVisits=V, temperaturePlies=30, autoRefill=True, **kw)
 s.reset(seed=1)
 lane = np.arange(G)
 for t in range(20):
