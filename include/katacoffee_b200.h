@@ -107,6 +107,24 @@ int kc_model_create(kc_ctx* ctx, const kc_model_desc* desc, kc_model** out);
 int kc_model_destroy(kc_model* model);
 
 /* ---------------------------------------------------------------------------------------------
+ * Model files.  Replaces ModelDesc::loadFromFileMaybeGZipped (cpp/neuralnet/desc.cpp:1146-1204) and
+ * the ModelDesc / layer parsers behind it (desc.cpp:27-92 readFloats with "@BIN@" blocks, :107-155 conv, :175-219 batch norm,
+ * :239-258 activation, :274-340 matmul / matbias, :354-456 blocks, :562-696 trunk, :751-925 heads, :977-1094 model) for Coffee
+ * models: version 1, 15 + 1 input channels, policy 4 channels (+ the format's gpoolToPassMul, parsed and ignored), value 2,
+ * misc 2, ownership 1.  File kinds by suffix: .txt, .bin, .txt.gz, .bin.gz, .gz (binary first, then text).
+ * expectedSha256 (NULL or "" = do not check) is compared with the SHA-256 of the file as stored (cpp/core/fileutils.cpp:113-140).
+ * No GPU is needed.  The returned description stays valid until kc_modelfile_free; kc_model_create copies what it needs.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kc_modelfile kc_modelfile;
+int kc_modelfile_load(const char* path, const char* expectedSha256, kc_modelfile** out);
+int kc_modelfile_free(kc_modelfile* f);
+const kc_model_desc* kc_modelfile_desc(const kc_modelfile* f);
+const char* kc_modelfile_name(const kc_modelfile* f);
+const char* kc_modelfile_sha256(const kc_modelfile* f);
+/* Writes `desc` in the same format (suffix .txt, .bin, .txt.gz or .bin.gz); activations are written with their kind. */
+int kc_modelfile_write(const kc_model_desc* desc, const char* name, const char* path);
+
+/* ---------------------------------------------------------------------------------------------
  * Compute handle.  Replaces createComputeHandle / createInputBuffers / getOutput
  * (nninterface.h:77-117).
  * ------------------------------------------------------------------------------------------- */

@@ -6,6 +6,7 @@ reference's own tests/testnn.cpp; every call goes through the C ABI (capi) and r
 (the StringError analogue) on failure.  `Games` wraps the batched rules/features entry points.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -39,6 +40,37 @@ class LoadedModel:
         if self._p:
             lib().kc_model_destroy(self._p)
             self._p = C.c_void_p()
+
+
+class ModelFile:
+    """A parsed model file (NeuralNet::loadModelFile's parsing half; cpp/neuralnet/desc.cpp).  No GPU needed.
+    `.desc` is a capi.ModelDesc whose pointers stay valid while this object lives."""
+
+    def __init__(self, path, expectedSha256=""):
+        self._p = C.c_void_p()
+        check(lib().kc_modelfile_load(os.fsencode(path), (expectedSha256 or "").encode(), C.byref(self._p)))
+        self.desc = C.cast(lib().kc_modelfile_desc(self._p), C.POINTER(capi.ModelDesc)).contents
+        self.name = lib().kc_modelfile_name(self._p).decode()
+        self.sha256 = lib().kc_modelfile_sha256(self._p).decode()
+
+    def close(self):
+        if self._p:
+            lib().kc_modelfile_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+
+def writeModelFile(model, path, name=None):
+    """Writes a modeldesc.Model (or anything with a .desc) in the reference's model format (.txt/.bin[.gz])."""
+    check(lib().kc_modelfile_write(C.byref(model.desc), (name or getattr(model, "name", "model")).encode(), os.fsencode(path)))
+
+
+def loadModelFile(ctx, path, expectedSha256=""):
+    """NeuralNet::loadModelFile (cpp/neuralnet/nninterface.h:42): parse the file and build the device model."""
+    mf = ModelFile(path, expectedSha256)
+    return LoadedModel(ctx, mf)
 
 
 class ComputeHandle:

@@ -107,6 +107,12 @@ PROTOTYPES = {
     "kc_games_run_timed": (C.c_int, [vp, vp, C.c_int, C.c_size_t, C.POINTER(Stats), C.POINTER(C.c_float)]),
     "kc_games_launch_count": (C.c_int64, [vp]),
     "kc_games_last_kernel_ms": (C.c_float, [vp]),
+    "kc_modelfile_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(vp)]),
+    "kc_modelfile_free": (C.c_int, [vp]),
+    "kc_modelfile_desc": (vp, [vp]),
+    "kc_modelfile_name": (C.c_char_p, [vp]),
+    "kc_modelfile_sha256": (C.c_char_p, [vp]),
+    "kc_modelfile_write": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "kc_search_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SearchParams), C.POINTER(vp)]),
     "kc_search_destroy": (C.c_int, [vp]),
     "kc_search_games": (vp, [vp]),

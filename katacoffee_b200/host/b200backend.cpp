@@ -58,6 +58,17 @@ struct LoadedModel {
     return k;
   }
 
+  kc_modelfile* file = nullptr;   // standalone build: the parsed model file owning the weights `pod` points to
+  // standalone loadModelFile: the file parser lives behind the C ABI (kc_modelfile_load); only the scalar fields of ModelDesc are filled
+  explicit LoadedModel(kc_modelfile* f) : file(f) {
+    pod = *kc_modelfile_desc(f);
+    modelDesc.name = kc_modelfile_name(f);
+    modelDesc.version = pod.version; modelDesc.numInputChannels = pod.numInputChannels; modelDesc.numInputGlobalChannels = pod.numInputGlobalChannels;
+  }
+  ~LoadedModel() { if(file) kc_modelfile_free(file); }
+  LoadedModel(const LoadedModel&) = delete;
+  LoadedModel& operator=(const LoadedModel&) = delete;
+
   explicit LoadedModel(ModelDesc&& d) : modelDesc(std::move(d)) {
     const TrunkDesc& t = modelDesc.trunk;
     for(const auto& b : t.blocks) {
@@ -131,8 +142,10 @@ LoadedModel* loadModelFile(const string& file, const string& expectedSha256) {
   ModelDesc::loadFromFileMaybeGZipped(file, desc, expectedSha256);   // the reference's own parser (desc.cpp:1146-1204)
   return new LoadedModel(std::move(desc));
 #else
-  (void)file; (void)expectedSha256;
-  throw StringError("B200 backend: model files are parsed by the reference's desc.cpp; the standalone build takes a ModelDesc (loadModelFromDesc)");
+  // standalone: the Coffee model-file parser behind the C ABI (csrc/modelfile.cpp restates desc.cpp's format)
+  kc_modelfile* f = nullptr;
+  kcCheck(kc_modelfile_load(file.c_str(), expectedSha256.c_str(), &f), "loadModelFile");
+  return new LoadedModel(f);
 #endif
 }
 void freeLoadedModel(LoadedModel* m) { delete m; }

@@ -137,6 +137,40 @@ int main() {
   bool threw = false;
   try { NeuralNet::loadModelFile("nonexistent.bin.gz", ""); } catch(const StringError&) { threw = true; }
   REQUIRE(threw);
+  {
+    // NeuralNet::loadModelFile: write the model in the reference's file format, load it back through the backend API and
+    // check that the loaded model evaluates bit-identically to the in-memory one
+    const char* path = "/tmp/kc_cpp_test_model.bin.gz";
+    REQUIRE(kc_modelfile_write(static_cast<const kc_model_desc*>(NeuralNet::getB200ModelDescPOD(model)), "cpp-test-file", path) == 0);
+    LoadedModel* fromFile = NeuralNet::loadModelFile(path, "");
+    REQUIRE(NeuralNet::getModelName(fromFile) == "cpp-test-file" && NeuralNet::getModelVersion(fromFile) == 1);
+    std::vector<float> pols[2];
+    LoadedModel* ms[2] = {model, fromFile};
+    for(int k = 0; k < 2; k++) {
+      ComputeContext* ctx = NeuralNet::createComputeContext({0}, nullptr, W, H, "", "", false, enabled_t::True, enabled_t::Auto, ms[k]);
+      ComputeHandle* h = NeuralNet::createComputeHandle(ctx, ms[k], nullptr, 64, true, false, 0, 0);
+      InputBuffers* ib = NeuralNet::createInputBuffers(ms[k], 64, W, H);
+      std::vector<NNResultBuf> bufs(N); std::vector<NNResultBuf*> bufPtrs(N);
+      std::vector<NNOutput> outs(N); std::vector<NNOutput*> outPtrs(N);
+      for(int i = 0; i < N; i++) {
+        bufs[i].rowSpatial = spatial[i].data(); bufs[i].rowGlobal = global[i].data();
+        bufs[i].rowSpatialSize = 15 * HW; bufs[i].rowGlobalSize = 1; bufs[i].symmetry = i % 8;
+        bufPtrs[i] = &bufs[i]; outPtrs[i] = &outs[i];
+      }
+      NeuralNet::getOutput(h, ib, N, bufPtrs.data(), outPtrs);
+      for(int i = 0; i < N; i++) { pols[k].insert(pols[k].end(), outs[i].policyProbs, outs[i].policyProbs + 4 * HW); pols[k].push_back(outs[i].whiteWinProb); }
+      NeuralNet::freeInputBuffers(ib); NeuralNet::freeComputeHandle(h); NeuralNet::freeComputeContext(ctx);
+    }
+    REQUIRE(pols[0].size() == pols[1].size() && memcmp(pols[0].data(), pols[1].data(), pols[0].size() * 4) == 0);
+    std::string sha;
+    { kc_modelfile* f = nullptr; REQUIRE(kc_modelfile_load(path, nullptr, &f) == 0); sha = kc_modelfile_sha256(f); kc_modelfile_free(f); }
+    NeuralNet::freeLoadedModel(NeuralNet::loadModelFile(path, sha));   // the right hash passes
+    threw = false;
+    try { NeuralNet::loadModelFile(path, std::string(64, 'a')); } catch(const StringError&) { threw = true; }
+    REQUIRE(threw);
+    NeuralNet::freeLoadedModel(fromFile);
+    remove(path);
+  }
   NeuralNet::freeLoadedModel(model);
   NeuralNet::globalCleanup();
   printf("b200backend ok\n");

@@ -487,6 +487,34 @@ def test_bf16_full_batch_and_odd_sizes(ctx, oracle):
     h.close(); lm.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("suffix", [".bin.gz", ".txt"])
+def test_model_file_evaluates_like_the_model_in_memory(ctx, tmp_path, suffix):
+    """NeuralNet::loadModelFile path: a net written in the reference's model format and loaded back gives bit-identical
+    outputs on both device paths."""
+    from katacoffee_b200 import backend, modeldesc
+    G, W, H = 300, 5, 5
+    model = modeldesc.Model("b2c32", seed=8)
+    path = str(tmp_path / ("net" + suffix))
+    backend.writeModelFile(model, path)
+    lm0 = backend.LoadedModel(ctx, model)
+    lm1 = backend.loadModelFile(ctx, path)
+    games = backend.Games(ctx, G, W, H, 4)
+    games.reset(seed=3)
+    for _ in range(9):
+        games.step()
+    for fp32 in (True, False):
+        outs = []
+        for lm in (lm0, lm1):
+            h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=fp32)
+            games.eval(h)
+            outs.append(h.readOutputs(G))
+            h.close()
+        for a, b in zip(outs[0], outs[1]):
+            assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+    games.close(); lm0.close(); lm1.close()
+
+
 def test_cpp_nninterface_backend(ctx):
     """The C++ drop-in (host/b200backend.cpp: every NeuralNet:: function of nninterface.h) driven the way
     NNEvaluator::serve drives a backend; its outputs equal direct C-ABI calls bit for bit."""
