@@ -125,6 +125,19 @@ const char* kc_modelfile_sha256(const kc_modelfile* f);
 int kc_modelfile_write(const kc_model_desc* desc, const char* name, const char* path);
 
 /* ---------------------------------------------------------------------------------------------
+ * Custom Coffee SGF (README.md:33-35, cpp/dataio/sgf.cpp:42-154, 1526-1548): a move is B[xyd] / W[xyd],
+ * x and y the column / row letters (a..z, A..Z) and d in a..d the direction | - \ / (0..3); header
+ * "(;FF[4]GM[Coffee]SZ[n]WLL[k]PB[..]PW[..]RE[B+|W+|0]", AB / AW placements = the starting position.  Moves are policy indices
+ * dir*H*W + y*W + x (-1 = no move), players 1 black / 2 white, winner -1 unfinished / 0 draw / 1 / 2.  Host-only.
+ * kc_sgf_write: *outLen receives the length; fails if outCap is too small.  kc_sgf_parse follows the main line; initialStones
+ * [H*W] (may be NULL); *numMoves is the number of moves in the file even if it exceeds maxMoves.
+ * ------------------------------------------------------------------------------------------- */
+int kc_sgf_write(int xSize, int ySize, int winLen, const char* blackName, const char* whiteName, const int8_t* initialStones, int numMoves,
+                 const int16_t* movePos, const int8_t* movePla, int winner, char* out, size_t outCap, size_t* outLen);
+int kc_sgf_parse(const char* sgf, int* xSize, int* ySize, int* winLen, int8_t* initialStones, int maxMoves, int16_t* movePos,
+                 int8_t* movePla, int* numMoves, int* winner);
+
+/* ---------------------------------------------------------------------------------------------
  * Compute handle.  Replaces createComputeHandle / createInputBuffers / getOutput
  * (nninterface.h:77-117).
  * ------------------------------------------------------------------------------------------- */

@@ -73,6 +73,29 @@ def loadModelFile(ctx, path, expectedSha256=""):
     return LoadedModel(ctx, mf)
 
 
+def writeSgf(xSize, ySize, winLen, moves, players=None, winner=-1, blackName="B200", whiteName="B200", initialStones=None):
+    """Custom Coffee SGF text of a game (README.md:33-35): moves are policy indices, players default to black first."""
+    mv = np.ascontiguousarray(moves, np.int16)
+    pl = np.ascontiguousarray(players if players is not None else [1 + (i % 2) for i in range(len(mv))], np.int8)
+    st = None if initialStones is None else np.ascontiguousarray(initialStones, np.int8).reshape(-1)
+    cap = 256 + 8 * len(mv) + 4 * xSize * ySize + len(blackName) + len(whiteName)
+    buf = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    check(lib().kc_sgf_write(xSize, ySize, winLen, blackName.encode(), whiteName.encode(), None if st is None else ptr(st), len(mv),
+                             ptr(mv) if len(mv) else None, ptr(pl) if len(mv) else None, winner, buf, cap, C.byref(n)))
+    return buf.value.decode()
+
+
+def parseSgf(text, maxMoves=400):
+    """dict(xSize, ySize, winLen, initialStones [H, W], moves, players, winner) of the main line of a Coffee SGF."""
+    x, y, k, n, w = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    stones = np.zeros(100, np.int8); mv = np.zeros(maxMoves, np.int16); pl = np.zeros(maxMoves, np.int8)
+    check(lib().kc_sgf_parse(text.encode(), C.byref(x), C.byref(y), C.byref(k), ptr(stones), maxMoves, ptr(mv), ptr(pl), C.byref(n), C.byref(w)))
+    m = min(n.value, maxMoves)
+    return dict(xSize=x.value, ySize=y.value, winLen=k.value, initialStones=stones[:x.value * y.value].reshape(y.value, x.value).copy(),
+                moves=mv[:m].copy(), players=pl[:m].copy(), winner=w.value, numMoves=n.value)
+
+
 class ComputeHandle:
     def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False):
         self.ctx, self.loadedModel = ctx, loadedModel
