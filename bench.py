@@ -188,10 +188,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+CONFIGS = {
+    # --config: net, board, games per GPU, self-play stagger, rules+features bytes per game-step, BASELINE.json config
+    "5x5": ("b10c128", 5, 148 * 128, 20, 1572, "configs[2] net on configs[1]-style concurrent random-legal games"),
+    # 6x6 k=4 with b15c192: 3 boards per CTA work item -> 148 * 3 * 32 games, no tail
+    "6x6": ("b15c192", 6, 148 * 3 * 32, 28, 2236, "configs[4]: non-default board size and the larger trunk"),
+}
+
+
+def select_config(name):
+    global NET, W, H, GAMES_PER_GPU, SELFPLAY_STAGGER, BYTES_PER_STEP_FP32, CONFIG_NOTE
+    NET, W, GAMES_PER_GPU, SELFPLAY_STAGGER, BYTES_PER_STEP_FP32, CONFIG_NOTE = CONFIGS[name]
+    H = W
+
+
+CONFIG_NOTE = CONFIGS["5x5"][5]
+
+
 def workload_config(games_per_gpu):
-    return {"workload": f"5x5 k=4 Coffee leaf evaluation: rules step + V1 planes + {NET} forward per ply "
-                        "(BASELINE.json configs[2] net on configs[1]-style concurrent random-legal games)",
-            "net": NET, "board": "5x5", "win_len": WINLEN, "games_per_gpu": games_per_gpu, "seed": SEED,
+    return {"workload": f"{W}x{H} k=4 Coffee leaf evaluation: rules step + V1 planes + {NET} forward per ply "
+                        f"(BASELINE.json {CONFIG_NOTE})",
+            "net": NET, "board": f"{W}x{H}", "win_len": WINLEN, "games_per_gpu": games_per_gpu, "seed": SEED,
             "weights": "random-init (modeldesc rms-calibrated)", "l2": f"{L2_FLUSH_BYTES >> 20} MiB scratch overwritten between timed steps"}
 
 
@@ -201,12 +218,15 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--config", default="5x5", choices=sorted(CONFIGS), help="5x5: b10c128 on 5x5 k=4 (the headline metric); 6x6: b15c192 on 6x6 k=4 (BASELINE configs[4])")
+    ap.add_argument("--games", type=int, default=0, help="games per GPU (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
     ap.add_argument("--selfplay-moves", type=int, default=1, help="moves per game timed in the self-play arm")
     args = ap.parse_args()
+    select_config(args.config)
+    args.games = args.games or GAMES_PER_GPU
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
@@ -338,13 +358,13 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "trunk_kernel (tcgen05 whole-net forward)", "bound": "tensor", "achieved": achieved,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-                         "traffic": load_traffic("prof_trunk"), "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "traffic": load_traffic("prof_trunk") if args.config == "5x5" else None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
             "roofline_rules_features": {"kernel": "games_multi_kernel (rules step + fp32 NCHW planes, 8 plies per launch, 4-slot plane ring) at 65536 games",
                                         "bound": "hbm", "plies_per_launch": 8,
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
-                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": load_traffic("prof_games_multi") or load_traffic("prof_games")},
+                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": (load_traffic("prof_games_multi") or load_traffic("prof_games")) if args.config == "5x5" else None},
             "selfplay": selfplay,
             "selfplay_graph": selfplay_graph,
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
