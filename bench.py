@@ -339,8 +339,8 @@ def main():
     if not args.no_selfplay:
         # BASELINE.json configs[3]: graph search + subtree value bias (cpp/configs/training/selfplay1.cfg:180-183)
         selfplay_graph = selfplay_arm("lock-step PUCT per game, useGraphSearch + subtreeValueBiasFactor 0.30 / WeightExponent 0.8 (selfplay1.cfg:180-183), "
-                                      "valueWeightExponent 0, visit-proportional move choice, no tree re-use",
-                                      useGraphSearch=True, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightExponent=0.8)
+                                      "subtreeValueBiasFreeProp 0.8, valueWeightExponent 0, visit-proportional move choice, tree re-use",
+                                      useGraphSearch=True, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightExponent=0.8, reuseTree=True)
         selfplay = selfplay_arm("lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
                                 reuseTree=True)
 

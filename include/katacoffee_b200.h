@@ -271,12 +271,14 @@ typedef struct {
   int32_t reuseTree;            /* keep the subtree of the move played for the next search (Search::makeMove); its visits count
                                    towards maxVisits, so later searches need fewer evaluations */
   int32_t useGraphSearch;       /* SearchParams::useGraphSearch: positions with equal stones, player to move and last move share one
-                                   node (cpp/search/search.cpp:704-757); not together with reuseTree */
+                                   node (cpp/search/search.cpp:704-757) */
   double cpuctExploration;      /* SearchParams::cpuctExploration (1.0) */
   double fpuReductionMax;       /* SearchParams::fpuReductionMax (0.2) */
   double rootFpuReductionMax;   /* SearchParams::rootFpuReductionMax (0.2) */
   double subtreeValueBiasFactor;          /* SearchParams::subtreeValueBiasFactor (0 = off; selfplay1.cfg:180 uses 0.30) */
   double subtreeValueBiasWeightExponent;  /* SearchParams::subtreeValueBiasWeightExponent (0.5 default, selfplay1.cfg:181 0.8) */
+  double subtreeValueBiasFreeProp;        /* SearchParams::subtreeValueBiasFreeProp (0.8): share of a dropped node's contribution
+                                             given back to its entry when the tree is re-used */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

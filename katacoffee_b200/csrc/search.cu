@@ -54,7 +54,7 @@ struct SearchCfg {
   int polOff;        // byte offset of the per-move arrays inside a node
   int tableCap;      // graph mode: slots of the per-game transposition and bias tables (power of two, >= 2 * maxNodes)
   double cpuct, fpuRed, rootFpuRed;
-  double biasFactor, biasExp;   // SearchParams::subtreeValueBiasFactor / subtreeValueBiasWeightExponent
+  double biasFactor, biasExp, biasFreeProp;   // SearchParams::subtreeValueBiasFactor / WeightExponent / FreeProp
   uint64_t seed;
 };
 
@@ -82,6 +82,9 @@ struct TreeMem {
   uint64_t* leafKey;      // [G][2] transposition key of a new node
   uint64_t* leafBiasKey;  // [G][2] bias key of a new node (key0 == 0: none)
   int* leafTarget;        // [G] existing node a new edge transposes to
+  // graph mode with tree re-use: re-rooting rebuilds the tables into a second set, then the two swap (like nodes / nodesAlt)
+  uint64_t* tblKeysAlt; int* tblValsAlt; uint64_t* biasKeysAlt; double* biasValsAlt;
+  int* remap;             // [G][maxNodes] old node index -> new index (-1: dropped)
 };
 constexpr int NUM_STATS = 16;
 
@@ -105,7 +108,8 @@ struct TrainMem {
 // node layout, tree mode:  header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 |
 //                           policy[P] f32 | child[P] i32 | edgeN[P] i32 | order[P] u8            (polOff = 32 + 8 P)
 //              graph mode: header { int visits; int numChildren; int nextPla; int biasEntry; double weightSum, utilityAvg,
-//                           nnUtility, lastBiasDeltaSum, lastBiasWeight, pad } | policy | child | edgeN | order   (polOff = 64)
+//                           nnUtility, lastBiasDeltaSum, lastBiasWeight; int depth (stones on the board), pad;
+//                           uint64 key[2] (transposition key) } | policy | child | edgeN | order          (polOff = 80)
 struct NodeRef {
   uint8_t* base; int P; int polOff;
   __device__ __forceinline__ int& N() const { return *reinterpret_cast<int*>(base); }
@@ -124,6 +128,8 @@ struct NodeRef {
   __device__ __forceinline__ double& nnUtility() const { return *reinterpret_cast<double*>(base + 32); }
   __device__ __forceinline__ double& lastDelta() const { return *reinterpret_cast<double*>(base + 40); }
   __device__ __forceinline__ double& lastWeight() const { return *reinterpret_cast<double*>(base + 48); }
+  __device__ __forceinline__ int& depth() const { return *reinterpret_cast<int*>(base + 56); }
+  __device__ __forceinline__ uint64_t* key() const { return reinterpret_cast<uint64_t*>(base + 64); }
 };
 // child codes: -1 none, >= 0 node index, -2 terminal draw, -3 terminal black win, -4 terminal white win
 __device__ __forceinline__ double terminalValue(int winner) { return winner == 2 ? 1.0 : winner == 1 ? -1.0 : 0.0; }
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
   if(lane == 0) {
     if(kind != 0) *t.active = 1;
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
-    t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
+    t.leafNextPla[gi] = ((flagsOf(s.misc) >> 3) & 3) | (numTurnsOf(s.misc) << 8);   // + the position's depth (stones on the board)
     t.leafKey[2 * (size_t)gi] = key0; t.leafKey[2 * (size_t)gi + 1] = key1;
     t.leafBiasKey[2 * (size_t)gi] = bk0; t.leafBiasKey[2 * (size_t)gi + 1] = bk1;
     t.leafTarget[gi] = target;
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
 }
 
 // recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
-__device__ __forceinline__ void recomputeNode(const SearchCfg& c, const TreeMem& t, int gi, uint8_t* treeBase, NodeRef nd, int lane) {
+__device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, uint8_t* treeBase, NodeRef nd, int lane, int inc) {
   const int* ch = nd.child(); const int* eN = nd.edgeN();
   double sumW = 0.0, sumWU = 0.0;
   for(int pos = lane; pos < c.P; pos += 32) {
@@ -542,7 +548,7 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, const TreeMem&
     double utility = nd.nnUtility();
     const int be = nd.biasEntry();
     if(c.biasFactor != 0.0 && be >= 0) {
-      double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
+      double* E = biasValsOfGame + (size_t)be * 2;
       double ed = E[0], ew = E[1];
       if(sumW > 1e-10) {
         const double uc = __ddiv_rn(sumWU, sumW);
@@ -557,7 +563,7 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, const TreeMem&
     }
     nd.utilityAvg() = __ddiv_rn(__dadd_rn(sumWU, utility), __dadd_rn(sumW, 1.0));
     nd.weightSum() = __dadd_rn(sumW, 1.0);
-    nd.N() = nd.N() + 1;
+    nd.N() = nd.N() + inc;
   }
   __syncwarp();
 }
@@ -596,8 +602,10 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
         const double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
         if(E[1] > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, E[0]), E[1]));   // addLeafValue :27-37
       }
-      nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi]; nd.biasEntry() = be;
+      nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi] & 0xff; nd.biasEntry() = be;
       nd.weightSum() = 1.0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
+      nd.depth() = t.leafNextPla[gi] >> 8;
+      nd.key()[0] = kind == 1 ? t.leafKey[2 * (size_t)gi] : 0; nd.key()[1] = kind == 1 ? t.leafKey[2 * (size_t)gi + 1] : 0;
       t.nodeCount[gi] = newIdx + 1;
       if(kind == 1 && c.useTable) {
         uint64_t* keys = t.tblKeys + (size_t)gi * c.tableCap * 2;
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
     }
     __syncwarp();
-    recomputeNode(c, t, gi, treeBase, nd, lane);
+    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, treeBase, nd, lane, 1);
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
@@ -630,6 +638,132 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
   else if(kind == 2 || kind == 3) atomicAdd(&t.stats[2], 1ULL);
   else if(kind == 6) atomicAdd(&t.stats[8], 1ULL);
   else atomicAdd(&t.stats[9], 1ULL);
+}
+
+// Tree re-use in graph mode: Search::makeMove (cpp/search/search.cpp:262-331) followed by the next beginSearch's
+// recursivelyRecomputeStats (:670-690, 834-910), one warp per game.  Canonical order of the order-dependent steps:
+//  1. the subgraph reachable from the played child is copied breadth first into the other node buffer (children in policy-index
+//     order get the next free indices); the new root is a COPY of the child without bias entry (searchnode.cpp:149-188) and is
+//     not in the transposition table;
+//  2. every other node -- the old copy of the child included -- is dropped, in old-index order, and gives
+//     subtreeValueBiasFreeProp of its last contribution back to its entry (removeSubtreeValueBias, search.cpp:773-786);
+//  3. both tables are rebuilt for the kept nodes; bias entries without a kept node disappear (clearUnusedSynchronous);
+//  4. with the bias on, every kept node is re-computed children first (deepest position first, ties by new index) without
+//     adding a visit; a node without children gets its plain evaluation back (search.cpp:877-897).
+__global__ void __launch_bounds__(128) k_reroot_graph(const SearchCfg c, TreeMem t, State root, const int16_t* __restrict__ chosen) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(gi >= c.numGames) return;
+  uint8_t* src = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
+  uint8_t* dst = t.nodesAlt + (size_t)gi * c.maxNodes * c.nodeStride;
+  int* queue = t.rerootQueue + (size_t)gi * c.maxNodes;
+  int* remap = t.remap + (size_t)gi * c.maxNodes;
+  const size_t tb = (size_t)gi * c.tableCap;
+  const uint64_t* oldBiasKeys = t.biasKeys + tb * 2;
+  double* oldBiasVals = t.biasVals + tb * 2;
+  uint64_t* newTblKeys = t.tblKeysAlt + tb * 2; int* newTblVals = t.tblValsAlt + tb;
+  uint64_t* newBiasKeys = t.biasKeysAlt + tb * 2; double* newBiasVals = t.biasValsAlt + tb * 2;
+  for(int k = lane; k < c.tableCap; k += 32) {
+    newTblVals[k] = 0; newBiasKeys[2 * k] = 0; newBiasKeys[2 * k + 1] = 0; newBiasVals[2 * k] = 0.0; newBiasVals[2 * k + 1] = 0.0;
+  }
+  const int oldCount = t.nodeCount[gi];
+  const int move = chosen[gi];
+  int c0 = -1;
+  if(move >= 0 && oldCount > 0 && !(flagsOf(root.misc[gi]) & 1)) c0 = NodeRef{src, c.P, c.polOff}.child()[move];
+  int count = 0;
+  if(c0 >= 0) {
+    for(int k = lane; k < oldCount; k += 32) remap[k] = -1;
+    __syncwarp();
+    if(lane == 0) { queue[0] = c0; remap[c0] = 0; }
+    count = 1;
+    __syncwarp();
+    for(int i = 0; i < count; i++) {
+      const int old = queue[i];
+      const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)old * c.nodeStride);
+      uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)i * c.nodeStride);
+      for(int k = lane; k < c.nodeStride / 16; k += 32) d4[k] = s4[k];
+      __syncwarp();
+      int* dch = NodeRef{dst + (size_t)i * c.nodeStride, c.P, c.polOff}.child();
+      for(int p0 = 0; p0 < c.P; p0 += 32) {
+        const int pos = p0 + lane;
+        const int ch = pos < c.P ? dch[pos] : -1;
+        const int r = ch >= 0 ? remap[ch] : 0;
+        const bool isNew = ch >= 0 && r < 0;
+        const unsigned m = __ballot_sync(0xffffffffu, isNew);
+        if(isNew) {
+          const int ni = count + __popc(m & ((1u << lane) - 1));
+          queue[ni] = ch; remap[ch] = ni; dch[pos] = ni;
+        } else if(ch >= 0) dch[pos] = r;
+        count += __popc(m);
+        __syncwarp();
+      }
+    }
+    if(lane == 0) {
+      // 2. dropped nodes release their bias contribution
+      if(c.biasFactor != 0.0)
+        for(int k = 0; k < oldCount; k++)
+          if(remap[k] < 0 || k == c0) {
+            NodeRef nd{src + (size_t)k * c.nodeStride, c.P, c.polOff};
+            const int be = nd.biasEntry();
+            if(be >= 0) {
+              oldBiasVals[2 * be] = __dsub_rn(oldBiasVals[2 * be], __dmul_rn(nd.lastDelta(), c.biasFreeProp));
+              oldBiasVals[2 * be + 1] = __dsub_rn(oldBiasVals[2 * be + 1], __dmul_rn(nd.lastWeight(), c.biasFreeProp));
+            }
+          }
+      NodeRef nr{dst, c.P, c.polOff};
+      nr.biasEntry() = -1; nr.lastDelta() = 0.0; nr.lastWeight() = 0.0;
+      // 3. tables of the kept nodes
+      for(int i = 1; i < count; i++) {
+        NodeRef nd{dst + (size_t)i * c.nodeStride, c.P, c.polOff};
+        if(c.useTable) {
+          const uint64_t k0 = nd.key()[0], k1 = nd.key()[1];
+          int slot = (int)(k0 & (uint64_t)(c.tableCap - 1));
+          while(newTblVals[slot] != 0) slot = (slot + 1) & (c.tableCap - 1);
+          newTblKeys[2 * slot] = k0; newTblKeys[2 * slot + 1] = k1; newTblVals[slot] = i + 1;
+        }
+        const int be = nd.biasEntry();
+        if(be >= 0) {
+          const uint64_t bk0 = oldBiasKeys[2 * be], bk1 = oldBiasKeys[2 * be + 1];
+          int slot = (int)(splitmix64(bk0 ^ splitmix64(bk1)) & (uint64_t)(c.tableCap - 1));
+          while(true) {
+            if(newBiasKeys[2 * slot] == 0) {
+              newBiasKeys[2 * slot] = bk0; newBiasKeys[2 * slot + 1] = bk1;
+              newBiasVals[2 * slot] = oldBiasVals[2 * be]; newBiasVals[2 * slot + 1] = oldBiasVals[2 * be + 1];
+              break;
+            }
+            if(newBiasKeys[2 * slot] == bk0 && newBiasKeys[2 * slot + 1] == bk1) break;
+            slot = (slot + 1) & (c.tableCap - 1);
+          }
+          nd.biasEntry() = slot;
+        }
+      }
+    }
+    __syncwarp();
+    // 4. children-first re-computation
+    if(c.biasFactor != 0.0) {
+      int lo = 1 << 20, hi = -1;
+      for(int i = lane; i < count; i += 32) {
+        const int d = NodeRef{dst + (size_t)i * c.nodeStride, c.P, c.polOff}.depth();
+        lo = min(lo, d); hi = max(hi, d);
+      }
+      for(int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+      for(int d = hi; d >= lo; d--)
+        for(int base = 0; base < count; base += 32) {
+          const int i = base + lane;
+          const bool match = i < count && NodeRef{dst + (size_t)i * c.nodeStride, c.P, c.polOff}.depth() == d;
+          unsigned m = __ballot_sync(0xffffffffu, match);
+          while(m) {
+            const int j = base + __ffs(m) - 1;
+            m &= m - 1;
+            NodeRef nd{dst + (size_t)j * c.nodeStride, c.P, c.polOff};
+            if(nd.numChildren() == 0) {
+              if(lane == 0) nd.utilityAvg() = nd.nnUtility();
+              __syncwarp();
+            } else recomputeNode(c, newBiasVals, dst, nd, lane, 0);
+          }
+        }
+    }
+  }
+  if(lane == 0) t.nodeCount[gi] = count;
 }
 
 // hash over every node of every game's graph (creation order = node index), compared with the oracle's
@@ -972,7 +1106,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(ctx && p && out, "kc_search_create: null argument");
   KC_CHECK(p->maxVisits >= 1 && p->maxVisits <= 65536, "kc_search_create: maxVisits must be within 1..65536");
   KC_CHECK(p->cpuctExploration > 0 && p->fpuReductionMax >= 0 && p->rootFpuReductionMax >= 0, "kc_search_create: bad exploration parameters");
-  KC_CHECK(!(p->useGraphSearch || p->subtreeValueBiasFactor != 0.0) || !p->reuseTree, "kc_search_create: graph search / subtree value bias with reuseTree is not supported");
+  KC_CHECK(p->subtreeValueBiasFreeProp >= 0.0 && p->subtreeValueBiasFreeProp <= 1.0, "kc_search_create: subtreeValueBiasFreeProp must be within 0..1");
   KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
@@ -983,12 +1117,15 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.P = 4 * xSize * ySize; c.LW = (c.P + 31) / 32;
   c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0) ? 1 : 0;
   c.useTable = p->useGraphSearch ? 1 : 0;
-  c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent;
-  c.polOff = c.graph ? 64 : 32 + 8 * c.P;
+  c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent; c.biasFreeProp = p->subtreeValueBiasFreeProp;
+  c.polOff = c.graph ? 80 : 32 + 8 * c.P;
   c.nodeStride = (c.polOff + 13 * c.P + 15) / 16 * 16;
+  // graph mode with re-use: a kept subgraph can hold nodes whose creating visits went through another root child, so the
+  // pool is a quarter larger than maxVisits; a visit that finds it empty is dropped (the oracle does the same)
+  c.maxNodes = p->maxVisits + ((c.graph && p->reuseTree) ? p->maxVisits / 4 : 0);
   c.tableCap = 16;
-  while(c.tableCap < 2 * p->maxVisits) c.tableCap *= 2;
-  c.maxNodes = p->maxVisits; c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
+  while(c.tableCap < 2 * c.maxNodes) c.tableCap *= 2;
+  c.maxVisits = p->maxVisits; c.temperaturePlies = p->temperaturePlies;
   c.numGames = numGames; c.autoRefill = p->autoRefill ? 1 : 0;
   c.compact = (handleOrNull && kc::handleIsBf16(handleOrNull) && !p->noCompaction) ? 1 : 0;
   c.reuseTree = p->reuseTree ? 1 : 0;
@@ -1018,6 +1155,11 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     KC_CUDA(cudaMalloc(&S->tree.biasKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.biasVals, slots * 16));
     KC_CUDA(cudaMalloc(&S->tree.leafKey, n * 16)); KC_CUDA(cudaMalloc(&S->tree.leafBiasKey, n * 16)); KC_CUDA(cudaMalloc(&S->tree.leafTarget, n * 4));
     KC_CUDA(cudaMemset(S->tree.tblVals, 0, slots * 4)); KC_CUDA(cudaMemset(S->tree.biasKeys, 0, slots * 16)); KC_CUDA(cudaMemset(S->tree.biasVals, 0, slots * 16));
+    if(c.reuseTree) {
+      KC_CUDA(cudaMalloc(&S->tree.tblKeysAlt, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.tblValsAlt, slots * 4));
+      KC_CUDA(cudaMalloc(&S->tree.biasKeysAlt, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.biasValsAlt, slots * 16));
+      KC_CUDA(cudaMalloc(&S->tree.remap, n * c.maxNodes * 4));
+    }
   }
   KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
@@ -1037,6 +1179,7 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.nodesAlt); cudaFree(S->tree.rerootQueue); cudaFree(S->tree.active);
   cudaFree(S->tree.tblKeys); cudaFree(S->tree.tblVals); cudaFree(S->tree.biasKeys); cudaFree(S->tree.biasVals);
   cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget);
+  cudaFree(S->tree.tblKeysAlt); cudaFree(S->tree.tblValsAlt); cudaFree(S->tree.biasKeysAlt); cudaFree(S->tree.biasValsAlt); cudaFree(S->tree.remap);
   { kc::TrainMem& t = S->train;
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
@@ -1056,6 +1199,8 @@ int kc_search_reset(kc_search* S, uint64_t seed, uint64_t firstGameId) {
   if(kc_games_reset(S->root, seed, firstGameId, 0)) return 1;
   KC_CUDA(cudaMemset(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4));
   KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
+  if(clearTables(S, S->leaf->stream)) return 1;
+  KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
   return 0;
 }
 
@@ -1126,13 +1271,17 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     }
     if(!c.reuseTree) KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
     KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
-    if(clearTables(S, st)) return 1;
+    if(!c.reuseTree && clearTables(S, st)) return 1;   // with re-use the re-rooting keeps the tables in step with the graph
     if(runVisits(S)) return 1;
     if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
     S->launches++;
     if(c.reuseTree) {
-      k_reroot<<<(c.numGames * 32 + 127) / 128, 128, 0, st>>>(c, S->tree, R->st, S->d_chosen);
+      if(c.graph) {
+        k_reroot_graph<<<(c.numGames * 32 + 127) / 128, 128, 0, st>>>(c, S->tree, R->st, S->d_chosen);
+        std::swap(S->tree.tblKeys, S->tree.tblKeysAlt); std::swap(S->tree.tblVals, S->tree.tblValsAlt);
+        std::swap(S->tree.biasKeys, S->tree.biasKeysAlt); std::swap(S->tree.biasVals, S->tree.biasValsAlt);
+      } else k_reroot<<<(c.numGames * 32 + 127) / 128, 128, 0, st>>>(c, S->tree, R->st, S->d_chosen);
       std::swap(S->tree.nodes, S->tree.nodesAlt);
       S->launches++;
     }

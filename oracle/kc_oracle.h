@@ -216,7 +216,7 @@ void ko_postprocess(float* policy, int policySize, const uint32_t* legalMask, fl
 typedef struct {
   int32_t maxVisits, temperaturePlies, autoRefill, noCompaction, reuseTree, useGraphSearch;
   double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
-  double subtreeValueBiasFactor, subtreeValueBiasWeightExponent;
+  double subtreeValueBiasFactor, subtreeValueBiasWeightExponent, subtreeValueBiasFreeProp;
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
@@ -226,6 +226,14 @@ void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_sea
 void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                          int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                          uint8_t* orderOut, uint64_t counters[5], uint64_t* digest);
+typedef struct ko_graph_search ko_graph_search;   /* persistent graph: continue() searches on, advance() re-roots (tree re-use) */
+ko_graph_search* ko_graph_search_create(int x_size, int y_size, const ko_search_params* p);
+void ko_graph_search_destroy(ko_graph_search* s);
+void ko_graph_search_continue(ko_graph_search* s, const ko_game* rootGame, const ko_model* modelOrNull, int32_t* rootVisits, double* rootUtilitySum,
+                              int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut, uint8_t* orderOut, uint64_t counters[5], uint64_t* digest);
+void ko_graph_search_advance(ko_graph_search* s, int movePos);
+uint64_t ko_graph_search_digest(const ko_graph_search* s);
+int ko_graph_search_num_nodes(const ko_graph_search* s);
 typedef struct ko_search ko_search;   /* persistent tree: continue() searches on, advance() re-roots at the move played */
 ko_search* ko_search_create(void);
 void ko_search_destroy(ko_search* s);

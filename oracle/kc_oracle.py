@@ -96,6 +96,14 @@ def lib():
         l.ko_search_run_graph.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_graph_hash.argtypes = [vp, vp, C.c_int, vp]
         l.ko_game_recent_move_pos.argtypes = [vp, C.c_int]
+        l.ko_graph_search_create.restype = vp
+        l.ko_graph_search_create.argtypes = [C.c_int, C.c_int, vp]
+        l.ko_graph_search_destroy.argtypes = [vp]
+        l.ko_graph_search_continue.argtypes = [vp] * 11
+        l.ko_graph_search_advance.argtypes = [vp, C.c_int]
+        l.ko_graph_search_digest.argtypes = [vp]
+        l.ko_graph_search_digest.restype = C.c_uint64
+        l.ko_graph_search_num_nodes.argtypes = [vp]
         l.ko_search_create.restype = vp
         l.ko_search_destroy.argtypes = [vp]
         l.ko_search_clear.argtypes = [vp]
@@ -284,7 +292,7 @@ class SearchParams(C.Structure):
     """Same layout as kc_search_params (include/katacoffee_b200.h)."""
     _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("useGraphSearch", C.c_int32),
                 ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double),
-                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double)]
+                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double), ("subtreeValueBiasFreeProp", C.c_double)]
 
 
 def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
@@ -313,6 +321,39 @@ def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=
                               _p(pol), _p(order), _p(cnt), _p(dg))
     return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
             "counters": cnt, "digest": int(dg[0])}
+
+
+class PersistentGraphSearch:
+    """Oracle graph search (transpositions + subtree value bias) that re-roots its graph at the move played (tree re-use)."""
+
+    def __init__(self, W, H, max_visits, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5, free_prop=0.8):
+        self.P = 4 * W * H
+        sp = SearchParams(max_visits, 0, 0, 0, 1, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent, free_prop)
+        self._s = lib().ko_graph_search_create(W, H, C.byref(sp))
+
+    def __del__(self):
+        if getattr(self, "_s", None):
+            lib().ko_graph_search_destroy(self._s)
+            self._s = None
+
+    def run(self, game, model=None):
+        P = self.P
+        rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
+        ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
+        cnt = np.zeros(5, np.uint64); dg = np.zeros(1, np.uint64)
+        lib().ko_graph_search_continue(self._s, game._g, None if model is None else model._m, _p(rv), _p(rw), _p(ev), _p(ew), _p(pol), _p(order),
+                                       _p(cnt), _p(dg))
+        return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
+                "counters": cnt, "digest": int(dg[0])}
+
+    def advance(self, move_pos):
+        lib().ko_graph_search_advance(self._s, int(move_pos))
+
+    def digest(self):
+        return int(lib().ko_graph_search_digest(self._s))
+
+    def num_nodes(self):
+        return int(lib().ko_graph_search_num_nodes(self._s))
 
 
 class PersistentSearch:

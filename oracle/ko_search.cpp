@@ -253,16 +253,17 @@ double biasPow(double x, double e) {
   return detExp(e * detLog(x));
 }
 
+typedef std::pair<uint64_t, uint64_t> Key;
 struct GNode {
-  int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1;
+  int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1, depth = 0;
   double weightSum = 0.0, utilityAvg = 0.0, nnUtility = 0.0, lastDelta = 0.0, lastWeight = 0.0;
+  Key key = Key(0, 0);
   std::vector<float> policy;
   std::vector<int> child, edgeN;
   std::vector<uint8_t> order;
   explicit GNode(int P) : policy(P, -1.0f), child(P, -1), edgeN(P, 0), order(P, 0) {}
 };
-struct BiasEntry { double deltaSum = 0.0, weightSum = 0.0; };
-typedef std::pair<uint64_t, uint64_t> Key;
+struct BiasEntry { double deltaSum = 0.0, weightSum = 0.0; Key key = Key(0, 0); };
 
 struct GraphSearch {
   int W, H, P;
@@ -298,7 +299,7 @@ struct GraphSearch {
   }
   static double childWeight(double cw, int e, int cv) { return cw * ((double)e / (double)std::max(cv, 1)); }
 
-  void recompute(GNode& nd) {
+  void recompute(GNode& nd, int inc = 1) {
     double partW[32] = {0}, partWU[32] = {0};
     for(int pos = 0; pos < P; pos++)
       if(nd.child[pos] != -1) {
@@ -326,7 +327,63 @@ struct GraphSearch {
     }
     nd.utilityAvg = (sumWU + utility) / (sumW + 1.0);
     nd.weightSum = sumW + 1.0;
-    nd.visits += 1;
+    nd.visits += inc;
+  }
+
+  // Search::makeMove with tree re-use in graph mode (search.cpp:262-331) followed by the next beginSearch's
+  // recursivelyRecomputeStats (search.cpp:670-690, 834-910).  Canonical order of the order-dependent steps:
+  //  1. the subgraph reachable from the played child is kept, renumbered breadth first (children in policy-index order); the new
+  //     root is a COPY of the child without bias entry (SearchNode copy constructor, searchnode.cpp:149-188) and is not in the table;
+  //  2. every other node -- the old copy of the child included -- is deleted in old-index order and gives
+  //     subtreeValueBiasFreeProp of its last contribution back (removeSubtreeValueBias, search.cpp:773-786);
+  //  3. bias entries no kept node refers to are erased (clearUnusedSynchronous);
+  //  4. if the bias is on, every kept node is re-computed children first (deepest position first, ties by new index) without
+  //     adding a visit; a node without children gets its plain evaluation back (search.cpp:877-897).
+  void advance(int movePos) {
+    int c0 = -1;
+    if(!nodes.empty() && movePos >= 0) c0 = nodes[0].child[movePos];
+    if(c0 < 0) { nodes.clear(); table.clear(); biasIndex.clear(); bias.clear(); return; }
+    std::vector<int> remap(nodes.size(), -1), queue{c0};
+    remap[c0] = 0;
+    std::vector<GNode> out;
+    for(size_t i = 0; i < queue.size(); i++) {
+      GNode n = nodes[queue[i]];
+      for(int pos = 0; pos < P; pos++)
+        if(n.child[pos] >= 0) {
+          if(remap[n.child[pos]] < 0) { remap[n.child[pos]] = (int)queue.size(); queue.push_back(n.child[pos]); }
+          n.child[pos] = remap[n.child[pos]];
+        }
+      out.push_back(std::move(n));
+    }
+    for(size_t i = 0; i < nodes.size(); i++)
+      if((remap[i] < 0 || (int)i == c0) && nodes[i].biasEntry >= 0) {
+        BiasEntry& E = bias[nodes[i].biasEntry];
+        E.deltaSum = E.deltaSum - nodes[i].lastDelta * p->subtreeValueBiasFreeProp;
+        E.weightSum = E.weightSum - nodes[i].lastWeight * p->subtreeValueBiasFreeProp;
+      }
+    out[0].biasEntry = -1; out[0].lastDelta = 0.0; out[0].lastWeight = 0.0;
+    std::vector<BiasEntry> nbias;
+    std::map<Key, int> nindex, ntable;
+    for(size_t i = 1; i < out.size(); i++) {
+      ntable[out[i].key] = (int)i;
+      if(out[i].biasEntry >= 0) {
+        const BiasEntry& E = bias[out[i].biasEntry];
+        auto f = nindex.find(E.key);
+        if(f == nindex.end()) { f = nindex.insert({E.key, (int)nbias.size()}).first; nbias.push_back(E); }
+        out[i].biasEntry = f->second;
+      }
+    }
+    nodes.swap(out); table.swap(ntable); biasIndex.swap(nindex); bias.swap(nbias);
+    if(p->subtreeValueBiasFactor != 0.0) {
+      int lo = 1 << 20, hi = -1;
+      for(const GNode& n : nodes) { lo = std::min(lo, n.depth); hi = std::max(hi, n.depth); }
+      for(int d = hi; d >= lo; d--)
+        for(GNode& n : nodes)
+          if(n.depth == d) {
+            if(n.numChildren == 0) n.utilityAvg = n.nnUtility;
+            else recompute(n, 0);
+          }
+    }
   }
 };
 
@@ -338,13 +395,30 @@ extern "C" {
 // edgeUtilitySum[pos] = child's utilityAvg * edgeVisits (one rounding each); counters += visits, evaluations, terminal visits,
 // transposition hits (new edge to an existing node), catch-up visits (edge behind its child: no descent); digest (may be NULL)
 // receives a hash over every node of the graph in creation order.
-void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
-                         int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
-                         uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
+static uint64_t graphDigest(const GraphSearch& S) {
+  const int P = S.P;
+  uint64_t h = 0;
+  for(size_t i = 0; i < S.nodes.size(); i++) {
+    const GNode& nd = S.nodes[i];
+    uint64_t wb, ub;
+    memcpy(&wb, &nd.weightSum, 8); memcpy(&ub, &nd.utilityAvg, 8);
+    uint64_t nh = ko_splitmix64((uint64_t)nd.visits ^ ((uint64_t)nd.numChildren << 32)) ^ ko_splitmix64(wb ^ PHI) ^ ko_splitmix64(ub + PHI);
+    for(int pos = 0; pos < P; pos++)
+      if(nd.child[pos] != -1)
+        nh ^= ko_splitmix64(((uint64_t)(uint32_t)nd.child[pos] << 32 | (uint64_t)(uint32_t)nd.edgeN[pos]) + (uint64_t)(pos + 1) * PHI + nd.order[pos]);
+    h ^= ko_splitmix64(nh + (uint64_t)(i + 1) * PHI);
+  }
+  return h;
+}
+
+static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                     int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                     uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
   const int P = 4 * x_size * y_size;
   Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
-  GraphSearch S{x_size, y_size, P, p, {}, {}, {}, {}};
-  S.nodes.reserve(p->maxVisits);
+  S.p = p;
+  const size_t maxNodes = (size_t)p->maxVisits + (p->reuseTree ? (size_t)p->maxVisits / 4 : 0);   // the device's node pool
+  S.nodes.reserve(maxNodes);
   uint64_t cnt[5] = {0, 0, 0, 0, 0};
   ko_game* g = ko_game_create(x_size, y_size, 4);
   ko_game* before = ko_game_create(x_size, y_size, 4);
@@ -424,6 +498,7 @@ void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const 
       }
     }
     if(kind == 0) continue;
+    if((kind == 1 || kind == 4) && S.nodes.size() >= maxNodes) continue;   // node pool exhausted (re-use in graph mode only): the visit is dropped
     int newIdx = -1;
     if(kind == 1 || kind == 4) {
       ev.eval(g, pol.data(), wl);
@@ -432,11 +507,12 @@ void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const 
       S.nodes.emplace_back(P);
       GNode& nn = S.nodes.back();
       nn.visits = 1; nn.weightSum = 1.0; nn.nnUtility = v; nn.nextPla = ko_game_next_pla(g);
+      nn.key = kind == 1 ? leafKey : Key(0, 0); nn.depth = ko_game_num_turns(g);
       for(int pos = 0; pos < P; pos++) nn.policy[pos] = pol[pos];
       double utility = v;
       if(haveBias) {
         auto f = S.biasIndex.find(leafBias);
-        if(f == S.biasIndex.end()) { f = S.biasIndex.insert({leafBias, (int)S.bias.size()}).first; S.bias.emplace_back(); }
+        if(f == S.biasIndex.end()) { f = S.biasIndex.insert({leafBias, (int)S.bias.size()}).first; S.bias.emplace_back(); S.bias.back().key = leafBias; }
         nn.biasEntry = f->second;
         const BiasEntry& E = S.bias[nn.biasEntry];
         if(E.weightSum > 0.001) utility = utility + (p->subtreeValueBiasFactor * E.deltaSum) / E.weightSum;   // addLeafValue :27-37
@@ -475,21 +551,32 @@ void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const 
     if(orderOut) orderOut[pos] = ex ? S.nodes[0].order[pos] : 255;
   }
   if(counters) for(int i = 0; i < 5; i++) counters[i] += cnt[i];
-  if(digest) {
-    uint64_t h = 0;
-    for(size_t i = 0; i < S.nodes.size(); i++) {
-      const GNode& nd = S.nodes[i];
-      uint64_t wb, ub;
-      memcpy(&wb, &nd.weightSum, 8); memcpy(&ub, &nd.utilityAvg, 8);
-      uint64_t nh = ko_splitmix64((uint64_t)nd.visits ^ ((uint64_t)nd.numChildren << 32)) ^ ko_splitmix64(wb ^ PHI) ^ ko_splitmix64(ub + PHI);
-      for(int pos = 0; pos < P; pos++)
-        if(nd.child[pos] != -1)
-          nh ^= ko_splitmix64(((uint64_t)(uint32_t)nd.child[pos] << 32 | (uint64_t)(uint32_t)nd.edgeN[pos]) + (uint64_t)(pos + 1) * PHI + nd.order[pos]);
-      h ^= ko_splitmix64(nh + (uint64_t)(i + 1) * PHI);
-    }
-    *digest = h;
-  }
+  if(digest) *digest = graphDigest(S);
 }
+
+void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
+                         int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
+                         uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
+  GraphSearch S{x_size, y_size, 4 * x_size * y_size, p, {}, {}, {}, {}};
+  graphRun(S, rootGame, x_size, y_size, p, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters, digest);
+}
+
+// Persistent graph search with re-use between moves: continue() searches the current graph on until the root has maxVisits
+// visits, advance() re-roots it at the move played (GraphSearch::advance).
+struct ko_graph_search { GraphSearch S; ko_search_params params; };
+ko_graph_search* ko_graph_search_create(int x_size, int y_size, const ko_search_params* p) {
+  ko_graph_search* s = new ko_graph_search{GraphSearch{x_size, y_size, 4 * x_size * y_size, nullptr, {}, {}, {}, {}}, *p};
+  s->S.p = &s->params;
+  return s;
+}
+void ko_graph_search_destroy(ko_graph_search* s) { delete s; }
+void ko_graph_search_continue(ko_graph_search* s, const ko_game* rootGame, const ko_model* modelOrNull, int32_t* rootVisits, double* rootUtilitySum,
+                              int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut, uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
+  graphRun(s->S, rootGame, s->S.W, s->S.H, &s->params, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters, digest);
+}
+void ko_graph_search_advance(ko_graph_search* s, int movePos) { s->S.p = &s->params; s->S.advance(movePos); }
+uint64_t ko_graph_search_digest(const ko_graph_search* s) { return graphDigest(s->S); }
+int ko_graph_search_num_nodes(const ko_graph_search* s) { return (int)s->S.nodes.size(); }
 
 }  // extern "C"
 

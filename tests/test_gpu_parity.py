@@ -743,6 +743,46 @@ def test_search_graph_selfplay_counters_match_oracle(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("W,H,K,graph,factor,exponent", [(5, 5, 4, True, 0.30, 0.8), (5, 5, 4, True, 0.0, 0.5), (5, 5, 4, False, 0.45, 0.5),
+                                                         (4, 5, 3, True, 0.30, 1.0)])
+def test_search_graph_tree_reuse_matches_oracle(ctx, oracle, W, H, K, graph, factor, exponent):
+    """Tree re-use in graph mode (Search::makeMove: breadth-first copy of the kept subgraph, dropped nodes give
+    subtreeValueBiasFreeProp of their contribution back, tables rebuilt, children-first re-computation): after every move the
+    whole re-rooted graph of every game equals the oracle's (digest), and so do moves and counters to the end of the games."""
+    from katacoffee_b200 import backend, capi
+    G, V, seed, T = 64, 72, 29, 5
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, temperaturePlies=T, reuseTree=True, useGraphSearch=graph,
+                       subtreeValueBiasFactor=factor, subtreeValueBiasWeightExponent=exponent, subtreeValueBiasFreeProp=0.8)
+    s.reset(seed=seed, firstGameId=300)
+    ogames = [oracle.Game(W, H, K) for _ in range(G)]
+    osearch = [oracle.PersistentGraphSearch(W, H, V, graph=graph, bias_factor=factor, bias_exponent=exponent, free_prop=0.8) for _ in range(G)]
+    stats = capi.SearchStats()
+    ocnt = np.zeros(5, np.uint64)
+    for ply in range(W * H):
+        _, chosen, _ = s.play(1, stats)
+        dig = s.treeDigest()
+        for g in range(G):
+            og = ogames[g]
+            if og.finished():
+                assert chosen[g] == -1
+                continue
+            r = osearch[g].run(og)
+            assert r["rootVisits"] == V
+            ocnt += r["counters"]
+            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 300 + g)
+            assert chosen[g] == mv, (ply, g, chosen[g], mv)
+            og.play(mv)
+            osearch[g].advance(mv)
+            if og.finished():
+                continue    # the device drops the tree of a finished game; the oracle object is not used again
+            assert int(dig[g]) == osearch[g].digest(), (ply, g, osearch[g].num_nodes())
+    assert all(og.finished() for og in ogames)
+    assert (stats.visits, stats.netEvals, stats.terminalVisits, stats.transpositionHits, stats.catchUpVisits) == tuple(int(x) for x in ocnt)
+    assert stats.visits < 0.9 * stats.movesPlayed * V          # re-use really saved visits
+    s.close()
+
+
+@pytest.mark.gpu
 def test_search_selfplay_moves_match_oracle(ctx, oracle):
     """search -> choose (visit-proportional for the first plies, then most visited) -> play, repeated to the end of the
     games: the move sequences, results and counters equal the oracle's."""
