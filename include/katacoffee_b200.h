@@ -148,6 +148,11 @@ int kc_sgf_parse(const char* sgf, int* xSize, int* ySize, int* winLen, int8_t* i
                                        makes it a true symmetry of the game; default is the reference backends' spatial-only copy.
                                        Applies to kc_forward and kc_games_eval; kc_games_features is always spatial-only. */
 
+/* Page-locked host memory for the buffers handed to kc_forward (InputBuffers of nninterface.h:92-93): with pinned rows the
+ * chunked H2D / D2H copies of kc_forward are asynchronous DMA that overlap the kernels; pageable memory works but serialises. */
+int kc_host_alloc(size_t bytes, void** out);
+int kc_host_free(void* p);
+
 int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLen, int nnYLen,
                      unsigned flags, kc_handle** out);
 int kc_handle_destroy(kc_handle* h);

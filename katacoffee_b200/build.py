@@ -60,9 +60,9 @@ def build_host(force=False):
     if not force and os.path.exists(lib) and os.path.exists(exe) and min(os.path.getmtime(lib), os.path.getmtime(exe)) >= newest:
         return lib, exe
     inc = ["-I" + os.path.join(HERE, "..", "include"), "-I" + host]
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall"] + inc + [src, "-o", lib, "-L" + HERE, "-lkatacoffee_b200",
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wall"] + inc + [src, "-o", lib, "-L" + HERE, "-lkatacoffee_b200",
                     "-Wl,-rpath,$ORIGIN"], check=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [test, "-o", exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-Wall"] + inc + [test, "-o", exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
                     "-Wl,-rpath," + HERE], check=True)
     return lib, exe
 

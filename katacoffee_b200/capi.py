@@ -115,6 +115,8 @@ PROTOTYPES = {
     "kc_modelfile_write": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "kc_sgf_write": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, vp, C.c_int, vp, vp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "kc_sgf_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_int, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "kc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "kc_host_free": (C.c_int, [vp]),
     "kc_search_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SearchParams), C.POINTER(vp)]),
     "kc_search_destroy": (C.c_int, [vp]),
     "kc_search_games": (vp, [vp]),

@@ -575,6 +575,16 @@ int kc_handle_read_outputs(kc_handle* h, int n, float* policy, float* value, flo
   return 0;
 }
 
+int kc_host_alloc(size_t bytes, void** out) {
+  KC_CHECK(out && bytes > 0, "kc_host_alloc: bad argument");
+  KC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+int kc_host_free(void* p) {
+  if(p) KC_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
 int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, const int8_t* symmetry,
                float* policy, float* value, float* misc, float* ownership) {
   KC_CHECK(h && spatial && global && policy && value && misc, "kc_forward: null argument");

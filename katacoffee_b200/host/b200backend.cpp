@@ -119,9 +119,20 @@ struct ComputeHandle {
 
 struct InputBuffers {
   int maxBatchSize, singleInputElts, singleInputGlobalElts, policySize, hw;
-  // host staging in the batch layout kc_forward takes; pinned so that the H2D copies are asynchronous DMA
-  vector<float> spatial, global, policy, value, misc, ownership;
-  vector<int8_t> symmetry;
+  // host staging in the batch layout kc_forward takes; page-locked (kc_host_alloc) so that its chunked copies are asynchronous DMA
+  template <class T> struct Pinned {
+    T* p = nullptr; size_t n = 0;
+    void resize(size_t count) {
+      void* v = nullptr;
+      kcCheck(kc_host_alloc(count * sizeof(T) + 16, &v), "kc_host_alloc");
+      p = static_cast<T*>(v); n = count;
+    }
+    ~Pinned() { kc_host_free(p); }
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
+  };
+  Pinned<float> spatial, global, policy, value, misc, ownership;
+  Pinned<int8_t> symmetry;
 };
 
 namespace NeuralNet {
@@ -201,15 +212,20 @@ void freeInputBuffers(InputBuffers* b) { delete b; }
 void getOutput(ComputeHandle* h, InputBuffers* b, int numBatchEltsFilled, NNResultBuf** inputBufs, vector<NNOutput*>& outputs) {
   const int n = numBatchEltsFilled;
   if(n <= 0 || n > b->maxBatchSize || (int)outputs.size() != n) throw StringError("B200 backend: getOutput called with a bad batch size");
+  for(int i = 0; i < n; i++)
+    if(inputBufs[i]->rowSpatialSize != b->singleInputElts || inputBufs[i]->rowGlobalSize != b->singleInputGlobalElts)
+      throw StringError("B200 backend: row sizes do not match the model");
+  // gather the rows of the batch (every backend does this copy, e.g. eigenbackend.cpp:1700-1730); large batches on several threads
+#pragma omp parallel for schedule(static) num_threads(8) if(n >= 1024)
   for(int i = 0; i < n; i++) {
     const NNResultBuf* r = inputBufs[i];
-    if(r->rowSpatialSize != b->singleInputElts || r->rowGlobalSize != b->singleInputGlobalElts) throw StringError("B200 backend: row sizes do not match the model");
     memcpy(&b->spatial[(size_t)i * b->singleInputElts], r->rowSpatial, sizeof(float) * b->singleInputElts);
     memcpy(&b->global[(size_t)i * b->singleInputGlobalElts], r->rowGlobal, sizeof(float) * b->singleInputGlobalElts);
     b->symmetry[i] = (int8_t)r->symmetry;
   }
   kcCheck(kc_forward(h->handle, n, b->spatial.data(), b->global.data(), b->symmetry.data(), b->policy.data(), b->value.data(), b->misc.data(),
                      b->ownership.data()), "kc_forward");
+#pragma omp parallel for schedule(static) num_threads(8) if(n >= 1024)
   for(int i = 0; i < n; i++) {
     NNOutput* o = outputs[i];
     // logits, already in NNPos order and inverse-symmetrised; nnHash / noisedPolicyProbs are not touched (eigenbackend.cpp:1765-1767)

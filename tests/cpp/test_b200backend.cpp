@@ -4,6 +4,7 @@
 // Checks: (1) the shim's outputs equal a direct kc_forward call bit for bit, for the bf16 and the
 // fp32 path, with per-row symmetry and with/without the owner map; (2) the fp32 and bf16 paths agree
 // to bf16 tolerance; (3) the literal 1x1-convolution vector of testnn.cpp:161-207.  Exit code 0 = pass.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -133,6 +134,31 @@ int main() {
     REQUIRE(out.size() == 72);
     for(size_t i = 0; i < expectFirst.size(); i++) REQUIRE(std::fabs(out[i] - expectFirst[i]) < 1e-4);
     REQUIRE(!NeuralNet::testEvaluateConv(&d, 2, 4, 3, true, false, in, out));   // fp16 layer hooks: unsupported -> false
+  }
+  {
+    // throughput of the drop-in call itself at a self-play sized batch: rows gathered from NNResultBufs, one getOutput, logits
+    // scattered into NNOutputs (b10c128-shaped trunk, bf16 path)
+    const int B = 148 * 128;
+    LoadedModel* big = NeuralNet::loadModelFromDesc(makeModel(128, 128, 96, 32, 10));
+    ComputeContext* ctx = NeuralNet::createComputeContext({0}, nullptr, W, H, "", "", false, enabled_t::True, enabled_t::Auto, big);
+    ComputeHandle* h = NeuralNet::createComputeHandle(ctx, big, nullptr, B, true, false, 0, 0);
+    InputBuffers* ib = NeuralNet::createInputBuffers(big, B, W, H);
+    std::vector<NNResultBuf> bufs(B); std::vector<NNResultBuf*> bufPtrs(B);
+    std::vector<NNOutput> outs(B); std::vector<NNOutput*> outPtrs(B);
+    for(int i = 0; i < B; i++) {
+      bufs[i].rowSpatial = spatial[i % N].data(); bufs[i].rowGlobal = global[i % N].data();
+      bufs[i].rowSpatialSize = 15 * HW; bufs[i].rowGlobalSize = 1; bufs[i].symmetry = i % 8;
+      bufPtrs[i] = &bufs[i]; outPtrs[i] = &outs[i];
+    }
+    for(int rep = 0; rep < 3; rep++) NeuralNet::getOutput(h, ib, B, bufPtrs.data(), outPtrs);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int reps = 10;
+    for(int rep = 0; rep < reps; rep++) NeuralNet::getOutput(h, ib, B, bufPtrs.data(), outPtrs);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("NeuralNet::getOutput, %d rows per call (b10c128 shape, bf16): %.3f ms per call, %.3f M evals/s incl. the host gather / scatter\n", B,
+           sec / reps * 1e3, B * reps / sec / 1e6);
+    for(int i = 0; i < N; i++) REQUIRE(memcmp(outs[i].policyProbs, outs[i + N * 8].policyProbs, 4 * HW * 4) == 0);   // same row, same symmetry
+    NeuralNet::freeInputBuffers(ib); NeuralNet::freeComputeHandle(h); NeuralNet::freeComputeContext(ctx); NeuralNet::freeLoadedModel(big);
   }
   bool threw = false;
   try { NeuralNet::loadModelFile("nonexistent.bin.gz", ""); } catch(const StringError&) { threw = true; }
