@@ -217,6 +217,11 @@ typedef struct {
   int32_t maxVisits, temperaturePlies, autoRefill, noCompaction, reuseTree, useGraphSearch;
   double cpuctExploration, fpuReductionMax, rootFpuReductionMax;
   double subtreeValueBiasFactor, subtreeValueBiasWeightExponent, subtreeValueBiasFreeProp;
+  int32_t rootNoiseEnabled, fpuParentWeightByVisitedPolicy;
+  double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight;
+  double rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
+  double fpuParentWeightByVisitedPolicyPow, rootDesiredPerChildVisitsCoeff;
+  uint64_t noiseSeed, noiseGameId;   /* oracle only (one game per call): what kc_search_reset's seed and the game id are on the device */
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,

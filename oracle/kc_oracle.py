@@ -292,7 +292,21 @@ class SearchParams(C.Structure):
     """Same layout as kc_search_params (include/katacoffee_b200.h)."""
     _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("useGraphSearch", C.c_int32),
                 ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double),
-                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double), ("subtreeValueBiasFreeProp", C.c_double)]
+                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double), ("subtreeValueBiasFreeProp", C.c_double),
+                ("rootNoiseEnabled", C.c_int32), ("fpuParentWeightByVisitedPolicy", C.c_int32),
+                ("rootDirichletNoiseTotalConcentration", C.c_double), ("rootDirichletNoiseWeight", C.c_double),
+                ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
+                ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double),
+                ("noiseSeed", C.c_uint64), ("noiseGameId", C.c_uint64)]   # the last two exist in the oracle only
+
+
+def _with_extras(sp, extra):
+    """Sets the optional search options (root noise / temperature, FPU parent weight, ...) given as keyword arguments."""
+    for k, v in extra.items():
+        if not hasattr(sp, k):
+            raise TypeError(f"unknown search option {k}")
+        setattr(sp, k, v)
+    return sp
 
 
 def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
@@ -309,11 +323,11 @@ def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
             "counters": cnt}
 
 
-def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5):
+def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5, **extra):
     """One oracle graph search (transpositions + subtree value bias) from `game`; see ko_search.cpp.  counters = visits,
     evaluations, terminal visits, transposition hits, catch-up visits; digest = hash over the whole graph."""
     P = 4 * game.HW
-    sp = SearchParams(max_visits, 0, 0, 0, 0, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent)
+    sp = _with_extras(SearchParams(max_visits, 0, 0, 0, 0, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent), extra)
     rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
     ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
     cnt = np.zeros(5, np.uint64); dg = np.zeros(1, np.uint64)
@@ -326,9 +340,9 @@ def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=
 class PersistentGraphSearch:
     """Oracle graph search (transpositions + subtree value bias) that re-roots its graph at the move played (tree re-use)."""
 
-    def __init__(self, W, H, max_visits, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5, free_prop=0.8):
+    def __init__(self, W, H, max_visits, cpuct=1.0, fpu=0.2, root_fpu=0.2, graph=True, bias_factor=0.0, bias_exponent=0.5, free_prop=0.8, **extra):
         self.P = 4 * W * H
-        sp = SearchParams(max_visits, 0, 0, 0, 1, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent, free_prop)
+        sp = _with_extras(SearchParams(max_visits, 0, 0, 0, 1, int(graph), cpuct, fpu, root_fpu, bias_factor, bias_exponent, free_prop), extra)
         self._s = lib().ko_graph_search_create(W, H, C.byref(sp))
 
     def __del__(self):

@@ -254,7 +254,100 @@ double biasPow(double x, double e) {
 }
 
 typedef std::pair<uint64_t, uint64_t> Key;
+// Root policy temperature and shaped Dirichlet noise (Search::maybeAddPolicyNoiseAndTemp / addDirichletNoise /
+// computeDirichletAlphaDistribution, cpp/search/searchhelpers.cpp:51-221; Rand::nextGamma / nextGaussian / nextDouble,
+// cpp/core/rand.cpp:335-363, rand.h:235-288) with the two things that cannot be shared with a GPU replaced: the generator is
+// a counter-based splitmix64 stream keyed by (seed, game id, ply), and log / exp / pow are detLog / detExp.
+constexpr uint64_t NOISE_SALT = 0xD1A1C4137E5EEDULL;
+struct DetRng {
+  uint64_t s; bool hasG = false; double g = 0.0;
+  DetRng(uint64_t seed, uint64_t gameId, int ply) : s(ko_splitmix64(seed ^ (gameId * PHI) ^ (uint64_t)ply ^ NOISE_SALT)) {}
+  uint64_t nextU64() { s += PHI; return ko_splitmix64(s); }
+  double nextDouble() { return (double)(nextU64() & ((1ULL << 53) - 1ULL)) * (1.0 / 9007199254740992.0); }
+  double nextGaussian() {
+    if(hasG) { hasG = false; return g; }
+    double v1, v2, q;
+    do {
+      v1 = nextDouble() * 2.0 - 1.0;
+      v2 = nextDouble() * 2.0 - 1.0;
+      q = v1 * v1 + v2 * v2;
+    } while(q >= 1.0 || q == 0.0);
+    const double mult = std::sqrt((-2.0 * detLog(q)) / q);
+    g = v2 * mult; hasG = true;
+    return v1 * mult;
+  }
+  double nextGamma(double a) {
+    if(a <= 1.0) {
+      const double r = nextGamma(a + 1.0);
+      const double inva = 1.0 / a;
+      const double u = nextDouble();
+      const double scale = u == 0.0 ? 0.0 : detExp(inva * detLog(u));
+      return r * scale;
+    }
+    const double d = a - 1.0 / 3.0;
+    const double c = (1.0 / 3.0) / std::sqrt(d);
+    while(true) {
+      const double x = nextGaussian();
+      const double vtmp = 1.0 + c * x;
+      if(vtmp <= 0.0) continue;
+      const double v = (vtmp * vtmp) * vtmp;
+      const double u = nextDouble();
+      const double xx = x * x;
+      if(u < 1.0 - (0.0331 * xx) * xx) return d * v;
+      if(u == 0.0 || detLog(u) < 0.5 * xx + d * ((1.0 - v) + detLog(v))) return d * v;
+    }
+  }
+};
+
+// in place on the root's policy (illegal = negative entries stay as they are)
+void rootPolicyNoiseAndTemp(const ko_search_params* p, int P, int boardArea, int turn, uint64_t seed, uint64_t gameId, float* pol) {
+  const double tEarly = p->rootPolicyTemperatureEarly > 0.0 ? p->rootPolicyTemperatureEarly : 1.0;
+  const double tLate = p->rootPolicyTemperature > 0.0 ? p->rootPolicyTemperature : 1.0;
+  if(tEarly != 1.0 || tLate != 1.0) {
+    const double halflife = p->chosenMoveTemperatureHalflife > 0.0 ? p->chosenMoveTemperatureHalflife : 19.0;
+    const double halflives = (((double)turn / halflife) * 19.0) / std::sqrt((double)boardArea);     // interpolateEarly :463-467
+    const double T = tLate + (tEarly - tLate) * detExp(halflives * detLog(0.5));
+    double maxValue = 0.0;
+    for(int i = 0; i < P; i++) if((double)pol[i] > maxValue) maxValue = (double)pol[i];
+    if(maxValue > 0.0) {
+      const double logMax = detLog(maxValue), invTemp = 1.0 / T;
+      double sum = 0.0;
+      for(int i = 0; i < P; i++)
+        if(pol[i] > 0) { const float q = (float)detExp((detLog((double)pol[i]) - logMax) * invTemp); pol[i] = q; sum += (double)q; }
+      for(int i = 0; i < P; i++) if(pol[i] >= 0) pol[i] = (float)((double)pol[i] / sum);
+    }
+  }
+  if(p->rootNoiseEnabled) {
+    std::vector<double> r(P, 0.0);
+    int legalCount = 0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0) legalCount++;
+    if(legalCount == 0) return;
+    double logSum = 0.0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0) { r[i] = detLog(std::min(0.01, (double)pol[i]) + 1e-20); logSum += r[i]; }
+    const double logMean = logSum / (double)legalCount;
+    double alphaPropSum = 0.0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0) { r[i] = std::max(0.0, r[i] - logMean); alphaPropSum += r[i]; }
+    const double uniformProb = 1.0 / (double)legalCount;
+    for(int i = 0; i < P; i++)
+      if(pol[i] >= 0) r[i] = alphaPropSum <= 0.0 ? uniformProb : 0.5 * (r[i] / alphaPropSum + uniformProb);
+    DetRng rng(seed, gameId, turn);
+    double rSum = 0.0;
+    for(int i = 0; i < P; i++) {
+      if(pol[i] >= 0) { r[i] = rng.nextGamma(r[i] * p->rootDirichletNoiseTotalConcentration); rSum += r[i]; }
+      else r[i] = 0.0;
+    }
+    const double w = p->rootDirichletNoiseWeight;
+    for(int i = 0; i < P; i++)
+      if(pol[i] >= 0) pol[i] = (float)((r[i] / rSum) * w + (double)pol[i] * (1.0 - w));
+  }
+}
+bool wantsRootPolicyChange(const ko_search_params* p) {
+  return p->rootNoiseEnabled || (p->rootPolicyTemperature > 0.0 && p->rootPolicyTemperature != 1.0) ||
+         (p->rootPolicyTemperatureEarly > 0.0 && p->rootPolicyTemperatureEarly != 1.0);
+}
+
 struct GNode {
+  bool noised = false;
   int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1, depth = 0;
   double weightSum = 0.0, utilityAvg = 0.0, nnUtility = 0.0, lastDelta = 0.0, lastWeight = 0.0;
   Key key = Key(0, 0);
@@ -272,6 +365,13 @@ struct GraphSearch {
   std::map<Key, int> table;       // transposition key -> node
   std::map<Key, int> biasIndex;   // bias key -> entry
   std::vector<BiasEntry> bias;
+  uint64_t seed = 0, gameId = 0;  // key the root noise stream
+
+  void maybeNoiseRoot(const ko_game* rootGame) {
+    if(nodes.empty() || nodes[0].noised) return;
+    nodes[0].noised = true;
+    if(wantsRootPolicyChange(p)) rootPolicyNoiseAndTemp(p, P, W * H, ko_game_num_turns(rootGame), seed, gameId, nodes[0].policy.data());
+  }
 
   static Key stateKey(const ko_game* g) {
     uint64_t h[2];
@@ -361,7 +461,7 @@ struct GraphSearch {
         E.deltaSum = E.deltaSum - nodes[i].lastDelta * p->subtreeValueBiasFreeProp;
         E.weightSum = E.weightSum - nodes[i].lastWeight * p->subtreeValueBiasFreeProp;
       }
-    out[0].biasEntry = -1; out[0].lastDelta = 0.0; out[0].lastWeight = 0.0;
+    out[0].biasEntry = -1; out[0].lastDelta = 0.0; out[0].lastWeight = 0.0; out[0].noised = false;
     std::vector<BiasEntry> nbias;
     std::map<Key, int> nindex, ntable;
     for(size_t i = 1; i < out.size(); i++) {
@@ -424,6 +524,7 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
   ko_game* before = ko_game_create(x_size, y_size, 4);
   std::vector<float> pol(P);
   float wl[2];
+  if(!ko_game_finished(rootGame)) S.maybeNoiseRoot(rootGame);
   for(int it = 0; it < p->maxVisits && !ko_game_finished(rootGame); it++) {
     ko_game_copy(g, rootGame);
     std::vector<std::pair<int, int>> path;
@@ -448,8 +549,15 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
           }
         const double total = butterfly(partT), mass = butterfly(partM);
         const double parentUtility = nd.utilityAvg;
+        double parentUtilityForFPU = parentUtility;
+        if(p->fpuParentWeightByVisitedPolicy) {   // searchexplorehelpers.cpp:279-282
+          const double pw = p->fpuParentWeightByVisitedPolicyPow;
+          const double raised = mass <= 0.0 ? 0.0 : pw == 1.0 ? mass : pw == 2.0 ? mass * mass : detExp(pw * detLog(mass));
+          const double avgWeight = std::min(1.0, raised);
+          parentUtilityForFPU = avgWeight * parentUtility + (1.0 - avgWeight) * nd.nnUtility;
+        }
         const double red = (depth == 0 ? p->rootFpuReductionMax : p->fpuReductionMax) * std::sqrt(mass);
-        const double fpu = pla == 2 ? parentUtility - red : parentUtility + red;
+        const double fpu = pla == 2 ? parentUtilityForFPU - red : parentUtilityForFPU + red;
         const double scale = p->cpuctExploration * std::sqrt(total + 0.01);
         double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
         float newP = -1.0f; int newPos = -1;
@@ -459,7 +567,10 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
             int cv; double cw, cu;
             S.childStats(nd, pos, cv, cw, cu);
             const double w = GraphSearch::childWeight(cw, nd.edgeN[pos], cv);
-            const double val = (scale * (double)pr) / (1.0 + w) + (pla == 2 ? cu : -cu);
+            double val = (scale * (double)pr) / (1.0 + w) + (pla == 2 ? cu : -cu);
+            // rootDesiredPerChildVisitsCoeff: funnel visits into under-visited root children (searchexplorehelpers.cpp:150-155)
+            if(depth == 0 && p->rootDesiredPerChildVisitsCoeff > 0.0 && pr > 0 &&
+               w < std::sqrt(((double)pr * total) * p->rootDesiredPerChildVisitsCoeff)) val = 1e20;
             const int o = nd.order[pos];
             if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
           } else if(pr >= 0.0f) {
@@ -519,6 +630,7 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
       }
       nn.utilityAvg = utility;
       if(kind == 1 && p->useGraphSearch) S.table[leafKey] = newIdx;
+      if(kind == 4) S.maybeNoiseRoot(rootGame);
     }
     for(int d = (int)path.size() - 1; d >= 0; d--) {
       GNode& nd = S.nodes[path[d].first];
@@ -558,6 +670,7 @@ void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const 
                          int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                          uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
   GraphSearch S{x_size, y_size, 4 * x_size * y_size, p, {}, {}, {}, {}};
+  S.seed = p->noiseSeed; S.gameId = p->noiseGameId;
   graphRun(S, rootGame, x_size, y_size, p, modelOrNull, rootVisits, rootUtilitySum, edgeVisits, edgeUtilitySum, policyOut, orderOut, counters, digest);
 }
 
@@ -567,6 +680,7 @@ struct ko_graph_search { GraphSearch S; ko_search_params params; };
 ko_graph_search* ko_graph_search_create(int x_size, int y_size, const ko_search_params* p) {
   ko_graph_search* s = new ko_graph_search{GraphSearch{x_size, y_size, 4 * x_size * y_size, nullptr, {}, {}, {}, {}}, *p};
   s->S.p = &s->params;
+  s->S.seed = p->noiseSeed; s->S.gameId = p->noiseGameId;
   return s;
 }
 void ko_graph_search_destroy(ko_graph_search* s) { delete s; }
