@@ -284,6 +284,19 @@ typedef struct {
   double subtreeValueBiasWeightExponent;  /* SearchParams::subtreeValueBiasWeightExponent (0.5 default, selfplay1.cfg:181 0.8) */
   double subtreeValueBiasFreeProp;        /* SearchParams::subtreeValueBiasFreeProp (0.8): share of a dropped node's contribution
                                              given back to its entry when the tree is re-used */
+  /* Further SearchParams of the self-play configuration (cpp/configs/training/selfplay1.cfg:144-185); zero = off.  Any of them
+   * (like useGraphSearch and the bias) selects the graph mode of the search. */
+  int32_t rootNoiseEnabled;               /* shaped Dirichlet noise on the root policy (searchhelpers.cpp:51-120), drawn from a
+                                             counter-based stream keyed by (kc_search_reset's seed, game id, ply) */
+  int32_t fpuParentWeightByVisitedPolicy; /* FPU base = avgWeight * utilityAvg + (1 - avgWeight) * own evaluation, avgWeight =
+                                             min(1, visitedPolicyMass ^ Pow) (searchexplorehelpers.cpp:279-282) */
+  double rootDirichletNoiseTotalConcentration; /* 10.83 */
+  double rootDirichletNoiseWeight;             /* 0.25 */
+  double rootPolicyTemperature;           /* root policy ^ (1/T), T interpolated from ...Early by 0.5 ^ (turn / halflife * 19 / sqrt(area)) */
+  double rootPolicyTemperatureEarly;      /* (searchhelpers.cpp:143-175, 463-467); 0 or 1 = off */
+  double chosenMoveTemperatureHalflife;   /* 19 */
+  double fpuParentWeightByVisitedPolicyPow;    /* 2.0 in selfplay1.cfg:185 */
+  double rootDesiredPerChildVisitsCoeff;  /* a root child with weight < sqrt(prior * totalChildWeight * coeff) is searched first (2 in selfplay1.cfg:147) */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

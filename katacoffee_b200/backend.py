@@ -295,11 +295,18 @@ class Search:
 
     def __init__(self, ctx, handle, numGames, xSize=5, ySize=5, winLen=4, maxVisits=800, temperaturePlies=0, autoRefill=False,
                  cpuctExploration=1.0, fpuReductionMax=0.2, rootFpuReductionMax=0.2, noCompaction=False, reuseTree=False,
-                 useGraphSearch=False, subtreeValueBiasFactor=0.0, subtreeValueBiasWeightExponent=0.5, subtreeValueBiasFreeProp=0.8):
+                 useGraphSearch=False, subtreeValueBiasFactor=0.0, subtreeValueBiasWeightExponent=0.5, subtreeValueBiasFreeProp=0.8, **options):
+        """options: further kc_search_params fields by name (rootNoiseEnabled, rootDirichletNoiseTotalConcentration,
+        rootDirichletNoiseWeight, rootPolicyTemperature[Early], chosenMoveTemperatureHalflife, fpuParentWeightByVisitedPolicy[Pow],
+        rootDesiredPerChildVisitsCoeff)."""
         self.ctx, self.G, self.W, self.H = ctx, numGames, xSize, ySize
         self.P = 4 * xSize * ySize
         self.params = capi.SearchParams(maxVisits, temperaturePlies, int(autoRefill), int(noCompaction), int(reuseTree), int(useGraphSearch), cpuctExploration, fpuReductionMax, rootFpuReductionMax,
                                         subtreeValueBiasFactor, subtreeValueBiasWeightExponent, subtreeValueBiasFreeProp)
+        for k, v in options.items():
+            if k not in dict(capi.SearchParams._fields_):
+                raise TypeError(f"unknown search option {k}")
+            setattr(self.params, k, v)
         self._p = C.c_void_p()
         check(lib().kc_search_create(ctx._p, handle._p if handle is not None else None, numGames, xSize, ySize, winLen,
                                      C.byref(self.params), C.byref(self._p)))

@@ -60,7 +60,11 @@ class Stats(C.Structure):
 class SearchParams(C.Structure):
     _fields_ = [("maxVisits", C.c_int32), ("temperaturePlies", C.c_int32), ("autoRefill", C.c_int32), ("noCompaction", C.c_int32), ("reuseTree", C.c_int32), ("useGraphSearch", C.c_int32),
                 ("cpuctExploration", C.c_double), ("fpuReductionMax", C.c_double), ("rootFpuReductionMax", C.c_double),
-                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double), ("subtreeValueBiasFreeProp", C.c_double)]
+                ("subtreeValueBiasFactor", C.c_double), ("subtreeValueBiasWeightExponent", C.c_double), ("subtreeValueBiasFreeProp", C.c_double),
+                ("rootNoiseEnabled", C.c_int32), ("fpuParentWeightByVisitedPolicy", C.c_int32),
+                ("rootDirichletNoiseTotalConcentration", C.c_double), ("rootDirichletNoiseWeight", C.c_double),
+                ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
+                ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double)]
 
 
 class SearchStats(C.Structure):

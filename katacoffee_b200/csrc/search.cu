@@ -55,6 +55,9 @@ struct SearchCfg {
   int tableCap;      // graph mode: slots of the per-game transposition and bias tables (power of two, >= 2 * maxNodes)
   double cpuct, fpuRed, rootFpuRed;
   double biasFactor, biasExp, biasFreeProp;   // SearchParams::subtreeValueBiasFactor / WeightExponent / FreeProp
+  // graph mode options (SearchParams of the same names; 0 / 1.0 = off)
+  int rootNoise, fpuPW;
+  double noiseConc, noiseWeight, rootTemp, rootTempEarly, tempHalflife, fpuPWPow, rootDesired;
   uint64_t seed;
 };
 
@@ -108,7 +111,7 @@ struct TrainMem {
 // node layout, tree mode:  header { int N; int numChildren; int nextPla; int pad; double W; double pad } | edgeW[P] f64 |
 //                           policy[P] f32 | child[P] i32 | edgeN[P] i32 | order[P] u8            (polOff = 32 + 8 P)
 //              graph mode: header { int visits; int numChildren; int nextPla; int biasEntry; double weightSum, utilityAvg,
-//                           nnUtility, lastBiasDeltaSum, lastBiasWeight; int depth (stones on the board), pad;
+//                           nnUtility, lastBiasDeltaSum, lastBiasWeight; int depth (stones on the board), noised;
 //                           uint64 key[2] (transposition key) } | policy | child | edgeN | order          (polOff = 80)
 struct NodeRef {
   uint8_t* base; int P; int polOff;
@@ -129,6 +132,7 @@ struct NodeRef {
   __device__ __forceinline__ double& lastDelta() const { return *reinterpret_cast<double*>(base + 40); }
   __device__ __forceinline__ double& lastWeight() const { return *reinterpret_cast<double*>(base + 48); }
   __device__ __forceinline__ int& depth() const { return *reinterpret_cast<int*>(base + 56); }
+  __device__ __forceinline__ int& noised() const { return *reinterpret_cast<int*>(base + 60); }   // root policy already noised / tempered
   __device__ __forceinline__ uint64_t* key() const { return reinterpret_cast<uint64_t*>(base + 64); }
 };
 // child codes: -1 none, >= 0 node index, -2 terminal draw, -3 terminal black win, -4 terminal white win
@@ -356,6 +360,7 @@ __device__ __forceinline__ double detLog(double x) {
   return __dadd_rn(__dmul_rn((double)k, 0.69314718055994531), __dmul_rn(__dmul_rn(2.0, z), s));
 }
 __device__ __forceinline__ double detExp(double y) {
+  if(y < -700.0) return 0.0;   // below the normal range of the 2^n scaling
   const double n = rint(__dmul_rn(y, 1.4426950408889634));
   const double r = __dsub_rn(__dsub_rn(y, __dmul_rn(n, 0.693147180369123816490)), __dmul_rn(n, 1.90821492927058770002e-10));
   double s = __ddiv_rn(1.0, 6227020800.0);
@@ -418,8 +423,14 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
       }
       total = warpSumD(total);
       mass = warpSumD(mass);
+      double parentUtilityForFPU = parentUtility;
+      if(c.fpuPW) {   // fpuParentWeightByVisitedPolicy (searchexplorehelpers.cpp:279-282)
+        const double raised = mass <= 0.0 ? 0.0 : c.fpuPWPow == 1.0 ? mass : c.fpuPWPow == 2.0 ? __dmul_rn(mass, mass) : detExp(__dmul_rn(c.fpuPWPow, detLog(mass)));
+        const double avgWeight = fmin(1.0, raised);
+        parentUtilityForFPU = __dadd_rn(__dmul_rn(avgWeight, parentUtility), __dmul_rn(__dsub_rn(1.0, avgWeight), nd.nnUtility()));
+      }
       const double red = __dmul_rn(depth == 0 ? c.rootFpuRed : c.fpuRed, __dsqrt_rn(mass));
-      const double fpu = pla == 2 ? __dsub_rn(parentUtility, red) : __dadd_rn(parentUtility, red);
+      const double fpu = pla == 2 ? __dsub_rn(parentUtilityForFPU, red) : __dadd_rn(parentUtilityForFPU, red);
       const double scale = __dmul_rn(c.cpuct, __dsqrt_rn(__dadd_rn(total, 0.01)));
       double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
       float newP = -1.0f; int newPos = -1;
@@ -430,7 +441,9 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
           int cv; double cw, cu;
           childStats(c, treeBase, cc, eN[pos], cv, cw, cu);
           const double w = childWeightOf(cw, eN[pos], cv);
-          const double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, w)), pla == 2 ? cu : -cu);
+          double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, w)), pla == 2 ? cu : -cu);
+          // rootDesiredPerChildVisitsCoeff (searchexplorehelpers.cpp:150-155)
+          if(depth == 0 && c.rootDesired > 0.0 && p > 0.0f && w < __dsqrt_rn(__dmul_rn(__dmul_rn((double)p, total), c.rootDesired))) val = 1e20;
           const int o = ord[pos];
           if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
         } else if(p >= 0.0f) {
@@ -604,7 +617,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       }
       nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi] & 0xff; nd.biasEntry() = be;
       nd.weightSum() = 1.0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
-      nd.depth() = t.leafNextPla[gi] >> 8;
+      nd.depth() = t.leafNextPla[gi] >> 8; nd.noised() = 0;
       nd.key()[0] = kind == 1 ? t.leafKey[2 * (size_t)gi] : 0; nd.key()[1] = kind == 1 ? t.leafKey[2 * (size_t)gi + 1] : 0;
       t.nodeCount[gi] = newIdx + 1;
       if(kind == 1 && c.useTable) {
@@ -638,6 +651,107 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
   else if(kind == 2 || kind == 3) atomicAdd(&t.stats[2], 1ULL);
   else if(kind == 6) atomicAdd(&t.stats[8], 1ULL);
   else atomicAdd(&t.stats[9], 1ULL);
+}
+
+// Root policy temperature and shaped Dirichlet noise: Search::maybeAddPolicyNoiseAndTemp / addDirichletNoise /
+// computeDirichletAlphaDistribution (cpp/search/searchhelpers.cpp:51-221) with Rand::nextGamma / nextGaussian / nextDouble
+// (cpp/core/rand.cpp:335-363, rand.h:235-288).  Two things cannot be shared between a CPU and a GPU and are replaced: the
+// generator is a counter-based splitmix64 stream keyed by (seed, game id, ply), and log / exp / pow are detLog / detExp; the
+// oracle computes the same bits.  One thread per game, once per search, in place on the root's priors (the reference keeps
+// a separate noisedPolicyProbs; nothing else reads the root's raw policy afterwards).
+constexpr uint64_t NOISE_SALT = 0xD1A1C4137E5EEDULL;
+struct DetRng {
+  uint64_t s; bool hasG; double g;
+  __device__ DetRng(uint64_t seed, uint64_t gameId, int ply) : s(splitmix64(seed ^ (gameId * PHI) ^ (uint64_t)ply ^ NOISE_SALT)), hasG(false), g(0.0) {}
+  __device__ uint64_t nextU64() { s += PHI; return splitmix64(s); }
+  __device__ double nextDouble() { return __dmul_rn((double)(nextU64() & ((1ULL << 53) - 1ULL)), 1.0 / 9007199254740992.0); }
+  __device__ double nextGaussian() {
+    if(hasG) { hasG = false; return g; }
+    double v1, v2, q;
+    do {
+      v1 = __dsub_rn(__dmul_rn(nextDouble(), 2.0), 1.0);
+      v2 = __dsub_rn(__dmul_rn(nextDouble(), 2.0), 1.0);
+      q = __dadd_rn(__dmul_rn(v1, v1), __dmul_rn(v2, v2));
+    } while(q >= 1.0 || q == 0.0);
+    const double mult = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, detLog(q)), q));
+    g = __dmul_rn(v2, mult); hasG = true;
+    return __dmul_rn(v1, mult);
+  }
+  __device__ double gammaAbove1(double a) {   // Marsaglia-Tsang, a > 1
+    const double d = __dsub_rn(a, 1.0 / 3.0);
+    const double c = __ddiv_rn(1.0 / 3.0, __dsqrt_rn(d));
+    while(true) {
+      const double x = nextGaussian();
+      const double vtmp = __dadd_rn(1.0, __dmul_rn(c, x));
+      if(vtmp <= 0.0) continue;
+      const double v = __dmul_rn(__dmul_rn(vtmp, vtmp), vtmp);
+      const double u = nextDouble();
+      const double xx = __dmul_rn(x, x);
+      if(u < __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.0331, xx), xx))) return __dmul_rn(d, v);
+      if(u == 0.0 || detLog(u) < __dadd_rn(__dmul_rn(0.5, xx), __dmul_rn(d, __dadd_rn(__dsub_rn(1.0, v), detLog(v))))) return __dmul_rn(d, v);
+    }
+  }
+  __device__ double nextGamma(double a) {
+    if(a > 1.0) return gammaAbove1(a);
+    const double r = gammaAbove1(__dadd_rn(a, 1.0));
+    const double inva = __ddiv_rn(1.0, a);
+    const double u = nextDouble();
+    const double scale = u == 0.0 ? 0.0 : detExp(__dmul_rn(inva, detLog(u)));
+    return __dmul_rn(r, scale);
+  }
+};
+constexpr int MAX_POLICY = 4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN;
+
+__global__ void __launch_bounds__(64) k_root_noise(const SearchCfg c, TreeMem t, State root, int boardArea) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if(gi >= c.numGames) return;
+  if(t.nodeCount[gi] <= 0 || (flagsOf(root.misc[gi]) & 1)) return;
+  NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P, c.polOff};
+  if(nd.noised()) return;
+  nd.noised() = 1;
+  float* pol = nd.policy();
+  const int P = c.P, turn = numTurnsOf(root.misc[gi]);
+  const double tEarly = c.rootTempEarly > 0.0 ? c.rootTempEarly : 1.0, tLate = c.rootTemp > 0.0 ? c.rootTemp : 1.0;
+  if(tEarly != 1.0 || tLate != 1.0) {
+    const double halflife = c.tempHalflife > 0.0 ? c.tempHalflife : 19.0;
+    const double halflives = __ddiv_rn(__dmul_rn(__ddiv_rn((double)turn, halflife), 19.0), __dsqrt_rn((double)boardArea));
+    const double T = __dadd_rn(tLate, __dmul_rn(__dsub_rn(tEarly, tLate), detExp(__dmul_rn(halflives, detLog(0.5)))));
+    double maxValue = 0.0;
+    for(int i = 0; i < P; i++) if((double)pol[i] > maxValue) maxValue = (double)pol[i];
+    if(maxValue > 0.0) {
+      const double logMax = detLog(maxValue), invTemp = __ddiv_rn(1.0, T);
+      double sum = 0.0;
+      for(int i = 0; i < P; i++)
+        if(pol[i] > 0.0f) {
+          const float q = __double2float_rn(detExp(__dmul_rn(__dsub_rn(detLog((double)pol[i]), logMax), invTemp)));
+          pol[i] = q; sum = __dadd_rn(sum, (double)q);
+        }
+      for(int i = 0; i < P; i++) if(pol[i] >= 0.0f) pol[i] = __double2float_rn(__ddiv_rn((double)pol[i], sum));
+    }
+  }
+  if(c.rootNoise) {
+    double r[MAX_POLICY];
+    int legalCount = 0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0.0f) legalCount++;
+    if(legalCount == 0) return;
+    double logSum = 0.0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0.0f) { r[i] = detLog(__dadd_rn(fmin(0.01, (double)pol[i]), 1e-20)); logSum = __dadd_rn(logSum, r[i]); }
+    const double logMean = __ddiv_rn(logSum, (double)legalCount);
+    double alphaPropSum = 0.0;
+    for(int i = 0; i < P; i++) if(pol[i] >= 0.0f) { r[i] = fmax(0.0, __dsub_rn(r[i], logMean)); alphaPropSum = __dadd_rn(alphaPropSum, r[i]); }
+    const double uniformProb = __ddiv_rn(1.0, (double)legalCount);
+    for(int i = 0; i < P; i++)
+      if(pol[i] >= 0.0f) r[i] = alphaPropSum <= 0.0 ? uniformProb : __dmul_rn(0.5, __dadd_rn(__ddiv_rn(r[i], alphaPropSum), uniformProb));
+    DetRng rng(c.seed, root.gameId[gi], turn);
+    double rSum = 0.0;
+    for(int i = 0; i < P; i++) {
+      if(pol[i] >= 0.0f) { r[i] = rng.nextGamma(__dmul_rn(r[i], c.noiseConc)); rSum = __dadd_rn(rSum, r[i]); }
+      else r[i] = 0.0;
+    }
+    const double w = c.noiseWeight;
+    for(int i = 0; i < P; i++)
+      if(pol[i] >= 0.0f) pol[i] = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn(r[i], rSum), w), __dmul_rn((double)pol[i], __dsub_rn(1.0, w))));
+  }
 }
 
 // Tree re-use in graph mode: Search::makeMove (cpp/search/search.cpp:262-331) followed by the next beginSearch's
@@ -1066,7 +1180,11 @@ int runVisits(kc_search* S) {
   kc_games* R = S->root; kc_games* Lf = S->leaf;
   cudaStream_t st = Lf->stream;
   const int warpBlocks = (c.numGames * 32 + 127) / 128;
+  const bool rootPolicyChange = c.graph && (c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0));
   for(int it = 0; it < c.maxVisits; it++) {
+    // root noise / temperature: once per search, on roots kept by tree re-use (before the first descent) and on roots created by
+    // the first iteration (before the second)
+    if(rootPolicyChange && it <= 1) { k_root_noise<<<(c.numGames + 63) / 64, 64, 0, st>>>(c, S->tree, R->st, R->geom.HW); S->launches++; }
     if(c.reuseTree && it > 0 && (it & 31) == 0) {
       // games that kept a subtree finish their visit budget early: stop once no game had a visit left to make
       int active = 0;
@@ -1107,6 +1225,9 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->maxVisits >= 1 && p->maxVisits <= 65536, "kc_search_create: maxVisits must be within 1..65536");
   KC_CHECK(p->cpuctExploration > 0 && p->fpuReductionMax >= 0 && p->rootFpuReductionMax >= 0, "kc_search_create: bad exploration parameters");
   KC_CHECK(p->subtreeValueBiasFreeProp >= 0.0 && p->subtreeValueBiasFreeProp <= 1.0, "kc_search_create: subtreeValueBiasFreeProp must be within 0..1");
+  KC_CHECK(!p->rootNoiseEnabled || (p->rootDirichletNoiseTotalConcentration > 0.0 && p->rootDirichletNoiseWeight >= 0.0 && p->rootDirichletNoiseWeight <= 1.0),
+           "kc_search_create: root noise needs rootDirichletNoiseTotalConcentration > 0 and a weight within 0..1");
+  KC_CHECK(p->rootPolicyTemperature >= 0.0 && p->rootPolicyTemperatureEarly >= 0.0 && p->rootDesiredPerChildVisitsCoeff >= 0.0, "kc_search_create: negative root option");
   KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
@@ -1115,7 +1236,13 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   if(handleOrNull && kc::handleCheckGeometry(handleOrNull, xSize, ySize, numGames)) { kc_games_destroy(S->root); kc_games_destroy(S->leaf); delete S; return 1; }
   SearchCfg& c = S->cfg;
   c.P = 4 * xSize * ySize; c.LW = (c.P + 31) / 32;
-  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0) ? 1 : 0;
+  c.rootNoise = p->rootNoiseEnabled ? 1 : 0; c.fpuPW = p->fpuParentWeightByVisitedPolicy ? 1 : 0;
+  c.noiseConc = p->rootDirichletNoiseTotalConcentration; c.noiseWeight = p->rootDirichletNoiseWeight;
+  c.rootTemp = p->rootPolicyTemperature; c.rootTempEarly = p->rootPolicyTemperatureEarly; c.tempHalflife = p->chosenMoveTemperatureHalflife;
+  c.fpuPWPow = p->fpuParentWeightByVisitedPolicyPow > 0.0 ? p->fpuParentWeightByVisitedPolicyPow : 1.0; c.rootDesired = p->rootDesiredPerChildVisitsCoeff;
+  const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);
+  // every option beyond plain PUCT runs on the node-centric statistics of graph mode
+  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0) ? 1 : 0;
   c.useTable = p->useGraphSearch ? 1 : 0;
   c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent; c.biasFreeProp = p->subtreeValueBiasFreeProp;
   c.polOff = c.graph ? 80 : 32 + 8 * c.P;

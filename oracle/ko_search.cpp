@@ -237,6 +237,7 @@ double detLog(double x) {
   return (double)k * 0.69314718055994531 + (2.0 * z) * s;
 }
 double detExp(double y) {
+  if(y < -700.0) return 0.0;   // below the normal range of the 2^n scaling
   const double n = std::nearbyint(y * 1.4426950408889634);
   const double r = (y - n * 0.693147180369123816490) - n * 1.90821492927058770002e-10;
   double s = 1.0 / 6227020800.0;                                 // 1/13!

@@ -711,6 +711,86 @@ def test_search_graph_and_value_bias_bit_exact(ctx, oracle, W, H, K, G, V, graph
     s.close()
 
 
+SELFPLAY1_CFG = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1,
+                     rootPolicyTemperatureEarly=1.25, chosenMoveTemperatureHalflife=19.0, fpuParentWeightByVisitedPolicy=1,
+                     fpuParentWeightByVisitedPolicyPow=2.0, rootDesiredPerChildVisitsCoeff=2.0)   # cpp/configs/training/selfplay1.cfg:144-185
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,K,G,V,opts", [
+    (5, 5, 4, 128, 160, SELFPLAY1_CFG),
+    (6, 6, 4, 40, 100, SELFPLAY1_CFG),
+    (5, 5, 4, 64, 120, dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=3.0, rootDirichletNoiseWeight=0.5)),   # gamma shapes below 1
+    (5, 5, 4, 64, 120, dict(rootPolicyTemperature=0.8, rootPolicyTemperatureEarly=1.5, chosenMoveTemperatureHalflife=7.0)),
+    (5, 5, 4, 64, 120, dict(fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=1.5, rootDesiredPerChildVisitsCoeff=1.0))])
+def test_search_selfplay_options_bit_exact(ctx, oracle, W, H, K, G, V, opts):
+    """The self-play configuration's remaining search options -- shaped Dirichlet root noise (deterministic gamma sampler), root
+    policy temperature, FPU parent weighting by visited policy, rootDesiredPerChildVisitsCoeff -- on top of graph search and the
+    value bias: the noised root priors and the whole graph equal the oracle's bit for bit."""
+    from katacoffee_b200 import backend
+    seed = 123
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8,
+                       cpuctExploration=1.1, rootFpuReductionMax=0.0, **opts)
+    s.reset(seed=seed, firstGameId=40)
+    plies = np.array([g % 14 for g in range(G)])
+    ogames = _advance_device_like_oracle(oracle, s, W, H, K, seed, plies)
+    s.runVisits()
+    got = s.readRoot()
+    dig = s.treeDigest()
+    changed = 0
+    for g in range(G):
+        if ogames[g].finished():
+            continue
+        ref = oracle.search_run_graph(ogames[g], V, graph=True, bias_factor=0.3, bias_exponent=0.8, cpuct=1.1, root_fpu=0.0, noiseSeed=seed,
+                                      noiseGameId=40 + g, **opts)
+        plain = oracle.search_run_graph(ogames[g], 1)["policy"]
+        changed += (plain != ref["policy"]).any()
+        assert (got["policy"][g] == ref["policy"]).all(), (g, np.abs(got["policy"][g] - ref["policy"]).max())
+        assert abs(float(ref["policy"][ref["policy"] >= 0].sum()) - 1.0) < 1e-5
+        assert got["rootVisits"][g] == ref["rootVisits"] and (got["edgeVisits"][g] == ref["edgeVisits"]).all(), g
+        assert (got["order"][g] == ref["order"]).all() and got["rootUtilitySum"][g] == ref["rootUtilitySum"], g
+        assert int(dig[g]) == ref["digest"], g
+    if "rootNoiseEnabled" in opts or "rootPolicyTemperature" in opts:
+        assert changed > 0.9 * G
+    s.close()
+
+
+@pytest.mark.gpu
+def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
+    """selfplay1.cfg's search options together with tree re-use, self-played to the end: fresh noise on every new root, moves,
+    counters and the re-rooted graphs equal the oracle's."""
+    from katacoffee_b200 import backend, capi
+    W = H = 5
+    G, V, seed, T = 48, 64, 77, 6
+    s = backend.Search(ctx, None, G, W, H, 4, maxVisits=V, temperaturePlies=T, reuseTree=True, useGraphSearch=True, subtreeValueBiasFactor=0.3,
+                       subtreeValueBiasWeightExponent=0.8, cpuctExploration=1.1, rootFpuReductionMax=0.0, **SELFPLAY1_CFG)
+    s.reset(seed=seed, firstGameId=900)
+    ogames = [oracle.Game(W, H, 4) for _ in range(G)]
+    osearch = [oracle.PersistentGraphSearch(W, H, V, graph=True, bias_factor=0.3, bias_exponent=0.8, free_prop=0.8, cpuct=1.1, root_fpu=0.0,
+                                            noiseSeed=seed, noiseGameId=900 + g, **SELFPLAY1_CFG) for g in range(G)]
+    stats = capi.SearchStats()
+    ocnt = np.zeros(5, np.uint64)
+    for ply in range(W * H):
+        _, chosen, _ = s.play(1, stats)
+        dig = s.treeDigest()
+        for g in range(G):
+            og = ogames[g]
+            if og.finished():
+                assert chosen[g] == -1
+                continue
+            r = osearch[g].run(og)
+            ocnt += r["counters"]
+            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 900 + g)
+            assert chosen[g] == mv, (ply, g, chosen[g], mv)
+            og.play(mv)
+            osearch[g].advance(mv)
+            if not og.finished():
+                assert int(dig[g]) == osearch[g].digest(), (ply, g)
+    assert all(og.finished() for og in ogames)
+    assert (stats.visits, stats.netEvals, stats.terminalVisits, stats.transpositionHits, stats.catchUpVisits) == tuple(int(x) for x in ocnt)
+    s.close()
+
+
 @pytest.mark.gpu
 def test_search_graph_selfplay_counters_match_oracle(ctx, oracle):
     """Self-play with graph search + subtree value bias: moves, results and the visit / evaluation / transposition /
