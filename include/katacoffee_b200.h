@@ -297,6 +297,8 @@ typedef struct {
   double chosenMoveTemperatureHalflife;   /* 19 */
   double fpuParentWeightByVisitedPolicyPow;    /* 2.0 in selfplay1.cfg:185 */
   double rootDesiredPerChildVisitsCoeff;  /* a root child with weight < sqrt(prior * totalChildWeight * coeff) is searched first (2 in selfplay1.cfg:147) */
+  double valueWeightExponent;             /* SearchParams::valueWeightExponent (0.5 in SearchParams() and selfplay1.cfg:179): children
+                                             whose utility is implausibly low next to their siblings count less in the parent */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

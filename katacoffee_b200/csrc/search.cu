@@ -27,6 +27,7 @@
 //  All search arithmetic is IEEE double without fused multiply-add (explicit round-to-nearest intrinsics here,
 //  -ffp-contract=off in the oracle), so trees agree exactly whenever the leaf evaluations agree exactly.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "games.h"
@@ -57,7 +58,7 @@ struct SearchCfg {
   double biasFactor, biasExp, biasFreeProp;   // SearchParams::subtreeValueBiasFactor / WeightExponent / FreeProp
   // graph mode options (SearchParams of the same names; 0 / 1.0 = off)
   int rootNoise, fpuPW;
-  double noiseConc, noiseWeight, rootTemp, rootTempEarly, tempHalflife, fpuPWPow, rootDesired;
+  double noiseConc, noiseWeight, rootTemp, rootTempEarly, tempHalflife, fpuPWPow, rootDesired, vwExp;
   uint64_t seed;
 };
 
@@ -88,6 +89,7 @@ struct TreeMem {
   // graph mode with tree re-use: re-rooting rebuilds the tables into a second set, then the two swap (like nodes / nodesAlt)
   uint64_t* tblKeysAlt; int* tblValsAlt; uint64_t* biasKeysAlt; double* biasValsAlt;
   int* remap;             // [G][maxNodes] old node index -> new index (-1: dropped)
+  const double* tcdf;     // [2000] Student-t (3 degrees of freedom) cdf on [-50, 50] for valueWeightExponent
 };
 constexpr int NUM_STATS = 16;
 
@@ -540,7 +542,9 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
 }
 
 // recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
-__device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, uint8_t* treeBase, NodeRef nd, int lane, int inc) {
+constexpr int MAX_POLICY_SLOTS = 4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN;
+__device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, const double* __restrict__ tcdfTable, uint8_t* treeBase, NodeRef nd,
+                                              int lane, int inc) {
   const int* ch = nd.child(); const int* eN = nd.edgeN();
   double sumW = 0.0, sumWU = 0.0;
   for(int pos = lane; pos < c.P; pos += 32) {
@@ -557,6 +561,52 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
   }
   sumW = warpSumD(sumW);
   sumWU = warpSumD(sumWU);
+  if(c.vwExp != 0.0 && sumW > 0.0) {
+    // valueWeightExponent (downweightBadChildrenAndNormalizeWeight, searchupdatehelpers.cpp:330-417): a child keeps
+    // weight * cdf(z)^exponent, z = its utility's distance from the siblings' weighted mean in standard errors, cdf = Student t
+    // (3 degrees of freedom) from the interpolated 2,000-point table; the total child weight stays what it was
+    const double simpleValue = __ddiv_rn(sumWU, sumW);
+    const int pla = nd.nextPla();
+    double nwl[(MAX_POLICY_SLOTS + 31) / 32];
+    double totalNew = 0.0;
+    int k = 0;
+    for(int pos = lane; pos < c.P; pos += 32, k++) {
+      nwl[k] = 0.0;
+      const int cc = ch[pos];
+      if(cc == -1) continue;
+      int cv; double cw, cu;
+      const int e = eN[pos];
+      childStats(c, treeBase, cc, e, cv, cw, cu);
+      if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
+      const double w = childWeightOf(cw, e, cv);
+      const double stdev = __dsqrt_rn(__dadd_rn(0.00000001, __ddiv_rn(1.0, __dmul_rn(1.5, __dsqrt_rn(w)))));
+      const double diff = pla == 2 ? __dsub_rn(cu, simpleValue) : __dsub_rn(simpleValue, cu);
+      const double z = __ddiv_rn(diff, stdev);
+      const double d = __ddiv_rn(__dmul_rn(1999.0, __dsub_rn(z, -50.0)), 100.0);
+      double cdf;
+      if(d <= 0) cdf = 0.0;
+      else {
+        const int idx = (int)d;
+        if(idx >= 1999) cdf = 1.0;
+        else cdf = __dadd_rn(tcdfTable[idx], __dmul_rn(__dsub_rn(d, (double)idx), __dsub_rn(tcdfTable[idx + 1], tcdfTable[idx])));
+      }
+      const double pr = __dadd_rn(cdf, 0.0001);
+      const double raised = c.vwExp == 0.5 ? __dsqrt_rn(pr) : c.vwExp == 0.25 ? __dsqrt_rn(__dsqrt_rn(pr)) : c.vwExp == 1.0 ? pr : detExp(__dmul_rn(c.vwExp, detLog(pr)));
+      nwl[k] = __dmul_rn(w, raised);
+      totalNew = __dadd_rn(totalNew, nwl[k]);
+    }
+    totalNew = warpSumD(totalNew);
+    const double factor = __ddiv_rn(sumW, totalNew);
+    double part = 0.0;
+    k = 0;
+    for(int pos = lane; pos < c.P; pos += 32, k++)
+      if(nwl[k] != 0.0) {
+        int cv; double cw, cu;
+        childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
+        part = __dadd_rn(part, __dmul_rn(__dmul_rn(nwl[k], factor), cu));
+      }
+    sumWU = warpSumD(part);
+  }
   if(lane == 0) {
     double utility = nd.nnUtility();
     const int be = nd.biasEntry();
@@ -643,7 +693,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
     }
     __syncwarp();
-    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, treeBase, nd, lane, 1);
+    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, treeBase, nd, lane, 1);
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
@@ -872,7 +922,7 @@ __global__ void __launch_bounds__(128) k_reroot_graph(const SearchCfg c, TreeMem
             if(nd.numChildren() == 0) {
               if(lane == 0) nd.utilityAvg() = nd.nnUtility();
               __syncwarp();
-            } else recomputeNode(c, newBiasVals, dst, nd, lane, 0);
+            } else recomputeNode(c, newBiasVals, t.tcdf, dst, nd, lane, 0);
           }
         }
     }
@@ -1227,6 +1277,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->subtreeValueBiasFreeProp >= 0.0 && p->subtreeValueBiasFreeProp <= 1.0, "kc_search_create: subtreeValueBiasFreeProp must be within 0..1");
   KC_CHECK(!p->rootNoiseEnabled || (p->rootDirichletNoiseTotalConcentration > 0.0 && p->rootDirichletNoiseWeight >= 0.0 && p->rootDirichletNoiseWeight <= 1.0),
            "kc_search_create: root noise needs rootDirichletNoiseTotalConcentration > 0 and a weight within 0..1");
+  KC_CHECK(p->valueWeightExponent >= 0.0 && p->valueWeightExponent <= 1.0, "kc_search_create: valueWeightExponent must be within 0..1");
   KC_CHECK(p->rootPolicyTemperature >= 0.0 && p->rootPolicyTemperatureEarly >= 0.0 && p->rootDesiredPerChildVisitsCoeff >= 0.0, "kc_search_create: negative root option");
   KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
   KC_CUDA(cudaSetDevice(ctx->device));
@@ -1240,9 +1291,10 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.noiseConc = p->rootDirichletNoiseTotalConcentration; c.noiseWeight = p->rootDirichletNoiseWeight;
   c.rootTemp = p->rootPolicyTemperature; c.rootTempEarly = p->rootPolicyTemperatureEarly; c.tempHalflife = p->chosenMoveTemperatureHalflife;
   c.fpuPWPow = p->fpuParentWeightByVisitedPolicyPow > 0.0 ? p->fpuParentWeightByVisitedPolicyPow : 1.0; c.rootDesired = p->rootDesiredPerChildVisitsCoeff;
+  c.vwExp = p->valueWeightExponent;
   const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);
   // every option beyond plain PUCT runs on the node-centric statistics of graph mode
-  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0) ? 1 : 0;
+  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0 || c.vwExp != 0.0) ? 1 : 0;
   c.useTable = p->useGraphSearch ? 1 : 0;
   c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent; c.biasFreeProp = p->subtreeValueBiasFreeProp;
   c.polOff = c.graph ? 80 : 32 + 8 * c.P;
@@ -1277,6 +1329,18 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CUDA(cudaMalloc(&S->tree.evalCount, 4)); KC_CUDA(cudaMemset(S->tree.evalCount, 0, 4));
   KC_CUDA(cudaMalloc(&S->tree.stats, NUM_STATS * 8)); KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
   if(c.graph) {
+    {   // DistributionTable of the Student-t cdf, 3 degrees of freedom, closed form (search.cpp:111-116, distributiontable.cpp)
+      std::vector<double> tab(2000);
+      const double PI = 3.14159265358979323846, s3 = std::sqrt(3.0);
+      for(int i = 0; i < 2000; i++) {
+        const double z = -50.0 + (double)i * 100.0 / 1999.0, x = z / s3;
+        tab[i] = i == 0 ? 0.0 : i == 1999 ? 1.0 : 0.5 + (x / (1.0 + x * x) + std::atan(x)) / PI;
+      }
+      double* d = nullptr;
+      KC_CUDA(cudaMalloc(&d, 2000 * 8));
+      KC_CUDA(cudaMemcpy(d, tab.data(), 2000 * 8, cudaMemcpyHostToDevice));
+      S->tree.tcdf = d;
+    }
     const size_t slots = n * c.tableCap;
     KC_CUDA(cudaMalloc(&S->tree.tblKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.tblVals, slots * 4));
     KC_CUDA(cudaMalloc(&S->tree.biasKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.biasVals, slots * 16));
@@ -1305,7 +1369,7 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
   cudaFree(S->tree.nodesAlt); cudaFree(S->tree.rerootQueue); cudaFree(S->tree.active);
   cudaFree(S->tree.tblKeys); cudaFree(S->tree.tblVals); cudaFree(S->tree.biasKeys); cudaFree(S->tree.biasVals);
-  cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget);
+  cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget); cudaFree(const_cast<double*>(S->tree.tcdf));
   cudaFree(S->tree.tblKeysAlt); cudaFree(S->tree.tblValsAlt); cudaFree(S->tree.biasKeysAlt); cudaFree(S->tree.biasValsAlt); cudaFree(S->tree.remap);
   { kc::TrainMem& t = S->train;
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);

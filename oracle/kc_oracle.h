@@ -220,7 +220,7 @@ typedef struct {
   int32_t rootNoiseEnabled, fpuParentWeightByVisitedPolicy;
   double rootDirichletNoiseTotalConcentration, rootDirichletNoiseWeight;
   double rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
-  double fpuParentWeightByVisitedPolicyPow, rootDesiredPerChildVisitsCoeff;
+  double fpuParentWeightByVisitedPolicyPow, rootDesiredPerChildVisitsCoeff, valueWeightExponent;
   uint64_t noiseSeed, noiseGameId;   /* oracle only (one game per call): what kc_search_reset's seed and the game id are on the device */
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,

@@ -347,6 +347,41 @@ bool wantsRootPolicyChange(const ko_search_params* p) {
          (p->rootPolicyTemperatureEarly > 0.0 && p->rootPolicyTemperatureEarly != 1.0);
 }
 
+// valueWeightExponent (downweightBadChildrenAndNormalizeWeight, cpp/search/searchupdatehelpers.cpp:330-417): a child whose
+// utility lies z standard errors below the weighted mean of its siblings keeps weight * cdf(z)^exponent, cdf = Student t with
+// 3 degrees of freedom tabulated at 2,000 points on [-50, 50] and interpolated (DistributionTable, search.cpp:111-116).
+// Canonical: the table is filled from the closed form of the df = 3 cdf (the reference goes through an incomplete beta
+// function); p^exponent is sqrt / sqrt(sqrt) for 0.5 / 0.25, detPow otherwise.
+struct TCdfTable {
+  double cdf[2000];
+  TCdfTable() {
+    const double PI = 3.14159265358979323846, s3 = std::sqrt(3.0);
+    for(int i = 0; i < 2000; i++) {
+      if(i == 0) cdf[i] = 0.0;
+      else if(i == 1999) cdf[i] = 1.0;
+      else {
+        const double z = -50.0 + (double)i * 100.0 / 1999.0, x = z / s3;
+        cdf[i] = 0.5 + (x / (1.0 + x * x) + std::atan(x)) / PI;
+      }
+    }
+  }
+  double get(double z) const {   // DistributionTable::getCdf
+    const double d = (1999.0 * (z - -50.0)) / 100.0;
+    if(d <= 0) return 0.0;
+    const int idx = (int)d;
+    if(idx >= 1999) return 1.0;
+    const double lambda = d - (double)idx;
+    return cdf[idx] + lambda * (cdf[idx + 1] - cdf[idx]);
+  }
+};
+const TCdfTable& tcdf() { static TCdfTable t; return t; }
+double valueWeightPow(double x, double e) {
+  if(e == 0.5) return std::sqrt(x);
+  if(e == 0.25) return std::sqrt(std::sqrt(x));
+  if(e == 1.0) return x;
+  return detExp(e * detLog(x));
+}
+
 struct GNode {
   bool noised = false;
   int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1, depth = 0;
@@ -412,7 +447,36 @@ struct GraphSearch {
         partW[pos & 31] = partW[pos & 31] + w;
         partWU[pos & 31] = partWU[pos & 31] + w * cu;
       }
-    const double sumW = butterfly(partW), sumWU = butterfly(partWU);
+    const double sumW = butterfly(partW);
+    double sumWU = butterfly(partWU);
+    if(p->valueWeightExponent != 0.0 && sumW > 0.0) {
+      // re-weight the children by how plausible their utility is next to their siblings'; the total weight stays sumW
+      const double simpleValue = sumWU / sumW;   // selfUtility is +-utility, handled through the sign below
+      double partN[32] = {0};
+      std::vector<double> nw(P, 0.0);
+      for(int pos = 0; pos < P; pos++)
+        if(nd.child[pos] != -1) {
+          int cv; double cw, cu;
+          childStats(nd, pos, cv, cw, cu);
+          const int e = nd.edgeN[pos];
+          if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
+          const double w = childWeight(cw, e, cv);
+          const double stdev = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt(w)));
+          const double diff = nd.nextPla == 2 ? cu - simpleValue : simpleValue - cu;   // selfUtility - simpleValue (own view)
+          const double pr = tcdf().get(diff / stdev) + 0.0001;
+          nw[pos] = w * valueWeightPow(pr, p->valueWeightExponent);
+          partN[pos & 31] = partN[pos & 31] + nw[pos];
+        }
+      const double factor = sumW / butterfly(partN);
+      double partU[32] = {0};
+      for(int pos = 0; pos < P; pos++)
+        if(nw[pos] != 0.0) {
+          int cv; double cw, cu;
+          childStats(nd, pos, cv, cw, cu);
+          partU[pos & 31] = partU[pos & 31] + (nw[pos] * factor) * cu;
+        }
+      sumWU = butterfly(partU);
+    }
     double utility = nd.nnUtility;
     if(p->subtreeValueBiasFactor != 0.0 && nd.biasEntry >= 0) {
       BiasEntry& E = bias[nd.biasEntry];

@@ -713,7 +713,7 @@ def test_search_graph_and_value_bias_bit_exact(ctx, oracle, W, H, K, G, V, graph
 
 SELFPLAY1_CFG = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1,
                      rootPolicyTemperatureEarly=1.25, chosenMoveTemperatureHalflife=19.0, fpuParentWeightByVisitedPolicy=1,
-                     fpuParentWeightByVisitedPolicyPow=2.0, rootDesiredPerChildVisitsCoeff=2.0)   # cpp/configs/training/selfplay1.cfg:144-185
+                     fpuParentWeightByVisitedPolicyPow=2.0, rootDesiredPerChildVisitsCoeff=2.0, valueWeightExponent=0.5)   # cpp/configs/training/selfplay1.cfg:144-185
 
 
 @pytest.mark.gpu
@@ -722,7 +722,9 @@ SELFPLAY1_CFG = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10
     (6, 6, 4, 40, 100, SELFPLAY1_CFG),
     (5, 5, 4, 64, 120, dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=3.0, rootDirichletNoiseWeight=0.5)),   # gamma shapes below 1
     (5, 5, 4, 64, 120, dict(rootPolicyTemperature=0.8, rootPolicyTemperatureEarly=1.5, chosenMoveTemperatureHalflife=7.0)),
-    (5, 5, 4, 64, 120, dict(fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=1.5, rootDesiredPerChildVisitsCoeff=1.0))])
+    (5, 5, 4, 64, 120, dict(fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=1.5, rootDesiredPerChildVisitsCoeff=1.0)),
+    (5, 5, 4, 96, 200, dict(valueWeightExponent=0.25)),    # setup.cpp:519 default
+    (4, 5, 3, 40, 120, dict(valueWeightExponent=0.7))])
 def test_search_selfplay_options_bit_exact(ctx, oracle, W, H, K, G, V, opts):
     """The self-play configuration's remaining search options -- shaped Dirichlet root noise (deterministic gamma sampler), root
     policy temperature, FPU parent weighting by visited policy, rootDesiredPerChildVisitsCoeff -- on top of graph search and the
