@@ -6,6 +6,7 @@
 // within 1e-4; it also backs the layer-level hooks (nninterface.h:127-169).  The production path
 // is the bf16 tcgen05 trunk in net_bf16.cu; this file owns the handle and dispatches to it.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 
@@ -601,14 +602,22 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
     const int NB = boardsPerTile(h->W, h->H);
     const int wave = 2 * NB * h->ctx->smCount;                 // rows that give every SM one work item
     // Tapered schedule (in waves): a small first chunk so that compute starts after a short copy, a small last chunk so
-    // that little is left to copy back when the last kernel ends, at most 4 waves in between: 16 waves -> 1,2,4,4,4,1.
+    // that little is left to copy back when the last kernel ends: 16 waves -> 1,3,11,1.
     const int totalWaves = (n + wave - 1) / wave;
     std::vector<int> sizes;
-    if(totalWaves >= 8) {
-      sizes.push_back(1); sizes.push_back(2);
-      int mid = totalWaves - 4;
-      while(mid > 0) { int s = std::min(4, mid); sizes.push_back(s); mid -= s; }
-      sizes.push_back(1);
+    if(const char* env = getenv("KC_FORWARD_SCHEDULE")) {   // diagnostic override: chunk sizes in waves, e.g. "1,3,6,5,1" (the rest goes to a last chunk)
+      int left = totalWaves;
+      for(const char* q = env; *q && left > 0;) {
+        const int v = std::max(1, std::min(left, atoi(q)));
+        sizes.push_back(v); left -= v;
+        while(*q && *q != ',') q++;
+        if(*q == ',') q++;
+      }
+      if(left > 0) sizes.push_back(left);
+    } else if(totalWaves >= 8) {
+      // 1, 3, the bulk, 1: every chunk boundary costs a kernel prologue + the un-overlapped epilogue of its last work item
+      // (about 25 us), so few chunks; measured at 16 waves: 1,2,4,4,4,1 6.63 / 1,2,4,8,1 6.64 / 1,4,10,1 6.64 / 1,3,11,1 6.75 M evals/s
+      sizes.push_back(1); sizes.push_back(3); sizes.push_back(totalWaves - 5); sizes.push_back(1);
     } else {
       for(int w = 0; w < totalWaves; w += 2) sizes.push_back(std::min(2, totalWaves - w));
     }
