@@ -1013,13 +1013,15 @@ def test_play_mode_symmetry_permutes_direction_channels(ctx, oracle, mode):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("W,H,K", [(5, 5, 4), (6, 6, 4)])
-def test_training_rows_match_oracle(ctx, oracle, tmp_path, W, H, K):
+@pytest.mark.parametrize("mode", ["tree", "graph"])
+def test_training_rows_match_oracle(ctx, oracle, tmp_path, W, H, K, mode):
     """Self-play training rows: every array of every row equals the oracle's restatement of
     TrainingWriteBuffers::addRow for the same games, bit for bit (hash evaluator, so the searches are identical)."""
     from katacoffee_b200 import backend
     G, V, seed, T = 40, 40, 9, 6
     P = 4 * W * H
-    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, temperaturePlies=T)
+    gkw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8) if mode == "graph" else {}
+    s = backend.Search(ctx, None, G, W, H, K, maxVisits=V, temperaturePlies=T, **gkw)
     s.reset(seed=seed, firstGameId=500)
     s.enableTrainingRows(G * W * H)
     # the same games through the oracle, keeping what a row needs from every search
@@ -1028,7 +1030,7 @@ def test_training_rows_match_oracle(ctx, oracle, tmp_path, W, H, K):
         og = oracle.Game(W, H, K)
         moves, rn, rw, vis = [], [], [], []
         while not og.finished():
-            r = oracle.search_run(og, V)
+            r = oracle.search_run_graph(og, V, graph=True, bias_factor=0.3, bias_exponent=0.8) if mode == "graph" else oracle.search_run(og, V)
             mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 500 + g)
             moves.append(mv); rn.append(r["rootVisits"]); rw.append(r["rootUtilitySum"])
             vis.append(np.where(r["order"] != 255, r["edgeVisits"], 0).astype(np.int16))
