@@ -76,7 +76,7 @@ struct TrunkCfg {
   // barriers (8 bytes each)
   static constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + NT,
                        BAR_IN = BAR_ACTFREE + NT, BAR_HEAD = BAR_IN + NT, BAR_CHUNK = BAR_HEAD + NT, BAR_FULLP = BAR_CHUNK + NT * NCH,
-                       BAR_INP = BAR_FULLP + NSTAGES, NUM_BARS = BAR_INP + NT;   // FULLP / INP: the peer CTA's weights / input tile landed
+                       BAR_INP = BAR_FULLP + NSTAGES, BAR_SKEW = BAR_INP + NT, NUM_BARS = BAR_SKEW + 1;   // FULLP / INP: the peer CTA's weights / input tile landed
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM = OFF_TMEM + 16;
   static_assert(NT * 2 * MAXC <= 512, "TMEM: every tile needs a trunk region and a block-internal region");
@@ -127,6 +127,8 @@ struct TrunkParams {
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
   int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
+  int skew;          // two tiles per CTA: tile 1's MMA issuer starts this many weight stages after tile 0's, so that the layer boundary of
+                     // one tile (accumulator -> epilogue -> first chunk published, ~1,200 clk) is covered by the other tile's MMAs
   int g1Act, p1Act, v1Act, v2Act;   // head activations
   int* abortFlag;
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
@@ -534,7 +536,15 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
     return mbar_wait(bar, parity, abortFlag, code);
   };
   const int itemStep = K::PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  // skew between the two tiles of a CTA: tile 0 signals once it has issued P.skew stages, tile 1 starts then; the lead keeps itself
+  // (both tiles pay the same boundary stalls) and is bounded by the ring, whose slots are only refilled once both tiles have used them
+  const bool skewed = K::NT == 2 && P.skew > 0;
+  int stagesToSignal = (skewed && t == 0) ? P.skew : -1;
+  auto stageIssued = [&]() {
+    if(stagesToSignal > 0 && --stagesToSignal == 0) { if(leader) mbar_arrive(bars + K::BAR_SKEW * 8); stagesToSignal = -1; }
+  };
   for(int item = K::PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x; item < numItems; item += itemStep, itemCount++) {   // pair mode: item = item pair
+    if(skewed && t == 1 && itemCount == 0 && !mbar_wait(bars + K::BAR_SKEW * 8, 0, abortFlag, 28)) return;
     if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
     if(K::PAIR && !waitc(bars + (K::BAR_INP + t) * 8, itemCount & 1, 26)) return;
     if(itemCount > 0 && !waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
@@ -577,6 +587,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
             }
             __syncwarp();
             accum = 1u;
+            stageIssued();
             if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
           }
         }
@@ -602,6 +613,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
           }
           if(leader) commit(barEmpty + slot * 8);
           __syncwarp();
+          stageIssued();
           if(++slot == K::NSTAGES) { slot = 0; phase ^= 1; }
         }
       }
@@ -615,6 +627,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
       }
       __syncwarp();
     }
+    if(stagesToSignal > 0) { if(leader) mbar_arrive(bars + K::BAR_SKEW * 8); stagesToSignal = -1; }   // a net with fewer stages than the skew
   }
 }
 
@@ -644,6 +657,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
     for(int i = 0; i < K::NSTAGES; i++) {
       mbar_init(bars + (K::BAR_FULL + i) * 8, 1); mbar_init(bars + (K::BAR_EMPTY + i) * 8, NT);   // every MMA issuer releases a slot
       mbar_init(bars + (K::BAR_FULLP + i) * 8, 1);
+      if(i == 0) mbar_init(bars + K::BAR_SKEW * 8, 1);
     }
     for(int t = 0; t < NT; t++) {
       mbar_init(bars + (K::BAR_ACC + t) * 8, 1); mbar_init(bars + (K::BAR_ACTFREE + t) * 8, 1); mbar_init(bars + (K::BAR_IN + t) * 8, 1);
@@ -1157,6 +1171,10 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   if(timed) cudaEventRecord(h->evPool[h->evUsed], st);
   // CTA pairs (cta_group::2) are the default for trunks up to 128 channels; KC_TRUNK_PAIR=0 selects the single-CTA kernel
   static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }();
+  // tile skew (see TrunkParams::skew): 5 of the 14 ring stages in pair mode, measured +1.5 % burst / +1 % under the power cap
+  // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
+  static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();
+  P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 5 : 2;
   if(T->cfg == 0 && usePair) {
     // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
     P.wstream = T->d_wPair;
