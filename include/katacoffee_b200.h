@@ -299,6 +299,10 @@ typedef struct {
   double rootDesiredPerChildVisitsCoeff;  /* a root child with weight < sqrt(prior * totalChildWeight * coeff) is searched first (2 in selfplay1.cfg:147) */
   double valueWeightExponent;             /* SearchParams::valueWeightExponent (0.5 in SearchParams() and selfplay1.cfg:179): children
                                              whose utility is implausibly low next to their siblings count less in the parent */
+  /* Move choice under the reference's temperature schedule (searchresults.cpp:287-298, searchhelpers.cpp:12-49): if either
+   * temperature is > 0 it replaces temperaturePlies -- edge visits, minus min(subtract, max/64), zero below min(prune, max/64),
+   * raised to 1/T, T going from ...Early to chosenMoveTemperature with chosenMoveTemperatureHalflife (selfplay1.cfg:137-141). */
+  double chosenMoveTemperature, chosenMoveTemperatureEarly, chosenMoveSubtract, chosenMovePrune;
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

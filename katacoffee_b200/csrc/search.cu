@@ -59,6 +59,8 @@ struct SearchCfg {
   // graph mode options (SearchParams of the same names; 0 / 1.0 = off)
   int rootNoise, fpuPW;
   double noiseConc, noiseWeight, rootTemp, rootTempEarly, tempHalflife, fpuPWPow, rootDesired, vwExp;
+  double moveTemp, moveTempEarly, moveSubtract, movePrune;   // chosenMoveTemperature / Early / Subtract / Prune (either temperature > 0: schedule)
+  int boardArea;
   uint64_t seed;
 };
 
@@ -976,7 +978,47 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
         if(eN[pos] > bestN || (eN[pos] == bestN && ord[pos] < bestOrd)) { bestN = eN[pos]; bestOrd = ord[pos]; bestPos = pos; }
       }
     const int ply = numTurnsOf(s.misc);
-    if(ply < c.temperaturePlies && total > 0) {
+    if((c.moveTemp > 0.0 || c.moveTempEarly > 0.0) && bestN > 0) {
+      // the reference's temperature schedule (searchresults.cpp:287-298, searchhelpers.cpp:12-49, 463-467): play-selection value = edge
+      // visits, pruned / reduced, raised to 1/T with T interpolated from the early to the late temperature by 0.5^(turn/halflife...)
+      const double maxValue = (double)bestN;
+      const double amountToSubtract = fmin(c.moveSubtract, __ddiv_rn(maxValue, 64.0)), amountToPrune = fmin(c.movePrune, __ddiv_rn(maxValue, 64.0));
+      double newMax = 0.0;
+      int bPos = -1, bOrd = 1 << 20;
+      for(int pos = 0; pos < c.P; pos++) {
+        if(ch[pos] == -1) continue;
+        double x = (double)eN[pos];
+        if(x < amountToPrune) x = 0.0;
+        else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
+        if(x > newMax || (x == newMax && x > 0.0 && ord[pos] < bOrd)) { newMax = x; bPos = pos; bOrd = ord[pos]; }
+      }
+      const double hl = c.tempHalflife > 0.0 ? c.tempHalflife : 19.0;
+      const double halflives = __ddiv_rn(__dmul_rn(__ddiv_rn((double)ply, hl), 19.0), __dsqrt_rn((double)c.boardArea));
+      const double T = __dadd_rn(c.moveTemp, __dmul_rn(__dsub_rn(c.moveTempEarly, c.moveTemp), detExp(__dmul_rn(halflives, detLog(0.5)))));
+      if(T <= 1.0e-4 || newMax <= 0.0) move = bPos;
+      else {
+        const double logMax = detLog(newMax);
+        auto weightOf = [&](int pos) -> double {
+          double x = (double)eN[pos];
+          if(x < amountToPrune) x = 0.0;
+          else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
+          return x <= 0.0 ? 0.0 : detExp(__ddiv_rn(__dsub_rn(detLog(x), logMax), T));
+        };
+        double sum = 0.0;
+        for(int pos = 0; pos < c.P; pos++) if(ch[pos] != -1) sum = __dadd_rn(sum, weightOf(pos));
+        const uint64_t r = splitmix64(c.seed ^ (s.id * PHI) ^ (uint64_t)ply ^ CHOOSE_SALT);
+        const double d = __dmul_rn(__dmul_rn((double)(r & ((1ULL << 53) - 1ULL)), 1.0 / 9007199254740992.0), sum);
+        double acc = 0.0;
+        int last = -1;
+        for(int pos = 0; pos < c.P; pos++) {
+          if(ch[pos] == -1) continue;
+          last = pos;
+          acc = __dadd_rn(acc, weightOf(pos));
+          if(acc > d) { move = pos; break; }
+        }
+        if(move < 0) move = last;
+      }
+    } else if(ply < c.temperaturePlies && total > 0) {
       const uint64_t r = splitmix64(c.seed ^ (s.id * PHI) ^ (uint64_t)ply ^ CHOOSE_SALT);
       long long k = (long long)(r % (uint64_t)total);
       for(int pos = 0; pos < c.P; pos++)
@@ -1277,6 +1319,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->subtreeValueBiasFreeProp >= 0.0 && p->subtreeValueBiasFreeProp <= 1.0, "kc_search_create: subtreeValueBiasFreeProp must be within 0..1");
   KC_CHECK(!p->rootNoiseEnabled || (p->rootDirichletNoiseTotalConcentration > 0.0 && p->rootDirichletNoiseWeight >= 0.0 && p->rootDirichletNoiseWeight <= 1.0),
            "kc_search_create: root noise needs rootDirichletNoiseTotalConcentration > 0 and a weight within 0..1");
+  KC_CHECK(p->chosenMoveTemperature >= 0.0 && p->chosenMoveTemperatureEarly >= 0.0 && p->chosenMoveSubtract >= 0.0 && p->chosenMovePrune >= 0.0,
+           "kc_search_create: negative move-choice option");
   KC_CHECK(p->valueWeightExponent >= 0.0 && p->valueWeightExponent <= 1.0, "kc_search_create: valueWeightExponent must be within 0..1");
   KC_CHECK(p->rootPolicyTemperature >= 0.0 && p->rootPolicyTemperatureEarly >= 0.0 && p->rootDesiredPerChildVisitsCoeff >= 0.0, "kc_search_create: negative root option");
   KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
@@ -1292,6 +1336,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.rootTemp = p->rootPolicyTemperature; c.rootTempEarly = p->rootPolicyTemperatureEarly; c.tempHalflife = p->chosenMoveTemperatureHalflife;
   c.fpuPWPow = p->fpuParentWeightByVisitedPolicyPow > 0.0 ? p->fpuParentWeightByVisitedPolicyPow : 1.0; c.rootDesired = p->rootDesiredPerChildVisitsCoeff;
   c.vwExp = p->valueWeightExponent;
+  c.moveTemp = p->chosenMoveTemperature; c.moveTempEarly = p->chosenMoveTemperatureEarly; c.moveSubtract = p->chosenMoveSubtract; c.movePrune = p->chosenMovePrune;
+  c.boardArea = xSize * ySize;
   const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);
   // every option beyond plain PUCT runs on the node-centric statistics of graph mode
   c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0 || c.vwExp != 0.0) ? 1 : 0;

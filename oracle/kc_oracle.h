@@ -248,6 +248,9 @@ void ko_search_continue(ko_search* s, const ko_game* rootGame, int x_size, int y
                         uint8_t* orderOut, uint64_t counters[3]);
 void ko_search_advance(ko_search* s, int movePos);
 int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int ply, int temperaturePlies, uint64_t seed, uint64_t gameId);
+/* the reference's temperature schedule for the move choice (see ko_search.cpp) */
+int ko_search_choose_temperature(const int32_t* edgeVisits, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
+                                 double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId);
 /* Training rows of one finished game (restatement of TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566, with the
  * canonical choices documented at kc_search_read_training_rows); arrays as in the reference's npz, R rows. */
 void ko_training_rows(int x_size, int y_size, int win_len, int R, const int32_t* movePos, const int32_t* rootN, const double* rootW,

@@ -93,6 +93,7 @@ def lib():
         l.ko_postprocess.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp, C.c_int]
         l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        l.ko_search_choose_temperature.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
         l.ko_search_run_graph.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_graph_hash.argtypes = [vp, vp, C.c_int, vp]
         l.ko_game_recent_move_pos.argtypes = [vp, C.c_int]
@@ -399,6 +400,11 @@ class PersistentSearch:
 def search_choose(edge_visits, order, ply, temperature_plies, seed, game_id):
     ev = np.ascontiguousarray(edge_visits, np.int32); od = np.ascontiguousarray(order, np.uint8)
     return lib().ko_search_choose(_p(ev), _p(od), len(ev), ply, temperature_plies, seed, game_id)
+
+
+def search_choose_temperature(edge_visits, order, board_area, ply, temp_early, temp_late, halflife, subtract, prune, seed, game_id):
+    ev = np.ascontiguousarray(edge_visits, np.int32); od = np.ascontiguousarray(order, np.uint8)
+    return lib().ko_search_choose_temperature(_p(ev), _p(od), len(ev), board_area, ply, temp_early, temp_late, halflife, subtract, prune, seed, game_id)
 
 
 def training_rows(x, y, k, moves, root_n, root_w, visits, game_id):

@@ -808,6 +808,48 @@ int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int
   return bestPos;
 }
 
+// The move played after a search under the reference's temperature schedule (Search::getChosenMoveLoc -> getPlaySelectionValues'
+// subtract / prune step, cpp/search/searchresults.cpp:287-298; chooseIndexWithTemperature, cpp/search/searchhelpers.cpp:12-49;
+// interpolateEarly :463-467).  Canonical: the play-selection value of a move is its edge visit count (no LCB, no reduced
+// weights), candidates are walked in policy-index order, the uniform draw comes from the counter stream of ko_search_choose,
+// log / exp are detLog / detExp.  T <= 1e-4 picks the most visited move (ties: earliest created).
+int ko_search_choose_temperature(const int32_t* edgeVisits, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
+                                 double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId) {
+  double maxValue = 0.0;
+  for(int pos = 0; pos < P; pos++) if(order[pos] != 255 && (double)edgeVisits[pos] > maxValue) maxValue = (double)edgeVisits[pos];
+  if(maxValue <= 0.0) return -1;
+  const double amountToSubtract = std::min(subtract, maxValue / 64.0), amountToPrune = std::min(prune, maxValue / 64.0);
+  std::vector<double> v(P, 0.0);
+  double newMax = 0.0;
+  int bestPos = -1, bestOrd = 1 << 20;
+  for(int pos = 0; pos < P; pos++) {
+    if(order[pos] == 255) continue;
+    double x = (double)edgeVisits[pos];
+    if(x < amountToPrune) x = 0.0;
+    else { x = x - amountToSubtract; if(x <= 0.0) x = 0.0; }
+    v[pos] = x;
+    if(x > newMax || (x == newMax && x > 0.0 && order[pos] < bestOrd)) { newMax = x; bestPos = pos; bestOrd = order[pos]; }
+  }
+  const double hl = halflife > 0.0 ? halflife : 19.0;
+  const double halflives = (((double)ply / hl) * 19.0) / std::sqrt((double)boardArea);
+  const double T = tempLate + (tempEarly - tempLate) * detExp(halflives * detLog(0.5));
+  if(T <= 1.0e-4 || newMax <= 0.0) return bestPos;
+  const double logMax = detLog(newMax);
+  double sum = 0.0;
+  for(int pos = 0; pos < P; pos++) { v[pos] = v[pos] <= 0.0 ? 0.0 : detExp((detLog(v[pos]) - logMax) / T); sum += v[pos]; }
+  const uint64_t r = ko_splitmix64(seed ^ (gameId * PHI) ^ (uint64_t)ply ^ CHOOSE_SALT);
+  const double d = ((double)(r & ((1ULL << 53) - 1ULL)) * (1.0 / 9007199254740992.0)) * sum;
+  double acc = 0.0;
+  int last = -1;
+  for(int pos = 0; pos < P; pos++) {
+    if(order[pos] == 255) continue;
+    last = pos;
+    acc += v[pos];
+    if(acc > d) return pos;
+  }
+  return last;
+}
+
 // Training rows of one finished game (TrainingWriteBuffers::addRow, cpp/dataio/trainingwrite.cpp:316-566, restated with the
 // canonical choices listed at kc_search_read_training_rows in include/katacoffee_b200.h): the game is replayed from the
 // empty board with `movePos`, turn i carries the root visits / utility sum / visit counts of the search that chose move i.

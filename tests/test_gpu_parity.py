@@ -764,14 +764,16 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
     from katacoffee_b200 import backend, capi
     W = H = 5
     G, V, seed, T = 48, 64, 77, 6
+    MOVE = dict(chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMoveSubtract=0.0, chosenMovePrune=1.0)   # selfplay1.cfg:137-141
     s = backend.Search(ctx, None, G, W, H, 4, maxVisits=V, temperaturePlies=T, reuseTree=True, useGraphSearch=True, subtreeValueBiasFactor=0.3,
-                       subtreeValueBiasWeightExponent=0.8, cpuctExploration=1.1, rootFpuReductionMax=0.0, **SELFPLAY1_CFG)
+                       subtreeValueBiasWeightExponent=0.8, cpuctExploration=1.1, rootFpuReductionMax=0.0, **SELFPLAY1_CFG, **MOVE)
     s.reset(seed=seed, firstGameId=900)
     ogames = [oracle.Game(W, H, 4) for _ in range(G)]
     osearch = [oracle.PersistentGraphSearch(W, H, V, graph=True, bias_factor=0.3, bias_exponent=0.8, free_prop=0.8, cpuct=1.1, root_fpu=0.0,
                                             noiseSeed=seed, noiseGameId=900 + g, **SELFPLAY1_CFG) for g in range(G)]
     stats = capi.SearchStats()
     ocnt = np.zeros(5, np.uint64)
+    argmax = nmoves = 0
     for ply in range(W * H):
         _, chosen, _ = s.play(1, stats)
         dig = s.treeDigest()
@@ -782,7 +784,9 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
                 continue
             r = osearch[g].run(og)
             ocnt += r["counters"]
-            mv = oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), T, seed, 900 + g)
+            mv = oracle.search_choose_temperature(r["edgeVisits"], r["order"], W * H, og.num_turns(), 0.75, 0.15, 19.0, 0.0, 1.0, seed, 900 + g)
+            argmax += mv == oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), 0, seed, 900 + g)
+            nmoves += 1
             assert chosen[g] == mv, (ply, g, chosen[g], mv)
             og.play(mv)
             osearch[g].advance(mv)
@@ -790,6 +794,7 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
                 assert int(dig[g]) == osearch[g].digest(), (ply, g)
     assert all(og.finished() for og in ogames)
     assert (stats.visits, stats.netEvals, stats.terminalVisits, stats.transpositionHits, stats.catchUpVisits) == tuple(int(x) for x in ocnt)
+    assert 0.3 * nmoves < argmax < nmoves      # the temperature schedule really samples: not always, but often, the most visited move
     s.close()
 
 
