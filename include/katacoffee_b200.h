@@ -253,6 +253,9 @@ int kc_games_run(kc_games* g, kc_handle* h, int plies, kc_stats* statsAccum);
  * *msTotal receives the sum of the per-ply durations; flushL2Bytes > 0 overwrites a scratch buffer of
  * that size between plies (outside the timed windows) so no ply finds its inputs in L2 by accident. */
 int kc_games_run_timed(kc_games* g, kc_handle* h, int plies, size_t flushL2Bytes, kc_stats* statsAccum, float* msTotal);
+/* What the last ply of the last rules+features run (kc_games_run / kc_games_run_timed with h == NULL) left in the device buffers:
+ * planes [G][15*H*W] fp32 NCHW, global [G], legal [G][LW], status [G], sitHash [G][2], played [G]; any may be NULL. */
+int kc_games_read_run_outputs(kc_games* g, float* planes, float* global, uint32_t* legal, uint32_t* status, uint64_t* sitHash, int16_t* played);
 int64_t kc_games_launch_count(const kc_games* g);
 /* Average device time in ms per ply of the rules+features kernel in the last kc_games_run. */
 float kc_games_last_kernel_ms(const kc_games* g);

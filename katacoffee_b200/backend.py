@@ -277,6 +277,15 @@ class Games:
         check(lib().kc_games_run_timed(self._p, handle._p if handle is not None else None, plies, flushL2Bytes, C.byref(st), C.byref(ms)))
         return st, ms.value
 
+    def readRunOutputs(self):
+        """What the last ply of the last rules+features run(None, plies) wrote: dict(planes [G, 15*HW], global, legal, status, sitHash, played)."""
+        G, HW = self.G, self.HW
+        out = dict(planes=np.empty((G, 15 * HW), np.float32), glob=np.empty(G, np.float32), legal=np.empty((G, self.LW), np.uint32),
+                   status=np.empty(G, np.uint32), sitHash=np.empty((G, 2), np.uint64), played=np.empty(G, np.int16))
+        check(lib().kc_games_read_run_outputs(self._p, ptr(out["planes"]), ptr(out["glob"]), ptr(out["legal"]), ptr(out["status"]),
+                                              ptr(out["sitHash"]), ptr(out["played"])))
+        return out
+
     def launchCount(self):
         return int(lib().kc_games_launch_count(self._p))
 

@@ -122,6 +122,7 @@ PROTOTYPES = {
     "kc_sgf_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_int, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "kc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "kc_host_free": (C.c_int, [vp]),
+    "kc_games_read_run_outputs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "kc_search_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SearchParams), C.POINTER(vp)]),
     "kc_search_destroy": (C.c_int, [vp]),
     "kc_search_games": (vp, [vp]),

@@ -697,6 +697,7 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       G->launches++;
       KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups + 1], G->stream));
       nGroups++;
+      G->lastRunPlanes = ring.slot[(np - 1) & 3];
     }
   }
   for(int p = 0; h && p < plies; p++) {
@@ -741,6 +742,22 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     acc->gamesFinished += hs[2]; acc->blackWins += hs[3]; acc->whiteWins += hs[4]; acc->draws += hs[5];
     acc->checksum ^= hs[6];
   }
+  return 0;
+}
+
+int kc_games_read_run_outputs(kc_games* G, float* planes, float* global, uint32_t* legal, uint32_t* status, uint64_t* sitHash, int16_t* played) {
+  KC_CHECK(G, "kc_games_read_run_outputs: null argument");
+  KC_CHECK(G->lastRunPlanes, "kc_games_read_run_outputs: call kc_games_run without a handle first");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  const size_t n = (size_t)g.numGames;
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  if(planes) KC_CUDA(cudaMemcpy(planes, G->lastRunPlanes, n * 15 * g.HW * 4, cudaMemcpyDeviceToHost));
+  if(global) KC_CUDA(cudaMemcpy(global, G->d_global, n * 4, cudaMemcpyDeviceToHost));
+  if(legal) KC_CUDA(cudaMemcpy(legal, G->d_legal, n * g.LW * 4, cudaMemcpyDeviceToHost));
+  if(status) KC_CUDA(cudaMemcpy(status, G->d_status, n * 4, cudaMemcpyDeviceToHost));
+  if(sitHash) KC_CUDA(cudaMemcpy(sitHash, G->d_sitHash, n * 16, cudaMemcpyDeviceToHost));
+  if(played) KC_CUDA(cudaMemcpy(played, G->d_played, n * 2, cudaMemcpyDeviceToHost));
   return 0;
 }
 

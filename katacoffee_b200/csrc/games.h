@@ -24,6 +24,7 @@ struct kc_games {
   // rules+features-only timing: consecutive plies write their planes to different ring slots (4 x G x 15*HW fp32 > L2),
   // so a ply never overwrites lines of the previous one that are still dirty in L2
   float* d_planesRing[3] = {nullptr, nullptr, nullptr};
+  const float* lastRunPlanes = nullptr;   // where the last ply of the last rules+features kc_games_run wrote its planes
 };
 
 

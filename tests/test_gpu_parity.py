@@ -436,6 +436,36 @@ def test_run_counters_and_checksum(ctx, oracle):
     games.close()
 
 
+@pytest.mark.parametrize("W,H,K,G,plies,flush", [(5, 5, 4, 3000, 1, 0), (5, 5, 4, 3000, 6, 0), (5, 5, 4, 2500, 11, 1 << 20), (5, 5, 4, 70, 19, 1 << 20),
+                                                 (6, 6, 4, 900, 7, 1 << 20), (4, 5, 3, 333, 10, 0)])
+def test_fused_multi_ply_kernel_outputs_bit_exact(ctx, oracle, W, H, K, G, plies, flush):
+    """The kernel the rules+features bench times (games_multi_kernel: up to 8 plies per launch, state in registers, planes to a
+    ring of buffers): what its last ply leaves in the device buffers -- planes, masks, status words, hashes, moves -- equals the
+    oracle's position after the same number of plies, with and without the plane ring (flush > 0), with auto-refill."""
+    from katacoffee_b200 import backend
+    seed = 17
+    games = backend.Games(ctx, G, W, H, K)
+    games.reset(seed=seed, autoRefill=True)
+    games.runTimed(None, plies, flush)
+    out = games.readRunOutputs()
+    for g in range(G):
+        # auto-refill: a finished game restarts with id + G before its next ply
+        og, gid = oracle.Game(W, H, K), g
+        last = -1
+        for _ in range(plies):
+            if og.finished():
+                og, gid = oracle.Game(W, H, K), gid + G
+            last = og.choose(seed, gid)
+            og.play(last)
+        assert int(out["status"][g]) == og.status(), g
+        assert int(out["played"][g]) == last, g
+        assert (out["sitHash"][g] == og.sit_hash()).all(), g
+        assert (out["legal"][g] == og.legal_mask()[0]).all(), g
+        assert (out["planes"][g] == og.fill_row_v1()[0]).all(), g
+        assert out["glob"][g] == K
+    games.close()
+
+
 def test_million_positions_full_size_parity(ctx, oracle):
     """BASELINE config 2 at full size (65536 concurrent 5x5 games to terminal, ~1.3 M positions):
     size-independent check = checksum-of-sit-hashes + outcome counters against the oracle, plus
