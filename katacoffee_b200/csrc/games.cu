@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kc_internal.h"
@@ -391,6 +392,147 @@ __global__ void __launch_bounds__(TB_PLAIN) games_multi_kernel(const Geom g, Sta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same several-plies launch with the two phases of a ply on different warps: a CTA of 128 threads owns 64 games; warps 0, 1
+// (producers) step their 32 games and pack the planes into a shared bit string, warps 2, 3 (consumers) expand the bit string
+// of the producer two warps below them into fp32 and stream it out.  Bit strings are double-buffered and handed over with
+// named barriers (bar.arrive / bar.sync on 64 threads: full[pair][buf], empty[pair][buf]), so a producer runs the bitboard
+// arithmetic of ply p+1 while its consumer is still storing ply p.  The grid is still one CTA per 64 games, but twice the warps
+// are resident (28 instead of 14 per SM at 65,536 games), and the store stream no longer pauses for the rules phase.
+// Same outputs as games_multi_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <class D, int NC>   // NC consumer warps per producer warp
+__global__ void __launch_bounds__((1 + NC) * TB_PLAIN) games_multi_split_kernel(const Geom g, State st, const uint64_t* __restrict__ zob, StepOut so,
+                                                                         PlaneRing ring, float* __restrict__ global, int plies, int firstSlot) {
+  constexpr int GPB = TB_PLAIN;                       // games per CTA
+  constexpr int WORDS = 15 * 49;                      // bit-string words of 32 games (E bits each), sized for 7x7
+  __shared__ uint64_t sPlanes[15][GPB + 1];
+  __shared__ uint32_t sBits[2][2][WORDS + 1];         // [pair][buffer]
+  const D dm(g);
+  using BB = typename D::BB;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int pair = w & 1, role = w >> 1;              // role 0: producer (rules + pack), 1..NC: consumers (expand + store)
+  constexpr int NTHR = 32 * (1 + NC);                 // threads meeting at a hand-over barrier
+  const int gBase = blockIdx.x * GPB;
+  const int E = 15 * dm.HW();
+  const int ngw = min(32, g.numGames - gBase - pair * 32);
+  if(ngw <= 0) return;                                // both warps of the pair leave together
+  const int barFull = 1 + pair * 4, barEmpty = 3 + pair * 4;   // + buffer index
+  if(role >= 1) {
+    const int ci = role - 1;
+    for(int p = 0; p < plies; p++) {
+      const int buf = p & 1;
+      named_sync(barFull + buf, NTHR);
+      const uint32_t* bits = sBits[pair][buf];
+      const int total = ngw * E;
+      float* out = ring.slot[(firstSlot + p) & 3] + ((size_t)gBase + pair * 32) * E;
+      float4* out4 = reinterpret_cast<float4*>(out);
+      const int nvec = total >> 2;
+#pragma unroll 4
+      for(int j = lane + 32 * ci; j < nvec; j += 32 * NC) {
+        uint32_t b = bits[j >> 3] >> ((j & 7) * 4);
+        float4 v = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+        __stcs(&out4[j], v);
+      }
+      if(ci == 0) for(int e = (nvec << 2) + lane; e < total; e += 32) out[e] = (float)((bits[e >> 5] >> (e & 31)) & 1u);
+      if(p + 2 < plies) named_arrive(barEmpty + buf, NTHR);   // the producer may refill this buffer
+    }
+    if(ci == 0 && global && lane < ngw) global[gBase + pair * 32 + lane] = (float)dm.K();
+    return;
+  }
+  // ---- producer
+  const int tl = pair * 32 + lane;                    // game within the CTA
+  const int gi = gBase + tl;
+  const bool active = gi < g.numGames;
+  GameRegs<BB> s;
+  s.black = 0; s.white = 0; s.h0 = s.h1 = s.id = s.misc = 0;
+  if(active) {
+    s.black = (BB)st.black[gi]; s.white = (BB)st.white[gi]; s.h0 = st.hash0[gi]; s.h1 = st.hash1[gi];
+    s.id = st.gameId[gi]; s.misc = st.misc[gi];
+  }
+  unsigned long long cSteps = 0, cFin = 0, cB = 0, cW = 0, cD = 0, cXor = 0;
+  for(int p = 0; p < plies; p++) {
+    const int buf = p & 1;
+    if(p >= 2) named_sync(barEmpty + buf, NTHR);      // the consumers have finished with this buffer (ply p - 2)
+    uint32_t* bits = sBits[pair][buf];
+    for(int i = lane; i < E; i += 32) bits[i] = 0;
+    __syncwarp();
+    if(active) {
+      BB L[4];
+      bool illegal = false;
+      const int played = stepGame(dm, g, s, -1, false, zob, L, illegal);
+      const int fl = flagsOf(s.misc);
+      const int nextPla = (fl >> 3) & 3;
+      const uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
+      if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
+      if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
+      if(so.played) so.played[gi] = (int16_t)played;
+      if(so.legal) {
+        uint64_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for(int d = 0; d < 4; d++) {
+          uint64_t dense = toDense(dm, L[d]);
+          int off = d * dm.HW(), wq = off >> 6, sh = off & 63;
+#pragma unroll
+          for(int q = 0; q < 4; q++) {
+            if(q == wq) acc[q] |= dense << sh;
+            if(q == wq + 1 && sh) acc[q] |= dense >> (64 - sh);
+          }
+        }
+        for(int wd = 0; wd < g.LW; wd++) so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
+      }
+      if(played >= 0) {
+        cSteps += 1;
+        cXor ^= sh0;
+        if(fl & 1) { cFin += 1; int wn = (fl >> 1) & 3; cB += wn == 1; cW += wn == 2; cD += wn == 0; }
+      }
+      v1Planes(dm, g, s, L, &sPlanes[0][tl], GPB + 1);
+      uint32_t bitPos = (uint32_t)lane * E, wi = bitPos >> 5;
+      int fill = bitPos & 31;
+      uint64_t acc = 0;
+      auto append = [&](uint64_t b, int n) {
+        acc |= b << fill;
+        fill += n;
+        if(fill >= 32) { atomicOr(&bits[wi++], (uint32_t)acc); acc >>= 32; fill -= 32; }
+      };
+#pragma unroll 1
+      for(int c = 0; c < 15; c++) {
+        uint64_t Dn = toDense(dm, (BB)sPlanes[c][tl]);
+        if(dm.HW() <= 25) append(Dn, dm.HW());
+        else { append(Dn & 0x1FFFFFFULL, 25); append(Dn >> 25, dm.HW() - 25); }
+      }
+      if(fill) atomicOr(&bits[wi], (uint32_t)acc);
+    }
+    __syncwarp();
+    named_arrive(barFull + buf, NTHR);                // hand the bit string of this ply to the consumers
+  }
+  if(active) {
+    st.black[gi] = (uint64_t)s.black; st.white[gi] = (uint64_t)s.white; st.hash0[gi] = s.h0; st.hash1[gi] = s.h1;
+    st.gameId[gi] = s.id; st.misc[gi] = s.misc;
+  }
+  if(so.stats) {
+    for(int o = 16; o > 0; o >>= 1) {
+      cSteps += __shfl_xor_sync(0xffffffffu, cSteps, o);
+      cFin += __shfl_xor_sync(0xffffffffu, cFin, o);
+      cB += __shfl_xor_sync(0xffffffffu, cB, o);
+      cW += __shfl_xor_sync(0xffffffffu, cW, o);
+      cD += __shfl_xor_sync(0xffffffffu, cD, o);
+      cXor ^= __shfl_xor_sync(0xffffffffu, cXor, o);
+    }
+    if(lane == 0) {
+      if(cSteps) atomicAdd(&so.stats[0], cSteps);
+      if(cFin) atomicAdd(&so.stats[2], cFin);
+      if(cB) atomicAdd(&so.stats[3], cB);
+      if(cW) atomicAdd(&so.stats[4], cW);
+      if(cD) atomicAdd(&so.stats[5], cD);
+      if(cXor) atomicXor(&so.stats[6], cXor);
+    }
+  }
+}
+
 }  // namespace kc
 
 // =============================================================================================
@@ -690,7 +832,19 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
       KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups], G->stream));
       StepOut so = stepOutOf(G, true);
-      if(g.W == 5 && g.H == 5 && g.K == 4)
+      // producer / consumer warps for the static 5x5 instantiation (5.72 -> 6.10 TB/s algorithmic at 65,536 games); the generic
+      // 64-bit kernel is bound by its rolled rules code and got slower when split (6x6: 4.46 -> 3.83 TB/s), so it keeps one warp
+      // per 32 games.  KC_GAMES_MULTI_SPLIT = 0 / 1 forces one form for every board.
+      static const int splitEnv = [] { const char* e = getenv("KC_GAMES_MULTI_SPLIT"); return e ? atoi(e) : -1; }();
+      const bool static5 = g.W == 5 && g.H == 5 && g.K == 4;
+      if(splitEnv < 0 ? static5 : splitEnv != 0) {
+        if(static5 && splitEnv == 2)
+          games_multi_split_kernel<StaticDims<5, 5, 4>, 2><<<blocks, 3 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+        else if(static5)
+          games_multi_split_kernel<StaticDims<5, 5, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+        else
+          games_multi_split_kernel<DynDims, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+      } else if(g.W == 5 && g.H == 5 && g.K == 4)
         games_multi_kernel<StaticDims<5, 5, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
       else
         games_multi_kernel<DynDims><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
