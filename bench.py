@@ -367,8 +367,7 @@ def main():
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                          "traffic": load_traffic("prof_trunk") if args.config == "5x5" else None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                          "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
-            "roofline_rules_features": {"kernel": ("games_multi_split_kernel (rules step + fp32 NCHW planes, 8 plies per launch, producer / consumer warps, 4-slot plane ring)"
-                                                   if args.config == "5x5" else "games_multi_kernel (rules step + fp32 NCHW planes, 8 plies per launch, 4-slot plane ring)") + " at 65536 games",
+            "roofline_rules_features": {"kernel": "games_multi_split_kernel (rules step + fp32 NCHW planes, 8 plies per launch, producer / consumer warps, 4-slot plane ring) at 65536 games",
                                         "bound": "hbm", "plies_per_launch": 8,
                                         "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                         "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,

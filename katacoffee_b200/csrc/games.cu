@@ -543,6 +543,9 @@ __global__ void __launch_bounds__((1 + NC) * TB_PLAIN) games_multi_split_kernel(
 namespace {
 using namespace kc;
 
+// BASELINE configs[4] (6x6 k=4) also has a compile-time instantiation (64-bit bitboards, unrolled); KC_GAMES_STATIC6=0 disables it
+bool static6() { static const bool on = [] { const char* e = getenv("KC_GAMES_STATIC6"); return !e || atoi(e) != 0; }(); return on; }
+
 template <bool DO_STEP, class D>
 void launchGamesD(kc_games* G, int feat, int useMoves, const StepOut& so, const FeatOut& fo, int blocks) {
   switch(feat) {
@@ -559,6 +562,7 @@ void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
   const Geom& g = G->geom;
   if(g.W == 5 && g.H == 5 && g.K == 4) launchGamesD<DO_STEP, StaticDims<5, 5, 4>>(G, feat, useMoves, so, fo, blocks);
+  else if(g.W == 6 && g.H == 6 && g.K == 4 && static6()) launchGamesD<DO_STEP, StaticDims<6, 6, 4>>(G, feat, useMoves, so, fo, blocks);
   else launchGamesD<DO_STEP, DynDims>(G, feat, useMoves, so, fo, blocks);
   G->launches++;
 }
@@ -837,7 +841,13 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       // per 32 games.  KC_GAMES_MULTI_SPLIT = 0 / 1 forces one form for every board.
       static const int splitEnv = [] { const char* e = getenv("KC_GAMES_MULTI_SPLIT"); return e ? atoi(e) : -1; }();
       const bool static5 = g.W == 5 && g.H == 5 && g.K == 4;
-      if(splitEnv < 0 ? static5 : splitEnv != 0) {
+      const bool stat6 = g.W == 6 && g.H == 6 && g.K == 4 && static6();
+      if(stat6) {
+        if(splitEnv != 0)
+          games_multi_split_kernel<StaticDims<6, 6, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+        else
+          games_multi_kernel<StaticDims<6, 6, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+      } else if(splitEnv < 0 ? static5 : splitEnv != 0) {
         if(static5 && splitEnv == 2)
           games_multi_split_kernel<StaticDims<5, 5, 4>, 2><<<blocks, 3 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
         else if(static5)

@@ -43,12 +43,14 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {  // cpp/core/hash.c
 // Board dimensions: compile-time for the hot 5x5 k=4 configuration (30-bit bitboards in 32-bit registers,
 // every loop unrolls into straight-line code), run-time otherwise (64-bit bitboards, rolled loops: the
 // generic kernel is instruction-cache sensitive).
+template <bool Narrow> struct StaticBB { using type = uint32_t; };
+template <> struct StaticBB<false> { using type = uint64_t; };
 template <int CW, int CH, int CK>
 struct StaticDims {
-  static_assert(CH * (CW + 1) <= 32, "static boards must fit a 32-bit bitboard");
+  static_assert(CH * (CW + 1) <= 64, "static boards must fit a 64-bit bitboard");
   static constexpr bool kStatic = true;
   static constexpr int kUnroll = 16;
-  using BB = uint32_t;
+  using BB = typename StaticBB<(CH * (CW + 1) <= 32)>::type;   // 5x5: 30 bits in a 32-bit register; 6x6: 42 bits
   __device__ __forceinline__ explicit StaticDims(const Geom&) {}
   __device__ __forceinline__ constexpr int W() const { return CW; }
   __device__ __forceinline__ constexpr int H() const { return CH; }
