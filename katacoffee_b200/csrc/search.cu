@@ -165,7 +165,7 @@ __device__ __forceinline__ double warpSumD(double v) {   // butterfly: every lan
 // select: one warp per game descends from the root to a leaf
 // ---------------------------------------------------------------------------------------------
 template <class D>
-__global__ void __launch_bounds__(128, 8) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+__global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
   const D dm(g);
   using BB = typename D::BB;
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
