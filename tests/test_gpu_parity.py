@@ -290,6 +290,11 @@ def check_bf16_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym
         assert np.abs(a - r).max() <= 2.5 * np.abs(b - r).max() + 1e-3, ("T1 max", np.abs(a - r).max(), np.abs(b - r).max())
     gp, gv = postprocessed(oracle, got, recs_sel, HW)
     rp, rv = postprocessed(oracle, ref, recs_sel, HW)
+    # policy KL(fp32 || bf16) over the legal moves: the reference's third acceptance statistic (testnnevalcanary.cpp:417-418:
+    # 99th percentile <= 0.002, max <= 0.004)
+    m = rp > 0
+    kl = np.where(m, rp * (np.log(np.where(m, rp, 1.0)) - np.log(np.where(m, np.maximum(gp, 1e-30), 1.0))), 0.0).sum(1)
+    assert kl.max() <= 0.004 and np.percentile(kl, 99) <= 0.002, ("policy KL", kl.max(), np.percentile(kl, 99))
     if not strict:
         dp, dv = np.abs(gp - rp).max(1), np.abs(gv - rv).max(1)
         assert dv.max() <= 0.05 and np.percentile(dv, 99) <= 0.02, ("T3 winrate", dv.max())
