@@ -306,6 +306,10 @@ typedef struct {
    * temperature is > 0 it replaces temperaturePlies -- edge visits, minus min(subtract, max/64), zero below min(prune, max/64),
    * raised to 1/T, T going from ...Early to chosenMoveTemperature with chosenMoveTemperatureHalflife (selfplay1.cfg:137-141). */
   double chosenMoveTemperature, chosenMoveTemperatureEarly, chosenMoveSubtract, chosenMovePrune;
+  int32_t noPipeline;           /* 0 (default): with the bf16 net and at least two trunk work items per SM pair the games are searched as two
+                                   half batches on two streams, so that one half's select / expand kernels run under the other half's trunk
+                                   kernel; 1: one batch.  Results are identical either way. */
+  int32_t pad2_;
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

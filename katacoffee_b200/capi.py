@@ -65,7 +65,8 @@ class SearchParams(C.Structure):
                 ("rootDirichletNoiseTotalConcentration", C.c_double), ("rootDirichletNoiseWeight", C.c_double),
                 ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
                 ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double), ("valueWeightExponent", C.c_double),
-                ("chosenMoveTemperature", C.c_double), ("chosenMoveTemperatureEarly", C.c_double), ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double)]
+                ("chosenMoveTemperature", C.c_double), ("chosenMoveTemperatureEarly", C.c_double), ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double),
+                ("noPipeline", C.c_int32), ("pad2_", C.c_int32)]
 
 
 class SearchStats(C.Structure):

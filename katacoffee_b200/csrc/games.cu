@@ -773,12 +773,13 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) { return kc
 }  // extern "C"
 
 namespace kc {
-int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev) {
+int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset) {
   KC_CHECK(G && h, "kc_games_eval: null argument");
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const Geom& g = G->geom;
   size_t n = (size_t)g.numGames;
-  if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
+  if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames + rowOffset)) return 1;
+  KC_CHECK(rowOffset == 0 || (kc::handleIsBf16(h) && rowOffset % (2 * g.NB) == 0), "kc_games_eval: a row offset needs the bf16 path and whole work items");
   if(symmetry) KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
   FeatOut fo{};
   fo.symmetry = symmetry ? G->d_sym : nullptr;
@@ -786,14 +787,14 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   StepOut so = stepOutOf(G, true);   // also refreshes legal masks / status / sit-hashes of the evaluated positions
   so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {
-    fo.tiles = (uint4*)kc::handleInputTiles(h);
+    fo.tiles = (uint4*)kc::handleInputTiles(h) + (size_t)(rowOffset / g.NB) * 2 * TILE_ROWS;
     launchGames<false>(G, 3, 0, so, fo);
   } else {
     fo.planes = kc::handleInputNHWC(h); fo.global = kc::handleInputGlobal(h);
     launchGames<false>(G, 2, 0, so, fo);
   }
   KC_CUDA(cudaGetLastError());
-  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr, nDev);
+  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr, nDev, rowOffset);
 }
 }  // namespace kc
 

@@ -632,7 +632,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
 }
 
 template <class K>
-__global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams P) {
+__global__ void __launch_bounds__(K::PAIR ? 512 : K::THREADS, 1) trunk_kernel(const TrunkParams P) {
   constexpr int NT = K::NT;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -676,6 +676,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) trunk_kernel(const TrunkParams 
   if constexpr(K::PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(smem + K::OFF_TMEM);
+  if constexpr(K::PAIR) {
+    // register re-allocation between the warpgroups: the launch takes 128 registers per thread (launch bound 512), the producer /
+    // issuer / relay warpgroup gives back all but 56, the two epilogue warpgroups grow to 160
+    if(warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+  }
 
   if(warp == 0) {
     // =========================== TMA producer (every CTA; pair mode: its half of each weight stage) ===========================

@@ -369,13 +369,15 @@ float* handleInputNHWC(kc_handle* h) { return h->f32.in; }
 float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
 int handleCheckAbort(kc_handle* h) { return checkTrunkAbort(h); }
 void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, const uint32_t* status_dev, const uint64_t* sitHash_dev,
-                       float policyTemperature, float* policy_dev, float* winLoss_dev, float* misc_dev, uint64_t* nnHash_dev, cudaStream_t stream) {
-  k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy, h->d_value, h->d_misc, legal_dev, status_dev, sitHash_dev, n,
+                       float policyTemperature, float* policy_dev, float* winLoss_dev, float* misc_dev, uint64_t* nnHash_dev, cudaStream_t stream,
+                       int rowOffset) {
+  const size_t ro = (size_t)rowOffset;
+  k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy + ro * 4 * h->W * h->H, h->d_value + ro * 2, h->d_misc + ro * 2, legal_dev, status_dev, sitHash_dev, n,
                                                                  4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
 }
-int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev) {
-  h->lastN = n;
-  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, 0, nDev);
+int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev, int rowOffset) {
+  h->lastN = n + rowOffset;
+  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, rowOffset, nDev);
   return runFp32(h, n, stream, sym_dev);
 }
 

@@ -28,6 +28,7 @@
 //  -ffp-contract=off in the oracle), so trees agree exactly whenever the leaf evaluations agree exactly.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "games.h"
@@ -50,6 +51,7 @@ struct SearchCfg {
   int autoRefill;
   int compact;       // leaves that need the net are packed into a dense batch (slot = arrival order); 0: slot = game
   int reuseTree;     // keep the chosen child's subtree for the next search (Search::makeMove)
+  int gOff, gCnt, half;   // the games a per-iteration kernel launch covers: [gOff, gOff + gCnt); half = index of its batch counter
   int graph;         // node-centric statistics (graph search and / or subtree value bias), see "graph mode" below
   int useTable;      // graph mode: look new positions up in the transposition table (SearchParams::useGraphSearch)
   int polOff;        // byte offset of the per-move arrays inside a node
@@ -168,8 +170,9 @@ template <class D>
 __global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
   const D dm(g);
   using BB = typename D::BB;
-  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if(gi >= c.numGames) return;
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
   GameRegs<BB> s;
   s.black = (BB)root.black[gi]; s.white = (BB)root.white[gi]; s.h0 = root.hash0[gi]; s.h1 = root.hash1[gi];
   s.id = root.gameId[gi]; s.misc = root.misc[gi];
@@ -247,14 +250,14 @@ __global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCf
     }
   }
   if(lane == 0) {
-    if(kind != 0) *t.active = 1;
+    if(kind != 0) t.active[c.half] = 1;
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
     t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
     const bool needsNet = kind == 1 || kind == 4;
     // the position handed to the evaluator.  Compact mode: only leaves that need the net take a row, in arrival order
     // (an evaluation does not depend on its row); otherwise row = game and idle rows are evaluated and ignored.
     if(needsNet || !c.compact) {
-      const int slot = c.compact ? atomicAdd(t.evalCount, 1) : gi;
+      const int slot = c.compact ? atomicAdd(t.evalCount + c.half, 1) : li;
       t.leafSlot[gi] = slot;
       leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
       leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
@@ -293,8 +296,9 @@ __global__ void k_hash_eval(int n, int P, int LW, const uint32_t* __restrict__ l
 // expand + backup: one warp per game
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
-  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if(gi >= c.numGames) return;
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
   const int kind = t.leafKind[gi];
   if(kind == 0) return;
   uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
@@ -395,8 +399,9 @@ template <class D>
 __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
   const D dm(g);
   using BB = typename D::BB;
-  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if(gi >= c.numGames) return;
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
   GameRegs<BB> s;
   s.black = (BB)root.black[gi]; s.white = (BB)root.white[gi]; s.h0 = root.hash0[gi]; s.h1 = root.hash1[gi];
   s.id = root.gameId[gi]; s.misc = root.misc[gi];
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
     }
   }
   if(lane == 0) {
-    if(kind != 0) *t.active = 1;
+    if(kind != 0) t.active[c.half] = 1;
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
     t.leafNextPla[gi] = ((flagsOf(s.misc) >> 3) & 3) | (numTurnsOf(s.misc) << 8);   // + the position's depth (stones on the board)
     t.leafKey[2 * (size_t)gi] = key0; t.leafKey[2 * (size_t)gi + 1] = key1;
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
     t.leafTarget[gi] = target;
     const bool needsNet = kind == 1 || kind == 4;
     if(needsNet || !c.compact) {
-      const int slot = c.compact ? atomicAdd(t.evalCount, 1) : gi;
+      const int slot = c.compact ? atomicAdd(t.evalCount + c.half, 1) : li;
       t.leafSlot[gi] = slot;
       leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
       leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
@@ -634,8 +639,9 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
 }
 
 __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
-  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if(gi >= c.numGames) return;
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
   const int kind = t.leafKind[gi];
   if(kind == 0) return;
   uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
@@ -755,8 +761,9 @@ struct DetRng {
 constexpr int MAX_POLICY = 4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN;
 
 __global__ void __launch_bounds__(64) k_root_noise(const SearchCfg c, TreeMem t, State root, int boardArea) {
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  if(gi >= c.numGames) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
   if(t.nodeCount[gi] <= 0 || (flagsOf(root.misc[gi]) & 1)) return;
   NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P, c.polOff};
   if(nd.noised()) return;
@@ -1248,6 +1255,11 @@ struct kc_search {
   kc::TrainMem train = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
+  // half batches (see runVisits): leaf positions of games [halfOff[h], halfOff[h] + halfCnt[h]) on their own stream
+  bool pipelined = false;
+  kc_games* leafHalf[2] = {nullptr, nullptr};
+  int halfOff[2] = {0, 0}, halfCnt[2] = {0, 0};
+  cudaEvent_t evFork = nullptr, evJoin[2] = {nullptr, nullptr};
 };
 
 using namespace kc;
@@ -1269,42 +1281,75 @@ int clearTables(kc_search* S, cudaStream_t st) {
 
 int runVisits(kc_search* S) {
   const SearchCfg& c = S->cfg;
-  kc_games* R = S->root; kc_games* Lf = S->leaf;
-  cudaStream_t st = Lf->stream;
-  const int warpBlocks = (c.numGames * 32 + 127) / 128;
+  kc_games* R = S->root;
+  cudaStream_t st = S->leaf->stream;
   const bool rootPolicyChange = c.graph && (c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0));
+  // One batch (every game, on the search's stream), or two half batches on their own streams: the small kernels of one half
+  // (post-processing, expand / backup, select, root noise) then run while the trunk kernel of the other half has the tensor
+  // cores -- the trunk's launch leaves 16 k registers per SM free for them (setmaxnreg, net_bf16.cu).  Trees of different games
+  // never interact, so the split changes no result.
+  const int nh = S->pipelined ? 2 : 1;
+  struct HalfRun { kc_games* leaf; SearchCfg c; cudaStream_t st; float* policy; float* winLoss; float* misc; uint64_t* nnHash; int rowOff; };
+  HalfRun H[2];
+  for(int h = 0; h < nh; h++) {
+    H[h].leaf = S->pipelined ? S->leafHalf[h] : S->leaf;
+    H[h].c = c;
+    H[h].c.gOff = S->pipelined ? S->halfOff[h] : 0;
+    H[h].c.gCnt = S->pipelined ? S->halfCnt[h] : c.numGames;
+    H[h].c.half = h;
+    H[h].st = H[h].leaf->stream;
+    H[h].rowOff = H[h].c.gOff;
+    H[h].policy = S->d_policy + (size_t)H[h].rowOff * c.P; H[h].winLoss = S->d_winLoss + (size_t)H[h].rowOff * 2;
+    H[h].misc = S->d_misc + (size_t)H[h].rowOff * 2; H[h].nnHash = S->d_nnHash + (size_t)H[h].rowOff * 2;
+  }
+  if(S->pipelined) {
+    KC_CUDA(cudaEventRecord(S->evFork, st));
+    for(int h = 0; h < nh; h++) KC_CUDA(cudaStreamWaitEvent(H[h].st, S->evFork, 0));
+  }
   for(int it = 0; it < c.maxVisits; it++) {
-    // root noise / temperature: once per search, on roots kept by tree re-use (before the first descent) and on roots created by
-    // the first iteration (before the second)
-    if(rootPolicyChange && it <= 1) { k_root_noise<<<(c.numGames + 63) / 64, 64, 0, st>>>(c, S->tree, R->st, R->geom.HW); S->launches++; }
     if(c.reuseTree && it > 0 && (it & 31) == 0) {
       // games that kept a subtree finish their visit budget early: stop once no game had a visit left to make
-      int active = 0;
-      KC_CUDA(cudaMemcpyAsync(&active, S->tree.active, 4, cudaMemcpyDeviceToHost, st));
-      KC_CUDA(cudaStreamSynchronize(st));
-      if(!active) break;
-      KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
+      int active[2] = {0, 0};
+      for(int h = 0; h < nh; h++) KC_CUDA(cudaMemcpyAsync(&active[h], S->tree.active + h, 4, cudaMemcpyDeviceToHost, H[h].st));
+      for(int h = 0; h < nh; h++) KC_CUDA(cudaStreamSynchronize(H[h].st));
+      if(!active[0] && !active[1]) break;
+      for(int h = 0; h < nh; h++) KC_CUDA(cudaMemsetAsync(S->tree.active + h, 0, 4, H[h].st));
     }
-    if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount, 0, 4, st));
-    if(c.graph) {
-      if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
-      else k_select_graph<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
-    } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
-    else k_select<DynDims><<<warpBlocks, 128, 0, st>>>(R->geom, c, R->st, Lf->st, S->tree, R->d_zob);
-    S->launches++;
-    if(S->handle) {
-      if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount : nullptr)) return 1;
-      kc::launchPostprocess(S->handle, c.numGames, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, S->d_policy, S->d_winLoss, S->d_misc, S->d_nnHash, st);
-      S->launches += 3;
-    } else {
-      if(kc::gamesRefreshOutputs(Lf)) return 1;
-      k_hash_eval<<<warpBlocks, 128, 0, st>>>(c.numGames, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, S->d_policy, S->d_winLoss);
-      S->launches += 2;
+    for(int h = 0; h < nh; h++) {
+      const SearchCfg& ch = H[h].c;
+      kc_games* Lf = H[h].leaf;
+      cudaStream_t hs = H[h].st;
+      const int warpBlocks = (ch.gCnt * 32 + 127) / 128;
+      // root noise / temperature: once per search, on roots kept by tree re-use (before the first descent) and on roots created
+      // by the first iteration (before the second)
+      if(rootPolicyChange && it <= 1) { k_root_noise<<<(ch.gCnt + 63) / 64, 64, 0, hs>>>(ch, S->tree, R->st, R->geom.HW); S->launches++; }
+      if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount + h, 0, 4, hs));
+      if(c.graph) {
+        if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
+        else k_select_graph<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
+      } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
+      else k_select<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
+      S->launches++;
+      if(S->handle) {
+        if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff)) return 1;
+        kc::launchPostprocess(S->handle, ch.gCnt, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, H[h].policy, H[h].winLoss, H[h].misc, H[h].nnHash, hs,
+                              H[h].rowOff);
+        S->launches += 3;
+      } else {
+        if(kc::gamesRefreshOutputs(Lf)) return 1;
+        k_hash_eval<<<warpBlocks, 128, 0, hs>>>(ch.gCnt, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, H[h].policy, H[h].winLoss);
+        S->launches += 2;
+      }
+      if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
+      else k_expand_backup<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
+      S->launches++;
     }
-    if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
-    else k_expand_backup<<<warpBlocks, 128, 0, st>>>(c, S->tree, S->d_policy, S->d_winLoss);
-    S->launches++;
   }
+  if(S->pipelined)
+    for(int h = 0; h < nh; h++) {
+      KC_CUDA(cudaEventRecord(S->evJoin[h], H[h].st));
+      KC_CUDA(cudaStreamWaitEvent(st, S->evJoin[h], 0));
+    }
   KC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1366,13 +1411,13 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     KC_CUDA(cudaMalloc(&S->tree.nodesAlt, treeBytes / 2));
     KC_CUDA(cudaMalloc(&S->tree.rerootQueue, n * c.maxNodes * 4));
   }
-  KC_CUDA(cudaMalloc(&S->tree.active, 4)); KC_CUDA(cudaMemset(S->tree.active, 0, 4));
+  KC_CUDA(cudaMalloc(&S->tree.active, 8)); KC_CUDA(cudaMemset(S->tree.active, 0, 8));
   KC_CUDA(cudaMalloc(&S->tree.nodeCount, n * 4)); KC_CUDA(cudaMemset(S->tree.nodeCount, 0, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.pathNode, n * MAX_PATH * 4)); KC_CUDA(cudaMalloc(&S->tree.pathPos, n * MAX_PATH));
   KC_CUDA(cudaMalloc(&S->tree.pathLen, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafKind, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.leafValue, n * 8)); KC_CUDA(cudaMalloc(&S->tree.leafNextPla, n * 4));
   KC_CUDA(cudaMalloc(&S->tree.leafSlot, n * 4)); KC_CUDA(cudaMemset(S->tree.leafSlot, 0, n * 4));
-  KC_CUDA(cudaMalloc(&S->tree.evalCount, 4)); KC_CUDA(cudaMemset(S->tree.evalCount, 0, 4));
+  KC_CUDA(cudaMalloc(&S->tree.evalCount, 8)); KC_CUDA(cudaMemset(S->tree.evalCount, 0, 8));
   KC_CUDA(cudaMalloc(&S->tree.stats, NUM_STATS * 8)); KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
   if(c.graph) {
     {   // DistributionTable of the Student-t cdf, 3 degrees of freedom, closed form (search.cpp:111-116, distributiontable.cpp)
@@ -1402,6 +1447,20 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
   KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
   KC_CUDA(cudaEventCreate(&S->ev0)); KC_CUDA(cudaEventCreate(&S->ev1));
+  {
+    // two half batches when each still gives every SM pair a work item of the trunk kernel (bf16 path with device-side batching);
+    // KC_SEARCH_PIPELINE=0 keeps one batch
+    static const bool allow = [] { const char* e = getenv("KC_SEARCH_PIPELINE"); return !e || atoi(e) != 0; }();
+    const int item = 2 * kc::boardsPerTile(xSize, ySize);                 // boards per CTA work item
+    const int half = ((numGames + 1) / 2 + item - 1) / item * item;
+    if(allow && !p->noPipeline && c.compact && half >= item * ctx->smCount && numGames - half > 0) {
+      S->pipelined = true;
+      S->halfOff[0] = 0; S->halfCnt[0] = half; S->halfOff[1] = half; S->halfCnt[1] = numGames - half;
+      for(int h = 0; h < 2; h++) if(kc_games_create(ctx, S->halfCnt[h], xSize, ySize, winLen, &S->leafHalf[h])) return 1;
+      KC_CUDA(cudaEventCreateWithFlags(&S->evFork, cudaEventDisableTiming));
+      for(int h = 0; h < 2; h++) KC_CUDA(cudaEventCreateWithFlags(&S->evJoin[h], cudaEventDisableTiming));
+    }
+  }
   *out = S;
   return 0;
 }
@@ -1422,6 +1481,8 @@ int kc_search_destroy(kc_search* S) {
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
+  for(int h = 0; h < 2; h++) { if(S->leafHalf[h]) { cudaStreamSynchronize(S->leafHalf[h]->stream); kc_games_destroy(S->leafHalf[h]); } if(S->evJoin[h]) cudaEventDestroy(S->evJoin[h]); }
+  if(S->evFork) cudaEventDestroy(S->evFork);
   kc_games_destroy(S->root); kc_games_destroy(S->leaf);
   delete S;
   return 0;
@@ -1507,7 +1568,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
       S->launches++;
     }
     if(!c.reuseTree) KC_CUDA(cudaMemsetAsync(S->tree.nodeCount, 0, (size_t)c.numGames * 4, st));
-    KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 4, st));
+    KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 8, st));
     if(!c.reuseTree && clearTables(S, st)) return 1;   // with re-use the re-rooting keeps the tables in step with the graph
     if(runVisits(S)) return 1;
     if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
@@ -1612,6 +1673,11 @@ int kc_search_tree_digest(kc_search* S, uint64_t* digest) {
   return 0;
 }
 
-int64_t kc_search_launch_count(const kc_search* S) { return S ? S->launches + kc_games_launch_count(S->leaf) : 0; }
+int64_t kc_search_launch_count(const kc_search* S) {
+  if(!S) return 0;
+  int64_t n = S->launches + kc_games_launch_count(S->leaf);
+  for(int h = 0; h < 2; h++) if(S->leafHalf[h]) n += kc_games_launch_count(S->leafHalf[h]);
+  return n;
+}
 
 }  // extern "C"

@@ -15,5 +15,7 @@ s.reset(seed=1)
 lane = np.arange(G)
 for t in range(20):
     s.games.step(np.where(lane % 20 > t, -2, -1).astype(np.int16))
+h.trunkTime()
 st, _, ms = s.play(1)
-print(f"{ms/V:.3f} ms/iteration, net evals {st.netEvals/st.visits:.3f} of visits")
+tms, tcnt = h.trunkTime()
+print(f"{ms/V:.3f} ms/iteration, net evals {st.netEvals/st.visits:.3f} of visits; trunk launches {tcnt}, {tms/V:.3f} ms of trunk per iteration")

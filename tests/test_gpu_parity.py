@@ -834,6 +834,42 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_search_half_batch_pipeline_changes_nothing(ctx, graph):
+    """With the bf16 net and enough games the search runs two half batches on two streams (select / expand of one half under
+    the trunk kernel of the other).  Trees of different games never interact and an evaluation does not depend on its row, so
+    moves, root statistics and counters are identical to the single-batch run."""
+    from katacoffee_b200 import backend, modeldesc, capi
+    W = H = 5
+    G, V = 2 * 148 * 8 + 40, 24          # two uneven halves, each at least one trunk work item per SM
+    lm = backend.LoadedModel(ctx, modeldesc.Model("b2c32", seed=12))
+    h = backend.createComputeHandle(ctx, lm, G, W, H)
+    kw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8, rootNoiseEnabled=1,
+              rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, valueWeightExponent=0.5) if graph else {}
+    res = []
+    for nopipe in (1, 0):
+        s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, temperaturePlies=8, reuseTree=True, noPipeline=nopipe, **kw)
+        s.reset(seed=31)
+        lane = np.arange(G)
+        for t in range(12):
+            s.games.step(np.where(lane % 12 > t, -2, -1).astype(np.int16))
+        st = capi.SearchStats()
+        moves = []
+        for _ in range(4):
+            _, chosen, _ = s.play(1, st)
+            moves.append(chosen.copy())
+        s.runVisits()
+        root = s.readRoot()
+        res.append((np.stack(moves), root, (st.visits, st.netEvals, st.terminalVisits, st.transpositionHits, st.catchUpVisits, st.gamesFinished)))
+        s.close()
+    assert (res[0][0] == res[1][0]).all()
+    for k in ("rootVisits", "rootUtilitySum", "edgeVisits", "edgeUtilitySum", "policy", "order"):
+        assert (res[0][1][k] == res[1][1][k]).all(), k
+    assert res[0][2] == res[1][2]
+    h.close(); lm.close()
+
+
+@pytest.mark.gpu
 def test_search_graph_selfplay_counters_match_oracle(ctx, oracle):
     """Self-play with graph search + subtree value bias: moves, results and the visit / evaluation / transposition /
     catch-up counters equal the oracle's, move after move to the end of the games."""
