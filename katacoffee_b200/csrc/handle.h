@@ -14,6 +14,7 @@ struct kc_handle {
   kc_ctx* ctx = nullptr;
   const kc_model* model = nullptr;
   int maxBatch = 0, W = 0, H = 0;
+  bool leaveRegisters = false;   // launch the trunk variant that leaves registers to co-resident kernels (set by a pipelined search)
   unsigned flags = 0;
   bool bf16 = true;
   cudaStream_t stream = nullptr;

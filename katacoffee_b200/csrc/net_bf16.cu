@@ -52,10 +52,11 @@ constexpr int MAX_V2 = 128;
 // 128 activation rows from each CTA, the weight block split in halves between the two shared memories), so each SM reads
 // and stages only half of the weights: shared-memory operand traffic drops from 128 to 96 B/clk and the L2 -> SM weight
 // stream halves.
-template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false>
+template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false>
 struct TrunkCfg {
   static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_;
   static constexpr bool PAIR = PAIR_;
+  static constexpr bool REALLOC = REALLOC_;   // launch with 128 registers per thread and re-allocate between the warpgroups (setmaxnreg)
   static constexpr int NCTA = PAIR ? 2 : 1;
   static constexpr int NCH = MAXC / 16;                       // 16-channel chunks the epilogue publishes
   static constexpr int MAXG = MAXC / 4 < 32 ? 32 : MAXC / 3;  // gpool channels: 32 (c128), 64 (c192)
@@ -85,6 +86,7 @@ struct TrunkCfg {
 };
 using Cfg128 = TrunkCfg<128, 2, 7>;
 using Cfg128P = TrunkCfg<128, 2, 14, true>;
+using Cfg128PR = TrunkCfg<128, 2, 14, true, true>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
@@ -632,7 +634,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
 }
 
 template <class K>
-__global__ void __launch_bounds__(K::PAIR ? 512 : K::THREADS, 1) trunk_kernel(const TrunkParams P) {
+__global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel(const TrunkParams P) {
   constexpr int NT = K::NT;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(K::PAIR ? 512 : K::THREADS, 1) trunk_kernel(co
   if constexpr(K::PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(smem + K::OFF_TMEM);
-  if constexpr(K::PAIR) {
+  if constexpr(K::REALLOC) {
     // register re-allocation between the warpgroups: the launch takes 128 registers per thread (launch bound 512), the producer /
     // issuer / relay warpgroup gives back all but 56, the two epilogue warpgroups grow to 160
     if(warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -1114,6 +1116,7 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PR::SMEM));
   return 0;
 }
 void freeTrunkBuffers(kc_handle* h) {
@@ -1192,7 +1195,10 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
+    // the re-allocating variant only where something wants to run beside the trunk (the search's half batches); KC_TRUNK_REALLOC forces
+    static const int reallocEnv = [] { const char* e = getenv("KC_TRUNK_REALLOC"); return e ? atoi(e) : -1; }();
+    if(reallocEnv >= 0 ? reallocEnv != 0 : h->leaveRegisters) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128PR>, P));
+    else KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
   }
   else if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
   else trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);

@@ -375,6 +375,7 @@ void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, c
   k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy + ro * 4 * h->W * h->H, h->d_value + ro * 2, h->d_misc + ro * 2, legal_dev, status_dev, sitHash_dev, n,
                                                                  4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
 }
+void handleLeaveRegisters(kc_handle* h, bool on) { h->leaveRegisters = on; }
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev, int rowOffset) {
   h->lastN = n + rowOffset;
   if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, rowOffset, nDev);

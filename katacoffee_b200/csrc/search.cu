@@ -1455,6 +1455,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     const int half = ((numGames + 1) / 2 + item - 1) / item * item;
     if(allow && !p->noPipeline && c.compact && half >= item * ctx->smCount && numGames - half > 0) {
       S->pipelined = true;
+      kc::handleLeaveRegisters(handleOrNull, true);
       S->halfOff[0] = 0; S->halfCnt[0] = half; S->halfOff[1] = half; S->halfCnt[1] = numGames - half;
       for(int h = 0; h < 2; h++) if(kc_games_create(ctx, S->halfCnt[h], xSize, ySize, winLen, &S->leafHalf[h])) return 1;
       KC_CUDA(cudaEventCreateWithFlags(&S->evFork, cudaEventDisableTiming));
