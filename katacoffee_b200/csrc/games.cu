@@ -50,11 +50,13 @@ struct FeatOut {
 };
 
 template <bool DO_STEP, int FEAT, class D>
-__global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
+__global__ void __launch_bounds__(FEAT >= 3 ? TB_TILES : TB_PLAIN) games_kernel(const Geom g, State st, const int16_t* __restrict__ moves,
                                                         int useMoves, const uint64_t* __restrict__ zob,
                                                         StepOut so, FeatOut fo) {
-  constexpr int THREADS = FEAT == 3 ? TB_TILES : TB_PLAIN;
-  constexpr int GPB = FEAT == 3 ? 32 : TB_PLAIN;       // most games a CTA can hold
+  constexpr int THREADS = FEAT >= 3 ? TB_TILES : TB_PLAIN;
+  // most games a CTA can hold.  FEAT 4 = FEAT 3 (bf16 trunk tiles) with one work item (two tiles) per CTA: 1.5 KB of shared memory, so the
+  // kernel fits beside a resident trunk kernel (the search's half batches)
+  constexpr int GPB = FEAT == 3 ? 32 : FEAT == 4 ? 8 : TB_PLAIN;
   __shared__ uint64_t sPlanes[15][GPB + 1];
   __shared__ uint8_t sSrcPad[8][52];   // [symmetry][dst cell] -> padded bit index of the source cell
   __shared__ int8_t sSym[GPB];
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(FEAT == 3 ? TB_TILES : TB_PLAIN) games_kernel(
     }
     for(int e = (nvec << 2) + t; e < total; e += THREADS) out[e] = elem(e);
     if(fo.global && t < ng) fo.global[gBase + t] = (float)dm.K();   // nninputs.cpp:656
-  } else if(FEAT == 3) {
+  } else if(FEAT >= 3) {
     // trunk input tiles: row = y*tileRowW + b*(W+1) + x, 16 bf16 channels per row as two 16 B chunks
     // (channels 0..14 = V1 planes, channel 15 = the global feature win_len broadcast on board cells)
     const int ntiles = (ng + g.NB - 1) / g.NB;
@@ -552,12 +554,13 @@ void launchGamesD(kc_games* G, int feat, int useMoves, const StepOut& so, const 
     case 0: games_kernel<DO_STEP, 0, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
     case 1: games_kernel<DO_STEP, 1, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
     case 2: games_kernel<DO_STEP, 2, D><<<blocks, TB_PLAIN, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
-    default: games_kernel<DO_STEP, 3, D><<<blocks, TB_TILES, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    case 3: games_kernel<DO_STEP, 3, D><<<blocks, TB_TILES, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
+    default: games_kernel<DO_STEP, 4, D><<<blocks, TB_TILES, 0, G->stream>>>(G->geom, G->st, G->d_moves, useMoves, G->d_zob, so, fo); break;
   }
 }
 template <bool DO_STEP>
 void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
-  int gpb = feat == 3 ? G->geom.NB * 8 : TB_PLAIN;   // FEAT 3: whole trunk tiles per CTA
+  int gpb = feat == 3 ? G->geom.NB * 8 : feat == 4 ? G->geom.NB * 2 : TB_PLAIN;   // FEAT 3 / 4: whole trunk tiles per CTA
   fo.gamesPerBlock = gpb;
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
   const Geom& g = G->geom;
@@ -773,7 +776,7 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) { return kc
 }  // extern "C"
 
 namespace kc {
-int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset) {
+int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset, bool smallCtas) {
   KC_CHECK(G && h, "kc_games_eval: null argument");
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const Geom& g = G->geom;
@@ -788,7 +791,7 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {
     fo.tiles = (uint4*)kc::handleInputTiles(h) + (size_t)(rowOffset / g.NB) * 2 * TILE_ROWS;
-    launchGames<false>(G, 3, 0, so, fo);
+    launchGames<false>(G, smallCtas ? 4 : 3, 0, so, fo);
   } else {
     fo.planes = kc::handleInputNHWC(h); fo.global = kc::handleInputGlobal(h);
     launchGames<false>(G, 2, 0, so, fo);

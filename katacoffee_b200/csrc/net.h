@@ -25,6 +25,7 @@ float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 // pointer, may be null) is used for the inverse symmetry of the spatial outputs.
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev, const int* nDev = nullptr, int rowOffset = 0);   // nDev, rowOffset: bf16 path only
 int handleCheckAbort(kc_handle* h);   // after a synchronise
+bool handleCanLeaveRegisters(const kc_handle* h);
 void handleLeaveRegisters(kc_handle* h, bool on);   // bf16 pair-mode trunk: use the setmaxnreg variant (16 k registers per SM stay free)
 // NNEvaluator::evaluate post-processing (nneval.cpp:702-815) of the handle's last outputs, on `stream`
 void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, const uint32_t* status_dev, const uint64_t* sitHash_dev,

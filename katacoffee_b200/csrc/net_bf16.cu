@@ -1144,6 +1144,10 @@ int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev,
   return 0;
 }
 
+static bool trunkUsesPairs() { static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }(); return usePair; }
+// true if this handle's trunk kernel has a variant that leaves registers to co-resident kernels (pair mode, trunks up to 128 channels)
+bool handleCanLeaveRegisters(const kc_handle* h) { return h->bf16 && h->model->trunk && h->model->trunk->cfg == 0 && trunkUsesPairs(); }
+
 int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset, const int* nDev) {
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
@@ -1179,7 +1183,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   bool timed = (int)h->evPool.size() >= h->evUsed + 2;
   if(timed) cudaEventRecord(h->evPool[h->evUsed], st);
   // CTA pairs (cta_group::2) are the default for trunks up to 128 channels; KC_TRUNK_PAIR=0 selects the single-CTA kernel
-  static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }();
+  const bool usePair = trunkUsesPairs();
   // tile skew (see TrunkParams::skew): 5 of the 14 ring stages in pair mode, measured +1.5 % burst / +1 % under the power cap
   // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
   static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();

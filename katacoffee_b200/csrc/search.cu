@@ -1331,7 +1331,7 @@ int runVisits(kc_search* S) {
       else k_select<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
       S->launches++;
       if(S->handle) {
-        if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff)) return 1;
+        if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff, S->pipelined)) return 1;
         kc::launchPostprocess(S->handle, ch.gCnt, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, H[h].policy, H[h].winLoss, H[h].misc, H[h].nnHash, hs,
                               H[h].rowOff);
         S->launches += 3;
@@ -1453,7 +1453,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     static const bool allow = [] { const char* e = getenv("KC_SEARCH_PIPELINE"); return !e || atoi(e) != 0; }();
     const int item = 2 * kc::boardsPerTile(xSize, ySize);                 // boards per CTA work item
     const int half = ((numGames + 1) / 2 + item - 1) / item * item;
-    if(allow && !p->noPipeline && c.compact && half >= item * ctx->smCount && numGames - half > 0) {
+    if(allow && !p->noPipeline && c.compact && kc::handleCanLeaveRegisters(handleOrNull) && half >= item * ctx->smCount && numGames - half > 0) {
       S->pipelined = true;
       kc::handleLeaveRegisters(handleOrNull, true);
       S->halfOff[0] = 0; S->halfCnt[0] = half; S->halfOff[1] = half; S->halfCnt[1] = numGames - half;
