@@ -117,3 +117,64 @@ def test_literal_graph_hash_is_path_dependent(oracle):
     g2, h2 = chain([p(2, 0, 1), p(1, 0, 1), p(0, 0, 1), p(4, 0, 1)])
     assert tuple(g1.sit_hash()) == tuple(g2.sit_hash())
     assert tuple(h1) != tuple(h2)
+
+
+SELFPLAY_OPTS = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1,
+                     rootPolicyTemperatureEarly=1.25, chosenMoveTemperatureHalflife=19.0)
+
+
+def test_oracle_root_noise_is_a_deterministic_dirichlet_mixture(oracle):
+    """Root noise / temperature of the oracle search (the definition the device reproduces bit for bit): a probability vector over
+    exactly the legal moves, a pure function of (seed, game id, ply), different for another game id, and on average
+    0.75 * policy + 0.25 * alpha with alpha the shaped Dirichlet mean (searchhelpers.cpp:51-120)."""
+    og = _midgame(oracle, 5, 5, 4, 3, 1, 4)
+    base = oracle.search_run_graph(og, 1)["policy"]
+    a = oracle.search_run_graph(og, 1, noiseSeed=5, noiseGameId=9, **SELFPLAY_OPTS)["policy"]
+    b = oracle.search_run_graph(og, 1, noiseSeed=5, noiseGameId=9, **SELFPLAY_OPTS)["policy"]
+    c = oracle.search_run_graph(og, 1, noiseSeed=5, noiseGameId=10, **SELFPLAY_OPTS)["policy"]
+    assert (a == b).all() and (a != c).any() and (a != base).any()
+    assert ((a < 0) == (base < 0)).all() and abs(float(a[a >= 0].sum()) - 1.0) < 1e-5
+    legal = base >= 0
+    p = base[legal].astype(np.float64)
+    la = np.log(np.minimum(0.01, p) + 1e-20)
+    la = np.maximum(0.0, la - la.mean())
+    alpha = 0.5 * (la / la.sum() + 1.0 / legal.sum()) if la.sum() > 0 else np.full(legal.sum(), 1.0 / legal.sum())
+    acc, n = np.zeros(legal.sum()), 400
+    for k in range(n):
+        acc += oracle.search_run_graph(og, 1, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25,
+                                       noiseSeed=11, noiseGameId=k)["policy"][legal]
+    assert np.abs(acc / n - (0.75 * p + 0.25 * alpha)).max() < 0.006
+
+
+def test_oracle_move_choice_temperature_schedule(oracle):
+    """chooseIndexWithTemperature restated (searchhelpers.cpp:12-49): T -> 0 picks the most visited move, prune removes rarely
+    visited moves, and at T = 1 the choice frequencies follow the visit counts."""
+    P = 100
+    ev = np.zeros(P, np.int32); order = np.full(P, 255, np.uint8)
+    ev[[3, 40, 77, 90]] = [60, 25, 14, 1]; order[[3, 40, 77, 90]] = [0, 1, 2, 3]
+    assert oracle.search_choose_temperature(ev, order, 25, 0, 0.0, 0.0, 19.0, 0.0, 0.0, 1, 1) == 3
+    counts = {3: 0, 40: 0, 77: 0, 90: 0}
+    for gid in range(3000):
+        counts[oracle.search_choose_temperature(ev, order, 25, 0, 1.0, 1.0, 19.0, 0.0, 0.0, 7, gid)] += 1
+    assert abs(counts[3] / 3000 - 0.60) < 0.03 and abs(counts[40] / 3000 - 0.25) < 0.03 and 0 < counts[90] < 90
+    pruned = [oracle.search_choose_temperature(ev, order, 25, 0, 1.0, 1.0, 19.0, 0.0, 1.0, 7, gid) for gid in range(3000)]
+    assert 90 in pruned            # prune is min(1, max/64 = 0.94): a move with one visit survives (the reference's "< amountToPrune")
+    pruned2 = [oracle.search_choose_temperature(ev * 2, order, 25, 0, 1.0, 1.0, 19.0, 0.0, 2.0, 7, gid) for gid in range(3000)]
+    assert 90 in pruned2 and pruned2.count(3) > pruned2.count(40) > pruned2.count(77)
+    # the schedule cools down with the turn number: late in the game the choice is nearly greedy
+    late = [oracle.search_choose_temperature(ev, order, 25, 200, 0.75, 0.05, 19.0, 0.0, 0.0, 7, gid) for gid in range(500)]
+    assert late.count(3) >= 495
+
+
+def test_oracle_value_weighting_and_fpu_options_run(oracle):
+    """valueWeightExponent / fpuParentWeightByVisitedPolicy / rootDesiredPerChildVisitsCoeff: searches complete with the visit
+    budget spent and differ from the plain search."""
+    og = _midgame(oracle, 5, 5, 4, 3, 2, 6)
+    plain = oracle.search_run_graph(og, 300)
+    for opts in (dict(valueWeightExponent=0.5), dict(fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=2.0),
+                 dict(rootDesiredPerChildVisitsCoeff=2.0)):
+        r = oracle.search_run_graph(og, 300, **opts)
+        assert r["rootVisits"] == 300 and r["edgeVisits"].sum() == 299
+        assert r["digest"] != plain["digest"]
+    wide = oracle.search_run_graph(og, 300, rootDesiredPerChildVisitsCoeff=2.0)
+    assert (wide["edgeVisits"] > 0).sum() >= (plain["edgeVisits"] > 0).sum()    # the coefficient funnels visits into more root children
