@@ -309,7 +309,10 @@ typedef struct {
   int32_t noPipeline;           /* 0 (default): with the bf16 net and at least two trunk work items per SM pair the games are searched as two
                                    half batches on two streams, so that one half's select / expand kernels run under the other half's trunk
                                    kernel; 1: one batch.  Results are identical either way. */
-  int32_t pad2_;
+  int32_t nnRandomize;          /* NNEvaluator's nnRandomize (cpp/neuralnet/nneval.cpp:515-524): every leaf is evaluated under one of the 8
+                                   symmetries (inputs symmetrised, outputs mapped back).  The symmetry is drawn from the position's sit-hash
+                                   and the seed, not from a shared stream, so a position gets the same one whichever game reaches it.  With a
+                                   KC_FLAG_SYM_PERMUTE_DIRS handle it is a true symmetry of the game; without, the reference backends' spatial copy. */
 } kc_search_params;
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;

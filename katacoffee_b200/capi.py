@@ -66,7 +66,7 @@ class SearchParams(C.Structure):
                 ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
                 ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double), ("valueWeightExponent", C.c_double),
                 ("chosenMoveTemperature", C.c_double), ("chosenMoveTemperatureEarly", C.c_double), ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double),
-                ("noPipeline", C.c_int32), ("pad2_", C.c_int32)]
+                ("noPipeline", C.c_int32), ("nnRandomize", C.c_int32)]
 
 
 class SearchStats(C.Structure):

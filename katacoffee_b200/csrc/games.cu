@@ -643,7 +643,7 @@ int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen,
   KC_CUDA(cudaMalloc(&G->d_stats, 8 * 8));
   KC_CUDA(cudaMemset(G->d_stats, 0, 64));
   KC_CUDA(cudaMalloc(&G->d_planes, n * 15 * g.HW * 4)); KC_CUDA(cudaMalloc(&G->d_global, n * 4));
-  KC_CUDA(cudaMalloc(&G->d_sym, n));
+  KC_CUDA(cudaMalloc(&G->d_sym, n)); KC_CUDA(cudaMemset(G->d_sym, 0, n));
   KC_CUDA(cudaStreamCreateWithFlags(&G->stream, cudaStreamNonBlocking));
   KC_CUDA(cudaEventCreate(&G->ev0)); KC_CUDA(cudaEventCreate(&G->ev1));
   *out = G;
@@ -776,7 +776,7 @@ int kc_games_eval(kc_games* G, kc_handle* h, const int8_t* symmetry) { return kc
 }  // extern "C"
 
 namespace kc {
-int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset, bool smallCtas) {
+int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset, bool smallCtas, bool symOnDevice) {
   KC_CHECK(G && h, "kc_games_eval: null argument");
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const Geom& g = G->geom;
@@ -784,9 +784,10 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames + rowOffset)) return 1;
   KC_CHECK(rowOffset == 0 || (kc::handleIsBf16(h) && rowOffset % (2 * g.NB) == 0), "kc_games_eval: a row offset needs the bf16 path and whole work items");
   if(symmetry) KC_CUDA(cudaMemcpyAsync(G->d_sym, symmetry, n, cudaMemcpyHostToDevice, G->stream));
+  const bool haveSym = symmetry != nullptr || symOnDevice;   // symOnDevice: d_sym was filled by a kernel (the search's nnRandomize)
   FeatOut fo{};
-  fo.symmetry = symmetry ? G->d_sym : nullptr;
-  fo.permuteDirs = (symmetry && kc::handlePermutesDirs(h)) ? 1 : 0;
+  fo.symmetry = haveSym ? G->d_sym : nullptr;
+  fo.permuteDirs = (haveSym && kc::handlePermutesDirs(h)) ? 1 : 0;
   StepOut so = stepOutOf(G, true);   // also refreshes legal masks / status / sit-hashes of the evaluated positions
   so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {
@@ -797,7 +798,7 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
     launchGames<false>(G, 2, 0, so, fo);
   }
   KC_CUDA(cudaGetLastError());
-  return kc::handleRunOnStream(h, g.numGames, G->stream, symmetry ? G->d_sym : nullptr, nDev, rowOffset);
+  return kc::handleRunOnStream(h, g.numGames, G->stream, haveSym ? G->d_sym : nullptr, nDev, rowOffset, /*symIsLocal=*/true);
 }
 }  // namespace kc
 

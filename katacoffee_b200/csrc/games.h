@@ -31,5 +31,5 @@ struct kc_games {
 namespace kc {
 int gamesRefreshOutputs(kc_games* G);   // games.cu: launches on G->stream, does not synchronise
 // kc_games_eval with an optional device-side row count (bf16 path): only the first *nDev lanes are evaluated
-int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset = 0, bool smallCtas = false);
+int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev, int rowOffset = 0, bool smallCtas = false, bool symOnDevice = false);
 }

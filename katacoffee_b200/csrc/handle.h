@@ -48,6 +48,6 @@ void freeTrunkBuffers(kc_handle* h);
 // rowOffset (a multiple of 2*NB rows) selects a chunk of the batch: inputs, tiles and outputs are all offset by it
 int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev, cudaStream_t st, int rowOffset = 0);
 // nDev (device pointer, may be null): the live row count of a batch that was compacted on the device; n is then its upper bound
-int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset = 0, const int* nDev = nullptr);
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset = 0, const int* nDev = nullptr, bool symIsLocal = false);
 int checkTrunkAbort(kc_handle* h);   // after a synchronise: non-zero (and error set) if the kernel bailed out
 }  // namespace kc

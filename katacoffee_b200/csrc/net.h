@@ -23,7 +23,8 @@ float* handleInputNHWC(kc_handle* h);      // fp32 path: [n][H*W][15]
 float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 // Runs the net on the handle's (already symmetrised) input buffer on `stream`; symmetry_dev (device
 // pointer, may be null) is used for the inverse symmetry of the spatial outputs.
-int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev, const int* nDev = nullptr, int rowOffset = 0);   // nDev, rowOffset: bf16 path only
+int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev, const int* nDev = nullptr, int rowOffset = 0,
+                      bool symIsLocal = false);   // nDev, rowOffset: bf16 path only; symIsLocal: symmetry_dev[0] belongs to row rowOffset
 int handleCheckAbort(kc_handle* h);   // after a synchronise
 bool handleCanLeaveRegisters(const kc_handle* h);
 void handleLeaveRegisters(kc_handle* h, bool on);   // bf16 pair-mode trunk: use the setmaxnreg variant (16 k registers per SM stay free)

@@ -1148,7 +1148,7 @@ static bool trunkUsesPairs() { static const bool usePair = [] { const char* e = 
 // true if this handle's trunk kernel has a variant that leaves registers to co-resident kernels (pair mode, trunks up to 128 channels)
 bool handleCanLeaveRegisters(const kc_handle* h) { return h->bf16 && h->model->trunk && h->model->trunk->cfg == 0 && trunkUsesPairs(); }
 
-int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset, const int* nDev) {
+int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, int rowOffset, const int* nDev, bool symIsLocal) {
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
   TrunkParams P{};
@@ -1162,7 +1162,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.n = n;
   P.nDev = nDev;
   P.tiles = (const uint4*)h->d_tiles + (size_t)(rowOffset / P.NB) * 2 * TILE_ROWS;
-  P.sym = sym_dev ? sym_dev + rowOffset : nullptr; P.dstOfSrcRev = h->d_dstOfSrcRev;
+  P.sym = sym_dev ? sym_dev + (symIsLocal ? 0 : rowOffset) : nullptr; P.dstOfSrcRev = h->d_dstOfSrcRev;
   P.policy = h->d_policy + (size_t)rowOffset * 4 * P.HW; P.value = h->d_value + (size_t)rowOffset * 2;
   P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;

@@ -376,9 +376,9 @@ void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, c
                                                                  4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
 }
 void handleLeaveRegisters(kc_handle* h, bool on) { h->leaveRegisters = on; }
-int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev, int rowOffset) {
+int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev, int rowOffset, bool symIsLocal) {
   h->lastN = n + rowOffset;
-  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, rowOffset, nDev);
+  if(h->bf16) return runTrunkBf16(h, n, stream, sym_dev, rowOffset, nDev, symIsLocal);
   return runFp32(h, n, stream, sym_dev);
 }
 

@@ -39,6 +39,7 @@ namespace kc {
 constexpr int MAX_PATH = 52;   // a 7x7 game has at most 49 plies
 constexpr uint64_t PHI = 0x9E3779B97F4A7C15ULL;
 constexpr uint64_t CHOOSE_SALT = 0xC0FFEE5EA4C4ULL;
+constexpr uint64_t SYM_SALT = 0x5A11E7C0FFEEULL;
 
 struct SearchCfg {
   int P;             // policy size 4*H*W
@@ -51,6 +52,7 @@ struct SearchCfg {
   int autoRefill;
   int compact;       // leaves that need the net are packed into a dense batch (slot = arrival order); 0: slot = game
   int reuseTree;     // keep the chosen child's subtree for the next search (Search::makeMove)
+  int randomSym;     // NNEvaluator's nnRandomize: every leaf is evaluated under a symmetry drawn from its position (nneval.cpp:515-524)
   int gOff, gCnt, half;   // the games a per-iteration kernel launch covers: [gOff, gOff + gCnt); half = index of its batch counter
   int graph;         // node-centric statistics (graph search and / or subtree value bias), see "graph mode" below
   int useTable;      // graph mode: look new positions up in the transposition table (SearchParams::useGraphSearch)
@@ -167,7 +169,7 @@ __device__ __forceinline__ double warpSumD(double v) {   // butterfly: every lan
 // select: one warp per game descends from the root to a leaf
 // ---------------------------------------------------------------------------------------------
 template <class D>
-__global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+__global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob, int8_t* __restrict__ leafSym) {
   const D dm(g);
   using BB = typename D::BB;
   const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -261,6 +263,10 @@ __global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCf
       t.leafSlot[gi] = slot;
       leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
       leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
+      if(c.randomSym) {   // position-keyed, so a position is evaluated under the same symmetry whichever game or path reaches it
+        const int np = (flagsOf(s.misc) >> 3) & 3;
+        leafSym[slot] = (int8_t)(splitmix64(c.seed ^ s.h0 ^ g.playerHash[np][0] ^ SYM_SALT) & 7);
+      }
     }
   }
 }
@@ -396,7 +402,7 @@ __device__ __forceinline__ void childStats(const SearchCfg& c, uint8_t* treeBase
 __device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
 
 template <class D>
-__global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob) {
+__global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob, int8_t* __restrict__ leafSym) {
   const D dm(g);
   using BB = typename D::BB;
   const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -544,6 +550,10 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
       t.leafSlot[gi] = slot;
       leaf.black[slot] = (uint64_t)s.black; leaf.white[slot] = (uint64_t)s.white; leaf.hash0[slot] = s.h0; leaf.hash1[slot] = s.h1;
       leaf.gameId[slot] = s.id; leaf.misc[slot] = s.misc;
+      if(c.randomSym) {   // position-keyed, so a position is evaluated under the same symmetry whichever game or path reaches it
+        const int np = (flagsOf(s.misc) >> 3) & 3;
+        leafSym[slot] = (int8_t)(splitmix64(c.seed ^ s.h0 ^ g.playerHash[np][0] ^ SYM_SALT) & 7);
+      }
     }
   }
 }
@@ -1325,13 +1335,13 @@ int runVisits(kc_search* S) {
       if(rootPolicyChange && it <= 1) { k_root_noise<<<(ch.gCnt + 63) / 64, 64, 0, hs>>>(ch, S->tree, R->st, R->geom.HW); S->launches++; }
       if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount + h, 0, 4, hs));
       if(c.graph) {
-        if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
-        else k_select_graph<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
-      } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
-      else k_select<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob);
+        if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+        else k_select_graph<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+      } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+      else k_select<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
       S->launches++;
       if(S->handle) {
-        if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff, S->pipelined)) return 1;
+        if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff, S->pipelined, c.randomSym != 0)) return 1;
         kc::launchPostprocess(S->handle, ch.gCnt, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, H[h].policy, H[h].winLoss, H[h].misc, H[h].nnHash, hs,
                               H[h].rowOff);
         S->launches += 3;
@@ -1381,6 +1391,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.rootTemp = p->rootPolicyTemperature; c.rootTempEarly = p->rootPolicyTemperatureEarly; c.tempHalflife = p->chosenMoveTemperatureHalflife;
   c.fpuPWPow = p->fpuParentWeightByVisitedPolicyPow > 0.0 ? p->fpuParentWeightByVisitedPolicyPow : 1.0; c.rootDesired = p->rootDesiredPerChildVisitsCoeff;
   c.vwExp = p->valueWeightExponent;
+  c.randomSym = (p->nnRandomize && handleOrNull) ? 1 : 0;
   c.moveTemp = p->chosenMoveTemperature; c.moveTempEarly = p->chosenMoveTemperatureEarly; c.moveSubtract = p->chosenMoveSubtract; c.movePrune = p->chosenMovePrune;
   c.boardArea = xSize * ySize;
   const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);

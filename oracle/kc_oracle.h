@@ -222,6 +222,7 @@ typedef struct {
   double rootPolicyTemperature, rootPolicyTemperatureEarly, chosenMoveTemperatureHalflife;
   double fpuParentWeightByVisitedPolicyPow, rootDesiredPerChildVisitsCoeff, valueWeightExponent;
   uint64_t noiseSeed, noiseGameId;   /* oracle only (one game per call): what kc_search_reset's seed and the game id are on the device */
+  int32_t nnRandomize, pad3_;        /* leaves evaluated under a symmetry drawn from (noiseSeed, sit-hash) */
 } ko_search_params;   /* same layout as kc_search_params */
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,

@@ -298,7 +298,7 @@ class SearchParams(C.Structure):
                 ("rootDirichletNoiseTotalConcentration", C.c_double), ("rootDirichletNoiseWeight", C.c_double),
                 ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
                 ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double), ("valueWeightExponent", C.c_double),
-                ("noiseSeed", C.c_uint64), ("noiseGameId", C.c_uint64)]   # the last two exist in the oracle only
+                ("noiseSeed", C.c_uint64), ("noiseGameId", C.c_uint64), ("nnRandomize", C.c_int32), ("pad3_", C.c_int32)]   # oracle-only tail
 
 
 def _with_extras(sp, extra):
@@ -310,11 +310,11 @@ def _with_extras(sp, extra):
     return sp
 
 
-def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2):
+def search_run(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=0.2, **extra):
     """One oracle search from `game` (a Game); model=None uses the integer-hash evaluator.  Returns a dict with the
     root statistics (arrays over the policy index) and the visit counters."""
     P = 4 * game.HW
-    sp = SearchParams(max_visits, 0, 0, 0, 0, 0, cpuct, fpu, root_fpu)
+    sp = _with_extras(SearchParams(max_visits, 0, 0, 0, 0, 0, cpuct, fpu, root_fpu), extra)
     rv = np.zeros(1, np.int32); rw = np.zeros(1, np.float64)
     ev = np.zeros(P, np.int32); ew = np.zeros(P, np.float64); pol = np.zeros(P, np.float32); order = np.zeros(P, np.uint8)
     cnt = np.zeros(3, np.uint64)

@@ -48,9 +48,12 @@ double butterfly(double part[32]) {
   return cur[0];
 }
 
+constexpr uint64_t SYM_SALT = 0x5A11E7C0FFEEULL;
 struct Evaluator {
   const ko_model* model;   // null: integer-hash evaluator
   int W, H, P, LW;
+  bool randomSym = false;  // nnRandomize (nneval.cpp:515-524): symmetry drawn from the position's sit-hash and the seed
+  uint64_t seed = 0;
   // fills policy [P] (-1 illegal) and (whiteWin, whiteLoss) for the position in g (player to move = next player)
   void eval(const ko_game* g, float* policy, float winLoss[2]) const {
     std::vector<uint32_t> legal(LW);
@@ -75,7 +78,13 @@ struct Evaluator {
     std::vector<float> planes((size_t)15 * W * H), own((size_t)W * H);
     float glob = 0.f, value[2], misc[2];
     ko_game_fill_row_v1(g, pla, W, H, 0, planes.data(), &glob);
-    ko_model_forward(model, 1, W, H, 0, planes.data(), &glob, nullptr, policy, value, misc, own.data(), 0, 1);
+    int8_t sym = 0;
+    if(randomSym) {
+      uint64_t h[2];
+      ko_game_sit_hash(g, pla, h);
+      sym = (int8_t)(ko_splitmix64(seed ^ h[0] ^ SYM_SALT) & 7);
+    }
+    ko_model_forward(model, 1, W, H, 0, planes.data(), &glob, randomSym ? &sym : nullptr, policy, value, misc, own.data(), 0, 1);
     ko_postprocess(policy, P, legal.data(), 1.0f, value, misc, pla);
     winLoss[0] = value[0]; winLoss[1] = value[1];
   }
@@ -90,6 +99,7 @@ static void searchRunOnTree(std::vector<Node>& nodes, const ko_game* rootGame, i
                             double* edgeUtilitySum, float* policyOut, uint8_t* orderOut, uint64_t counters[3]) {
   const int P = 4 * x_size * y_size;
   Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
+  ev.randomSym = p->nnRandomize != 0; ev.seed = p->noiseSeed;
   nodes.reserve(p->maxVisits);
   uint64_t cVisits = 0, cEvals = 0, cTerminal = 0;
   ko_game* g = ko_game_create(x_size, y_size, 4);
@@ -581,6 +591,7 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
                      uint8_t* orderOut, uint64_t counters[5], uint64_t* digest) {
   const int P = 4 * x_size * y_size;
   Evaluator ev{modelOrNull, x_size, y_size, P, (P + 31) / 32};
+  ev.randomSym = p->nnRandomize != 0; ev.seed = S.seed;
   S.p = p;
   const size_t maxNodes = (size_t)p->maxVisits + (p->reuseTree ? (size_t)p->maxVisits / 4 : 0);   // the device's node pool
   S.nodes.reserve(maxNodes);

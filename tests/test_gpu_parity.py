@@ -835,6 +835,58 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", [False, True])
+def test_search_nn_randomize_matches_oracle(ctx, oracle, graph):
+    """nnRandomize (NNEvaluator::serve picks a symmetry per row, nneval.cpp:515-524): every leaf is evaluated under a symmetry
+    keyed by its position; the fp32 check path against the oracle's search with the same symmetric evaluations -- root priors to
+    1e-4, visit distributions identical for most games -- and really different from the unsymmetrised search."""
+    from katacoffee_b200 import backend, modeldesc
+    W = H = 5
+    G, V, seed = 48, 40, 19
+    model = modeldesc.Model("b2c32", seed=23)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=True)
+    gkw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8) if graph else {}
+    got = {}
+    for rnd in (1, 0):
+        s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, nnRandomize=rnd, **gkw)
+        s.reset(seed=seed)
+        for _ in range(4):
+            s.games.step()
+        s.runVisits()
+        got[rnd] = s.readRoot()
+        s.close()
+    same = differs = 0
+    for g in range(G):
+        og = oracle.Game(W, H, 4)
+        for _ in range(4):
+            og.play(og.choose(seed, g))
+        if graph:
+            ref = oracle.search_run_graph(og, V, model=om, graph=True, bias_factor=0.3, bias_exponent=0.8, nnRandomize=1, noiseSeed=seed)
+        else:
+            ref = oracle.search_run(og, V, model=om, nnRandomize=1, noiseSeed=seed)
+        assert np.abs(got[1]["policy"][g] - ref["policy"]).max() < 1e-4, g
+        assert got[1]["rootVisits"][g] == ref["rootVisits"] == V
+        same += (got[1]["edgeVisits"][g] == ref["edgeVisits"]).all()
+        assert np.abs(got[1]["edgeVisits"][g] - ref["edgeVisits"]).sum() <= V // 2
+        differs += np.abs(got[1]["policy"][g] - got[0]["policy"][g]).max() > 1e-3
+    assert same >= 0.8 * G, same
+    assert differs >= 0.5 * G, differs      # 7 of 8 symmetries change the evaluation of a randomly initialised net
+    # the bf16 tensor path takes the same per-row symmetries (device-resident, with batching of the leaves)
+    hb = backend.createComputeHandle(ctx, lm, G, W, H)
+    sb = backend.Search(ctx, hb, G, W, H, 4, maxVisits=V, nnRandomize=1, **gkw)
+    sb.reset(seed=seed)
+    for _ in range(4):
+        sb.games.step()
+    sb.runVisits()
+    rb = sb.readRoot()
+    legal = got[1]["policy"] >= 0
+    assert ((rb["policy"] >= 0) == legal).all() and np.abs(rb["policy"] - got[1]["policy"])[legal].max() < 0.03
+    sb.close(); hb.close(); h.close(); lm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
 def test_search_half_batch_pipeline_changes_nothing(ctx, graph):
     """With the bf16 net and enough games the search runs two half batches on two streams (select / expand of one half under
     the trunk kernel of the other).  Trees of different games never interact and an evaluation does not depend on its row, so
@@ -845,7 +897,7 @@ def test_search_half_batch_pipeline_changes_nothing(ctx, graph):
     lm = backend.LoadedModel(ctx, modeldesc.Model("b2c32", seed=12))
     h = backend.createComputeHandle(ctx, lm, G, W, H)
     kw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8, rootNoiseEnabled=1,
-              rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, valueWeightExponent=0.5) if graph else {}
+              rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, valueWeightExponent=0.5, nnRandomize=1) if graph else {}
     res = []
     for nopipe in (1, 0):
         s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, temperaturePlies=8, reuseTree=True, noPipeline=nopipe, **kw)
