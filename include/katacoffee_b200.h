@@ -362,6 +362,100 @@ int kc_search_read_training_rows(kc_search* s, int* numRows, int* numDropped, ui
 int kc_search_tree_digest(kc_search* s, uint64_t* digest);
 int64_t kc_search_launch_count(const kc_search* s);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluator front end.  Replaces NNEvaluator::evaluate / serve and NNCacheTable
+ * (cpp/neuralnet/nneval.h:17-42,80-249; nneval.cpp:341-586 server loop, :588-815 evaluate, :820-932 cache) for callers
+ * that search on the CPU with many threads (the reference's own Search):
+ *  - clients hand over a POSITION (stones, player to move, last five moves), not filled rows: the 100 isLegal calls of
+ *    fillRowV1 (nninputs.cpp:635-647) and the 100 of the post-processing (nneval.cpp:712-715) run on the device
+ *    (rules kernel -> bf16 trunk tiles -> net -> masked softmax), 40 bytes per row cross PCIe instead of 1.5 KB;
+ *  - the submit path takes no lock: a client claims a row with one atomic add on a ticket counter and packs its position
+ *    straight into the page-locked staging of the batch that ticket belongs to (the reference serialises every client on
+ *    one bufferMutex, nneval.cpp:663-676, and allocates an NNOutput per row, :505-515); a server thread closes a batch by
+ *    moving the ticket counter to the next batch boundary, exactly when the reference's would (as soon as it is free and
+ *    at least one row waits);
+ *  - the cache keeps results inline in one flat table (no shared_ptr per entry) behind a striped mutex pool, keyed by
+ *    NNInputs::getHash (nninputs.cpp:463-502) ^ mix(last five moves + last direction): SURVEY.md ledger 8.1-E -- the
+ *    literal hash alone collides between positions whose stones agree and whose forced lines differ.  The literal
+ *    hash is what kc_eval_output.nnHash reports.
+ * kc_evaluator_evaluate is thread-safe and blocks until the result is there (NNEvaluator::evaluate's contract).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kc_evaluator kc_evaluator;
+#define KC_SYMMETRY_NOTSPECIFIED (-1) /* NNInputs::SYMMETRY_NOTSPECIFIED: the evaluator chooses (doRandomize / defaultSymmetry) */
+typedef struct {
+  int nnXLen, nnYLen, winLen;  /* exact board size (requireExactNNLen) */
+  int maxBatch;                /* rows per batch = NNEvaluator's maxBatchSize */
+  int maxConcurrentEvals;      /* staging ring = maxConcurrentEvals / maxBatch + 3 batches, rounded up to a power of two (nneval.cpp:128-136) */
+  int numServerThreads;        /* each owns a compute handle on the context's device (nneval.cpp:341-362) */
+  int cacheSizePowerOfTwo;     /* < 0: no cache (nneval.cpp:139-140) */
+  int mutexPoolSizePowerOfTwo;
+  int doRandomize;             /* rows without a symmetry get one drawn from (randSeed, cache key): a position is always evaluated the same way */
+  int defaultSymmetry;         /* used when doRandomize == 0 */
+  uint64_t randSeed;
+  float policyTemperature;     /* MiscNNInputParams::nnPolicyTemperature, folded into the hash as nninputs.cpp:485-492 does */
+  unsigned handleFlags;        /* KC_FLAG_FP32_CHECK | KC_FLAG_SYM_PERMUTE_DIRS for the server threads' handles */
+} kc_evaluator_config;
+/* A position as kc_games_load takes it: stones [H*W] (0 empty, 1 black, 2 white), nextPla 1 / 2, moves [5][2] = last five
+ * (policy index, player) pairs oldest first, -1 = none (NULL = no history), numTurns.  It must have a legal move
+ * (nneval.cpp:730 asserts the same). */
+typedef struct {
+  const int8_t* stones;
+  const int16_t* moves;
+  int32_t numTurns;
+  int8_t nextPla;
+} kc_eval_position;
+/* NNOutput after NNEvaluator::evaluate's post-processing (nninputs.h:75-118, nneval.cpp:702-815): policyProbs [4*H*W]
+ * (caller's buffer; illegal = -1), white's win / loss probabilities, varTimeLeft, shorttermWinlossError, whiteOwnerMap
+ * [H*W] (caller's buffer or NULL; tanh, white's perspective). */
+typedef struct {
+  float* policyProbs;
+  float* whiteOwnerMap;
+  float whiteWinProb, whiteLossProb, varTimeLeft, shorttermWinlossError;
+  uint64_t nnHash[2];
+  int32_t symmetry;   /* the symmetry the row was evaluated under (of the evaluation that filled the cache, on a hit) */
+  int32_t cacheHit;
+} kc_eval_output;
+typedef struct {
+  uint64_t rowsProcessed, batchesProcessed;  /* NNEvaluator::numRowsProcessed / numBatchesProcessed */
+  uint64_t cacheHits, cacheMisses, ownerMapUpgrades;
+  uint64_t backpressureWaits;                /* submits that found the staging ring full (more than maxConcurrentEvals in flight) */
+} kc_evaluator_stats;
+/* One closed batch, as a server thread hands it to its backend.  Inputs are the packed device format of the games
+ * kernels (csrc/games_device.cuh: bitboards with row stride W+1, pos_hash pair, misc = last five moves / direction /
+ * numTurns / next player); kc_eval_unpack_position turns a row back into a kc_eval_position.  The backend fills
+ * policyProbs [n][4*H*W], whiteWinLoss [n][2], miscOut [n][2] (all post-processed as nneval.cpp:702-801 does) and,
+ * when wantOwnership != 0, ownership [n][H*W] = the net's raw ownership output (player to move's perspective). */
+typedef struct {
+  int n, wantOwnership;
+  float policyTemperature;
+  const uint64_t *black, *white, *hash0, *hash1, *misc;
+  const int8_t* symmetry;
+  float *policyProbs, *whiteWinLoss, *miscOut, *ownership;
+} kc_eval_batch;
+typedef int (*kc_eval_backend_fn)(void* user, int serverThread, const kc_eval_batch* batch);
+
+int kc_evaluator_create(kc_ctx* ctx, const kc_model* model, const kc_evaluator_config* cfg, kc_evaluator** out);
+/* The same front end over a caller-supplied batch function instead of the device (needs no GPU): the host-logic tests
+ * drive it with the CPU oracle; a non-zero return fails every row of the batch with `kc_last_error` = "backend failed". */
+int kc_evaluator_create_custom(const kc_evaluator_config* cfg, kc_eval_backend_fn fn, void* user, kc_evaluator** out);
+/* Joins the server threads; no kc_evaluator_evaluate may be in flight (NNEvaluator::~NNEvaluator / killServerThreads). */
+int kc_evaluator_destroy(kc_evaluator* ev);
+int kc_evaluator_evaluate(kc_evaluator* ev, const kc_eval_position* pos, int symmetry, int skipCache, int includeOwnerMap,
+                          kc_eval_output* out);
+/* n positions from one client thread (a batched CPU search): rows are submitted without waiting for one another and
+ * collected afterwards; results are exactly those of n kc_evaluator_evaluate calls. */
+int kc_evaluator_evaluate_many(kc_evaluator* ev, int n, const kc_eval_position* pos, const int8_t* symmetryOrNull, int skipCache,
+                               int includeOwnerMap, kc_eval_output* out);
+int kc_evaluator_clear_cache(kc_evaluator* ev);  /* NNEvaluator::clearCache */
+int kc_evaluator_get_stats(const kc_evaluator* ev, kc_evaluator_stats* out);
+int kc_evaluator_clear_stats(kc_evaluator* ev);  /* NNEvaluator::clearStats */
+/* Host helpers: the literal NNInputs::getHash of a position (policy temperature folded in when != 1) and the cache key
+ * the evaluator uses for it; the inverse of the packing for custom backends. */
+int kc_eval_position_hash(int xSize, int ySize, const kc_eval_position* pos, float policyTemperature, uint64_t nnHash[2], uint64_t cacheKey[2]);
+int kc_eval_unpack_position(int xSize, int ySize, uint64_t black, uint64_t white, uint64_t misc, int8_t* stones, int8_t* nextPla,
+                            int16_t* movesCellPla, int32_t* numTurns, int32_t* lastDir);
+
 #ifdef __cplusplus
 }
 #endif

@@ -386,6 +386,129 @@ class Search:
             self._p = C.c_void_p()
 
 
+class NNEvaluator:
+    """The evaluator front end (kc_evaluator_*): NNEvaluator::evaluate / serve / NNCacheTable of cpp/neuralnet/nneval.h:17-249
+    for CPU search threads.  `evaluate` is thread-safe and blocks (ctypes releases the GIL for its duration).
+    With `customBackend` (a callable (serverThread, EvalBatch) -> status) no device is used: host-logic tests only."""
+
+    def __init__(self, ctx=None, loadedModel=None, nnXLen=5, nnYLen=5, winLen=4, maxBatchSize=1024, maxConcurrentEvals=None, numThreads=1,
+                 nnCacheSizePowerOfTwo=16, nnMutexPoolSizePowerofTwo=10, doRandomize=False, defaultSymmetry=0, randSeed=0,
+                 nnPolicyTemperature=1.0, useFP32Check=False, playModeSymmetry=False, customBackend=None):
+        self.nnXLen, self.nnYLen, self.winLen = nnXLen, nnYLen, winLen
+        self.cfg = capi.EvaluatorConfig(nnXLen, nnYLen, winLen, maxBatchSize, maxConcurrentEvals or 2 * maxBatchSize, numThreads,
+                                        nnCacheSizePowerOfTwo, nnMutexPoolSizePowerofTwo, int(doRandomize), defaultSymmetry, randSeed,
+                                        nnPolicyTemperature,
+                                        (capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0))
+        self._p = C.c_void_p()
+        self._keep = (ctx, loadedModel)
+        if customBackend is not None:
+            def tramp(user, serverThread, batch):
+                try:
+                    return int(customBackend(serverThread, batch.contents) or 0)
+                except Exception:   # an exception must not unwind through the C server thread
+                    import traceback
+                    traceback.print_exc()
+                    return 99
+            self._fn = capi.EVAL_BACKEND_FN(tramp)
+            check(lib().kc_evaluator_create_custom(C.byref(self.cfg), self._fn, None, C.byref(self._p)))
+        else:
+            check(lib().kc_evaluator_create(ctx._p, loadedModel._p, C.byref(self.cfg), C.byref(self._p)))
+
+    def _position(self, stones, nextPla, moves, numTurns, keep):
+        st = np.ascontiguousarray(stones, dtype=np.int8).reshape(-1)
+        assert st.size == self.nnXLen * self.nnYLen
+        keep.append(st)
+        mv = None
+        if moves is not None:
+            mv = np.ascontiguousarray(moves, dtype=np.int16).reshape(-1)
+            assert mv.size == 10
+            keep.append(mv)
+        return capi.EvalPosition(st.ctypes.data_as(C.POINTER(C.c_int8)), mv.ctypes.data_as(C.POINTER(C.c_int16)) if mv is not None else None,
+                                 int(numTurns), int(nextPla))
+
+    def _result(self, out, policy, own):
+        return {"policyProbs": policy, "whiteOwnerMap": own, "whiteWinProb": out.whiteWinProb, "whiteLossProb": out.whiteLossProb,
+                "varTimeLeft": out.varTimeLeft, "shorttermWinlossError": out.shorttermWinlossError,
+                "nnHash": (int(out.nnHash[0]), int(out.nnHash[1])), "symmetry": int(out.symmetry), "cacheHit": bool(out.cacheHit)}
+
+    def evaluate(self, stones, nextPla, moves=None, numTurns=0, symmetry=-1, skipCache=False, includeOwnerMap=False):
+        """stones [H*W] (0/1/2), moves [5][2] last five (policy index, player) oldest first with -1 = none."""
+        keep = []
+        pos = self._position(stones, nextPla, moves, numTurns, keep)
+        HW = self.nnXLen * self.nnYLen
+        policy = np.empty(4 * HW, np.float32)
+        own = np.empty(HW, np.float32) if includeOwnerMap else None
+        out = capi.EvalOutput()
+        out.policyProbs = policy.ctypes.data_as(capi.c_float_p)
+        out.whiteOwnerMap = own.ctypes.data_as(capi.c_float_p) if own is not None else None
+        check(lib().kc_evaluator_evaluate(self._p, C.byref(pos), symmetry, int(skipCache), int(includeOwnerMap), C.byref(out)))
+        return self._result(out, policy, own)
+
+    def evaluateMany(self, stones, nextPla, moves=None, numTurns=None, symmetry=None, skipCache=False, includeOwnerMap=False):
+        """stones [n][H*W], nextPla [n], moves [n][5][2] or None, numTurns [n] or None, symmetry [n] (int8) or None."""
+        stones = np.ascontiguousarray(stones, dtype=np.int8)
+        n, HW = stones.shape[0], self.nnXLen * self.nnYLen
+        keep = []
+        pos = (capi.EvalPosition * n)()
+        for i in range(n):
+            pos[i] = self._position(stones[i], nextPla[i], None if moves is None else moves[i], 0 if numTurns is None else numTurns[i], keep)
+        policy = np.empty((n, 4 * HW), np.float32)
+        own = np.empty((n, HW), np.float32) if includeOwnerMap else None
+        outs = (capi.EvalOutput * n)()
+        for i in range(n):
+            outs[i].policyProbs = policy[i].ctypes.data_as(capi.c_float_p)
+            outs[i].whiteOwnerMap = own[i].ctypes.data_as(capi.c_float_p) if own is not None else None
+        sym = None if symmetry is None else np.ascontiguousarray(symmetry, dtype=np.int8)
+        check(lib().kc_evaluator_evaluate_many(self._p, n, pos, ptr(sym), int(skipCache), int(includeOwnerMap), outs))
+        return [self._result(outs[i], policy[i], None if own is None else own[i]) for i in range(n)]
+
+    def clearCache(self):
+        check(lib().kc_evaluator_clear_cache(self._p))
+
+    def stats(self):
+        st = capi.EvaluatorStats()
+        check(lib().kc_evaluator_get_stats(self._p, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in st._fields_}
+
+    def clearStats(self):
+        check(lib().kc_evaluator_clear_stats(self._p))
+
+    def numRowsProcessed(self):
+        return self.stats()["rowsProcessed"]
+
+    def numBatchesProcessed(self):
+        return self.stats()["batchesProcessed"]
+
+    def averageProcessedBatchSize(self):
+        st = self.stats()
+        return st["rowsProcessed"] / max(st["batchesProcessed"], 1)
+
+    def close(self):
+        if self._p:
+            lib().kc_evaluator_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+def evalPositionHash(xSize, ySize, stones, nextPla, moves=None, numTurns=0, policyTemperature=1.0):
+    """(NNInputs::getHash, the evaluator's cache key) of a position, computed on the host."""
+    st = np.ascontiguousarray(stones, dtype=np.int8).reshape(-1)
+    mv = None if moves is None else np.ascontiguousarray(moves, dtype=np.int16).reshape(-1)
+    pos = capi.EvalPosition(st.ctypes.data_as(C.POINTER(C.c_int8)), mv.ctypes.data_as(C.POINTER(C.c_int16)) if mv is not None else None,
+                            int(numTurns), int(nextPla))
+    h, k = (C.c_uint64 * 2)(), (C.c_uint64 * 2)()
+    check(lib().kc_eval_position_hash(xSize, ySize, C.byref(pos), policyTemperature, h, k))
+    return (int(h[0]), int(h[1])), (int(k[0]), int(k[1]))
+
+
+def evalUnpackPosition(xSize, ySize, black, white, misc):
+    """Inverse of the evaluator's row packing: (stones [H*W], nextPla, moves [5][2] = (cell, player) oldest first, numTurns, lastDir)."""
+    stones = np.zeros(xSize * ySize, np.int8)
+    moves = np.zeros((5, 2), np.int16)
+    pla, nt, ld = C.c_int8(), C.c_int32(), C.c_int32()
+    check(lib().kc_eval_unpack_position(xSize, ySize, int(black), int(white), int(misc), ptr(stones), C.byref(pla), ptr(moves), C.byref(nt), C.byref(ld)))
+    return stones, int(pla.value), moves, int(nt.value), int(ld.value)
+
+
 def zobristTables():
     board = np.zeros((133, 4, 2), np.uint64)
     player = np.zeros((4, 2), np.uint64)

@@ -74,6 +74,37 @@ class SearchStats(C.Structure):
                                           "whiteWins", "draws", "batchRows", "transpositionHits", "catchUpVisits")]
 
 
+class EvaluatorConfig(C.Structure):
+    _fields_ = [("nnXLen", C.c_int32), ("nnYLen", C.c_int32), ("winLen", C.c_int32), ("maxBatch", C.c_int32),
+                ("maxConcurrentEvals", C.c_int32), ("numServerThreads", C.c_int32), ("cacheSizePowerOfTwo", C.c_int32),
+                ("mutexPoolSizePowerOfTwo", C.c_int32), ("doRandomize", C.c_int32), ("defaultSymmetry", C.c_int32),
+                ("randSeed", C.c_uint64), ("policyTemperature", C.c_float), ("handleFlags", C.c_uint32)]
+
+
+class EvalPosition(C.Structure):
+    _fields_ = [("stones", C.POINTER(C.c_int8)), ("moves", C.POINTER(C.c_int16)), ("numTurns", C.c_int32), ("nextPla", C.c_int8)]
+
+
+class EvalOutput(C.Structure):
+    _fields_ = [("policyProbs", c_float_p), ("whiteOwnerMap", c_float_p), ("whiteWinProb", C.c_float), ("whiteLossProb", C.c_float),
+                ("varTimeLeft", C.c_float), ("shorttermWinlossError", C.c_float), ("nnHash", C.c_uint64 * 2), ("symmetry", C.c_int32),
+                ("cacheHit", C.c_int32)]
+
+
+class EvaluatorStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rowsProcessed", "batchesProcessed", "cacheHits", "cacheMisses", "ownerMapUpgrades",
+                                          "backpressureWaits")]
+
+
+class EvalBatch(C.Structure):
+    _fields_ = [("n", C.c_int32), ("wantOwnership", C.c_int32), ("policyTemperature", C.c_float),
+                ("black", C.POINTER(C.c_uint64)), ("white", C.POINTER(C.c_uint64)), ("hash0", C.POINTER(C.c_uint64)),
+                ("hash1", C.POINTER(C.c_uint64)), ("misc", C.POINTER(C.c_uint64)), ("symmetry", C.POINTER(C.c_int8)),
+                ("policyProbs", c_float_p), ("whiteWinLoss", c_float_p), ("miscOut", c_float_p), ("ownership", c_float_p)]
+
+
+EVAL_BACKEND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(EvalBatch))
+
 FLAG_FP32_CHECK = 1
 FLAG_INPUTS_NHWC = 2
 FLAG_SYM_PERMUTE_DIRS = 4
@@ -135,6 +166,17 @@ PROTOTYPES = {
     "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
     "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
+    "kc_evaluator_create": (C.c_int, [vp, vp, C.POINTER(EvaluatorConfig), C.POINTER(vp)]),
+    "kc_evaluator_create_custom": (C.c_int, [C.POINTER(EvaluatorConfig), EVAL_BACKEND_FN, vp, C.POINTER(vp)]),
+    "kc_evaluator_destroy": (C.c_int, [vp]),
+    "kc_evaluator_evaluate": (C.c_int, [vp, C.POINTER(EvalPosition), C.c_int, C.c_int, C.c_int, C.POINTER(EvalOutput)]),
+    "kc_evaluator_evaluate_many": (C.c_int, [vp, C.c_int, C.POINTER(EvalPosition), vp, C.c_int, C.c_int, C.POINTER(EvalOutput)]),
+    "kc_evaluator_clear_cache": (C.c_int, [vp]),
+    "kc_evaluator_get_stats": (C.c_int, [vp, C.POINTER(EvaluatorStats)]),
+    "kc_evaluator_clear_stats": (C.c_int, [vp]),
+    "kc_eval_position_hash": (C.c_int, [C.c_int, C.c_int, C.POINTER(EvalPosition), C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kc_eval_unpack_position": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.POINTER(C.c_int8), vp,
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

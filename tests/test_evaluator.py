@@ -1,0 +1,330 @@
+"""CPU checks of the evaluator front end (kc_evaluator_*): the lock-free submit path, batch closing,
+staging-ring recycling, the inline cache, the owner-map upgrade and the error path, driven through
+`kc_evaluator_create_custom` with the CPU oracle as the batch function (rules -> V1 planes -> net -> post-processing,
+nneval.cpp:588-815).  The device backend of the same front end is covered by tests/test_z_gpu_evaluator.py."""
+import threading
+
+import numpy as np
+import pytest
+
+W, H, K = 5, 5, 4
+HW = W * H
+
+
+def make_positions(oracle, n, seed, min_plies=0, max_plies=14):
+    """Positions reached by the counter-RNG playouts of SURVEY.md 8(d): stones, player to move, last five moves, numTurns."""
+    out = []
+    g = 0
+    og = oracle.Game(W, H, K)
+    while len(out) < n:
+        og.reset()
+        stones = np.zeros(HW, np.int8)
+        hist = []
+        plies = min_plies + (g * 7 + seed) % (max_plies - min_plies + 1)
+        for _ in range(plies):
+            pos = og.choose(seed, g)
+            pla = og.next_pla()
+            if pos < 0 or not og.play(pos):
+                break
+            stones[pos % HW] = pla
+            hist.append((pos, pla))
+            if og.finished():
+                break
+        g += 1
+        if og.finished() or og.legal_mask()[1] == 0:
+            continue
+        moves = np.full((5, 2), -1, np.int16)
+        last = hist[-5:]
+        for j, m in enumerate(last):
+            moves[5 - len(last) + j] = m
+        out.append({"stones": stones.copy(), "nextPla": og.next_pla(), "moves": moves, "numTurns": len(hist), "hist": list(hist)})
+    return out
+
+
+def oracle_game_of(oracle, stones, next_pla, hist, num_turns):
+    og = oracle.Game(W, H, K)
+    for c in range(HW):
+        if stones[c]:
+            og.set_stone(c % W, c // W, int(stones[c]))
+    og.set_history([(int(p), int(pl)) for p, pl in hist], int(num_turns), int(next_pla))
+    return og
+
+
+def expected_output(oracle, omodel, p, sym, temp=1.0):
+    """NNEvaluator::evaluate of one position with the oracle: planes -> net under `sym` -> post-processing."""
+    og = oracle_game_of(oracle, p["stones"], p["nextPla"], p["hist"][-5:], p["numTurns"])
+    row, glob = og.fill_row_v1()
+    pol, val, misc, own = omodel.forward(row[None], glob[None], W, H, symmetry=np.array([sym], np.int8))
+    legal, n = og.legal_mask()
+    assert n > 0
+    ep, ev, em = oracle.postprocess(pol[0], legal, val[0], misc[0], p["nextPla"], temp)
+    sign = 1.0 if p["nextPla"] == 2 else -1.0
+    return {"policy": ep, "winLoss": ev, "misc": em, "owner": sign * np.tanh(own[0]), "nnHash": og.nn_hash(temp=temp)}
+
+
+class OracleBackend:
+    """The batch function: unpacks the rows the front end staged and evaluates them with the oracle."""
+
+    def __init__(self, oracle, omodel, fail_on_batch=None):
+        self.oracle, self.omodel = oracle, omodel
+        self.batch_sizes = []
+        self.servers = set()
+        self.fail_on_batch = fail_on_batch
+        self.lock = threading.Lock()
+
+    def __call__(self, server, b):
+        from katacoffee_b200 import backend
+        with self.lock:
+            self.batch_sizes.append(b.n)
+            self.servers.add(server)
+            idx = len(self.batch_sizes) - 1
+        if self.fail_on_batch is not None and idx == self.fail_on_batch:
+            return 7
+        n = b.n
+        pol = np.ctypeslib.as_array(b.policyProbs, shape=(n, 4 * HW))
+        wl = np.ctypeslib.as_array(b.whiteWinLoss, shape=(n, 2))
+        mo = np.ctypeslib.as_array(b.miscOut, shape=(n, 2))
+        ow = np.ctypeslib.as_array(b.ownership, shape=(n, HW))
+        for i in range(n):
+            stones, pla, moves, nt, last_dir = backend.evalUnpackPosition(W, H, b.black[i], b.white[i], b.misc[i])
+            hist = [(int(c), int(pl)) for c, pl in moves if pl]
+            if hist:
+                hist[-1] = (last_dir * HW + hist[-1][0], hist[-1][1])   # only the last move's direction is kept (and needed)
+            og = oracle_game_of(self.oracle, stones, pla, hist, nt)
+            sh = og.sit_hash(pla)
+            zp = backend.zobristTables()[1]
+            assert int(b.hash0[i]) ^ int(zp[pla][0]) == int(sh[0]) and int(b.hash1[i]) ^ int(zp[pla][1]) == int(sh[1]), "packed pos_hash"
+            row, glob = og.fill_row_v1()
+            p, v, m, o = self.omodel.forward(row[None], glob[None], W, H, symmetry=np.array([b.symmetry[i]], np.int8))
+            legal, _ = og.legal_mask()
+            ep, ev, em = self.oracle.postprocess(p[0], legal, v[0], m[0], pla, b.policyTemperature)
+            pol[i], wl[i], mo[i] = ep, ev, em
+            if b.wantOwnership:
+                ow[i] = o[0]
+        return 0
+
+
+@pytest.fixture(scope="module")
+def omodel(oracle, built_lib):
+    from katacoffee_b200 import modeldesc
+    return oracle.Model(modeldesc.Model("b2c32", seed=4))
+
+
+def check_result(r, e, owner=False):
+    assert np.abs(r["policyProbs"] - e["policy"]).max() < 1e-6
+    assert abs(r["whiteWinProb"] - e["winLoss"][0]) < 1e-6 and abs(r["whiteLossProb"] - e["winLoss"][1]) < 1e-6
+    assert np.allclose([r["varTimeLeft"], r["shorttermWinlossError"]], e["misc"], rtol=1e-6, atol=1e-7)
+    assert r["nnHash"] == (int(e["nnHash"][0]), int(e["nnHash"][1]))
+    if owner:
+        assert np.abs(r["whiteOwnerMap"] - e["owner"]).max() < 1e-6
+
+
+def test_position_hash_and_cache_key(oracle, built_lib):
+    """kc_eval_position_hash: literal NNInputs::getHash (nninputs.cpp:463-502, incl. the policy-temperature fold) and a cache
+    key that separates what the literal hash confuses (ledger 8.1-E)."""
+    from katacoffee_b200 import backend
+    ps = make_positions(oracle, 60, seed=5)
+    keys = set()
+    for p in ps:
+        og = oracle_game_of(oracle, p["stones"], p["nextPla"], p["hist"][-5:], p["numTurns"])
+        for temp in (1.0, 0.7, 1.25):
+            h, k = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"], temp)
+            e = og.nn_hash(temp=temp)
+            assert h == (int(e[0]), int(e[1])), temp
+        keys.add(backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"])[1])
+    assert len(keys) == len({(p["stones"].tobytes(), p["nextPla"], p["moves"][:, 0].tobytes()) for p in ps})
+    # same stones and player, different last direction: same literal hash, different legality, different key
+    p = next(q for q in ps if q["numTurns"] >= 2)
+    m2 = p["moves"].copy()
+    m2[4, 0] = (m2[4, 0] + HW) % (4 * HW)
+    h1, k1 = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+    h2, k2 = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], m2, p["numTurns"])
+    assert h1 == h2 and k1 != k2
+    # numTurns is in neither (the planes do not read it)
+    assert backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"] + 2) == (h1, k1)
+    # round trip of the packing
+    st, pla, mv, nt, ld = backend.evalUnpackPosition(W, H, 0b100001, 0b10, (3 | (1 << 6)) | (2 << 40) | (9 << 48) | ((2 << 3) << 56))
+    assert st[0] == 1 and st[5 - 0] == 0 and st[1] == 2 and pla == 2 and nt == 9 and ld == 2 and tuple(mv[4]) == (3, 1) and mv[3][1] == 0
+
+
+@pytest.mark.timeout(300)
+def test_threads_batches_cache_against_oracle(oracle, built_lib, omodel):
+    """8 client threads x 30 evaluations over 90 distinct positions, 2 server threads, batches of at most 8 rows: every result
+    equals the oracle's NNEvaluator::evaluate; rows + hits account for every request; batches never exceed maxBatch."""
+    from katacoffee_b200 import backend
+    ps = make_positions(oracle, 90, seed=11)
+    be = OracleBackend(oracle, omodel)
+    ev = backend.NNEvaluator(nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=8, maxConcurrentEvals=16, numThreads=2, nnCacheSizePowerOfTwo=12,
+                             nnMutexPoolSizePowerofTwo=4, defaultSymmetry=3, customBackend=be)
+    exp = [expected_output(oracle, omodel, p, 3) for p in ps]
+    errors = []
+
+    def client(t):
+        try:
+            rng = np.random.default_rng(t)
+            for _ in range(30):
+                i = int(rng.integers(0, len(ps)))
+                p = ps[i]
+                r = ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+                check_result(r, exp[i])
+                assert r["symmetry"] == 3
+        except BaseException as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    st = ev.stats()
+    assert st["cacheHits"] + st["cacheMisses"] == 240 and st["cacheHits"] > 0
+    assert st["rowsProcessed"] == st["cacheMisses"] == sum(be.batch_sizes)
+    assert st["batchesProcessed"] == len(be.batch_sizes) and max(be.batch_sizes) <= 8
+    assert abs(ev.averageProcessedBatchSize() - np.mean(be.batch_sizes)) < 1e-9
+    # an explicit symmetry is honoured (skipCache: the row is evaluated again, nneval.cpp:611) and stored
+    r = ev.evaluate(ps[0]["stones"], ps[0]["nextPla"], ps[0]["moves"], ps[0]["numTurns"], symmetry=6, skipCache=True)
+    check_result(r, expected_output(oracle, omodel, ps[0], 6))
+    r2 = ev.evaluate(ps[0]["stones"], ps[0]["nextPla"], ps[0]["moves"], ps[0]["numTurns"])
+    assert r2["cacheHit"] and r2["symmetry"] == 6 and (r2["policyProbs"] == r["policyProbs"]).all()
+    # clearCache / clearStats
+    ev.clearCache()
+    ev.clearStats()
+    r3 = ev.evaluate(ps[0]["stones"], ps[0]["nextPla"], ps[0]["moves"], ps[0]["numTurns"])
+    assert not r3["cacheHit"] and ev.stats()["rowsProcessed"] == 1 and ev.stats()["cacheMisses"] == 1
+    ev.close()
+
+
+@pytest.mark.timeout(300)
+def test_owner_map_upgrade_and_randomized_symmetry(oracle, built_lib, omodel):
+    """nneval.cpp:612-623, 689-701: a cached result without owner map is re-evaluated for the map only, its policy and
+    values are kept; nneval.cpp:817-838: tanh and flip to white.  doRandomize draws the symmetry from (seed, position)."""
+    from katacoffee_b200 import backend
+    ps = make_positions(oracle, 24, seed=3, min_plies=2)
+    be = OracleBackend(oracle, omodel)
+    ev = backend.NNEvaluator(nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=4, numThreads=1, nnCacheSizePowerOfTwo=10, doRandomize=True, randSeed=77,
+                             customBackend=be)
+    syms = set()
+    for p in ps:
+        a = ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+        assert not a["cacheHit"] and a["whiteOwnerMap"] is None
+        syms.add(a["symmetry"])
+        e = expected_output(oracle, omodel, p, a["symmetry"])
+        check_result(a, e)
+        b = ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"], includeOwnerMap=True)
+        assert not b["cacheHit"] and (b["policyProbs"] == a["policyProbs"]).all() and b["whiteWinProb"] == a["whiteWinProb"]
+        check_result(b, e, owner=True)
+        c = ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"], includeOwnerMap=True)
+        assert c["cacheHit"] and (c["whiteOwnerMap"] == b["whiteOwnerMap"]).all() and c["symmetry"] == a["symmetry"]
+        d = ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"], skipCache=True)
+        assert d["symmetry"] == a["symmetry"], "a position is always evaluated under the same symmetry"
+    st = ev.stats()
+    assert st["ownerMapUpgrades"] == len(ps) and st["cacheHits"] == len(ps) and st["cacheMisses"] == len(ps)
+    assert st["rowsProcessed"] == 3 * len(ps)
+    assert len(syms) >= 4, syms
+    ev.close()
+
+
+@pytest.mark.timeout(300)
+def test_evaluate_many_with_a_full_ring(oracle, built_lib, omodel):
+    """Three threads push 150 rows each through a 4-buffer ring of 4-row batches (far more than maxConcurrentEvals in
+    flight): submits wait for recycled buffers, nothing deadlocks, every result is right; policy temperature 0.7."""
+    from katacoffee_b200 import backend
+    ps = make_positions(oracle, 150, seed=21)
+    be = OracleBackend(oracle, omodel)
+    ev = backend.NNEvaluator(nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=4, maxConcurrentEvals=4, numThreads=2, nnCacheSizePowerOfTwo=-1,
+                             defaultSymmetry=5, nnPolicyTemperature=0.7, customBackend=be)
+    exp = [expected_output(oracle, omodel, p, 5, temp=0.7) for p in ps]
+    stones = np.stack([p["stones"] for p in ps])
+    nextPla = [p["nextPla"] for p in ps]
+    moves = np.stack([p["moves"] for p in ps])
+    numTurns = [p["numTurns"] for p in ps]
+    errors = []
+
+    def client(t):
+        try:
+            order = np.random.default_rng(t).permutation(len(ps))
+            res = ev.evaluateMany(stones[order], [nextPla[i] for i in order], moves[order], [numTurns[i] for i in order], includeOwnerMap=(t == 1))
+            for r, i in zip(res, order):
+                check_result(r, exp[i], owner=(t == 1))
+        except BaseException as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    st = ev.stats()
+    assert st["rowsProcessed"] == 450 and st["cacheHits"] == 0 and st["cacheMisses"] == 0   # no cache: nothing counted
+    assert st["backpressureWaits"] > 0
+    assert max(be.batch_sizes) <= 4 and be.servers == {0, 1}
+    ev.close()
+
+
+@pytest.mark.timeout(120)
+def test_backend_failure_and_argument_errors(oracle, built_lib, omodel):
+    from katacoffee_b200 import backend, capi
+    ps = make_positions(oracle, 6, seed=2)
+    be = OracleBackend(oracle, omodel, fail_on_batch=1)
+    ev = backend.NNEvaluator(nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=4, numThreads=1, customBackend=be)
+    p = ps[0]
+    ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+    with pytest.raises(capi.KCError, match="backend failed"):
+        ev.evaluate(ps[1]["stones"], ps[1]["nextPla"], ps[1]["moves"], ps[1]["numTurns"])
+    # the failed row was not cached and the evaluator keeps serving
+    r = ev.evaluate(ps[1]["stones"], ps[1]["nextPla"], ps[1]["moves"], ps[1]["numTurns"])
+    assert not r["cacheHit"]
+    check_result(r, expected_output(oracle, omodel, ps[1], 0))
+    with pytest.raises(capi.KCError, match="symmetry"):
+        ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"], symmetry=8)
+    with pytest.raises(capi.KCError, match="nextPla"):
+        ev.evaluate(p["stones"], 3, p["moves"], p["numTurns"])
+    bad = p["stones"].copy()
+    bad[0] = 5
+    with pytest.raises(capi.KCError, match="stone colour"):
+        ev.evaluate(bad, p["nextPla"], p["moves"], p["numTurns"])
+    ev.close()
+    for kw, msg in (({"maxBatchSize": 0}, "maxBatchSize"), ({"numThreads": 0}, "numServerThreads"), ({"nnXLen": 9}, "board size"),
+                    ({"defaultSymmetry": 8}, "defaultSymmetry"), ({"nnPolicyTemperature": 0.0}, "policyTemperature"),
+                    ({"nnCacheSizePowerOfTwo": 40}, "cacheSizePowerOfTwo")):
+        with pytest.raises(capi.KCError, match=msg):
+            backend.NNEvaluator(**{"nnXLen": W, "nnYLen": H, "winLen": K, "maxBatchSize": 4, "customBackend": be, **kw})
+    # without a device the real backend must refuse (no CPU fallback)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.KCError):
+            backend.createComputeContext(0)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("tsan", [False, True])
+def test_cpp_stress(built_lib, tmp_path, tsan):
+    """tests/cpp/test_evaluator_stress.cpp: 12 native client threads (single rows and evaluate_many chunks, owner maps,
+    skipCache) against 3 servers, a 4-buffer ring and a 512-entry cache; every result is recomputed and compared bit for
+    bit.  Second build: the queue and cache compiled alone under -fsanitize=thread (no data race reported)."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "test_evaluator_stress.cpp")
+    exe = str(tmp_path / ("stress_tsan" if tsan else "stress"))
+    inc = ["-I" + os.path.join(root, "include")]
+    if tsan:
+        csrc = os.path.join(root, "katacoffee_b200", "csrc")
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DKC_EVALUATOR_HOST_ONLY", "-w"] + inc + ["-I" + csrc, "-I/usr/local/cuda/include",
+               "-x", "c++", src, os.path.join(csrc, "evaluator.cpp"), os.path.join(csrc, "zobrist.cpp"), "-o", exe, "-lpthread"]
+    else:
+        libdir = os.path.join(root, "katacoffee_b200")
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall"] + inc + [src, "-o", exe, "-L" + libdir, "-lkatacoffee_b200", "-Wl,-rpath," + libdir, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if tsan and r.returncode != 0 and "tsan" in r.stderr:
+        pytest.skip("libtsan is not installed")
+    assert r.returncode == 0, r.stderr
+    args = ["12", "6000", "1500"] if tsan else ["12", "20000", "3000"]
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=500, env={**os.environ, "TSAN_OPTIONS": "halt_on_error=1"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ThreadSanitizer" not in r.stderr, r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["mismatches"] == 0 and rep["accounting"] and rep["cacheHits"] > 0 and rep["upgrades"] > 0 and rep["backpressureWaits"] > 0
