@@ -1,0 +1,112 @@
+"""GPU checks of the evaluator front end's device backend (kc_evaluator_create): packed positions -> rules kernel -> bf16 trunk
+tiles -> net -> masked softmax, batched from concurrent client threads, must give what kc_games_load + kc_games_eval +
+kc_games_postprocess give for the same positions and symmetries, and stay within the reduced-precision bars of the fp32 oracle.
+(Named test_z_* so that it runs after the parity suite.)"""
+import json
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from test_evaluator import HW, H, K, W, expected_output, make_positions
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _arrays(ps):
+    return (np.stack([p["stones"] for p in ps]), np.array([p["nextPla"] for p in ps], np.int8), np.stack([p["moves"] for p in ps]),
+            np.array([p["numTurns"] for p in ps], np.int32))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
+    from katacoffee_b200 import backend, modeldesc
+    N = 300
+    ps = make_positions(oracle, N, seed=41)
+    stones, nextPla, moves, numTurns = _arrays(ps)
+    model = modeldesc.Model("b2c32", seed=4)
+    omodel = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    # the direct path: all positions in one games object, explicit symmetries
+    sym = (np.arange(N) % 8).astype(np.int8)
+    h = backend.createComputeHandle(ctx, lm, N, W, H, useFP32Check=(mode == "fp32"))
+    games = backend.Games(ctx, N, W, H, K)
+    games.load(0, stones, nextPla, moves, numTurns)
+    games.eval(h, sym)
+    dpol, dwl, dmisc, dhash = games.postprocess(h, 1.0)
+    down = h.readOutputs(N)[3]
+    # the evaluator: batches of at most 64 rows closed whenever a server is free, 2 servers, 6 client threads
+    ev = backend.NNEvaluator(ctx, lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=64, maxConcurrentEvals=256, numThreads=2, nnCacheSizePowerOfTwo=12,
+                             useFP32Check=(mode == "fp32"))
+    results = [None] * N
+    errors = []
+
+    def client(t):
+        try:
+            idx = list(range(t, N, 6))
+            if t % 2 == 0:
+                for i in idx:
+                    results[i] = ev.evaluate(stones[i], nextPla[i], moves[i], numTurns[i], symmetry=int(sym[i]), includeOwnerMap=True)
+            else:
+                res = ev.evaluateMany(stones[idx], nextPla[idx], moves[idx], numTurns[idx], symmetry=sym[idx], includeOwnerMap=True)
+                for i, r in zip(idx, res):
+                    results[i] = r
+        except BaseException as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    tol = 2e-6
+    worst = 0.0
+    for i, r in enumerate(results):
+        assert r["nnHash"] == (int(dhash[i][0]), int(dhash[i][1])), "host NNInputs::getHash != the device's"
+        assert ((r["policyProbs"] == -1) == (dpol[i] == -1)).all(), "legal mask"
+        assert np.abs(r["policyProbs"] - dpol[i]).max() <= tol, i
+        assert abs(r["whiteWinProb"] - dwl[i][0]) <= tol and abs(r["whiteLossProb"] - dwl[i][1]) <= tol
+        assert np.allclose([r["varTimeLeft"], r["shorttermWinlossError"]], dmisc[i], rtol=1e-6, atol=1e-6)
+        sign = 1.0 if nextPla[i] == 2 else -1.0
+        assert np.abs(r["whiteOwnerMap"] - sign * np.tanh(down[i])).max() <= 1e-5
+        assert r["symmetry"] == sym[i] and not r["cacheHit"]
+        if i % 5 == 0:   # against the fp32 oracle: nneval post-processed quantities
+            e = expected_output(oracle, omodel, ps[i], int(sym[i]))
+            bar = 1e-4 if mode == "fp32" else 1e-2
+            worst = max(worst, np.abs(r["policyProbs"] - e["policy"]).max(), abs(r["whiteWinProb"] - e["winLoss"][0]))
+            assert np.abs(r["policyProbs"] - e["policy"]).max() < bar and abs(r["whiteWinProb"] - e["winLoss"][0]) < bar
+            assert np.abs(r["whiteOwnerMap"] - e["owner"]).max() < (1e-4 if mode == "fp32" else 3e-2)
+    st = ev.stats()
+    assert st["rowsProcessed"] == N and st["cacheMisses"] == N and st["batchesProcessed"] >= (N + 63) // 64
+    # second pass: everything from the cache, identical
+    for i in range(0, N, 7):
+        r = ev.evaluate(stones[i], nextPla[i], moves[i], numTurns[i], includeOwnerMap=True)
+        assert r["cacheHit"] and (r["policyProbs"] == results[i]["policyProbs"]).all() and (r["whiteOwnerMap"] == results[i]["whiteOwnerMap"]).all()
+    assert ev.stats()["rowsProcessed"] == N
+    print(f"evaluator[{mode}]: {st['batchesProcessed']} batches, avg {ev.averageProcessedBatchSize():.1f} rows; worst |diff| vs fp32 oracle {worst:.2e}")
+    for x in (ev, games, h, lm):
+        x.close()
+
+
+@pytest.mark.timeout(600)
+def test_native_clients_throughput_tool(ctx, tmp_path):
+    """tests/cpp/bench_evaluator.cpp (built by build_host) runs on the device: all rows processed, no failures, cache hits with --repeat."""
+    from katacoffee_b200 import backend, modeldesc
+    exe = os.path.join(ROOT, "katacoffee_b200", "host", "bench_evaluator")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    path = str(tmp_path / "b6c96.bin.gz")
+    backend.writeModelFile(modeldesc.Model("b6c96", seed=11), path)
+    r = subprocess.run([exe, path, "--clients", "4", "--rows", "20000", "--batch", "2048", "--servers", "2", "--chunk", "256"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["failures"] == 0 and rep["rowsProcessed"] == rep["requests"] and rep["value"] > 0
+    print("evaluator throughput (b6c96, 4 clients):", rep)
+    r = subprocess.run([exe, path, "--clients", "4", "--rows", "20000", "--batch", "2048", "--cache", "16", "--repeat", "500", "--single"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["failures"] == 0 and rep["cacheHits"] > 0.9 * rep["requests"]
