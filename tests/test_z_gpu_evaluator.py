@@ -25,8 +25,16 @@ def _arrays(ps):
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
 def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
     from katacoffee_b200 import backend, modeldesc
-    N = 300
-    ps = make_positions(oracle, N, seed=41)
+    # distinct positions only: the cache (like the reference's) ignores the symmetry, so a repeated position would be served
+    # the result of its first evaluation, under that one's symmetry
+    seen, ps = set(), []
+    for p in make_positions(oracle, 330, seed=41):
+        key = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"])[1]
+        if key not in seen:
+            seen.add(key)
+            ps.append(p)
+    N = len(ps)
+    assert N >= 250
     stones, nextPla, moves, numTurns = _arrays(ps)
     model = modeldesc.Model("b2c32", seed=4)
     omodel = oracle.Model(model)
@@ -40,7 +48,7 @@ def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
     dpol, dwl, dmisc, dhash = games.postprocess(h, 1.0)
     down = h.readOutputs(N)[3]
     # the evaluator: batches of at most 64 rows closed whenever a server is free, 2 servers, 6 client threads
-    ev = backend.NNEvaluator(ctx, lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=64, maxConcurrentEvals=256, numThreads=2, nnCacheSizePowerOfTwo=12,
+    ev = backend.NNEvaluator(ctx, lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=64, maxConcurrentEvals=256, numThreads=2, nnCacheSizePowerOfTwo=16,
                              useFP32Check=(mode == "fp32"))
     results = [None] * N
     errors = []
@@ -84,10 +92,14 @@ def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
     st = ev.stats()
     assert st["rowsProcessed"] == N and st["cacheMisses"] == N and st["batchesProcessed"] >= (N + 63) // 64
     # second pass: everything from the cache, identical
+    hits = 0
     for i in range(0, N, 7):
         r = ev.evaluate(stones[i], nextPla[i], moves[i], numTurns[i], includeOwnerMap=True)
-        assert r["cacheHit"] and (r["policyProbs"] == results[i]["policyProbs"]).all() and (r["whiteOwnerMap"] == results[i]["whiteOwnerMap"]).all()
-    assert ev.stats()["rowsProcessed"] == N
+        if r["cacheHit"]:   # (a direct-mapped table: a few of the N entries have been evicted by another position)
+            hits += 1
+            assert (r["policyProbs"] == results[i]["policyProbs"]).all() and (r["whiteOwnerMap"] == results[i]["whiteOwnerMap"]).all() and r["symmetry"] == sym[i]
+    checked = len(range(0, N, 7))
+    assert hits >= 0.8 * checked and ev.stats()["rowsProcessed"] == N + checked - hits
     print(f"evaluator[{mode}]: {st['batchesProcessed']} batches, avg {ev.averageProcessedBatchSize():.1f} rows; worst |diff| vs fp32 oracle {worst:.2e}")
     for x in (ev, games, h, lm):
         x.close()
