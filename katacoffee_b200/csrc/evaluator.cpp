@@ -166,6 +166,7 @@ struct Staging {
   std::mutex m;
   std::condition_variable cv;       // completion of the batch, and recycling of the buffer
   uint64_t completedSeq = ~0ULL;    // under m
+  std::atomic<uint64_t> completedFast{~0ULL};   // the same value, published after n / status: lets a client skip the mutex when its batch is already done
   int n = 0, status = 0;            // under m (written before completedSeq)
   std::string err;                  // under m
 };
@@ -206,6 +207,7 @@ struct DeviceServer {
   std::vector<kc_games*> tiers;     // ascending numGames; a batch of n rows runs on the smallest tier that holds it
   float *dP = nullptr, *dV = nullptr, *dM = nullptr;
   uint64_t* dH = nullptr;   // the device's own NNInputs::getHash of the rows (k_postprocess always writes it)
+  int *dN = nullptr, *hN = nullptr;   // the batch's row count for the trunk kernel (device copy, page-locked source)
   int P = 0, HW = 0;
 
   int create(kc_ctx* c, const kc_model* model, const kc_evaluator_config& cfg) {
@@ -224,6 +226,8 @@ struct DeviceServer {
     const size_t mb = (size_t)cfg.maxBatch;
     KC_CUDA(cudaMalloc(&dP, mb * P * 4)); KC_CUDA(cudaMalloc(&dV, mb * 8)); KC_CUDA(cudaMalloc(&dM, mb * 8));
     KC_CUDA(cudaMalloc(&dH, mb * 16));
+    KC_CUDA(cudaMalloc(&dN, 4));
+    KC_CUDA(cudaHostAlloc(&hN, 4, cudaHostAllocDefault));
     return 0;
   }
   void destroy() {
@@ -232,8 +236,9 @@ struct DeviceServer {
     tiers.clear();
     if(handle) kc_handle_destroy(handle);
     handle = nullptr;
-    cudaFree(dP); cudaFree(dV); cudaFree(dM); cudaFree(dH);
-    dP = dV = dM = nullptr; dH = nullptr;
+    cudaFree(dP); cudaFree(dV); cudaFree(dM); cudaFree(dH); cudaFree(dN);
+    if(hN) cudaFreeHost(hN);
+    dP = dV = dM = nullptr; dH = nullptr; dN = hN = nullptr;
   }
   int run(const kc_eval_batch* b) {
     KC_CUDA(cudaSetDevice(ctx->device));
@@ -248,10 +253,16 @@ struct DeviceServer {
     KC_CUDA(cudaMemcpyAsync(G->st.hash1, b->hash1, n * 8, cudaMemcpyHostToDevice, st));
     KC_CUDA(cudaMemcpyAsync(G->st.misc, b->misc, n * 8, cudaMemcpyHostToDevice, st));
     KC_CUDA(cudaMemcpyAsync(G->d_sym, b->symmetry, n, cudaMemcpyHostToDevice, st));
-    // lanes >= n keep the (valid) positions and symmetries of earlier batches; their rows are computed and ignored
-    if(kc::gamesEval(G, handle, nullptr, nullptr, 0, false, /*symOnDevice=*/true)) return 1;
-    const int T = G->geom.numGames;
-    kc::launchPostprocess(handle, T, G->geom.LW, G->d_legal, G->d_status, G->d_sitHash, b->policyTemperature, dP, dV, dM, dH, st);
+    // lanes >= n keep the (valid) positions and symmetries of earlier batches: the rules kernel still writes their tiles, the trunk
+    // kernel stops at the row count it reads from dN (bf16 path; the fp32 check path evaluates the whole tier), nothing of them is read back
+    const int* nDev = nullptr;
+    if(kc::handleIsBf16(handle)) {
+      *hN = b->n;
+      KC_CUDA(cudaMemcpyAsync(dN, hN, 4, cudaMemcpyHostToDevice, st));
+      nDev = dN;
+    }
+    if(kc::gamesEval(G, handle, nullptr, nDev, 0, false, /*symOnDevice=*/true)) return 1;
+    kc::launchPostprocess(handle, b->n, G->geom.LW, G->d_legal, G->d_status, G->d_sitHash, b->policyTemperature, dP, dV, dM, dH, st);
     KC_CUDA(cudaGetLastError());
     KC_CUDA(cudaMemcpyAsync(b->policyProbs, dP, n * P * 4, cudaMemcpyDeviceToHost, st));
     KC_CUDA(cudaMemcpyAsync(b->whiteWinLoss, dV, n * 8, cudaMemcpyDeviceToHost, st));
@@ -337,6 +348,7 @@ void serveLoop(kc_evaluator* ev, int serverIdx) {
       std::lock_guard<std::mutex> lock(b.m);
       b.n = n; b.status = status; b.err = err;
       b.completedSeq = q;
+      b.completedFast.store(q, std::memory_order_release);
     }
     b.cv.notify_all();
   }
@@ -384,7 +396,9 @@ int collectRow(kc_evaluator* ev, const Pending& pd, bool wantOwner, kc_eval_outp
   Staging& b = ev->bufs[pd.q & (uint64_t)(ev->ring - 1)];
   int n, status;
   std::string err;
-  {
+  if(b.completedFast.load(std::memory_order_acquire) == pd.q && b.status == 0) {
+    n = b.n; status = 0;   // n and status are stable until this row has been consumed
+  } else {
     std::unique_lock<std::mutex> lock(b.m);
     b.cv.wait(lock, [&] { return b.completedSeq == pd.q; });
     n = b.n; status = b.status;
