@@ -169,6 +169,30 @@ def cpu_selfplay_run(threads, visits=24):
     return sum(done) / (time.perf_counter() - t0)
 
 
+def evaluator_arm(net, W, H):
+    """The evaluator front end (kc_evaluator_*, the NNEvaluator of cpp/neuralnet/nneval.cpp for CPU search threads) with native client
+    threads: tests/cpp/bench_evaluator.cpp in its own process (positions in host memory, results in host memory).  Never fatal."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "katacoffee_b200", "host", "bench_evaluator")
+    try:
+        from katacoffee_b200 import backend, modeldesc
+        threads = os.cpu_count() or 1
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, net + ".bin.gz")
+            backend.writeModelFile(modeldesc.Model(net, seed=11), path)
+            p = subprocess.run([exe, path, "--size", str(W), "--clients", str(threads), "--rows", "300000", "--batch", "18944", "--servers", "2", "--chunk", "2368"],
+                               capture_output=True, text=True, timeout=180)
+        if p.returncode != 0:
+            return {"error": (p.stderr or p.stdout)[-300:]}
+        rep = json.loads(p.stdout.strip().splitlines()[-1])
+        rep["unit"] = "positions/s"
+        rep["api"] = "kc_evaluator_evaluate_many (NNEvaluator::evaluate): host positions in, post-processed NNOutput out, native client threads"
+        return rep
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -222,6 +246,7 @@ def main():
     ap.add_argument("--games", type=int, default=0, help="games per GPU (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-evaluator", action="store_true", help="skip the evaluator front-end arm (native client threads in a child process)")
     ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
     ap.add_argument("--selfplay-moves", type=int, default=1, help="moves per game timed in the self-play arm")
     args = ap.parse_args()
@@ -388,6 +413,8 @@ def main():
                                     "selfplay_moves_per_s": sp_visits_s / args.visits, "selfplay_visits_per_s": sp_visits_s,
                                     "selfplay_sample": f"{threads} games x 24 visits, oracle search + fp32 {NET} forward, one position per call",
                                     "sample": f"{n} positions: oracle rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward (Eigen-algorithm restatement), batch 4 per thread"}
+        if world == 1 and not args.no_evaluator and W == H:
+            line["evaluator"] = evaluator_arm(NET, W, H)
         print(json.dumps(line), flush=True)
     for o in (games, handle, lm, ctx):
         o.close()
