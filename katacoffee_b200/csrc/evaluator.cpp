@@ -201,78 +201,56 @@ namespace {
 
 #ifndef KC_EVALUATOR_HOST_ONLY
 // ---- the device backend of one server thread ---------------------------------------------------------------------------
+// The staging buffers are page-locked and mapped (unified addressing: the device uses the host pointers), so a batch needs no
+// copy calls: the rules kernel reads the packed rows straight from the staging, k_postprocess writes the results straight into it.
 struct DeviceServer {
   kc_ctx* ctx = nullptr;
   kc_handle* handle = nullptr;
-  std::vector<kc_games*> tiers;     // ascending numGames; a batch of n rows runs on the smallest tier that holds it
-  float *dP = nullptr, *dV = nullptr, *dM = nullptr;
-  uint64_t* dH = nullptr;   // the device's own NNInputs::getHash of the rows (k_postprocess always writes it)
-  int *dN = nullptr, *hN = nullptr;   // the batch's row count for the trunk kernel (device copy, page-locked source)
+  kc_games* games = nullptr;        // maxBatch lanes; a batch of n rows runs with geom.numGames = n
+  uint64_t* dH = nullptr;           // the device's own NNInputs::getHash of the rows (k_postprocess always writes it)
   int P = 0, HW = 0;
 
   int create(kc_ctx* c, const kc_model* model, const kc_evaluator_config& cfg) {
     ctx = c; HW = cfg.nnXLen * cfg.nnYLen; P = 4 * HW;
     if(kc_handle_create(c, model, cfg.maxBatch, cfg.nnXLen, cfg.nnYLen, cfg.handleFlags & ~KC_FLAG_INPUTS_NHWC, &handle)) return 1;
-    std::vector<int> sizes;
-    for(int s = cfg.maxBatch; ; s = (s + 7) / 8) {
-      sizes.insert(sizes.begin(), s);
-      if(s <= 64) break;
-    }
-    for(int s : sizes) {
-      kc_games* g = nullptr;
-      if(kc_games_create(c, s, cfg.nnXLen, cfg.nnYLen, cfg.winLen, &g)) return 1;
-      tiers.push_back(g);
-    }
-    const size_t mb = (size_t)cfg.maxBatch;
-    KC_CUDA(cudaMalloc(&dP, mb * P * 4)); KC_CUDA(cudaMalloc(&dV, mb * 8)); KC_CUDA(cudaMalloc(&dM, mb * 8));
-    KC_CUDA(cudaMalloc(&dH, mb * 16));
-    KC_CUDA(cudaMalloc(&dN, 4));
-    KC_CUDA(cudaHostAlloc(&hN, 4, cudaHostAllocDefault));
+    if(kc_games_create(c, cfg.maxBatch, cfg.nnXLen, cfg.nnYLen, cfg.winLen, &games)) return 1;
+    KC_CUDA(cudaMalloc(&dH, (size_t)cfg.maxBatch * 16));
     return 0;
   }
   void destroy() {
     if(ctx) cudaSetDevice(ctx->device);
-    for(kc_games* g : tiers) kc_games_destroy(g);
-    tiers.clear();
+    if(games) kc_games_destroy(games);
     if(handle) kc_handle_destroy(handle);
-    handle = nullptr;
-    cudaFree(dP); cudaFree(dV); cudaFree(dM); cudaFree(dH); cudaFree(dN);
-    if(hN) cudaFreeHost(hN);
-    dP = dV = dM = nullptr; dH = nullptr; dN = hN = nullptr;
+    games = nullptr; handle = nullptr;
+    cudaFree(dH);
+    dH = nullptr;
   }
   int run(const kc_eval_batch* b) {
     KC_CUDA(cudaSetDevice(ctx->device));
-    kc_games* G = nullptr;
-    for(kc_games* g : tiers) if(g->geom.numGames >= b->n) { G = g; break; }
-    KC_CHECK(G, "kc_evaluator: batch larger than maxBatch");
+    kc_games* G = games;
+    KC_CHECK(b->n > 0 && b->n <= handle->maxBatch, "kc_evaluator: batch larger than maxBatch");
     const size_t n = (size_t)b->n;
     cudaStream_t st = G->stream;
-    KC_CUDA(cudaMemcpyAsync(G->st.black, b->black, n * 8, cudaMemcpyHostToDevice, st));
-    KC_CUDA(cudaMemcpyAsync(G->st.white, b->white, n * 8, cudaMemcpyHostToDevice, st));
-    KC_CUDA(cudaMemcpyAsync(G->st.hash0, b->hash0, n * 8, cudaMemcpyHostToDevice, st));
-    KC_CUDA(cudaMemcpyAsync(G->st.hash1, b->hash1, n * 8, cudaMemcpyHostToDevice, st));
-    KC_CUDA(cudaMemcpyAsync(G->st.misc, b->misc, n * 8, cudaMemcpyHostToDevice, st));
+    // the symmetries are read again by the trunk kernel's epilogue: those stay in device memory
     KC_CUDA(cudaMemcpyAsync(G->d_sym, b->symmetry, n, cudaMemcpyHostToDevice, st));
-    // lanes >= n keep the (valid) positions and symmetries of earlier batches: the rules kernel still writes their tiles, the trunk
-    // kernel stops at the row count it reads from dN (bf16 path; the fp32 check path evaluates the whole tier), nothing of them is read back
-    const int* nDev = nullptr;
-    if(kc::handleIsBf16(handle)) {
-      *hN = b->n;
-      KC_CUDA(cudaMemcpyAsync(dN, hN, 4, cudaMemcpyHostToDevice, st));
-      nDev = dN;
-    }
-    if(kc::gamesEval(G, handle, nullptr, nDev, 0, false, /*symOnDevice=*/true)) return 1;
-    kc::launchPostprocess(handle, b->n, G->geom.LW, G->d_legal, G->d_status, G->d_sitHash, b->policyTemperature, dP, dV, dM, dH, st);
+    const kc::State saved = G->st;
+    const int savedN = G->geom.numGames;
+    G->st.black = const_cast<uint64_t*>(b->black); G->st.white = const_cast<uint64_t*>(b->white);
+    G->st.hash0 = const_cast<uint64_t*>(b->hash0); G->st.hash1 = const_cast<uint64_t*>(b->hash1);
+    G->st.misc = const_cast<uint64_t*>(b->misc);   // (gameId stays the device array: the kernel loads it, nothing here depends on it)
+    G->geom.numGames = b->n;
+    const int rc = kc::gamesEval(G, handle, nullptr, nullptr, 0, false, /*symOnDevice=*/true);   // read-only on the state (no step)
+    G->st = saved;
+    G->geom.numGames = savedN;
+    if(rc) return 1;
+    kc::launchPostprocess(handle, b->n, G->geom.LW, G->d_legal, G->d_status, G->d_sitHash, b->policyTemperature, b->policyProbs, b->whiteWinLoss,
+                          b->miscOut, dH, st);
     KC_CUDA(cudaGetLastError());
-    KC_CUDA(cudaMemcpyAsync(b->policyProbs, dP, n * P * 4, cudaMemcpyDeviceToHost, st));
-    KC_CUDA(cudaMemcpyAsync(b->whiteWinLoss, dV, n * 8, cudaMemcpyDeviceToHost, st));
-    KC_CUDA(cudaMemcpyAsync(b->miscOut, dM, n * 8, cudaMemcpyDeviceToHost, st));
     if(b->wantOwnership) KC_CUDA(cudaMemcpyAsync(b->ownership, handle->d_own, n * HW * 4, cudaMemcpyDeviceToHost, st));
     KC_CUDA(cudaStreamSynchronize(st));
     return kc::handleCheckAbort(handle);
   }
 };
-
 #else
 struct DeviceServer {
   kc_ctx* ctx = nullptr;
@@ -284,7 +262,11 @@ struct DeviceServer {
 void* stagingAlloc(bool pinned, size_t bytes) {
   void* p = nullptr;
 #ifndef KC_EVALUATOR_HOST_ONLY
-  if(pinned) { if(cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr; }
+  if(pinned) {
+    void* d = nullptr;
+    if(cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    if(cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess || d != p) { cudaFreeHost(p); return nullptr; }   // kernels use the host pointers
+  }
   else
 #endif
     p = malloc(bytes);
