@@ -386,7 +386,7 @@ typedef struct kc_evaluator kc_evaluator;
 typedef struct {
   int nnXLen, nnYLen, winLen;  /* exact board size (requireExactNNLen) */
   int maxBatch;                /* rows per batch = NNEvaluator's maxBatchSize */
-  int maxConcurrentEvals;      /* staging ring = maxConcurrentEvals / maxBatch + 3 batches, rounded up to a power of two (nneval.cpp:128-136) */
+  int maxConcurrentEvals;      /* staging ring = maxConcurrentEvals / maxBatch + 3 (nneval.cpp:128-136) + numServerThreads batches, rounded up to a power of two */
   int numServerThreads;        /* each owns a compute handle on the context's device (nneval.cpp:341-362) */
   int cacheSizePowerOfTwo;     /* < 0: no cache (nneval.cpp:139-140) */
   int mutexPoolSizePowerOfTwo;

@@ -469,7 +469,9 @@ static int evaluatorCreateCommon(const kc_evaluator_config* cfg, bool pinned, kc
   std::unique_ptr<kc_evaluator> ev(new kc_evaluator());
   ev->cfg = *cfg;
   ev->W = cfg->nnXLen; ev->H = cfg->nnYLen; ev->HW = ev->W * ev->H; ev->P = 4 * ev->HW;
-  int r = cfg->maxConcurrentEvals / cfg->maxBatch + 3;   // nneval.cpp:128-136
+  // nneval.cpp:128-136, plus one buffer per server: a batch stays in its staging buffer while it is processed (the reference's
+  // servers swap the row list out of the ring instead)
+  int r = cfg->maxConcurrentEvals / cfg->maxBatch + 3 + cfg->numServerThreads;
   int ring = 1;
   while(ring < r) ring *= 2;
   ev->ring = ring;

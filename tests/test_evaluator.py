@@ -227,7 +227,7 @@ def test_owner_map_upgrade_and_randomized_symmetry(oracle, built_lib, omodel):
 
 @pytest.mark.timeout(300)
 def test_evaluate_many_with_a_full_ring(oracle, built_lib, omodel):
-    """Three threads push 150 rows each through a 4-buffer ring of 4-row batches (far more than maxConcurrentEvals in
+    """Three threads push 150 rows each through an 8-buffer ring of 4-row batches (far more than maxConcurrentEvals in
     flight): submits wait for recycled buffers, nothing deadlocks, every result is right; policy temperature 0.7."""
     from katacoffee_b200 import backend
     ps = make_positions(oracle, 150, seed=21)
@@ -302,7 +302,7 @@ def test_backend_failure_and_argument_errors(oracle, built_lib, omodel):
 @pytest.mark.parametrize("tsan", [False, True])
 def test_cpp_stress(built_lib, tmp_path, tsan):
     """tests/cpp/test_evaluator_stress.cpp: 12 native client threads (single rows and evaluate_many chunks, owner maps,
-    skipCache) against 3 servers, a 4-buffer ring and a 512-entry cache; every result is recomputed and compared bit for
+    skipCache) against 3 servers, an 8-buffer ring and a 512-entry cache; every result is recomputed and compared bit for
     bit.  Second build: the queue and cache compiled alone under -fsanitize=thread (no data race reported)."""
     import json
     import os
