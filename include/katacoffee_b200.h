@@ -436,6 +436,11 @@ typedef struct {
 typedef int (*kc_eval_backend_fn)(void* user, int serverThread, const kc_eval_batch* batch);
 
 int kc_evaluator_create(kc_ctx* ctx, const kc_model* model, const kc_evaluator_config* cfg, kc_evaluator** out);
+/* One evaluator over several GPUs, the reference's gpuIdxByServerThread (nneval.h:100, nneval.cpp:341-362; cpp/program/setup.cpp:190-229):
+ * server thread i works on ctxs[i] with models[i] (a copy of the weights created on that context); numServers == cfg->numServerThreads.
+ * The staging ring and the cache are shared, so the clients do not know which GPU serves them. */
+int kc_evaluator_create_multi(int numServers, kc_ctx* const* ctxs, const kc_model* const* models, const kc_evaluator_config* cfg,
+                              kc_evaluator** out);
 /* The same front end over a caller-supplied batch function instead of the device (needs no GPU): the host-logic tests
  * drive it with the CPU oracle; a non-zero return fails every row of the batch with `kc_last_error` = "backend failed". */
 int kc_evaluator_create_custom(const kc_evaluator_config* cfg, kc_eval_backend_fn fn, void* user, kc_evaluator** out);

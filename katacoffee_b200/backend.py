@@ -411,6 +411,11 @@ class NNEvaluator:
                     return 99
             self._fn = capi.EVAL_BACKEND_FN(tramp)
             check(lib().kc_evaluator_create_custom(C.byref(self.cfg), self._fn, None, C.byref(self._p)))
+        elif isinstance(ctx, (list, tuple)):   # gpuIdxByServerThread: one (context, model) pair per server thread
+            assert len(ctx) == len(loadedModel) == numThreads
+            cs = (C.c_void_p * numThreads)(*[c._p for c in ctx])
+            ms = (C.c_void_p * numThreads)(*[m._p for m in loadedModel])
+            check(lib().kc_evaluator_create_multi(numThreads, cs, ms, C.byref(self.cfg), C.byref(self._p)))
         else:
             check(lib().kc_evaluator_create(ctx._p, loadedModel._p, C.byref(self.cfg), C.byref(self._p)))
 

@@ -167,6 +167,7 @@ PROTOTYPES = {
     "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
     "kc_evaluator_create": (C.c_int, [vp, vp, C.POINTER(EvaluatorConfig), C.POINTER(vp)]),
+    "kc_evaluator_create_multi": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(EvaluatorConfig), C.POINTER(vp)]),
     "kc_evaluator_create_custom": (C.c_int, [C.POINTER(EvaluatorConfig), EVAL_BACKEND_FN, vp, C.POINTER(vp)]),
     "kc_evaluator_destroy": (C.c_int, [vp]),
     "kc_evaluator_evaluate": (C.c_int, [vp, C.POINTER(EvalPosition), C.c_int, C.c_int, C.c_int, C.POINTER(EvalOutput)]),

@@ -507,15 +507,20 @@ static void evaluatorSpawn(kc_evaluator* ev) {
 }
 
 #ifndef KC_EVALUATOR_HOST_ONLY
-int kc_evaluator_create(kc_ctx* ctx, const kc_model* model, const kc_evaluator_config* cfg, kc_evaluator** out) {
-  KC_CHECK(ctx && model, "kc_evaluator_create: null argument");
-  KC_CUDA(cudaSetDevice(ctx->device));
+int kc_evaluator_create_multi(int numServers, kc_ctx* const* ctxs, const kc_model* const* models, const kc_evaluator_config* cfg, kc_evaluator** out) {
+  KC_CHECK(ctxs && models && cfg && out, "kc_evaluator_create: null argument");
+  KC_CHECK(numServers == cfg->numServerThreads, "kc_evaluator_create_multi: one (context, model) pair per server thread is required");
+  for(int i = 0; i < numServers; i++) {
+    KC_CHECK(ctxs[i] && models[i], "kc_evaluator_create: null context or model");
+    KC_CHECK(models[i]->ctx == ctxs[i], "kc_evaluator_create: a model must have been created on its server's context");
+  }
+  KC_CUDA(cudaSetDevice(ctxs[0]->device));
   kc_evaluator* ev = nullptr;
   if(evaluatorCreateCommon(cfg, true, &ev)) return 1;
-  for(int i = 0; i < cfg->numServerThreads; i++) {
+  for(int i = 0; i < numServers; i++) {
     DeviceServer* d = new DeviceServer();
     ev->devs.push_back(d);
-    if(d->create(ctx, model, *cfg)) {
+    if(d->create(ctxs[i], models[i], *cfg)) {
       const std::string msg = kc_last_error();
       kc_evaluator_destroy(ev);
       return kc::fail(msg);
@@ -524,6 +529,14 @@ int kc_evaluator_create(kc_ctx* ctx, const kc_model* model, const kc_evaluator_c
   evaluatorSpawn(ev);
   *out = ev;
   return 0;
+}
+
+int kc_evaluator_create(kc_ctx* ctx, const kc_model* model, const kc_evaluator_config* cfg, kc_evaluator** out) {
+  KC_CHECK(ctx && model && cfg, "kc_evaluator_create: null argument");
+  KC_CHECK(cfg->numServerThreads >= 1 && cfg->numServerThreads <= 64, "kc_evaluator_create: numServerThreads must be within 1..64");
+  std::vector<kc_ctx*> ctxs((size_t)cfg->numServerThreads, ctx);
+  std::vector<const kc_model*> models((size_t)cfg->numServerThreads, model);
+  return kc_evaluator_create_multi(cfg->numServerThreads, ctxs.data(), models.data(), cfg, out);
 }
 #endif
 

@@ -48,8 +48,9 @@ def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
     dpol, dwl, dmisc, dhash = games.postprocess(h, 1.0)
     down = h.readOutputs(N)[3]
     # the evaluator: batches of at most 64 rows closed whenever a server is free, 2 servers, 6 client threads
-    ev = backend.NNEvaluator(ctx, lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=64, maxConcurrentEvals=256, numThreads=2, nnCacheSizePowerOfTwo=16,
-                             useFP32Check=(mode == "fp32"))
+    # (fp32: through kc_evaluator_create_multi, one (context, model) pair per server thread -- here the same device twice)
+    ev = backend.NNEvaluator([ctx, ctx] if mode == "fp32" else ctx, [lm, lm] if mode == "fp32" else lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=64,
+                             maxConcurrentEvals=256, numThreads=2, nnCacheSizePowerOfTwo=16, useFP32Check=(mode == "fp32"))
     results = [None] * N
     errors = []
 
