@@ -58,12 +58,19 @@ def build_host(force=False):
     test = os.path.join(HERE, "..", "tests", "cpp", "test_b200backend.cpp")
     bench_src = os.path.join(HERE, "..", "tests", "cpp", "bench_evaluator.cpp")
     bench_exe = os.path.join(host, "bench_evaluator")   # native throughput driver of the evaluator front end (bench.py --evaluator)
-    newest = max(os.path.getmtime(p) for p in (src, test, bench_src, os.path.join(host, "reftypes.h"), os.path.join(HERE, "..", "include", "katacoffee_b200.h")))
-    if not force and all(os.path.exists(p) for p in (lib, exe, bench_exe)) and min(os.path.getmtime(p) for p in (lib, exe, bench_exe)) >= newest:
+    nneval_src = os.path.join(host, "b200nneval.cpp")   # class NNEvaluator (nneval.h) over kc_evaluator_*
+    nneval_test = os.path.join(HERE, "..", "tests", "cpp", "test_b200nneval.cpp")
+    nneval_exe = os.path.join(host, "test_b200nneval")
+    newest = max(os.path.getmtime(p) for p in (src, test, bench_src, nneval_src, nneval_test, os.path.join(host, "b200nneval.h"), os.path.join(host, "reftypes.h"),
+                                               os.path.join(HERE, "..", "include", "katacoffee_b200.h")))
+    outs = (lib, exe, bench_exe, nneval_exe)
+    if not force and all(os.path.exists(p) for p in outs) and min(os.path.getmtime(p) for p in outs) >= newest:
         return lib, exe
     inc = ["-I" + os.path.join(HERE, "..", "include"), "-I" + host]
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wall"] + inc + [src, "-o", lib, "-L" + HERE, "-lkatacoffee_b200",
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wall"] + inc + [src, nneval_src, "-o", lib, "-L" + HERE, "-lkatacoffee_b200",
                     "-Wl,-rpath,$ORIGIN"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [nneval_test, "-o", nneval_exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
+                    "-Wl,-rpath," + HERE, "-lpthread"], check=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-Wall"] + inc + [test, "-o", exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
                     "-Wl,-rpath," + HERE], check=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [bench_src, "-o", bench_exe, "-L" + HERE, "-lkatacoffee_b200", "-Wl,-rpath," + HERE, "-lpthread"],

@@ -159,6 +159,11 @@ void printDevices() {
 
 LoadedModel* loadModelFromDesc(ModelDesc&& desc) { return new LoadedModel(std::move(desc)); }
 const void* getB200ModelDescPOD(const LoadedModel* m) { return &m->pod; }
+void getB200ContextAndModel(ComputeContext* context, int gpuIdx, void** kcCtx, void** kcModel) {
+  auto cm = context->get(gpuIdx < 0 ? 0 : gpuIdx);
+  *kcCtx = cm.first; *kcModel = cm.second;
+}
+bool getB200UseFP32Check(const ComputeContext* context) { return context->useFP32Check; }
 LoadedModel* loadModelFile(const string& file, const string& expectedSha256) {
 #ifdef KC_IN_REFERENCE_TREE
   ModelDesc desc;

@@ -7,6 +7,7 @@
 // (field lists from cpp/neuralnet/desc.h:13-304, nninputs.h:75-118, nneval.h:45-65,
 // core/commontypes.h:4-5).  Nothing here is used by the CUDA library itself.
 #pragma once
+#include <cstdint>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -54,19 +55,55 @@ struct ModelDesc {
 };
 
 namespace NNPos { constexpr int MAX_BOARD_LEN = 10; constexpr int MAX_NN_POLICY_SIZE = MAX_BOARD_LEN * MAX_BOARD_LEN * 4; }  // nninputs.h:13-16
-struct NNOutput {   // nninputs.h:75-118 (fields the backend writes)
+struct Hash128 { uint64_t hash0 = 0, hash1 = 0; Hash128() {} Hash128(uint64_t a, uint64_t b) : hash0(a), hash1(b) {}   // core/hash.h
+                 bool operator==(const Hash128& o) const { return hash0 == o.hash0 && hash1 == o.hash1; } };
+struct NNOutput {   // nninputs.h:75-118 (fields the backend and the evaluator write)
+  Hash128 nnHash;
   float whiteWinProb, whiteLossProb, varTimeLeft, shorttermWinlossError;
   float policyProbs[NNPos::MAX_NN_POLICY_SIZE];
   int nnXLen, nnYLen;
   float* whiteOwnerMap = nullptr;
   float* noisedPolicyProbs = nullptr;
 };
-struct NNResultBuf {  // nneval.h:45-65 (fields the backend reads)
+struct NNResultBuf {  // nneval.h:45-65 (fields the backend reads, and the result the evaluator hands back)
+  bool hasResult = false;
   bool includeOwnerMap = false;
   int rowSpatialSize = 0, rowGlobalSize = 0;
   float* rowSpatial = nullptr; float* rowGlobal = nullptr;
+  std::shared_ptr<NNOutput> result;
   int symmetry = 0; double policyOptimism = 0.0;
 };
+
+// ---- game types NNEvaluator::evaluate reads (cpp/game/board.h:24-48, 74-75, 216-222; boardhistory.h:12-31; nninputs.h:36-46) ----
+typedef int8_t Player; typedef int8_t Color; typedef int8_t Direction; typedef short Spot;
+static constexpr Player P_BLACK = 1, P_WHITE = 2;
+static constexpr Color C_EMPTY = 0, C_BLACK = 1, C_WHITE = 2, C_WALL = 3;
+static constexpr Direction D_NORTH = 0, D_WEST = 1, D_NORTHWEST = 2, D_NORTHEAST = 3, D_NONE = 4;
+struct Loc { Spot spot; Direction dir; Loc() : spot(0), dir(D_NONE) {} Loc(Spot s, Direction d) : spot(s), dir(d) {} };
+struct Move { Loc loc; Player pla; Move() : pla(0) {} Move(Loc l, Player p) : loc(l), pla(p) {} };
+namespace Location {
+inline Spot getSpot(int x, int y, int x_size) { return (Spot)((x + 1) + (y + 1) * (x_size + 1)); }
+inline int getX(Spot spot, int x_size) { return spot % (x_size + 1) - 1; }
+inline int getY(Spot spot, int x_size) { return spot / (x_size + 1) - 1; }
+}
+struct Board {
+  static constexpr int MAX_LEN = 10, MAX_ARR_SIZE = (MAX_LEN + 1) * (MAX_LEN + 2) + 1;
+  int x_size, y_size, win_len;
+  Color colors[MAX_ARR_SIZE];
+  Board(int x = 5, int y = 5, int k = 4) : x_size(x), y_size(y), win_len(k) {
+    for(int i = 0; i < MAX_ARR_SIZE; i++) colors[i] = C_WALL;
+    for(int yy = 0; yy < y; yy++) for(int xx = 0; xx < x; xx++) colors[Location::getSpot(xx, yy, x)] = C_EMPTY;
+  }
+};
+struct BoardHistory { std::vector<Move> moveHistory; int numTurns = 0; bool isGameFinished = false; };
+namespace NNInputs { constexpr int SYMMETRY_NOTSPECIFIED = -1; }
+struct MiscNNInputParams { double playoutDoublingAdvantage = 0.0; float nnPolicyTemperature = 1.0f; int symmetry = NNInputs::SYMMETRY_NOTSPECIFIED; double policyOptimism = 0.0; };
+namespace NNPos {
+inline int getPolicySize(int nnXLen, int nnYLen) { return nnXLen * nnYLen * 4; }   // nninputs.cpp:47-49
+inline int locToPos(Loc loc, int boardXSize, int nnXLen, int nnYLen) {            // nninputs.cpp:6-14
+  return (int)loc.dir * nnXLen * nnYLen + Location::getY(loc.spot, boardXSize) * nnXLen + Location::getX(loc.spot, boardXSize);
+}
+}
 
 struct ComputeContext; struct ComputeHandle; struct InputBuffers; struct LoadedModel;
 namespace NeuralNet {
@@ -74,6 +111,9 @@ void globalInitialize(); void globalCleanup(); void printDevices();
 LoadedModel* loadModelFile(const std::string& file, const std::string& expectedSha256);
 LoadedModel* loadModelFromDesc(ModelDesc&& desc);   // standalone helper: the file parser is the reference's desc.cpp
 const void* getB200ModelDescPOD(const LoadedModel*);   // the kc_model_desc view handed to the C ABI (test hook)
+// the (kc_ctx*, kc_model*) pair of a GPU inside a ComputeContext (created on first use), for b200nneval.cpp
+void getB200ContextAndModel(ComputeContext* context, int gpuIdx, void** kcCtx, void** kcModel);
+bool getB200UseFP32Check(const ComputeContext* context);
 void freeLoadedModel(LoadedModel*);
 std::string getModelName(const LoadedModel*); int getModelVersion(const LoadedModel*);
 ModelPostProcessParams getPostProcessParams(const LoadedModel*);

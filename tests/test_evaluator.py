@@ -328,3 +328,21 @@ def test_cpp_stress(built_lib, tmp_path, tsan):
     assert "ThreadSanitizer" not in r.stderr, r.stderr
     rep = json.loads(r.stdout.strip().splitlines()[-1])
     assert rep["mismatches"] == 0 and rep["accounting"] and rep["cacheHits"] > 0 and rep["upgrades"] > 0 and rep["backpressureWaits"] > 0
+
+
+@pytest.mark.timeout(300)
+def test_cpp_nnevaluator_class(built_lib, tmp_path):
+    """host/b200nneval.cpp: class NNEvaluator with the reference's interface (nneval.h:80-175) over the front end, driven by
+    tests/cpp/test_b200nneval.cpp like the reference's search threads drive it (constructor and size-check errors with the
+    reference's wording, four threads, owner maps, cache / clearCache, run-time symmetry settings, a second policy temperature,
+    kill / setNumThreads / respawn); the batch function is a pure function of the staged row."""
+    import os
+    import subprocess
+    from katacoffee_b200 import backend, modeldesc
+    from katacoffee_b200 import build as kb
+    kb.build_host()
+    exe = os.path.join(os.path.dirname(kb.HERE), "katacoffee_b200", "host", "test_b200nneval")
+    path = str(tmp_path / "b2c32.bin.gz")
+    backend.writeModelFile(modeldesc.Model("b2c32", seed=4), path)
+    r = subprocess.run([exe, path, "cpu"], capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0 and "test_b200nneval cpu: ok" in r.stdout, r.stdout + r.stderr

@@ -123,3 +123,18 @@ def test_native_clients_throughput_tool(ctx, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     rep = json.loads(r.stdout.strip().splitlines()[-1])
     assert rep["failures"] == 0 and rep["cacheHits"] > 0.9 * rep["requests"]
+
+
+@pytest.mark.timeout(300)
+def test_cpp_nnevaluator_class_on_the_device(ctx, tmp_path):
+    """class NNEvaluator (host/b200nneval.cpp) with two server threads on GPU 0: four search threads, explicit symmetries, owner maps;
+    normalised policies over legal moves only, win + loss = 1."""
+    from katacoffee_b200 import backend, modeldesc
+    from katacoffee_b200 import build as kb
+    kb.build_host()
+    exe = os.path.join(ROOT, "katacoffee_b200", "host", "test_b200nneval")
+    path = str(tmp_path / "b6c96.bin.gz")
+    backend.writeModelFile(modeldesc.Model("b6c96", seed=11), path)
+    r = subprocess.run([exe, path, "gpu"], capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0 and "test_b200nneval gpu: ok" in r.stdout, r.stdout + r.stderr
+    print(r.stdout.strip())
