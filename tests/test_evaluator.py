@@ -11,8 +11,10 @@ W, H, K = 5, 5, 4
 HW = W * H
 
 
-def make_positions(oracle, n, seed, min_plies=0, max_plies=14):
+def make_positions(oracle, n, seed, min_plies=0, max_plies=14, dims=None):
     """Positions reached by the counter-RNG playouts of SURVEY.md 8(d): stones, player to move, last five moves, numTurns."""
+    W, H, K = dims or (5, 5, 4)
+    HW = W * H
     out = []
     g = 0
     og = oracle.Game(W, H, K)
@@ -41,7 +43,9 @@ def make_positions(oracle, n, seed, min_plies=0, max_plies=14):
     return out
 
 
-def oracle_game_of(oracle, stones, next_pla, hist, num_turns):
+def oracle_game_of(oracle, stones, next_pla, hist, num_turns, dims=None):
+    W, H, K = dims or (5, 5, 4)
+    HW = W * H
     og = oracle.Game(W, H, K)
     for c in range(HW):
         if stones[c]:
@@ -50,9 +54,10 @@ def oracle_game_of(oracle, stones, next_pla, hist, num_turns):
     return og
 
 
-def expected_output(oracle, omodel, p, sym, temp=1.0):
+def expected_output(oracle, omodel, p, sym, temp=1.0, dims=None):
     """NNEvaluator::evaluate of one position with the oracle: planes -> net under `sym` -> post-processing."""
-    og = oracle_game_of(oracle, p["stones"], p["nextPla"], p["hist"][-5:], p["numTurns"])
+    W, H, K = dims or (5, 5, 4)
+    og = oracle_game_of(oracle, p["stones"], p["nextPla"], p["hist"][-5:], p["numTurns"], dims)
     row, glob = og.fill_row_v1()
     pol, val, misc, own = omodel.forward(row[None], glob[None], W, H, symmetry=np.array([sym], np.int8))
     legal, n = og.legal_mask()
@@ -65,8 +70,9 @@ def expected_output(oracle, omodel, p, sym, temp=1.0):
 class OracleBackend:
     """The batch function: unpacks the rows the front end staged and evaluates them with the oracle."""
 
-    def __init__(self, oracle, omodel, fail_on_batch=None):
+    def __init__(self, oracle, omodel, fail_on_batch=None, dims=None):
         self.oracle, self.omodel = oracle, omodel
+        self.dims = dims or (5, 5, 4)
         self.batch_sizes = []
         self.servers = set()
         self.fail_on_batch = fail_on_batch
@@ -80,6 +86,8 @@ class OracleBackend:
             idx = len(self.batch_sizes) - 1
         if self.fail_on_batch is not None and idx == self.fail_on_batch:
             return 7
+        W, H, K = self.dims
+        HW = W * H
         n = b.n
         pol = np.ctypeslib.as_array(b.policyProbs, shape=(n, 4 * HW))
         wl = np.ctypeslib.as_array(b.whiteWinLoss, shape=(n, 2))
@@ -90,7 +98,7 @@ class OracleBackend:
             hist = [(int(c), int(pl)) for c, pl in moves if pl]
             if hist:
                 hist[-1] = (last_dir * HW + hist[-1][0], hist[-1][1])   # only the last move's direction is kept (and needed)
-            og = oracle_game_of(self.oracle, stones, pla, hist, nt)
+            og = oracle_game_of(self.oracle, stones, pla, hist, nt, self.dims)
             sh = og.sit_hash(pla)
             zp = backend.zobristTables()[1]
             assert int(b.hash0[i]) ^ int(zp[pla][0]) == int(sh[0]) and int(b.hash1[i]) ^ int(zp[pla][1]) == int(sh[1]), "packed pos_hash"
@@ -346,3 +354,32 @@ def test_cpp_nnevaluator_class(built_lib, tmp_path):
     backend.writeModelFile(modeldesc.Model("b2c32", seed=4), path)
     r = subprocess.run([exe, path, "cpu"], capture_output=True, text=True, timeout=200)
     assert r.returncode == 0 and "test_b200nneval cpu: ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("dims", [(6, 6, 4), (4, 3, 3), (7, 7, 5)])
+def test_other_board_sizes(oracle, built_lib, omodel, dims):
+    """6x6 k=4 (BASELINE configs[4]), a non-square board (the transposing symmetries are then flips only, nninputs.cpp:252-357) and the
+    largest device board: packing, hashes (SIZE_X / SIZE_Y Zobrist terms), symmetries and results against the oracle pipeline."""
+    from katacoffee_b200 import backend
+    Wd, Hd, Kd = dims
+    ps = make_positions(oracle, 40, seed=9, max_plies=Wd * Hd // 2, dims=dims)
+    be = OracleBackend(oracle, omodel, dims=dims)
+    ev = backend.NNEvaluator(nnXLen=Wd, nnYLen=Hd, winLen=Kd, maxBatchSize=8, numThreads=2, nnCacheSizePowerOfTwo=10, customBackend=be)
+    res = ev.evaluateMany(np.stack([p["stones"] for p in ps]), [p["nextPla"] for p in ps], np.stack([p["moves"] for p in ps]),
+                          [p["numTurns"] for p in ps], symmetry=np.arange(len(ps)) % 8, includeOwnerMap=True)
+    seen = set()
+    for i, (p, r) in enumerate(zip(ps, res)):
+        og = oracle_game_of(oracle, p["stones"], p["nextPla"], p["hist"][-5:], p["numTurns"], dims)
+        h, k = backend.evalPositionHash(Wd, Hd, p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+        assert h == tuple(int(x) for x in og.nn_hash()) == r["nnHash"]
+        if k in seen:
+            assert r["cacheHit"] or True   # a repeated position may have been served from the cache under another symmetry
+            continue
+        seen.add(k)
+        sym = r["symmetry"]
+        e = expected_output(oracle, omodel, p, sym, dims=dims)
+        assert np.abs(r["policyProbs"] - e["policy"]).max() < 1e-6 and np.abs(r["whiteOwnerMap"] - e["owner"]).max() < 1e-6
+        assert abs(r["whiteWinProb"] - e["winLoss"][0]) < 1e-6
+        assert (r["policyProbs"] >= 0).sum() == og.legal_mask()[1]
+    ev.close()
