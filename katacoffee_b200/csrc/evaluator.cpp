@@ -11,7 +11,8 @@
 //   owner-map post-processing nneval.cpp:817-838   tanh, flipped to white's perspective
 //
 // Built differently (nothing here is the reference's code):
-//   * rows travel as packed positions (5 x u64) and the device does rules -> planes -> net -> masked softmax;
+//   * rows travel as packed positions (5 x u64) and the device does rules -> planes -> net -> masked softmax, reading the rows
+//     from and writing the results to the mapped staging itself (no copy calls per batch);
 //   * submit path: ticket = fetch_add(1); batch = ticket / maxBatch, slot = ticket % maxBatch; the client writes its row
 //     into the staging of that batch and bumps its `ready` counter.  A server closes batch q by CAS-ing the ticket counter
 //     up to (q+1)*maxBatch and waits for `ready` to reach the number of claimed slots;
@@ -154,7 +155,7 @@ struct Cache {
 
 // ---- one staging buffer of the ring ------------------------------------------------------------------------------------
 struct Staging {
-  // inputs (page-locked when the device backend is used), SoA so that each array is one H2D copy
+  // inputs: the packed rows as five arrays (the layout of kc::State); mapped page-locked memory when the device backend is used
   uint64_t *black = nullptr, *white = nullptr, *hash0 = nullptr, *hash1 = nullptr, *misc = nullptr;
   int8_t* symmetry = nullptr;
   uint8_t* wantOwner = nullptr;
@@ -342,9 +343,6 @@ struct Pending {   // a row in flight
   bool cachedValues = false;   // owner-map upgrade: keep the cached policy / values
   int nextPla = 0;
 };
-
-// claim a ticket and write the row; `mayBlock` == false returns -1 instead of waiting for the buffer to be recycled
-struct Claim { uint64_t ticket; };
 
 bool bufferReady(Staging& b, uint64_t q) { return b.seq.load(std::memory_order_acquire) == q; }
 
