@@ -359,6 +359,12 @@ int kc_search_read_training_rows(kc_search* s, int* numRows, int* numDropped, ui
 /* Graph-mode searches (useGraphSearch or subtreeValueBiasFactor != 0): digest [G] = order-independent hash over every node of
  * each game's graph (visits, weightSum and utilityAvg bit patterns, edges with their visit counts and creation order), the
  * quantity the oracle's ko_search_run_graph reports, for whole-graph comparisons. */
+/* The rows as the reference's training-data file (TrainingWriteBuffers::writeToZipFile, cpp/dataio/trainingwrite.cpp:566-587): a zip
+ * archive of five deflated numpy arrays with NumpyBuffer's 256-byte headers (cpp/dataio/numpywrite.cpp:110-222) under the member names
+ * binaryInputNCHWPacked [N,15,ceil(HW/8)] u1, globalInputNC [N,1] f4, policyTargetsNCMove [N,2,4HW] i2, globalTargetsNC [N,64] f4,
+ * valueTargetsNCHW [N,5,H,W] i1 -- what python/shuffle.py and numpy.load read.  Host-only; written to path + ".tmp" and renamed. */
+int kc_training_write_npz(const char* path, int numRows, int xSize, int ySize, const uint8_t* binaryInputNCHWPacked, const float* globalInputNC,
+                          const int16_t* policyTargetsNCMove, const float* globalTargetsNC, const int8_t* valueTargetsNCHW);
 int kc_search_tree_digest(kc_search* s, uint64_t* digest);
 int64_t kc_search_launch_count(const kc_search* s);
 

@@ -374,7 +374,7 @@ class Search:
     def writeTrainingNpz(self, path, clear=True):
         """numpy .npz with the reference's array names (TrainingWriteBuffers::writeToZipFile, trainingwrite.cpp:566-587)."""
         rows, dropped = self.readTrainingRows(clear)
-        np.savez_compressed(path, **rows)
+        writeTrainingNpz(path, self.W, self.H, rows)
         return len(rows["globalInputNC"]), dropped
 
     def launchCount(self):
@@ -512,6 +512,16 @@ def evalUnpackPosition(xSize, ySize, black, white, misc):
     pla, nt, ld = C.c_int8(), C.c_int32(), C.c_int32()
     check(lib().kc_eval_unpack_position(xSize, ySize, int(black), int(white), int(misc), ptr(stones), C.byref(pla), ptr(moves), C.byref(nt), C.byref(ld)))
     return stones, int(pla.value), moves, int(nt.value), int(ld.value)
+
+
+def writeTrainingNpz(path, xSize, ySize, rows):
+    """kc_training_write_npz: the reference's training-data file (trainingwrite.cpp:566-587) from a dict of the five row arrays."""
+    n = len(rows["globalInputNC"])
+    a = [np.ascontiguousarray(rows[k], dt) for k, dt in (("binaryInputNCHWPacked", np.uint8), ("globalInputNC", np.float32), ("policyTargetsNCMove", np.int16),
+                                                          ("globalTargetsNC", np.float32), ("valueTargetsNCHW", np.int8))]
+    HW = xSize * ySize
+    assert a[0].shape == (n, 15, (HW + 7) // 8) and a[1].shape == (n, 1) and a[2].shape == (n, 2, 4 * HW) and a[3].shape == (n, 64) and a[4].shape == (n, 5, ySize, xSize)
+    check(lib().kc_training_write_npz(os.fsencode(path), n, xSize, ySize, *[ptr(x) for x in a]))
 
 
 def zobristTables():

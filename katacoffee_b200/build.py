@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkatacoffee_b200.so")
-SOURCES = ["zobrist.cpp", "modelfile.cpp", "sgf.cpp", "evaluator.cpp", "games.cu", "net_fp32.cu", "net_bf16.cu", "search.cu"]
+SOURCES = ["zobrist.cpp", "modelfile.cpp", "sgf.cpp", "npzwrite.cpp", "evaluator.cpp", "games.cu", "net_fp32.cu", "net_bf16.cu", "search.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -164,6 +164,7 @@ PROTOTYPES = {
     "kc_search_play": (C.c_int, [vp, C.c_int, vp, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
     "kc_search_enable_training_rows": (C.c_int, [vp, C.c_int]),
     "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
+    "kc_training_write_npz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
     "kc_evaluator_create": (C.c_int, [vp, vp, C.POINTER(EvaluatorConfig), C.POINTER(vp)]),
