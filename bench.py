@@ -177,7 +177,7 @@ def evaluator_arm(net, W, H):
     exe = os.path.join(ROOT, "katacoffee_b200", "host", "bench_evaluator")
     try:
         from katacoffee_b200 import backend, modeldesc
-        threads = os.cpu_count() or 1
+        threads = min(os.cpu_count() or 1, 32)
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, net + ".bin.gz")
             backend.writeModelFile(modeldesc.Model(net, seed=11), path)
