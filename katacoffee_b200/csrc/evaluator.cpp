@@ -25,6 +25,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <thread>
 
 #ifndef KC_EVALUATOR_HOST_ONLY   // the thread-sanitizer build of tests/cpp/test_evaluator_stress.cpp compiles the queue and cache alone
@@ -116,9 +117,13 @@ struct Cache {
     if(mutexPow2 > sizePow2) mutexPow2 = sizePow2;   // nneval.cpp:860-861
     size = 1ULL << sizePow2; mask = size - 1; mutexMask = (1u << mutexPow2) - 1;
     P = P_; HW = HW_; rowFloats = P + 4 + HW;
-    tags.reset(new Tag[size]());
-    rows.reset(new float[size * (size_t)rowFloats]);
-    mutexes.reset(new std::mutex[(size_t)mutexMask + 1]);
+    try {   // no C++ exception may cross the C ABI
+      tags.reset(new Tag[size]());
+      rows.reset(new float[size * (size_t)rowFloats]);
+      mutexes.reset(new std::mutex[(size_t)mutexMask + 1]);
+    } catch(const std::bad_alloc&) {
+      return kc::fail("kc_evaluator: out of memory for a cache of 2^" + std::to_string(sizePow2) + " entries of " + std::to_string(rowFloats * 4 + 24) + " bytes");
+    }
     return 0;
   }
   // true on a hit; *needOwner is set when the entry lacks the owner map the caller wants (policy / values are still copied)
@@ -500,8 +505,13 @@ static int evaluatorCreateCommon(const kc_evaluator_config* cfg, bool pinned, kc
   return 0;
 }
 
-static void evaluatorSpawn(kc_evaluator* ev) {
-  for(int i = 0; i < ev->cfg.numServerThreads; i++) ev->threads.emplace_back(serveLoop, ev, i);
+static int evaluatorSpawn(kc_evaluator* ev) {
+  try {
+    for(int i = 0; i < ev->cfg.numServerThreads; i++) ev->threads.emplace_back(serveLoop, ev, i);
+  } catch(const std::exception& e) {
+    return kc::fail(std::string("kc_evaluator_create: cannot start a server thread: ") + e.what());
+  }
+  return 0;
 }
 
 #ifndef KC_EVALUATOR_HOST_ONLY
@@ -524,7 +534,7 @@ int kc_evaluator_create_multi(int numServers, kc_ctx* const* ctxs, const kc_mode
       return kc::fail(msg);
     }
   }
-  evaluatorSpawn(ev);
+  if(evaluatorSpawn(ev)) { const std::string msg = kc_last_error(); kc_evaluator_destroy(ev); return kc::fail(msg); }
   *out = ev;
   return 0;
 }
@@ -543,7 +553,7 @@ int kc_evaluator_create_custom(const kc_evaluator_config* cfg, kc_eval_backend_f
   kc_evaluator* ev = nullptr;
   if(evaluatorCreateCommon(cfg, false, &ev)) return 1;
   ev->fn = fn; ev->user = user;
-  evaluatorSpawn(ev);
+  if(evaluatorSpawn(ev)) { const std::string msg = kc_last_error(); kc_evaluator_destroy(ev); return kc::fail(msg); }
   *out = ev;
   return 0;
 }
