@@ -63,3 +63,20 @@ def test_symmetry_tables_match_oracle(oracle, built_lib):
             inv = oracle.copy_outputs_with_symmetry(a, 1, h, w, sym)
             if h == w or not (sym & 4):
                 assert (inv == src).all(), (h, w, sym)   # outputs symmetry undoes inputs symmetry
+
+
+def test_header_is_c_and_c_program_links(built_lib, tmp_path):
+    """The boundary is plain C: the header compiles as C99 with -pedantic, and tests/cpp/test_cabi.c (C99, no C++) links against the library
+    and drives the host-only entry points (hashes, the evaluator front end over a C batch function, SGF, the training-data file)."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "katacoffee_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = os.path.join(ROOT, "katacoffee_b200")
+    exe = str(tmp_path / "test_cabi")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I" + inc, os.path.join(ROOT, "tests", "cpp", "test_cabi.c"), "-o", exe,
+                        "-L" + libdir, "-lkatacoffee_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "test_cabi: ok" in r.stdout, r.stdout + r.stderr
