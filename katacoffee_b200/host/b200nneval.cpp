@@ -102,9 +102,7 @@ kc_evaluator* NNEvaluator::instanceFor(int winLen, float temperature) {
   return ev;
 }
 
-void NNEvaluator::evaluate(Board& board, const BoardHistory& history, Player nextPlayer, const MiscNNInputParams& nnInputParams, NNResultBuf& buf,
-                           bool skipCache, bool includeOwnerMap) {
-  buf.hasResult = false;
+void NNEvaluator::checkBoard(const Board& board, const MiscNNInputParams& nnInputParams) const {
   if(board.x_size > nnXLen || board.y_size > nnYLen)   // nneval.cpp:599-603
     throw StringError("NNEvaluator was configured with nnXLen = " + to_string(nnXLen) + " nnYLen = " + to_string(nnYLen) +
                       " but was asked to evaluate board with larger x or y size");
@@ -113,27 +111,95 @@ void NNEvaluator::evaluate(Board& board, const BoardHistory& history, Player nex
                       " and requireExactNNLen, but was asked to evaluate board with different x or y size");
   if(nnInputParams.playoutDoublingAdvantage != 0 || nnInputParams.policyOptimism > 0)
     throw StringError("B200 NNEvaluator: playoutDoublingAdvantage / policyOptimism are not inputs of the Coffee V1 features");
-  kc_evaluator* ev = instanceFor(board.win_len, nnInputParams.nnPolicyTemperature);
+}
 
-  int8_t stones[NNPos::MAX_BOARD_LEN * NNPos::MAX_BOARD_LEN];
+// (Board, BoardHistory) -> the position format of the C ABI: stones [H*W], the last five moves oldest first
+static kc_eval_position toPosition(const Board& board, const BoardHistory& history, Player nextPlayer, int nnXLen, int nnYLen, int8_t* stones, int16_t* moves) {
   for(int y = 0; y < board.y_size; y++)
     for(int x = 0; x < board.x_size; x++) stones[y * board.x_size + x] = board.colors[Location::getSpot(x, y, board.x_size)];
-  int16_t moves[10];
   const size_t n = history.moveHistory.size();
-  for(int k = 0; k < 5; k++) {   // the last five moves, oldest first
+  for(int k = 0; k < 5; k++) {
     const bool have = n >= (size_t)(5 - k);
     if(have) {
       const Move& m = history.moveHistory[n - 5 + k];
       moves[2 * k] = (int16_t)NNPos::locToPos(m.loc, board.x_size, nnXLen, nnYLen); moves[2 * k + 1] = m.pla;
     } else { moves[2 * k] = -1; moves[2 * k + 1] = 0; }
   }
-  kc_eval_position pos{stones, moves, history.numTurns, (int8_t)nextPlayer};
+  return kc_eval_position{stones, moves, history.numTurns, (int8_t)nextPlayer};
+}
 
+static std::shared_ptr<NNOutput> newOutput() {
 #ifdef KC_IN_REFERENCE_TREE
-  buf.result = std::make_shared<NNOutput>();   // NNOutput's destructor frees the owner map
+  return std::make_shared<NNOutput>();   // NNOutput's destructor frees the owner map
 #else
-  buf.result = std::shared_ptr<NNOutput>(new NNOutput(), [](NNOutput* o) { delete[] o->whiteOwnerMap; delete o; });
+  return std::shared_ptr<NNOutput>(new NNOutput(), [](NNOutput* o) { delete[] o->whiteOwnerMap; delete o; });
 #endif
+}
+
+void NNEvaluator::evaluateAveragedOverSymmetries(Board& board, const BoardHistory& history, Player nextPlayer, const MiscNNInputParams& nnInputParams,
+                                                 const int* symmetries, int numSymmetries, NNResultBuf& buf, bool includeOwnerMap) {
+  buf.hasResult = false;
+  if(numSymmetries < 1 || numSymmetries > 8 || symmetries == nullptr) throw StringError("NNEvaluator::evaluateAveragedOverSymmetries: 1..8 symmetries are required");
+  checkBoard(board, nnInputParams);
+  kc_evaluator* ev = instanceFor(board.win_len, nnInputParams.nnPolicyTemperature);
+  int8_t stones[NNPos::MAX_BOARD_LEN * NNPos::MAX_BOARD_LEN];
+  int16_t moves[10];
+  const kc_eval_position one = toPosition(board, history, nextPlayer, nnXLen, nnYLen, stones, moves);
+  const int area = nnXLen * nnYLen;
+  vector<kc_eval_position> pos((size_t)numSymmetries, one);
+  vector<kc_eval_output> outs((size_t)numSymmetries);
+  vector<int8_t> syms((size_t)numSymmetries);
+  vector<float> policies((size_t)numSymmetries * policySize), owners(includeOwnerMap ? (size_t)numSymmetries * area : 0);
+  for(int i = 0; i < numSymmetries; i++) {
+    if(symmetries[i] < 0 || symmetries[i] > 7) throw StringError("NNEvaluator::evaluateAveragedOverSymmetries: symmetry out of range");
+    syms[i] = (int8_t)symmetries[i];
+    outs[i] = kc_eval_output{};
+    outs[i].policyProbs = policies.data() + (size_t)i * policySize;
+    outs[i].whiteOwnerMap = includeOwnerMap ? owners.data() + (size_t)i * area : nullptr;
+  }
+  if(kc_evaluator_evaluate_many(ev, numSymmetries, pos.data(), syms.data(), /*skipCache*/ 1, includeOwnerMap ? 1 : 0, outs.data()))
+    throw StringError(string("B200 NNEvaluator: ") + kc_last_error());
+  buf.result = newOutput();
+  NNOutput& o = *buf.result;
+  const float len = (float)numSymmetries;   // nninputs.cpp:95-170: plain means; the legal sets agree because it is one position
+  o.nnXLen = nnXLen; o.nnYLen = nnYLen;
+  o.nnHash = Hash128(outs[0].nnHash[0], outs[0].nnHash[1]);
+  o.whiteWinProb = o.whiteLossProb = o.varTimeLeft = o.shorttermWinlossError = 0.0f;
+  for(int i = 0; i < numSymmetries; i++) {
+    o.whiteWinProb += outs[i].whiteWinProb; o.whiteLossProb += outs[i].whiteLossProb;
+    o.varTimeLeft += outs[i].varTimeLeft; o.shorttermWinlossError += outs[i].shorttermWinlossError;
+  }
+  o.whiteWinProb /= len; o.whiteLossProb /= len; o.varTimeLeft /= len; o.shorttermWinlossError /= len;
+  for(int p = 0; p < policySize; p++) {
+    float sum = 0.0f;
+    for(int i = 0; i < numSymmetries; i++) sum += policies[(size_t)i * policySize + p];
+    o.policyProbs[p] = sum / len;
+  }
+  for(int p = policySize; p < NNPos::MAX_NN_POLICY_SIZE; p++) o.policyProbs[p] = -1.0f;
+  o.whiteOwnerMap = nullptr;
+  if(includeOwnerMap) {
+    o.whiteOwnerMap = new float[(size_t)area];
+    for(int p = 0; p < area; p++) {
+      float sum = 0.0f;
+      for(int i = 0; i < numSymmetries; i++) sum += owners[(size_t)i * area + p];
+      o.whiteOwnerMap[p] = sum / len;
+    }
+  }
+  buf.symmetry = symmetries[0];
+  buf.includeOwnerMap = includeOwnerMap;
+  buf.hasResult = true;
+}
+
+void NNEvaluator::evaluate(Board& board, const BoardHistory& history, Player nextPlayer, const MiscNNInputParams& nnInputParams, NNResultBuf& buf,
+                           bool skipCache, bool includeOwnerMap) {
+  buf.hasResult = false;
+  checkBoard(board, nnInputParams);
+  kc_evaluator* ev = instanceFor(board.win_len, nnInputParams.nnPolicyTemperature);
+
+  int8_t stones[NNPos::MAX_BOARD_LEN * NNPos::MAX_BOARD_LEN];
+  int16_t moves[10];
+  kc_eval_position pos = toPosition(board, history, nextPlayer, nnXLen, nnYLen, stones, moves);
+  buf.result = newOutput();
   NNOutput& o = *buf.result;
   o.nnXLen = nnXLen; o.nnYLen = nnYLen;
   o.whiteOwnerMap = includeOwnerMap ? new float[(size_t)nnXLen * nnYLen] : nullptr;

@@ -53,6 +53,12 @@ class NNEvaluator {
   // Blocks until the result is in buf.result (nneval.cpp:588-845); thread-safe.
   void evaluate(Board& board, const BoardHistory& history, Player nextPlayer, const MiscNNInputParams& nnInputParams, NNResultBuf& buf, bool skipCache,
                 bool includeOwnerMap);
+  // The root evaluation of Search::initNodeNNOutput under rootNumSymmetriesToSample > 1 (cpp/search/searchnnhelpers.cpp:67-83) in one call: the
+  // position goes into the queue once per symmetry (cache skipped, as there), the rows travel in the same batch, and buf.result is their average
+  // exactly as NNOutput::NNOutput(const vector<shared_ptr<NNOutput>>&) forms it (cpp/neuralnet/nninputs.cpp:95-170).  Not in the reference's
+  // class: there the search thread blocks on numSymmetries consecutive evaluate() calls (which also works with this class).
+  void evaluateAveragedOverSymmetries(Board& board, const BoardHistory& history, Player nextPlayer, const MiscNNInputParams& nnInputParams,
+                                      const int* symmetries, int numSymmetries, NNResultBuf& buf, bool includeOwnerMap);
   void waitForNextNNEvalIfAny() {}   // only used to pace pondering threads in the reference; evaluations here never stall a caller that has none pending
   void spawnServerThreads();
   void killServerThreads();
@@ -73,6 +79,7 @@ class NNEvaluator {
  private:
   struct Instance { int winLen; float temperature; kc_evaluator* ev; };   // one front end per (win_len, nnPolicyTemperature) seen
   kc_evaluator* instanceFor(int winLen, float temperature);
+  void checkBoard(const Board& board, const MiscNNInputParams& nnInputParams) const;
 
   const std::string modelName, modelFileName;
   const int nnXLen, nnYLen;

@@ -4,6 +4,7 @@
 //
 //   test_b200nneval <model file> cpu    batch function = a pure function of the staged row (no GPU): interface, errors, cache, statistics
 //   test_b200nneval <model file> gpu    the device: results equal kc_evaluator_evaluate on the same positions, probabilities are normalised
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -187,6 +188,29 @@ static void cpuMode(const std::string& modelFile) {
   NNResultBuf buf2;
   nnEval->evaluate(ps[2].board, ps[2].hist, ps[2].nextPla, params, buf2, false, false);
   EXPECT(!(buf.result->nnHash == buf2.result->nnHash));   // the temperature is folded into the hash (nninputs.cpp:485-492)
+  {   // the root under several symmetries at once, averaged as NNOutput's averaging constructor does (nninputs.cpp:95-170)
+    const int syms[4] = {1, 4, 6, 3};
+    const Position& p = ps[5];
+    const uint64_t before = nnEval->numRowsProcessed();
+    NNResultBuf avg;
+    nnEval->evaluateAveragedOverSymmetries(ps[5].board, ps[5].hist, ps[5].nextPla, params, syms, 4, avg, true);
+    EXPECT(avg.hasResult && nnEval->numRowsProcessed() == before + 4);
+    bool ok = true;
+    for(int j = 0; j < 100; j++) {
+      float sum = 0.0f;
+      for(int k = 0; k < 4; k++) sum += valueOf(p.black, p.white, p.misc, syms[k], j);
+      ok = ok && avg.result->policyProbs[j] == sum / 4.0f;
+    }
+    for(int j = 100; j < NNPos::MAX_NN_POLICY_SIZE; j++) ok = ok && avg.result->policyProbs[j] == -1.0f;
+    EXPECT(ok);
+    float w = 0.0f;
+    for(int k = 0; k < 4; k++) w += valueOf(p.black, p.white, p.misc, syms[k], 1000);
+    EXPECT(avg.result->whiteWinProb == w / 4.0f && avg.result->varTimeLeft == 3.f);
+    EXPECT(avg.result->whiteOwnerMap != nullptr && std::fabs(avg.result->whiteOwnerMap[3] - (p.nextPla == P_WHITE ? 1.f : -1.f) * std::tanh(0.25f)) < 1e-6f);
+    EXPECT(throwsWith([&] { nnEval->evaluateAveragedOverSymmetries(ps[5].board, ps[5].hist, ps[5].nextPla, params, syms, 0, avg, false); }, "1..8 symmetries"));
+    const int bad[2] = {0, 8};
+    EXPECT(throwsWith([&] { nnEval->evaluateAveragedOverSymmetries(ps[5].board, ps[5].hist, ps[5].nextPla, params, bad, 2, avg, false); }, "out of range"));
+  }
   nnEval->clearStats();
   EXPECT(nnEval->numRowsProcessed() == 0);
   nnEval->killServerThreads();
@@ -227,6 +251,25 @@ static void gpuMode(const std::string& modelFile) {
     for(int c = 0; c < 25; c++)
       if(ps[i].board.colors[Location::getSpot(c % 5, c / 5, 5)] != C_EMPTY)
         for(int d = 0; d < 4; d++) EXPECT(o.policyProbs[d * 25 + c] == -1.0f);
+  }
+  {   // all eight symmetries in one call = the mean of eight single evaluations
+    const int syms[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    const Position& p = ps[11];
+    Position q = p;
+    NNResultBuf avg, one;
+    MiscNNInputParams params;
+    nnEval->evaluateAveragedOverSymmetries(q.board, q.hist, q.nextPla, params, syms, 8, avg, false);
+    std::vector<double> mean(100, 0.0);
+    double win = 0.0;
+    for(int s = 0; s < 8; s++) {
+      params.symmetry = s;
+      nnEval->evaluate(q.board, q.hist, q.nextPla, params, one, true, false);
+      for(int j = 0; j < 100; j++) mean[j] += one.result->policyProbs[j] / 8.0;
+      win += one.result->whiteWinProb / 8.0;
+    }
+    double worst = 0.0;
+    for(int j = 0; j < 100; j++) worst = std::max(worst, std::fabs(mean[j] - (double)avg.result->policyProbs[j]));
+    EXPECT(worst < 1e-4 && std::fabs(win - (double)avg.result->whiteWinProb) < 1e-4);
   }
   EXPECT(nnEval->numRowsProcessed() > 0 && nnEval->isAnyThreadUsingFP16());
   printf("NNEvaluator on the device: %llu rows in %llu batches\n", (unsigned long long)nnEval->numRowsProcessed(), (unsigned long long)nnEval->numBatchesProcessed());
