@@ -150,6 +150,15 @@ def test_position_hash_and_cache_key(oracle, built_lib):
     assert h1 == h2 and k1 != k2
     # numTurns is in neither (the planes do not read it)
     assert backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"] + 2) == (h1, k1)
+    # pinned to the values SURVEY.md 8(c) derived with the reference's own md5.cpp / sha2.cpp: the empty boards' hashes are
+    # SIZE_X[n] ^ SIZE_Y[n] ^ ZOBRIST_PLAYER_HASH[pla]
+    PLAYER = {1: (0xc535f97fd0cc7e76, 0x8a2a2a2ff24dbb6d), 2: (0x392045e5c8d9bd73, 0xd3c1c132e034dcb0)}
+    SIZE = {5: ((0x478fc9704f6fb627, 0xb1ea08b4f90dfbf6), (0x8ae2f36ea4707544, 0x4a0b61a306b2d937)),
+            6: ((0xcbfa3568128cb44f, 0x7e0be6bb36f9ec98), (0x30cb3b6e8ff75c22, 0xc24be82a513dfb9e))}
+    for n, (sx, sy) in SIZE.items():
+        for pla, ph in PLAYER.items():
+            hh, _ = backend.evalPositionHash(n, n, np.zeros(n * n, np.int8), pla)
+            assert hh == (sx[0] ^ sy[0] ^ ph[0], sx[1] ^ sy[1] ^ ph[1]), (n, pla)
     # round trip of the packing
     st, pla, mv, nt, ld = backend.evalUnpackPosition(W, H, 0b100001, 0b10, (3 | (1 << 6)) | (2 << 40) | (9 << 48) | ((2 << 3) << 56))
     assert st[0] == 1 and st[5 - 0] == 0 and st[1] == 2 and pla == 2 and nt == 9 and ld == 2 and tuple(mv[4]) == (3, 1) and mv[3][1] == 0
