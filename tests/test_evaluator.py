@@ -363,6 +363,20 @@ def test_cpp_nnevaluator_class(built_lib, tmp_path):
     backend.writeModelFile(modeldesc.Model("b2c32", seed=4), path)
     r = subprocess.run([exe, path, "cpu"], capture_output=True, text=True, timeout=200)
     assert r.returncode == 0 and "test_b200nneval cpu: ok" in r.stdout, r.stdout + r.stderr
+    # the same driver with the class, the shim and the front end compiled under -fsanitize=thread
+    root = os.path.dirname(kb.HERE)
+    host, csrc, libdir = os.path.join(kb.HERE, "host"), os.path.join(kb.HERE, "csrc"), kb.HERE
+    tsan_exe = str(tmp_path / "nneval_tsan")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fopenmp", "-DKC_EVALUATOR_HOST_ONLY", "-w", "-I" + os.path.join(root, "include"), "-I" + host,
+           "-I" + csrc, "-I/usr/local/cuda/include", os.path.join(root, "tests", "cpp", "test_b200nneval.cpp"), os.path.join(host, "b200nneval.cpp"),
+           os.path.join(host, "b200backend.cpp"), "-x", "c++", os.path.join(csrc, "evaluator.cpp"), os.path.join(csrc, "zobrist.cpp"), "-o", tsan_exe,
+           "-L" + libdir, "-lkatacoffee_b200", "-Wl,-rpath," + libdir, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in r.stderr:
+        pytest.skip("libtsan is not installed")
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([tsan_exe, path, "cpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr and "test_b200nneval cpu: ok" in r.stdout, r.stdout + r.stderr[-2000:]
 
 
 @pytest.mark.timeout(300)
