@@ -406,3 +406,57 @@ def test_other_board_sizes(oracle, built_lib, omodel, dims):
         assert abs(r["whiteWinProb"] - e["winLoss"][0]) < 1e-6
         assert (r["policyProbs"] >= 0).sum() == og.legal_mask()[1]
     ev.close()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("dims", [(2, 2, 2), (3, 7, 3), (5, 5, 4), (7, 7, 4), (7, 4, 4)])
+def test_packing_round_trip_on_arbitrary_positions(oracle, built_lib, dims):
+    """Random stone placements and histories (not only reachable ones), every supported shape: what the front end stages unpacks to what
+    was submitted, its pos_hash / NNInputs::getHash are the oracle's, and the cache key separates any two different (stones, player,
+    last five (cell, player), last direction) tuples."""
+    from katacoffee_b200 import backend
+    Wd, Hd, Kd = dims
+    HWd = Wd * Hd
+    rng = np.random.default_rng(Wd * 100 + Hd)
+    n = 120
+    stones = rng.integers(0, 3, (n, HWd)).astype(np.int8)
+    nextPla = rng.integers(1, 3, n).astype(np.int8)
+    moves = np.full((n, 5, 2), -1, np.int16)
+    numTurns = rng.integers(0, 200, n).astype(np.int32)
+    for i in range(n):
+        k = int(rng.integers(0, 6))
+        for j in range(5 - k, 5):
+            moves[i, j] = (int(rng.integers(0, 4 * HWd)), int(rng.integers(1, 3)))
+    staged = {}
+
+    def record(server, b):
+        for i in range(b.n):
+            st, pla, mv, nt, ld = backend.evalUnpackPosition(Wd, Hd, b.black[i], b.white[i], b.misc[i])
+            staged[(st.tobytes(), pla, mv.tobytes(), nt, ld)] = (int(b.hash0[i]), int(b.hash1[i]))
+            np.ctypeslib.as_array(b.policyProbs, shape=(b.n, 4 * HWd))[i] = 0.0
+        return 0
+
+    ev = backend.NNEvaluator(nnXLen=Wd, nnYLen=Hd, winLen=Kd, maxBatchSize=16, numThreads=1, nnCacheSizePowerOfTwo=-1, customBackend=record)
+    res = ev.evaluateMany(stones, nextPla, moves, numTurns)
+    ev.close()
+    zp = backend.zobristTables()[1]
+    keys = {}
+    for i in range(n):
+        cells = np.array([[m[0] % HWd if m[0] >= 0 else -1, m[1] if m[0] >= 0 else 0] for m in moves[i]], np.int16)
+        last_dir = int(moves[i, 4, 0]) // HWd if moves[i, 4, 0] >= 0 else 4
+        key = (stones[i].tobytes(), int(nextPla[i]), cells.tobytes(), int(numTurns[i]), last_dir)
+        assert key in staged, i
+        og = oracle.Game(Wd, Hd, Kd)
+        for c in range(HWd):
+            if stones[i, c]:
+                og.set_stone(c % Wd, c // Wd, int(stones[i, c]))
+        hist = [(int(m[0]), int(m[1])) for m in moves[i] if m[0] >= 0]
+        og.set_history(hist, int(numTurns[i]), int(nextPla[i]))
+        sh = og.sit_hash(int(nextPla[i]))
+        h0, h1 = staged[key]
+        assert (h0 ^ int(zp[nextPla[i]][0]), h1 ^ int(zp[nextPla[i]][1])) == (int(sh[0]), int(sh[1]))
+        assert res[i]["nnHash"] == tuple(int(x) for x in og.nn_hash())
+        ck = backend.evalPositionHash(Wd, Hd, stones[i], nextPla[i], moves[i], numTurns[i])[1]
+        ident = (stones[i].tobytes(), int(nextPla[i]), cells.tobytes(), last_dir)
+        assert keys.setdefault(ck, ident) == ident
+    assert len(keys) == len({v for v in keys.values()})
