@@ -16,6 +16,13 @@
 
 using namespace std;
 
+#ifdef KC_IN_REFERENCE_TREE
+namespace NeuralNet {   // exported by b200backend.cpp next to the nninterface.h functions (declared in reftypes.h for the standalone build)
+void getB200ContextAndModel(ComputeContext* context, int gpuIdx, void** kcCtx, void** kcModel);
+bool getB200UseFP32Check(const ComputeContext* context);
+}
+#endif
+
 static uint64_t hashSeed(const string& s) {   // FNV-1a: the seed only has to differ between evaluators
   uint64_t h = 1469598103934665603ULL;
   for(unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
