@@ -141,12 +141,18 @@ int kc_sgf_parse(const char* sgf, int* xSize, int* ySize, int* winLen, int8_t* i
  * Compute handle.  Replaces createComputeHandle / createInputBuffers / getOutput
  * (nninterface.h:77-117).
  * ------------------------------------------------------------------------------------------- */
-#define KC_FLAG_FP32_CHECK 1u       /* CUDA-core fp32 path (1e-4 gate); default is bf16 tcgen05 */
+#define KC_FLAG_FP32_CHECK 1u       /* CUDA-core fp32 path (1e-4 gate); default is the tcgen05 tensor-core path */
 #define KC_FLAG_INPUTS_NHWC 2u      /* kc_forward spatial rows are NHWC (inputsUseNHWC)          */
 #define KC_FLAG_SYM_PERMUTE_DIRS 4u /* play mode, SURVEY.md 8.1-K: a symmetry also permutes the direction channels (inputs 3..6 by
                                        getSymDir, cpp/neuralnet/nninputs.cpp:409-433, the 4 policy channels by its inverse), which
                                        makes it a true symmetry of the game; default is the reference backends' spatial-only copy.
                                        Applies to kc_forward and kc_games_eval; kc_games_features is always spatial-only. */
+
+#define KC_FLAG_OPERANDS_BF16 8u    /* tensor-core path: weights and activations as bf16 operands.  Default is fp16 operands (tcgen05
+                                       kind::f16 takes either format at the same rate, fp32 accumulation and an fp32 residual stream
+                                       in both): 3 more mantissa bits bring raw policy / ownership logits inside 1e-2 of the fp32
+                                       reference (bf16 operands: 2-4e-2, profiles/r02_bf16_error_by_layer.json).  Activations and
+                                       weights saturate at +-65504 instead of overflowing. */
 
 /* Page-locked host memory for the buffers handed to kc_forward (InputBuffers of nninterface.h:92-93): with pinned rows the
  * chunked H2D / D2H copies of kc_forward are asynchronous DMA that overlap the kernels; pageable memory works but serialises. */
@@ -156,7 +162,8 @@ int kc_host_free(void* p);
 int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLen, int nnYLen,
                      unsigned flags, kc_handle** out);
 int kc_handle_destroy(kc_handle* h);
-int kc_handle_uses_bf16(const kc_handle* h); /* isUsingFP16 analogue, nninterface.h:88 */
+int kc_handle_uses_bf16(const kc_handle* h); /* isUsingFP16 analogue, nninterface.h:88: 1 on the tensor-core path (either 16-bit operand format) */
+int kc_handle_operand_format(const kc_handle* h); /* arithmetic type of the convolutions' operands: 0 fp16, 1 bf16 (both: fp32 accumulation), 2 fp32 (check path) */
 /* NeuralNet::getOutput (nninterface.h:112-117).  Inputs: spatial [n][15*H*W] fp32 (NCHW, or NHWC
  * with KC_FLAG_INPUTS_NHWC), global [n][1], symmetry [n] in 0..7 (NULL = 0).  Outputs are raw
  * logits, inverse-symmetrised, NNPos order (cpp/neuralnet/nninputs.cpp:6-14): policy [n][4*H*W],

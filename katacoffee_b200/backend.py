@@ -97,17 +97,22 @@ def parseSgf(text, maxMoves=400):
 
 
 class ComputeHandle:
-    def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False):
+    def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False,
+                 operandsBF16=False):
         self.ctx, self.loadedModel = ctx, loadedModel
         self.maxBatch, self.nnXLen, self.nnYLen = maxBatchSize, nnXLen, nnYLen
         self.inputsUseNHWC = inputsUseNHWC
         flags = ((capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_INPUTS_NHWC if inputsUseNHWC else 0) |
-                 (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0))
+                 (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0) | (capi.FLAG_OPERANDS_BF16 if operandsBF16 else 0))
         self._p = C.c_void_p()
         check(lib().kc_handle_create(ctx._p, loadedModel._p, maxBatchSize, nnXLen, nnYLen, flags, C.byref(self._p)))
 
     def isUsingBF16(self):
+        """isUsingFP16 analogue (nninterface.h:88): true on the tensor-core path, whichever 16-bit operand format it runs."""
         return bool(lib().kc_handle_uses_bf16(self._p))
+
+    def operandFormat(self):
+        return ("fp16", "bf16", "fp32")[lib().kc_handle_operand_format(self._p)]
 
     def launchCount(self):
         return int(lib().kc_handle_launch_count(self._p))
@@ -132,8 +137,9 @@ class ComputeHandle:
             self._p = C.c_void_p()
 
 
-def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False):
-    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC, playModeSymmetry)
+def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False,
+                        operandsBF16=False):
+    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC, playModeSymmetry, operandsBF16)
 
 
 def getOutput(handle, rowSpatial, rowGlobal, symmetry=None, ownership=True, out=None):

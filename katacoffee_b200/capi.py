@@ -108,6 +108,7 @@ EVAL_BACKEND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(EvalBatch)
 FLAG_FP32_CHECK = 1
 FLAG_INPUTS_NHWC = 2
 FLAG_SYM_PERMUTE_DIRS = 4
+FLAG_OPERANDS_BF16 = 8
 
 vp = C.c_void_p
 # name -> (restype, argtypes); must list every symbol include/katacoffee_b200.h declares
@@ -123,6 +124,7 @@ PROTOTYPES = {
     "kc_handle_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
     "kc_handle_destroy": (C.c_int, [vp]),
     "kc_handle_uses_bf16": (C.c_int, [vp]),
+    "kc_handle_operand_format": (C.c_int, [vp]),
     "kc_forward": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "kc_handle_read_outputs": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "kc_handle_launch_count": (C.c_int64, [vp]),

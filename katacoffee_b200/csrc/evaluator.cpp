@@ -18,6 +18,7 @@
 //     up to (q+1)*maxBatch and waits for `ready` to reach the number of claimed slots;
 //   * a staging buffer is recycled by the last client that has copied its result out (`consumed` == n);
 //   * cache entries are inline rows of one float array.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
@@ -83,7 +84,10 @@ int packPosition(int W, int H, const kc_eval_position* p, float policyTemperatur
     }
   }
   m |= ((uint64_t)lastDir << 40);
-  const uint64_t historyBits = m;   // last five (cell, player) + last direction: with the stones, everything the planes and legality read
+  // last five (cell, player) + last direction + min(numTurns, 5): with the stones, everything the planes and legality read -- the history
+  // planes 7..10 are gated on numTurns >= 2..5 (games_device.cuh v1Planes, as nninputs.cpp:575-620), so two requests with equal moves
+  // and different numTurns have different inputs and must not share a cache entry
+  const uint64_t historyBits = m | ((uint64_t)std::min(p->numTurns, 5) << 44);
   m |= ((uint64_t)p->numTurns << 48) | ((uint64_t)(p->nextPla << 3) << 56);
   r.black = bb; r.white = ww; r.hash0 = a0; r.hash1 = a1; r.misc = m;
   // NNInputs::getHash: getSitHash(nextPla) = pos_hash ^ ZOBRIST_PLAYER_HASH[pla] (board.cpp:288-292); never finished here

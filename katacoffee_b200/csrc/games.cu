@@ -47,6 +47,7 @@ struct FeatOut {
   const int8_t* symmetry;   // per game or null
   int permuteDirs;          // play mode (ledger K): with a symmetry, channels 3..6 follow symDir
   int gamesPerBlock;
+  uint32_t tileOne, tileK;  // FEAT 3: bit patterns of 1.0 and of win_len in the handle's 16-bit operand format (fp16 or bf16: both exact)
 };
 
 template <bool DO_STEP, int FEAT, class D>
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(FEAT >= 3 ? TB_TILES : TB_PLAIN) games_kernel(
     // (channels 0..14 = V1 planes, channel 15 = the global feature win_len broadcast on board cells)
     const int ntiles = (ng + g.NB - 1) / g.NB;
     const int tileBase = gBase / g.NB;
-    const uint32_t ONE = 0x3f80u;
-    const uint32_t kval = (uint32_t)__bfloat16_as_ushort(__float2bfloat16((float)dm.K()));
+    const uint32_t ONE = fo.tileOne;
+    const uint32_t kval = fo.tileK;
     for(int j = t; j < ntiles * 256; j += THREADS) {
       int tile = j >> 8, chunk = (j >> 7) & 1, row = j & 127;
       int y = row / g.tileRowW, rr = row - y * g.tileRowW;
@@ -658,6 +659,7 @@ int kc_games_destroy(kc_games* G) {
   cudaFree(G->st.gameId); cudaFree(G->st.misc); cudaFree(G->d_moves); cudaFree(G->d_legal); cudaFree(G->d_status);
   cudaFree(G->d_sitHash); cudaFree(G->d_played); cudaFree(G->d_stats); cudaFree(G->d_planes); cudaFree(G->d_global);
   cudaFree(G->d_sym); cudaFree(G->d_flush);
+  cudaFree(G->d_ppPolicy); cudaFree(G->d_ppWinLoss); cudaFree(G->d_ppMisc); cudaFree(G->d_ppHash);
   for(float* p : G->d_planesRing) cudaFree(p);
   for(cudaEvent_t e : G->evPool) cudaEventDestroy(e);
   cudaEventDestroy(G->ev0); cudaEventDestroy(G->ev1);
@@ -792,6 +794,7 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   so.played = nullptr; so.stats = nullptr;
   if(kc::handleIsBf16(h)) {
     fo.tiles = (uint4*)kc::handleInputTiles(h) + (size_t)(rowOffset / g.NB) * 2 * TILE_ROWS;
+    kc::handleTileConstants(h, (float)g.K, &fo.tileOne, &fo.tileK);
     launchGames<false>(G, smallCtas ? 4 : 3, 0, so, fo);
   } else {
     fo.planes = kc::handleInputNHWC(h); fo.global = kc::handleInputGlobal(h);
@@ -883,6 +886,7 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       launchGames<true>(G, 1, 0, so, fo);
     } else if(kc::handleIsBf16(h)) {
       fo.tiles = (uint4*)kc::handleInputTiles(h);
+      kc::handleTileConstants(h, (float)g.K, &fo.tileOne, &fo.tileK);
       launchGames<true>(G, 3, 0, so, fo);
       if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
     } else {
@@ -941,8 +945,11 @@ int kc_games_postprocess(kc_games* G, kc_handle* h, float policyTemperature, flo
   const Geom& g = G->geom;
   if(kc::handleCheckGeometry(h, g.W, g.H, g.numGames)) return 1;
   size_t n = (size_t)g.numGames;
-  float *dP, *dV, *dM; uint64_t* dH;
-  KC_CUDA(cudaMalloc(&dP, n * 4 * g.HW * 4)); KC_CUDA(cudaMalloc(&dV, n * 8)); KC_CUDA(cudaMalloc(&dM, n * 8)); KC_CUDA(cudaMalloc(&dH, n * 16));
+  if(!G->d_ppPolicy) {   // owned by the games object: no allocation (and no implicit device synchronisation) per call
+    KC_CUDA(cudaMalloc(&G->d_ppPolicy, n * 4 * g.HW * 4)); KC_CUDA(cudaMalloc(&G->d_ppWinLoss, n * 8));
+    KC_CUDA(cudaMalloc(&G->d_ppMisc, n * 8)); KC_CUDA(cudaMalloc(&G->d_ppHash, n * 16));
+  }
+  float *dP = G->d_ppPolicy, *dV = G->d_ppWinLoss, *dM = G->d_ppMisc; uint64_t* dH = G->d_ppHash;
   kc::launchPostprocess(h, g.numGames, g.LW, G->d_legal, G->d_status, G->d_sitHash, policyTemperature, dP, dV, dM, dH, G->stream);
   G->launches++;
   KC_CUDA(cudaGetLastError());
@@ -951,7 +958,6 @@ int kc_games_postprocess(kc_games* G, kc_handle* h, float policyTemperature, flo
   if(misc) KC_CUDA(cudaMemcpyAsync(misc, dM, n * 8, cudaMemcpyDeviceToHost, G->stream));
   if(nnHash) KC_CUDA(cudaMemcpyAsync(nnHash, dH, n * 16, cudaMemcpyDeviceToHost, G->stream));
   KC_CUDA(cudaStreamSynchronize(G->stream));
-  cudaFree(dP); cudaFree(dV); cudaFree(dM); cudaFree(dH);
   return 0;
 }
 

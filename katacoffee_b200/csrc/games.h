@@ -25,6 +25,8 @@ struct kc_games {
   // so a ply never overwrites lines of the previous one that are still dirty in L2
   float* d_planesRing[3] = {nullptr, nullptr, nullptr};
   const float* lastRunPlanes = nullptr;   // where the last ply of the last rules+features kc_games_run wrote its planes
+  // kc_games_postprocess outputs, allocated on first use and kept: [G][4*HW] probabilities, [G][2] win/loss, [G][2] misc, [G][2] nnHash
+  float *d_ppPolicy = nullptr, *d_ppWinLoss = nullptr, *d_ppMisc = nullptr; uint64_t* d_ppHash = nullptr;
 };
 
 

@@ -10,7 +10,10 @@
 // Canonical readings:
 //  * version must be 1 (cpp/neuralnet/modelversion.h:7-12).  As written desc.cpp:989-998 rejects every version (< 3 and > 1).
 //  * an activation layer is its name, optionally followed by ACTIVATION_IDENTITY / ACTIVATION_RELU / ACTIVATION_MISH (the
-//    reference reads the kind only for version >= 11, desc.cpp:243-256; without it the activation is ReLU).
+//    reference reads the kind only for version >= 11, desc.cpp:243-256; without it the activation is ReLU).  The writer emits
+//    ReLU layers without the token (= the reference's version-1 format) and the token only for identity / Mish (an extension).
+//  * sizes from the file are bounded (channels <= 8192, filters <= 9, floats <= what the rest of the file can hold) before any
+//    allocation, and every exception is turned into an error return at the C ABI.
 //  * Coffee head shapes: p2Conv 4 output channels (one per direction); gpoolToPassMul is part of the format and is parsed,
 //    checked (inChannels = 3 x g1 channels) and ignored -- Coffee has no pass; v3 2 outputs (win, loss); sv3 2 outputs
 //    (varTimeLeft, shorttermWinlossError); ownership 1 channel.
@@ -18,6 +21,7 @@
 // No GPU is needed for anything in this file.
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -134,6 +138,10 @@ struct Cursor {
   }
   // readFloats (desc.cpp:37-92)
   std::vector<float> floats(size_t n, const std::string& name) {
+    // a header can claim any size: nothing is allocated that the rest of the file could not fill (a binary float takes 4 bytes, a text
+    // float at least 2 characters incl. its separator)
+    const size_t remaining = s.size() - std::min(pos, s.size());
+    if(n > remaining / (binary ? 4 : 2) + 1) throw ParseError{name + ": did not find the expected number of floats (the file is too short for " + std::to_string(n) + " weights)"};
     std::vector<float> buf(n);
     if(!binary) {
       for(size_t i = 0; i < n; i++) {
@@ -154,7 +162,7 @@ struct Cursor {
       }
       if(s.compare(pos, 4, "BIN@") != 0) throw ParseError{name + ": did not find expected header for binary float block"};
       pos += 4;
-      if(pos + n * 4 > s.size()) throw ParseError{name + ": did not find the expected number of floats in binary float block"};
+      if(n > (s.size() - pos) / 4) throw ParseError{name + ": did not find the expected number of floats in binary float block"};
       const unsigned char* p = (const unsigned char*)s.data() + pos;
       for(size_t i = 0; i < n; i++) {   // little-endian on every host
         const uint32_t u = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
@@ -168,6 +176,8 @@ struct Cursor {
   }
 };
 
+constexpr int MAX_CHANNELS = 8192, MAX_FILTER = 9;   // far above any KataGo-family net; keeps every size product inside size_t
+
 kc_conv_desc parseConv(Cursor& c, Layers& L) {
   const std::string name = c.token("convlayer");
   kc_conv_desc d{};
@@ -178,6 +188,9 @@ kc_conv_desc parseConv(Cursor& c, Layers& L) {
   if(dilX <= 0 || dilY <= 0) throw ParseError{name + ": dilation factors must be positive"};
   if(d.convXSize % 2 != 1 || d.convYSize % 2 != 1) throw ParseError{name + ": convolution filter sizes must be odd, found even sizes"};
   if(dilX != 1 || dilY != 1) throw ParseError{name + ": dilated convolutions are not supported by the B200 backend"};
+  // bounds before any size arithmetic: 9 * 9 * 8192 * 8192 fits size_t with room to spare
+  if(d.convXSize > MAX_FILTER || d.convYSize > MAX_FILTER) throw ParseError{name + ": convolution filter size above " + std::to_string(MAX_FILTER)};
+  if(d.inChannels > MAX_CHANNELS || d.outChannels > MAX_CHANNELS) throw ParseError{name + ": more than " + std::to_string(MAX_CHANNELS) + " channels"};
   const std::vector<float> f = c.floats((size_t)d.convYSize * d.convXSize * d.inChannels * d.outChannels, name);
   // file order y,x,ic,oc -> oc,ic,y,x (desc.cpp:131-152)
   std::vector<float> w(f.size());
@@ -196,6 +209,7 @@ kc_bn_desc parseBN(Cursor& c, Layers& L) {
   kc_bn_desc d{};
   d.numChannels = c.integer(name); d.epsilon = c.real(name); d.hasScale = c.integer(name); d.hasBias = c.integer(name);
   if(d.numChannels < 1) throw ParseError{name + ": numChannels (" + std::to_string(d.numChannels) + ") < 1"};
+  if(d.numChannels > MAX_CHANNELS) throw ParseError{name + ": more than " + std::to_string(MAX_CHANNELS) + " channels"};
   if(!(d.epsilon > 0)) throw ParseError{name + ": epsilon (" + std::to_string(d.epsilon) + ") <= 0"};
   const size_t n = (size_t)d.numChannels;
   d.mean = L.keep(c.floats(n, name));
@@ -221,6 +235,7 @@ kc_matmul_desc parseMatMul(Cursor& c, Layers& L) {
   kc_matmul_desc d{};
   d.inChannels = c.integer(name); d.outChannels = c.integer(name);
   if(d.inChannels <= 0 || d.outChannels <= 0) throw ParseError{name + ": number of in and out channels must be positive"};
+  if(d.inChannels > 3 * MAX_CHANNELS || d.outChannels > MAX_CHANNELS) throw ParseError{name + ": matrix dimensions out of range"};
   d.weights = L.keep(c.floats((size_t)d.inChannels * d.outChannels, name));   // file order ic,oc is the layout used (desc.cpp:284-299)
   return d;
 }
@@ -230,6 +245,7 @@ kc_matbias_desc parseMatBias(Cursor& c, Layers& L) {
   kc_matbias_desc d{};
   d.numChannels = c.integer(name);
   if(d.numChannels <= 0) throw ParseError{name + ": number of channels must be positive"};
+  if(d.numChannels > MAX_CHANNELS) throw ParseError{name + ": more than " + std::to_string(MAX_CHANNELS) + " channels"};
   d.weights = L.keep(c.floats((size_t)d.numChannels, name));
   return d;
 }
@@ -387,7 +403,10 @@ struct Writer {
     if(hs) floats(d.scale, d.numChannels);
     if(hb) floats(d.bias, d.numChannels);
   }
-  void act(const std::string& name, int a) { tok(name); tok(a == 0 ? "ACTIVATION_IDENTITY" : a == 2 ? "ACTIVATION_MISH" : "ACTIVATION_RELU"); }
+  // Version 1 < 11: the reference's ActivationLayerDesc reads no kind token and means ReLU (desc.cpp:243-256), so a ReLU layer is written
+  // as its name alone -- a file of a ReLU net is in the reference's format.  Identity / Mish have no version-1 spelling: their kind
+  // token is this parser's extension (see the header), and such a file is readable by kc_modelfile_load only.
+  void act(const std::string& name, int a) { tok(name); if(a != 1) tok(a == 0 ? "ACTIVATION_IDENTITY" : "ACTIVATION_MISH"); }
   void matmul(const std::string& name, const kc_matmul_desc& d) { tok(name); ints({d.inChannels, d.outChannels}); floats(d.weights, (size_t)d.inChannels * d.outChannels); }
   void matbias(const std::string& name, const kc_matbias_desc& d) { tok(name); ints({d.numChannels}); floats(d.weights, d.numChannels); }
 };
@@ -444,6 +463,8 @@ int kc_modelfile_load(const char* path, const char* expectedSha256, kc_modelfile
                        "it's probably the wrong file, renaming will probably NOT help)."};
   } catch(const ParseError& e) {
     return kc::fail("Error loading or parsing model file " + file + ": " + e.msg);
+  } catch(const std::exception& e) {   // bad_alloc / length_error from a corrupt header: no C++ exception crosses the C ABI
+    return kc::fail("Error loading or parsing model file " + file + ": " + e.what());
   }
   *out = m.release();
   return 0;
@@ -460,6 +481,7 @@ int kc_modelfile_write(const kc_model_desc* d, const char* name, const char* pat
   KC_CHECK(isSuffix(lower, ".txt") || isSuffix(lower, ".bin") || isSuffix(lower, ".txt.gz") || isSuffix(lower, ".bin.gz"),
            "kc_modelfile_write: the file name must end with .txt, .bin, .txt.gz or .bin.gz");
   KC_CHECK(d->numBlocks >= 1, "kc_modelfile_write: the format needs at least one block (desc.cpp:661-662)");
+  try {   // no C++ exception (bad_alloc on a huge description) crosses the C ABI
   Writer w;
   w.binary = isSuffix(lower, ".bin") || isSuffix(lower, ".bin.gz");
   w.tok(name);
@@ -502,6 +524,7 @@ int kc_modelfile_write(const kc_model_desc* d, const char* name, const char* pat
   out.write(bytes.data(), (std::streamsize)bytes.size());
   out.close();
   KC_CHECK(out.good(), "kc_modelfile_write: write to " + file + " failed");
+  } catch(const std::exception& e) { return kc::fail(std::string("kc_modelfile_write: ") + e.what()); }
   return 0;
 }
 

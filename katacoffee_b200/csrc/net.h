@@ -18,7 +18,10 @@ constexpr int ACT_ROWS = TILE_ROWS + 2 * HALO_ROWS;
 int handleCheckGeometry(kc_handle* h, int W, int H, int n);
 bool handleIsBf16(const kc_handle* h);
 bool handlePermutesDirs(const kc_handle* h);   // KC_FLAG_SYM_PERMUTE_DIRS
-void* handleInputTiles(kc_handle* h);      // bf16 path: [tiles][2][128] 16-byte chunks
+void* handleInputTiles(kc_handle* h);      // tensor path: [tiles][2][128] 16-byte chunks, 8 channels each in the handle's 16-bit operand format
+// bit patterns of 1.0 and of `k` (the win length, a small integer) in the handle's operand format: what a tile producer writes.
+// (tcgen05 kind::f16 wants A and B in ONE format: an MMA with bf16 tiles against fp16 weights is an illegal instruction on B200.)
+void handleTileConstants(const kc_handle* h, float k, uint32_t* one, uint32_t* kBits);
 float* handleInputNHWC(kc_handle* h);      // fp32 path: [n][H*W][15]
 float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 // Runs the net on the handle's (already symmetrised) input buffer on `stream`; symmetry_dev (device

@@ -25,6 +25,7 @@
 //  * Global pooling, the pooled matmuls, both heads, the inverse output symmetry and the final
 //    stores are done by the epilogue warps in fp32 on CUDA cores (they are < 0.5 % of the FLOPs).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
@@ -110,8 +111,9 @@ constexpr int MAX_LAYERS = 48;   // 1 + 2*blocks + 1; the table travels in the k
 
 struct TrunkProgram {
   std::vector<LayerDesc> layers;
-  uint8_t* d_w = nullptr;
-  uint8_t* d_wPair = nullptr;   // the same stream with every stage split in halves of the output channels (pair mode)
+  // weight streams per operand format (index = the tcgen05 format code: 0 fp16, 1 bf16)
+  uint8_t* d_w[2] = {nullptr, nullptr};
+  uint8_t* d_wPair[2] = {nullptr, nullptr};   // the same stream with every stage split in halves of the output channels (pair mode)
   float* d_params = nullptr;
   LayerDesc* d_layers = nullptr;
   size_t wBytes = 0;
@@ -129,6 +131,8 @@ struct TrunkParams {
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
   int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
+  int opFmt;         // tensor-core operand format of the input tiles, the weights and the activations: 0 fp16 (default), 1 bf16
+                     // (KC_FLAG_OPERANDS_BF16).  One format for A and B: a kind::f16 MMA with mixed formats is an illegal instruction.
   int skew;          // two tiles per CTA: tile 1's MMA issuer starts this many weight stages after tile 0's, so that the layer boundary of
                      // one tile (accumulator -> epilogue -> first chunk published, ~1,200 clk) is covered by the other tile's MMAs
   int g1Act, p1Act, v1Act, v2Act;   // head activations
@@ -157,6 +161,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// two activations as tensor-core operands: fp16 (saturating: an activation beyond 65504 stays finite) or bf16; `f16` is warp-uniform
+__device__ __forceinline__ uint32_t packOp(float a, float b, bool f16) {
+  if(f16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
+    return r;
+  }
+  return pack2(a, b);
+}
 
 struct EpiCtx {
   int t;            // tile within the CTA
@@ -168,6 +181,7 @@ struct EpiCtx {
   uint8_t* act;     // this tile's activation buffer
   uint32_t barChunk;  // address of actReady[t][0] (pair mode: shared::cluster address in the leader CTA)
   bool remote;        // pair mode, peer CTA: barriers the MMA issuer waits on live in the leader
+  bool f16;           // activations are published as fp16 (else bf16)
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
   const float* par;  // staged folded BN of the layer being finished: scale[MAXC] | bias[MAXC]
   long long* dbg;    // non-null for the one thread / layer whose timeline is recorded
@@ -192,8 +206,8 @@ __device__ __forceinline__ void publish16T(const EpiCtx& c, int cc, const float 
       a2 = actf(fmaf(x2, s.z, bb.z), act); a3 = actf(fmaf(x3, s.w, bb.w), act);
     }
     if(!c.valid) { a0 = a1 = a2 = a3 = 0.f; }
-    pk[2 * q] = pack2(a0, a1);
-    pk[2 * q + 1] = pack2(a2, a3);
+    pk[2 * q] = packOp(a0, a1, c.f16);
+    pk[2 * q + 1] = packOp(a2, a3, c.f16);
   }
   uint8_t* dst = c.act + (size_t)(2 * cc) * CHUNK_BYTES + (size_t)(HALO_ROWS + c.r) * 16;
   *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -554,7 +568,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
     if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) P.dbg[20] = clock64();
     for(int l = 0; l < P.numLayers; l++) {
       const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
-      const uint32_t idesc = idesc_bf16_f32(128 * K::NCTA, N);
+      const uint32_t idesc = idesc_f16kind_f32(128 * K::NCTA, N, (uint32_t)P.opFmt, (uint32_t)P.opFmt);   // A and B must share the format
       const uint32_t d = tmemBase + t * (2 * K::MAXC) + (P.layers[l].outSel ? K::MAXC : 0);
       const uint32_t bStep = 2 * N / K::NCTA;                    // one K-step of weights = N*32 bytes (per CTA: its half of the rows)
       const uint32_t bLbo = (uint32_t)(N / K::NCTA) << 16;       // LBO = rows*16 bytes
@@ -760,6 +774,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     c.tmemLane = tmemBase + ((uint32_t)(q * 32) << 16) + c.t * (2 * K::MAXC);
     c.act = smem + K::OFF_ACT + c.t * K::ACT_BYTES;
     c.remote = K::PAIR && rank != 0;
+    c.f16 = P.opFmt == 0;
     c.barChunk = bars + (K::BAR_CHUNK + c.t * K::NCH) * 8;
     uint32_t barHead = bars + (K::BAR_HEAD + c.t) * 8;
     if(c.remote) { c.barChunk = mapa(c.barChunk, 0); barHead = mapa(barHead, 0); }
@@ -821,7 +836,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
 // kc_forward input conversion: raw fp32 rows (NCHW/NHWC) + global -> symmetrised bf16 tiles
 __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __restrict__ rawGlobal, const int8_t* __restrict__ sym,
                                 const uint8_t* __restrict__ dstOfSrc, uint4* __restrict__ tiles, int n, int numTiles,
-                                int NB, int W, int H, int rawNHWC, int permuteDirs) {
+                                int NB, int W, int H, int rawNHWC, int permuteDirs, int f16) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if(j >= numTiles * 256) return;
   const int HW = W * H, stride = W + 1, tileRowW = NB * stride;
@@ -843,7 +858,7 @@ __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __re
       if(c < 15) f[q] = rawNHWC ? raw[((size_t)game * HW + srcCell) * 15 + c] : raw[((size_t)game * 15 + c) * HW + srcCell];
       else f[q] = rawGlobal[game];
     }
-    v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    v = make_uint4(packOp(f[0], f[1], f16), packOp(f[2], f[3], f16), packOp(f[4], f[5], f16), packOp(f[6], f[7], f16));
   }
   tiles[((size_t)tile * 2 + chunk) * 128 + row] = v;
 }
@@ -937,6 +952,7 @@ struct Packer {
   std::vector<uint8_t> w;
   std::vector<float> p;
   // append the stages of one conv layer. rows(n, cin, tap) returns the weight.
+  int fmt = 0;   // operand format the stream is packed in: 0 fp16 (saturating), 1 bf16
   template <class F>
   unsigned addConv(int N, int cinPadded, int ntaps, F weightAt) {
     unsigned off = (unsigned)w.size();
@@ -945,11 +961,16 @@ struct Packer {
       for(int tap = 0; tap < ntaps; tap++) {
         size_t base = w.size();
         w.resize(base + (size_t)N * 32);
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(w.data() + base);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(w.data() + base);
         for(int h = 0; h < 2; h++)
           for(int n = 0; n < N; n++)
-            for(int j = 0; j < 8; j++)
-              dst[((size_t)h * N + n) * 8 + j] = __float2bfloat16(weightAt(n, cc * 16 + h * 8 + j, tap));
+            for(int j = 0; j < 8; j++) {
+              const float v = weightAt(n, cc * 16 + h * 8 + j, tap);
+              uint16_t bits;
+              if(fmt == 1) { __nv_bfloat16 q = __float2bfloat16(v); memcpy(&bits, &q, 2); }
+              else { __half q = __float2half_rn(std::min(std::max(v, -65504.0f), 65504.0f)); memcpy(&bits, &q, 2); }
+              dst[((size_t)h * N + n) * 8 + j] = bits;
+            }
       }
     return off;
   }
@@ -996,8 +1017,11 @@ int buildTrunkProgram(kc_model* m) {
   if(2 * m->blocks.size() + 2 > (size_t)MAX_LAYERS) return unsupported("too many blocks for the tcgen05 kernel's layer table");
   TrunkProgram* T = new TrunkProgram();
   T->cfg = cfg;
-  Packer pk;
   double macs = 0;
+  // the layer table and the fp32 parameters do not depend on the operand format; the weight stream is packed once per format
+  auto packAll = [&](Packer& pk) {
+  T->layers.clear();
+  macs = 0;
   auto bnOf = [&](size_t blockIdx) -> const BNW& { return blockIdx < m->blocks.size() ? m->blocks[blockIdx].preBN : m->trunkTipBN; };
   {
     // layer 0: initial 3x3 conv over 15 planes + the global feature as a 16th input channel whose
@@ -1055,23 +1079,31 @@ int buildTrunkProgram(kc_model* m) {
     T->layers.push_back(L);
     macs += 3.0 * HEADC * C;
   }
+  };
+  Packer pk, pkB;
+  pk.fmt = 0; pkB.fmt = 1;
+  packAll(pkB);
+  packAll(pk);
   // Note: cat() above relies on each sub-block keeping the exact sizes the kernel indexes with
   // (HEADC, 96*HEADC, ...); alignment padding is only appended after the whole block.
   T->v2C = m->v2Mul.oc;
   T->wBytes = pk.w.size();
   T->flopsPerEval = 2.0 * macs;   // per board cell; multiplied by H*W by the caller
-  if(cudaMalloc(&T->d_w, pk.w.size()) != cudaSuccess || cudaMalloc(&T->d_params, pk.p.size() * 4) != cudaSuccess ||
+  if(cudaMalloc(&T->d_params, pk.p.size() * 4) != cudaSuccess ||
      cudaMalloc(&T->d_layers, T->layers.size() * sizeof(LayerDesc)) != cudaSuccess) {
     delete T;
     return kc::fail("buildTrunkProgram: out of device memory");
   }
-  cudaMemcpy(T->d_w, pk.w.data(), pk.w.size(), cudaMemcpyHostToDevice);
-  if(cfg == 0) {
+  for(int fmt = 0; fmt < 2; fmt++) {
+    const std::vector<uint8_t>& ws = fmt == 0 ? pk.w : pkB.w;
+    if(cudaMalloc(&T->d_w[fmt], ws.size()) != cudaSuccess) { delete T; return kc::fail("buildTrunkProgram: out of device memory"); }
+    cudaMemcpy(T->d_w[fmt], ws.data(), ws.size(), cudaMemcpyHostToDevice);
+    if(cfg != 0) continue;
     // pair-mode stream: per stage [rank 0: rows 0..N/2 of every K-step][rank 1: rows N/2..N], each K-step still [2][rows][8]
-    std::vector<uint8_t> w2(pk.w.size());
+    std::vector<uint8_t> w2(ws.size());
     for(const LayerDesc& L : T->layers) {
       const int N = L.N, half = N / 2;
-      const uint8_t* src = pk.w.data() + L.wOffset;
+      const uint8_t* src = ws.data() + L.wOffset;
       uint8_t* dst = w2.data() + L.wOffset;
       for(int k0 = 0; k0 < L.nk; k0 += KSTEPS_PER_STAGE) {
         const int ks = std::min(KSTEPS_PER_STAGE, L.nk - k0);
@@ -1081,11 +1113,10 @@ int buildTrunkProgram(kc_model* m) {
               memcpy(dst, src + (size_t)(k0 + k) * N * 32 + (size_t)kc * N * 16 + (size_t)h * half * 16, (size_t)half * 16);
               dst += (size_t)half * 16;
             }
-        src += 0;
       }
     }
-    if(cudaMalloc(&T->d_wPair, w2.size()) != cudaSuccess) { delete T; return kc::fail("buildTrunkProgram: out of device memory"); }
-    cudaMemcpy(T->d_wPair, w2.data(), w2.size(), cudaMemcpyHostToDevice);
+    if(cudaMalloc(&T->d_wPair[fmt], w2.size()) != cudaSuccess) { delete T; return kc::fail("buildTrunkProgram: out of device memory"); }
+    cudaMemcpy(T->d_wPair[fmt], w2.data(), w2.size(), cudaMemcpyHostToDevice);
   }
   cudaMemcpy(T->d_params, pk.p.data(), pk.p.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(T->d_layers, T->layers.data(), T->layers.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice);
@@ -1095,7 +1126,8 @@ int buildTrunkProgram(kc_model* m) {
 
 void freeTrunkProgram(kc_model* m) {
   if(!m->trunk) return;
-  cudaFree(m->trunk->d_w); cudaFree(m->trunk->d_wPair); cudaFree(m->trunk->d_params); cudaFree(m->trunk->d_layers);
+  for(int fmt = 0; fmt < 2; fmt++) { cudaFree(m->trunk->d_w[fmt]); cudaFree(m->trunk->d_wPair[fmt]); }
+  cudaFree(m->trunk->d_params); cudaFree(m->trunk->d_layers);
   delete m->trunk;
   m->trunk = nullptr;
 }
@@ -1138,10 +1170,18 @@ int convertInputToTiles(kc_handle* h, int n, int rawNHWC, const int8_t* sym_dev,
   uint4* tiles = (uint4*)h->d_tiles + (size_t)(rowOffset / NB) * 2 * TILE_ROWS;
   k_convert_tiles<<<(numTiles * 256 + 255) / 256, 256, 0, st>>>(h->d_raw + (size_t)rowOffset * 15 * HW, h->d_rawGlobal + rowOffset,
                                                                sym_dev ? sym_dev + rowOffset : nullptr, h->d_dstOfSrc, tiles, n, numTiles,
-                                                               NB, h->W, h->H, rawNHWC, (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0);
+                                                               NB, h->W, h->H, rawNHWC, (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0,
+                                                               (h->flags & KC_FLAG_OPERANDS_BF16) ? 0 : 1);
   h->launches++;
   KC_CUDA(cudaGetLastError());
   return 0;
+}
+
+void handleTileConstants(const kc_handle* h, float k, uint32_t* one, uint32_t* kBits) {
+  uint16_t a, b;
+  if(h->flags & KC_FLAG_OPERANDS_BF16) { __nv_bfloat16 x = __float2bfloat16(1.0f), y = __float2bfloat16(k); memcpy(&a, &x, 2); memcpy(&b, &y, 2); }
+  else { __half x = __float2half_rn(1.0f), y = __float2half_rn(k); memcpy(&a, &x, 2); memcpy(&b, &y, 2); }
+  *one = a; *kBits = b;
 }
 
 static bool trunkUsesPairs() { static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }(); return usePair; }
@@ -1152,7 +1192,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   const kc_model* m = h->model;
   const TrunkProgram* T = m->trunk;
   TrunkParams P{};
-  P.wstream = T->d_w; P.params = T->d_params;
+  P.opFmt = (h->flags & KC_FLAG_OPERANDS_BF16) ? 1 : 0;
+  P.wstream = T->d_w[P.opFmt]; P.params = T->d_params;
   P.numLayers = (int)T->layers.size();
   for(int i = 0; i < P.numLayers; i++) P.layers[i] = T->layers[i];
   P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride;
@@ -1190,7 +1231,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 5 : 2;
   if(T->cfg == 0 && usePair) {
     // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
-    P.wstream = T->d_wPair;
+    P.wstream = T->d_wPair[P.opFmt];
     const int numUnits = nDev ? h->ctx->smCount / 2 : (P.numItems + 1) / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(numUnits, h->ctx->smCount / 2)); cfg.blockDim = dim3(Cfg128P::THREADS);

@@ -550,6 +550,7 @@ int kc_handle_destroy(kc_handle* h) {
 }
 
 int kc_handle_uses_bf16(const kc_handle* h) { return h && h->bf16 ? 1 : 0; }
+int kc_handle_operand_format(const kc_handle* h) { return !h || !h->bf16 ? 2 : (h->flags & KC_FLAG_OPERANDS_BF16) ? 1 : 0; }
 int64_t kc_handle_launch_count(const kc_handle* h) { return h ? h->launches : 0; }
 int kc_handle_trunk_time(kc_handle* h, float* sumMs, int* count) {
   KC_CHECK(h && sumMs && count, "kc_handle_trunk_time: null argument");

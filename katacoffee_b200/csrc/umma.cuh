@@ -79,6 +79,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lboBytes, 
   d |= (uint64_t)1 << 46;   // descriptor version for sm_100
   return d;                 // base offset 0, swizzle none
 }
+// kind::f16 with fp32 accumulation; aFmt / bFmt: 0 = fp16, 1 = bf16 (the two operands choose independently, same MMA rate)
+__host__ __device__ __forceinline__ uint32_t idesc_f16kind_f32(int M, int N, uint32_t aFmt, uint32_t bFmt) {
+  return (1u << 4) | (aFmt << 7) | (bFmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ __forceinline__ uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

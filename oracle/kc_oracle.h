@@ -191,11 +191,17 @@ void ko_model_destroy(ko_model* m);
  * mode 0 = direct fp32 convolution (the checker), 1 = Winograd F(4x4,3x3) + GEMM as the Eigen
  * backend does (eigenbackend.cpp:417-667; used for the CPU baseline), 2 = mode 0 with every
  * tensor-core convolution's weights and input activations rounded to bf16 (precision model of the
- * tcgen05 path: separates rounding from kernel bugs in the parity tests). */
+ * tcgen05 path: separates rounding from kernel bugs in the parity tests).  KO_MODE_EMUL(a, w) selects
+ * the operand formats of that emulation: activations a, weights w; 0 bf16, 1 fp16, 2 fp32 (exact). */
+#define KO_MODE_EMUL(a, w) (2 | ((a) << 4) | ((w) << 6))
 void ko_model_forward(const ko_model* m, int n, int nnXLen, int nnYLen, int inputsNHWC,
                       const float* rowSpatial, const float* rowGlobal, const int8_t* symmetry,
                       float* policy, float* value, float* misc, float* ownership, int mode,
                       int threads);
+/* Diagnostic: one un-chunked forward (NCHW rows, no symmetry) that also copies the trunk after the initial conv, after
+ * every block and after trunkTipBN into trace [numBlocks + 2][n][H*W][trunkC] (NHWC). */
+void ko_model_forward_trace(const ko_model* m, int n, int nnXLen, int nnYLen, const float* rowSpatial, const float* rowGlobal,
+                            float* policy, float* value, float* misc, float* ownership, int mode, float* trace);
 /* Layer-level hooks = NeuralNet::testEvaluate* (nninterface.h:127-169); buffers NHWC or NCHW. */
 void ko_test_conv(const ko_conv_desc* d, int n, int xLen, int yLen, int useNHWC, const float* in,
                   float* out, int mode);

@@ -87,6 +87,7 @@ def lib():
         l.ko_model_create.argtypes = [vp]
         l.ko_model_destroy.argtypes = [vp]
         l.ko_model_forward.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        l.ko_model_forward_trace.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp]
         l.ko_test_conv.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
         l.ko_test_batchnorm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         l.ko_test_resblock.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int]
@@ -255,6 +256,26 @@ class Model:
         own = np.zeros((n, hw), np.float32)
         lib().ko_model_forward(self._m, n, x, y, int(nhwc), _p(rs), _p(rg), _p(sym), _p(policy), _p(value), _p(misc), _p(own), mode, threads)
         return policy, value, misc, own
+
+
+def mode_emul(act_fmt, w_fmt):
+    """Operand formats of the reduced-precision emulation (KO_MODE_EMUL): 'bf16', 'fp16' or 'fp32' for activations / weights."""
+    f = {"bf16": 0, "fp16": 1, "fp32": 2}
+    return 2 | (f[act_fmt] << 4) | (f[w_fmt] << 6)
+
+
+def forward_trace(om, rowSpatial, rowGlobal, x, y, mode=0):
+    """(policy, value, misc, own, trace) with trace [numBlocks + 2][n][hw][trunkC]: the trunk after the initial conv, each block, the tip."""
+    n, hw = rowSpatial.shape[0], x * y
+    rs = np.ascontiguousarray(rowSpatial, np.float32)
+    rg = np.ascontiguousarray(rowGlobal, np.float32)
+    policy = np.zeros((n, 4 * hw), np.float32)
+    value = np.zeros((n, 2), np.float32)
+    misc = np.zeros((n, 2), np.float32)
+    own = np.zeros((n, hw), np.float32)
+    trace = np.zeros((om.model.num_blocks + 2, n, hw, om.model.trunk), np.float32)
+    lib().ko_model_forward_trace(om._m, n, x, y, _p(rs), _p(rg), _p(policy), _p(value), _p(misc), _p(own), mode, _p(trace))
+    return policy, value, misc, own, trace
 
 
 def test_conv(desc_struct, n, xlen, ylen, nhwc, inp, out_channels, mode=0):

@@ -282,19 +282,27 @@ inline float bf16r(float x) {
   return x;
 }
 
-// mode 2 = "bf16 emulation": the same arithmetic as mode 0 with the convolution's weights and input
-// activations rounded to bf16 first (products are then exact in fp32, accumulation stays fp32) --
-// the precision model of the tcgen05 path, used to tell rounding apart from kernel bugs.
-void convApplyBf16(const Conv& cv, int n, int H, int W, const float* in, float* out, bool accumulate) {
+// Reduced-precision emulation ("mode & 15 == 2"): the same arithmetic as mode 0 with the convolution's weights and
+// input activations rounded to the tensor-core operand formats first (products are then exact in fp32, accumulation
+// stays fp32) -- the precision model of the tcgen05 path, used to tell rounding apart from kernel bugs.
+// Operand formats ride in the mode word: bits 4-5 = activations, bits 6-7 = weights; 0 bf16, 1 fp16, 2 fp32 (not rounded).
+// So mode 2 = bf16 x bf16, KO_MODE_EMUL(1, 1) = 2 | 16 | 64 = fp16 x fp16 (tcgen05 kind::f16 takes either format at one rate).
+inline float f16r(float x) {
+  if(!(std::fabs(x) <= 65504.0f)) return x > 0 ? 65504.0f : x < 0 ? -65504.0f : x;   // cvt.rn.satfinite
+  return (float)(_Float16)x;
+}
+inline float roundFmt(float x, int fmt) { return fmt == 0 ? bf16r(x) : fmt == 1 ? f16r(x) : x; }
+void convApplyEmul(const Conv& cv, int n, int H, int W, const float* in, float* out, bool accumulate, int mode) {
+  const int aFmt = (mode >> 4) & 3, wFmt = (mode >> 6) & 3;
   Conv q = cv;
-  for(float& v : q.wTap) v = bf16r(v);
+  for(float& v : q.wTap) v = roundFmt(v, wFmt);
   std::vector<float> a((size_t)n * H * W * cv.ic);
-  for(size_t i = 0; i < a.size(); i++) a[i] = bf16r(in[i]);
+  for(size_t i = 0; i < a.size(); i++) a[i] = roundFmt(in[i], aFmt);
   convDirect(q, n, H, W, a.data(), out, accumulate);
 }
 
 void convApply(const Conv& cv, int n, int H, int W, const float* in, float* out, bool accumulate, int mode) {
-  if(mode == 2) convApplyBf16(cv, n, H, W, in, out, accumulate);
+  if((mode & 15) == 2) convApplyEmul(cv, n, H, W, in, out, accumulate, mode);
   else if(mode == 1 && cv.ky == 3 && cv.kx == 3) convWinograd3x3(cv, n, H, W, in, out, accumulate);
   else if(mode == 1 && cv.ky == 1 && cv.kx == 1) conv1x1Gemm(cv, n, H, W, in, out, accumulate);
   else convDirect(cv, n, H, W, in, out, accumulate);
@@ -382,7 +390,7 @@ struct ko_model {
 
   void forwardChunk(int n, int H, int W, int inputsNHWC, const float* rowSpatial, const float* rowGlobal,
                     const int8_t* symmetry, float* policy, float* value, float* misc, float* ownership,
-                    int mode) const {
+                    int mode, float* trace = nullptr) const {
     const int hw = H * W, C = numInputChannels;
     // eigenbackend.cpp:1696-1704: per row, copy global and copyInputsWithSymmetry into the NHWC batch
     std::vector<float> in((size_t)n * hw * C);
@@ -407,16 +415,23 @@ struct ko_model {
     // trunk (eigenbackend.cpp:1202-1226)
     std::vector<float> trunk((size_t)n * hw * trunkC), gb((size_t)n * trunkC);
     convApply(initialConv, n, H, W, in.data(), trunk.data(), false, mode);
-    if(mode == 2) {   // the tensor-core path folds this matmul into the initial conv as a 16th bf16 input channel
+    if((mode & 15) == 2) {   // the tensor-core path folds this matmul into the initial conv as a 16th reduced-precision input channel
       MatMul q = initialMatMul;
-      for(float& v : q.w) v = bf16r(v);
+      for(float& v : q.w) v = roundFmt(v, (mode >> 6) & 3);
       for(int b = 0; b < n; b++) q.apply(rowGlobal + (size_t)b * numInputGlobalChannels, &gb[(size_t)b * trunkC]);
     } else
     for(int b = 0; b < n; b++) initialMatMul.apply(rowGlobal + (size_t)b * numInputGlobalChannels, &gb[(size_t)b * trunkC]);
     addNCBias(n, hw, trunkC, trunk.data(), gb.data());
-    for(const Block& blk : blocks) blk.apply(n, H, W, trunk.data(), mask.data(), maskSum.data(), mode);
+    // trace (diagnostic): the trunk after the initial conv, after every block, and the tip, [numBlocks + 2][n][hw][trunkC]
+    const size_t tsz = trunk.size();
+    if(trace) std::copy(trunk.begin(), trunk.end(), trace);
+    for(size_t bi = 0; bi < blocks.size(); bi++) {
+      blocks[bi].apply(n, H, W, trunk.data(), mask.data(), maskSum.data(), mode);
+      if(trace) std::copy(trunk.begin(), trunk.end(), trace + (bi + 1) * tsz);
+    }
     std::vector<float> tip((size_t)n * hw * trunkC);
     bnApply(trunkTipBN, trunkTipAct, n, hw, trunk.data(), mask.data(), tip.data());
+    if(trace) std::copy(tip.begin(), tip.end(), trace + (blocks.size() + 1) * tsz);
     // policy head (eigenbackend.cpp:1265-1298), no pass output (ledger H)
     {
       int pc = p1Conv.oc, gc = g1Conv.oc;
@@ -429,7 +444,7 @@ struct ko_model {
       for(int b = 0; b < n; b++) gpoolToBiasMul.apply(&cat[(size_t)b * 3 * gc], &bias[(size_t)b * pc]);
       addNCBias(n, hw, pc, p1.data(), bias.data());
       bnApply(p1BN, p1Act, n, hw, p1.data(), mask.data(), p12.data());
-      convApply(p2Conv, n, H, W, p12.data(), pol.data(), false, mode == 2 ? 0 : mode);   // fp32 on CUDA cores in the bf16 path
+      convApply(p2Conv, n, H, W, p12.data(), pol.data(), false, (mode & 15) == 2 ? 0 : mode);   // fp32 on CUDA cores in the tensor-core path
       // NHWC [hw][4] -> NNPos order dir*HW + y*W + x, inverse spatial symmetry per direction channel
       // (eigenbackend.cpp:1776: copyOutputsWithSymmetry; ledger H, K parity mode)
       int D = p2Conv.oc;
@@ -461,7 +476,7 @@ struct ko_model {
       }
       if(ownership) {
         std::vector<float> own((size_t)n * hw);
-        convApply(vOwnershipConv, n, H, W, v12.data(), own.data(), false, mode == 2 ? 0 : mode);
+        convApply(vOwnershipConv, n, H, W, v12.data(), own.data(), false, (mode & 15) == 2 ? 0 : mode);
         for(int b = 0; b < n; b++)
           ko_copy_outputs_with_symmetry(&own[(size_t)b * hw], ownership + (size_t)b * hw, 1, H, W,
                                         symmetry ? symmetry[b] : 0);
@@ -520,6 +535,11 @@ void ko_model_forward(const ko_model* m, int n, int nnXLen, int nnYLen, int inpu
   std::vector<std::thread> th;
   for(int t = 0; t < threads; t++) th.emplace_back(work, t);
   for(auto& t : th) t.join();
+}
+
+void ko_model_forward_trace(const ko_model* m, int n, int nnXLen, int nnYLen, const float* rowSpatial, const float* rowGlobal,
+                            float* policy, float* value, float* misc, float* ownership, int mode, float* trace) {
+  m->forwardChunk(n, nnYLen, nnXLen, 0, rowSpatial, rowGlobal, nullptr, policy, value, misc, ownership, mode, trace);
 }
 
 static void toNHWC(const float* in, float* out, int n, int c, int hw) {

@@ -148,8 +148,14 @@ def test_position_hash_and_cache_key(oracle, built_lib):
     h1, k1 = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"])
     h2, k2 = backend.evalPositionHash(W, H, p["stones"], p["nextPla"], m2, p["numTurns"])
     assert h1 == h2 and k1 != k2
-    # numTurns is in neither (the planes do not read it)
-    assert backend.evalPositionHash(W, H, p["stones"], p["nextPla"], p["moves"], p["numTurns"] + 2) == (h1, k1)
+    # numTurns: never in the literal hash; in the cache key as min(numTurns, 5), because the history planes 7..10 are gated on
+    # numTurns >= 2..5 (nninputs.cpp:575-620) -- equal moves with numTurns 1 and 5 are different inputs
+    q = next(q for q in ps if q["numTurns"] >= 5)
+    hq, kq = backend.evalPositionHash(W, H, q["stones"], q["nextPla"], q["moves"], q["numTurns"])
+    assert backend.evalPositionHash(W, H, q["stones"], q["nextPla"], q["moves"], q["numTurns"] + 2) == (hq, kq)
+    for nt in (1, 2, 3, 4):
+        hn, kn = backend.evalPositionHash(W, H, q["stones"], q["nextPla"], q["moves"], nt)
+        assert hn == hq and kn != kq, nt
     # pinned to the values SURVEY.md 8(c) derived with the reference's own md5.cpp / sha2.cpp: the empty boards' hashes are
     # SIZE_X[n] ^ SIZE_Y[n] ^ ZOBRIST_PLAYER_HASH[pla]
     PLAYER = {1: (0xc535f97fd0cc7e76, 0x8a2a2a2ff24dbb6d), 2: (0x392045e5c8d9bd73, 0xd3c1c132e034dcb0)}
@@ -162,6 +168,25 @@ def test_position_hash_and_cache_key(oracle, built_lib):
     # round trip of the packing
     st, pla, mv, nt, ld = backend.evalUnpackPosition(W, H, 0b100001, 0b10, (3 | (1 << 6)) | (2 << 40) | (9 << 48) | ((2 << 3) << 56))
     assert st[0] == 1 and st[5 - 0] == 0 and st[1] == 2 and pla == 2 and nt == 9 and ld == 2 and tuple(mv[4]) == (3, 1) and mv[3][1] == 0
+
+
+def test_cache_separates_equal_moves_with_different_num_turns(oracle, built_lib, omodel):
+    """Two requests with the same stones, player and last five moves but numTurns 1 and 5 have different V1 planes (history planes
+    7..10 need numTurns >= 2..5): each must get its own evaluation, also when the other one is already in the cache."""
+    from katacoffee_b200 import backend
+    p = next(q for q in make_positions(oracle, 40, seed=11, min_plies=6) if q["numTurns"] >= 5)
+    be = OracleBackend(oracle, omodel)
+    ev = backend.NNEvaluator(nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=8, maxConcurrentEvals=16, numThreads=1,
+                             nnCacheSizePowerOfTwo=10, customBackend=be)
+    outs = {}
+    for nt in (p["numTurns"], 1, p["numTurns"], 1):
+        r = ev.evaluate(p["stones"], p["nextPla"], p["moves"], nt, symmetry=0)
+        e = expected_output(oracle, omodel, dict(p, numTurns=nt), 0)
+        check_result(r, e)
+        outs.setdefault(nt, []).append(r)
+    assert not outs[1][0]["cacheHit"] and outs[1][1]["cacheHit"] and outs[p["numTurns"]][1]["cacheHit"]
+    assert np.abs(outs[1][0]["policyProbs"] - outs[p["numTurns"]][0]["policyProbs"]).max() > 1e-6   # the inputs really differ
+    ev.close()
 
 
 @pytest.mark.timeout(300)

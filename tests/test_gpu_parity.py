@@ -10,7 +10,8 @@ from conftest import golden
 pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 1e-4
-TOL_BF16 = 1e-2
+TOL_TC = 1e-2      # north-star bar of the tensor-core path on raw logits (fp16 operands)
+TOL_BF16 = TOL_TC
 
 
 def bf16_bits(a):
@@ -268,21 +269,30 @@ def postprocessed(oracle, outs, recs_sel, HW):
     return np.array(pols), np.array(vals)
 
 
-def check_bf16_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym, strict):
-    """The bf16 bars for deep nets (DESIGN.md 'precision'; shallow nets are compared pointwise in
-    test_bf16_shallow_pointwise):
-    T1 the error against the fp32 oracle is no larger than the bf16-emulating oracle's (mode 2: same
-       arithmetic, operands rounded to bf16) -- statistically, because after a few layers two bf16
+def emu_mode(oracle, fmt):
+    """The oracle's operand-rounding emulation (KO_MODE_EMUL) of the tensor path's operand format `fmt` ('f16' default, 'bf16')."""
+    return oracle.mode_emul("fp16", "fp16") if fmt == "f16" else 2
+
+
+def check_tensor_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym, fmt, calibrate):
+    """The bars of the tensor-core path against the fp32 oracle (DESIGN.md 'precision'; shallow nets are compared pointwise in
+    test_tensor_shallow_pointwise).  `fmt` is the operand format of the handle: 'f16' (default) or 'bf16' (KC_FLAG_OPERANDS_BF16).
+    T1 the error against the fp32 oracle is no larger than that of the oracle's emulation of the same operand format (same
+       arithmetic, operands rounded, fp32 accumulation) -- statistically, because after a few layers two reduced-precision
        evaluations with different fp32 summation orders round different activations;
-    T2 (strict: the north-star config, b10c128 with the default init) vs the fp32 oracle on what
-       NNOutput hands to search: value/misc logits and post-processed policy / win-loss probabilities
-       within 1e-2 absolute, raw policy/ownership logits within the reference's own reduced-precision
-       tolerance 0.03*max(|x|,|y|,3) (testnn.cpp:8-15);
-    T3 (every other net / init, incl. the trained-like 'full' calibration where mean subtraction
-       amplifies rounding) the reference's own acceptance thresholds for a reduced-precision backend
-       (testnnevalcanary.cpp:417-418: winrate max <= 5 %, policy max <= 6 %, 99th pct <= 2 % / 2.5 %)."""
+    T2 the reference's acceptance statistics for a reduced-precision backend (testnnevalcanary.cpp:417-418): policy KL 99th
+       percentile <= 0.002 / max <= 0.004, win rate max <= 5 % / 99 % <= 2 %, top policy max <= 6 % / 99 % <= 2.5 %;
+    T3 THE NORTH-STAR BAR, fp16 operands, every net, default ('rms') and uncalibrated init: max |x - ref| < 1e-2 on every raw
+       output the backend hands over (nninterface.h:112-117) -- policy logits, ownership logits, value and misc logits -- and
+       on the post-processed policy / win-loss probabilities;
+    T4 explicitly looser, and only here:
+       * fp16 operands on the 'full' calibration (BN means set like a trained net's: the mean subtraction amplifies operand
+         rounding; the emulation itself is at 1.4-1.7e-2 there): raw logits < 2.5e-2, value / misc and probabilities < 1e-2;
+       * bf16 operands (the emulation itself is at 2-4e-2 on raw logits): value / misc logits and probabilities < 1e-2 and raw
+         policy / ownership logits within the reference's reduced-precision tolerance 0.03*max(|x|,|y|,3) (testnn.cpp:8-15) on
+         the 'rms' / uncalibrated nets; T1 + T2 only on 'full'."""
     HW = W * H
-    emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
+    emu = om.forward(planes, glob, W, H, symmetry=sym, mode=emu_mode(oracle, fmt), threads=8)
     ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
     for a, b, r in zip(got, emu, ref):
         rms_got, rms_emu = np.sqrt(np.mean((a - r) ** 2)), np.sqrt(np.mean((b - r) ** 2))
@@ -290,37 +300,42 @@ def check_bf16_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, sym
         assert np.abs(a - r).max() <= 2.5 * np.abs(b - r).max() + 1e-3, ("T1 max", np.abs(a - r).max(), np.abs(b - r).max())
     gp, gv = postprocessed(oracle, got, recs_sel, HW)
     rp, rv = postprocessed(oracle, ref, recs_sel, HW)
-    # policy KL(fp32 || bf16) over the legal moves: the reference's third acceptance statistic (testnnevalcanary.cpp:417-418:
-    # 99th percentile <= 0.002, max <= 0.004)
     m = rp > 0
     kl = np.where(m, rp * (np.log(np.where(m, rp, 1.0)) - np.log(np.where(m, np.maximum(gp, 1e-30), 1.0))), 0.0).sum(1)
-    assert kl.max() <= 0.004 and np.percentile(kl, 99) <= 0.002, ("policy KL", kl.max(), np.percentile(kl, 99))
-    if not strict:
-        dp, dv = np.abs(gp - rp).max(1), np.abs(gv - rv).max(1)
-        assert dv.max() <= 0.05 and np.percentile(dv, 99) <= 0.02, ("T3 winrate", dv.max())
-        assert dp.max() <= 0.06 and np.percentile(dp, 99) <= 0.025, ("T3 policy", dp.max())
-        return
-    assert np.abs(got[1] - ref[1]).max() < TOL_BF16 and np.abs(got[2] - ref[2]).max() < TOL_BF16, "T2 value/misc logits"
-    assert np.abs(gp - rp).max() < TOL_BF16 and np.abs(gv - rv).max() < TOL_BF16, ("T2 post-processed", np.abs(gp - rp).max())
-    for a, b in ((got[0], ref[0]), (got[3], ref[3])):
-        tol = 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)
-        assert (np.abs(a - b) < tol).all(), ("T2 raw logits", np.abs(a - b).max())
+    assert kl.max() <= 0.004 and np.percentile(kl, 99) <= 0.002, ("T2 policy KL", kl.max(), np.percentile(kl, 99))
+    dp, dv = np.abs(gp - rp).max(1), np.abs(gv - rv).max(1)
+    assert dv.max() <= 0.05 and np.percentile(dv, 99) <= 0.02, ("T2 winrate", dv.max())
+    assert dp.max() <= 0.06 and np.percentile(dp, 99) <= 0.025, ("T2 policy", dp.max())
+    raw = {k: float(np.abs(a - r).max()) for k, a, r in zip(("policy", "value", "misc", "ownership"), got, ref)}
+    if fmt == "f16" and calibrate != "full":
+        assert max(raw.values()) < TOL_TC, ("T3 raw logits", raw)
+        assert np.abs(gp - rp).max() < TOL_TC and np.abs(gv - rv).max() < TOL_TC, ("T3 post-processed", np.abs(gp - rp).max())
+    elif fmt == "f16":
+        assert raw["policy"] < 2.5e-2 and raw["ownership"] < 2.5e-2 and raw["value"] < TOL_TC and raw["misc"] < TOL_TC, ("T4 f16 / full", raw)
+        assert np.abs(gp - rp).max() < TOL_TC and np.abs(gv - rv).max() < TOL_TC, ("T4 post-processed", np.abs(gp - rp).max())
+    elif calibrate != "full":
+        assert raw["value"] < TOL_TC and raw["misc"] < TOL_TC, ("T4 bf16 value/misc", raw)
+        for a, b in ((got[0], ref[0]), (got[3], ref[3])):
+            assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), ("T4 bf16 raw logits", raw)
+    return raw
 
 
 @pytest.mark.parametrize("net,W,H,n,calibrate", [("b2c32", 5, 5, 37, "rms"), ("b6c96", 5, 5, 200, "rms"), ("b10c128", 5, 5, 300, "rms"),
                                                  ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none"),
                                                  ("b15c192", 6, 6, 61, "rms"), ("b15c192", 5, 5, 45, "rms")])
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "f16", "bf16"])
 def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
-    """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward."""
+    """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward: the fp32 check path, the
+    tensor-core path with its default fp16 operands, and with bf16 operands (KC_FLAG_OPERANDS_BF16)."""
     from katacoffee_b200 import backend, modeldesc
     model = modeldesc.Model(net, seed=5, calibrate=calibrate)
     om = oracle.Model(model)
     planes, glob, rsel = position_batch_full(oracle, W, H, 4, 3, n)
     sym = (np.arange(n) % 8).astype(np.int8)
     lm = backend.LoadedModel(ctx, model)
-    h = backend.createComputeHandle(ctx, lm, maxBatchSize=max(n, 64), nnXLen=W, nnYLen=H, useFP32Check=(mode == "fp32"))
-    assert h.isUsingBF16() == (mode == "bf16")
+    h = backend.createComputeHandle(ctx, lm, maxBatchSize=max(n, 64), nnXLen=W, nnYLen=H, useFP32Check=(mode == "fp32"), operandsBF16=(mode == "bf16"))
+    assert h.isUsingBF16() == (mode != "fp32")
+    assert h.operandFormat() == {"fp32": "fp32", "f16": "fp16", "bf16": "bf16"}[mode]
     got = backend.getOutput(h, planes, glob, sym)
     ep = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
     assert np.abs(ep[0]).max() > 0.05 and np.abs(ep[1]).max() > 0.01     # the comparison is not vacuous
@@ -328,14 +343,19 @@ def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
         errs = [np.abs(a - b).max() for a, b in zip(got, ep)]
         assert max(errs) < TOL_FP32, errs
     else:
-        # per-row symmetry: raw outputs against the fp32 oracle with the reference's reduced-precision tolerance
+        # per-row symmetry: raw outputs against the fp32 oracle
         for a, b in zip(got, ep):
-            assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all() or calibrate == "full"
+            if mode == "f16" and calibrate != "full":
+                assert np.abs(a - b).max() < TOL_TC, np.abs(a - b).max()                  # the north-star bar
+            elif mode == "f16":
+                assert np.abs(a - b).max() < 2.5e-2, np.abs(a - b).max()                  # 'full' calibration, see check_tensor_against_oracle T4
+            elif calibrate != "full":                                                     # bf16 operands: the reference's reduced-precision tolerance
+                assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), np.abs(a - b).max()
         # symmetry is applied to planes, not to legality: the post-processed bars are checked without symmetry
         got0 = backend.getOutput(h, planes, glob, None)
-        check_bf16_against_oracle(oracle, om, got0, planes, glob, rsel, W, H, None, strict=(net == "b10c128" and calibrate == "rms"))
+        check_tensor_against_oracle(oracle, om, got0, planes, glob, rsel, W, H, None, mode, calibrate)
     # NHWC rows, no symmetry
-    h2 = backend.createComputeHandle(ctx, lm, max(n, 64), W, H, useFP32Check=(mode == "fp32"), inputsUseNHWC=True)
+    h2 = backend.createComputeHandle(ctx, lm, max(n, 64), W, H, useFP32Check=(mode == "fp32"), inputsUseNHWC=True, operandsBF16=(mode == "bf16"))
     nhwc = planes.reshape(n, 15, W * H).transpose(0, 2, 1).reshape(n, -1)
     got2 = backend.getOutput(h2, nhwc, glob, None)
     if mode == "fp32":
@@ -348,7 +368,7 @@ def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
         x.close()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
 def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
     """kc_games_eval: planes generated on the device straight into the net input (no PCIe), with symmetry."""
     from katacoffee_b200 import backend, modeldesc
@@ -372,16 +392,17 @@ def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
         via_host = backend.getOutput(h, planes, glob, sym)
         assert all((a == b).all() for a, b in zip(got, via_host))
         ref = om.forward(planes, glob, W, H, symmetry=sym, mode=0, threads=8)
-        assert np.abs(got[1] - ref[1]).max() < TOL_BF16 and np.abs(got[2] - ref[2]).max() < TOL_BF16
+        assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_TC
     for x in (games, h, lm):
         x.close()
 
 
 @pytest.mark.parametrize("net", ["b0c32", "b1c32", "b1c32g", "b1c192g"])
 @pytest.mark.parametrize("W,H", [(5, 5), (6, 6)])
-def test_bf16_shallow_pointwise(ctx, oracle, net, W, H):
-    """Kernel exactness: on nets of depth 0-1 the tcgen05 path equals the bf16-emulating oracle
-    (mode 2: identical arithmetic with operands rounded to bf16, fp32 accumulation) pointwise."""
+@pytest.mark.parametrize("fmt", ["f16", "bf16"])
+def test_tensor_shallow_pointwise(ctx, oracle, net, W, H, fmt):
+    """Kernel exactness: on nets of depth 0-1 the tcgen05 path equals the oracle's emulation of its operand format
+    (identical arithmetic with operands rounded to fp16 / bf16, fp32 accumulation) pointwise."""
     from katacoffee_b200 import backend, modeldesc
     n = 200
     model = modeldesc.Model(net, seed=13)
@@ -389,17 +410,18 @@ def test_bf16_shallow_pointwise(ctx, oracle, net, W, H):
     planes, glob, _ = position_batch_full(oracle, W, H, 4, 5, n)
     sym = (np.arange(n) % 8).astype(np.int8)
     lm = backend.LoadedModel(ctx, model)
-    h = backend.createComputeHandle(ctx, lm, n, W, H)
+    h = backend.createComputeHandle(ctx, lm, n, W, H, operandsBF16=(fmt == "bf16"))
     got = backend.getOutput(h, planes, glob, sym)
-    emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
+    emu = om.forward(planes, glob, W, H, symmetry=sym, mode=emu_mode(oracle, fmt), threads=8)
     # depth 0: nothing has been rounded twice -> tight; depth 1: a handful of activations sit within
-    # fp32 summation noise of a bf16 rounding boundary and land one ulp apart (each worth <= ~5e-3 on a
-    # logit), so the bound is one such flip and the bulk must still agree to 1e-3
-    tol = 2e-3 if net == "b0c32" else 1e-2
+    # fp32 summation noise of a rounding boundary and land one ulp apart (each worth <= ~5e-3 on a
+    # logit with bf16, 1/8 of that with fp16), so the bound is one such flip and the bulk must still agree
+    ulp = 1.0 if fmt == "bf16" else 0.125
+    tol = (2e-3 if net == "b0c32" else 1e-2) * ulp + 2e-4
     errs = [np.abs(a - b).max() for a, b in zip(got, emu)]
     assert max(errs) < tol, errs
-    for a, b in zip(got, emu):
-        assert (np.abs(a - b) > 1e-3).mean() < 0.05
+    for a, b in zip(got, emu):   # (fp32 summation-order noise of a 9 x 192-term sum is ~1e-4 by itself)
+        assert (np.abs(a - b) > (1e-3 if fmt == "bf16" else 5e-4)).mean() < 0.05
     assert np.abs(emu[0]).max() > 0.1
     h.close(); lm.close()
 
@@ -517,8 +539,7 @@ def test_bf16_full_batch_and_odd_sizes(ctx, oracle):
         p, v, m, o = backend.getOutput(h, planes[:n], glob[:n], None)
         # a row's result does not depend on which tile / CTA / wave it lands in
         assert (p == full[0][:n]).all() and (v == full[1][:n]).all() and (m == full[2][:n]).all() and (o == full[3][:n]).all(), n
-        assert max(np.abs(v - ev[:n]).max(), np.abs(m - em[:n]).max()) < TOL_BF16, n
-        assert (np.abs(p - ep[:n]) < 0.03 * np.maximum(np.maximum(np.abs(p), np.abs(ep[:n])), 3.0)).all(), n
+        assert max(np.abs(v - ev[:n]).max(), np.abs(m - em[:n]).max(), np.abs(p - ep[:n]).max(), np.abs(o - eo[:n]).max()) < TOL_TC, n
     h.close(); lm.close()
 
 
@@ -619,9 +640,7 @@ def test_b15c192_6x6_device_resident_and_unsupported_width_rejected(ctx, oracle)
     games.eval(h)
     got = h.readOutputs(G)
     ref = om.forward(planes, glob, W, H, mode=0, threads=8)
-    for a, b in zip(got, ref):
-        assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), np.abs(a - b).max()
-    assert np.abs(got[1] - ref[1]).max() < 2e-2
+    assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_TC   # the north-star bar on every raw output (fp16 operands)
     games.close(); h.close(); lm.close()
     wide = modeldesc.Model("b2c256", seed=2)
     lm2 = backend.LoadedModel(ctx, wide)
@@ -1242,11 +1261,10 @@ def test_mish_activation_both_paths(ctx, oracle, net, W, H, n):
     hb = backend.createComputeHandle(ctx, lm, n, W, H)
     assert hb.isUsingBF16()
     gb = backend.getOutput(hb, planes, glob, sym)
-    for a, b in zip(gb, ref):
-        assert (np.abs(a - b) < 0.03 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 3.0)).all(), np.abs(a - b).max()
-    if net == "b1c32g":      # shallow: pointwise against the bf16-emulating oracle
-        emu = om.forward(planes, glob, W, H, symmetry=sym, mode=2, threads=8)
-        assert max(np.abs(a - b).max() for a, b in zip(gb, emu)) < 1e-2
+    assert max(np.abs(a - b).max() for a, b in zip(gb, ref)) < TOL_TC        # fp16 operands: the north-star bar on raw logits
+    if net == "b1c32g":      # shallow: pointwise against the fp16-emulating oracle
+        emu = om.forward(planes, glob, W, H, symmetry=sym, mode=emu_mode(oracle, "f16"), threads=8)
+        assert max(np.abs(a - b).max() for a, b in zip(gb, emu)) < 2e-3
     relu = backend.getOutput(backend.createComputeHandle(ctx, backend.LoadedModel(ctx, modeldesc.Model(net, seed=8)), n, W, H), planes, glob, sym)
     assert np.abs(relu[0] - gb[0]).max() > 1e-2        # the activation really differs from the ReLU net's
     for x in (hf, hb, lm):

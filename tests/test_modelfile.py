@@ -109,10 +109,18 @@ def test_modelfile_ambiguous_gz_and_errors(tmp_path):
         backend.ModelFile(variant("p.txt", lambda l: l.__setitem__(i + 1, "1 1 32 2 1 1")))
     with pytest.raises(capi.KCError, match="Nan or infinite"):
         backend.ModelFile(variant("nan.txt", lambda l: l.__setitem__(l.index("conv1") + 2, "nan " + l[l.index("conv1") + 2].split(" ", 1)[1])))
-    # version < 11 style activations (name only) parse as ReLU (desc.cpp:243-256)
-    def strip_kinds(l):
-        l[:] = [x for x in l if not x.startswith("ACTIVATION_")]
-    mf = backend.ModelFile(variant("old.txt", strip_kinds))
+    # hostile headers: dimensions whose product wraps size_t, or that no file could fill, are errors -- not crashes, not allocations
+    ci = lines.index("conv1")
+    for k, dims in enumerate(("3 3 2147483647 2147483647 1 1", "3 3 65536 65536 1 1", "3 3 8192 8192 1 1", "99 99 15 32 1 1")):
+        for suffix in ("txt", "bin"):
+            with pytest.raises(capi.KCError, match="channels|filter size|too short"):
+                backend.ModelFile(variant(f"h{k}.{suffix}", lambda l: l.__setitem__(ci + 1, dims)))
+    # the writer emits ReLU activation layers as their name alone, which is the reference's version-1 format (desc.cpp:243-256)
+    assert not any(x.startswith("ACTIVATION_") for x in lines)
+    # ... and a file that does spell the kind out parses the same
+    def add_kinds(l):
+        l[:] = [y for x in l for y in ((x, "ACTIVATION_RELU") if x.endswith("/actv") or "/actv" in x else (x,))]
+    mf = backend.ModelFile(variant("kinds.txt", add_kinds))
     assert mf.desc.trunkTipActivation == 1 and mf.desc.blocks[0].preActivation == 1
     mf.close()
     with pytest.raises(capi.KCError, match="at least one block"):

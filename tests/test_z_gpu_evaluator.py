@@ -89,7 +89,7 @@ def test_device_evaluator_matches_direct_path_and_oracle(ctx, oracle, mode):
             bar = 1e-4 if mode == "fp32" else 1e-2
             worst = max(worst, np.abs(r["policyProbs"] - e["policy"]).max(), abs(r["whiteWinProb"] - e["winLoss"][0]))
             assert np.abs(r["policyProbs"] - e["policy"]).max() < bar and abs(r["whiteWinProb"] - e["winLoss"][0]) < bar
-            assert np.abs(r["whiteOwnerMap"] - e["owner"]).max() < (1e-4 if mode == "fp32" else 3e-2)
+            assert np.abs(r["whiteOwnerMap"] - e["owner"]).max() < (1e-4 if mode == "fp32" else 1e-2)
     st = ev.stats()
     assert st["rowsProcessed"] == N and st["cacheMisses"] == N and st["batchesProcessed"] >= (N + 63) // 64
     # second pass: everything from the cache, identical
