@@ -14,9 +14,18 @@
  *   - conv / batchnorm / residual block / gpool residual block, symmetry copies: PINNED against
  *     the literal vectors of cpp/tests/testnn.cpp and cpp/tests/results/runOutputTests.txt
  *     (tests/golden/, extracted by tests/golden/make_golden.py).
- *   - Coffee rules (isLegal, win/draw), getSitHash values over positions, V1 planes, whole-net
- *     outputs with Coffee head shapes: PARITY UNPINNED (no reference test or runnable reference
- *     exists for them); the restatement below follows the cited lines and is the definition.
+ *   - Coffee rules and hashing over positions -- Board::initHash tables, the Rand stream, isLegal (full masks), playMoveAssumeLegal,
+ *     maxConsecutives / checkGameEnd, BoardHistory::makeBoardMove (numTurns / finished / winner), getSitHash, NNInputs::getHash with
+ *     every fold, fillRowV1 planes 0..10 + global (NCHW / NHWC), the SymmetryHelpers and NNPos::locToPos: PINNED against the
+ *     reference's OWN code -- game/board.cpp, game/boardhistory.cpp, neuralnet/nninputs.cpp, core/hash.cpp, core/rand.cpp compiled
+ *     from a patched scratch copy into oracle/_ref/libkc_ref_rules.so (oracle/ref_patch.sh lists each one-line edit with the
+ *     SURVEY.md 0.2 defect / 8.1 ledger row behind it) -- over > 10^6 playout positions and arbitrary positions on boards from
+ *     2x2 to 10x10 (tests/test_oracle_ref_rules.py).
+ *   - PARITY UNPINNED, because the literal code is unusable there (ledger rows, asserted where it can be shown): the draw rule (C),
+ *     V1 planes 11..14 (F: legal plane indexed by spot over 4 channels past channel 15; G: fillRowWithLine walks orthogonal
+ *     neighbours and wall spots), NNPos::posToLoc (I); and whole-net outputs with Coffee head shapes and the search, for which
+ *     no reference test or runnable reference code exists (eigenbackend.cpp needs Eigen and still carries Go heads).  The
+ *     restatement follows the cited lines under the ledger and is the definition there.
  */
 #ifndef KC_ORACLE_H_
 #define KC_ORACLE_H_
@@ -124,7 +133,7 @@ int ko_playout_choose(const ko_game* g, uint64_t seed, uint64_t gameIdx, uint64_
 typedef struct {
   uint32_t game;       /* game index */
   uint32_t status;     /* ko_game_status */
-  uint32_t legal[7];   /* isLegal mask of the player to move (raw, also when finished); 7x7 needs 196 bits */
+  uint32_t legal[13];  /* isLegal mask of the player to move (raw, also when finished); 10x10 needs 400 bits */
   int32_t  movePos;    /* move that led here, -1 for the initial position */
   uint64_t sitHash[2]; /* getSitHash(next player) */
   uint64_t nnHash[2];  /* NNInputs::getHash with default params */

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkc_oracle.so")
 REF_HASH_PATH = os.path.join(_HERE, "_ref", "libkc_ref_hash.so")
+REF_RULES_PATH = os.path.join(_HERE, "_ref", "libkc_ref_rules.so")
 
 
 def build(force=False):
@@ -22,15 +23,19 @@ def build(force=False):
         subprocess.run(["make", "-C", _HERE, "libkc_oracle.so"], check=True, stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/cpp/core/sha2.cpp") and (force or not os.path.exists(REF_HASH_PATH)):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
+    rules_srcs = [os.path.join(_HERE, f) for f in ("ref_patch.sh", "ref_rules_shim.cpp")]
+    if os.path.exists("/root/reference/cpp/game/board.cpp") and (
+            force or not os.path.exists(REF_RULES_PATH) or os.path.getmtime(REF_RULES_PATH) < max(os.path.getmtime(s) for s in rules_srcs)):
+        subprocess.run(["make", "-C", _HERE, "refrules"], check=True, stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
 class StepRecord(C.Structure):
-    _fields_ = [("game", C.c_uint32), ("status", C.c_uint32), ("legal", C.c_uint32 * 7), ("movePos", C.c_int32),
+    _fields_ = [("game", C.c_uint32), ("status", C.c_uint32), ("legal", C.c_uint32 * 13), ("movePos", C.c_int32),
                 ("sitHash", C.c_uint64 * 2), ("nnHash", C.c_uint64 * 2)]
 
 
-STEP_DTYPE = np.dtype([("game", "<u4"), ("status", "<u4"), ("legal", "<u4", (7,)), ("movePos", "<i4"),
+STEP_DTYPE = np.dtype([("game", "<u4"), ("status", "<u4"), ("legal", "<u4", (13,)), ("movePos", "<i4"),
                        ("sitHash", "<u8", (2,)), ("nnHash", "<u8", (2,))], align=True)
 
 _lib = None
@@ -128,6 +133,67 @@ def ref_hash_lib():
     return l
 
 
+_ref_rules = None
+
+
+def ref_rules_lib():
+    """oracle/_ref/libkc_ref_rules.so: the reference's OWN board / boardhistory / nninputs / hash / rand code (patched scratch copy,
+    oracle/ref_patch.sh) behind the C entry points of oracle/ref_rules_shim.cpp, or None where it has not been built."""
+    global _ref_rules
+    if _ref_rules is None:
+        if not os.path.exists(REF_RULES_PATH):
+            return None
+        l = C.CDLL(REF_RULES_PATH)
+        l.kc_ref_tables.restype = C.c_int
+        l.kc_ref_tables.argtypes = [vp, vp, vp, vp]
+        l.kc_ref_rand.argtypes = [C.c_char_p, C.c_int, vp, vp]
+        l.kc_ref_playout_run.restype = C.c_long
+        l.kc_ref_playout_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, C.c_long, vp, C.c_int, vp]
+        l.kc_ref_position.restype = C.c_int
+        l.kc_ref_position.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        l.kc_ref_nn_hash_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_double, vp]
+        l.kc_ref_copy_inputs_with_symmetry.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.kc_ref_copy_outputs_with_symmetry.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.kc_ref_sym_xy.argtypes = [C.c_int] * 5 + [vp, vp]
+        l.kc_ref_pos_to_loc.argtypes = [C.c_int] * 5 + [vp, vp, vp]
+        l.kc_ref_init()
+        _ref_rules = l
+    return _ref_rules
+
+
+def ref_playout_run(x, y, k, seed, g0, n, max_plies=255, planes=True, nhwc=False, max_records=None):
+    """The same synthetic playouts as playout_run, played on the reference's own Board / BoardHistory; planes are the literal
+    fillRowV1 rows [records][16*H*W] (channels 0..10 meaningful, see oracle/ref_rules_shim.cpp)."""
+    l = ref_rules_lib()
+    cap = max_records if max_records is not None else n * (x * y + 2)
+    recs = np.zeros(cap, STEP_DTYPE)
+    pl = np.zeros((cap, 16 * x * y), np.float32) if planes else None
+    gl = np.zeros(cap, np.float32) if planes else None
+    got = l.kc_ref_playout_run(x, y, k, seed, g0, n, max_plies, _p(recs), cap, _p(pl), int(nhwc), _p(gl))
+    assert got >= 0
+    return recs[:got], (pl[:got] if planes else None), (gl[:got] if planes else None)
+
+
+def zobrist_tables():
+    """The restatement's Board::initHash tables: board [133][4][2], player [4][2], sizeX / sizeY [11][2] (hash0, hash1)."""
+    board = np.zeros((133, 4, 2), np.uint64); player = np.zeros((4, 2), np.uint64)
+    sx = np.zeros((11, 2), np.uint64); sy = np.zeros((11, 2), np.uint64)
+    lib().ko_zobrist_tables(_p(board), _p(player), _p(sx), _p(sy))
+    return {"board": board, "player": player, "sizeX": sx, "sizeY": sy}
+
+
+def rand_stream(seed, n):
+    """n values of Rand(seed).nextUInt() and, from a fresh generator, n of nextUInt64()."""
+    l = lib()
+    a = l.ko_rand_create(seed.encode())
+    v32 = np.array([l.ko_rand_next_uint(a) for _ in range(n)], np.uint32)
+    l.ko_rand_destroy(a)
+    b = l.ko_rand_create(seed.encode())
+    v64 = np.array([l.ko_rand_next_uint64(b) for _ in range(n)], np.uint64)
+    l.ko_rand_destroy(b)
+    return v32, v64
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(vp)
 
@@ -190,6 +256,9 @@ class Game:
         out = np.zeros(2, np.uint64)
         lib().ko_game_sit_hash(self._g, self.next_pla() if pla is None else pla, _p(out))
         return out
+
+    def max_consecutives(self, x, y):
+        return lib().ko_game_max_consecutives(self._g, x, y)
 
     def nn_hash(self, pla=None, pda=0.0, temp=1.0, optimism=0.0):
         out = np.zeros(2, np.uint64)

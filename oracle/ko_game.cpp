@@ -550,7 +550,7 @@ long ko_playout_run(int x_size, int y_size, int win_len, uint64_t seed, uint64_t
             ko_step_record& r = records[idx];
             r.game = (uint32_t)(g0 + i);
             r.status = ko_game_status(g);
-            for(int w = 0; w < 7; w++) r.legal[w] = 0;
+            for(int w = 0; w < 13; w++) r.legal[w] = 0;
             ko_game_legal_mask(g, pla, r.legal);  // raw isLegal mask, also on finished positions
             r.movePos = movePos;
             ko_game_sit_hash(g, pla, r.sitHash);
