@@ -156,6 +156,7 @@ def ref_rules_lib():
         l.kc_ref_copy_outputs_with_symmetry.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         l.kc_ref_sym_xy.argtypes = [C.c_int] * 5 + [vp, vp]
         l.kc_ref_pos_to_loc.argtypes = [C.c_int] * 5 + [vp, vp, vp]
+        l.kc_ref_graph_hash_chain.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         l.kc_ref_init()
         _ref_rules = l
     return _ref_rules

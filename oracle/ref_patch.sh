@@ -16,7 +16,7 @@ rm -rf "$B"
 mkdir -p "$B/core" "$B/game" "$B/neuralnet"
 for f in core/global.h core/global.cpp core/hash.h core/hash.cpp core/rand.h core/rand.cpp core/rand_helpers.h core/rand_helpers.cpp \
          core/md5.h core/md5.cpp core/sha2.h core/sha2.cpp core/os.h core/test.h core/test.cpp core/timer.h core/timer.cpp core/bsearch.h \
-         core/bsearch.cpp core/using.h core/commontypes.h game/board.h game/board.cpp game/boardhistory.h game/boardhistory.cpp \
+         core/bsearch.cpp core/using.h core/commontypes.h game/board.h game/board.cpp game/boardhistory.h game/boardhistory.cpp game/graphhash.h game/graphhash.cpp \
          neuralnet/nninputs.h neuralnet/nninputs.cpp; do
   cp "$REF/cpp/$f" "$B/$f"
 done
@@ -67,6 +67,6 @@ sed -i 's|^  extern bool historyChannelWithDirection;|  extern bool historyChann
 CXX="${CXX:-g++}"
 # -DNDEBUG: fillRowV1 asserts currentFeatureIdx == 11 even when the history is short (ledger F) and whiteWinsOfWinner asserts on a draw
 $CXX -std=c++17 -O2 -fPIC -shared -DNDEBUG -DKC_REF_LEGAL_WORDS=13 -w -I"$B" -o "$HERE/_ref/libkc_ref_rules.so" "$HERE/ref_rules_shim.cpp" \
-  "$B/game/board.cpp" "$B/game/boardhistory.cpp" "$B/neuralnet/nninputs.cpp" "$B/core/hash.cpp" "$B/core/rand.cpp" "$B/core/rand_helpers.cpp" \
+  "$B/game/board.cpp" "$B/game/boardhistory.cpp" "$B/game/graphhash.cpp" "$B/neuralnet/nninputs.cpp" "$B/core/hash.cpp" "$B/core/rand.cpp" "$B/core/rand_helpers.cpp" \
   "$B/core/md5.cpp" "$B/core/sha2.cpp" "$B/core/global.cpp" "$B/core/test.cpp" "$B/core/timer.cpp" "$B/core/bsearch.cpp" -lpthread
 echo "built oracle/_ref/libkc_ref_rules.so from $REF (patched scratch copy in oracle/_ref/build)"

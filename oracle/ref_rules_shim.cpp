@@ -4,6 +4,7 @@
 //   Board::initHash / isLegal / playMoveAssumeLegal / maxConsecutives / checkGameEnd / getSitHash   (cpp/game/board.cpp)
 //   BoardHistory::makeBoardMove / makeBoardMoveAssumeLegal                                          (cpp/game/boardhistory.cpp)
 //   NNInputs::getHash / fillRowV1, NNPos::*, SymmetryHelpers::*                                     (cpp/neuralnet/nninputs.cpp)
+//   GraphHash::getGraphHash / getGraphHashFromScratch                                                (cpp/game/graphhash.cpp)
 //   Rand                                                                                             (cpp/core/rand.cpp)
 // so that tests/test_oracle_ref_rules.py can hold the restatement in oracle/ko_game.cpp / ko_hash.cpp against the literal code.
 //
@@ -23,6 +24,7 @@
 #include "core/rand.h"
 #include "game/board.h"
 #include "game/boardhistory.h"
+#include "game/graphhash.h"
 #include "neuralnet/nninputs.h"
 
 namespace {
@@ -163,6 +165,25 @@ int kc_ref_position(int xSize, int ySize, int winLen, const int8_t* stones, int 
   sitHash[0] = sh.hash0; sitHash[1] = sh.hash1;
   posHash[0] = b.pos_hash.hash0; posHash[1] = b.pos_hash.hash1;
   return n;
+}
+
+// GraphHash::getGraphHash (graphhash.cpp:14-29) chained along a move sequence from the empty board: out[i] = the hash after i moves
+// (out[0] = the hash of the initial position), and GraphHash::getGraphHashFromScratch of the final history in out[numMoves + 1]
+void kc_ref_graph_hash_chain(int xSize, int ySize, int winLen, int numMoves, const int32_t* movePos, uint64_t* out) {
+  Board::initHash();
+  Board board(xSize, ySize, winLen);
+  BoardHistory hist(board, P_BLACK);
+  const int hw = xSize * ySize;
+  Hash128 h = GraphHash::getGraphHash(Hash128(), hist, hist.presumedNextMovePla);
+  out[0] = h.hash0; out[1] = h.hash1;
+  for(int i = 0; i < numMoves; i++) {
+    const int d = movePos[i] / hw, rem = movePos[i] % hw;
+    hist.makeBoardMove(board, Loc(Location::getSpot(rem % xSize, rem / xSize, xSize), (Direction)d), hist.presumedNextMovePla);
+    h = GraphHash::getGraphHash(h, hist, hist.presumedNextMovePla);
+    out[2 * (i + 1)] = h.hash0; out[2 * (i + 1) + 1] = h.hash1;
+  }
+  const Hash128 s = GraphHash::getGraphHashFromScratch(hist, hist.presumedNextMovePla);
+  out[2 * (numMoves + 1)] = s.hash0; out[2 * (numMoves + 1) + 1] = s.hash1;
 }
 
 // NNInputs::getHash on an empty board of the given size with every MiscNNInputParams fold (nninputs.cpp:463-502)

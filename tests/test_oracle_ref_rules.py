@@ -134,6 +134,39 @@ def test_nn_hash_folds_equal_the_literal_code(oracle, ref):
                 assert (og.nn_hash(pla, pda=pda, temp=temp, optimism=opt) == out).all(), (W, pla, pda, temp, opt)
 
 
+def test_literal_graph_hash_chain(oracle, ref):
+    """GraphHash::getGraphHash (graphhash.cpp:14-29) chained over whole games: the oracle's ko_graph_hash equals the literal code, and the
+    literal getGraphHashFromScratch reproduces the chained value (with the getRecentBoard(0) the literal makeBoardMove leaves:
+    recentBoards is pushed twice per move, ledger D, but slot 0 is always the current board)."""
+    for (W, H, K) in ((5, 5, 4), (6, 6, 4)):
+        for g in range(40):
+            og = oracle.Game(W, H, K)
+            moves, chain = [], []
+            h = np.zeros(2, np.uint64)
+            nh = np.zeros(2, np.uint64)
+            oracle.lib().ko_graph_hash(_p(h), og._g, og.next_pla(), _p(nh))
+            chain.append(nh.copy()); h = nh.copy()
+            while not og.finished():
+                pos = og.choose(99, g)
+                if pos < 0:
+                    break
+                og.play(pos); moves.append(pos)
+                nh = np.zeros(2, np.uint64)
+                oracle.lib().ko_graph_hash(_p(h), og._g, og.next_pla(), _p(nh))
+                chain.append(nh.copy()); h = nh.copy()
+                if og.finished():
+                    break
+            mv = np.array(moves, np.int32)
+            out = np.zeros((len(moves) + 2, 2), np.uint64)
+            ref.kc_ref_graph_hash_chain(W, H, K, len(moves), _p(mv), _p(out))
+            # the oracle's game may have ended in a draw the literal history does not know (ledger C): compare up to the last move
+            # whose position the literal code also sees as unfinished or won
+            drawn = og.finished() and og.winner() == 0
+            upto = len(moves) + (0 if drawn else 1)
+            assert (np.array(chain[:upto]) == out[:upto]).all(), (W, g)
+            assert (out[len(moves)] == out[len(moves) + 1]).all()
+
+
 def test_symmetry_helpers_equal_the_literal_code(oracle, ref):
     rng = np.random.default_rng(3)
     for (n, h, w, c) in ((2, 5, 5, 15), (1, 6, 6, 3), (3, 4, 5, 2), (1, 7, 3, 1)):
