@@ -11,7 +11,7 @@ namespace kc {
 // out-of-board taps fall into the zero halo above/below the tile.
 inline int boardsPerTile(int W, int H) { int nb = 128 / (H * (W + 1)); return nb > 4 ? 4 : nb; }
 constexpr int TILE_ROWS = 128;
-constexpr int HALO_ROWS = 32;                    // >= NB*(W+1)+1 for every supported size
+constexpr int HALO_ROWS = 28;                    // >= NB*(W+1)+1 for every supported size (5x5: 25, 6x6: 22); 28 keeps chunks 128-byte aligned
 constexpr int ACT_ROWS = TILE_ROWS + 2 * HALO_ROWS;
 
 // ---- handle accessors used by games.cu ----------------------------------------------------------

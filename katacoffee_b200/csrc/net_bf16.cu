@@ -40,7 +40,6 @@ namespace kc {
 using namespace ptx;
 
 constexpr int CHUNK_BYTES = ACT_ROWS * 16;             // one 8-channel chunk of an activation tile
-constexpr int KSTEPS_PER_STAGE = 3;
 constexpr int SCR_STRIDE = 17;
 constexpr int MAX_NB = 4;
 constexpr int HEADC = 32;   // p1 = g1 = v1 = 32 channels
@@ -53,9 +52,13 @@ constexpr int MAX_V2 = 128;
 // 128 activation rows from each CTA, the weight block split in halves between the two shared memories), so each SM reads
 // and stages only half of the weights: shared-memory operand traffic drops from 128 to 96 B/clk and the L2 -> SM weight
 // stream halves.
-template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false>
+// KSTEPS: K-steps (16 input channels x 1 tap each) per weight stage.  3 = one kernel row of a 16-channel chunk; 9 = the whole chunk
+// (pair mode): one barrier round and one commit per 9 MMAs, because the single issuing thread -- not the tensor pipe -- is what
+// runs out first with small stages (an MMA of a CTA pair is 64 clk of pipe time; three waits + a commit per 192 clk did not fit).
+template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false, int KSTEPS_ = 3>
 struct TrunkCfg {
-  static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_;
+  static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_, KSTEPS = KSTEPS_;
+  static_assert(KSTEPS == 3 || KSTEPS == 9, "a stage is one kernel row or one whole 16-channel chunk of a 3x3 layer");
   static constexpr bool PAIR = PAIR_;
   static constexpr bool REALLOC = REALLOC_;   // launch with 128 registers per thread and re-allocate between the warpgroups (setmaxnreg)
   static constexpr int NCTA = PAIR ? 2 : 1;
@@ -64,15 +67,16 @@ struct TrunkCfg {
   static constexpr int POOLW = 3 * MAXG;                      // pooled vector per board (>= 96 for the heads)
   static constexpr int THREADS = 128 + NT * 128;              // warp 0 TMA producer, 1..NT MMA issuers, 4.. epilogue (4 warps per tile)
   static constexpr int ACT_BYTES = (MAXC / 8) * CHUNK_BYTES;
-  static constexpr int STAGE_BYTES = KSTEPS_PER_STAGE * MAXC * 32 / NCTA;   // per CTA
+  static constexpr int STAGE_BYTES = KSTEPS * MAXC * 32 / NCTA;   // per CTA
   static constexpr int OFF_ACT = 0;
   static constexpr int OFF_RING = OFF_ACT + NT * ACT_BYTES;
   static constexpr int OFF_SCR = OFF_RING + NSTAGES * STAGE_BYTES;
   static constexpr int OFF_POOLA = OFF_SCR + NT * 128 * SCR_STRIDE * 4;
   static constexpr int OFF_POOLB = OFF_POOLA + NT * MAX_NB * POOLW * 4;
-  static constexpr int OFF_BIAS = OFF_POOLB + NT * MAX_NB * POOLW * 4;
-  static constexpr int OFF_V2 = OFF_BIAS + NT * MAX_NB * MAXC * 4;
-  static constexpr int OFF_SYM = OFF_V2 + NT * MAX_NB * MAX_V2 * 4;
+  // the per-board bias buffer [MAX_NB][MAXC] and the v2 buffer [MAX_NB][MAX_V2] of the gpool / head epilogues live in the pooling
+  // scratch: they are written after the last pooling pass has been read (named barrier in between) and read before the next one
+  static_assert((MAX_NB * MAXC + MAX_NB * MAX_V2) * 4 <= 128 * SCR_STRIDE * 4, "bias + v2 buffers alias the pooling scratch");
+  static constexpr int OFF_SYM = OFF_POOLB + NT * MAX_NB * POOLW * 4;
   static constexpr int OFF_PAR = OFF_SYM + 448;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
   static constexpr int OFF_BAR = OFF_PAR + NT * 2 * 2 * MAXC * 4; // folded BN, staged while the tensor core is still busy with it
   // barriers (8 bytes each)
@@ -80,14 +84,15 @@ struct TrunkCfg {
                        BAR_IN = BAR_ACTFREE + NT, BAR_HEAD = BAR_IN + NT, BAR_CHUNK = BAR_HEAD + NT, BAR_FULLP = BAR_CHUNK + NT * NCH,
                        BAR_INP = BAR_FULLP + NSTAGES, BAR_SKEW = BAR_INP + NT, NUM_BARS = BAR_SKEW + 1;   // FULLP / INP: the peer CTA's weights / input tile landed
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int OFF_PROG = OFF_TMEM + 8;     // stages issued so far by tile 0's MMA issuer (read by tile 1's: the enforced lag)
   static constexpr int SMEM = OFF_TMEM + 16;
   static_assert(NT * 2 * MAXC <= 512, "TMEM: every tile needs a trunk region and a block-internal region");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(POOLW >= 96, "the heads pool 32 channels three ways");
 };
 using Cfg128 = TrunkCfg<128, 2, 7>;
-using Cfg128P = TrunkCfg<128, 2, 14, true>;
-using Cfg128PR = TrunkCfg<128, 2, 14, true, true>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
+using Cfg128P = TrunkCfg<128, 2, 5, true, false, 9>;
+using Cfg128PR = TrunkCfg<128, 2, 5, true, true, 9>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
@@ -133,8 +138,10 @@ struct TrunkParams {
   int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
   int opFmt;         // tensor-core operand format of the input tiles, the weights and the activations: 0 fp16 (default), 1 bf16
                      // (KC_FLAG_OPERANDS_BF16).  One format for A and B: a kind::f16 MMA with mixed formats is an illegal instruction.
-  int skew;          // two tiles per CTA: tile 1's MMA issuer starts this many weight stages after tile 0's, so that the layer boundary of
-                     // one tile (accumulator -> epilogue -> first chunk published, ~1,200 clk) is covered by the other tile's MMAs
+  int skew;          // two tiles per CTA: tile 1's MMA issuer starts EVERY layer only once tile 0's has issued this many weight stages of
+                     // it, so that the layer boundary of one tile (accumulator -> epilogue -> first chunk published, ~1,200 clk of no
+                     // MMAs) is covered by the other tile's MMAs.  Enforced per layer: left alone the two issuers fall into lock step
+                     // (they share the weight ring, and the one ahead is the one that waits for slots)
   int g1Act, p1Act, v1Act, v2Act;   // head activations
   int* abortFlag;
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
@@ -552,15 +559,29 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
     return mbar_wait(bar, parity, abortFlag, code);
   };
   const int itemStep = K::PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
-  // skew between the two tiles of a CTA: tile 0 signals once it has issued P.skew stages, tile 1 starts then; the lead keeps itself
-  // (both tiles pay the same boundary stalls) and is bounded by the ring, whose slots are only refilled once both tiles have used them
+  // enforced lag between the two tiles of a CTA (TrunkParams::skew): tile 0 publishes how many stages it has issued, tile 1 starts a
+  // layer only when tile 0 is `skew` stages into it (or through it, if the layer is shorter)
   const bool skewed = K::NT == 2 && P.skew > 0;
-  int stagesToSignal = (skewed && t == 0) ? P.skew : -1;
+  volatile int* progress = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(sbase)) + K::OFF_PROG);
+  int stagesIssued = 0;   // by this issuer, over all layers and items
   auto stageIssued = [&]() {
-    if(stagesToSignal > 0 && --stagesToSignal == 0) { if(leader) mbar_arrive(bars + K::BAR_SKEW * 8); stagesToSignal = -1; }
+    stagesIssued++;
+    if(skewed && t == 0 && leader) *progress = stagesIssued;
+  };
+  auto waitForLeadTile = [&](int nst) -> bool {   // tile 1, at the start of a layer of nst stages
+    if(!(skewed && t == 1)) return true;
+    const int need = stagesIssued + min(P.skew, nst);
+    if(*progress >= need) return true;
+    long long t0 = clock64();
+    for(uint32_t it = 1;; it++) {
+      if(*progress >= need) return true;
+      if((it & 63u) == 0) {
+        if(*abortFlag != 0) return false;
+        if(clock64() - t0 > (1LL << 32)) { *abortFlag = 28; return false; }
+      }
+    }
   };
   for(int item = K::PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x; item < numItems; item += itemStep, itemCount++) {   // pair mode: item = item pair
-    if(skewed && t == 1 && itemCount == 0 && !mbar_wait(bars + K::BAR_SKEW * 8, 0, abortFlag, 28)) return;
     if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
     if(K::PAIR && !waitc(bars + (K::BAR_INP + t) * 8, itemCount & 1, 26)) return;
     if(itemCount > 0 && !waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
@@ -575,6 +596,8 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
       uint32_t accum = P.layers[l].accumulate ? 1u : 0u;
       if(ntaps == 9) {
         const int nchunks = nk / 9;
+        constexpr int ROWS_PER_STAGE = K::KSTEPS / 3;          // kernel rows (dy) per weight stage: 1 or 3
+        if(!waitForLeadTile(nchunks * (3 / ROWS_PER_STAGE))) return;
         for(int cc = 0; cc < nchunks; cc++) {
           const bool probe = P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && cc == 0 && leader;
           if(probe) P.dbg[6] = clock64();
@@ -587,19 +610,24 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
           if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 1 && cc == 0 && leader) P.dbg[23] = clock64();
           const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
 #pragma unroll
-          for(int dy = 0; dy < 3; dy++) {
+          for(int dy0 = 0; dy0 < 3; dy0 += ROWS_PER_STAGE) {
             if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
             if(K::PAIR && !mbar_wait(barFullP + slot * 8, phase, abortFlag, 27)) return;
             tc_fence_after();
             const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
-            const uint32_t aLoR = aLoC + (dy - 1) * P.tileRowW - 1;
             if(leader) {
-              mma(d, desc(aLoR), desc(bLo), idesc, accum);
-              mma(d, desc(aLoR + 1), desc(bLo + bStep), idesc, 1u);
-              mma(d, desc(aLoR + 2), desc(bLo + 2 * bStep), idesc, 1u);
+#pragma unroll
+              for(int r = 0; r < ROWS_PER_STAGE; r++) {
+                const uint32_t aLoR = aLoC + (dy0 + r - 1) * P.tileRowW - 1;
+                const uint32_t bLoR = bLo + 3 * r * bStep;
+                mma(d, desc(aLoR), desc(bLoR), idesc, accum);
+                mma(d, desc(aLoR + 1), desc(bLoR + bStep), idesc, 1u);
+                mma(d, desc(aLoR + 2), desc(bLoR + 2 * bStep), idesc, 1u);
+                accum = 1u;
+              }
               commit(barEmpty + slot * 8);
-              if(probe && dy == 0) P.dbg[5] = clock64();
-              if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && dy == 2 && cc < 7) P.dbg[8 + cc] = clock64();
+              if(probe && dy0 == 0) P.dbg[5] = clock64();
+              if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && dy0 + ROWS_PER_STAGE == 3 && cc < 7) P.dbg[8 + cc] = clock64();
             }
             __syncwarp();
             accum = 1u;
@@ -609,14 +637,15 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
         }
       } else {
         // 1x1 layers: K-step = one 16-channel chunk, stages of up to 3 K-steps
-        const int nst = (nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+        const int nst = (nk + K::KSTEPS - 1) / K::KSTEPS;
+        if(!waitForLeadTile(nst)) return;
         for(int s = 0; s < nst; s++) {
           if(!mbar_wait(barFull + slot * 8, phase, abortFlag, 23)) return;
           if(K::PAIR && !mbar_wait(barFullP + slot * 8, phase, abortFlag, 27)) return;
           const uint32_t bLo = (ringLo0 + slot * (K::STAGE_BYTES >> 4)) | bLbo;
-          const int ks = min(KSTEPS_PER_STAGE, nk - s * KSTEPS_PER_STAGE);
+          const int ks = min(K::KSTEPS, nk - s * K::KSTEPS);
           for(int kk = 0; kk < ks; kk++) {
-            const int cc = s * KSTEPS_PER_STAGE + kk;
+            const int cc = s * K::KSTEPS + kk;
             if(l > 0) {
               const uint32_t bit = 1u << cc;
               if(!waitc(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, 24)) return;
@@ -643,7 +672,6 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
       }
       __syncwarp();
     }
-    if(stagesToSignal > 0) { if(leader) mbar_arrive(bars + K::BAR_SKEW * 8); stagesToSignal = -1; }   // a net with fewer stages than the skew
   }
 }
 
@@ -670,6 +698,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
   for(int i = threadIdx.x; i < NT * K::ACT_BYTES / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
   for(int i = threadIdx.x; i < 8 * P.HW; i += K::THREADS) sSym[i] = P.dstOfSrcRev[i];
   if(threadIdx.x == 0) {
+    *reinterpret_cast<volatile int*>(smem + K::OFF_PROG) = 0;
     for(int i = 0; i < K::NSTAGES; i++) {
       mbar_init(bars + (K::BAR_FULL + i) * 8, 1); mbar_init(bars + (K::BAR_EMPTY + i) * 8, NT);   // every MMA issuer releases a slot
       mbar_init(bars + (K::BAR_FULLP + i) * 8, 1);
@@ -718,10 +747,10 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         }
         for(int l = 0; l < P.numLayers && alive; l++) {
           const LayerDesc L = P.layers[l];
-          const int nst = (L.nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+          const int nst = (L.nk + K::KSTEPS - 1) / K::KSTEPS;
           const uint8_t* w = P.wstream + L.wOffset;
           for(int s = 0; s < nst; s++) {
-            int ks = min(KSTEPS_PER_STAGE, L.nk - s * KSTEPS_PER_STAGE);
+            int ks = min(K::KSTEPS, L.nk - s * K::KSTEPS);
             uint32_t bytes = (uint32_t)ks * L.N * 32;          // whole stage; the stream holds [rank 0 half][rank 1 half] per stage
             alive = mbar_wait(bars + (K::BAR_EMPTY + slot) * 8, phase ^ 1, abortFlag, 12);
             if(!alive) break;
@@ -749,7 +778,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
           if(alive) mbar_arrive_cluster(mapa(bars + (K::BAR_INP + t) * 8, 0));
         }
         for(int l = 0; l < P.numLayers && alive; l++) {
-          const int nst = (P.layers[l].nk + KSTEPS_PER_STAGE - 1) / KSTEPS_PER_STAGE;
+          const int nst = (P.layers[l].nk + K::KSTEPS - 1) / K::KSTEPS;
           for(int s = 0; s < nst && alive; s++) {
             alive = mbar_wait(bars + (K::BAR_FULL + slot) * 8, phase, abortFlag, 14);
             if(alive) mbar_arrive_cluster(mapa(bars + (K::BAR_FULLP + slot) * 8, 0));
@@ -781,8 +810,8 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     c.scr = reinterpret_cast<float*>(smem + K::OFF_SCR) + c.t * 128 * SCR_STRIDE;
     c.poolA = reinterpret_cast<float*>(smem + K::OFF_POOLA) + c.t * MAX_NB * K::POOLW;
     c.poolB = reinterpret_cast<float*>(smem + K::OFF_POOLB) + c.t * MAX_NB * K::POOLW;
-    c.biasBuf = reinterpret_cast<float*>(smem + K::OFF_BIAS) + c.t * MAX_NB * K::MAXC;
-    c.v2buf = reinterpret_cast<float*>(smem + K::OFF_V2) + c.t * MAX_NB * MAX_V2;
+    c.biasBuf = c.scr;                          // aliases (see TrunkCfg)
+    c.v2buf = c.scr + MAX_NB * K::MAXC;
     uint32_t layerCount = 0;
     bool alive = true;
     stageHeadParams(P, P.layers[P.numLayers - 1], c.e, c.t, sHeadPar[c.t]);   // read after the first layer's named barrier at the earliest
@@ -1105,8 +1134,8 @@ int buildTrunkProgram(kc_model* m) {
       const int N = L.N, half = N / 2;
       const uint8_t* src = ws.data() + L.wOffset;
       uint8_t* dst = w2.data() + L.wOffset;
-      for(int k0 = 0; k0 < L.nk; k0 += KSTEPS_PER_STAGE) {
-        const int ks = std::min(KSTEPS_PER_STAGE, L.nk - k0);
+      for(int k0 = 0; k0 < L.nk; k0 += Cfg128P::KSTEPS) {
+        const int ks = std::min(Cfg128P::KSTEPS, L.nk - k0);
         for(int h = 0; h < 2; h++)
           for(int k = 0; k < ks; k++)
             for(int kc = 0; kc < 2; kc++) {
@@ -1228,7 +1257,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   // tile skew (see TrunkParams::skew): 5 of the 14 ring stages in pair mode, measured +1.5 % burst / +1 % under the power cap
   // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
   static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();
-  P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 5 : 2;
+  P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 2 : 2;
   if(T->cfg == 0 && usePair) {
     // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
     P.wstream = T->d_wPair[P.opFmt];
