@@ -184,7 +184,9 @@ int kc_handle_trunk_time(kc_handle* h, float* sumMs, int* count);
  * starts waiting, 4 its wait is over, 5 its first MMAs are issued, 8..14 the MMAs of its input chunks 0..6 are issued,
  * 15 its last MMA is issued; item boundary: 16 head conv issued, 17 head epilogue starts, 18 it has released TMEM,
  * 19 it ends, 20 issuer starts the next item, 21 has issued its layer 0, 22 epilogue sees layer 0, 23 issuer has
- * the first chunk of layer 1; 24..29 phases inside the head epilogue. */
+ * the first chunk of layer 1; 24..29 phases inside the head epilogue.  out[64 + ((tile * 48 + layer) * 8 + k)]: the whole second
+ * item of CTA 0 -- k = 0 the MMA issuer reaches the layer, 1 its first input chunk is there, 2 the layer is issued, 3 the epilogue
+ * sees the accumulator, 4 the epilogue is done (tests/diag_timeline.py prints it).  out must hold 64 + 2 * 48 * 8 words. */
 int kc_handle_trunk_probe(kc_handle* h, int64_t* out);
 /* Self-test of the tcgen05 descriptor conventions the trunk kernel relies on: D[128][N] =
  * A[shift:shift+128][K] * B[N][K]^T on the tensor core (A, B bf16 bit patterns, D fp32).  ws != 0 uses the

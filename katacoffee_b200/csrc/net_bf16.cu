@@ -94,6 +94,7 @@ using Cfg128 = TrunkCfg<128, 2, 7>;
 using Cfg128P = TrunkCfg<128, 2, 5, true, false, 9>;
 using Cfg128PR = TrunkCfg<128, 2, 5, true, true, 9>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
+using Cfg192P = TrunkCfg<192, 1, 4, true, false, 9>;   // b15c192 as CTA pairs: each CTA stages half of the 192 output channels (27 KB stages)
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
 
@@ -111,6 +112,7 @@ struct LayerDesc {
   unsigned wOffset; // byte offset of this layer's first stage in the weight stream
   int pOff;        // float offset of this layer's parameters
 };
+constexpr int KC_TRUNK_PROBE_WORDS = 64 + 2 * 48 * 8;   // kc_handle_trunk_probe: 64 point probes + the whole-item timeline [tile][layer][8]
 constexpr int MAX_LAYERS = 48;   // 1 + 2*blocks + 1; the table travels in the kernel parameter block (constant bank:
                                  // warp-uniform loads, so the MMA issue loop stays on the uniform datapath)
 
@@ -589,6 +591,10 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
     if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) P.dbg[20] = clock64();
     for(int l = 0; l < P.numLayers; l++) {
       const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
+      // whole-item timeline (KC_TRUNK_PROBE): CTA 0, second item (steady state): [64 + ((t * MAX_LAYERS + l) * 8 + k)]
+      //   k = 0 issuer reaches the layer, 1 first chunk available, 2 layer issued and committed, 3 epilogue sees the accumulator, 4 epilogue done
+      long long* tl = (P.dbg && blockIdx.x == 0 && itemCount == 1 && leader) ? P.dbg + 64 + (t * MAX_LAYERS + l) * 8 : nullptr;
+      if(tl) tl[0] = clock64();
       const uint32_t idesc = idesc_f16kind_f32(128 * K::NCTA, N, (uint32_t)P.opFmt, (uint32_t)P.opFmt);   // A and B must share the format
       const uint32_t d = tmemBase + t * (2 * K::MAXC) + (P.layers[l].outSel ? K::MAXC : 0);
       const uint32_t bStep = 2 * N / K::NCTA;                    // one K-step of weights = N*32 bytes (per CTA: its half of the rows)
@@ -607,6 +613,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
             chunkPhase ^= bit;
           }
           if(probe) P.dbg[4] = clock64();
+          if(tl && cc == 0) tl[1] = clock64();
           if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 1 && cc == 0 && leader) P.dbg[23] = clock64();
           const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
 #pragma unroll
@@ -664,6 +671,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
       }
       if(leader) {
         commit(bars + (K::BAR_ACC + t) * 8);
+        if(tl) tl[2] = clock64();
         if(l == P.numLayers - 1) commit(bars + (K::BAR_ACTFREE + t) * 8);
         if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 5) P.dbg[0] = clock64();
         if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6) P.dbg[15] = clock64();
@@ -840,6 +848,9 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         }
         alive = mbar_wait(bars + (K::BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
         if(!alive) break;
+        long long* tl = (P.dbg && blockIdx.x == 0 && c.e == 0 && (int)layerCount >= P.numLayers && (int)layerCount < 2 * P.numLayers)
+                          ? P.dbg + 64 + (c.t * MAX_LAYERS + l) * 8 : nullptr;
+        if(tl) tl[3] = clock64();
         c.dbg = (P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && layerCount == 5) ? P.dbg : nullptr;
         if(c.dbg) c.dbg[1] = clock64();
         const bool probeHead = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers - 1;
@@ -850,6 +861,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
         else epilogueHead<K>(P, L, c, item * NT + c.t, barHead, sSym, nRows);
         if(probeHead) P.dbg[19] = clock64();
+        if(tl) tl[4] = clock64();
       }
     }
   }
@@ -1127,13 +1139,13 @@ int buildTrunkProgram(kc_model* m) {
     const std::vector<uint8_t>& ws = fmt == 0 ? pk.w : pkB.w;
     if(cudaMalloc(&T->d_w[fmt], ws.size()) != cudaSuccess) { delete T; return kc::fail("buildTrunkProgram: out of device memory"); }
     cudaMemcpy(T->d_w[fmt], ws.data(), ws.size(), cudaMemcpyHostToDevice);
-    if(cfg != 0) continue;
     // pair-mode stream: per stage [rank 0: rows 0..N/2 of every K-step][rank 1: rows N/2..N], each K-step still [2][rows][8]
     std::vector<uint8_t> w2(ws.size());
     for(const LayerDesc& L : T->layers) {
       const int N = L.N, half = N / 2;
       const uint8_t* src = ws.data() + L.wOffset;
       uint8_t* dst = w2.data() + L.wOffset;
+      static_assert(Cfg128P::KSTEPS == Cfg192P::KSTEPS, "one pair-mode stream layout");
       for(int k0 = 0; k0 < L.nk; k0 += Cfg128P::KSTEPS) {
         const int ks = std::min(Cfg128P::KSTEPS, L.nk - k0);
         for(int h = 0; h < 2; h++)
@@ -1173,9 +1185,10 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaMemset(h->d_tiles, 0, bytes));
   KC_CUDA(cudaMalloc(&h->d_abort, 4));
   KC_CUDA(cudaMemset(h->d_abort, 0, 4));
-  if(getenv("KC_TRUNK_PROBE")) { KC_CUDA(cudaMalloc(&h->d_dbg, 32 * 8)); KC_CUDA(cudaMemset(h->d_dbg, 0, 32 * 8)); }
+  if(getenv("KC_TRUNK_PROBE")) { KC_CUDA(cudaMalloc(&h->d_dbg, KC_TRUNK_PROBE_WORDS * 8)); KC_CUDA(cudaMemset(h->d_dbg, 0, KC_TRUNK_PROBE_WORDS * 8)); }
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PR::SMEM));
   return 0;
@@ -1258,20 +1271,21 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
   static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();
   P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 2 : 2;
-  if(T->cfg == 0 && usePair) {
+  if(usePair) {
     // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
     P.wstream = T->d_wPair[P.opFmt];
     const int numUnits = nDev ? h->ctx->smCount / 2 : (P.numItems + 1) / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * std::min(numUnits, h->ctx->smCount / 2)); cfg.blockDim = dim3(Cfg128P::THREADS);
-    cfg.dynamicSmemBytes = Cfg128P::SMEM; cfg.stream = st;
+    cfg.gridDim = dim3(2 * std::min(numUnits, h->ctx->smCount / 2)); cfg.blockDim = dim3(T->cfg == 0 ? Cfg128P::THREADS : Cfg192P::THREADS);
+    cfg.dynamicSmemBytes = T->cfg == 0 ? Cfg128P::SMEM : Cfg192P::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     // the re-allocating variant only where something wants to run beside the trunk (the search's half batches); KC_TRUNK_REALLOC forces
     static const int reallocEnv = [] { const char* e = getenv("KC_TRUNK_REALLOC"); return e ? atoi(e) : -1; }();
-    if(reallocEnv >= 0 ? reallocEnv != 0 : h->leaveRegisters) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128PR>, P));
+    if(T->cfg != 0) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg192P>, P));
+    else if(reallocEnv >= 0 ? reallocEnv != 0 : h->leaveRegisters) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128PR>, P));
     else KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
   }
   else if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
@@ -1290,7 +1304,7 @@ int kc_handle_trunk_probe(kc_handle* h, int64_t* out) {
   KC_CHECK(h->d_dbg, "kc_handle_trunk_probe: set KC_TRUNK_PROBE=1 before creating the handle");
   KC_CUDA(cudaSetDevice(h->ctx->device));
   KC_CUDA(cudaDeviceSynchronize());
-  KC_CUDA(cudaMemcpy(out, h->d_dbg, 32 * 8, cudaMemcpyDeviceToHost));
+  KC_CUDA(cudaMemcpy(out, h->d_dbg, kc::KC_TRUNK_PROBE_WORDS * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 // Self-test of the UMMA descriptor conventions the trunk kernel relies on (row-shifted K-major

@@ -13,7 +13,7 @@ h = backend.createComputeHandle(ctx, lm, G, 5, 5)
 games = backend.Games(ctx, G, 5, 5, 4); games.reset(seed=1, autoRefill=True)
 for rep in range(3):
     games.run(h, 2)
-    out = np.zeros(32, np.int64)
+    out = np.zeros(64 + 2 * 48 * 8, np.int64)
     check(lib().kc_handle_trunk_probe(h._p, ptr(out)))
     t0 = out[0]
     print("rel. to last MMA issue of layer 5:", {k: int(out[i] - t0) for k, i in (("issuer starts waiting", 6), ("epilogue sees ACC", 1), ("first tmem_ld done", 2),

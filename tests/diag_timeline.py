@@ -17,11 +17,10 @@ G = 18944 if W == 5 else 148 * 3 * 32
 h = backend.createComputeHandle(ctx, lm, G, W, W)
 games = backend.Games(ctx, G, W, W, 4); games.reset(seed=1, autoRefill=True)
 games.run(h, 3)
-WORDS = 64 + 2 * 48 * 8 + 3 * 64
+WORDS = 64 + 2 * 48 * 8
 out = np.zeros(WORDS, np.int64)
 check(lib().kc_handle_trunk_probe(h._p, ptr(out)))
 tl = out[64:64 + 768].reshape(2, 48, 8)
-st = out[64 + 768:].reshape(64, 3)
 nl = 2 * model.num_blocks + 2
 t0 = tl[0, 0, 0]
 rows = []
@@ -36,17 +35,12 @@ for t in range(2):
         if l == 0:
             chunk = reach
         nxt = int(tl[t, l + 1, 1] - t0) if l + 1 < nl and tl[t, l + 1, 1] else None
-        rows.append(dict(tile=t, layer=l, reach=reach, first_chunk=chunk, issued=issued, epi_sees_acc=esee, epi_done=edone, wait_weights=int(r[5]), wait_chunks=int(r[6]), in_issue=int(r[7])))
+        rows.append(dict(tile=t, layer=l, reach=reach, first_chunk=chunk, issued=issued, epi_sees_acc=esee, epi_done=edone))
         print(f"{t:3d} {l:5d} | {reach:7d} {chunk:7d} {issued:7d} | {chunk - reach:6d} {issued - chunk:7d} | {esee:7d} {edone:7d} | {esee - issued:6d} {edone - esee:6d} | "
-              f"{'' if nxt is None else nxt - issued} | waits: weights {int(r[5])} chunks>0 {int(r[6])} in-issue {int(r[7])}")
+              f"{'' if nxt is None else nxt - issued}")
 for t in range(2):
     if tl[t, 0, 0] and tl[t, nl - 1, 2]:
         print(f"tile {t}: item span (reach layer 0 -> head conv issued) {int(tl[t, nl - 1, 2] - tl[t, 0, 0])} clk; "
               f"sum of issue spans {sum(r['issued'] - r['first_chunk'] for r in rows if r['tile'] == t)}; sum of chunk waits {sum(r['first_chunk'] - r['reach'] for r in rows if r['tile'] == t)}")
-print("weight stages of layers 5..7 (tile-0 clock): slot wait start, copy issued (slot freed), landed | wait for slot, issue->landed")
-for i in range(64):
-    a, b, c = [int(x - t0) for x in st[i]]
-    if st[i][1]:
-        print(f"  stage {i:2d}: {a:7d} {b:7d} {c:7d} | {b - a:6d} {c - b:6d}")
 if len(sys.argv) > 3:
     json.dump(rows, open(sys.argv[3], "w"), indent=0)
