@@ -7,12 +7,14 @@
 Workload (BASELINE.json: "NN evals/s ... 5x5 k=4, b10c128"): every GPU owns G concurrent 5x5 k=4
 Coffee games.  One STEP = one ply of the fused leaf-evaluation hot path for all G games:
   rules kernel (random-legal move, win/draw, sit-hash, legal mask, auto-refill of finished games)
-  -> V1 planes written in bf16 straight into the trunk's input tiles
-  -> b10c128 forward (one persistent tcgen05 kernel) -> policy / value / misc / ownership logits,
+  -> V1 planes written as fp16 straight into the trunk's input tiles
+  -> b10c128 forward (one persistent tcgen05 kernel, fp16 operands, fp32 accumulation) -> policy / value / misc / ownership logits,
 so a step evaluates G positions.  `value` = positions evaluated per second, whole job, inputs
 resident in HBM, timed per step with CUDA events on the launching stream (max over ranks).
-`e2e` = the same metric through the reference-facing call (kc_forward == NeuralNet::getOutput)
-with HOST rows in pinned memory: H2D of the planes and D2H of the logits inside the timed region.
+`e2e` = the same metric through the C ABI's getOutput entry point (kc_forward, called from Python via ctypes) with HOST rows in
+pinned memory: H2D of the planes and D2H of the logits inside the timed region.  `batch1024` = the C++ drop-in itself
+(NeuralNet::getOutput of host/b200backend.cpp, native driver in a child process) at BASELINE configs[2]'s 1024 rows and at the
+bench batch; `config_6x6` = the same measurement for BASELINE configs[4] (6x6 k=4, b15c192) at reduced steps.
 `--impl reference` times the CPU restatement of the reference's own path (oracle: mailbox rules +
 fillRowV1 + Winograd/GEMM fp32 forward as the Eigen backend does) on all host threads.
 """
@@ -204,9 +206,9 @@ def run_reference(args):
         "impl": "reference", "metric": "nn_evals_per_s", "value": evals_s, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.games), cpu_sample_positions_per_step=n),
+        "config": workload_config(args.games),      # identical to our arm's: the CPU arm evaluates a bounded sample of it per step and reports a rate
         "cpu_baseline": {"value": evals_s, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} positions per step: oracle mailbox rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward, batch 4 per thread"},
+                         "sample": f"{n} positions per step of the same workload: oracle mailbox rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward, batch 4 per thread"},
         "e2e": {"value": evals_s, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

@@ -171,6 +171,14 @@ int kc_handle_operand_format(const kc_handle* h); /* arithmetic type of the conv
  * ownership [n][H*W] or NULL.  Synchronous: results are valid on return.  0 < n <= maxBatch. */
 int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, const int8_t* symmetry,
                float* policy, float* value, float* misc, float* ownership);
+/* The same call for rows that lie scattered in host memory -- what NeuralNet::getOutput is handed: spatialRows[i] / globalRows[i] are
+ * NNResultBuf::rowSpatial / rowGlobal (nneval.h:45-65), policyRows[i] is NNOutput::policyProbs, scalarRows[i] points at NNOutput's
+ * four contiguous scalars {whiteWinProb, whiteLossProb, varTimeLeft, shorttermWinlossError} (nninputs.h:75-90; all logits),
+ * ownerRows[i] is NNOutput::whiteOwnerMap (the array or any entry may be NULL).  The library gathers into its own page-locked
+ * staging with worker threads (KC_FORWARD_ROWS_THREADS, default min(4, cores / 2); batches under three chunks stay on the calling thread) and pipelines gather / H2D / kernels / D2H /
+ * scatter over row chunks; results are bit-identical to kc_forward on the gathered rows. */
+int kc_forward_rows(kc_handle* h, int n, const float* const* spatialRows, const float* const* globalRows, const int8_t* symmetry,
+                    float* const* policyRows, float* const* scalarRows, float* const* ownerRows);
 /* Copies the outputs of the last device-resident evaluation (kc_games_eval) to the host. */
 int kc_handle_read_outputs(kc_handle* h, int n, float* policy, float* value, float* misc, float* ownership);
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */

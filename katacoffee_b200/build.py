@@ -58,12 +58,14 @@ def build_host(force=False):
     test = os.path.join(HERE, "..", "tests", "cpp", "test_b200backend.cpp")
     bench_src = os.path.join(HERE, "..", "tests", "cpp", "bench_evaluator.cpp")
     bench_exe = os.path.join(host, "bench_evaluator")   # native throughput driver of the evaluator front end (bench.py --evaluator)
+    go_src = os.path.join(HERE, "..", "tests", "cpp", "bench_getoutput.cpp")
+    go_exe = os.path.join(host, "bench_getoutput")      # native driver of NeuralNet::getOutput itself (bench.py "batch1024")
     nneval_src = os.path.join(host, "b200nneval.cpp")   # class NNEvaluator (nneval.h) over kc_evaluator_*
     nneval_test = os.path.join(HERE, "..", "tests", "cpp", "test_b200nneval.cpp")
     nneval_exe = os.path.join(host, "test_b200nneval")
-    newest = max(os.path.getmtime(p) for p in (src, test, bench_src, nneval_src, nneval_test, os.path.join(host, "b200nneval.h"), os.path.join(host, "reftypes.h"),
+    newest = max(os.path.getmtime(p) for p in (src, test, bench_src, go_src, nneval_src, nneval_test, os.path.join(host, "b200nneval.h"), os.path.join(host, "reftypes.h"),
                                                os.path.join(HERE, "..", "include", "katacoffee_b200.h")))
-    outs = (lib, exe, bench_exe, nneval_exe)
+    outs = (lib, exe, bench_exe, nneval_exe, go_exe)
     if not force and all(os.path.exists(p) for p in outs) and min(os.path.getmtime(p) for p in outs) >= newest:
         return lib, exe
     inc = ["-I" + os.path.join(HERE, "..", "include"), "-I" + host]
@@ -75,6 +77,8 @@ def build_host(force=False):
                     "-Wl,-rpath," + HERE], check=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [bench_src, "-o", bench_exe, "-L" + HERE, "-lkatacoffee_b200", "-Wl,-rpath," + HERE, "-lpthread"],
                    check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall"] + inc + [go_src, "-o", go_exe, "-L" + HERE, "-lkc_b200backend", "-lkatacoffee_b200",
+                    "-Wl,-rpath," + HERE], check=True)
     return lib, exe
 
 

@@ -126,6 +126,7 @@ PROTOTYPES = {
     "kc_handle_uses_bf16": (C.c_int, [vp]),
     "kc_handle_operand_format": (C.c_int, [vp]),
     "kc_forward": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "kc_forward_rows": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
     "kc_handle_read_outputs": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "kc_handle_launch_count": (C.c_int64, [vp]),
     "kc_handle_trunk_time": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

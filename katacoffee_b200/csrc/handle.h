@@ -10,6 +10,8 @@ struct Fp32Buffers {
 };
 }  // namespace kc
 
+namespace kc { struct RowStaging; }
+
 struct kc_handle {
   kc_ctx* ctx = nullptr;
   const kc_model* model = nullptr;
@@ -39,6 +41,7 @@ struct kc_handle {
   std::vector<cudaEvent_t> evPool;
   int evUsed = 0;
   int lastN = 0;
+  kc::RowStaging* rows = nullptr;   // kc_forward_rows: page-locked staging + gather / scatter worker threads, created on first use
 };
 
 namespace kc {

@@ -29,6 +29,7 @@ float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* symmetry_dev, const int* nDev = nullptr, int rowOffset = 0,
                       bool symIsLocal = false);   // nDev, rowOffset: bf16 path only; symIsLocal: symmetry_dev[0] belongs to row rowOffset
 int handleCheckAbort(kc_handle* h);   // after a synchronise
+int handleTilesPerItem(const kc_handle* h);   // tensor path: activation tiles one CTA work item holds (TrunkCfg::NT)
 bool handleCanLeaveRegisters(const kc_handle* h);
 void handleLeaveRegisters(kc_handle* h, bool on);   // bf16 pair-mode trunk: use the setmaxnreg variant (16 k registers per SM stay free)
 // NNEvaluator::evaluate post-processing (nneval.cpp:702-815) of the handle's last outputs, on `stream`

@@ -1226,6 +1226,8 @@ void handleTileConstants(const kc_handle* h, float k, uint32_t* one, uint32_t* k
   *one = a; *kBits = b;
 }
 
+int handleTilesPerItem(const kc_handle* h) { return h->model->trunk && h->model->trunk->cfg != 0 ? Cfg192::NT : Cfg128::NT; }
+
 static bool trunkUsesPairs() { static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }(); return usePair; }
 // true if this handle's trunk kernel has a variant that leaves registers to co-resident kernels (pair mode, trunks up to 128 channels)
 bool handleCanLeaveRegisters(const kc_handle* h) { return h->bf16 && h->model->trunk && h->model->trunk->cfg == 0 && trunkUsesPairs(); }

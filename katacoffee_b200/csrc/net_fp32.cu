@@ -6,9 +6,14 @@
 // within 1e-4; it also backs the layer-level hooks (nninterface.h:127-169).  The production path
 // is the bf16 tcgen05 trunk in net_bf16.cu; this file owns the handle and dispatches to it.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "handle.h"
 
@@ -386,6 +391,120 @@ int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sy
 
 using namespace kc;
 
+namespace kc {
+// kc_forward / kc_forward_rows on the tensor path are pipelined over row chunks: H2D of chunk i+1 and D2H of chunk i-1 overlap
+// the trunk kernel of chunk i (three streams, one event pair per chunk).  A chunk is a whole number of waves (rows that give every
+// SM one work item).  Returns the chunk sizes in waves.
+static std::vector<int> forwardChunkWaves(const kc_handle* h, int n, int* waveRows, bool hostGather = false) {
+  const int NB = boardsPerTile(h->W, h->H);
+  const int NT = handleTilesPerItem(h);
+  const int wave = NT * NB * h->ctx->smCount;
+  *waveRows = wave;
+  // Tapered schedule (in waves): a small first chunk so that compute starts after a short copy, a small last chunk so
+  // that little is left to copy back when the last kernel ends: 16 waves -> 1,3,11,1.
+  const int totalWaves = (n + wave - 1) / wave;
+  std::vector<int> sizes;
+  if(hostGather && !getenv("KC_FORWARD_SCHEDULE")) {
+    // kc_forward_rows: the host gathers chunk i+1 and scatters chunk i-1 while chunk i is on the device, so the chunks are even and
+    // small enough that the first gather and the last scatter -- the two steps nothing overlaps -- stay short
+    // Worker threads gather different chunks at the same time, so chunk c only has to be ready when the device gets to it: the
+    // first chunks are one wave (the device starts after one short gather), then they grow (every chunk costs ~12 runtime calls on
+    // the enqueueing thread), and the last one is a single wave again (its copy back and scatter overlap nothing).
+    int left = totalWaves;
+    const int ramp[] = {1, 1, 2};
+    for(int i = 0; i < 3 && left > 1; i++) { const int v = std::min(ramp[i], left - 1); sizes.push_back(v); left -= v; }
+    while(left > 1) { const int v = std::min(4, left - 1); sizes.push_back(v); left -= v; }
+    if(left > 0) sizes.push_back(left);
+    return sizes;
+  }
+  if(const char* env = getenv("KC_FORWARD_SCHEDULE")) {   // diagnostic override: chunk sizes in waves, e.g. "1,3,6,5,1" (the rest goes to a last chunk)
+    int left = totalWaves;
+    for(const char* q = env; *q && left > 0;) {
+      const int v = std::max(1, std::min(left, atoi(q)));
+      sizes.push_back(v); left -= v;
+      while(*q && *q != ',') q++;
+      if(*q == ',') q++;
+    }
+    if(left > 0) sizes.push_back(left);
+  } else if(totalWaves >= 8) {
+    // 1, 3, the bulk, 1: every chunk boundary costs a kernel prologue + the un-overlapped epilogue of its last work item
+    // (about 25 us), so few chunks; measured at 16 waves: 1,2,4,4,4,1 6.63 / 1,2,4,8,1 6.64 / 1,4,10,1 6.64 / 1,3,11,1 6.75 M evals/s
+    sizes.push_back(1); sizes.push_back(3); sizes.push_back(totalWaves - 5); sizes.push_back(1);
+  } else {
+    for(int w = 0; w < totalWaves; w += 2) sizes.push_back(std::min(2, totalWaves - w));
+  }
+  return sizes;
+}
+
+// ---- kc_forward_rows: scattered host rows in, scattered outputs back ------------------------------------------------------------
+// Worker threads for the host-side gather / scatter.  One wake-up per call: a job is a function every worker (and the caller) runs
+// once; inside, the threads take whole row chunks from shared atomic counters, so there is no fork / join per chunk.
+struct RowWorkers {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable wake, done;
+  const std::function<void()>* job = nullptr;
+  int generation = 0, pending = 0;
+  bool stop = false;
+  explicit RowWorkers(int n) {
+    for(int i = 0; i < n; i++)
+      threads.emplace_back([this] {
+        int seen = 0;
+        for(;;) {
+          std::unique_lock<std::mutex> lk(m);
+          wake.wait(lk, [&] { return stop || generation != seen; });
+          if(stop) return;
+          seen = generation;
+          const std::function<void()>* f = job;
+          lk.unlock();
+          (*f)();
+          lk.lock();
+          if(--pending == 0) done.notify_one();
+        }
+      });
+  }
+  ~RowWorkers() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    wake.notify_all();
+    for(std::thread& t : threads) t.join();
+  }
+  void start(const std::function<void()>& f) {   // f must stay alive until finish() returns
+    if(threads.empty()) return;
+    { std::lock_guard<std::mutex> lk(m); job = &f; pending = (int)threads.size(); generation++; }
+    wake.notify_all();
+  }
+  void finish() {
+    if(threads.empty()) return;
+    std::unique_lock<std::mutex> lk(m);
+    done.wait(lk, [&] { return pending == 0; });
+  }
+};
+struct RowStaging {
+  float *spatial = nullptr, *global = nullptr, *policy = nullptr, *value = nullptr, *misc = nullptr, *own = nullptr;   // page-locked, [maxBatch] rows
+  int8_t* sym = nullptr;
+  RowWorkers workers;
+  explicit RowStaging(int nWorkers) : workers(nWorkers) {}
+  ~RowStaging() { cudaFreeHost(spatial); cudaFreeHost(global); cudaFreeHost(policy); cudaFreeHost(value); cudaFreeHost(misc); cudaFreeHost(own); cudaFreeHost(sym); }
+};
+void freeRowStaging(kc_handle* h) { delete h->rows; h->rows = nullptr; }
+
+static int rowStaging(kc_handle* h) {
+  if(h->rows) return 0;
+  static const int nEnv = [] { const char* e = getenv("KC_FORWARD_ROWS_THREADS"); return e ? atoi(e) : -1; }();
+  const int hc = (int)std::thread::hardware_concurrency();
+  const int nThreads = nEnv >= 0 ? nEnv : std::max(1, std::min(4, hc > 0 ? hc / 2 : 2));   // gather / scatter workers beside the caller (which enqueues)
+  RowStaging* r = new RowStaging(h->maxBatch >= 4096 ? nThreads : 0);
+  h->rows = r;
+  const size_t B = (size_t)h->maxBatch, HW = (size_t)h->W * h->H;
+  KC_CUDA(cudaHostAlloc(&r->spatial, B * 15 * HW * 4, cudaHostAllocDefault)); KC_CUDA(cudaHostAlloc(&r->global, B * 4, cudaHostAllocDefault));
+  KC_CUDA(cudaHostAlloc(&r->policy, B * 4 * HW * 4, cudaHostAllocDefault)); KC_CUDA(cudaHostAlloc(&r->value, B * 8, cudaHostAllocDefault));
+  KC_CUDA(cudaHostAlloc(&r->misc, B * 8, cudaHostAllocDefault)); KC_CUDA(cudaHostAlloc(&r->own, B * HW * 4, cudaHostAllocDefault));
+  KC_CUDA(cudaHostAlloc(&r->sym, B, cudaHostAllocDefault));
+  return 0;
+}
+
+}  // namespace kc
+
 extern "C" {
 
 int kc_device_count(int* count) {
@@ -539,6 +658,7 @@ int kc_handle_destroy(kc_handle* h) {
   cudaFree(f.in); cudaFree(f.global); cudaFree(f.mask); cudaFree(f.maskSum); cudaFree(f.trunk); cudaFree(f.tip); cudaFree(f.a); cudaFree(f.b);
   cudaFree(f.c); cudaFree(f.pool); cudaFree(f.bias);
   freeTrunkBuffers(h);
+  freeRowStaging(h);
   if(h->ev0) cudaEventDestroy(h->ev0);
   if(h->ev1) cudaEventDestroy(h->ev1);
   if(h->stream) cudaStreamDestroy(h->stream);
@@ -603,28 +723,8 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
   if(h->bf16) {
     // Pipelined over row chunks: H2D of chunk i+1 and D2H of chunk i-1 overlap the trunk kernel of chunk i
     // (three streams, one event pair per chunk).  A chunk is a whole number of CTA work items per SM.
-    const int NB = boardsPerTile(h->W, h->H);
-    const int wave = 2 * NB * h->ctx->smCount;                 // rows that give every SM one work item
-    // Tapered schedule (in waves): a small first chunk so that compute starts after a short copy, a small last chunk so
-    // that little is left to copy back when the last kernel ends: 16 waves -> 1,3,11,1.
-    const int totalWaves = (n + wave - 1) / wave;
-    std::vector<int> sizes;
-    if(const char* env = getenv("KC_FORWARD_SCHEDULE")) {   // diagnostic override: chunk sizes in waves, e.g. "1,3,6,5,1" (the rest goes to a last chunk)
-      int left = totalWaves;
-      for(const char* q = env; *q && left > 0;) {
-        const int v = std::max(1, std::min(left, atoi(q)));
-        sizes.push_back(v); left -= v;
-        while(*q && *q != ',') q++;
-        if(*q == ',') q++;
-      }
-      if(left > 0) sizes.push_back(left);
-    } else if(totalWaves >= 8) {
-      // 1, 3, the bulk, 1: every chunk boundary costs a kernel prologue + the un-overlapped epilogue of its last work item
-      // (about 25 us), so few chunks; measured at 16 waves: 1,2,4,4,4,1 6.63 / 1,2,4,8,1 6.64 / 1,4,10,1 6.64 / 1,3,11,1 6.75 M evals/s
-      sizes.push_back(1); sizes.push_back(3); sizes.push_back(totalWaves - 5); sizes.push_back(1);
-    } else {
-      for(int w = 0; w < totalWaves; w += 2) sizes.push_back(std::min(2, totalWaves - w));
-    }
+    int wave = 0;
+    const std::vector<int> sizes = forwardChunkWaves(h, n, &wave);
     const int numChunks = (int)sizes.size();
     while((int)h->chunkEvents.size() < 2 * numChunks) {
       cudaEvent_t e;
@@ -667,6 +767,118 @@ int kc_forward(kc_handle* h, int n, const float* spatial, const float* global, c
   if(ownership) KC_CUDA(cudaMemcpyAsync(ownership, h->d_own, (size_t)n * HW * 4, cudaMemcpyDeviceToHost, st));
   KC_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+// NeuralNet::getOutput over rows that lie scattered in host memory (the NNResultBuf / NNOutput objects of nneval.h:45-65,
+// nninputs.h:75-118): the gather into page-locked staging, the copies, the kernels and the scatter of chunk i run while the host
+// gathers chunk i+1 and scatters chunk i-1.  Same results as kc_forward on the gathered rows, bit for bit.
+int kc_forward_rows(kc_handle* h, int n, const float* const* spatialRows, const float* const* globalRows, const int8_t* symmetry,
+                    float* const* policyRows, float* const* scalarRows, float* const* ownerRows) {
+  KC_CHECK(h && spatialRows && globalRows && policyRows && scalarRows, "kc_forward_rows: null argument");
+  KC_CHECK(n > 0 && n <= h->maxBatch, "kc_forward_rows: need 0 < n <= maxBatch (nninterface.h:112-117)");
+  KC_CUDA(cudaSetDevice(h->ctx->device));
+  if(symmetry)
+    for(int i = 0; i < n; i++) KC_CHECK(symmetry[i] >= 0 && symmetry[i] < 8, "kc_forward_rows: symmetry must be within 0..7");
+  if(rowStaging(h)) return 1;
+  RowStaging& R = *h->rows;
+  const int HW = h->H * h->W;
+  const size_t rowBytes = (size_t)15 * HW * 4;
+  auto gather = [&](int r0, int rows) {
+    for(int i = r0; i < r0 + rows; i++) {
+      memcpy(R.spatial + (size_t)i * 15 * HW, spatialRows[i], rowBytes);
+      R.global[i] = globalRows[i][0];
+      R.sym[i] = symmetry ? symmetry[i] : 0;
+    }
+  };
+  auto scatter = [&](int r0, int rows) {
+    for(int i = r0; i < r0 + rows; i++) {
+      memcpy(policyRows[i], R.policy + (size_t)i * 4 * HW, (size_t)4 * HW * 4);
+      float* sc = scalarRows[i];
+      sc[0] = R.value[2 * i]; sc[1] = R.value[2 * i + 1]; sc[2] = R.misc[2 * i]; sc[3] = R.misc[2 * i + 1];
+      if(ownerRows && ownerRows[i]) memcpy(ownerRows[i], R.own + (size_t)i * HW, (size_t)HW * 4);
+    }
+  };
+  if(!h->bf16) {   // check path: no pipeline
+    gather(0, n);
+    if(kc_forward(h, n, R.spatial, R.global, symmetry ? R.sym : nullptr, R.policy, R.value, R.misc, R.own)) return 1;
+    scatter(0, n);
+    return 0;
+  }
+  cudaStream_t st = h->stream;
+  const int rawNHWC = (h->flags & KC_FLAG_INPUTS_NHWC) ? 1 : 0;
+  int wave = 0;
+  const std::vector<int> sizes = forwardChunkWaves(h, n, &wave, true);
+  const int numChunks = (int)sizes.size();
+  while((int)h->chunkEvents.size() < 3 * numChunks) {
+    cudaEvent_t e;
+    KC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->chunkEvents.push_back(e);
+  }
+  std::vector<int> start(numChunks + 1, 0);
+  for(int c = 0; c < numChunks; c++) start[c + 1] = std::min(n, start[c] + sizes[c] * wave);
+  // Host side: every thread takes whole chunks -- first to gather (in chunk order), then, once a chunk's copy back has been enqueued
+  // and has finished, to scatter.  The caller's thread enqueues chunk c as soon as it is gathered, then joins the scattering.
+  std::vector<std::atomic<int>> gathered(numChunks), enqueued(numChunks);
+  for(int c = 0; c < numChunks; c++) { gathered[c].store(0); enqueued[c].store(0); }
+  std::atomic<int> nextGather{0}, nextScatter{0}, failed{0};
+  const int device = h->ctx->device;
+  auto scatterLoop = [&]() {
+    for(int c; (c = nextScatter.fetch_add(1)) < numChunks;) {
+      while(!enqueued[c].load(std::memory_order_acquire)) {
+        if(failed.load()) return;
+        std::this_thread::yield();
+      }
+      if(cudaEventSynchronize(h->chunkEvents[3 * c + 2]) != cudaSuccess) { failed.store(1); return; }
+      scatter(start[c], start[c + 1] - start[c]);
+    }
+  };
+  const std::function<void()> workerJob = [&]() {
+    cudaSetDevice(device);
+    for(int c; (c = nextGather.fetch_add(1)) < numChunks;) {
+      gather(start[c], start[c + 1] - start[c]);
+      gathered[c].store(1, std::memory_order_release);
+    }
+    scatterLoop();
+  };
+  const bool useWorkers = numChunks >= 3 && !R.workers.threads.empty();   // small batches: the caller does everything, no wake-up
+  if(useWorkers) R.workers.start(workerJob);
+  int status = 0;
+  for(int c = 0; c < numChunks && !status; c++) {
+    const int r0 = start[c], rows = start[c + 1] - r0;
+    if(!useWorkers) {
+      if(nextGather.fetch_add(1) == c) { gather(r0, rows); gathered[c].store(1); }
+    }
+    while(!gathered[c].load(std::memory_order_acquire)) std::this_thread::yield();
+    auto enqueue = [&]() -> int {
+      if(rows <= 0) return 0;
+      KC_CUDA(cudaMemcpyAsync(h->d_raw + (size_t)r0 * 15 * HW, R.spatial + (size_t)r0 * 15 * HW, (size_t)rows * rowBytes, cudaMemcpyHostToDevice, h->h2dStream));
+      KC_CUDA(cudaMemcpyAsync(h->d_rawGlobal + r0, R.global + r0, (size_t)rows * 4, cudaMemcpyHostToDevice, h->h2dStream));
+      if(symmetry) KC_CUDA(cudaMemcpyAsync(h->d_sym + r0, R.sym + r0, (size_t)rows, cudaMemcpyHostToDevice, h->h2dStream));
+      KC_CUDA(cudaEventRecord(h->chunkEvents[3 * c], h->h2dStream));
+      KC_CUDA(cudaStreamWaitEvent(st, h->chunkEvents[3 * c], 0));
+      if(convertInputToTiles(h, rows, rawNHWC, symmetry ? h->d_sym : nullptr, st, r0)) return 1;
+      if(runTrunkBf16(h, rows, st, symmetry ? h->d_sym : nullptr, r0)) return 1;
+      KC_CUDA(cudaEventRecord(h->chunkEvents[3 * c + 1], st));
+      KC_CUDA(cudaStreamWaitEvent(h->d2hStream, h->chunkEvents[3 * c + 1], 0));
+      KC_CUDA(cudaMemcpyAsync(R.policy + (size_t)r0 * 4 * HW, h->d_policy + (size_t)r0 * 4 * HW, (size_t)rows * 4 * HW * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+      KC_CUDA(cudaMemcpyAsync(R.value + (size_t)r0 * 2, h->d_value + (size_t)r0 * 2, (size_t)rows * 8, cudaMemcpyDeviceToHost, h->d2hStream));
+      KC_CUDA(cudaMemcpyAsync(R.misc + (size_t)r0 * 2, h->d_misc + (size_t)r0 * 2, (size_t)rows * 8, cudaMemcpyDeviceToHost, h->d2hStream));
+      if(ownerRows) KC_CUDA(cudaMemcpyAsync(R.own + (size_t)r0 * HW, h->d_own + (size_t)r0 * HW, (size_t)rows * HW * 4, cudaMemcpyDeviceToHost, h->d2hStream));
+      KC_CUDA(cudaEventRecord(h->chunkEvents[3 * c + 2], h->d2hStream));
+      return 0;
+    };
+    status = enqueue();
+    if(status) failed.store(1);
+    else enqueued[c].store(1, std::memory_order_release);
+  }
+  if(!status) scatterLoop();
+  if(useWorkers) R.workers.finish();
+  h->lastN = n;
+  if(status) return 1;
+  KC_CHECK(!failed.load(), "kc_forward_rows: a device copy failed");
+  KC_CUDA(cudaStreamSynchronize(h->d2hStream));
+  KC_CUDA(cudaStreamSynchronize(st));
+  return checkTrunkAbort(h);
 }
 
 // ---- layer hooks (nninterface.h:127-169) ---------------------------------------------------------

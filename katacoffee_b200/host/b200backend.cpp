@@ -16,6 +16,7 @@
 #include "reftypes.h"
 #endif
 
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -24,16 +25,6 @@
 #include "katacoffee_b200.h"
 
 using namespace std;
-
-// threads for the row gather / scatter of large batches: the machine's, at most 12 (KC_SHIM_THREADS overrides; 8 / 12 / 16 measured 4.1 / 3.7 / 3.8 ms per 18,944-row call)
-static int gatherThreads() {
-  static const int n = [] {
-    const char* e = getenv("KC_SHIM_THREADS");
-    int t = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return t < 1 ? 1 : t > 12 ? 12 : t;
-  }();
-  return n;
-}
 
 static void kcCheck(int status, const char* what) {
   if(status != 0) throw StringError(string("B200 backend: ") + what + ": " + kc_last_error());
@@ -131,20 +122,10 @@ struct ComputeHandle {
 
 struct InputBuffers {
   int maxBatchSize, singleInputElts, singleInputGlobalElts, policySize, hw;
-  // host staging in the batch layout kc_forward takes; page-locked (kc_host_alloc) so that its chunked copies are asynchronous DMA
-  template <class T> struct Pinned {
-    T* p = nullptr; size_t n = 0;
-    void resize(size_t count) {
-      void* v = nullptr;
-      kcCheck(kc_host_alloc(count * sizeof(T) + 16, &v), "kc_host_alloc");
-      p = static_cast<T*>(v); n = count;
-    }
-    ~Pinned() { kc_host_free(p); }
-    T* data() { return p; }
-    T& operator[](size_t i) { return p[i]; }
-  };
-  Pinned<float> spatial, global, policy, value, misc, ownership;
-  Pinned<int8_t> symmetry;
+  // per-batch pointer tables handed to kc_forward_rows; the row staging itself is page-locked memory owned by the compute handle
+  vector<const float*> spatialRows, globalRows;
+  vector<float*> policyRows, scalarRows, ownerRows;
+  vector<int8_t> symmetry;
 };
 
 namespace NeuralNet {
@@ -219,9 +200,7 @@ InputBuffers* createInputBuffers(const LoadedModel* loadedModel, int maxBatchSiz
   b->singleInputElts = loadedModel->modelDesc.numInputChannels * b->hw;
   b->singleInputGlobalElts = loadedModel->modelDesc.numInputGlobalChannels;
   b->policySize = 4 * b->hw;
-  b->spatial.resize((size_t)maxBatchSize * b->singleInputElts); b->global.resize((size_t)maxBatchSize * b->singleInputGlobalElts);
-  b->policy.resize((size_t)maxBatchSize * b->policySize); b->value.resize((size_t)maxBatchSize * 2); b->misc.resize((size_t)maxBatchSize * 2);
-  b->ownership.resize((size_t)maxBatchSize * b->hw); b->symmetry.resize(maxBatchSize);
+  b->symmetry.resize(maxBatchSize);   // the row staging itself is page-locked memory owned by the compute handle (kc_forward_rows)
   return b;
 }
 void freeInputBuffers(InputBuffers* b) { delete b; }
@@ -232,26 +211,24 @@ void getOutput(ComputeHandle* h, InputBuffers* b, int numBatchEltsFilled, NNResu
   for(int i = 0; i < n; i++)
     if(inputBufs[i]->rowSpatialSize != b->singleInputElts || inputBufs[i]->rowGlobalSize != b->singleInputGlobalElts)
       throw StringError("B200 backend: row sizes do not match the model");
-  // gather the rows of the batch (every backend does this copy, e.g. eigenbackend.cpp:1700-1730); large batches on several threads
-#pragma omp parallel for schedule(static) num_threads(gatherThreads()) if(n >= 1024)
+  // Rows and outputs stay where they are: the C ABI takes the NNResultBuf / NNOutput pointers and gathers, copies, evaluates and
+  // scatters chunk by chunk (kc_forward_rows), so the host copies every backend makes here (e.g. eigenbackend.cpp:1700-1730,
+  // 1755-1843) overlap the device work instead of running before and after it.
+  static_assert(offsetof(NNOutput, whiteLossProb) == offsetof(NNOutput, whiteWinProb) + 4 && offsetof(NNOutput, varTimeLeft) == offsetof(NNOutput, whiteWinProb) + 8 &&
+                offsetof(NNOutput, shorttermWinlossError) == offsetof(NNOutput, whiteWinProb) + 12, "NNOutput's four scalars are contiguous (nninputs.h:75-90)");
+  b->spatialRows.resize(n); b->globalRows.resize(n); b->policyRows.resize(n); b->scalarRows.resize(n); b->ownerRows.resize(n);
+  bool anyOwner = false;
   for(int i = 0; i < n; i++) {
     const NNResultBuf* r = inputBufs[i];
-    memcpy(&b->spatial[(size_t)i * b->singleInputElts], r->rowSpatial, sizeof(float) * b->singleInputElts);
-    memcpy(&b->global[(size_t)i * b->singleInputGlobalElts], r->rowGlobal, sizeof(float) * b->singleInputGlobalElts);
-    b->symmetry[i] = (int8_t)r->symmetry;
-  }
-  kcCheck(kc_forward(h->handle, n, b->spatial.data(), b->global.data(), b->symmetry.data(), b->policy.data(), b->value.data(), b->misc.data(),
-                     b->ownership.data()), "kc_forward");
-#pragma omp parallel for schedule(static) num_threads(gatherThreads()) if(n >= 1024)
-  for(int i = 0; i < n; i++) {
     NNOutput* o = outputs[i];
+    b->spatialRows[i] = r->rowSpatial; b->globalRows[i] = r->rowGlobal; b->symmetry[i] = (int8_t)r->symmetry;
     // logits, already in NNPos order and inverse-symmetrised; nnHash / noisedPolicyProbs are not touched (eigenbackend.cpp:1765-1767)
-    memcpy(o->policyProbs, &b->policy[(size_t)i * b->policySize], sizeof(float) * b->policySize);
-    o->whiteWinProb = b->value[2 * i]; o->whiteLossProb = b->value[2 * i + 1];
-    o->varTimeLeft = b->misc[2 * i]; o->shorttermWinlossError = b->misc[2 * i + 1];
+    b->policyRows[i] = o->policyProbs; b->scalarRows[i] = &o->whiteWinProb; b->ownerRows[i] = o->whiteOwnerMap;
+    anyOwner = anyOwner || o->whiteOwnerMap != nullptr;
     o->nnXLen = h->nnXLen; o->nnYLen = h->nnYLen;
-    if(o->whiteOwnerMap != nullptr) memcpy(o->whiteOwnerMap, &b->ownership[(size_t)i * b->hw], sizeof(float) * b->hw);
   }
+  kcCheck(kc_forward_rows(h->handle, n, b->spatialRows.data(), b->globalRows.data(), b->symmetry.data(), b->policyRows.data(), b->scalarRows.data(),
+                          anyOwner ? b->ownerRows.data() : nullptr), "kc_forward_rows");
 }
 
 static kc_ctx* testCtx() {

@@ -158,6 +158,29 @@ int main() {
     printf("NeuralNet::getOutput, %d rows per call (b10c128 shape, bf16): %.3f ms per call, %.3f M evals/s incl. the host gather / scatter\n", B,
            sec / reps * 1e3, B * reps / sec / 1e6);
     for(int i = 0; i < N; i++) REQUIRE(memcmp(outs[i].policyProbs, outs[i + N * 8].policyProbs, 4 * HW * 4) == 0);   // same row, same symmetry
+    {
+      // the pipelined, multi-threaded gather / scatter (kc_forward_rows) against one plain kc_forward over the gathered rows: every
+      // row of the large batch bit for bit, with owner maps on every third row
+      std::vector<std::vector<float>> owner(B);
+      for(int i = 0; i < B; i += 3) { owner[i].assign(HW, -7.f); outs[i].whiteOwnerMap = owner[i].data(); }
+      NeuralNet::getOutput(h, ib, B, bufPtrs.data(), outPtrs);
+      kc_ctx* kc = nullptr; kc_model* km = nullptr; kc_handle* kh = nullptr;
+      REQUIRE(kc_ctx_create(0, &kc) == 0);
+      REQUIRE(kc_model_create(kc, static_cast<const kc_model_desc*>(NeuralNet::getB200ModelDescPOD(big)), &km) == 0);
+      REQUIRE(kc_handle_create(kc, km, B, W, H, 0u, &kh) == 0);
+      std::vector<float> sp((size_t)B * 15 * HW), gl(B, 4.0f), pol((size_t)B * 4 * HW), val(2 * B), misc(2 * B), own((size_t)B * HW);
+      std::vector<int8_t> sym(B);
+      for(int i = 0; i < B; i++) { memcpy(&sp[(size_t)i * 15 * HW], spatial[i % N].data(), 15 * HW * 4); sym[i] = (int8_t)(i % 8); }
+      REQUIRE(kc_forward(kh, B, sp.data(), gl.data(), sym.data(), pol.data(), val.data(), misc.data(), own.data()) == 0);
+      for(int i = 0; i < B; i++) {
+        REQUIRE(memcmp(outs[i].policyProbs, &pol[(size_t)i * 4 * HW], 4 * HW * 4) == 0);
+        REQUIRE(outs[i].whiteWinProb == val[2 * i] && outs[i].whiteLossProb == val[2 * i + 1]);
+        REQUIRE(outs[i].varTimeLeft == misc[2 * i] && outs[i].shorttermWinlossError == misc[2 * i + 1]);
+        if(i % 3 == 0) REQUIRE(memcmp(owner[i].data(), &own[(size_t)i * HW], HW * 4) == 0);
+      }
+      for(int i = 0; i < B; i += 3) outs[i].whiteOwnerMap = nullptr;
+      kc_handle_destroy(kh); kc_model_destroy(km); kc_ctx_destroy(kc);
+    }
     NeuralNet::freeInputBuffers(ib); NeuralNet::freeComputeHandle(h); NeuralNet::freeComputeContext(ctx); NeuralNet::freeLoadedModel(big);
   }
   bool threw = false;
