@@ -195,6 +195,40 @@ def evaluator_arm(net, W, H):
         return {"error": repr(e)[:300]}
 
 
+def getoutput_arm(net, size, batches, reps=300):
+    """NeuralNet::getOutput of the C++ drop-in (host/b200backend.cpp) driven natively: tests/cpp/bench_getoutput.cpp in its own process,
+    NNResultBuf rows in host memory in, NNOutput logits in host memory out.  Never fatal."""
+    import tempfile
+    exe = os.path.join(ROOT, "katacoffee_b200", "host", "bench_getoutput")
+    try:
+        from katacoffee_b200 import backend, modeldesc
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, net + ".bin.gz")
+            backend.writeModelFile(modeldesc.Model(net, seed=11), path)
+            p = subprocess.run([exe, path, "--size", str(size), "--batches", ",".join(str(b) for b in batches), "--reps", str(reps)],
+                               capture_output=True, text=True, timeout=240)
+        if p.returncode != 0:
+            return {"error": (p.stderr or p.stdout)[-300:]}
+        return json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def config_6x6_arm(steps, warmup):
+    """BASELINE configs[4] (6x6 k=4, b15c192) at reduced steps: this script again in a child process with --config 6x6, without the
+    self-play / CPU / evaluator arms.  Returns the child's value / e2e / roofline / clocks.  Never fatal."""
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "6x6", "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline",
+                            "--no-selfplay", "--no-evaluator", "--no-extra-configs"], capture_output=True, text=True, timeout=600)
+        if p.returncode != 0:
+            return {"error": (p.stderr or p.stdout)[-300:]}
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+        return {k: d[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "e2e", "getoutput_cpp", "clocks", "roofline",
+                                  "roofline_rules_features", "gpu_launches") if k in d}
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -249,8 +283,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-evaluator", action="store_true", help="skip the evaluator front-end arm (native client threads in a child process)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the batch1024 (BASELINE configs[2]) and config_6x6 (configs[4]) objects")
     ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
-    ap.add_argument("--selfplay-moves", type=int, default=1, help="moves per game timed in the self-play arm")
+    ap.add_argument("--selfplay-moves", type=int, default=8, help="consecutive moves per game lane timed in the self-play arm")
     args = ap.parse_args()
     select_config(args.config)
     args.games = args.games or GAMES_PER_GPU
@@ -300,6 +335,22 @@ def main():
     total_evals = G * args.steps * world
     value = total_evals / (ms_max * 1e-3)
 
+    # BASELINE configs[2] as stated: 1024 rows per call.  Device-resident first (1024 games stepped and evaluated per ply) ...
+    batch1024 = None
+    if rank == 0 and world == 1 and not args.no_extra_configs and args.config == "5x5":
+        h1k = backend.createComputeHandle(ctx, lm, 1024, W, H)
+        g1k = backend.Games(ctx, 1024, W, H, WINLEN)
+        g1k.reset(seed=SEED, autoRefill=True)
+        g1k.runTimed(h1k, 10, L2_FLUSH_BYTES)
+        h1k.trunkTime()
+        _, ms1k = g1k.runTimed(h1k, 50, L2_FLUSH_BYTES)
+        t1k_ms, t1k_n = h1k.trunkTime()
+        batch1024 = {"rows_per_call": 1024, "net": NET, "board": f"{W}x{H}",
+                     "device": {"evals_per_s": 1024 * 50 / (ms1k * 1e-3), "ms_per_step": ms1k / 50, "trunk_kernel_ms": t1k_ms / max(t1k_n, 1),
+                                "what": "rules step + fp16 tiles + trunk per ply for 1024 resident games, CUDA events, L2 flushed between steps; "
+                                        "1024 rows = 128 work items of 8 boards on 148 SMs: under one wave, latency-bound"}}
+        g1k.close(); h1k.close()
+
     # rules+features alone (the HBM-bound kernel), fp32 NCHW planes + masks + hashes: secondary roofline
     games_rf = backend.Games(ctx, 65536, W, H, WINLEN)
     games_rf.reset(seed=SEED, autoRefill=True)
@@ -336,31 +387,39 @@ def main():
     # the same G games under the batched device tree search: per iteration every game descends to one leaf and the G
     # leaves are one batch through the hot path; a move = SELFPLAY_VISITS iterations
     def selfplay_arm(label, **search_kw):
-        search = backend.Search(ctx, handle, G, W, H, WINLEN, maxVisits=args.visits, temperaturePlies=30, autoRefill=True, **search_kw)
-        search.reset(seed=SEED, firstGameId=shard.first_game_id(rank))
-        # steady-state mix of a self-play run: game g starts the timed move after (g mod STAGGER) random-legal plies, as
-        # games that were refilled at different times do (movePos -2 = the counter-RNG move, -1 = stay)
-        lane = np.arange(G)
-        for t in range(SELFPLAY_STAGGER):
-            search.games.step(np.where(lane % SELFPLAY_STAGGER > t, -2, -1).astype(np.int16))
-        # one untimed move first: with tree re-use it builds the trees whose chosen subtrees the timed move re-uses, as
-        # every move of a running self-play does (Search::makeMove)
-        search.play(1)
-        handle.trunkTime()
-        barrier()
-        sp_stats, _, sp_ms = search.play(args.selfplay_moves)
-        barrier()
-        sp_ms_max = shard.max_over_ranks(sp_ms, "cuda")
-        sp = shard.reduce_stats([sp_stats.movesPlayed, sp_stats.visits, sp_stats.netEvals, sp_stats.terminalVisits, sp_stats.gamesFinished,
-                                 sp_stats.batchRows, sp_stats.transpositionHits, sp_stats.catchUpVisits], "cuda")
-        out = {"metric": "selfplay_moves_per_s", "value": sp[0] / (sp_ms_max * 1e-3), "unit": "moves/s", "visits_per_move": args.visits,
-               "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves, "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / (sp_ms_max * 1e-3),
-               "batch_rows_per_s": sp[5] / (sp_ms_max * 1e-3), "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
-               "transposition_fraction_of_visits": (sp[6] + sp[7]) / max(sp[1], 1),
-               "ms_per_move_batch": sp_ms_max / args.selfplay_moves, "games_finished": int(sp[4]),
-               "search": label, "kernel_launches": int(search.launchCount())}
-        search.close()
-        return out
+        # kc_selfplay_run (csrc/selfplay.cpp): this rank's device as one native search pool.  Timed on the host clock around the
+        # whole loop: `--selfplay-moves` consecutive moves per game lane with refill of finished games, the finished games'
+        # training rows emitted on the device (k_emit_rows), read back and written as the reference's .npz files by the pool's
+        # writer thread -- all inside the timed region.  One untimed move first: with tree re-use it builds the trees whose
+        # chosen subtrees the timed moves re-use, as every move of a running self-play does (Search::makeMove).
+        import shutil
+        import tempfile
+        out_dir = tempfile.mkdtemp(prefix="kc_selfplay_")
+        chunk = max(1, min(4, args.selfplay_moves))
+        try:
+            barrier()
+            tot, rep = backend.selfplayRun(model, [local], G, W, H, WINLEN, moves=args.selfplay_moves, movesPerChunk=chunk, warmupMoves=1,
+                                           staggerPlies=SELFPLAY_STAGGER, maxRowsPerChunk=G * 3 * chunk, outputDir=out_dir, seed=SEED,
+                                           firstGameId=shard.first_game_id(rank), maxVisits=args.visits, autoRefill=1, temperaturePlies=30, **search_kw)
+            barrier()
+            files = len(os.listdir(out_dir))
+        finally:
+            shutil.rmtree(out_dir, ignore_errors=True)
+        sec = shard.max_over_ranks(rep.wallSeconds, "cuda")
+        dev_ms = shard.max_over_ranks(rep.deviceMsMax, "cuda")
+        sp = shard.reduce_stats([tot.movesPlayed, tot.visits, tot.netEvals, tot.terminalVisits, tot.gamesFinished, tot.batchRows, tot.transpositionHits,
+                                 tot.catchUpVisits, rep.rowsWritten, rep.rowsDropped, rep.bytesWritten, rep.kernelLaunches, files], "cuda")
+        return {"metric": "selfplay_moves_per_s", "value": sp[0] / sec, "unit": "moves/s", "visits_per_move": args.visits,
+                "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves,
+                "timed_region": "host clock around kc_selfplay_run's move loop: search, move choice, refill of finished games, k_emit_rows, row read-back "
+                                "and kc_training_write_npz (writer thread) all inside; max over ranks",
+                "seconds": sec, "device_seconds": dev_ms * 1e-3, "moves_per_s_device_time_only": sp[0] / (dev_ms * 1e-3),
+                "start_plies": f"game g starts at ply g mod {SELFPLAY_STAGGER} (random-legal prefix)", "visits_per_s": sp[1] / sec,
+                "batch_rows_per_s": sp[5] / sec, "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
+                "transposition_fraction_of_visits": (sp[6] + sp[7]) / max(sp[1], 1),
+                "ms_per_move_batch": sec * 1e3 / args.selfplay_moves, "games_finished": int(sp[4]),
+                "training_rows_written": int(sp[8]), "training_rows_dropped": int(sp[9]), "npz_files": int(sp[12]), "npz_bytes": int(sp[10]),
+                "search": label, "kernel_launches": int(sp[11])}
 
     selfplay = selfplay_graph = None
     if not args.no_selfplay:
@@ -382,23 +441,42 @@ def main():
         flops = modeldesc.flops_per_eval(NET, hw)
         trunk_avg_ms = trunk_ms / max(trunk_n, 1)
         achieved = flops * G / (trunk_avg_ms * 1e-3) / 1e12
+        # Which measured peak bounds the trunk kernel: every launch is timed alone between two events with an L2 flush before it, so
+        # unless the timed region is long enough for the power cap to settle (>= 2 s) the burst figure is the honest denominator.
+        region_s = ms_max * 1e-3
+        sustained = region_s >= 2.0
+        peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+        # rules+features: bytes one launch of the 8-ply kernel really moves per game-step = per ply planes 15*HW*4 + sit-hash 16 + legal
+        # 4*LW + status 4 + move 2 (every ply has its own ring slot) + per launch (state 48 B read + 48 B written + global 4) / 8 plies
+        rf_bytes = 15 * hw * 4 + 16 + 4 * ((4 * hw + 31) // 32) + 4 + 2 + (48 + 48 + 4) / 8
+        rf_traffic = (load_traffic("prof_games_multi") or load_traffic("prof_games")) if args.config == "5x5" else None
+        rf_launch_s = 8 * 65536 / rf_steps_s
         line = {
             "metric": "nn_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "config": workload_config(G),
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "kc_forward (NeuralNet::getOutput) with pinned host rows"},
+                    "api": "kc_forward, the C ABI's getOutput entry point, called from Python (ctypes) with pinned host rows in the batch layout; "
+                           "the C++ NeuralNet::getOutput shim over scattered NNResultBuf rows is `getoutput_cpp`"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "trunk_kernel (tcgen05 whole-net forward)", "bound": "tensor", "achieved": achieved,
-                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-                         "traffic": load_traffic("prof_trunk") if args.config == "5x5" else None, "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+            "roofline": {"kernel": "trunk_kernel (tcgen05 whole-net forward, fp16 operands, fp32 accumulation)", "bound": "tensor", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+                         "traffic": load_traffic("prof_trunk") if args.config == "5x5" else None,
+                         "peak_source": peaks["source"] + (" sustained (timed region %.2f s >= 2 s)" % region_s if sustained else
+                                                           " burst (timed region %.2f s < 2 s: every launch timed alone after an L2 flush)" % region_s),
+                         "timed_region_s": region_s, "sm_mhz_median": clocks["sm_mhz"] if clocks else None,
                          "flops_per_eval": flops, "evals_per_launch": G, "avg_launch_ms": trunk_avg_ms, "launches_timed": trunk_n},
-            "roofline_rules_features": {"kernel": "games_multi_split_kernel (rules step + fp32 NCHW planes, 8 plies per launch, producer / consumer warps, 4-slot plane ring) at 65536 games",
+            "roofline_rules_features": {"kernel": "games_multi_split_kernel (rules step + fp32 NCHW planes, 8 plies per launch, producer / consumer warps, "
+                                                  "every ply's planes / masks / status / hashes / moves to its own slot of a 4-slot ring) at 65536 games",
                                         "bound": "hbm", "plies_per_launch": 8,
-                                        "achieved": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                        "frac": rf_steps_s * BYTES_PER_STEP_FP32 / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
-                                        "bytes_per_game_step": BYTES_PER_STEP_FP32, "traffic": (load_traffic("prof_games_multi") or load_traffic("prof_games")) if args.config == "5x5" else None},
+                                        "achieved": rf_steps_s * rf_bytes / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "frac": rf_steps_s * rf_bytes / 1e9 / peaks["hbm_gbs"], "game_steps_per_s": rf_steps_s,
+                                        "bytes_per_game_step": rf_bytes, "bytes_per_launch": rf_bytes * 8 * 65536, "avg_launch_ms": rf_launch_s * 1e3,
+                                        "traffic": rf_traffic,
+                                        "frac_traffic": (rf_traffic / rf_launch_s / 1e9 / peaks["hbm_gbs"]) if rf_traffic else None,
+                                        "survey_bytes_per_game_step": BYTES_PER_STEP_FP32},
             "selfplay": selfplay,
             "selfplay_graph": selfplay_graph,
             "stats": {"game_steps": int(counters[0]), "evals": int(counters[1]), "games_finished": int(counters[2]),
@@ -417,9 +495,24 @@ def main():
                                     "sample": f"{n} positions: oracle rules + fillRowV1 + Winograd/GEMM fp32 {NET} forward (Eigen-algorithm restatement), batch 4 per thread"}
         if world == 1 and not args.no_evaluator and W == H:
             line["evaluator"] = evaluator_arm(NET, W, H)
-        print(json.dumps(line), flush=True)
+        if world == 1 and W == H:
+            # the C++ drop-in itself at the bench batch (and, for the headline configuration, at BASELINE configs[2]'s 1024 rows)
+            go = getoutput_arm(NET, W, [1024, G] if batch1024 is not None else [G])
+            if "batches" in go:
+                by_rows = {b["rows_per_call"]: b for b in go["batches"]}
+                line["getoutput_cpp"] = dict(by_rows[G], api=go["api"])
+                if batch1024 is not None:
+                    batch1024["e2e"] = dict(by_rows[1024], api=go["api"])
+            else:
+                line["getoutput_cpp"] = go
+        if batch1024 is not None:
+            line["batch1024"] = batch1024
     for o in (games, handle, lm, ctx):
         o.close()
+    if rank == 0:
+        if world == 1 and args.config == "5x5" and not args.no_extra_configs:
+            line["config_6x6"] = config_6x6_arm(max(10, min(args.steps, 20)), args.warmup)
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -273,6 +273,10 @@ int kc_games_run_timed(kc_games* g, kc_handle* h, int plies, size_t flushL2Bytes
 /* What the last ply of the last rules+features run (kc_games_run / kc_games_run_timed with h == NULL) left in the device buffers:
  * planes [G][15*H*W] fp32 NCHW, global [G], legal [G][LW], status [G], sitHash [G][2], played [G]; any may be NULL. */
 int kc_games_read_run_outputs(kc_games* g, float* planes, float* global, uint32_t* legal, uint32_t* status, uint64_t* sitHash, int16_t* played);
+/* The same for one of the last four plies of the last rules+features launch (pliesBack 0 = the last ply, 1 = the one before, ...;
+ * must be below min(4, plies the last launch stepped)): every ply of a launch writes its own slot of a 4-slot ring, so per-step masks,
+ * win/draw status words, sit-hashes, moves and (when the run used the plane ring, flushL2Bytes > 0) V1 planes are all delivered. */
+int kc_games_read_run_ply(kc_games* g, int pliesBack, float* planes, uint32_t* legal, uint32_t* status, uint64_t* sitHash, int16_t* played);
 int64_t kc_games_launch_count(const kc_games* g);
 /* Average device time in ms per ply of the rules+features kernel in the last kc_games_run. */
 float kc_games_last_kernel_ms(const kc_games* g);
@@ -384,6 +388,39 @@ int kc_training_write_npz(const char* path, int numRows, int xSize, int ySize, c
                           const int16_t* policyTargetsNCMove, const float* globalTargetsNC, const int8_t* valueTargetsNCHW);
 int kc_search_tree_digest(kc_search* s, uint64_t* digest);
 int64_t kc_search_launch_count(const kc_search* s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-play over several GPUs of one box from one process: one search pool (host thread, context, weights, compute handle,
+ * kc_search of gamesPerDevice games) per device and one data-writer thread per pool -- the reference's one NN server thread +
+ * ComputeHandle per GPU (cpp/program/setup.cpp:167-229, gpuIdxByServerThread) under the game loops and the data-writer thread of
+ * cpp/command/selfplay.cpp:226-260,390-392.  Games never cross devices; pool i plays the game ids firstGameId + i * 2^40 + ...
+ * The timed part plays `moves` moves per game lane in chunks of movesPerChunk; after every chunk the rows of the games that ended
+ * are read back and written as outputDir/poolNN_CCCCCC.npz (kc_training_write_npz) while the next chunk is searched.  At the end
+ * the pools' counters are summed on devices[0] with ONE ncclReduce (NCCL loaded with dlopen("libnccl.so.2"); with one device or
+ * noNccl != 0 they are summed on the host) -- the only exchange of the whole job.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t numDevices;
+  const int32_t* devices;     /* CUDA device indices */
+  int32_t gamesPerDevice, xSize, ySize, winLen;
+  int32_t moves;              /* moves per game lane in the timed part */
+  int32_t movesPerChunk;      /* 0 = one chunk */
+  int32_t warmupMoves;        /* untimed moves first (with reuseTree they build the trees the timed moves re-use); their rows are discarded */
+  int32_t staggerPlies;       /* lane g starts after (g mod staggerPlies) random-legal plies: the mix of a running self-play; 0 = empty boards */
+  int32_t maxRowsPerChunk;    /* device row buffer per pool; 0 = no training rows */
+  int32_t noNccl;             /* 1: sum the counters on the host */
+  uint32_t handleFlags;       /* kc_handle_create flags */
+  uint64_t seed, firstGameId;
+  const char* outputDir;      /* NULL: rows are read back, no file is written */
+} kc_selfplay_config;
+typedef struct {
+  double wallSeconds;         /* the timed part on the host clock: from all pools ready to the last pool's last file closed */
+  double deviceMsMax;         /* max over pools of the device time of its kc_search_play calls */
+  uint64_t rowsWritten, rowsDropped, filesWritten, bytesWritten, kernelLaunches;
+  int32_t reducedWithNccl;
+} kc_selfplay_report;
+int kc_selfplay_run(const kc_selfplay_config* cfg, const kc_model_desc* desc, const kc_search_params* params, kc_search_stats* total,
+                    kc_selfplay_report* report);
 
 
 /* ---------------------------------------------------------------------------------------------

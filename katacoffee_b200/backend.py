@@ -292,6 +292,15 @@ class Games:
                                               ptr(out["sitHash"]), ptr(out["played"])))
         return out
 
+    def readRunPly(self, pliesBack, planes=True):
+        """Outputs of one of the last four plies of the last rules+features launch (0 = last ply): dict(planes, legal, status, sitHash, played)."""
+        G, HW = self.G, self.HW
+        out = dict(planes=np.empty((G, 15 * HW), np.float32) if planes else None, legal=np.empty((G, self.LW), np.uint32),
+                   status=np.empty(G, np.uint32), sitHash=np.empty((G, 2), np.uint64), played=np.empty(G, np.int16))
+        check(lib().kc_games_read_run_ply(self._p, pliesBack, ptr(out["planes"]) if planes else None, ptr(out["legal"]), ptr(out["status"]),
+                                          ptr(out["sitHash"]), ptr(out["played"])))
+        return out
+
     def launchCount(self):
         return int(lib().kc_games_launch_count(self._p))
 
@@ -390,6 +399,25 @@ class Search:
         if self._p:
             lib().kc_search_destroy(self._p)
             self._p = C.c_void_p()
+
+
+def selfplayRun(model, devices, gamesPerDevice, xSize=5, ySize=5, winLen=4, moves=8, movesPerChunk=0, warmupMoves=1, staggerPlies=0,
+                maxRowsPerChunk=0, outputDir=None, seed=0, firstGameId=0, handleFlags=0, noNccl=False, maxVisits=800, **searchOptions):
+    """kc_selfplay_run: self-play on several GPUs from this one process (one search pool + writer thread per device, one ncclReduce
+    of the counters at the end).  searchOptions: kc_search_params fields by name.  Returns (capi.SearchStats totals, capi.SelfplayReport)."""
+    params = capi.SearchParams()
+    params.maxVisits, params.cpuctExploration, params.fpuReductionMax, params.rootFpuReductionMax = maxVisits, 1.0, 0.2, 0.2
+    params.subtreeValueBiasWeightExponent, params.subtreeValueBiasFreeProp = 0.5, 0.8
+    for k, v in searchOptions.items():
+        if k not in dict(capi.SearchParams._fields_):
+            raise TypeError(f"unknown search option {k}")
+        setattr(params, k, v)
+    devs = (C.c_int32 * len(devices))(*devices)
+    cfg = capi.SelfplayConfig(len(devices), devs, gamesPerDevice, xSize, ySize, winLen, moves, movesPerChunk, warmupMoves, staggerPlies,
+                              maxRowsPerChunk, int(noNccl), handleFlags, seed, firstGameId, os.fsencode(outputDir) if outputDir else None)
+    total, report = capi.SearchStats(), capi.SelfplayReport()
+    check(lib().kc_selfplay_run(C.byref(cfg), C.byref(model.desc), C.byref(params), C.byref(total), C.byref(report)))
+    return total, report
 
 
 class NNEvaluator:

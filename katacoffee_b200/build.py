@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkatacoffee_b200.so")
-SOURCES = ["zobrist.cpp", "modelfile.cpp", "sgf.cpp", "npzwrite.cpp", "evaluator.cpp", "games.cu", "net_fp32.cu", "net_bf16.cu", "search.cu"]
+SOURCES = ["zobrist.cpp", "modelfile.cpp", "sgf.cpp", "npzwrite.cpp", "evaluator.cpp", "selfplay.cpp", "games.cu", "net_fp32.cu", "net_bf16.cu", "search.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write("\n".join(logs))
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -74,6 +74,18 @@ class SearchStats(C.Structure):
                                           "whiteWins", "draws", "batchRows", "transpositionHits", "catchUpVisits")]
 
 
+class SelfplayConfig(C.Structure):
+    _fields_ = [("numDevices", C.c_int32), ("devices", C.POINTER(C.c_int32)), ("gamesPerDevice", C.c_int32), ("xSize", C.c_int32), ("ySize", C.c_int32),
+                ("winLen", C.c_int32), ("moves", C.c_int32), ("movesPerChunk", C.c_int32), ("warmupMoves", C.c_int32), ("staggerPlies", C.c_int32),
+                ("maxRowsPerChunk", C.c_int32), ("noNccl", C.c_int32), ("handleFlags", C.c_uint32), ("seed", C.c_uint64), ("firstGameId", C.c_uint64),
+                ("outputDir", C.c_char_p)]
+
+
+class SelfplayReport(C.Structure):
+    _fields_ = [("wallSeconds", C.c_double), ("deviceMsMax", C.c_double), ("rowsWritten", C.c_uint64), ("rowsDropped", C.c_uint64),
+                ("filesWritten", C.c_uint64), ("bytesWritten", C.c_uint64), ("kernelLaunches", C.c_uint64), ("reducedWithNccl", C.c_int32)]
+
+
 class EvaluatorConfig(C.Structure):
     _fields_ = [("nnXLen", C.c_int32), ("nnYLen", C.c_int32), ("winLen", C.c_int32), ("maxBatch", C.c_int32),
                 ("maxConcurrentEvals", C.c_int32), ("numServerThreads", C.c_int32), ("cacheSizePowerOfTwo", C.c_int32),
@@ -158,6 +170,7 @@ PROTOTYPES = {
     "kc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "kc_host_free": (C.c_int, [vp]),
     "kc_games_read_run_outputs": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "kc_games_read_run_ply": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "kc_search_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SearchParams), C.POINTER(vp)]),
     "kc_search_destroy": (C.c_int, [vp]),
     "kc_search_games": (vp, [vp]),
@@ -168,6 +181,7 @@ PROTOTYPES = {
     "kc_search_enable_training_rows": (C.c_int, [vp, C.c_int]),
     "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
     "kc_training_write_npz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "kc_selfplay_run": (C.c_int, [vp, vp, vp, vp, vp]),
     "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
     "kc_evaluator_create": (C.c_int, [vp, vp, C.POINTER(EvaluatorConfig), C.POINTER(vp)]),

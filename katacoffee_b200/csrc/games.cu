@@ -279,8 +279,9 @@ __global__ void __launch_bounds__(FEAT >= 3 ? TB_TILES : TB_PLAIN) games_kernel(
 // Several plies in one launch (rules + fp32 NCHW planes, random-legal moves, no symmetry): the state of a game stays
 // in registers between plies, and because every warp is autonomous the bitboard arithmetic of one warp's next ply
 // overlaps the plane stores of the others -- the single-ply kernel pays a store-free rules phase on every launch.
-// Ply p writes its planes to ring slot (firstSlot + p) % 4; masks, status words, hashes and moves are overwritten per
-// ply.  Semantically identical to `plies` launches of games_kernel<true, 1>.
+// Ply p writes its planes AND its masks, status words, hashes and moves to ring slot (firstSlot + p) % 4, so the outputs of the
+// last four plies of a launch are all in HBM for a consumer (kc_games_read_run_ply); the host picks firstSlot so that the last
+// ply lands in slot 0 = the object's ordinary buffers.  Semantically identical to `plies` launches of games_kernel<true, 1>.
 // ---------------------------------------------------------------------------------------------
 struct PlaneRing { float* slot[4]; };
 
@@ -311,15 +312,16 @@ __global__ void __launch_bounds__(TB_PLAIN) games_multi_kernel(const Geom g, Sta
     for(int i = lane; i < E; i += 32) bits[i] = 0;
     __syncwarp();
     if(active) {
+      const size_t gs = (size_t)((firstSlot + p) & 3) * g.numGames + gi;   // this ply's slot of the per-ply output ring
       BB L[4];
       bool illegal = false;
       const int played = stepGame(dm, g, s, -1, false, zob, L, illegal);
       const int fl = flagsOf(s.misc);
       const int nextPla = (fl >> 3) & 3;
       const uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
-      if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
-      if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
-      if(so.played) so.played[gi] = (int16_t)played;
+      if(so.status) so.status[gs] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
+      if(so.sitHash) { so.sitHash[2 * gs] = sh0; so.sitHash[2 * gs + 1] = sh1; }
+      if(so.played) so.played[gs] = (int16_t)played;
       if(so.legal) {
         uint64_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(TB_PLAIN) games_multi_kernel(const Geom g, Sta
             if(q == wq + 1 && sh) acc[q] |= dense >> (64 - sh);
           }
         }
-        for(int wd = 0; wd < g.LW; wd++) so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
+        for(int wd = 0; wd < g.LW; wd++) so.legal[gs * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
       }
       if(played >= 0) {
         cSteps += 1;
@@ -464,15 +466,16 @@ __global__ void __launch_bounds__((1 + NC) * TB_PLAIN) games_multi_split_kernel(
     for(int i = lane; i < E; i += 32) bits[i] = 0;
     __syncwarp();
     if(active) {
+      const size_t gs = (size_t)((firstSlot + p) & 3) * g.numGames + gi;   // this ply's slot of the per-ply output ring
       BB L[4];
       bool illegal = false;
       const int played = stepGame(dm, g, s, -1, false, zob, L, illegal);
       const int fl = flagsOf(s.misc);
       const int nextPla = (fl >> 3) & 3;
       const uint64_t sh0 = s.h0 ^ g.playerHash[nextPla][0], sh1 = s.h1 ^ g.playerHash[nextPla][1];
-      if(so.status) so.status[gi] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
-      if(so.sitHash) { so.sitHash[2 * (size_t)gi] = sh0; so.sitHash[2 * (size_t)gi + 1] = sh1; }
-      if(so.played) so.played[gi] = (int16_t)played;
+      if(so.status) so.status[gs] = (uint32_t)numTurnsOf(s.misc) | ((uint32_t)(fl & 1) << 8) | ((uint32_t)((fl >> 1) & 3) << 9) | ((uint32_t)nextPla << 11);
+      if(so.sitHash) { so.sitHash[2 * gs] = sh0; so.sitHash[2 * gs + 1] = sh1; }
+      if(so.played) so.played[gs] = (int16_t)played;
       if(so.legal) {
         uint64_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__((1 + NC) * TB_PLAIN) games_multi_split_kernel(
             if(q == wq + 1 && sh) acc[q] |= dense >> (64 - sh);
           }
         }
-        for(int wd = 0; wd < g.LW; wd++) so.legal[(size_t)gi * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
+        for(int wd = 0; wd < g.LW; wd++) so.legal[gs * g.LW + wd] = (uint32_t)(acc[wd >> 1] >> ((wd & 1) * 32));
       }
       if(played >= 0) {
         cSteps += 1;
@@ -639,8 +642,8 @@ int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen,
   KC_CUDA(cudaMalloc(&G->st.hash0, n * 8)); KC_CUDA(cudaMalloc(&G->st.hash1, n * 8));
   KC_CUDA(cudaMalloc(&G->st.gameId, n * 8)); KC_CUDA(cudaMalloc(&G->st.misc, n * 8));
   KC_CUDA(cudaMalloc(&G->d_moves, n * 2));
-  KC_CUDA(cudaMalloc(&G->d_legal, n * g.LW * 4)); KC_CUDA(cudaMalloc(&G->d_status, n * 4));
-  KC_CUDA(cudaMalloc(&G->d_sitHash, n * 16)); KC_CUDA(cudaMalloc(&G->d_played, n * 2));
+  KC_CUDA(cudaMalloc(&G->d_legal, 4 * n * g.LW * 4)); KC_CUDA(cudaMalloc(&G->d_status, 4 * n * 4));   // 4 slots: the per-ply ring of the multi-ply launches, slot 0 = the current position
+  KC_CUDA(cudaMalloc(&G->d_sitHash, 4 * n * 16)); KC_CUDA(cudaMalloc(&G->d_played, 4 * n * 2));
   KC_CUDA(cudaMalloc(&G->d_stats, 8 * 8));
   KC_CUDA(cudaMemset(G->d_stats, 0, 64));
   KC_CUDA(cudaMalloc(&G->d_planes, n * 15 * g.HW * 4)); KC_CUDA(cudaMalloc(&G->d_global, n * 4));
@@ -837,13 +840,15 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     // rules + features only: one multi-ply launch per group of RING plies, one event pair per launch
     PlaneRing ring;
     for(int i = 0; i < RING; i++) ring.slot[i] = (flushL2Bytes && i > 0) ? G->d_planesRing[i - 1] : G->d_planes;
+    // every ply's masks / status words / hashes / moves get their own slot too: the object's buffers hold 4 slots of G entries, slot 0 first
+    const StepOut so = stepOutOf(G, true);
     const int blocks = (g.numGames + TB_PLAIN - 1) / TB_PLAIN;
     constexpr int PLIES_PER_LAUNCH = 8;   // two turns of the 4-slot ring (412 MB > L2 between two writes of a slot)
     for(int p = 0; p < plies; p += PLIES_PER_LAUNCH) {
       const int np = std::min(PLIES_PER_LAUNCH, plies - p);
       if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
       KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups], G->stream));
-      StepOut so = stepOutOf(G, true);
+      const int first = (RING - ((np - 1) & 3)) & 3;   // the launch's last ply writes slot 0
       // producer / consumer warps for the static 5x5 instantiation (5.72 -> 6.10 TB/s algorithmic at 65,536 games); the generic
       // 64-bit kernel is bound by its rolled rules code and got slower when split (6x6: 4.46 -> 3.83 TB/s), so it keeps one warp
       // per 32 games.  KC_GAMES_MULTI_SPLIT = 0 / 1 forces one form for every board.
@@ -852,24 +857,25 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       const bool stat6 = g.W == 6 && g.H == 6 && g.K == 4 && static6();
       if(stat6) {
         if(splitEnv != 0)
-          games_multi_split_kernel<StaticDims<6, 6, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+          games_multi_split_kernel<StaticDims<6, 6, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
         else
-          games_multi_kernel<StaticDims<6, 6, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+          games_multi_kernel<StaticDims<6, 6, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
       } else if(splitEnv < 0 ? static5 : splitEnv != 0) {
         if(static5 && splitEnv == 2)
-          games_multi_split_kernel<StaticDims<5, 5, 4>, 2><<<blocks, 3 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+          games_multi_split_kernel<StaticDims<5, 5, 4>, 2><<<blocks, 3 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
         else if(static5)
-          games_multi_split_kernel<StaticDims<5, 5, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+          games_multi_split_kernel<StaticDims<5, 5, 4>, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
         else
-          games_multi_split_kernel<DynDims, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+          games_multi_split_kernel<DynDims, 1><<<blocks, 2 * TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
       } else if(g.W == 5 && g.H == 5 && g.K == 4)
-        games_multi_kernel<StaticDims<5, 5, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+        games_multi_kernel<StaticDims<5, 5, 4>><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
       else
-        games_multi_kernel<DynDims><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, 0);
+        games_multi_kernel<DynDims><<<blocks, TB_PLAIN, 0, G->stream>>>(g, G->st, G->d_zob, so, ring, G->d_global, np, first);
       G->launches++;
       KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups + 1], G->stream));
       nGroups++;
-      G->lastRunPlanes = ring.slot[(np - 1) & 3];
+      G->lastRunPlanes = ring.slot[0];
+      G->lastRunPlies = np; G->lastRunRing = flushL2Bytes != 0;
     }
   }
   for(int p = 0; h && p < plies; p++) {
@@ -915,6 +921,24 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     acc->gamesFinished += hs[2]; acc->blackWins += hs[3]; acc->whiteWins += hs[4]; acc->draws += hs[5];
     acc->checksum ^= hs[6];
   }
+  return 0;
+}
+
+int kc_games_read_run_ply(kc_games* G, int pliesBack, float* planes, uint32_t* legal, uint32_t* status, uint64_t* sitHash, int16_t* played) {
+  KC_CHECK(G, "kc_games_read_run_ply: null argument");
+  KC_CHECK(G->lastRunPlanes, "kc_games_read_run_ply: call kc_games_run without a handle first");
+  KC_CHECK(pliesBack >= 0 && pliesBack < 4 && pliesBack < G->lastRunPlies, "kc_games_read_run_ply: pliesBack must be below min(4, plies of the last launch)");
+  KC_CHECK(!planes || pliesBack == 0 || G->lastRunRing, "kc_games_read_run_ply: earlier plies' planes are kept only when the run used the plane ring (flushL2Bytes > 0)");
+  KC_CUDA(cudaSetDevice(G->ctx->device));
+  const Geom& g = G->geom;
+  const size_t n = (size_t)g.numGames;
+  const int slot = (4 - pliesBack) & 3;
+  KC_CUDA(cudaStreamSynchronize(G->stream));
+  if(planes) KC_CUDA(cudaMemcpy(planes, slot ? G->d_planesRing[slot - 1] : G->d_planes, n * 15 * g.HW * 4, cudaMemcpyDeviceToHost));
+  if(sitHash) KC_CUDA(cudaMemcpy(sitHash, G->d_sitHash + 2 * n * slot, n * 16, cudaMemcpyDeviceToHost));
+  if(legal) KC_CUDA(cudaMemcpy(legal, G->d_legal + n * g.LW * slot, n * g.LW * 4, cudaMemcpyDeviceToHost));
+  if(status) KC_CUDA(cudaMemcpy(status, G->d_status + n * slot, n * 4, cudaMemcpyDeviceToHost));
+  if(played) KC_CUDA(cudaMemcpy(played, G->d_played + n * slot, n * 2, cudaMemcpyDeviceToHost));
   return 0;
 }
 

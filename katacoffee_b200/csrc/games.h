@@ -11,7 +11,7 @@ struct kc_games {
   kc::State st;
   uint64_t* d_zob = nullptr;          // [HW][2 colours][2]
   int16_t* d_moves = nullptr;
-  uint32_t* d_legal = nullptr; uint32_t* d_status = nullptr; uint64_t* d_sitHash = nullptr; int16_t* d_played = nullptr;
+  uint32_t* d_legal = nullptr; uint32_t* d_status = nullptr; uint64_t* d_sitHash = nullptr; int16_t* d_played = nullptr;   // 4 slots of G entries each (slot 0 = current position; 1..3 = the multi-ply launches' per-ply ring)
   unsigned long long* d_stats = nullptr;  // 8 counters
   float* d_planes = nullptr; float* d_global = nullptr;  // fp32 feature outputs
   int8_t* d_sym = nullptr;
@@ -24,6 +24,7 @@ struct kc_games {
   // rules+features-only timing: consecutive plies write their planes to different ring slots (4 x G x 15*HW fp32 > L2),
   // so a ply never overwrites lines of the previous one that are still dirty in L2
   float* d_planesRing[3] = {nullptr, nullptr, nullptr};
+  int lastRunPlies = 0; bool lastRunRing = false;
   const float* lastRunPlanes = nullptr;   // where the last ply of the last rules+features kc_games_run wrote its planes
   // kc_games_postprocess outputs, allocated on first use and kept: [G][4*HW] probabilities, [G][2] win/loss, [G][2] misc, [G][2] nnHash
   float *d_ppPolicy = nullptr, *d_ppWinLoss = nullptr, *d_ppMisc = nullptr; uint64_t* d_ppHash = nullptr;

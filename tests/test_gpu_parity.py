@@ -475,15 +475,30 @@ def test_fused_multi_ply_kernel_outputs_bit_exact(ctx, oracle, W, H, K, G, plies
     games.reset(seed=seed, autoRefill=True)
     games.runTimed(None, plies, flush)
     out = games.readRunOutputs()
+    # every ply of a launch writes its own slot of a 4-slot ring: the last min(4, plies of the last launch) plies are all delivered
+    # (masks, status words, hashes, moves always; planes when the run used the plane ring)
+    back = min(4, (plies - 1) % 8 + 1)
+    earlier = {b: games.readRunPly(b, planes=flush > 0) for b in range(back)}
+    with pytest.raises(Exception):
+        games.readRunPly(back if back < 4 else 4)
     for g in range(G):
         # auto-refill: a finished game restarts with id + G before its next ply
         og, gid = oracle.Game(W, H, K), g
         last = -1
-        for _ in range(plies):
+        for t in range(plies):
             if og.finished():
                 og, gid = oracle.Game(W, H, K), gid + G
             last = og.choose(seed, gid)
             og.play(last)
+            b = plies - 1 - t
+            if b in earlier:
+                e = earlier[b]
+                assert int(e["status"][g]) == og.status(), (g, b)
+                assert int(e["played"][g]) == last, (g, b)
+                assert (e["sitHash"][g] == og.sit_hash()).all(), (g, b)
+                assert (e["legal"][g] == og.legal_mask()[0]).all(), (g, b)
+                if e["planes"] is not None:
+                    assert (e["planes"][g] == og.fill_row_v1()[0]).all(), (g, b)
         assert int(out["status"][g]) == og.status(), g
         assert int(out["played"][g]) == last, g
         assert (out["sitHash"][g] == og.sit_hash()).all(), g
@@ -1269,3 +1284,35 @@ def test_mish_activation_both_paths(ctx, oracle, net, W, H, n):
     assert np.abs(relu[0] - gb[0]).max() > 1e-2        # the activation really differs from the ReLU net's
     for x in (hf, hb, lm):
         x.close()
+
+
+@pytest.mark.gpu
+def test_selfplay_run_native_two_pools(ctx, tmp_path):
+    """kc_selfplay_run (csrc/selfplay.cpp): two search pools from one process (both on device 0 here, so the counters are summed on the
+    host; the ncclReduce path needs two devices and is exercised by `bench.py --selfplay-native` under gpurun --gpus 2): every lane
+    plays `moves` moves, the finished games' rows arrive as loadable .npz files of the reference's five arrays, the pools play
+    disjoint game ids, and a pool's games do not depend on how many pools run beside it."""
+    from katacoffee_b200 import backend, modeldesc
+    model = modeldesc.Model("b6c96", seed=5)
+    G, moves = 192, 9
+    kw = dict(xSize=5, ySize=5, winLen=4, moves=moves, movesPerChunk=3, warmupMoves=0, staggerPlies=6, maxRowsPerChunk=G * 30, seed=77, maxVisits=24,
+              autoRefill=1, temperaturePlies=30, reuseTree=1)
+    d2 = tmp_path / "two"; d2.mkdir()
+    tot2, rep2 = backend.selfplayRun(model, [0, 0], G, outputDir=str(d2), noNccl=True, **kw)
+    assert tot2.movesPlayed == 2 * G * moves
+    assert rep2.rowsDropped == 0 and rep2.rowsWritten > 0 and rep2.filesWritten == len(list(d2.iterdir())) and rep2.reducedWithNccl == 0
+    d1 = tmp_path / "one"; d1.mkdir()
+    tot1, rep1 = backend.selfplayRun(model, [0], G, outputDir=str(d1), **kw)
+    assert tot1.movesPlayed == G * moves and rep1.wallSeconds > 0 and rep1.deviceMsMax > 0
+
+    def rows_of(directory, pool):
+        parts = [np.load(f) for f in sorted(directory.glob(f"pool{pool:02d}_*.npz"))]
+        return {k: np.concatenate([p[k] for p in parts]) for k in ("binaryInputNCHWPacked", "globalInputNC", "policyTargetsNCMove", "globalTargetsNC", "valueTargetsNCHW")}
+    a, b, solo = rows_of(d2, 0), rows_of(d2, 1), rows_of(d1, 0)
+    assert len(a["globalInputNC"]) + len(b["globalInputNC"]) == rep2.rowsWritten
+    assert a["binaryInputNCHWPacked"].shape[1:] == (15, 4) and a["policyTargetsNCMove"].shape[1:] == (2, 100) and a["valueTargetsNCHW"].shape[1:] == (5, 5, 5)
+    for k in a:   # pool 0 of the two-pool run == the one-pool run, byte for byte
+        assert a[k].shape == solo[k].shape and (a[k] == solo[k]).all(), k
+    ha = {tuple(r) for r in a["globalTargetsNC"][:, 41:47].astype(np.int64)}
+    hb = {tuple(r) for r in b["globalTargetsNC"][:, 41:47].astype(np.int64)}
+    assert ha and hb and not (ha & hb)   # disjoint game hashes (ids first + pool * 2^40 + ...)
