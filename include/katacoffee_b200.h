@@ -334,7 +334,25 @@ typedef struct {
                                    symmetries (inputs symmetrised, outputs mapped back).  The symmetry is drawn from the position's sit-hash
                                    and the seed, not from a shared stream, so a position gets the same one whichever game reaches it.  With a
                                    KC_FLAG_SYM_PERMUTE_DIRS handle it is a true symmetry of the game; without, the reference backends' spatial copy. */
+  /* The rest of cpp/configs/training/selfplay1.cfg:144-185 (graph mode; zero = off). */
+  int32_t useLcbForSelection;   /* selfplay1.cfg:151: the move choice raises the child with the best lower confidence bound above every child it
+                                   beats (getPlaySelectionValues, cpp/search/searchresults.cpp:188-231; getSelfUtilityLCBAndRadius,
+                                   searchhelpers.cpp:469-522, from utilitySqAvg / weightSqSum kept per node) */
+  int32_t useNonBuggyLcb;       /* selfplay1.cfg:182; 0 = the historical form that never promotes the first-created child */
+  double lcbStdevs;             /* 5.0 in selfplay1.cfg:152 */
+  double minVisitPropForLCB;    /* 0.15 in selfplay1.cfg:153 */
+  int32_t rootNumSymmetriesToSample;   /* selfplay1.cfg:149 (4): every search starts by evaluating its root under that many distinct symmetries and
+                                          averaging the outputs (searchnnhelpers.cpp:67-83, 133-174; NNOutput's averaging constructor) */
+  int32_t useNoisePruning;      /* must be 0: pruneNoiseWeight (searchupdatehelpers.cpp:422-470) is not built; self-play leaves it off (setup.cpp:525) */
+  int32_t useUncertainty;       /* SearchParams::useUncertainty: a node's own evaluation weighs uncertaintyCoeff / (shorttermWinlossError ^ exponent +
+                                   coeff / maxWeight) instead of 1 (computeWeightFromNNOutput, searchupdatehelpers.cpp:91-113); off in self-play */
+  int32_t pad4_;
+  double uncertaintyCoeff, uncertaintyExponent, uncertaintyMaxWeight;   /* 0.25 / 1.0 / 8.0 in the GTP defaults (setup.cpp:545-560) */
 } kc_search_params;
+/* With any of chosenMoveTemperature[Early] or useLcbForSelection set in graph mode the move is chosen from the full
+ * Search::getPlaySelectionValues (child weights; children other than the most stably explored one cut down to the weight its final
+ * explore-selection value asks for, getReducedPlaySelectionWeight, rounded up; then LCB), and at a noised root the children that choice
+ * would prune count nothing in the root's statistics either (recomputeNodeStats, searchupdatehelpers.cpp:196-206). */
 typedef struct {
   uint64_t visits, netEvals, terminalVisits, movesPlayed, gamesFinished, blackWins, whiteWins, draws;
   uint64_t batchRows;           /* rows sent through the evaluator */
@@ -386,6 +404,8 @@ int kc_search_read_training_rows(kc_search* s, int* numRows, int* numDropped, ui
  * valueTargetsNCHW [N,5,H,W] i1 -- what python/shuffle.py and numpy.load read.  Host-only; written to path + ".tmp" and renamed. */
 int kc_training_write_npz(const char* path, int numRows, int xSize, int ySize, const uint8_t* binaryInputNCHWPacked, const float* globalInputNC,
                           const int16_t* policyTargetsNCMove, const float* globalTargetsNC, const int8_t* valueTargetsNCHW);
+/* The play-selection values [G][4*H*W] the last kc_search_play chose its last move from (0 for moves without a child). */
+int kc_search_read_play_selection(kc_search* s, double* playSelection);
 int kc_search_tree_digest(kc_search* s, uint64_t* digest);
 int64_t kc_search_launch_count(const kc_search* s);
 

@@ -356,6 +356,12 @@ class Search:
                                         ptr(out["edgeUtilitySum"]), ptr(out["policy"]), ptr(out["order"])))
         return out
 
+    def readPlaySelection(self):
+        """The play-selection values [G, P] the last play() chose its last move from."""
+        out = np.zeros((self.G, self.P), np.float64)
+        check(lib().kc_search_read_play_selection(self._p, ptr(out)))
+        return out
+
     def treeDigest(self):
         """Graph-mode searches: hash over every node of each game's graph (see kc_search_tree_digest)."""
         out = np.zeros(self.G, np.uint64)

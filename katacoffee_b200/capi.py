@@ -66,7 +66,10 @@ class SearchParams(C.Structure):
                 ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
                 ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double), ("valueWeightExponent", C.c_double),
                 ("chosenMoveTemperature", C.c_double), ("chosenMoveTemperatureEarly", C.c_double), ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double),
-                ("noPipeline", C.c_int32), ("nnRandomize", C.c_int32)]
+                ("noPipeline", C.c_int32), ("nnRandomize", C.c_int32),
+                ("useLcbForSelection", C.c_int32), ("useNonBuggyLcb", C.c_int32), ("lcbStdevs", C.c_double), ("minVisitPropForLCB", C.c_double),
+                ("rootNumSymmetriesToSample", C.c_int32), ("useNoisePruning", C.c_int32), ("useUncertainty", C.c_int32), ("pad4_", C.c_int32),
+                ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double)]
 
 
 class SearchStats(C.Structure):
@@ -182,6 +185,7 @@ PROTOTYPES = {
     "kc_search_read_training_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp, vp, vp, C.c_int]),
     "kc_training_write_npz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "kc_selfplay_run": (C.c_int, [vp, vp, vp, vp, vp]),
+    "kc_search_read_play_selection": (C.c_int, [vp, vp]),
     "kc_search_tree_digest": (C.c_int, [vp, vp]),
     "kc_search_launch_count": (C.c_int64, [vp]),
     "kc_evaluator_create": (C.c_int, [vp, vp, C.POINTER(EvaluatorConfig), C.POINTER(vp)]),

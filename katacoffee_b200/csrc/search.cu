@@ -65,6 +65,10 @@ struct SearchCfg {
   double noiseConc, noiseWeight, rootTemp, rootTempEarly, tempHalflife, fpuPWPow, rootDesired, vwExp;
   double moveTemp, moveTempEarly, moveSubtract, movePrune;   // chosenMoveTemperature / Early / Subtract / Prune (either temperature > 0: schedule)
   int boardArea;
+  // the rest of selfplay1.cfg / the GTP defaults: LCB move selection, root symmetry averaging, uncertainty weighting
+  int useLcb, nonBuggyLcb, rootSyms, noisePruning, useUncertainty;
+  double lcbStdevs, minVisitPropLcb, uncCoeff, uncExp, uncMaxWeight;
+  int fullPlaySelection;   // the move choice runs Search::getPlaySelectionValues (child weights, reduced weights, LCB) instead of plain edge visits
   uint64_t seed;
 };
 
@@ -120,7 +124,7 @@ struct TrainMem {
 //                           policy[P] f32 | child[P] i32 | edgeN[P] i32 | order[P] u8            (polOff = 32 + 8 P)
 //              graph mode: header { int visits; int numChildren; int nextPla; int biasEntry; double weightSum, utilityAvg,
 //                           nnUtility, lastBiasDeltaSum, lastBiasWeight; int depth (stones on the board), noised;
-//                           uint64 key[2] (transposition key) } | policy | child | edgeN | order          (polOff = 80)
+//                           uint64 key[2] (transposition key); double utilitySqAvg, weightSqSum, nnWeight } | policy | child | edgeN | order  (polOff = 104)
 struct NodeRef {
   uint8_t* base; int P; int polOff;
   __device__ __forceinline__ int& N() const { return *reinterpret_cast<int*>(base); }
@@ -142,7 +146,11 @@ struct NodeRef {
   __device__ __forceinline__ int& depth() const { return *reinterpret_cast<int*>(base + 56); }
   __device__ __forceinline__ int& noised() const { return *reinterpret_cast<int*>(base + 60); }   // root policy already noised / tempered
   __device__ __forceinline__ uint64_t* key() const { return reinterpret_cast<uint64_t*>(base + 64); }
+  __device__ __forceinline__ double& utilitySqAvg() const { return *reinterpret_cast<double*>(base + 80); }   // NodeStats::utilitySqAvg / weightSqSum
+  __device__ __forceinline__ double& weightSqSum() const { return *reinterpret_cast<double*>(base + 88); }    // (searchnode.h:44-48): what LCB reads
+  __device__ __forceinline__ double& nnWeight() const { return *reinterpret_cast<double*>(base + 96); }       // computeWeightFromNNOutput: 1 without useUncertainty
 };
+constexpr int GRAPH_POL_OFF = 104;
 // child codes: -1 none, >= 0 node index, -2 terminal draw, -3 terminal black win, -4 terminal white win
 __device__ __forceinline__ double terminalValue(int winner) { return winner == 2 ? 1.0 : winner == 1 ? -1.0 : 0.0; }
 
@@ -275,11 +283,16 @@ __global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCf
 // deterministic stand-in evaluator (integer hash of the situation -> exact fp32 policy / value), used to test the
 // search logic bit for bit against the oracle; the product path uses the net
 // ---------------------------------------------------------------------------------------------
+constexpr uint64_t ROOTSYM_SALT = 0x7007575E5A17ULL;
+__device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shorttermWinlossError);   // defined with the graph-mode helpers below
 __global__ void k_hash_eval(int n, int P, int LW, const uint32_t* __restrict__ legal, const uint64_t* __restrict__ sitHash,
-                            float* __restrict__ policy, float* __restrict__ winLoss) {
+                            float* __restrict__ policy, float* __restrict__ winLoss, float* __restrict__ misc, const int8_t* __restrict__ forcedSym) {
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(gi >= n) return;
-  const uint64_t h0 = sitHash[2 * (size_t)gi], h1 = sitHash[2 * (size_t)gi + 1];
+  uint64_t h0 = sitHash[2 * (size_t)gi], h1 = sitHash[2 * (size_t)gi + 1];
+  if(forcedSym) {   // the root's rootNumSymmetriesToSample evaluations: the symmetry is part of the hash, so a wrong choice shows
+    h0 ^= splitmix64(ROOTSYM_SALT + (uint64_t)forcedSym[gi]); h1 ^= splitmix64(ROOTSYM_SALT * 3 + (uint64_t)forcedSym[gi]);
+  }
   int sum = 0;
   for(int pos = lane; pos < P; pos += 32) {
     const bool ok = (legal[(size_t)gi * LW + (pos >> 5)] >> (pos & 31)) & 1u;
@@ -295,6 +308,84 @@ __global__ void k_hash_eval(int n, int P, int LW, const uint32_t* __restrict__ l
     const uint64_t r = splitmix64(h1);
     winLoss[2 * (size_t)gi] = (float)(r & 0xFFFF) * (1.0f / 131072.0f);
     winLoss[2 * (size_t)gi + 1] = (float)((r >> 16) & 0xFFFF) * (1.0f / 131072.0f);
+    if(misc) { misc[2 * (size_t)gi] = 0.f; misc[2 * (size_t)gi + 1] = (float)((r >> 32) & 0xFFFF) * (1.0f / 131072.0f); }   // shorttermWinlossError in [0, 0.5)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rootNumSymmetriesToSample (searchnnhelpers.cpp:67-83; for a root kept by tree re-use maybeRecomputeExistingNNOutput :133-174): at
+// the start of a search every root is evaluated under N distinct symmetries -- a partial Fisher-Yates shuffle of 0..7 drawn from a
+// counter stream keyed by (seed, game id, ply) -- and the post-processed outputs are averaged (NNOutput's averaging constructor,
+// nninputs.cpp:95-170: float sums in order, then / N).  Pass i: k_rootsym_prepare writes every unfinished root with its i-th
+// symmetry into the evaluation batch (row = game), the batch is evaluated, k_rootsym_accumulate adds the outputs up and, after
+// the last pass, installs the average: a fresh root becomes node 0 with its first visit, a kept root gets the new priors and
+// evaluation with its statistics untouched until the next re-computation (isReInit).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rootSymOf(const SearchCfg& c, uint64_t gameId, int ply, int pass) {
+  int idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  uint64_t st = splitmix64(c.seed ^ (gameId * PHI) ^ (uint64_t)ply ^ ROOTSYM_SALT);
+  for(int i = 0; i <= pass; i++) {
+    st += PHI;
+    const int j = i + (int)(splitmix64(st) % (uint64_t)(8 - i));
+    const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp;
+  }
+  return idx[pass];
+}
+__global__ void __launch_bounds__(128) k_rootsym_prepare(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, int8_t* __restrict__ leafSym, int pass) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
+  // row li = the root of game gi (finished games too: their row is evaluated and ignored)
+  leaf.black[li] = root.black[gi]; leaf.white[li] = root.white[gi]; leaf.hash0[li] = root.hash0[gi]; leaf.hash1[li] = root.hash1[gi];
+  leaf.gameId[li] = root.gameId[gi]; leaf.misc[li] = root.misc[gi];
+  leafSym[li] = (int8_t)rootSymOf(c, root.gameId[gi], numTurnsOf(root.misc[gi]), pass);
+  if(pass == 0 && c.compact) { if(li == 0) t.evalCount[c.half] = c.gCnt; }   // a full batch
+}
+__global__ void __launch_bounds__(128) k_rootsym_accumulate(const SearchCfg c, TreeMem t, State root, const float* __restrict__ policy, const float* __restrict__ winLoss,
+                                                            const float* __restrict__ misc, float* __restrict__ accPolicy, float* __restrict__ accScalars, int pass) {
+  const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(li >= c.gCnt) return;
+  const int gi = c.gOff + li;
+  if(flagsOf(root.misc[gi]) & 1) return;
+  if(t.nodeCount[gi] > 0 && NodeRef{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P, c.polOff}.noised()) return;   // this root has had its evaluations
+  const size_t row = (size_t)li;
+  float* ap = accPolicy + (size_t)gi * c.P;
+  float* as = accScalars + (size_t)gi * 4;
+  const bool last = pass == c.rootSyms - 1;
+  const float fl = (float)c.rootSyms;
+  for(int pos = lane; pos < c.P; pos += 32) {
+    float v = __fadd_rn(pass == 0 ? 0.0f : ap[pos], policy[row * c.P + pos]);
+    if(last) v = __fdiv_rn(v, fl);
+    ap[pos] = v;
+  }
+  float aw = 0.f, al = 0.f, ae = 0.f;
+  if(lane == 0) {
+    aw = __fadd_rn(pass == 0 ? 0.0f : as[0], winLoss[2 * row]); al = __fadd_rn(pass == 0 ? 0.0f : as[1], winLoss[2 * row + 1]);
+    ae = __fadd_rn(pass == 0 ? 0.0f : as[2], misc ? misc[2 * row + 1] : 0.0f);
+    if(last) { aw = __fdiv_rn(aw, fl); al = __fdiv_rn(al, fl); ae = __fdiv_rn(ae, fl); }
+    as[0] = aw; as[1] = al; as[2] = ae;
+    atomicAdd(&t.stats[1], 1ULL);
+  }
+  if(!last) return;
+  __syncwarp();
+  NodeRef nd{t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, c.P, c.polOff};
+  const bool fresh = t.nodeCount[gi] == 0;
+  for(int pos = lane; pos < c.P; pos += 32) {
+    nd.policy()[pos] = ap[pos];
+    if(fresh) { nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0; }
+  }
+  if(lane == 0) {
+    const double v = __dsub_rn((double)aw, (double)al);
+    const double w0 = nnWeightOf(c, ae);
+    if(fresh) {
+      nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = (flagsOf(root.misc[gi]) >> 3) & 3; nd.biasEntry() = -1;
+      nd.weightSum() = w0; nd.utilityAvg() = v; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
+      nd.utilitySqAvg() = __dmul_rn(v, v); nd.weightSqSum() = __dmul_rn(w0, w0); nd.nnWeight() = w0;
+      nd.depth() = numTurnsOf(root.misc[gi]); nd.key()[0] = 0; nd.key()[1] = 0;
+      t.nodeCount[gi] = 1;
+      atomicAdd(&t.stats[0], 1ULL);
+    } else { nd.nnUtility() = v; nd.nnWeight() = w0; }
+    nd.noised() = 0;
   }
 }
 
@@ -399,6 +490,14 @@ __device__ __forceinline__ void childStats(const SearchCfg& c, uint8_t* treeBase
     cv = ch.N(); cw = ch.weightSum(); cu = ch.utilityAvg();
   } else { cv = e; cw = (double)e; cu = terminalValue(-2 - cc); }
 }
+__device__ __forceinline__ void childStatsSq(const SearchCfg& c, uint8_t* treeBase, int cc, int e, int& cv, double& cw, double& cu, double& cusq, double& cwsq) {
+  if(cc >= 0) {
+    NodeRef ch{treeBase + (size_t)cc * c.nodeStride, c.P, c.polOff};
+    cv = ch.N(); cw = ch.weightSum(); cu = ch.utilityAvg(); cusq = ch.utilitySqAvg(); cwsq = ch.weightSqSum();
+  } else { cv = e; cw = (double)e; cu = terminalValue(-2 - cc); cusq = __dmul_rn(cu, cu); cwsq = (double)e; }
+}
+// computeWeightFromNNOutput (searchupdatehelpers.cpp:91-113) with Coffee's outputs (no score term)
+__device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shorttermWinlossError);
 __device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
 
 template <class D>
@@ -558,13 +657,24 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
   }
 }
 
+__device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shorttermWinlossError) {
+  if(!c.useUncertainty) return 1.0;
+  const double unc = (double)shorttermWinlossError;
+  const double powered = c.uncExp == 1.0 ? unc : c.uncExp == 0.5 ? __dsqrt_rn(unc) : (unc <= 0.0 ? 0.0 : detExp(__dmul_rn(c.uncExp, detLog(unc))));
+  const double baseline = __ddiv_rn(c.uncCoeff, c.uncMaxWeight);
+  return __ddiv_rn(c.uncCoeff, __dadd_rn(powered, baseline));
+}
+
 // recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
 constexpr int MAX_POLICY_SLOTS = 4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN;
 __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, const double* __restrict__ tcdfTable, uint8_t* treeBase, NodeRef nd,
-                                              int lane, int inc) {
+                                              int lane, int inc, bool isRoot) {
   const int* ch = nd.child(); const int* eN = nd.edgeN();
-  double sumW = 0.0, sumWU = 0.0;
-  for(int pos = lane; pos < c.P; pos += 32) {
+  double sumW = 0.0, sumWU = 0.0, maxW = 0.0;
+  double nwl[(MAX_POLICY_SLOTS + 31) / 32];   // this lane's children: weight, then desired weight
+  int k = 0;
+  for(int pos = lane; pos < c.P; pos += 32, k++) {
+    nwl[k] = 0.0;
     const int cc = ch[pos];
     if(cc != -1) {
       int cv; double cw, cu;
@@ -572,58 +682,76 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
       childStats(c, treeBase, cc, e, cv, cw, cu);
       if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
       const double w = childWeightOf(cw, e, cv);
+      nwl[k] = w;
+      maxW = fmax(maxW, w);
       sumW = __dadd_rn(sumW, w);
       sumWU = __dadd_rn(sumWU, __dmul_rn(w, cu));
     }
   }
   sumW = warpSumD(sumW);
   sumWU = warpSumD(sumWU);
-  if(c.vwExp != 0.0 && sumW > 0.0) {
-    // valueWeightExponent (downweightBadChildrenAndNormalizeWeight, searchupdatehelpers.cpp:330-417): a child keeps
-    // weight * cdf(z)^exponent, z = its utility's distance from the siblings' weighted mean in standard errors, cdf = Student t
+  // at a noised root the children the move choice would prune / reduce lose the same weight here (:196-206)
+  double amountToSubtract = 0.0, amountToPrune = 0.0;
+  if(isRoot && c.rootNoise && !c.noisePruning) {
+    for(int o = 16; o > 0; o >>= 1) maxW = fmax(maxW, __shfl_xor_sync(0xffffffffu, maxW, o));
+    amountToSubtract = fmin(c.moveSubtract, __ddiv_rn(maxW, 64.0));
+    amountToPrune = fmin(c.movePrune, __ddiv_rn(maxW, 64.0));
+  }
+  const bool reweigh = sumW > 0.0 && (c.vwExp != 0.0 || amountToSubtract > 0.0 || amountToPrune > 0.0);
+  if(reweigh) {
+    // downweightBadChildrenAndNormalizeWeight (searchupdatehelpers.cpp:330-417): prune / subtract, then (valueWeightExponent) a child
+    // keeps weight * cdf(z)^exponent, z = its utility's distance from the siblings' weighted mean in standard errors, cdf = Student t
     // (3 degrees of freedom) from the interpolated 2,000-point table; the total child weight stays what it was
     const double simpleValue = __ddiv_rn(sumWU, sumW);
     const int pla = nd.nextPla();
-    double nwl[(MAX_POLICY_SLOTS + 31) / 32];
     double totalNew = 0.0;
-    int k = 0;
+    k = 0;
     for(int pos = lane; pos < c.P; pos += 32, k++) {
-      nwl[k] = 0.0;
-      const int cc = ch[pos];
-      if(cc == -1) continue;
-      int cv; double cw, cu;
-      const int e = eN[pos];
-      childStats(c, treeBase, cc, e, cv, cw, cu);
-      if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
-      const double w = childWeightOf(cw, e, cv);
-      const double stdev = __dsqrt_rn(__dadd_rn(0.00000001, __ddiv_rn(1.0, __dmul_rn(1.5, __dsqrt_rn(w)))));
-      const double diff = pla == 2 ? __dsub_rn(cu, simpleValue) : __dsub_rn(simpleValue, cu);
-      const double z = __ddiv_rn(diff, stdev);
-      const double d = __ddiv_rn(__dmul_rn(1999.0, __dsub_rn(z, -50.0)), 100.0);
-      double cdf;
-      if(d <= 0) cdf = 0.0;
-      else {
-        const int idx = (int)d;
-        if(idx >= 1999) cdf = 1.0;
-        else cdf = __dadd_rn(tcdfTable[idx], __dmul_rn(__dsub_rn(d, (double)idx), __dsub_rn(tcdfTable[idx + 1], tcdfTable[idx])));
+      const double w = nwl[k];
+      if(w == 0.0) continue;
+      double x = w;
+      if(x < amountToPrune) x = 0.0;
+      else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
+      if(x > 0.0 && c.vwExp != 0.0) {
+        int cv; double cw, cu;
+        childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
+        const double stdev = __dsqrt_rn(__dadd_rn(0.00000001, __ddiv_rn(1.0, __dmul_rn(1.5, __dsqrt_rn(w)))));
+        const double diff = pla == 2 ? __dsub_rn(cu, simpleValue) : __dsub_rn(simpleValue, cu);
+        const double z = __ddiv_rn(diff, stdev);
+        const double d = __ddiv_rn(__dmul_rn(1999.0, __dsub_rn(z, -50.0)), 100.0);
+        double cdf;
+        if(d <= 0) cdf = 0.0;
+        else {
+          const int idx = (int)d;
+          if(idx >= 1999) cdf = 1.0;
+          else cdf = __dadd_rn(tcdfTable[idx], __dmul_rn(__dsub_rn(d, (double)idx), __dsub_rn(tcdfTable[idx + 1], tcdfTable[idx])));
+        }
+        const double pr = __dadd_rn(cdf, 0.0001);
+        const double raised = c.vwExp == 0.5 ? __dsqrt_rn(pr) : c.vwExp == 0.25 ? __dsqrt_rn(__dsqrt_rn(pr)) : c.vwExp == 1.0 ? pr : detExp(__dmul_rn(c.vwExp, detLog(pr)));
+        x = __dmul_rn(x, raised);
       }
-      const double pr = __dadd_rn(cdf, 0.0001);
-      const double raised = c.vwExp == 0.5 ? __dsqrt_rn(pr) : c.vwExp == 0.25 ? __dsqrt_rn(__dsqrt_rn(pr)) : c.vwExp == 1.0 ? pr : detExp(__dmul_rn(c.vwExp, detLog(pr)));
-      nwl[k] = __dmul_rn(w, raised);
-      totalNew = __dadd_rn(totalNew, nwl[k]);
+      nwl[k] = x;
+      totalNew = __dadd_rn(totalNew, x);
     }
     totalNew = warpSumD(totalNew);
     const double factor = __ddiv_rn(sumW, totalNew);
-    double part = 0.0;
     k = 0;
-    for(int pos = lane; pos < c.P; pos += 32, k++)
-      if(nwl[k] != 0.0) {
-        int cv; double cw, cu;
-        childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
-        part = __dadd_rn(part, __dmul_rn(__dmul_rn(nwl[k], factor), cu));
-      }
-    sumWU = warpSumD(part);
+    for(int pos = lane; pos < c.P; pos += 32, k++) nwl[k] = __dmul_rn(nwl[k], factor);
   }
+  double partU = 0.0, partUSq = 0.0, partWSq = 0.0;
+  k = 0;
+  for(int pos = lane; pos < c.P; pos += 32, k++)
+    if(nwl[k] != 0.0) {
+      int cv; double cw, cu, cusq, cwsq;
+      childStatsSq(c, treeBase, ch[pos], eN[pos], cv, cw, cu, cusq, cwsq);
+      const double scaling = __ddiv_rn(nwl[k], cw);
+      partU = __dadd_rn(partU, __dmul_rn(nwl[k], cu));
+      partUSq = __dadd_rn(partUSq, __dmul_rn(nwl[k], cusq));
+      partWSq = __dadd_rn(partWSq, __dmul_rn(__dmul_rn(scaling, scaling), cwsq));
+    }
+  partU = warpSumD(partU);
+  if(reweigh) sumWU = partU;
+  const double sumWUSq = warpSumD(partUSq), sumWSq = warpSumD(partWSq);
   if(lane == 0) {
     double utility = nd.nnUtility();
     const int be = nd.biasEntry();
@@ -641,14 +769,19 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
       }
       if(ew > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, ed), ew));
     }
-    nd.utilityAvg() = __ddiv_rn(__dadd_rn(sumWU, utility), __dadd_rn(sumW, 1.0));
-    nd.weightSum() = __dadd_rn(sumW, 1.0);
+    const double w0 = nd.nnWeight();
+    const double weightSum = __dadd_rn(sumW, w0);
+    nd.utilityAvg() = __ddiv_rn(__dadd_rn(sumWU, __dmul_rn(utility, w0)), weightSum);
+    nd.utilitySqAvg() = __ddiv_rn(__dadd_rn(sumWUSq, __dmul_rn(__dmul_rn(utility, utility), w0)), weightSum);
+    nd.weightSqSum() = __dadd_rn(sumWSq, __dmul_rn(w0, w0));
+    nd.weightSum() = weightSum;
     nd.N() = nd.N() + inc;
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss) {
+__global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss,
+                                                                const float* __restrict__ misc) {
   const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(li >= c.gCnt) return;
   const int gi = c.gOff + li;
@@ -683,8 +816,10 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
         const double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
         if(E[1] > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, E[0]), E[1]));   // addLeafValue :27-37
       }
+      const double w0 = nnWeightOf(c, misc ? misc[2 * row + 1] : 0.0f);
       nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi] & 0xff; nd.biasEntry() = be;
-      nd.weightSum() = 1.0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
+      nd.weightSum() = w0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
+      nd.utilitySqAvg() = __dmul_rn(utility, utility); nd.weightSqSum() = __dmul_rn(w0, w0); nd.nnWeight() = w0;
       nd.depth() = t.leafNextPla[gi] >> 8; nd.noised() = 0;
       nd.key()[0] = kind == 1 ? t.leafKey[2 * (size_t)gi] : 0; nd.key()[1] = kind == 1 ? t.leafKey[2 * (size_t)gi + 1] : 0;
       t.nodeCount[gi] = newIdx + 1;
@@ -711,7 +846,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
     }
     __syncwarp();
-    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, treeBase, nd, lane, 1);
+    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, treeBase, nd, lane, 1, d == 0);
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
@@ -939,9 +1074,9 @@ __global__ void __launch_bounds__(128) k_reroot_graph(const SearchCfg c, TreeMem
             m &= m - 1;
             NodeRef nd{dst + (size_t)j * c.nodeStride, c.P, c.polOff};
             if(nd.numChildren() == 0) {
-              if(lane == 0) nd.utilityAvg() = nd.nnUtility();
+              if(lane == 0) { nd.utilityAvg() = nd.nnUtility(); nd.utilitySqAvg() = __dmul_rn(nd.nnUtility(), nd.nnUtility()); }
               __syncwarp();
-            } else recomputeNode(c, newBiasVals, t.tcdf, dst, nd, lane, 0);
+            } else recomputeNode(c, newBiasVals, t.tcdf, dst, nd, lane, 0, j == 0);
           }
         }
     }
@@ -959,7 +1094,9 @@ __global__ void __launch_bounds__(128) k_tree_digest(const SearchCfg c, TreeMem 
   for(int i = lane; i < count; i += 32) {
     NodeRef nd{treeBase + (size_t)i * c.nodeStride, c.P, c.polOff};
     const uint64_t wb = (uint64_t)__double_as_longlong(nd.weightSum()), ub = (uint64_t)__double_as_longlong(nd.utilityAvg());
-    uint64_t nh = splitmix64((uint64_t)nd.N() ^ ((uint64_t)nd.numChildren() << 32)) ^ splitmix64(wb ^ PHI) ^ splitmix64(ub + PHI);
+    const uint64_t qb = (uint64_t)__double_as_longlong(nd.utilitySqAvg()), sb = (uint64_t)__double_as_longlong(nd.weightSqSum());
+    uint64_t nh = splitmix64((uint64_t)nd.N() ^ ((uint64_t)nd.numChildren() << 32)) ^ splitmix64(wb ^ PHI) ^ splitmix64(ub + PHI) ^
+                  splitmix64(qb ^ (PHI << 1)) ^ splitmix64(sb + (PHI << 1));
     for(int pos = 0; pos < c.P; pos++) {
       const int cc = nd.child()[pos];
       if(cc != -1)
@@ -971,11 +1108,102 @@ __global__ void __launch_bounds__(128) k_tree_digest(const SearchCfg c, TreeMem 
   if(lane == 0) out[gi] = h;
 }
 
+// Search::getPlaySelectionValues at the root (cpp/search/searchresults.cpp:66-231), graph mode, one thread: the value of a move is
+// its child's weight; children other than the most stably explored one are cut down to the weight the final explore-selection
+// value of that one would have asked for (getReducedPlaySelectionWeight, searchexplorehelpers.cpp:209-243, rounded up); with
+// useLcbForSelection the child with the best lower confidence bound (getSelfUtilityLCBAndRadius, searchhelpers.cpp:469-522) is
+// raised above every child it beats.  psv [P] (0 for moves without a child); lcb / radius are scratch [P].
+__device__ void playSelectionValues(const SearchCfg& c, uint8_t* treeBase, NodeRef nd, double* psv, double* lcb, double* radius) {
+  const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order(); const float* pol = nd.policy();
+  double total = 0.0;
+  int n = 0;
+  for(int pos = 0; pos < c.P; pos++) {
+    psv[pos] = 0.0;
+    if(ch[pos] == -1) continue;
+    int cv; double cw, cu;
+    childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
+    psv[pos] = childWeightOf(cw, eN[pos], cv);
+    total = __dadd_rn(total, psv[pos]);
+    n++;
+  }
+  if(n == 0) return;
+  int best = -1, bestOrd = 1 << 20;
+  double bestWeight = -1e30, maxGoodness = -1e30;
+  for(int pos = 0; pos < c.P; pos++) {
+    if(ch[pos] == -1) continue;
+    const double e = (double)eN[pos];
+    const double g = __dadd_rn(__ddiv_rn(__dmul_rn(psv[pos], fmax(0.0, __dsub_rn(e, 1.0))), fmax(1.0, e)), __dmul_rn(2.0, (double)pol[pos]));
+    if(g > maxGoodness || (g == maxGoodness && ord[pos] < bestOrd)) { maxGoodness = g; bestWeight = psv[pos]; best = pos; bestOrd = ord[pos]; }
+  }
+  const int pla = nd.nextPla();
+  {
+    const double scaling = __dmul_rn(c.cpuct, __dsqrt_rn(__dadd_rn(total, 0.01)));
+    int cv; double cw, cu;
+    childStats(c, treeBase, ch[best], eN[best], cv, cw, cu);
+    const double bestValue = __dadd_rn(__ddiv_rn(__dmul_rn(scaling, (double)pol[best]), __dadd_rn(1.0, psv[best])), pla == 2 ? cu : -cu);
+    for(int pos = 0; pos < c.P; pos++) {
+      if(ch[pos] == -1 || pos == best) continue;
+      childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
+      double reduced = 0.0;
+      if(cv > 0 && psv[pos] > 0.0) {
+        double wanted = 0.0;
+        if(pol[pos] >= 0.0f) {
+          const double exploreComponent = __dsub_rn(bestValue, pla == 2 ? cu : -cu);
+          if(exploreComponent <= 0) wanted = 1e100;
+          else { wanted = __dsub_rn(__ddiv_rn(__dmul_rn(scaling, (double)pol[pos]), exploreComponent), 1.0); if(wanted < 0) wanted = 0.0; }
+        }
+        reduced = psv[pos] > wanted ? wanted : psv[pos];
+      }
+      psv[pos] = ceil(reduced);
+    }
+  }
+  if(!c.useLcb) return;
+  double bestLcb = -1e10;
+  int bestLcbPos = -1, bestLcbOrd = 1 << 20;
+  for(int pos = 0; pos < c.P; pos++) {
+    if(ch[pos] == -1) continue;
+    int cv; double cw, cu, cusq, cwsq;
+    childStatsSq(c, treeBase, ch[pos], eN[pos], cv, cw, cu, cusq, cwsq);
+    const double ratio = __ddiv_rn((double)eN[pos], (double)max(cv, 1));
+    double weightSum = __dmul_rn(cw, ratio), weightSqSum = __dmul_rn(cwsq, ratio);
+    radius[pos] = __dmul_rn(2.0, c.lcbStdevs);   // utilityRangeRadius = winLossUtilityFactor = 1
+    lcb[pos] = -radius[pos];
+    if(!(cv <= 0 || weightSum <= 0.0 || weightSqSum <= 0.0)) {
+      double ess = __ddiv_rn(__dmul_rn(weightSum, weightSum), weightSqSum);
+      const double priorWeight = __ddiv_rn(weightSum, __dmul_rn(__dmul_rn(ess, ess), ess));
+      double usq = fmax(cusq, __dadd_rn(__dmul_rn(cu, cu), 1e-8));
+      usq = __ddiv_rn(__dadd_rn(__dmul_rn(usq, weightSum), __dmul_rn(__dadd_rn(usq, 1.0), priorWeight)), __dadd_rn(weightSum, priorWeight));
+      weightSum = __dadd_rn(weightSum, priorWeight);
+      weightSqSum = __dadd_rn(weightSqSum, __dmul_rn(priorWeight, priorWeight));
+      ess = __ddiv_rn(__dmul_rn(weightSum, weightSum), weightSqSum);
+      const double selfUtility = pla == 2 ? cu : -cu;
+      const double variance = __dsub_rn(usq, __dmul_rn(cu, cu));
+      const double r = __dmul_rn(__dsqrt_rn(__ddiv_rn(variance, ess)), c.lcbStdevs);
+      lcb[pos] = __dsub_rn(selfUtility, r);
+      radius[pos] = r;
+    }
+    if(psv[pos] > 0 && psv[pos] >= __dmul_rn(c.minVisitPropLcb, bestWeight))
+      if(lcb[pos] > bestLcb || (lcb[pos] == bestLcb && ord[pos] < bestLcbOrd)) { bestLcb = lcb[pos]; bestLcbPos = pos; bestLcbOrd = ord[pos]; }
+  }
+  if(bestLcbPos < 0 || (!c.nonBuggyLcb && ord[bestLcbPos] == 0)) return;   // useNonBuggyLcb false: the first-created child is never promoted
+  double adjusted = psv[bestLcbPos];
+  for(int pos = 0; pos < c.P; pos++) {
+    if(ch[pos] == -1 || pos == bestLcbPos) continue;
+    const double excess = __dsub_rn(bestLcb, lcb[pos]);
+    if(excess < 0) continue;
+    const double factor = __ddiv_rn(__dadd_rn(radius[pos], excess), __dadd_rn(radius[pos], __dmul_rn(0.20, excess)));
+    const double lbound = __dmul_rn(__dmul_rn(factor, factor), psv[pos]);
+    if(lbound > adjusted) adjusted = lbound;
+  }
+  psv[bestLcbPos] = adjusted;
+}
+
 // ---------------------------------------------------------------------------------------------
 // choose the move, play it on the root game, drop the tree; refill finished games
 // ---------------------------------------------------------------------------------------------
 template <class D>
-__global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeMem t, TrainMem tr, const uint64_t* __restrict__ zob, int16_t* __restrict__ chosen) {
+__global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeMem t, TrainMem tr, const uint64_t* __restrict__ zob, int16_t* __restrict__ chosen,
+                              double* __restrict__ psvOut) {
   const D dm(g);
   using BB = typename D::BB;
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -995,16 +1223,24 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
         if(eN[pos] > bestN || (eN[pos] == bestN && ord[pos] < bestOrd)) { bestN = eN[pos]; bestOrd = ord[pos]; bestPos = pos; }
       }
     const int ply = numTurnsOf(s.misc);
-    if((c.moveTemp > 0.0 || c.moveTempEarly > 0.0) && bestN > 0) {
+    double psv[MAX_POLICY];
+    if(c.fullPlaySelection) {
+      double lcb[MAX_POLICY], radius[MAX_POLICY];
+      playSelectionValues(c, t.nodes + (size_t)gi * c.maxNodes * c.nodeStride, nd, psv, lcb, radius);
+    } else
+      for(int pos = 0; pos < c.P; pos++) psv[pos] = ch[pos] != -1 ? (double)eN[pos] : 0.0;
+    if(psvOut) for(int pos = 0; pos < c.P; pos++) psvOut[(size_t)gi * c.P + pos] = psv[pos];
+    if((c.moveTemp > 0.0 || c.moveTempEarly > 0.0 || c.fullPlaySelection) && bestN > 0) {
       // the reference's temperature schedule (searchresults.cpp:287-298, searchhelpers.cpp:12-49, 463-467): play-selection value = edge
       // visits, pruned / reduced, raised to 1/T with T interpolated from the early to the late temperature by 0.5^(turn/halflife...)
-      const double maxValue = (double)bestN;
+      double maxValue = 0.0;
+      for(int pos = 0; pos < c.P; pos++) if(ch[pos] != -1 && psv[pos] > maxValue) maxValue = psv[pos];
       const double amountToSubtract = fmin(c.moveSubtract, __ddiv_rn(maxValue, 64.0)), amountToPrune = fmin(c.movePrune, __ddiv_rn(maxValue, 64.0));
       double newMax = 0.0;
       int bPos = -1, bOrd = 1 << 20;
       for(int pos = 0; pos < c.P; pos++) {
         if(ch[pos] == -1) continue;
-        double x = (double)eN[pos];
+        double x = psv[pos];
         if(x < amountToPrune) x = 0.0;
         else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
         if(x > newMax || (x == newMax && x > 0.0 && ord[pos] < bOrd)) { newMax = x; bPos = pos; bOrd = ord[pos]; }
@@ -1016,7 +1252,7 @@ __global__ void k_choose_play(const Geom g, const SearchCfg c, State root, TreeM
       else {
         const double logMax = detLog(newMax);
         auto weightOf = [&](int pos) -> double {
-          double x = (double)eN[pos];
+          double x = psv[pos];
           if(x < amountToPrune) x = 0.0;
           else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
           return x <= 0.0 ? 0.0 : detExp(__ddiv_rn(__dsub_rn(detLog(x), logMax), T));
@@ -1262,6 +1498,8 @@ struct kc_search {
   kc::TreeMem tree;
   float* d_policy = nullptr; float* d_winLoss = nullptr; float* d_misc = nullptr; uint64_t* d_nnHash = nullptr;
   int16_t* d_chosen = nullptr;
+  double* d_psv = nullptr;                                   // [G][P] play-selection values of the last move choice
+  float* d_rootAccPolicy = nullptr; float* d_rootAccScalars = nullptr;   // rootNumSymmetriesToSample: [G][P] and [G][4] running sums
   kc::TrainMem train = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
@@ -1316,6 +1554,29 @@ int runVisits(kc_search* S) {
     KC_CUDA(cudaEventRecord(S->evFork, st));
     for(int h = 0; h < nh; h++) KC_CUDA(cudaStreamWaitEvent(H[h].st, S->evFork, 0));
   }
+  if(c.rootSyms > 1) {
+    for(int pass = 0; pass < c.rootSyms; pass++)
+      for(int h = 0; h < nh; h++) {
+        const SearchCfg& ch = H[h].c;
+        kc_games* Lf = H[h].leaf;
+        cudaStream_t hs = H[h].st;
+        const int warpBlocks = (ch.gCnt * 32 + 127) / 128;
+        k_rootsym_prepare<<<(ch.gCnt + 127) / 128, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, Lf->d_sym, pass);
+        S->launches++;
+        if(S->handle) {
+          if(kc::gamesEval(Lf, S->handle, nullptr, c.compact ? S->tree.evalCount + h : nullptr, H[h].rowOff, S->pipelined, /*symOnDevice=*/true)) return 1;
+          kc::launchPostprocess(S->handle, ch.gCnt, c.LW, Lf->d_legal, Lf->d_status, Lf->d_sitHash, 1.0f, H[h].policy, H[h].winLoss, H[h].misc, H[h].nnHash, hs,
+                                H[h].rowOff);
+          S->launches += 3;
+        } else {
+          if(kc::gamesRefreshOutputs(Lf)) return 1;
+          k_hash_eval<<<warpBlocks, 128, 0, hs>>>(ch.gCnt, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, H[h].policy, H[h].winLoss, H[h].misc, Lf->d_sym);
+          S->launches += 2;
+        }
+        k_rootsym_accumulate<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, R->st, H[h].policy, H[h].winLoss, H[h].misc, S->d_rootAccPolicy, S->d_rootAccScalars, pass);
+        S->launches++;
+      }
+  }
   for(int it = 0; it < c.maxVisits; it++) {
     if(c.reuseTree && it > 0 && (it & 31) == 0) {
       // games that kept a subtree finish their visit budget early: stop once no game had a visit left to make
@@ -1332,7 +1593,7 @@ int runVisits(kc_search* S) {
       const int warpBlocks = (ch.gCnt * 32 + 127) / 128;
       // root noise / temperature: once per search, on roots kept by tree re-use (before the first descent) and on roots created
       // by the first iteration (before the second)
-      if(rootPolicyChange && it <= 1) { k_root_noise<<<(ch.gCnt + 63) / 64, 64, 0, hs>>>(ch, S->tree, R->st, R->geom.HW); S->launches++; }
+      if((rootPolicyChange || c.rootSyms > 1) && it <= 1) { k_root_noise<<<(ch.gCnt + 63) / 64, 64, 0, hs>>>(ch, S->tree, R->st, R->geom.HW); S->launches++; }
       if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount + h, 0, 4, hs));
       if(c.graph) {
         if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
@@ -1347,10 +1608,10 @@ int runVisits(kc_search* S) {
         S->launches += 3;
       } else {
         if(kc::gamesRefreshOutputs(Lf)) return 1;
-        k_hash_eval<<<warpBlocks, 128, 0, hs>>>(ch.gCnt, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, H[h].policy, H[h].winLoss);
+        k_hash_eval<<<warpBlocks, 128, 0, hs>>>(ch.gCnt, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, H[h].policy, H[h].winLoss, H[h].misc, nullptr);
         S->launches += 2;
       }
-      if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
+      if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
       else k_expand_backup<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
       S->launches++;
     }
@@ -1379,6 +1640,11 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->valueWeightExponent >= 0.0 && p->valueWeightExponent <= 1.0, "kc_search_create: valueWeightExponent must be within 0..1");
   KC_CHECK(p->rootPolicyTemperature >= 0.0 && p->rootPolicyTemperatureEarly >= 0.0 && p->rootDesiredPerChildVisitsCoeff >= 0.0, "kc_search_create: negative root option");
   KC_CHECK(p->subtreeValueBiasFactor == 0.0 || p->subtreeValueBiasWeightExponent > 0.0, "kc_search_create: subtreeValueBiasWeightExponent must be positive");
+  KC_CHECK(!p->useLcbForSelection || (p->lcbStdevs > 0.0 && p->minVisitPropForLCB >= 0.0), "kc_search_create: useLcbForSelection needs lcbStdevs > 0 and minVisitPropForLCB >= 0");
+  KC_CHECK(p->rootNumSymmetriesToSample >= 0 && p->rootNumSymmetriesToSample <= 8, "kc_search_create: rootNumSymmetriesToSample must be within 0..8");
+  KC_CHECK(!p->useUncertainty || (p->uncertaintyCoeff > 0.0 && p->uncertaintyExponent >= 0.0 && p->uncertaintyMaxWeight >= 1.0),
+           "kc_search_create: useUncertainty needs uncertaintyCoeff > 0, uncertaintyExponent >= 0 and uncertaintyMaxWeight >= 1");
+  KC_CHECK(!p->useNoisePruning, "kc_search_create: useNoisePruning (pruneNoiseWeight, searchupdatehelpers.cpp:422-470) is not built; the self-play configuration leaves it off (setup.cpp:525)");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
   S->ctx = ctx; S->handle = handleOrNull;
@@ -1395,11 +1661,18 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.moveTemp = p->chosenMoveTemperature; c.moveTempEarly = p->chosenMoveTemperatureEarly; c.moveSubtract = p->chosenMoveSubtract; c.movePrune = p->chosenMovePrune;
   c.boardArea = xSize * ySize;
   const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);
+  c.useLcb = p->useLcbForSelection ? 1 : 0; c.nonBuggyLcb = p->useNonBuggyLcb ? 1 : 0; c.lcbStdevs = p->lcbStdevs; c.minVisitPropLcb = p->minVisitPropForLCB;
+  c.rootSyms = p->rootNumSymmetriesToSample > 1 ? std::min(8, p->rootNumSymmetriesToSample) : 1;
+  c.noisePruning = p->useNoisePruning ? 1 : 0;
+  c.useUncertainty = p->useUncertainty ? 1 : 0; c.uncCoeff = p->uncertaintyCoeff; c.uncExp = p->uncertaintyExponent; c.uncMaxWeight = p->uncertaintyMaxWeight;
   // every option beyond plain PUCT runs on the node-centric statistics of graph mode
-  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0 || c.vwExp != 0.0) ? 1 : 0;
+  c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0 || c.vwExp != 0.0 || c.useLcb || c.rootSyms > 1 ||
+             c.useUncertainty) ? 1 : 0;
+  // graph mode under the reference's move-choice schedule (or LCB): the move is chosen from the full getPlaySelectionValues
+  c.fullPlaySelection = (c.graph && (c.useLcb || c.moveTemp > 0.0 || c.moveTempEarly > 0.0)) ? 1 : 0;
   c.useTable = p->useGraphSearch ? 1 : 0;
   c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent; c.biasFreeProp = p->subtreeValueBiasFreeProp;
-  c.polOff = c.graph ? 80 : 32 + 8 * c.P;
+  c.polOff = c.graph ? GRAPH_POL_OFF : 32 + 8 * c.P;
   c.nodeStride = (c.polOff + 13 * c.P + 15) / 16 * 16;
   // graph mode with re-use: a kept subgraph can hold nodes whose creating visits went through another root child, so the
   // pool is a quarter larger than maxVisits; a visit that finds it empty is dropped (the oracle does the same)
@@ -1457,6 +1730,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
   KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
+  KC_CUDA(cudaMalloc(&S->d_psv, n * c.P * 8)); KC_CUDA(cudaMemset(S->d_psv, 0, n * c.P * 8));
+  if(c.rootSyms > 1) { KC_CUDA(cudaMalloc(&S->d_rootAccPolicy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_rootAccScalars, n * 16)); }
   KC_CUDA(cudaEventCreate(&S->ev0)); KC_CUDA(cudaEventCreate(&S->ev1));
   {
     // two half batches when each still gives every SM pair a work item of the trunk kernel (bf16 path with device-side batching);
@@ -1492,6 +1767,7 @@ int kc_search_destroy(kc_search* S) {
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
+  cudaFree(S->d_psv); cudaFree(S->d_rootAccPolicy); cudaFree(S->d_rootAccScalars);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
   for(int h = 0; h < 2; h++) { if(S->leafHalf[h]) { cudaStreamSynchronize(S->leafHalf[h]->stream); kc_games_destroy(S->leafHalf[h]); } if(S->evJoin[h]) cudaEventDestroy(S->evJoin[h]); }
   if(S->evFork) cudaEventDestroy(S->evFork);
@@ -1583,8 +1859,8 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     KC_CUDA(cudaMemsetAsync(S->tree.active, 0, 8, st));
     if(!c.reuseTree && clearTables(S, st)) return 1;   // with re-use the re-rooting keeps the tables in step with the graph
     if(runVisits(S)) return 1;
-    if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
-    else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen);
+    if(isStatic5(R->geom)) k_choose_play<StaticDims<5, 5, 4>><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen, S->d_psv);
+    else k_choose_play<DynDims><<<blocks, 128, 0, st>>>(R->geom, c, R->st, S->tree, S->train, R->d_zob, S->d_chosen, S->d_psv);
     S->launches++;
     if(c.reuseTree) {
       if(c.graph) {
@@ -1666,6 +1942,14 @@ int kc_search_read_training_rows(kc_search* S, int* numRows, int* numDropped, ui
     if(valueTargetsNCHW) KC_CUDA(cudaMemcpy(valueTargetsNCHW, t.outValue, rows * 5 * g.HW, cudaMemcpyDeviceToHost));
   }
   if(clear) KC_CUDA(cudaMemset(t.rowCount, 0, 8));
+  return 0;
+}
+
+int kc_search_read_play_selection(kc_search* S, double* playSelection) {
+  KC_CHECK(S && playSelection, "kc_search_read_play_selection: null argument");
+  KC_CUDA(cudaSetDevice(S->ctx->device));
+  KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
+  KC_CUDA(cudaMemcpy(playSelection, S->d_psv, (size_t)S->cfg.numGames * S->cfg.P * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 

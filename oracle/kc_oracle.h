@@ -238,7 +238,17 @@ typedef struct {
   double fpuParentWeightByVisitedPolicyPow, rootDesiredPerChildVisitsCoeff, valueWeightExponent;
   uint64_t noiseSeed, noiseGameId;   /* oracle only (one game per call): what kc_search_reset's seed and the game id are on the device */
   int32_t nnRandomize, pad3_;        /* leaves evaluated under a symmetry drawn from (noiseSeed, sit-hash) */
-} ko_search_params;   /* same layout as kc_search_params */
+  /* the rest of cpp/configs/training/selfplay1.cfg:144-185 and of the GTP / analysis defaults (setup.cpp:520-560) */
+  int32_t useLcbForSelection, useNonBuggyLcb;
+  double lcbStdevs, minVisitPropForLCB;
+  int32_t rootNumSymmetriesToSample, useNoisePruning;   /* useNoisePruning: only its effect on the root's prune step (pruneNoiseWeight itself is not restated) */
+  int32_t useUncertainty, pad4_;
+  double uncertaintyCoeff, uncertaintyExponent, uncertaintyMaxWeight;
+  double chosenMoveSubtract, chosenMovePrune;           /* also applied to the root's children in recomputeNodeStats when the root is noised */
+} ko_search_params;
+void ko_search_last_play_selection(double* out, int P);
+int ko_search_choose_values(const double* values, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
+                            double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId);
 void ko_search_run(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
                    int32_t* rootVisits, double* rootUtilitySum, int32_t* edgeVisits, double* edgeUtilitySum, float* policyOut,
                    uint8_t* orderOut, uint64_t counters[3] /* += visits, evaluations, terminal visits */);

@@ -100,6 +100,8 @@ def lib():
         l.ko_search_run.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_search_choose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
         l.ko_search_choose_temperature.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
+        l.ko_search_choose_values.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
+        l.ko_search_last_play_selection.argtypes = [vp, C.c_int]
         l.ko_search_run_graph.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         l.ko_graph_hash.argtypes = [vp, vp, C.c_int, vp]
         l.ko_game_recent_move_pos.argtypes = [vp, C.c_int]
@@ -389,7 +391,11 @@ class SearchParams(C.Structure):
                 ("rootDirichletNoiseTotalConcentration", C.c_double), ("rootDirichletNoiseWeight", C.c_double),
                 ("rootPolicyTemperature", C.c_double), ("rootPolicyTemperatureEarly", C.c_double), ("chosenMoveTemperatureHalflife", C.c_double),
                 ("fpuParentWeightByVisitedPolicyPow", C.c_double), ("rootDesiredPerChildVisitsCoeff", C.c_double), ("valueWeightExponent", C.c_double),
-                ("noiseSeed", C.c_uint64), ("noiseGameId", C.c_uint64), ("nnRandomize", C.c_int32), ("pad3_", C.c_int32)]   # oracle-only tail
+                ("noiseSeed", C.c_uint64), ("noiseGameId", C.c_uint64), ("nnRandomize", C.c_int32), ("pad3_", C.c_int32),   # oracle-only tail
+                ("useLcbForSelection", C.c_int32), ("useNonBuggyLcb", C.c_int32), ("lcbStdevs", C.c_double), ("minVisitPropForLCB", C.c_double),
+                ("rootNumSymmetriesToSample", C.c_int32), ("useNoisePruning", C.c_int32), ("useUncertainty", C.c_int32), ("pad4_", C.c_int32),
+                ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double),
+                ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double)]
 
 
 def _with_extras(sp, extra):
@@ -426,7 +432,14 @@ def search_run_graph(game, max_visits, model=None, cpuct=1.0, fpu=0.2, root_fpu=
     lib().ko_search_run_graph(game._g, game.W, game.H, C.byref(sp), None if model is None else model._m, _p(rv), _p(rw), _p(ev), _p(ew),
                               _p(pol), _p(order), _p(cnt), _p(dg))
     return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
-            "counters": cnt, "digest": int(dg[0])}
+            "counters": cnt, "digest": int(dg[0]), "playSelection": _last_play_selection(P)}
+
+
+def _last_play_selection(P):
+    """Search::getPlaySelectionValues at the root of the graph search that just ran on this thread (see ko_search.cpp)."""
+    out = np.zeros(P, np.float64)
+    lib().ko_search_last_play_selection(_p(out), P)
+    return out
 
 
 class PersistentGraphSearch:
@@ -450,7 +463,7 @@ class PersistentGraphSearch:
         lib().ko_graph_search_continue(self._s, game._g, None if model is None else model._m, _p(rv), _p(rw), _p(ev), _p(ew), _p(pol), _p(order),
                                        _p(cnt), _p(dg))
         return {"rootVisits": int(rv[0]), "rootUtilitySum": float(rw[0]), "edgeVisits": ev, "edgeUtilitySum": ew, "policy": pol, "order": order,
-                "counters": cnt, "digest": int(dg[0])}
+                "counters": cnt, "digest": int(dg[0]), "playSelection": _last_play_selection(P)}
 
     def advance(self, move_pos):
         lib().ko_graph_search_advance(self._s, int(move_pos))
@@ -491,6 +504,12 @@ class PersistentSearch:
 def search_choose(edge_visits, order, ply, temperature_plies, seed, game_id):
     ev = np.ascontiguousarray(edge_visits, np.int32); od = np.ascontiguousarray(order, np.uint8)
     return lib().ko_search_choose(_p(ev), _p(od), len(ev), ply, temperature_plies, seed, game_id)
+
+
+def search_choose_values(values, order, board_area, ply, temp_early, temp_late, halflife, subtract, prune, seed, game_id):
+    """The move choice under the temperature schedule on full play-selection values (doubles)."""
+    v = np.ascontiguousarray(values, np.float64); od = np.ascontiguousarray(order, np.uint8)
+    return lib().ko_search_choose_values(_p(v), _p(od), len(v), board_area, ply, temp_early, temp_late, halflife, subtract, prune, seed, game_id)
 
 
 def search_choose_temperature(edge_visits, order, board_area, ply, temp_early, temp_late, halflife, subtract, prune, seed, game_id):

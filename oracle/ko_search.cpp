@@ -49,19 +49,23 @@ double butterfly(double part[32]) {
 }
 
 constexpr uint64_t SYM_SALT = 0x5A11E7C0FFEEULL;
+constexpr uint64_t ROOTSYM_SALT = 0x7007575E5A17ULL;
 struct Evaluator {
   const ko_model* model;   // null: integer-hash evaluator
   int W, H, P, LW;
   bool randomSym = false;  // nnRandomize (nneval.cpp:515-524): symmetry drawn from the position's sit-hash and the seed
   uint64_t seed = 0;
-  // fills policy [P] (-1 illegal) and (whiteWin, whiteLoss) for the position in g (player to move = next player)
-  void eval(const ko_game* g, float* policy, float winLoss[2]) const {
+  // fills policy [P] (-1 illegal), (whiteWin, whiteLoss) and, if asked, shorttermWinlossError for the position in g (player to move =
+  // next player).  forcedSym >= 0: evaluate under exactly that symmetry (the root's rootNumSymmetriesToSample evaluations); the
+  // integer-hash evaluator then mixes the symmetry into its hash, so a wrong symmetry choice shows up as a different result.
+  void eval(const ko_game* g, float* policy, float winLoss[2], int forcedSym = -1, float* shortErr = nullptr) const {
     std::vector<uint32_t> legal(LW);
     const int pla = ko_game_next_pla(g);
     ko_game_legal_mask(g, pla, legal.data());
     if(!model) {
       uint64_t h[2];
       ko_game_sit_hash(g, pla, h);
+      if(forcedSym >= 0) { h[0] ^= ko_splitmix64(ROOTSYM_SALT + (uint64_t)forcedSym); h[1] ^= ko_splitmix64(ROOTSYM_SALT * 3 + (uint64_t)forcedSym); }
       int sum = 0;
       for(int pos = 0; pos < P; pos++)
         if((legal[pos >> 5] >> (pos & 31)) & 1u) sum += 1 + (int)((ko_splitmix64(h[0] ^ ((uint64_t)(pos + 1) * PHI)) >> 20) & 255);
@@ -73,20 +77,23 @@ struct Evaluator {
       const uint64_t r = ko_splitmix64(h[1]);
       winLoss[0] = (float)(r & 0xFFFF) * (1.0f / 131072.0f);
       winLoss[1] = (float)((r >> 16) & 0xFFFF) * (1.0f / 131072.0f);
+      if(shortErr) *shortErr = (float)((r >> 32) & 0xFFFF) * (1.0f / 131072.0f);   // [0, 0.5)
       return;
     }
     std::vector<float> planes((size_t)15 * W * H), own((size_t)W * H);
     float glob = 0.f, value[2], misc[2];
     ko_game_fill_row_v1(g, pla, W, H, 0, planes.data(), &glob);
     int8_t sym = 0;
-    if(randomSym) {
+    if(forcedSym >= 0) sym = (int8_t)forcedSym;
+    else if(randomSym) {
       uint64_t h[2];
       ko_game_sit_hash(g, pla, h);
       sym = (int8_t)(ko_splitmix64(seed ^ h[0] ^ SYM_SALT) & 7);
     }
-    ko_model_forward(model, 1, W, H, 0, planes.data(), &glob, randomSym ? &sym : nullptr, policy, value, misc, own.data(), 0, 1);
+    ko_model_forward(model, 1, W, H, 0, planes.data(), &glob, (randomSym || forcedSym >= 0) ? &sym : nullptr, policy, value, misc, own.data(), 0, 1);
     ko_postprocess(policy, P, legal.data(), 1.0f, value, misc, pla);
     winLoss[0] = value[0]; winLoss[1] = value[1];
+    if(shortErr) *shortErr = misc[1];
   }
 };
 
@@ -392,10 +399,14 @@ double valueWeightPow(double x, double e) {
   return detExp(e * detLog(x));
 }
 
+thread_local std::vector<double> g_lastPlaySelection;
+
 struct GNode {
   bool noised = false;
   int visits = 0, numChildren = 0, nextPla = 0, biasEntry = -1, depth = 0;
   double weightSum = 0.0, utilityAvg = 0.0, nnUtility = 0.0, lastDelta = 0.0, lastWeight = 0.0;
+  double utilitySqAvg = 0.0, weightSqSum = 0.0;   // NodeStats::utilitySqAvg / weightSqSum (searchnode.h:44-48): what LCB reads
+  double nnWeight = 1.0;                          // computeWeightFromNNOutput (searchupdatehelpers.cpp:91-113): 1 without useUncertainty
   Key key = Key(0, 0);
   std::vector<float> policy;
   std::vector<int> child, edgeN;
@@ -443,50 +454,85 @@ struct GraphSearch {
     if(c >= 0) { cv = nodes[c].visits; cw = nodes[c].weightSum; cu = nodes[c].utilityAvg; }
     else { cv = nd.edgeN[pos]; cw = (double)nd.edgeN[pos]; cu = terminalValue(-2 - c); }
   }
+  // the same with utilitySqAvg and weightSqSum; a terminal child is a node that got addLeafValue(result, weight 1) on every visit
+  void childStatsSq(const GNode& nd, int pos, int& cv, double& cw, double& cu, double& cusq, double& cwsq) const {
+    const int c = nd.child[pos];
+    if(c >= 0) { cv = nodes[c].visits; cw = nodes[c].weightSum; cu = nodes[c].utilityAvg; cusq = nodes[c].utilitySqAvg; cwsq = nodes[c].weightSqSum; }
+    else { cv = nd.edgeN[pos]; cw = (double)nd.edgeN[pos]; cu = terminalValue(-2 - c); cusq = cu * cu; cwsq = (double)nd.edgeN[pos]; }
+  }
+  // computeWeightFromNNOutput (searchupdatehelpers.cpp:91-113) with Coffee's outputs: no score term
+  double nnWeightOf(float shorttermWinlossError) const {
+    if(!p->useUncertainty) return 1.0;
+    const double unc = (double)shorttermWinlossError;   // winLossUtilityFactor 1
+    const double powered = p->uncertaintyExponent == 1.0 ? unc : p->uncertaintyExponent == 0.5 ? std::sqrt(unc) : (unc <= 0.0 ? 0.0 : detExp(p->uncertaintyExponent * detLog(unc)));
+    const double baseline = p->uncertaintyCoeff / p->uncertaintyMaxWeight;
+    return p->uncertaintyCoeff / (powered + baseline);
+  }
   static double childWeight(double cw, int e, int cv) { return cw * ((double)e / (double)std::max(cv, 1)); }
 
-  void recompute(GNode& nd, int inc = 1) {
+  // recomputeNodeStats (searchupdatehelpers.cpp:151-326).  Canonical order of the order-dependent sums: lane = policy index mod 32,
+  // then the xor butterfly (what a warp does); the reference walks the children in creation order.
+  void recompute(GNode& nd, int inc = 1, bool isRoot = false) {
     double partW[32] = {0}, partWU[32] = {0};
+    double maxW = 0.0;
+    std::vector<double> w(P, 0.0);
     for(int pos = 0; pos < P; pos++)
       if(nd.child[pos] != -1) {
         int cv; double cw, cu;
         childStats(nd, pos, cv, cw, cu);
         const int e = nd.edgeN[pos];
         if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
-        const double w = childWeight(cw, e, cv);
-        partW[pos & 31] = partW[pos & 31] + w;
-        partWU[pos & 31] = partWU[pos & 31] + w * cu;
+        w[pos] = childWeight(cw, e, cv);
+        if(w[pos] > maxW) maxW = w[pos];
+        partW[pos & 31] = partW[pos & 31] + w[pos];
+        partWU[pos & 31] = partWU[pos & 31] + w[pos] * cu;
       }
     const double sumW = butterfly(partW);
     double sumWU = butterfly(partWU);
-    if(p->valueWeightExponent != 0.0 && sumW > 0.0) {
-      // re-weight the children by how plausible their utility is next to their siblings'; the total weight stays sumW
+    // at a noised root the children the move choice would prune / reduce lose the same weight here (:196-206)
+    double amountToSubtract = 0.0, amountToPrune = 0.0;
+    if(isRoot && p->rootNoiseEnabled && !p->useNoisePruning) {
+      amountToSubtract = std::min(p->chosenMoveSubtract, maxW / 64.0);
+      amountToPrune = std::min(p->chosenMovePrune, maxW / 64.0);
+    }
+    const bool reweigh = sumW > 0.0 && (p->valueWeightExponent != 0.0 || amountToSubtract > 0.0 || amountToPrune > 0.0);
+    std::vector<double> nw(w);
+    if(reweigh) {
+      // downweightBadChildrenAndNormalizeWeight (:330-417): prune / subtract, then (valueWeightExponent) a child keeps
+      // weight * cdf(z)^exponent, z = its utility's distance from the siblings' weighted mean in standard errors; the total stays sumW
       const double simpleValue = sumWU / sumW;   // selfUtility is +-utility, handled through the sign below
       double partN[32] = {0};
-      std::vector<double> nw(P, 0.0);
-      for(int pos = 0; pos < P; pos++)
-        if(nd.child[pos] != -1) {
+      for(int pos = 0; pos < P; pos++) {
+        if(w[pos] == 0.0) continue;
+        double x = w[pos];
+        if(x < amountToPrune) x = 0.0;
+        else { x = x - amountToSubtract; if(x <= 0.0) x = 0.0; }
+        if(x > 0.0 && p->valueWeightExponent != 0.0) {
           int cv; double cw, cu;
           childStats(nd, pos, cv, cw, cu);
-          const int e = nd.edgeN[pos];
-          if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
-          const double w = childWeight(cw, e, cv);
-          const double stdev = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt(w)));
+          const double stdev = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt(w[pos])));
           const double diff = nd.nextPla == 2 ? cu - simpleValue : simpleValue - cu;   // selfUtility - simpleValue (own view)
           const double pr = tcdf().get(diff / stdev) + 0.0001;
-          nw[pos] = w * valueWeightPow(pr, p->valueWeightExponent);
-          partN[pos & 31] = partN[pos & 31] + nw[pos];
+          x = x * valueWeightPow(pr, p->valueWeightExponent);
         }
+        nw[pos] = x;
+        partN[pos & 31] = partN[pos & 31] + x;
+      }
       const double factor = sumW / butterfly(partN);
-      double partU[32] = {0};
-      for(int pos = 0; pos < P; pos++)
-        if(nw[pos] != 0.0) {
-          int cv; double cw, cu;
-          childStats(nd, pos, cv, cw, cu);
-          partU[pos & 31] = partU[pos & 31] + (nw[pos] * factor) * cu;
-        }
-      sumWU = butterfly(partU);
+      for(int pos = 0; pos < P; pos++) nw[pos] = nw[pos] * factor;
     }
+    double partU[32] = {0}, partUSq[32] = {0}, partWSq[32] = {0};
+    for(int pos = 0; pos < P; pos++)
+      if(nw[pos] != 0.0) {
+        int cv; double cw, cu, cusq, cwsq;
+        childStatsSq(nd, pos, cv, cw, cu, cusq, cwsq);
+        const double scaling = nw[pos] / cw;
+        partU[pos & 31] = partU[pos & 31] + nw[pos] * cu;
+        partUSq[pos & 31] = partUSq[pos & 31] + nw[pos] * cusq;
+        partWSq[pos & 31] = partWSq[pos & 31] + (scaling * scaling) * cwsq;
+      }
+    if(reweigh) sumWU = butterfly(partU);
+    const double sumWUSq = butterfly(partUSq), sumWSq = butterfly(partWSq);
     double utility = nd.nnUtility;
     if(p->subtreeValueBiasFactor != 0.0 && nd.biasEntry >= 0) {
       BiasEntry& E = bias[nd.biasEntry];
@@ -500,9 +546,106 @@ struct GraphSearch {
       }
       if(E.weightSum > 0.001) utility = utility + (p->subtreeValueBiasFactor * E.deltaSum) / E.weightSum;
     }
-    nd.utilityAvg = (sumWU + utility) / (sumW + 1.0);
-    nd.weightSum = sumW + 1.0;
+    const double w0 = nd.nnWeight;
+    const double weightSum = sumW + w0;
+    nd.utilityAvg = (sumWU + utility * w0) / weightSum;
+    nd.utilitySqAvg = (sumWUSq + (utility * utility) * w0) / weightSum;
+    nd.weightSqSum = sumWSq + w0 * w0;
+    nd.weightSum = weightSum;
     nd.visits += inc;
+  }
+
+  // Search::getPlaySelectionValues at the root (cpp/search/searchresults.cpp:66-231): the value of a move is its child's weight; the
+  // children other than the most stably explored one are cut down to the weight the final explore-selection value of that one
+  // would have asked for (getReducedPlaySelectionWeight, searchexplorehelpers.cpp:209-243, rounded up); with useLcbForSelection
+  // the child with the best lower confidence bound (getSelfUtilityLCBAndRadius, searchhelpers.cpp:469-522) is raised above every
+  // child it beats.  Canonical: children are walked in policy-index order with creation order breaking ties (the reference walks
+  // creation order with strict comparisons -- the same choice); cpuctUtilityStdevScale 0, no pass, no score utility.
+  void playSelectionValues(double* psv) const {
+    const GNode& nd = nodes[0];
+    std::vector<double> lcb(P, 0.0), radius(P, 0.0);
+    double total = 0.0;
+    int n = 0;
+    for(int pos = 0; pos < P; pos++) {
+      psv[pos] = 0.0;
+      if(nd.child[pos] == -1) continue;
+      int cv; double cw, cu;
+      childStats(nd, pos, cv, cw, cu);
+      psv[pos] = childWeight(cw, nd.edgeN[pos], cv);
+      total = total + psv[pos];
+      n++;
+    }
+    if(n == 0) return;
+    int best = -1, bestOrd = 1 << 20;
+    double bestWeight = -1e30, maxGoodness = -1e30;
+    for(int pos = 0; pos < P; pos++) {
+      if(nd.child[pos] == -1) continue;
+      const double e = (double)nd.edgeN[pos];
+      const double g = (psv[pos] * std::max(0.0, e - 1.0)) / std::max(1.0, e) + 2.0 * (double)nd.policy[pos];
+      if(g > maxGoodness || (g == maxGoodness && nd.order[pos] < bestOrd)) { maxGoodness = g; bestWeight = psv[pos]; best = pos; bestOrd = nd.order[pos]; }
+    }
+    const int pla = nd.nextPla;
+    {
+      const double scaling = p->cpuctExploration * std::sqrt(total + 0.01);
+      int cv; double cw, cu;
+      childStats(nd, best, cv, cw, cu);
+      const double bestValue = (scaling * (double)nd.policy[best]) / (1.0 + psv[best]) + (pla == 2 ? cu : -cu);
+      for(int pos = 0; pos < P; pos++) {
+        if(nd.child[pos] == -1 || pos == best) continue;
+        childStats(nd, pos, cv, cw, cu);
+        double reduced = 0.0;
+        if(cv > 0 && psv[pos] > 0.0) {
+          double wanted = 0.0;
+          if(nd.policy[pos] >= 0) {
+            const double exploreComponent = bestValue - (pla == 2 ? cu : -cu);
+            if(exploreComponent <= 0) wanted = 1e100;
+            else { wanted = (scaling * (double)nd.policy[pos]) / exploreComponent - 1.0; if(wanted < 0) wanted = 0.0; }
+          }
+          reduced = psv[pos] > wanted ? wanted : psv[pos];
+        }
+        psv[pos] = std::ceil(reduced);
+      }
+    }
+    if(!p->useLcbForSelection) return;
+    double bestLcb = -1e10;
+    int bestLcbPos = -1, bestLcbOrd = 1 << 20;
+    for(int pos = 0; pos < P; pos++) {
+      if(nd.child[pos] == -1) continue;
+      int cv; double cw, cu, cusq, cwsq;
+      childStatsSq(nd, pos, cv, cw, cu, cusq, cwsq);
+      const double ratio = (double)nd.edgeN[pos] / (double)std::max(cv, 1);
+      double weightSum = cw * ratio, weightSqSum = cwsq * ratio;
+      radius[pos] = (2.0 * 1.0) * p->lcbStdevs;   // utilityRangeRadius = winLossUtilityFactor = 1
+      lcb[pos] = -radius[pos];
+      if(!(cv <= 0 || weightSum <= 0.0 || weightSqSum <= 0.0)) {
+        double ess = (weightSum * weightSum) / weightSqSum;
+        const double priorWeight = weightSum / ((ess * ess) * ess);
+        double usq = std::max(cusq, cu * cu + 1e-8);
+        usq = (usq * weightSum + (usq + 1.0) * priorWeight) / (weightSum + priorWeight);
+        weightSum = weightSum + priorWeight;
+        weightSqSum = weightSqSum + priorWeight * priorWeight;
+        ess = (weightSum * weightSum) / weightSqSum;
+        const double selfUtility = pla == 2 ? cu : -cu;
+        const double variance = usq - cu * cu;
+        const double r = std::sqrt(variance / ess) * p->lcbStdevs;
+        lcb[pos] = selfUtility - r;
+        radius[pos] = r;
+      }
+      if(psv[pos] > 0 && psv[pos] >= p->minVisitPropForLCB * bestWeight)
+        if(lcb[pos] > bestLcb || (lcb[pos] == bestLcb && nd.order[pos] < bestLcbOrd)) { bestLcb = lcb[pos]; bestLcbPos = pos; bestLcbOrd = nd.order[pos]; }
+    }
+    // useNonBuggyLcb false: the historical bug that never promotes the first-created child
+    if(bestLcbPos < 0 || (!p->useNonBuggyLcb && nd.order[bestLcbPos] == 0)) return;
+    double adjusted = psv[bestLcbPos];
+    for(int pos = 0; pos < P; pos++) {
+      if(nd.child[pos] == -1 || pos == bestLcbPos) continue;
+      const double excess = bestLcb - lcb[pos];
+      if(excess < 0) continue;
+      const double factor = (radius[pos] + excess) / (radius[pos] + 0.20 * excess);
+      const double lbound = (factor * factor) * psv[pos];
+      if(lbound > adjusted) adjusted = lbound;
+    }
+    psv[bestLcbPos] = adjusted;
   }
 
   // Search::makeMove with tree re-use in graph mode (search.cpp:262-331) followed by the next beginSearch's
@@ -555,8 +698,8 @@ struct GraphSearch {
       for(int d = hi; d >= lo; d--)
         for(GNode& n : nodes)
           if(n.depth == d) {
-            if(n.numChildren == 0) n.utilityAvg = n.nnUtility;
-            else recompute(n, 0);
+            if(n.numChildren == 0) { n.utilityAvg = n.nnUtility; n.utilitySqAvg = n.nnUtility * n.nnUtility; }
+            else recompute(n, 0, &n == &nodes[0]);
           }
     }
   }
@@ -575,9 +718,10 @@ static uint64_t graphDigest(const GraphSearch& S) {
   uint64_t h = 0;
   for(size_t i = 0; i < S.nodes.size(); i++) {
     const GNode& nd = S.nodes[i];
-    uint64_t wb, ub;
-    memcpy(&wb, &nd.weightSum, 8); memcpy(&ub, &nd.utilityAvg, 8);
-    uint64_t nh = ko_splitmix64((uint64_t)nd.visits ^ ((uint64_t)nd.numChildren << 32)) ^ ko_splitmix64(wb ^ PHI) ^ ko_splitmix64(ub + PHI);
+    uint64_t wb, ub, qb, sb;
+    memcpy(&wb, &nd.weightSum, 8); memcpy(&ub, &nd.utilityAvg, 8); memcpy(&qb, &nd.utilitySqAvg, 8); memcpy(&sb, &nd.weightSqSum, 8);
+    uint64_t nh = ko_splitmix64((uint64_t)nd.visits ^ ((uint64_t)nd.numChildren << 32)) ^ ko_splitmix64(wb ^ PHI) ^ ko_splitmix64(ub + PHI) ^
+                  ko_splitmix64(qb ^ (PHI << 1)) ^ ko_splitmix64(sb + (PHI << 1));
     for(int pos = 0; pos < P; pos++)
       if(nd.child[pos] != -1)
         nh ^= ko_splitmix64(((uint64_t)(uint32_t)nd.child[pos] << 32 | (uint64_t)(uint32_t)nd.edgeN[pos]) + (uint64_t)(pos + 1) * PHI + nd.order[pos]);
@@ -600,6 +744,43 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
   ko_game* before = ko_game_create(x_size, y_size, 4);
   std::vector<float> pol(P);
   float wl[2];
+  float shortErr = 0.f;
+  if(!ko_game_finished(rootGame) && p->rootNumSymmetriesToSample > 1 && (S.nodes.empty() || !S.nodes[0].noised)) {
+    // initNodeNNOutput at the root (searchnnhelpers.cpp:67-83; for a root kept by tree re-use maybeRecomputeExistingNNOutput :133-174):
+    // the root is evaluated under rootNumSymmetriesToSample distinct symmetries -- a partial Fisher-Yates shuffle of 0..7 -- and
+    // the outputs are averaged (NNOutput's averaging constructor, nninputs.cpp:95-170: float sums in order, then / n).  Canonical:
+    // the draws come from a counter stream keyed by (seed, game id, ply) instead of the search thread's generator.
+    const int N = std::min(8, p->rootNumSymmetriesToSample);
+    int idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    uint64_t st = ko_splitmix64(S.seed ^ (S.gameId * PHI) ^ (uint64_t)ko_game_num_turns(rootGame) ^ ROOTSYM_SALT);
+    std::vector<float> acc(P, 0.0f), one(P);
+    float aw = 0.f, al = 0.f, ae = 0.f;
+    for(int i = 0; i < N; i++) {
+      st += PHI;
+      const int j = i + (int)(ko_splitmix64(st) % (uint64_t)(8 - i));
+      std::swap(idx[i], idx[j]);
+      float w2[2], e1 = 0.f;
+      ev.eval(rootGame, one.data(), w2, idx[i], &e1);
+      for(int pos = 0; pos < P; pos++) acc[pos] += one[pos];
+      aw += w2[0]; al += w2[1]; ae += e1;
+    }
+    const float fl = (float)N;
+    for(int pos = 0; pos < P; pos++) acc[pos] /= fl;
+    aw /= fl; al /= fl; ae /= fl;
+    const double v = (double)aw - (double)al;
+    if(S.nodes.empty()) {   // a fresh root: this is its evaluation and its first visit
+      S.nodes.emplace_back(P);
+      GNode& nn = S.nodes.back();
+      nn.visits = 1; nn.nnUtility = v; nn.nextPla = ko_game_next_pla(rootGame); nn.depth = ko_game_num_turns(rootGame);
+      nn.nnWeight = S.nnWeightOf(ae);
+      nn.weightSum = nn.nnWeight; nn.weightSqSum = nn.nnWeight * nn.nnWeight; nn.utilityAvg = v; nn.utilitySqAvg = v * v;
+      cnt[0]++;
+    } else {                // a kept root: new policy and evaluation, statistics untouched until the next re-computation (isReInit)
+      S.nodes[0].nnUtility = v; S.nodes[0].nnWeight = S.nnWeightOf(ae);
+    }
+    for(int pos = 0; pos < P; pos++) S.nodes[0].policy[pos] = acc[pos];
+    cnt[1] += (uint64_t)N;
+  }
   if(!ko_game_finished(rootGame)) S.maybeNoiseRoot(rootGame);
   for(int it = 0; it < p->maxVisits && !ko_game_finished(rootGame); it++) {
     ko_game_copy(g, rootGame);
@@ -688,12 +869,13 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
     if((kind == 1 || kind == 4) && S.nodes.size() >= maxNodes) continue;   // node pool exhausted (re-use in graph mode only): the visit is dropped
     int newIdx = -1;
     if(kind == 1 || kind == 4) {
-      ev.eval(g, pol.data(), wl);
+      ev.eval(g, pol.data(), wl, -1, &shortErr);
       v = (double)wl[0] - (double)wl[1];
       newIdx = (int)S.nodes.size();
       S.nodes.emplace_back(P);
       GNode& nn = S.nodes.back();
-      nn.visits = 1; nn.weightSum = 1.0; nn.nnUtility = v; nn.nextPla = ko_game_next_pla(g);
+      nn.nnWeight = S.nnWeightOf(shortErr);
+      nn.visits = 1; nn.weightSum = nn.nnWeight; nn.weightSqSum = nn.nnWeight * nn.nnWeight; nn.nnUtility = v; nn.nextPla = ko_game_next_pla(g);
       nn.key = kind == 1 ? leafKey : Key(0, 0); nn.depth = ko_game_num_turns(g);
       for(int pos = 0; pos < P; pos++) nn.policy[pos] = pol[pos];
       double utility = v;
@@ -704,7 +886,7 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
         const BiasEntry& E = S.bias[nn.biasEntry];
         if(E.weightSum > 0.001) utility = utility + (p->subtreeValueBiasFactor * E.deltaSum) / E.weightSum;   // addLeafValue :27-37
       }
-      nn.utilityAvg = utility;
+      nn.utilityAvg = utility; nn.utilitySqAvg = utility * utility;
       if(kind == 1 && p->useGraphSearch) S.table[leafKey] = newIdx;
       if(kind == 4) S.maybeNoiseRoot(rootGame);
     }
@@ -717,7 +899,7 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
         nd.numChildren++;
       }
       nd.edgeN[pos] += 1;
-      S.recompute(nd);
+      S.recompute(nd, 1, d == 0);
     }
     cnt[0]++;
     if(kind == 1 || kind == 4) cnt[1]++;
@@ -740,6 +922,13 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
   }
   if(counters) for(int i = 0; i < 5; i++) counters[i] += cnt[i];
   if(digest) *digest = graphDigest(S);
+  g_lastPlaySelection.assign(P, 0.0);
+  if(have && !ko_game_finished(rootGame)) S.playSelectionValues(g_lastPlaySelection.data());
+}
+
+// play-selection values of the root after the last graph search on this thread ([P], 0 for moves without a child)
+void ko_search_last_play_selection(double* out, int P) {
+  for(int pos = 0; pos < P; pos++) out[pos] = pos < (int)g_lastPlaySelection.size() ? g_lastPlaySelection[pos] : 0.0;
 }
 
 void ko_search_run_graph(const ko_game* rootGame, int x_size, int y_size, const ko_search_params* p, const ko_model* modelOrNull,
@@ -824,8 +1013,18 @@ int ko_search_choose(const int32_t* edgeVisits, const uint8_t* order, int P, int
 // interpolateEarly :463-467).  Canonical: the play-selection value of a move is its edge visit count (no LCB, no reduced
 // weights), candidates are walked in policy-index order, the uniform draw comes from the counter stream of ko_search_choose,
 // log / exp are detLog / detExp.  T <= 1e-4 picks the most visited move (ties: earliest created).
+int ko_search_choose_values(const double* values, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
+                            double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId);
 int ko_search_choose_temperature(const int32_t* edgeVisits, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
                                  double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId) {
+  std::vector<double> v(P);
+  for(int pos = 0; pos < P; pos++) v[pos] = (double)edgeVisits[pos];
+  return ko_search_choose_values(v.data(), order, P, boardArea, ply, tempEarly, tempLate, halflife, subtract, prune, seed, gameId);
+}
+// the same on arbitrary play-selection values (the full getPlaySelectionValues of GraphSearch::playSelectionValues)
+int ko_search_choose_values(const double* values, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,
+                            double halflife, double subtract, double prune, uint64_t seed, uint64_t gameId) {
+  const double* edgeVisits = values;
   double maxValue = 0.0;
   for(int pos = 0; pos < P; pos++) if(order[pos] != 255 && (double)edgeVisits[pos] > maxValue) maxValue = (double)edgeVisits[pos];
   if(maxValue <= 0.0) return -1;

@@ -793,7 +793,13 @@ SELFPLAY1_CFG = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10
     (5, 5, 4, 64, 120, dict(rootPolicyTemperature=0.8, rootPolicyTemperatureEarly=1.5, chosenMoveTemperatureHalflife=7.0)),
     (5, 5, 4, 64, 120, dict(fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=1.5, rootDesiredPerChildVisitsCoeff=1.0)),
     (5, 5, 4, 96, 200, dict(valueWeightExponent=0.25)),    # setup.cpp:519 default
-    (4, 5, 3, 40, 120, dict(valueWeightExponent=0.7))])
+    (4, 5, 3, 40, 120, dict(valueWeightExponent=0.7)),
+    (5, 5, 4, 96, 120, dict(rootNumSymmetriesToSample=4)),                       # selfplay1.cfg:149
+    (5, 5, 4, 64, 120, dict(SELFPLAY1_CFG, rootNumSymmetriesToSample=4, chosenMoveSubtract=0.0, chosenMovePrune=1.0)),   # + the noised root's prune step
+    (6, 6, 4, 40, 100, dict(rootNumSymmetriesToSample=8, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25,
+                            chosenMovePrune=2.0, chosenMoveSubtract=0.5)),
+    (5, 5, 4, 96, 160, dict(useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)),   # setup.cpp:545-560 (GTP defaults)
+    (5, 5, 4, 64, 160, dict(SELFPLAY1_CFG, useUncertainty=1, uncertaintyCoeff=0.2, uncertaintyExponent=0.5, uncertaintyMaxWeight=4.0, rootNumSymmetriesToSample=2))])
 def test_search_selfplay_options_bit_exact(ctx, oracle, W, H, K, G, V, opts):
     """The self-play configuration's remaining search options -- shaped Dirichlet root noise (deterministic gamma sampler), root
     policy temperature, FPU parent weighting by visited policy, rootDesiredPerChildVisitsCoeff -- on top of graph search and the
@@ -821,31 +827,43 @@ def test_search_selfplay_options_bit_exact(ctx, oracle, W, H, K, G, V, opts):
         assert got["rootVisits"][g] == ref["rootVisits"] and (got["edgeVisits"][g] == ref["edgeVisits"]).all(), g
         assert (got["order"][g] == ref["order"]).all() and got["rootUtilitySum"][g] == ref["rootUtilitySum"], g
         assert int(dig[g]) == ref["digest"], g
-    if "rootNoiseEnabled" in opts or "rootPolicyTemperature" in opts:
+    if "rootNoiseEnabled" in opts or "rootPolicyTemperature" in opts or "rootNumSymmetriesToSample" in opts:
         assert changed > 0.9 * G
     s.close()
 
 
+LCB_CFG = dict(useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1)   # selfplay1.cfg:151-153, 182
+
+
 @pytest.mark.gpu
-def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
-    """selfplay1.cfg's search options together with tree re-use, self-played to the end: fresh noise on every new root, moves,
-    counters and the re-rooted graphs equal the oracle's."""
+@pytest.mark.parametrize("extra", [
+    {},                                                        # the temperature schedule on the full getPlaySelectionValues
+    LCB_CFG,                                                   # + LCB move selection
+    dict(LCB_CFG, rootNumSymmetriesToSample=4),                # + root symmetry averaging: the whole selfplay1.cfg:144-185 set
+    dict(LCB_CFG, useNonBuggyLcb=0, lcbStdevs=2.0, minVisitPropForLCB=0.05),   # the historical LCB form, sharper bound
+    dict(LCB_CFG, rootNumSymmetriesToSample=3, useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)])
+def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle, extra):
+    """selfplay1.cfg's search options together with tree re-use, self-played to the end: fresh noise and fresh averaged root evaluations
+    on every new root, play-selection values (reduced weights, LCB), moves, counters and the re-rooted graphs equal the oracle's."""
     from katacoffee_b200 import backend, capi
     W = H = 5
     G, V, seed, T = 48, 64, 77, 6
     MOVE = dict(chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMoveSubtract=0.0, chosenMovePrune=1.0)   # selfplay1.cfg:137-141
     s = backend.Search(ctx, None, G, W, H, 4, maxVisits=V, temperaturePlies=T, reuseTree=True, useGraphSearch=True, subtreeValueBiasFactor=0.3,
-                       subtreeValueBiasWeightExponent=0.8, cpuctExploration=1.1, rootFpuReductionMax=0.0, **SELFPLAY1_CFG, **MOVE)
+                       subtreeValueBiasWeightExponent=0.8, cpuctExploration=1.1, rootFpuReductionMax=0.0, **SELFPLAY1_CFG, **MOVE, **extra)
     s.reset(seed=seed, firstGameId=900)
     ogames = [oracle.Game(W, H, 4) for _ in range(G)]
     osearch = [oracle.PersistentGraphSearch(W, H, V, graph=True, bias_factor=0.3, bias_exponent=0.8, free_prop=0.8, cpuct=1.1, root_fpu=0.0,
-                                            noiseSeed=seed, noiseGameId=900 + g, **SELFPLAY1_CFG) for g in range(G)]
+                                            noiseSeed=seed, noiseGameId=900 + g, chosenMoveSubtract=0.0, chosenMovePrune=1.0, **SELFPLAY1_CFG, **extra)
+               for g in range(G)]
+    lcb_changed = 0
     stats = capi.SearchStats()
     ocnt = np.zeros(5, np.uint64)
     argmax = nmoves = 0
     for ply in range(W * H):
         _, chosen, _ = s.play(1, stats)
         dig = s.treeDigest()
+        psv = s.readPlaySelection()
         for g in range(G):
             og = ogames[g]
             if og.finished():
@@ -853,7 +871,9 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
                 continue
             r = osearch[g].run(og)
             ocnt += r["counters"]
-            mv = oracle.search_choose_temperature(r["edgeVisits"], r["order"], W * H, og.num_turns(), 0.75, 0.15, 19.0, 0.0, 1.0, seed, 900 + g)
+            assert (psv[g] == r["playSelection"]).all(), (ply, g, psv[g][psv[g] != r["playSelection"]], r["playSelection"][psv[g] != r["playSelection"]])
+            lcb_changed += int(np.argmax(r["playSelection"]) != np.argmax(r["edgeVisits"]))
+            mv = oracle.search_choose_values(r["playSelection"], r["order"], W * H, og.num_turns(), 0.75, 0.15, 19.0, 0.0, 1.0, seed, 900 + g)
             argmax += mv == oracle.search_choose(r["edgeVisits"], r["order"], og.num_turns(), 0, seed, 900 + g)
             nmoves += 1
             assert chosen[g] == mv, (ply, g, chosen[g], mv)
@@ -864,6 +884,8 @@ def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle):
     assert all(og.finished() for og in ogames)
     assert (stats.visits, stats.netEvals, stats.terminalVisits, stats.transpositionHits, stats.catchUpVisits) == tuple(int(x) for x in ocnt)
     assert 0.3 * nmoves < argmax < nmoves      # the temperature schedule really samples: not always, but often, the most visited move
+    if extra.get("useLcbForSelection"):
+        assert lcb_changed > 0                 # LCB did promote a move that was not the most visited one somewhere
     s.close()
 
 
@@ -1316,3 +1338,56 @@ def test_selfplay_run_native_two_pools(ctx, tmp_path):
     ha = {tuple(r) for r in a["globalTargetsNC"][:, 41:47].astype(np.int64)}
     hb = {tuple(r) for r in b["globalTargetsNC"][:, 41:47].astype(np.int64)}
     assert ha and hb and not (ha & hb)   # disjoint game hashes (ids first + pool * 2^40 + ...)
+
+
+@pytest.mark.gpu
+def test_search_root_symmetry_sampling_with_the_net(ctx, oracle):
+    """rootNumSymmetriesToSample with the real net (selfplay1.cfg:149): the root's priors are the average of four evaluations under
+    four distinct symmetries.  fp32 check path against the oracle's search (same symmetries from the counter stream, same
+    averaging): priors to 1e-4 and the same visit distribution for most games; really different from a single evaluation; the
+    tensor path (compacted batches, half-batch pipeline) agrees with the check path within its operand rounding."""
+    from katacoffee_b200 import backend, modeldesc
+    W = H = 5
+    G, V, seed = 48, 40, 31
+    model = modeldesc.Model("b2c32", seed=29)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=True)
+    got = {}
+    for n in (4, 1):
+        s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, useGraphSearch=True, rootNumSymmetriesToSample=n)
+        s.reset(seed=seed, firstGameId=70)
+        for _ in range(5):
+            s.games.step()
+        st, _, _ = s.play(1)
+        s2 = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, useGraphSearch=True, rootNumSymmetriesToSample=n)
+        s2.reset(seed=seed, firstGameId=70)
+        for _ in range(5):
+            s2.games.step()
+        s2.runVisits()
+        got[n] = s2.readRoot()
+        if n == 4:
+            assert st.netEvals >= 4 * G    # four evaluations per root on top of the leaves
+        s.close(); s2.close()
+    same = differs = 0
+    for g in range(G):
+        og = oracle.Game(W, H, 4)
+        for _ in range(5):
+            og.play(og.choose(seed, 70 + g))
+        ref = oracle.search_run_graph(og, V, model=om, graph=True, rootNumSymmetriesToSample=4, noiseSeed=seed, noiseGameId=70 + g)
+        assert np.abs(got[4]["policy"][g] - ref["policy"]).max() < 1e-4, g
+        assert got[4]["rootVisits"][g] == ref["rootVisits"] == V
+        same += (got[4]["edgeVisits"][g] == ref["edgeVisits"]).all()
+        differs += np.abs(got[4]["policy"][g] - got[1]["policy"][g]).max() > 1e-3
+    assert same >= 0.8 * G, same
+    assert differs >= 0.5 * G, differs
+    hb = backend.createComputeHandle(ctx, lm, G, W, H)
+    sb = backend.Search(ctx, hb, G, W, H, 4, maxVisits=V, useGraphSearch=True, rootNumSymmetriesToSample=4)
+    sb.reset(seed=seed, firstGameId=70)
+    for _ in range(5):
+        sb.games.step()
+    sb.runVisits()
+    rb = sb.readRoot()
+    legal = got[4]["policy"] >= 0
+    assert ((rb["policy"] >= 0) == legal).all() and np.abs(rb["policy"] - got[4]["policy"])[legal].max() < 0.03
+    sb.close(); hb.close(); h.close(); lm.close()
