@@ -427,13 +427,16 @@ def main():
         selfplay_graph = selfplay_arm("lock-step PUCT per game with the search options of cpp/configs/training/selfplay1.cfg:144-185: useGraphSearch, "
                                       "subtreeValueBiasFactor 0.30 / WeightExponent 0.8 / FreeProp 0.8, shaped Dirichlet root noise 10.83 / 0.25, root policy "
                                       "temperature 1.25 -> 1.1, fpuParentWeightByVisitedPolicy pow 2, rootDesiredPerChildVisitsCoeff 2, cpuct 1.1, root FPU "
-                                      "reduction 0, valueWeightExponent 0.5, move choice by the temperature schedule 0.75 -> 0.15 with prune 1, nnRandomize; tree re-use",
+                                      "reduction 0, valueWeightExponent 0.5, rootNumSymmetriesToSample 4, useLcbForSelection (lcbStdevs 5, minVisitPropForLCB 0.15, "
+                                      "useNonBuggyLcb), move choice from the full getPlaySelectionValues under the temperature schedule 0.75 -> 0.15 with prune 1, "
+                                      "nnRandomize; tree re-use.  Not built: nothing of that option set (useNoisePruning / useUncertainty are off in self-play, setup.cpp:525,543)",
                                       useGraphSearch=True, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightExponent=0.8, reuseTree=True,
                                       cpuctExploration=1.1, rootFpuReductionMax=0.0, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83,
                                       rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.25,
                                       chosenMoveTemperatureHalflife=19.0, fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=2.0,
                                       rootDesiredPerChildVisitsCoeff=2.0, valueWeightExponent=0.5,
-                                      chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, nnRandomize=1)
+                                      chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, nnRandomize=1,
+                                      rootNumSymmetriesToSample=4, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1)
         selfplay = selfplay_arm("lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
                                 reuseTree=True)
 

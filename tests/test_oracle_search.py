@@ -178,3 +178,54 @@ def test_oracle_value_weighting_and_fpu_options_run(oracle):
         assert r["digest"] != plain["digest"]
     wide = oracle.search_run_graph(og, 300, rootDesiredPerChildVisitsCoeff=2.0)
     assert (wide["edgeVisits"] > 0).sum() >= (plain["edgeVisits"] > 0).sum()    # the coefficient funnels visits into more root children
+
+
+def test_oracle_play_selection_values_reduced_weights_and_lcb(oracle):
+    """Search::getPlaySelectionValues as the oracle restates it (searchresults.cpp:66-231): without LCB the most stably explored child
+    keeps its weight (= its visits here) and every other child is an integer no larger than its visits (getReducedPlaySelectionWeight,
+    rounded up); with LCB at most one value differs -- the child with the best lower bound -- and it only grows; a very sharp
+    bound (lcbStdevs small) makes the promotion happen, and useNonBuggyLcb = 0 never promotes the first-created child."""
+    promoted = 0
+    for gid in range(24):
+        og = _midgame(oracle, 5, 5, 4, 11, gid, 3 + gid % 6)
+        if og.finished():
+            continue
+        base = oracle.search_run_graph(og, 200, graph=True, cpuct=1.1, valueWeightExponent=0.5)
+        psv, ev, order = base["playSelection"], base["edgeVisits"], base["order"]
+        kids = order != 255
+        assert (psv[~kids] == 0).all() and (psv[kids] <= ev[kids] + 1e-9).all()
+        best = int(np.argmax(np.where(kids, ev, -1)))
+        others = kids.copy(); others[best] = False
+        assert (psv[others] == np.ceil(psv[others])).all()
+        assert abs(psv[np.argmax(psv)] - ev[np.argmax(psv)]) < 1e-6          # the top value is an unreduced child weight
+        for stdevs, nonbuggy in ((5.0, 1), (0.5, 1), (0.5, 0)):
+            r = oracle.search_run_graph(og, 200, graph=True, cpuct=1.1, valueWeightExponent=0.5, useLcbForSelection=1, lcbStdevs=stdevs,
+                                        minVisitPropForLCB=0.15, useNonBuggyLcb=nonbuggy)
+            assert (r["edgeVisits"] == ev).all()                         # LCB touches the move choice, not the search
+            diff = np.flatnonzero(r["playSelection"] != psv)
+            assert len(diff) <= 1
+            if len(diff):
+                assert r["playSelection"][diff[0]] > psv[diff[0]]
+                promoted += stdevs == 0.5 and nonbuggy == 1
+                if not nonbuggy:
+                    assert order[diff[0]] != 0
+    assert promoted > 0
+
+
+def test_oracle_root_symmetry_sampling_and_uncertainty(oracle):
+    """rootNumSymmetriesToSample (searchnnhelpers.cpp:67-83): N extra evaluations per search, root priors that differ from a single
+    evaluation, depend on (seed, game id) for N < 8 and -- all eight symmetries averaged -- only on summation order for N = 8.
+    useUncertainty (searchupdatehelpers.cpp:91-113): the root's weight is no longer its visit count."""
+    og = _midgame(oracle, 5, 5, 4, 3, 1, 4)
+    one = oracle.search_run_graph(og, 50)
+    four = oracle.search_run_graph(og, 50, rootNumSymmetriesToSample=4, noiseSeed=5, noiseGameId=9)
+    again = oracle.search_run_graph(og, 50, rootNumSymmetriesToSample=4, noiseSeed=5, noiseGameId=9)
+    other = oracle.search_run_graph(og, 50, rootNumSymmetriesToSample=4, noiseSeed=5, noiseGameId=10)
+    assert int(four["counters"][1]) == int(one["counters"][1]) + 3 and four["rootVisits"] == one["rootVisits"] == 50
+    assert (four["policy"] == again["policy"]).all() and (four["policy"] != one["policy"]).any() and (four["policy"] != other["policy"]).any()
+    assert ((four["policy"] < 0) == (one["policy"] < 0)).all() and abs(float(four["policy"][four["policy"] >= 0].sum()) - 1.0) < 1e-5
+    e1 = oracle.search_run_graph(og, 1, rootNumSymmetriesToSample=8, noiseSeed=5, noiseGameId=9)["policy"]
+    e2 = oracle.search_run_graph(og, 1, rootNumSymmetriesToSample=8, noiseSeed=6, noiseGameId=11)["policy"]
+    assert np.abs(e1 - e2).max() < 1e-6
+    unc = oracle.search_run_graph(og, 50, useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)
+    assert unc["rootVisits"] == 50 and unc["digest"] != one["digest"] and (unc["edgeVisits"] != one["edgeVisits"]).any()
