@@ -100,6 +100,7 @@ struct TreeMem {
   uint64_t* tblKeysAlt; int* tblValsAlt; uint64_t* biasKeysAlt; double* biasValsAlt;
   int* remap;             // [G][maxNodes] old node index -> new index (-1: dropped)
   const double* tcdf;     // [2000] Student-t (3 degrees of freedom) cdf on [-50, 50] for valueWeightExponent
+  const double* stdevTab; // [1025] sqrt(1e-8 + 1 / (1.5 sqrt(w))) for integer child weights w (the common case): same bits as computing it
 };
 constexpr int NUM_STATS = 16;
 
@@ -124,7 +125,7 @@ struct TrainMem {
 //                           policy[P] f32 | child[P] i32 | edgeN[P] i32 | order[P] u8            (polOff = 32 + 8 P)
 //              graph mode: header { int visits; int numChildren; int nextPla; int biasEntry; double weightSum, utilityAvg,
 //                           nnUtility, lastBiasDeltaSum, lastBiasWeight; int depth (stones on the board), noised;
-//                           uint64 key[2] (transposition key); double utilitySqAvg, weightSqSum, nnWeight } | policy | child | edgeN | order  (polOff = 104)
+//                           uint64 key[2] (transposition key); double utilitySqAvg, weightSqSum, nnWeight } | policy | child | edgeN | order | list u8[P]  (polOff = 104)
 struct NodeRef {
   uint8_t* base; int P; int polOff;
   __device__ __forceinline__ int& N() const { return *reinterpret_cast<int*>(base); }
@@ -136,6 +137,7 @@ struct NodeRef {
   __device__ __forceinline__ int* child() const { return reinterpret_cast<int*>(base + polOff + 4 * P); }
   __device__ __forceinline__ int* edgeN() const { return reinterpret_cast<int*>(base + polOff + 8 * P); }
   __device__ __forceinline__ uint8_t* order() const { return base + polOff + 12 * P; }
+  __device__ __forceinline__ uint8_t* list() const { return base + polOff + 13 * P; }   // graph mode: policy index of the k-th created child
   // graph mode header
   __device__ __forceinline__ int& biasEntry() const { return *reinterpret_cast<int*>(base + 12); }
   __device__ __forceinline__ double& weightSum() const { return *reinterpret_cast<double*>(base + 16); }
@@ -498,7 +500,11 @@ __device__ __forceinline__ void childStatsSq(const SearchCfg& c, uint8_t* treeBa
 }
 // computeWeightFromNNOutput (searchupdatehelpers.cpp:91-113) with Coffee's outputs (no score term)
 __device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shorttermWinlossError);
-__device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
+// weightSum * edgeVisits / max(visits, 1) (searchnode.h:59-62).  An edge that carries all of its child's visits -- every edge of a
+// tree -- has ratio exactly 1.0 and cw * 1.0 == cw, so the division is skipped without changing a bit.
+__device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return e == max(cv, 1) ? cw : __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
+template <class D> struct PolicySlots { static constexpr int N = (4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN + 31) / 32; };   // children a lane can hold
+template <> struct PolicySlots<StaticDims<5, 5, 4>> { static constexpr int N = 4; };
 
 template <class D>
 __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob, int8_t* __restrict__ leafSym) {
@@ -524,15 +530,24 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
       NodeRef nd{treeBase + (size_t)node * c.nodeStride, c.P, c.polOff};
       const int pla = nd.nextPla();
       const double parentUtility = nd.utilityAvg();
-      const float* pol = nd.policy(); const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* ord = nd.order();
+      const float* pol = nd.policy(); const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* lst = nd.list();
+      // the children, k-th created child on lane k mod 32: statistics read once and kept in registers for both passes
+      constexpr int SL = PolicySlots<D>::N;
+      const int nc = nd.numChildren();
+      double wv[SL], cuv[SL]; float pv[SL]; int posv[SL];
       double total = 0.0, mass = 0.0;
-      for(int pos = lane; pos < c.P; pos += 32) {
-        const int cc = ch[pos];
-        if(cc != -1) {
+#pragma unroll
+      for(int m = 0; m < SL; m++) {
+        const int k = lane + 32 * m;
+        posv[m] = -1;
+        if(k < nc) {
+          const int pos = lst[k];
           int cv; double cw, cu;
-          childStats(c, treeBase, cc, eN[pos], cv, cw, cu);
-          total = __dadd_rn(total, childWeightOf(cw, eN[pos], cv));
-          mass = __dadd_rn(mass, (double)pol[pos]);
+          const int e = eN[pos];
+          childStats(c, treeBase, ch[pos], e, cv, cw, cu);
+          wv[m] = childWeightOf(cw, e, cv); cuv[m] = cu; pv[m] = pol[pos]; posv[m] = pos;
+          total = __dadd_rn(total, wv[m]);
+          mass = __dadd_rn(mass, (double)pv[m]);
         }
       }
       total = warpSumD(total);
@@ -548,21 +563,20 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
       const double scale = __dmul_rn(c.cpuct, __dsqrt_rn(__dadd_rn(total, 0.01)));
       double bestVal = 0.0; int bestOrd = 1 << 20, bestPos = -1;
       float newP = -1.0f; int newPos = -1;
+#pragma unroll
+      for(int m = 0; m < SL; m++) {
+        if(posv[m] < 0) continue;
+        const double w = wv[m];
+        const float p = pv[m];
+        double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, w)), pla == 2 ? cuv[m] : -cuv[m]);
+        // rootDesiredPerChildVisitsCoeff (searchexplorehelpers.cpp:150-155)
+        if(depth == 0 && c.rootDesired > 0.0 && p > 0.0f && w < __dsqrt_rn(__dmul_rn(__dmul_rn((double)p, total), c.rootDesired))) val = 1e20;
+        const int o = lane + 32 * m;   // creation order
+        if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = posv[m]; }
+      }
       for(int pos = lane; pos < c.P; pos += 32) {
         const float p = pol[pos];
-        const int cc = ch[pos];
-        if(cc != -1) {
-          int cv; double cw, cu;
-          childStats(c, treeBase, cc, eN[pos], cv, cw, cu);
-          const double w = childWeightOf(cw, eN[pos], cv);
-          double val = __dadd_rn(__ddiv_rn(__dmul_rn(scale, (double)p), __dadd_rn(1.0, w)), pla == 2 ? cu : -cu);
-          // rootDesiredPerChildVisitsCoeff (searchexplorehelpers.cpp:150-155)
-          if(depth == 0 && c.rootDesired > 0.0 && p > 0.0f && w < __dsqrt_rn(__dmul_rn(__dmul_rn((double)p, total), c.rootDesired))) val = 1e20;
-          const int o = ord[pos];
-          if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = pos; }
-        } else if(p >= 0.0f) {
-          if(p > newP) { newP = p; newPos = pos; }
-        }
+        if(p >= 0.0f && ch[pos] == -1 && p > newP) { newP = p; newPos = pos; }   // ascending pos within a lane: ties keep the lowest index
       }
       for(int o = 16; o > 0; o >>= 1) {
         const double v2 = __shfl_xor_sync(0xffffffffu, bestVal, o);
@@ -666,23 +680,28 @@ __device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shortterm
 }
 
 // recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
-constexpr int MAX_POLICY_SLOTS = 4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN;
-__device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, const double* __restrict__ tcdfTable, uint8_t* treeBase, NodeRef nd,
-                                              int lane, int inc, bool isRoot) {
-  const int* ch = nd.child(); const int* eN = nd.edgeN();
+// One warp; the k-th created child sits on lane k mod 32 (a node with at most 32 children -- nearly all -- runs the per-child code once),
+// its statistics are read once and kept in registers.  SL = children a lane can hold.
+template <int SL>
+__device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, const double* __restrict__ tcdfTable, const double* __restrict__ stdevTab,
+                                              uint8_t* treeBase, NodeRef nd, int lane, int inc, bool isRoot) {
+  const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* lst = nd.list();
+  const int nc = nd.numChildren();
   double sumW = 0.0, sumWU = 0.0, maxW = 0.0;
-  double nwl[(MAX_POLICY_SLOTS + 31) / 32];   // this lane's children: weight, then desired weight
-  int k = 0;
-  for(int pos = lane; pos < c.P; pos += 32, k++) {
-    nwl[k] = 0.0;
-    const int cc = ch[pos];
-    if(cc != -1) {
+  double nwl[SL], cuv[SL], cwv[SL];   // this lane's children: weight (then desired weight), utility, raw weightSum
+  int ccv[SL], ev[SL];
+#pragma unroll
+  for(int m = 0; m < SL; m++) {
+    const int k = lane + 32 * m;
+    nwl[m] = 0.0; cuv[m] = 0.0; cwv[m] = 1.0; ccv[m] = -1; ev[m] = 0;
+    if(k < nc) {
+      const int pos = lst[k];
       int cv; double cw, cu;
-      const int e = eN[pos];
+      const int e = eN[pos], cc = ch[pos];
       childStats(c, treeBase, cc, e, cv, cw, cu);
       if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
       const double w = childWeightOf(cw, e, cv);
-      nwl[k] = w;
+      nwl[m] = w; cuv[m] = cu; cwv[m] = cw; ccv[m] = cc; ev[m] = e;
       maxW = fmax(maxW, w);
       sumW = __dadd_rn(sumW, w);
       sumWU = __dadd_rn(sumWU, __dmul_rn(w, cu));
@@ -705,17 +724,21 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
     const double simpleValue = __ddiv_rn(sumWU, sumW);
     const int pla = nd.nextPla();
     double totalNew = 0.0;
-    k = 0;
-    for(int pos = lane; pos < c.P; pos += 32, k++) {
-      const double w = nwl[k];
+#pragma unroll
+    for(int m = 0; m < SL; m++) {
+      const double w = nwl[m];
       if(w == 0.0) continue;
       double x = w;
       if(x < amountToPrune) x = 0.0;
       else { x = __dsub_rn(x, amountToSubtract); if(x <= 0.0) x = 0.0; }
       if(x > 0.0 && c.vwExp != 0.0) {
-        int cv; double cw, cu;
-        childStats(c, treeBase, ch[pos], eN[pos], cv, cw, cu);
-        const double stdev = __dsqrt_rn(__dadd_rn(0.00000001, __ddiv_rn(1.0, __dmul_rn(1.5, __dsqrt_rn(w)))));
+        const double cu = cuv[m];
+        // stdev = sqrt(1e-8 + 1 / (1.5 sqrt(w))): from the table when w is a whole number (the bits are the same: every operation is
+        // correctly rounded on the host too)
+        double stdev;
+        const int wi = (int)w;
+        if(w <= 1024.0 && (double)wi == w) stdev = stdevTab[wi];
+        else stdev = __dsqrt_rn(__dadd_rn(0.00000001, __ddiv_rn(1.0, __dmul_rn(1.5, __dsqrt_rn(w)))));
         const double diff = pla == 2 ? __dsub_rn(cu, simpleValue) : __dsub_rn(simpleValue, cu);
         const double z = __ddiv_rn(diff, stdev);
         const double d = __ddiv_rn(__dmul_rn(1999.0, __dsub_rn(z, -50.0)), 100.0);
@@ -730,23 +753,27 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
         const double raised = c.vwExp == 0.5 ? __dsqrt_rn(pr) : c.vwExp == 0.25 ? __dsqrt_rn(__dsqrt_rn(pr)) : c.vwExp == 1.0 ? pr : detExp(__dmul_rn(c.vwExp, detLog(pr)));
         x = __dmul_rn(x, raised);
       }
-      nwl[k] = x;
+      nwl[m] = x;
       totalNew = __dadd_rn(totalNew, x);
     }
     totalNew = warpSumD(totalNew);
     const double factor = __ddiv_rn(sumW, totalNew);
-    k = 0;
-    for(int pos = lane; pos < c.P; pos += 32, k++) nwl[k] = __dmul_rn(nwl[k], factor);
+#pragma unroll
+    for(int m = 0; m < SL; m++) nwl[m] = __dmul_rn(nwl[m], factor);
   }
   double partU = 0.0, partUSq = 0.0, partWSq = 0.0;
-  k = 0;
-  for(int pos = lane; pos < c.P; pos += 32, k++)
-    if(nwl[k] != 0.0) {
-      int cv; double cw, cu, cusq, cwsq;
-      childStatsSq(c, treeBase, ch[pos], eN[pos], cv, cw, cu, cusq, cwsq);
-      const double scaling = __ddiv_rn(nwl[k], cw);
-      partU = __dadd_rn(partU, __dmul_rn(nwl[k], cu));
-      partUSq = __dadd_rn(partUSq, __dmul_rn(nwl[k], cusq));
+#pragma unroll
+  for(int m = 0; m < SL; m++)
+    if(nwl[m] != 0.0) {
+      double cusq, cwsq;
+      const int cc = ccv[m];
+      if(cc >= 0) {
+        NodeRef chn{treeBase + (size_t)cc * c.nodeStride, c.P, c.polOff};
+        cusq = chn.utilitySqAvg(); cwsq = chn.weightSqSum();
+      } else { cusq = __dmul_rn(cuv[m], cuv[m]); cwsq = (double)ev[m]; }
+      const double scaling = __ddiv_rn(nwl[m], cwv[m]);
+      partU = __dadd_rn(partU, __dmul_rn(nwl[m], cuv[m]));
+      partUSq = __dadd_rn(partUSq, __dmul_rn(nwl[m], cusq));
       partWSq = __dadd_rn(partWSq, __dmul_rn(__dmul_rn(scaling, scaling), cwsq));
     }
   partU = warpSumD(partU);
@@ -780,6 +807,8 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
   __syncwarp();
 }
 
+constexpr int MAX_POLICY_SLOTS_PER_LANE = (4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN + 31) / 32;
+template <int SL>
 __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss,
                                                                 const float* __restrict__ misc) {
   const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -841,12 +870,13 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       if(d == depth - 1 && (kind == 1 || kind == 2 || kind == 6)) {
         nd.child()[pos] = kind == 1 ? newIdx : kind == 6 ? t.leafTarget[gi] : (v > 0.0 ? -4 : v < 0.0 ? -3 : -2);
         nd.order()[pos] = (uint8_t)nd.numChildren();
+        nd.list()[nd.numChildren()] = (uint8_t)pos;
         nd.numChildren() = nd.numChildren() + 1;
       }
       nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
     }
     __syncwarp();
-    recomputeNode(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, treeBase, nd, lane, 1, d == 0);
+    recomputeNode<SL>(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, t.stdevTab, treeBase, nd, lane, 1, d == 0);
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
@@ -1076,7 +1106,7 @@ __global__ void __launch_bounds__(128) k_reroot_graph(const SearchCfg c, TreeMem
             if(nd.numChildren() == 0) {
               if(lane == 0) { nd.utilityAvg() = nd.nnUtility(); nd.utilitySqAvg() = __dmul_rn(nd.nnUtility(), nd.nnUtility()); }
               __syncwarp();
-            } else recomputeNode(c, newBiasVals, t.tcdf, dst, nd, lane, 0, j == 0);
+            } else recomputeNode<MAX_POLICY_SLOTS_PER_LANE>(c, newBiasVals, t.tcdf, t.stdevTab, dst, nd, lane, 0, j == 0);
           }
         }
     }
@@ -1611,7 +1641,10 @@ int runVisits(kc_search* S) {
         k_hash_eval<<<warpBlocks, 128, 0, hs>>>(ch.gCnt, c.P, c.LW, Lf->d_legal, Lf->d_sitHash, H[h].policy, H[h].winLoss, H[h].misc, nullptr);
         S->launches += 2;
       }
-      if(c.graph) k_expand_backup_graph<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+      if(c.graph) {
+        if(c.P <= 128) k_expand_backup_graph<4><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+        else k_expand_backup_graph<MAX_POLICY_SLOTS_PER_LANE><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+      }
       else k_expand_backup<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
       S->launches++;
     }
@@ -1673,7 +1706,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   c.useTable = p->useGraphSearch ? 1 : 0;
   c.biasFactor = p->subtreeValueBiasFactor; c.biasExp = p->subtreeValueBiasWeightExponent; c.biasFreeProp = p->subtreeValueBiasFreeProp;
   c.polOff = c.graph ? GRAPH_POL_OFF : 32 + 8 * c.P;
-  c.nodeStride = (c.polOff + 13 * c.P + 15) / 16 * 16;
+  c.nodeStride = (c.polOff + (c.graph ? 14 : 13) * c.P + 15) / 16 * 16;
   // graph mode with re-use: a kept subgraph can hold nodes whose creating visits went through another root child, so the
   // pool is a quarter larger than maxVisits; a visit that finds it empty is dropped (the oracle does the same)
   c.maxNodes = p->maxVisits + ((c.graph && p->reuseTree) ? p->maxVisits / 4 : 0);
@@ -1715,6 +1748,12 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
       KC_CUDA(cudaMalloc(&d, 2000 * 8));
       KC_CUDA(cudaMemcpy(d, tab.data(), 2000 * 8, cudaMemcpyHostToDevice));
       S->tree.tcdf = d;
+      std::vector<double> sd(1025, 0.0);
+      for(int w = 1; w <= 1024; w++) sd[w] = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt((double)w)));
+      double* d2 = nullptr;
+      KC_CUDA(cudaMalloc(&d2, 1025 * 8));
+      KC_CUDA(cudaMemcpy(d2, sd.data(), 1025 * 8, cudaMemcpyHostToDevice));
+      S->tree.stdevTab = d2;
     }
     const size_t slots = n * c.tableCap;
     KC_CUDA(cudaMalloc(&S->tree.tblKeys, slots * 16)); KC_CUDA(cudaMalloc(&S->tree.tblVals, slots * 4));
@@ -1761,7 +1800,7 @@ int kc_search_destroy(kc_search* S) {
   cudaFree(S->tree.leafSlot); cudaFree(S->tree.evalCount);
   cudaFree(S->tree.nodesAlt); cudaFree(S->tree.rerootQueue); cudaFree(S->tree.active);
   cudaFree(S->tree.tblKeys); cudaFree(S->tree.tblVals); cudaFree(S->tree.biasKeys); cudaFree(S->tree.biasVals);
-  cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget); cudaFree(const_cast<double*>(S->tree.tcdf));
+  cudaFree(S->tree.leafKey); cudaFree(S->tree.leafBiasKey); cudaFree(S->tree.leafTarget); cudaFree(const_cast<double*>(S->tree.tcdf)); cudaFree(const_cast<double*>(S->tree.stdevTab));
   cudaFree(S->tree.tblKeysAlt); cudaFree(S->tree.tblValsAlt); cudaFree(S->tree.biasKeysAlt); cudaFree(S->tree.biasValsAlt); cudaFree(S->tree.remap);
   { kc::TrainMem& t = S->train;
     cudaFree(t.recBlack); cudaFree(t.recWhite); cudaFree(t.recMisc); cudaFree(t.recN); cudaFree(t.recW); cudaFree(t.recVisits); cudaFree(t.recCount);

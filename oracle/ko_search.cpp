@@ -469,24 +469,33 @@ struct GraphSearch {
     return p->uncertaintyCoeff / (powered + baseline);
   }
   static double childWeight(double cw, int e, int cv) { return cw * ((double)e / (double)std::max(cv, 1)); }
+  // the node's children in creation order (policy indices): the order the reference's children array has.  Order-sensitive sums
+  // run over it the way a warp does: lane = creation index mod 32, then the xor butterfly.
+  std::vector<int> kids(const GNode& nd) const {
+    std::vector<int> k(nd.numChildren, -1);
+    for(int pos = 0; pos < P; pos++) if(nd.child[pos] != -1) k[nd.order[pos]] = pos;
+    return k;
+  }
 
   // recomputeNodeStats (searchupdatehelpers.cpp:151-326).  Canonical order of the order-dependent sums: lane = policy index mod 32,
   // then the xor butterfly (what a warp does); the reference walks the children in creation order.
   void recompute(GNode& nd, int inc = 1, bool isRoot = false) {
     double partW[32] = {0}, partWU[32] = {0};
     double maxW = 0.0;
-    std::vector<double> w(P, 0.0);
-    for(int pos = 0; pos < P; pos++)
-      if(nd.child[pos] != -1) {
-        int cv; double cw, cu;
-        childStats(nd, pos, cv, cw, cu);
-        const int e = nd.edgeN[pos];
-        if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
-        w[pos] = childWeight(cw, e, cv);
-        if(w[pos] > maxW) maxW = w[pos];
-        partW[pos & 31] = partW[pos & 31] + w[pos];
-        partWU[pos & 31] = partWU[pos & 31] + w[pos] * cu;
-      }
+    const std::vector<int> ks = kids(nd);
+    const int nk = (int)ks.size();
+    std::vector<double> w(nk, 0.0);
+    for(int k = 0; k < nk; k++) {
+      const int pos = ks[k];
+      int cv; double cw, cu;
+      childStats(nd, pos, cv, cw, cu);
+      const int e = nd.edgeN[pos];
+      if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
+      w[k] = childWeight(cw, e, cv);
+      if(w[k] > maxW) maxW = w[k];
+      partW[k & 31] = partW[k & 31] + w[k];
+      partWU[k & 31] = partWU[k & 31] + w[k] * cu;
+    }
     const double sumW = butterfly(partW);
     double sumWU = butterfly(partWU);
     // at a noised root the children the move choice would prune / reduce lose the same weight here (:196-206)
@@ -502,34 +511,35 @@ struct GraphSearch {
       // weight * cdf(z)^exponent, z = its utility's distance from the siblings' weighted mean in standard errors; the total stays sumW
       const double simpleValue = sumWU / sumW;   // selfUtility is +-utility, handled through the sign below
       double partN[32] = {0};
-      for(int pos = 0; pos < P; pos++) {
-        if(w[pos] == 0.0) continue;
-        double x = w[pos];
+      for(int k = 0; k < nk; k++) {
+        if(w[k] == 0.0) continue;
+        const int pos = ks[k];
+        double x = w[k];
         if(x < amountToPrune) x = 0.0;
         else { x = x - amountToSubtract; if(x <= 0.0) x = 0.0; }
         if(x > 0.0 && p->valueWeightExponent != 0.0) {
           int cv; double cw, cu;
           childStats(nd, pos, cv, cw, cu);
-          const double stdev = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt(w[pos])));
+          const double stdev = std::sqrt(0.00000001 + 1.0 / (1.5 * std::sqrt(w[k])));
           const double diff = nd.nextPla == 2 ? cu - simpleValue : simpleValue - cu;   // selfUtility - simpleValue (own view)
           const double pr = tcdf().get(diff / stdev) + 0.0001;
           x = x * valueWeightPow(pr, p->valueWeightExponent);
         }
-        nw[pos] = x;
-        partN[pos & 31] = partN[pos & 31] + x;
+        nw[k] = x;
+        partN[k & 31] = partN[k & 31] + x;
       }
       const double factor = sumW / butterfly(partN);
-      for(int pos = 0; pos < P; pos++) nw[pos] = nw[pos] * factor;
+      for(int k = 0; k < nk; k++) nw[k] = nw[k] * factor;
     }
     double partU[32] = {0}, partUSq[32] = {0}, partWSq[32] = {0};
-    for(int pos = 0; pos < P; pos++)
-      if(nw[pos] != 0.0) {
+    for(int k = 0; k < nk; k++)
+      if(nw[k] != 0.0) {
         int cv; double cw, cu, cusq, cwsq;
-        childStatsSq(nd, pos, cv, cw, cu, cusq, cwsq);
-        const double scaling = nw[pos] / cw;
-        partU[pos & 31] = partU[pos & 31] + nw[pos] * cu;
-        partUSq[pos & 31] = partUSq[pos & 31] + nw[pos] * cusq;
-        partWSq[pos & 31] = partWSq[pos & 31] + (scaling * scaling) * cwsq;
+        childStatsSq(nd, ks[k], cv, cw, cu, cusq, cwsq);
+        const double scaling = nw[k] / cw;
+        partU[k & 31] = partU[k & 31] + nw[k] * cu;
+        partUSq[k & 31] = partUSq[k & 31] + nw[k] * cusq;
+        partWSq[k & 31] = partWSq[k & 31] + (scaling * scaling) * cwsq;
       }
     if(reweigh) sumWU = butterfly(partU);
     const double sumWUSq = butterfly(partUSq), sumWSq = butterfly(partWSq);
@@ -797,13 +807,14 @@ static void graphRun(GraphSearch& S, const ko_game* rootGame, int x_size, int y_
         GNode& nd = S.nodes[node];
         const int pla = nd.nextPla;
         double partT[32] = {0}, partM[32] = {0};
-        for(int pos = 0; pos < P; pos++)
-          if(nd.child[pos] != -1) {
-            int cv; double cw, cu;
-            S.childStats(nd, pos, cv, cw, cu);
-            partT[pos & 31] = partT[pos & 31] + GraphSearch::childWeight(cw, nd.edgeN[pos], cv);
-            partM[pos & 31] = partM[pos & 31] + (double)nd.policy[pos];
-          }
+        const std::vector<int> ks = S.kids(nd);
+        for(int k = 0; k < (int)ks.size(); k++) {
+          const int pos = ks[k];
+          int cv; double cw, cu;
+          S.childStats(nd, pos, cv, cw, cu);
+          partT[k & 31] = partT[k & 31] + GraphSearch::childWeight(cw, nd.edgeN[pos], cv);
+          partM[k & 31] = partM[k & 31] + (double)nd.policy[pos];
+        }
         const double total = butterfly(partT), mass = butterfly(partM);
         const double parentUtility = nd.utilityAvg;
         double parentUtilityForFPU = parentUtility;
