@@ -153,6 +153,10 @@ int kc_sgf_parse(const char* sgf, int* xSize, int* ySize, int* winLen, int8_t* i
                                        in both): 3 more mantissa bits bring raw policy / ownership logits inside 1e-2 of the fp32
                                        reference (bf16 operands: 2-4e-2, profiles/r02_bf16_error_by_layer.json).  Activations and
                                        weights saturate at +-65504 instead of overflowing. */
+#define KC_FLAG_MASKED_BOARDS 16u   /* tensor-core path: boards may be smaller than nnXLen x nnYLen (requireExactNNLen = false, nninterface.h:73-76).
+                                     * Input channel 0 (the on-board plane) is the mask, as in the reference backends (eigenbackend.cpp:1438):
+                                     * off-board cells are zeroed after every normalisation, the pooling layers divide by each board's own
+                                     * cell count and take the maximum over on-board cells only (:141-166).  The fp32 check path always does this. */
 
 /* Page-locked host memory for the buffers handed to kc_forward (InputBuffers of nninterface.h:92-93): with pinned rows the
  * chunked H2D / D2H copies of kc_forward are asynchronous DMA that overlap the kernels; pageable memory works but serialises. */

@@ -98,12 +98,13 @@ def parseSgf(text, maxMoves=400):
 
 class ComputeHandle:
     def __init__(self, ctx, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False,
-                 operandsBF16=False):
+                 operandsBF16=False, requireExactNNLen=True):
         self.ctx, self.loadedModel = ctx, loadedModel
         self.maxBatch, self.nnXLen, self.nnYLen = maxBatchSize, nnXLen, nnYLen
         self.inputsUseNHWC = inputsUseNHWC
         flags = ((capi.FLAG_FP32_CHECK if useFP32Check else 0) | (capi.FLAG_INPUTS_NHWC if inputsUseNHWC else 0) |
-                 (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0) | (capi.FLAG_OPERANDS_BF16 if operandsBF16 else 0))
+                 (capi.FLAG_SYM_PERMUTE_DIRS if playModeSymmetry else 0) | (capi.FLAG_OPERANDS_BF16 if operandsBF16 else 0) |
+                 (0 if requireExactNNLen else capi.FLAG_MASKED_BOARDS))
         self._p = C.c_void_p()
         check(lib().kc_handle_create(ctx._p, loadedModel._p, maxBatchSize, nnXLen, nnYLen, flags, C.byref(self._p)))
 
@@ -138,8 +139,10 @@ class ComputeHandle:
 
 
 def createComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check=False, inputsUseNHWC=False, playModeSymmetry=False,
-                        operandsBF16=False):
-    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC, playModeSymmetry, operandsBF16)
+                        operandsBF16=False, requireExactNNLen=True):
+    """NeuralNet::createComputeHandle (nninterface.h:66-86).  requireExactNNLen=False: boards may be smaller than nnXLen x nnYLen
+    (input channel 0 is the mask), on either path."""
+    return ComputeHandle(context, loadedModel, maxBatchSize, nnXLen, nnYLen, useFP32Check, inputsUseNHWC, playModeSymmetry, operandsBF16, requireExactNNLen)
 
 
 def getOutput(handle, rowSpatial, rowGlobal, symmetry=None, ownership=True, out=None):

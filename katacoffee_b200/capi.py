@@ -124,6 +124,7 @@ FLAG_FP32_CHECK = 1
 FLAG_INPUTS_NHWC = 2
 FLAG_SYM_PERMUTE_DIRS = 4
 FLAG_OPERANDS_BF16 = 8
+FLAG_MASKED_BOARDS = 16
 
 vp = C.c_void_p
 # name -> (restype, argtypes); must list every symbol include/katacoffee_b200.h declares

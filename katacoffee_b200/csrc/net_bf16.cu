@@ -77,7 +77,8 @@ struct TrunkCfg {
   // scratch: they are written after the last pooling pass has been read (named barrier in between) and read before the next one
   static_assert((MAX_NB * MAXC + MAX_NB * MAX_V2) * 4 <= 128 * SCR_STRIDE * 4, "bias + v2 buffers alias the pooling scratch");
   static constexpr int OFF_SYM = OFF_POOLB + NT * MAX_NB * POOLW * 4;
-  static constexpr int OFF_PAR = OFF_SYM + 448;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
+  static constexpr int OFF_MASK = OFF_SYM + 448;                  // masked boards: [NT][128] row mask + [NT][MAX_NB][4] per-board pooling constants (fp32)
+  static constexpr int OFF_PAR = OFF_MASK + NT * (128 + MAX_NB * 4) * 4;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
   static constexpr int OFF_BAR = OFF_PAR + NT * 2 * 2 * MAXC * 4; // folded BN, staged while the tensor core is still busy with it
   // barriers (8 bytes each)
   static constexpr int BAR_FULL = 0, BAR_EMPTY = BAR_FULL + NSTAGES, BAR_ACC = BAR_EMPTY + NSTAGES, BAR_ACTFREE = BAR_ACC + NT,
@@ -149,6 +150,8 @@ struct TrunkParams {
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
   float poolScale1, poolScale2, invHW;
   int v2C;
+  int masked;        // KC_FLAG_MASKED_BOARDS: boards may be smaller than nnXLen x nnYLen; input channel 0 (the on-board plane) is the mask
+                     // (eigenbackend.cpp:1438) and the pooling divides by each board's own cell count (:141-166)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +189,7 @@ struct EpiCtx {
   int e;            // thread index within the tile's epilogue group (== r)
   bool valid;       // row is a board cell
   int b, cell;      // board within tile, dense cell index
+  int slotB, slotCell;   // the same for every cell of the board's nnXLen x nnYLen slot (slotCell -1: a pad row), whatever the mask says
   uint32_t tmemLane;  // tmem base + lane offset + tile column offset
   uint8_t* act;     // this tile's activation buffer
   uint32_t barChunk;  // address of actReady[t][0] (pair mode: shared::cluster address in the leader CTA)
@@ -193,6 +197,8 @@ struct EpiCtx {
   bool f16;           // activations are published as fp16 (else bf16)
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
   const float* par;  // staged folded BN of the layer being finished: scale[MAXC] | bias[MAXC]
+  const float* maskRow;   // masked boards: [128] 1.0 / 0.0 per row of this tile (shared), else null
+  const float* boardK;    // masked boards: [MAX_NB][4] = 1 / cells, (sqrt(cells) - 14) * 0.1, (sqrt(cells) - 14)^2 * 0.01 - 0.1 per board of this tile
   long long* dbg;    // non-null for the one thread / layer whose timeline is recorded
 };
 
@@ -249,6 +255,14 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
     const int y0 = part ? yMid : 0, y1 = part ? P.H : yMid;
     for(int y = y0; y < y1; y++) {
       const float* rowp = c.scr + (y * P.tileRowW + b * P.stride) * SCR_STRIDE + j;
+      if(c.maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
+        const float* mk = c.maskRow + y * P.tileRowW + b * P.stride;
+        for(int x = 0; x < P.W; x++) {
+          float v = rowp[x * SCR_STRIDE];
+          s += v;
+          m = fmaxf(m, v + (mk[x] - 1.0f));
+        }
+      } else
       for(int x = 0; x < P.W; x++) {
         float v = rowp[x * SCR_STRIDE];
         s += v;
@@ -342,9 +356,9 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
     poolBoards16(P, c, g, sum, mx);
     if(!(c.e & 1) && (c.e >> 1) < P.NB * 16) {
       int b = c.e >> 5, j = (c.e >> 1) & 15;
-      float mean = sum * P.invHW;
+      float mean = sum * (c.boardK ? c.boardK[b * 4] : P.invHW);
       pooled[b * 3 * G + half * 16 + j] = mean;
-      pooled[b * 3 * G + G + half * 16 + j] = mean * P.poolScale1;
+      pooled[b * 3 * G + G + half * 16 + j] = mean * (c.boardK ? c.boardK[b * 4 + 1] : P.poolScale1);
       pooled[b * 3 * G + 2 * G + half * 16 + j] = mx;
     }
   }
@@ -427,10 +441,12 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       g[j] = c.valid ? a : 0.f;
     }
     poolBoards16(P, c, g, sum, mx);
+    const float kInv = c.boardK ? c.boardK[pb * 4] : P.invHW, kS1 = c.boardK ? c.boardK[pb * 4 + 1] : P.poolScale1,
+                kS2 = c.boardK ? c.boardK[pb * 4 + 2] : P.poolScale2;
     if(poolOut) {
-      float mean = sum * P.invHW;
+      float mean = sum * kInv;
       pooledG[pb * 96 + half * 16 + pj] = mean;
-      pooledG[pb * 96 + 32 + half * 16 + pj] = mean * P.poolScale1;
+      pooledG[pb * 96 + 32 + half * 16 + pj] = mean * kS1;
       pooledG[pb * 96 + 64 + half * 16 + pj] = mx;
     }
     tmem_ld16(src + 2 * HEADC + half * 16, v);
@@ -442,10 +458,10 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     }
     poolBoards16(P, c, g, sum, mx);
     if(poolOut) {
-      float mean = sum * P.invHW;
+      float mean = sum * kInv;
       pooledV[pb * 96 + half * 16 + pj] = mean;
-      pooledV[pb * 96 + 32 + half * 16 + pj] = mean * P.poolScale1;
-      pooledV[pb * 96 + 64 + half * 16 + pj] = mean * P.poolScale2;
+      pooledV[pb * 96 + 32 + half * 16 + pj] = mean * kS1;
+      pooledV[pb * 96 + 64 + half * 16 + pj] = mean * kS2;
     }
   }
   if(hp) P.dbg[25] = clock64();
@@ -506,6 +522,15 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
   if(hp) P.dbg[29] = clock64();
   int game = gameBase + c.b;
+  if(c.maskRow && !c.valid && c.slotCell >= 0 && gameBase + c.slotB < nRows) {
+    // a cell of the nnXLen x nnYLen slot that is off this board: masked p1 / v1 through the bias-free 1x1 output convolutions = 0
+    const int g2 = gameBase + c.slotB;
+    const int s = P.sym ? P.sym[g2] : 0;
+    const int dst = sSym[s * P.HW + c.slotCell];
+    float* pol = P.policy + (size_t)g2 * 4 * P.HW;
+    pol[dst] = 0.f; pol[P.HW + dst] = 0.f; pol[2 * P.HW + dst] = 0.f; pol[3 * P.HW + dst] = 0.f;
+    P.own[(size_t)g2 * P.HW + dst] = 0.f;
+  }
   if(c.valid && game < nRows) {
     const float* add = c.biasBuf + c.b * 96;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, own = 0.f;
@@ -805,9 +830,16 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     int y = c.r / P.tileRowW, rr = c.r - y * P.tileRowW;
     c.b = rr / P.stride;
     int x = rr - c.b * P.stride;
-    c.valid = (y < P.H) && (x < P.W);
+    const bool slotValid = (y < P.H) && (x < P.W);
+    c.valid = slotValid;
     c.cell = y * P.W + x;
     if(!c.valid) { c.b = 0; c.cell = 0; }
+    c.slotB = c.b; c.slotCell = slotValid ? c.cell : -1;
+    float* maskRowW = reinterpret_cast<float*>(smem + K::OFF_MASK) + c.t * 128;
+    float* boardKW = reinterpret_cast<float*>(smem + K::OFF_MASK) + NT * 128 + c.t * MAX_NB * 4;
+    c.maskRow = P.masked ? maskRowW : nullptr;
+    c.boardK = P.masked ? boardKW : nullptr;
+    uint32_t itemCount = 0;
     c.tmemLane = tmemBase + ((uint32_t)(q * 32) << 16) + c.t * (2 * K::MAXC);
     c.act = smem + K::OFF_ACT + c.t * K::ACT_BYTES;
     c.remote = K::PAIR && rank != 0;
@@ -848,6 +880,26 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         }
         alive = mbar_wait(bars + (K::BAR_ACC + c.t) * 8, layerCount & 1, abortFlag, 31);
         if(!alive) break;
+        if(P.masked && l == 0) {
+          // the mask of this item's boards = input channel 0, still in the activation tile (the first layer's MMAs are done, its
+          // epilogue has not published yet).  The tile was written by the bulk copy: observe its barrier before reading.
+          alive = mbar_wait(bars + (K::BAR_IN + c.t) * 8, itemCount & 1, abortFlag, 32);
+          if(!alive) break;
+          const uint16_t onBoard = *reinterpret_cast<const volatile uint16_t*>(c.act + (size_t)(HALO_ROWS + c.r) * 16);
+          c.valid = c.slotCell >= 0 && onBoard != 0;
+          maskRowW[c.r] = c.valid ? 1.0f : 0.0f;
+          named_bar_sync(1 + c.t, 128);
+          if(c.e < P.NB) {
+            float cnt = 0.f;
+            for(int yy = 0; yy < P.H; yy++)
+              for(int xx = 0; xx < P.W; xx++) cnt += maskRowW[yy * P.tileRowW + c.e * P.stride + xx];
+            const float sq = sqrtf(cnt);
+            boardKW[c.e * 4] = cnt > 0.f ? 1.0f / cnt : 0.f;
+            boardKW[c.e * 4 + 1] = (sq - 14.0f) * 0.1f;
+            boardKW[c.e * 4 + 2] = (sq - 14.0f) * (sq - 14.0f) * 0.01f - 0.1f;
+          }
+          named_bar_sync(1 + c.t, 128);
+        }
         long long* tl = (P.dbg && blockIdx.x == 0 && c.e == 0 && (int)layerCount >= P.numLayers && (int)layerCount < 2 * P.numLayers)
                           ? P.dbg + 64 + (c.t * MAX_LAYERS + l) * 8 : nullptr;
         if(tl) tl[3] = clock64();
@@ -863,6 +915,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         if(probeHead) P.dbg[19] = clock64();
         if(tl) tl[4] = clock64();
       }
+      itemCount++;
     }
   }
   // ---- teardown ----
@@ -1252,6 +1305,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.misc = h->d_misc + (size_t)rowOffset * 2; P.own = h->d_own + (size_t)rowOffset * P.HW;
   P.abortFlag = h->d_abort;
   P.permuteDirs = (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) ? 1 : 0;
+  P.masked = (h->flags & KC_FLAG_MASKED_BOARDS) ? 1 : 0;
   P.g1Act = m->g1BN.act; P.p1Act = m->p1BN.act; P.v1Act = m->v1BN.act; P.v2Act = m->v2Act;
   P.dbg = h->d_dbg;
   float sq = sqrtf((float)P.HW);

@@ -181,10 +181,10 @@ void freeComputeContext(ComputeContext* c) {
 ComputeHandle* createComputeHandle(ComputeContext* context, const LoadedModel* loadedModel, Logger* logger, int maxBatchSize, bool requireExactNNLen,
                                    bool inputsUseNHWC, int gpuIdxForThisThread, int serverThreadIdx) {
   (void)logger; (void)serverThreadIdx; (void)loadedModel;
-  if(!requireExactNNLen && !context->useFP32Check)
-    throw StringError("B200 backend: the bf16 path needs requireExactNNLen (boards exactly nnXLen x nnYLen); use useFP16 = false for masked evaluation");
   auto cm = context->get(gpuIdxForThisThread < 0 ? 0 : gpuIdxForThisThread);
-  unsigned flags = (context->useFP32Check ? KC_FLAG_FP32_CHECK : 0u) | (inputsUseNHWC ? KC_FLAG_INPUTS_NHWC : 0u);
+  // requireExactNNLen = false: boards may be smaller than the net's slot; the tensor-core kernel then takes input channel 0 as the mask
+  // (the fp32 check path always does), as the reference backends do (nninterface.h:73-76, eigenbackend.cpp:1438)
+  unsigned flags = (context->useFP32Check ? KC_FLAG_FP32_CHECK : 0u) | (inputsUseNHWC ? KC_FLAG_INPUTS_NHWC : 0u) | (requireExactNNLen ? 0u : KC_FLAG_MASKED_BOARDS);
   ComputeHandle* h = new ComputeHandle();
   h->context = context; h->maxBatchSize = maxBatchSize; h->nnXLen = context->nnXLen; h->nnYLen = context->nnYLen; h->inputsUseNHWC = inputsUseNHWC;
   kcCheck(kc_handle_create(cm.first, cm.second, maxBatchSize, context->nnXLen, context->nnYLen, flags, &h->handle), "kc_handle_create");

@@ -1391,3 +1391,65 @@ def test_search_root_symmetry_sampling_with_the_net(ctx, oracle):
     legal = got[4]["policy"] >= 0
     assert ((rb["policy"] >= 0) == legal).all() and np.abs(rb["policy"] - got[4]["policy"])[legal].max() < 0.03
     sb.close(); hb.close(); h.close(); lm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("net,nnX,nnY,boards", [
+    ("b6c96", 5, 5, [(5, 5), (4, 4), (3, 5), (5, 2), (4, 5)]),      # boards of several sizes in one batch, inside a 5x5 slot
+    ("b10c128", 6, 6, [(6, 6), (5, 5), (4, 6), (3, 3)]),
+    ("b15c192", 6, 6, [(5, 5), (6, 4)]),                            # the wide-trunk kernel
+    ("b6c96-mish", 7, 7, [(7, 7), (5, 5), (6, 3)])])
+def test_masked_boards_on_the_tensor_path(ctx, oracle, net, nnX, nnY, boards):
+    """requireExactNNLen = false on the tensor-core path (nninterface.h:73-76): boards smaller than the net's nnXLen x nnYLen slot, the
+    on-board plane (input channel 0) as the mask (eigenbackend.cpp:1438), per-board pooling divisors and maxima over on-board cells
+    (:141-166).  Random-legal positions of several board sizes in one batch, every symmetry: raw outputs within 1e-2 of the fp32
+    oracle, exactly 0 at the off-board cells of the slot, and equal to the fp32 check path within the same bar."""
+    import ctypes as C
+    from katacoffee_b200 import backend, modeldesc
+    name, _, act = net.partition("-")
+    model = modeldesc.Model(name, seed=41, activation=act or "relu") if act else modeldesc.Model(name, seed=41)
+    om = oracle.Model(model)
+    lm = backend.LoadedModel(ctx, model)
+    rng = np.random.default_rng(5)
+    rows, globs, onboard = [], [], []
+    for i in range(96):
+        bw, bh = boards[i % len(boards)]
+        og = oracle.Game(bw, bh, min(4, bw, bh))
+        for _ in range(int(rng.integers(0, 6))):
+            if og.finished():
+                break
+            og.play(og.choose(9, i))
+        row = np.zeros(15 * nnX * nnY, np.float32); g = np.zeros(1, np.float32)
+        oracle.lib().ko_game_fill_row_v1(og._g, og.next_pla(), nnX, nnY, 0, row.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p))
+        rows.append(row); globs.append(g)
+        m = np.zeros((nnY, nnX), bool); m[:bh, :bw] = True
+        onboard.append(m.reshape(-1))
+    rows, globs, onboard = np.stack(rows), np.stack(globs), np.stack(onboard)
+    assert (rows[:, :nnX * nnY] == onboard).all()          # channel 0 is the mask
+    n = len(rows)
+    sym = (np.arange(n) % 8).astype(np.int8) if nnX == nnY else np.zeros(n, np.int8)
+    h = backend.createComputeHandle(ctx, lm, n, nnX, nnY, requireExactNNLen=False)
+    hc = backend.createComputeHandle(ctx, lm, n, nnX, nnY, useFP32Check=True)
+    assert h.isUsingBF16()
+    got = backend.getOutput(h, rows, globs, sym)
+    chk = backend.getOutput(hc, rows, globs, sym)
+    ref = om.forward(rows, globs, nnX, nnY, symmetry=sym, mode=0, threads=4)
+    names = ("policy", "value", "misc", "ownership")
+    for a, b, c, nm in zip(got, ref, chk, names):
+        assert np.abs(a - b).max() < 1e-2, (nm, float(np.abs(a - b).max()))
+        assert np.abs(a - c).max() < 1e-2, (nm, float(np.abs(a - c).max()))
+    # off-board cells of the slot: identity symmetry rows map cell to cell
+    ident = sym == 0
+    off = ~onboard[ident]
+    pol = got[0][ident].reshape(-1, 4, nnX * nnY)
+    assert (pol[np.broadcast_to(off[:, None, :], pol.shape)] == 0).all() and (got[3][ident][off] == 0).all()
+    # a mask really matters: the exact-size handle on the same rows gives different values for the small boards
+    he = backend.createComputeHandle(ctx, lm, n, nnX, nnY)
+    exact = backend.getOutput(he, rows, globs, sym)
+    small = onboard.sum(1) < nnX * nnY
+    assert np.abs(exact[1][small] - got[1][small]).max() > 1e-3
+    full = ~small
+    if full.any():   # and none for boards that fill the slot
+        assert np.abs(exact[0][full] - got[0][full]).max() < 1e-6 and np.abs(exact[1][full] - got[1][full]).max() < 1e-6
+    for o in (h, hc, he, lm):
+        o.close()
