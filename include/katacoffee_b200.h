@@ -331,9 +331,10 @@ typedef struct {
    * temperature is > 0 it replaces temperaturePlies -- edge visits, minus min(subtract, max/64), zero below min(prune, max/64),
    * raised to 1/T, T going from ...Early to chosenMoveTemperature with chosenMoveTemperatureHalflife (selfplay1.cfg:137-141). */
   double chosenMoveTemperature, chosenMoveTemperatureEarly, chosenMoveSubtract, chosenMovePrune;
-  int32_t noPipeline;           /* 0 (default): with the bf16 net and at least two trunk work items per SM pair the games are searched as two
-                                   half batches on two streams, so that one half's select / expand kernels run under the other half's trunk
-                                   kernel; 1: one batch.  Results are identical either way. */
+  int32_t noPipeline;           /* With KC_SEARCH_PIPELINE=1 in the environment, the bf16 net and at least two trunk work items per SM pair the
+                                   games are searched as two half batches on two streams, so that one half's select / expand kernels run under
+                                   the other half's trunk kernel; 2 here selects that pipeline too, 1 forces one batch.  One batch is the default (it measured 2.6 % faster
+                                   once the search kernels had been shortened); results are identical either way. */
   int32_t nnRandomize;          /* NNEvaluator's nnRandomize (cpp/neuralnet/nneval.cpp:515-524): every leaf is evaluated under one of the 8
                                    symmetries (inputs symmetrised, outputs mapped back).  The symmetry is drawn from the position's sit-hash
                                    and the seed, not from a shared stream, so a position gets the same one whichever game reaches it.  With a

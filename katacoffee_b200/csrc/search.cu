@@ -503,10 +503,18 @@ __device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shortterm
 // weightSum * edgeVisits / max(visits, 1) (searchnode.h:59-62).  An edge that carries all of its child's visits -- every edge of a
 // tree -- has ratio exactly 1.0 and cw * 1.0 == cw, so the division is skipped without changing a bit.
 __device__ __forceinline__ double childWeightOf(double cw, int e, int cv) { return e == max(cv, 1) ? cw : __dmul_rn(cw, __ddiv_rn((double)e, (double)max(cv, 1))); }
+// A per-position array held by a warp as reg[m] = array[lane + 32 m] (m < 4): the value at position `pos`, for any pos per lane
+template <class T>
+__device__ __forceinline__ T gather4(const T (&reg)[4], int pos) {
+  const int src = pos & 31, slot = pos >> 5;
+  const T a = __shfl_sync(0xffffffffu, reg[0], src), b = __shfl_sync(0xffffffffu, reg[1], src);
+  const T c = __shfl_sync(0xffffffffu, reg[2], src), d = __shfl_sync(0xffffffffu, reg[3], src);
+  return slot == 0 ? a : slot == 1 ? b : slot == 2 ? c : d;
+}
 template <class D> struct PolicySlots { static constexpr int N = (4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN + 31) / 32; };   // children a lane can hold
 template <> struct PolicySlots<StaticDims<5, 5, 4>> { static constexpr int N = 4; };
 
-template <class D>
+template <class D, bool PRE>
 __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const SearchCfg c, State root, State leaf, TreeMem t, const uint64_t* __restrict__ zob, int8_t* __restrict__ leafSym) {
   const D dm(g);
   using BB = typename D::BB;
@@ -536,16 +544,34 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
       const int nc = nd.numChildren();
       double wv[SL], cuv[SL]; float pv[SL]; int posv[SL];
       double total = 0.0, mass = 0.0;
+      // SL == 4 (policy size <= 128): the per-move arrays are fetched whole, coalesced and independent of the child list, so a level costs
+      // two dependent memory round trips (node, then the children's headers) instead of three; a child's entries come from the lane
+      // that holds its position (shuffles)
+      float polR[4]; int chR[4], eNR[4];
+      if constexpr(SL == 4 && PRE) {
+#pragma unroll
+        for(int m = 0; m < 4; m++) {
+          const int pos = lane + 32 * m;
+          const bool in = pos < c.P;
+          polR[m] = in ? pol[pos] : -1.0f; chR[m] = in ? ch[pos] : -1; eNR[m] = in ? eN[pos] : 0;
+        }
+      }
 #pragma unroll
       for(int m = 0; m < SL; m++) {
         const int k = lane + 32 * m;
         posv[m] = -1;
+        const bool anyK = 32 * m < nc;   // warp-uniform
+        int pos = 0, e = 0, cc = -1; float p = 0.f;
+        if constexpr(SL == 4 && PRE) {
+          if(anyK) {
+            pos = k < nc ? lst[k] : 0;
+            cc = gather4(chR, pos); e = gather4(eNR, pos); p = gather4(polR, pos);
+          }
+        } else if(k < nc) { pos = lst[k]; cc = ch[pos]; e = eN[pos]; p = pol[pos]; }
         if(k < nc) {
-          const int pos = lst[k];
           int cv; double cw, cu;
-          const int e = eN[pos];
-          childStats(c, treeBase, ch[pos], e, cv, cw, cu);
-          wv[m] = childWeightOf(cw, e, cv); cuv[m] = cu; pv[m] = pol[pos]; posv[m] = pos;
+          childStats(c, treeBase, cc, e, cv, cw, cu);
+          wv[m] = childWeightOf(cw, e, cv); cuv[m] = cu; pv[m] = p; posv[m] = pos;
           total = __dadd_rn(total, wv[m]);
           mass = __dadd_rn(mass, (double)pv[m]);
         }
@@ -574,6 +600,11 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
         const int o = lane + 32 * m;   // creation order
         if(bestPos < 0 || val > bestVal || (val == bestVal && o < bestOrd)) { bestVal = val; bestOrd = o; bestPos = posv[m]; }
       }
+      if constexpr(SL == 4 && PRE) {
+#pragma unroll
+        for(int m = 0; m < 4; m++)
+          if(polR[m] >= 0.0f && chR[m] == -1 && polR[m] > newP) { newP = polR[m]; newPos = lane + 32 * m; }
+      } else
       for(int pos = lane; pos < c.P; pos += 32) {
         const float p = pol[pos];
         if(p >= 0.0f && ch[pos] == -1 && p > newP) { newP = p; newPos = pos; }   // ascending pos within a lane: ties keep the lowest index
@@ -682,7 +713,7 @@ __device__ __forceinline__ double nnWeightOf(const SearchCfg& c, float shortterm
 // recomputeNodeStats (searchupdatehelpers.cpp:151-326) for one node by one warp; `inc` visits are added
 // One warp; the k-th created child sits on lane k mod 32 (a node with at most 32 children -- nearly all -- runs the per-child code once),
 // its statistics are read once and kept in registers.  SL = children a lane can hold.
-template <int SL>
+template <int SL, bool PRE>
 __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasValsOfGame, const double* __restrict__ tcdfTable, const double* __restrict__ stdevTab,
                                               uint8_t* treeBase, NodeRef nd, int lane, int inc, bool isRoot) {
   const int* ch = nd.child(); const int* eN = nd.edgeN(); const uint8_t* lst = nd.list();
@@ -690,14 +721,28 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
   double sumW = 0.0, sumWU = 0.0, maxW = 0.0;
   double nwl[SL], cuv[SL], cwv[SL];   // this lane's children: weight (then desired weight), utility, raw weightSum
   int ccv[SL], ev[SL];
+  int chR[4], eNR[4];
+  if constexpr(SL == 4 && PRE) {   // the per-move arrays whole and coalesced, independent of the child list (see k_select_graph)
+#pragma unroll
+    for(int m = 0; m < 4; m++) {
+      const int pos = lane + 32 * m;
+      const bool in = pos < c.P;
+      chR[m] = in ? ch[pos] : -1; eNR[m] = in ? eN[pos] : 0;
+    }
+  }
 #pragma unroll
   for(int m = 0; m < SL; m++) {
     const int k = lane + 32 * m;
     nwl[m] = 0.0; cuv[m] = 0.0; cwv[m] = 1.0; ccv[m] = -1; ev[m] = 0;
+    int e = 0, cc = -1;
+    if constexpr(SL == 4 && PRE) {
+      if(32 * m < nc) {   // warp-uniform
+        const int pos = k < nc ? lst[k] : 0;
+        cc = gather4(chR, pos); e = gather4(eNR, pos);
+      }
+    } else if(k < nc) { const int pos = lst[k]; e = eN[pos]; cc = ch[pos]; }
     if(k < nc) {
-      const int pos = lst[k];
       int cv; double cw, cu;
-      const int e = eN[pos], cc = ch[pos];
       childStats(c, treeBase, cc, e, cv, cw, cu);
       if(cv <= 0 || cw <= 0.0 || e <= 0) continue;
       const double w = childWeightOf(cw, e, cv);
@@ -808,7 +853,7 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
 }
 
 constexpr int MAX_POLICY_SLOTS_PER_LANE = (4 * KC_MAX_DEVICE_LEN * KC_MAX_DEVICE_LEN + 31) / 32;
-template <int SL>
+template <int SL, bool PRE>
 __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg c, TreeMem t, const float* __restrict__ policy, const float* __restrict__ winLoss,
                                                                 const float* __restrict__ misc) {
   const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -876,7 +921,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
       nd.edgeN()[pos] = nd.edgeN()[pos] + 1;
     }
     __syncwarp();
-    recomputeNode<SL>(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, t.stdevTab, treeBase, nd, lane, 1, d == 0);
+    recomputeNode<SL, PRE>(c, t.biasVals + (size_t)gi * c.tableCap * 2, t.tcdf, t.stdevTab, treeBase, nd, lane, 1, d == 0);
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
@@ -1106,7 +1151,7 @@ __global__ void __launch_bounds__(128) k_reroot_graph(const SearchCfg c, TreeMem
             if(nd.numChildren() == 0) {
               if(lane == 0) { nd.utilityAvg() = nd.nnUtility(); nd.utilitySqAvg() = __dmul_rn(nd.nnUtility(), nd.nnUtility()); }
               __syncwarp();
-            } else recomputeNode<MAX_POLICY_SLOTS_PER_LANE>(c, newBiasVals, t.tcdf, t.stdevTab, dst, nd, lane, 0, j == 0);
+            } else recomputeNode<MAX_POLICY_SLOTS_PER_LANE, false>(c, newBiasVals, t.tcdf, t.stdevTab, dst, nd, lane, 0, j == 0);
           }
         }
     }
@@ -1567,6 +1612,8 @@ int runVisits(kc_search* S) {
   // cores -- the trunk's launch leaves 16 k registers per SM free for them (setmaxnreg, net_bf16.cu).  Trees of different games
   // never interact, so the split changes no result.
   const int nh = S->pipelined ? 2 : 1;
+  // KC_SEARCH_PRELOAD=0: per-child loads instead of whole per-move arrays + shuffles in the graph-mode kernels (diagnostic)
+  static const bool preload = [] { const char* e = getenv("KC_SEARCH_PRELOAD"); return !e || atoi(e) != 0; }();
   struct HalfRun { kc_games* leaf; SearchCfg c; cudaStream_t st; float* policy; float* winLoss; float* misc; uint64_t* nnHash; int rowOff; };
   HalfRun H[2];
   for(int h = 0; h < nh; h++) {
@@ -1626,8 +1673,9 @@ int runVisits(kc_search* S) {
       if((rootPolicyChange || c.rootSyms > 1) && it <= 1) { k_root_noise<<<(ch.gCnt + 63) / 64, 64, 0, hs>>>(ch, S->tree, R->st, R->geom.HW); S->launches++; }
       if(c.compact) KC_CUDA(cudaMemsetAsync(S->tree.evalCount + h, 0, 4, hs));
       if(c.graph) {
-        if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
-        else k_select_graph<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+        if(isStatic5(R->geom) && preload) k_select_graph<StaticDims<5, 5, 4>, true><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+        else if(isStatic5(R->geom)) k_select_graph<StaticDims<5, 5, 4>, false><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
+        else k_select_graph<DynDims, false><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
       } else if(isStatic5(R->geom)) k_select<StaticDims<5, 5, 4>><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
       else k_select<DynDims><<<warpBlocks, 128, 0, hs>>>(R->geom, ch, R->st, Lf->st, S->tree, R->d_zob, Lf->d_sym);
       S->launches++;
@@ -1642,8 +1690,9 @@ int runVisits(kc_search* S) {
         S->launches += 2;
       }
       if(c.graph) {
-        if(c.P <= 128) k_expand_backup_graph<4><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
-        else k_expand_backup_graph<MAX_POLICY_SLOTS_PER_LANE><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+        if(c.P <= 128 && preload) k_expand_backup_graph<4, true><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+        else if(c.P <= 128) k_expand_backup_graph<4, false><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
+        else k_expand_backup_graph<MAX_POLICY_SLOTS_PER_LANE, false><<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss, H[h].misc);
       }
       else k_expand_backup<<<warpBlocks, 128, 0, hs>>>(ch, S->tree, H[h].policy, H[h].winLoss);
       S->launches++;
@@ -1775,10 +1824,14 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   {
     // two half batches when each still gives every SM pair a work item of the trunk kernel (bf16 path with device-side batching);
     // KC_SEARCH_PIPELINE=0 keeps one batch
-    static const bool allow = [] { const char* e = getenv("KC_SEARCH_PIPELINE"); return !e || atoi(e) != 0; }();
+    // Measured after the select / expand kernels got their compact child lists (b10c128, 18,944 games, full selfplay1.cfg, 4 moves):
+    // one batch 5.97 s, two half batches 6.13 s -- beside a resident trunk CTA the search kernels get 8 warps per SM instead of 32 and
+    // take about as long as the half trunk they hide under, while every half launch pays its own trunk prologue and wave tail.  So one
+    // batch is the default; KC_SEARCH_PIPELINE=1 selects the half-batch pipeline.
+    static const bool allow = [] { const char* e = getenv("KC_SEARCH_PIPELINE"); return e && atoi(e) != 0; }();
     const int item = 2 * kc::boardsPerTile(xSize, ySize);                 // boards per CTA work item
     const int half = ((numGames + 1) / 2 + item - 1) / item * item;
-    if(allow && !p->noPipeline && c.compact && kc::handleCanLeaveRegisters(handleOrNull) && half >= item * ctx->smCount && numGames - half > 0) {
+    if((p->noPipeline == 2 || (allow && p->noPipeline == 0)) && c.compact && kc::handleCanLeaveRegisters(handleOrNull) && half >= item * ctx->smCount && numGames - half > 0) {
       S->pipelined = true;
       kc::handleLeaveRegisters(handleOrNull, true);
       S->halfOff[0] = 0; S->halfCnt[0] = half; S->halfOff[1] = half; S->halfCnt[1] = numGames - half;

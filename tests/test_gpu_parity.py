@@ -944,7 +944,7 @@ def test_search_nn_randomize_matches_oracle(ctx, oracle, graph):
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", [False, True])
 def test_search_half_batch_pipeline_changes_nothing(ctx, graph):
-    """With the bf16 net and enough games the search runs two half batches on two streams (select / expand of one half under
+    """With the bf16 net and enough games the search can run two half batches on two streams (noPipeline = 2; select / expand of one half under
     the trunk kernel of the other).  Trees of different games never interact and an evaluation does not depend on its row, so
     moves, root statistics and counters are identical to the single-batch run."""
     from katacoffee_b200 import backend, modeldesc, capi
@@ -955,7 +955,7 @@ def test_search_half_batch_pipeline_changes_nothing(ctx, graph):
     kw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8, rootNoiseEnabled=1,
               rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, valueWeightExponent=0.5, nnRandomize=1) if graph else {}
     res = []
-    for nopipe in (1, 0):
+    for nopipe in (1, 2):    # 1: one batch (the default), 2: the half-batch pipeline
         s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, temperaturePlies=8, reuseTree=True, noPipeline=nopipe, **kw)
         s.reset(seed=31)
         lane = np.arange(G)
