@@ -11,7 +11,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_bytes.sum", "sm__cycles_elapsed.max", "smsp__inst_executed.sum", "dram__cycles_active", "sm__pipe_tensor_cycles_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct",
         "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
-        "gpc__cycles_elapsed.avg.per_second", "lts__t_sectors.avg.pct", "l1tex__throughput.avg.pct", "smsp__warp_issue_stalled"]
+        "gpc__cycles_elapsed.avg.per_second", "lts__t_sectors.avg.pct", "l1tex__throughput.avg.pct", "smsp__warp_issue_stalled",
+        "smsp__average_warps_issue_stalled", "sm__pipe_fp64_cycles_active.avg", "l1tex__t_sector_hit_rate"]
 path = os.path.join(ROOT, "gpurun_out", "launches.csv")
 if os.path.exists(path):
     rows = [l for l in open(path) if l.startswith('"')]
