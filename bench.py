@@ -429,7 +429,7 @@ def main():
                                       "temperature 1.25 -> 1.1, fpuParentWeightByVisitedPolicy pow 2, rootDesiredPerChildVisitsCoeff 2, cpuct 1.1, root FPU "
                                       "reduction 0, valueWeightExponent 0.5, rootNumSymmetriesToSample 4, useLcbForSelection (lcbStdevs 5, minVisitPropForLCB 0.15, "
                                       "useNonBuggyLcb), move choice from the full getPlaySelectionValues under the temperature schedule 0.75 -> 0.15 with prune 1, "
-                                      "nnRandomize; tree re-use.  Not built: nothing of that option set (useNoisePruning / useUncertainty are off in self-play, setup.cpp:525,543)",
+                                      "nnRandomize; tree re-use.  Nothing of that option set is left out (useNoisePruning / useUncertainty, built too, are off in self-play: setup.cpp:525,543)",
                                       useGraphSearch=True, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightExponent=0.8, reuseTree=True,
                                       cpuctExploration=1.1, rootFpuReductionMax=0.0, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83,
                                       rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.25,

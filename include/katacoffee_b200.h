@@ -348,11 +348,14 @@ typedef struct {
   double minVisitPropForLCB;    /* 0.15 in selfplay1.cfg:153 */
   int32_t rootNumSymmetriesToSample;   /* selfplay1.cfg:149 (4): every search starts by evaluating its root under that many distinct symmetries and
                                           averaging the outputs (searchnnhelpers.cpp:67-83, 133-174; NNOutput's averaging constructor) */
-  int32_t useNoisePruning;      /* must be 0: pruneNoiseWeight (searchupdatehelpers.cpp:422-470) is not built; self-play leaves it off (setup.cpp:525) */
+  int32_t useNoisePruning;      /* SearchParams::useNoisePruning (pruneNoiseWeight, searchupdatehelpers.cpp:422-470): in creation order, a child below the
+                                   weighted average of its elder siblings keeps at most twice its raw-policy share of their weight; off in self-play
+                                   (setup.cpp:525), on in the GTP / analysis defaults */
   int32_t useUncertainty;       /* SearchParams::useUncertainty: a node's own evaluation weighs uncertaintyCoeff / (shorttermWinlossError ^ exponent +
                                    coeff / maxWeight) instead of 1 (computeWeightFromNNOutput, searchupdatehelpers.cpp:91-113); off in self-play */
   int32_t pad4_;
   double uncertaintyCoeff, uncertaintyExponent, uncertaintyMaxWeight;   /* 0.25 / 1.0 / 8.0 in the GTP defaults (setup.cpp:545-560) */
+  double noisePruneUtilityScale, noisePruningCap;                        /* 0.15 / 1e50 (searchparams.cpp:27-28) */
 } kc_search_params;
 /* With any of chosenMoveTemperature[Early] or useLcbForSelection set in graph mode the move is chosen from the full
  * Search::getPlaySelectionValues (child weights; children other than the most stably explored one cut down to the weight its final

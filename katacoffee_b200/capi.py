@@ -69,7 +69,8 @@ class SearchParams(C.Structure):
                 ("noPipeline", C.c_int32), ("nnRandomize", C.c_int32),
                 ("useLcbForSelection", C.c_int32), ("useNonBuggyLcb", C.c_int32), ("lcbStdevs", C.c_double), ("minVisitPropForLCB", C.c_double),
                 ("rootNumSymmetriesToSample", C.c_int32), ("useNoisePruning", C.c_int32), ("useUncertainty", C.c_int32), ("pad4_", C.c_int32),
-                ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double)]
+                ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double),
+                ("noisePruneUtilityScale", C.c_double), ("noisePruningCap", C.c_double)]
 
 
 class SearchStats(C.Structure):

@@ -67,7 +67,7 @@ struct SearchCfg {
   int boardArea;
   // the rest of selfplay1.cfg / the GTP defaults: LCB move selection, root symmetry averaging, uncertainty weighting
   int useLcb, nonBuggyLcb, rootSyms, noisePruning, useUncertainty;
-  double lcbStdevs, minVisitPropLcb, uncCoeff, uncExp, uncMaxWeight;
+  double lcbStdevs, minVisitPropLcb, uncCoeff, uncExp, uncMaxWeight, noisePruneScale, noisePruneCap;
   int fullPlaySelection;   // the move choice runs Search::getPlaySelectionValues (child weights, reduced weights, LCB) instead of plain edge visits
   uint64_t seed;
 };
@@ -754,6 +754,52 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
   }
   sumW = warpSumD(sumW);
   sumWU = warpSumD(sumWU);
+  const double origW = sumW;   // origTotalChildWeight: what the subtree value bias weighs with
+  if(c.noisePruning) {
+    // pruneNoiseWeight (searchupdatehelpers.cpp:422-470): a sequential pass over the children in creation order.  Child k lives on lane
+    // k mod 32; every lane follows the same recurrence on broadcast values and the owner keeps the new weight.
+    int good = 0;
+#pragma unroll
+    for(int m = 0; m < SL; m++) good += nwl[m] != 0.0;
+    for(int o = 16; o > 0; o >>= 1) good += __shfl_xor_sync(0xffffffffu, good, o);
+    if(good > 1 && sumW > 0.00001) {
+      const float* pol = nd.policy();
+      const int pla = nd.nextPla();
+      double uSum = 0.0, wSum = 0.0, pSum = 0.0;
+#pragma unroll
+      for(int m = 0; m < SL; m++) {
+        const int kk = lane + 32 * m;
+        const double myPol = (kk < nc && nwl[m] != 0.0) ? fmax(1e-30, (double)pol[lst[kk]]) : 0.0;
+        const int cnt = min(32, nc - 32 * m);   // warp-uniform
+        for(int j = 0; j < cnt; j++) {
+          const double wk = __shfl_sync(0xffffffffu, nwl[m], j);
+          if(wk == 0.0) continue;   // uniform
+          const double cu = __shfl_sync(0xffffffffu, cuv[m], j);
+          const double rawPolicy = __shfl_sync(0xffffffffu, myPol, j);
+          const double utility = pla == 2 ? cu : -cu;
+          double nwk = wk;
+          if(wSum > 0 && pSum > 0) {
+            const double gap = __dsub_rn(__ddiv_rn(uSum, wSum), utility);
+            if(gap > 0) {
+              const double lenient = __dmul_rn(2.0, __ddiv_rn(__dmul_rn(wSum, rawPolicy), pSum));
+              if(wk > lenient) {
+                double toSub = __dmul_rn(__dsub_rn(wk, lenient), __dsub_rn(1.0, detExp(-__ddiv_rn(gap, c.noisePruneScale))));
+                if(toSub > c.noisePruneCap) toSub = c.noisePruneCap;
+                nwk = __dsub_rn(wk, toSub);
+              }
+            }
+          }
+          if(lane == j) nwl[m] = nwk;
+          uSum = __dadd_rn(uSum, __dmul_rn(utility, nwk)); wSum = __dadd_rn(wSum, nwk); pSum = __dadd_rn(pSum, rawPolicy);
+        }
+      }
+      sumW = wSum;
+      double part = 0.0;
+#pragma unroll
+      for(int m = 0; m < SL; m++) if(nwl[m] != 0.0) part = __dadd_rn(part, __dmul_rn(nwl[m], cuv[m]));
+      sumWU = warpSumD(part);
+    }
+  }
   // at a noised root the children the move choice would prune / reduce lose the same weight here (:196-206)
   double amountToSubtract = 0.0, amountToPrune = 0.0;
   if(isRoot && c.rootNoise && !c.noisePruning) {
@@ -832,7 +878,7 @@ __device__ __forceinline__ void recomputeNode(const SearchCfg& c, double* biasVa
       double ed = E[0], ew = E[1];
       if(sumW > 1e-10) {
         const double uc = __ddiv_rn(sumWU, sumW);
-        const double bw = biasPow(sumW, c.biasExp);
+        const double bw = biasPow(origW, c.biasExp);
         const double ds = __dmul_rn(__dsub_rn(uc, nd.nnUtility()), bw);
         ed = __dadd_rn(ed, __dsub_rn(ds, nd.lastDelta()));
         ew = __dadd_rn(ew, __dsub_rn(bw, nd.lastWeight()));
@@ -1726,7 +1772,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->rootNumSymmetriesToSample >= 0 && p->rootNumSymmetriesToSample <= 8, "kc_search_create: rootNumSymmetriesToSample must be within 0..8");
   KC_CHECK(!p->useUncertainty || (p->uncertaintyCoeff > 0.0 && p->uncertaintyExponent >= 0.0 && p->uncertaintyMaxWeight >= 1.0),
            "kc_search_create: useUncertainty needs uncertaintyCoeff > 0, uncertaintyExponent >= 0 and uncertaintyMaxWeight >= 1");
-  KC_CHECK(!p->useNoisePruning, "kc_search_create: useNoisePruning (pruneNoiseWeight, searchupdatehelpers.cpp:422-470) is not built; the self-play configuration leaves it off (setup.cpp:525)");
+  KC_CHECK(!p->useNoisePruning || (p->noisePruneUtilityScale > 0.0 && p->noisePruningCap >= 0.0), "kc_search_create: useNoisePruning needs noisePruneUtilityScale > 0 and noisePruningCap >= 0");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
   S->ctx = ctx; S->handle = handleOrNull;
@@ -1745,11 +1791,11 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   const bool rootPolicyChange = c.rootNoise || (c.rootTemp > 0.0 && c.rootTemp != 1.0) || (c.rootTempEarly > 0.0 && c.rootTempEarly != 1.0);
   c.useLcb = p->useLcbForSelection ? 1 : 0; c.nonBuggyLcb = p->useNonBuggyLcb ? 1 : 0; c.lcbStdevs = p->lcbStdevs; c.minVisitPropLcb = p->minVisitPropForLCB;
   c.rootSyms = p->rootNumSymmetriesToSample > 1 ? std::min(8, p->rootNumSymmetriesToSample) : 1;
-  c.noisePruning = p->useNoisePruning ? 1 : 0;
+  c.noisePruning = p->useNoisePruning ? 1 : 0; c.noisePruneScale = p->noisePruneUtilityScale; c.noisePruneCap = p->noisePruningCap;
   c.useUncertainty = p->useUncertainty ? 1 : 0; c.uncCoeff = p->uncertaintyCoeff; c.uncExp = p->uncertaintyExponent; c.uncMaxWeight = p->uncertaintyMaxWeight;
   // every option beyond plain PUCT runs on the node-centric statistics of graph mode
   c.graph = (p->useGraphSearch || p->subtreeValueBiasFactor != 0.0 || rootPolicyChange || c.fpuPW || c.rootDesired > 0.0 || c.vwExp != 0.0 || c.useLcb || c.rootSyms > 1 ||
-             c.useUncertainty) ? 1 : 0;
+             c.useUncertainty || c.noisePruning) ? 1 : 0;
   // graph mode under the reference's move-choice schedule (or LCB): the move is chosen from the full getPlaySelectionValues
   c.fullPlaySelection = (c.graph && (c.useLcb || c.moveTemp > 0.0 || c.moveTempEarly > 0.0)) ? 1 : 0;
   c.useTable = p->useGraphSearch ? 1 : 0;

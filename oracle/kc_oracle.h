@@ -241,10 +241,11 @@ typedef struct {
   /* the rest of cpp/configs/training/selfplay1.cfg:144-185 and of the GTP / analysis defaults (setup.cpp:520-560) */
   int32_t useLcbForSelection, useNonBuggyLcb;
   double lcbStdevs, minVisitPropForLCB;
-  int32_t rootNumSymmetriesToSample, useNoisePruning;   /* useNoisePruning: only its effect on the root's prune step (pruneNoiseWeight itself is not restated) */
+  int32_t rootNumSymmetriesToSample, useNoisePruning;
   int32_t useUncertainty, pad4_;
   double uncertaintyCoeff, uncertaintyExponent, uncertaintyMaxWeight;
   double chosenMoveSubtract, chosenMovePrune;           /* also applied to the root's children in recomputeNodeStats when the root is noised */
+  double noisePruneUtilityScale, noisePruningCap;       /* 0.15, 1e50 (searchparams.cpp:27-28) */
 } ko_search_params;
 void ko_search_last_play_selection(double* out, int P);
 int ko_search_choose_values(const double* values, const uint8_t* order, int P, int boardArea, int ply, double tempEarly, double tempLate,

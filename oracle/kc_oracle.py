@@ -395,7 +395,8 @@ class SearchParams(C.Structure):
                 ("useLcbForSelection", C.c_int32), ("useNonBuggyLcb", C.c_int32), ("lcbStdevs", C.c_double), ("minVisitPropForLCB", C.c_double),
                 ("rootNumSymmetriesToSample", C.c_int32), ("useNoisePruning", C.c_int32), ("useUncertainty", C.c_int32), ("pad4_", C.c_int32),
                 ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double),
-                ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double)]
+                ("chosenMoveSubtract", C.c_double), ("chosenMovePrune", C.c_double),
+                ("noisePruneUtilityScale", C.c_double), ("noisePruningCap", C.c_double)]
 
 
 def _with_extras(sp, extra):

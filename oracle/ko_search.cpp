@@ -496,8 +496,43 @@ struct GraphSearch {
       partW[k & 31] = partW[k & 31] + w[k];
       partWU[k & 31] = partWU[k & 31] + w[k] * cu;
     }
-    const double sumW = butterfly(partW);
+    const double origW = butterfly(partW);   // origTotalChildWeight: what the subtree value bias weighs with
+    double sumW = origW;
     double sumWU = butterfly(partWU);
+    if(p->useNoisePruning) {
+      // pruneNoiseWeight (searchupdatehelpers.cpp:422-470), children in creation order: a child whose utility lies below the weighted
+      // average of the children before it keeps at most twice its raw-policy share of their weight, the excess shrinking with the gap
+      int good = 0;
+      for(int k = 0; k < nk; k++) good += w[k] != 0.0;
+      if(good > 1 && sumW > 0.00001) {
+        double uSum = 0.0, wSum = 0.0, pSum = 0.0;
+        for(int k = 0; k < nk; k++) {
+          if(w[k] == 0.0) continue;
+          int cv; double cw, cu;
+          childStats(nd, ks[k], cv, cw, cu);
+          const double utility = nd.nextPla == 2 ? cu : -cu;
+          const double rawPolicy = std::max(1e-30, (double)nd.policy[ks[k]]);
+          double nwk = w[k];
+          if(wSum > 0 && pSum > 0) {
+            const double gap = uSum / wSum - utility;
+            if(gap > 0) {
+              const double lenient = 2.0 * ((wSum * rawPolicy) / pSum);
+              if(w[k] > lenient) {
+                double toSub = (w[k] - lenient) * (1.0 - detExp(-(gap / p->noisePruneUtilityScale)));
+                if(toSub > p->noisePruningCap) toSub = p->noisePruningCap;
+                nwk = w[k] - toSub;
+              }
+            }
+          }
+          w[k] = nwk;
+          uSum = uSum + utility * nwk; wSum = wSum + nwk; pSum = pSum + rawPolicy;
+        }
+        sumW = wSum;
+        double partP[32] = {0};
+        for(int k = 0; k < nk; k++) if(w[k] != 0.0) { int cv; double cw, cu; childStats(nd, ks[k], cv, cw, cu); partP[k & 31] = partP[k & 31] + w[k] * cu; }
+        sumWU = butterfly(partP);
+      }
+    }
     // at a noised root the children the move choice would prune / reduce lose the same weight here (:196-206)
     double amountToSubtract = 0.0, amountToPrune = 0.0;
     if(isRoot && p->rootNoiseEnabled && !p->useNoisePruning) {
@@ -548,7 +583,7 @@ struct GraphSearch {
       BiasEntry& E = bias[nd.biasEntry];
       if(sumW > 1e-10) {
         const double uc = sumWU / sumW;
-        const double bw = biasPow(sumW, p->subtreeValueBiasWeightExponent);
+        const double bw = biasPow(origW, p->subtreeValueBiasWeightExponent);
         const double ds = (uc - nd.nnUtility) * bw;
         E.deltaSum = E.deltaSum + (ds - nd.lastDelta);
         E.weightSum = E.weightSum + (bw - nd.lastWeight);

@@ -799,7 +799,10 @@ SELFPLAY1_CFG = dict(rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10
     (6, 6, 4, 40, 100, dict(rootNumSymmetriesToSample=8, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25,
                             chosenMovePrune=2.0, chosenMoveSubtract=0.5)),
     (5, 5, 4, 96, 160, dict(useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)),   # setup.cpp:545-560 (GTP defaults)
-    (5, 5, 4, 64, 160, dict(SELFPLAY1_CFG, useUncertainty=1, uncertaintyCoeff=0.2, uncertaintyExponent=0.5, uncertaintyMaxWeight=4.0, rootNumSymmetriesToSample=2))])
+    (5, 5, 4, 64, 160, dict(SELFPLAY1_CFG, useUncertainty=1, uncertaintyCoeff=0.2, uncertaintyExponent=0.5, uncertaintyMaxWeight=4.0, rootNumSymmetriesToSample=2)),
+    (5, 5, 4, 96, 200, dict(useNoisePruning=1, noisePruneUtilityScale=0.15, noisePruningCap=1e50)),                       # setup.cpp:520-538 (GTP defaults)
+    (6, 6, 4, 40, 120, dict(SELFPLAY1_CFG, useNoisePruning=1, noisePruneUtilityScale=0.05, noisePruningCap=3.0, useUncertainty=1, uncertaintyCoeff=0.25,
+                            uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0, valueWeightExponent=0.25))])               # the GTP / analysis combination
 def test_search_selfplay_options_bit_exact(ctx, oracle, W, H, K, G, V, opts):
     """The self-play configuration's remaining search options -- shaped Dirichlet root noise (deterministic gamma sampler), root
     policy temperature, FPU parent weighting by visited policy, rootDesiredPerChildVisitsCoeff -- on top of graph search and the
@@ -841,7 +844,8 @@ LCB_CFG = dict(useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, use
     LCB_CFG,                                                   # + LCB move selection
     dict(LCB_CFG, rootNumSymmetriesToSample=4),                # + root symmetry averaging: the whole selfplay1.cfg:144-185 set
     dict(LCB_CFG, useNonBuggyLcb=0, lcbStdevs=2.0, minVisitPropForLCB=0.05),   # the historical LCB form, sharper bound
-    dict(LCB_CFG, rootNumSymmetriesToSample=3, useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)])
+    dict(LCB_CFG, rootNumSymmetriesToSample=3, useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0),
+    dict(LCB_CFG, useNoisePruning=1, noisePruneUtilityScale=0.15, noisePruningCap=1e50)])
 def test_search_selfplay_config_tree_reuse_matches_oracle(ctx, oracle, extra):
     """selfplay1.cfg's search options together with tree re-use, self-played to the end: fresh noise and fresh averaged root evaluations
     on every new root, play-selection values (reduced weights, LCB), moves, counters and the re-rooted graphs equal the oracle's."""

@@ -229,3 +229,25 @@ def test_oracle_root_symmetry_sampling_and_uncertainty(oracle):
     assert np.abs(e1 - e2).max() < 1e-6
     unc = oracle.search_run_graph(og, 50, useUncertainty=1, uncertaintyCoeff=0.25, uncertaintyExponent=1.0, uncertaintyMaxWeight=8.0)
     assert unc["rootVisits"] == 50 and unc["digest"] != one["digest"] and (unc["edgeVisits"] != one["edgeVisits"]).any()
+
+
+def test_oracle_noise_pruning_changes_weights_not_visits_bookkeeping(oracle):
+    """useNoisePruning (pruneNoiseWeight, searchupdatehelpers.cpp:422-470): the search still makes maxVisits visits, the graph differs
+    from the unpruned one, a tighter utility scale prunes more (the root's weight drops further below its visit count), and a cap of 0
+    switches the pruning off bit for bit."""
+    changed = tighter = 0
+    for gid in range(12):
+        og = _midgame(oracle, 5, 5, 4, 3, gid, 2 + gid % 5)
+        if og.finished():
+            continue
+        kw = dict(valueWeightExponent=0.5, noiseSeed=5, noiseGameId=gid, **SELFPLAY_OPTS)   # root noise sends visits to low-prior moves: what the pruning is for
+        base = oracle.search_run_graph(og, 300, **kw)
+        on = oracle.search_run_graph(og, 300, useNoisePruning=1, noisePruneUtilityScale=0.15, noisePruningCap=1e50, **kw)
+        tight = oracle.search_run_graph(og, 300, useNoisePruning=1, noisePruneUtilityScale=0.01, noisePruningCap=1e50, **kw)
+        off = oracle.search_run_graph(og, 300, useNoisePruning=1, noisePruneUtilityScale=0.15, noisePruningCap=0.0, chosenMovePrune=0.0, **kw)
+        base0 = oracle.search_run_graph(og, 300, chosenMovePrune=0.0, **kw)
+        assert on["rootVisits"] == tight["rootVisits"] == base["rootVisits"] == 300
+        changed += on["digest"] != base["digest"]
+        tighter += tight["digest"] != on["digest"]
+        assert off["digest"] == base0["digest"] and (off["edgeVisits"] == base0["edgeVisits"]).all()
+    assert changed >= 6 and tighter >= 6
