@@ -77,7 +77,7 @@ struct TrunkCfg {
   // scratch: they are written after the last pooling pass has been read (named barrier in between) and read before the next one
   static_assert((MAX_NB * MAXC + MAX_NB * MAX_V2) * 4 <= 128 * SCR_STRIDE * 4, "bias + v2 buffers alias the pooling scratch");
   static constexpr int OFF_SYM = OFF_POOLB + NT * MAX_NB * POOLW * 4;
-  static constexpr int OFF_MASK = OFF_SYM + 448;                  // masked boards: [NT][128] row mask + [NT][MAX_NB][4] per-board pooling constants (fp32)
+  static constexpr int OFF_MASK = OFF_SYM + 800;                  // (OFF_SYM: the inverse symmetry maps, 8 x H*W bytes, up to 10x10)                  // masked boards: [NT][128] row mask + [NT][MAX_NB][4] per-board pooling constants (fp32)
   static constexpr int OFF_PAR = OFF_MASK + NT * (128 + MAX_NB * 4) * 4;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
   static constexpr int OFF_BAR = OFF_PAR + NT * 2 * 2 * MAXC * 4; // folded BN, staged while the tensor core is still busy with it
   // barriers (8 bytes each)

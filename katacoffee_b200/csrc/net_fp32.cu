@@ -608,8 +608,10 @@ int kc_handle_create(kc_ctx* ctx, const kc_model* model, int maxBatch, int nnXLe
   auto alloc = [&](auto** p, size_t bytes) { if(!rc && cudaMalloc((void**)p, bytes) != cudaSuccess) rc = kc::fail("kc_handle_create: out of device memory"); };
   if(h->bf16) {
     if(!model->trunk) { delete h; return kc::fail("kc_handle_create: bf16 tcgen05 path unavailable for this model: " + model->trunkUnsupportedWhy); }
-    if(nnXLen > KC_MAX_DEVICE_LEN || nnYLen > KC_MAX_DEVICE_LEN || boardsPerTile(nnXLen, nnYLen) < 1) {
-      delete h; return kc::fail("kc_handle_create: bf16 path needs H*(W+1) <= 128");
+    // a 128-row activation tile holds whole boards with one pad column each: every size up to the reference's 10x10 (board.h:120) fits
+    // (10 x 11 = 110 rows, one board per tile); the halo must cover one tile row + 1
+    if(boardsPerTile(nnXLen, nnYLen) < 1 || boardsPerTile(nnXLen, nnYLen) * (nnXLen + 1) + 1 > HALO_ROWS) {
+      delete h; return kc::fail("kc_handle_create: the tensor path needs H*(W+1) <= 128");
     }
   }
   if(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -1402,7 +1402,9 @@ def test_search_root_symmetry_sampling_with_the_net(ctx, oracle):
     ("b6c96", 5, 5, [(5, 5), (4, 4), (3, 5), (5, 2), (4, 5)]),      # boards of several sizes in one batch, inside a 5x5 slot
     ("b10c128", 6, 6, [(6, 6), (5, 5), (4, 6), (3, 3)]),
     ("b15c192", 6, 6, [(5, 5), (6, 4)]),                            # the wide-trunk kernel
-    ("b6c96-mish", 7, 7, [(7, 7), (5, 5), (6, 3)])])
+    ("b6c96-mish", 7, 7, [(7, 7), (5, 5), (6, 3)]),
+    ("b10c128", 10, 10, [(10, 10), (9, 9), (8, 8), (7, 10), (5, 5)]),   # the reference's maximum board (board.h:120): one board per 128-row tile
+    ("b6c96", 9, 8, [(9, 8), (8, 8), (9, 3)])])
 def test_masked_boards_on_the_tensor_path(ctx, oracle, net, nnX, nnY, boards):
     """requireExactNNLen = false on the tensor-core path (nninterface.h:73-76): boards smaller than the net's nnXLen x nnYLen slot, the
     on-board plane (input channel 0) as the mask (eigenbackend.cpp:1438), per-board pooling divisors and maxima over on-board cells
