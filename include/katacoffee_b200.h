@@ -33,7 +33,8 @@ extern "C" {
 #define KC_MAX_ARR_SIZE ((KC_MAX_LEN + 1) * (KC_MAX_LEN + 2) + 1) /* board.h:120-124 */
 #define KC_NUM_SPATIAL_V1 15                                 /* SURVEY.md 8.1-F      */
 #define KC_NUM_GLOBAL_V1 1
-#define KC_MAX_DEVICE_LEN 7  /* bitboard kernels: H*(W+1) <= 64 */
+#define KC_MAX_DEVICE_LEN 7  /* fast bitboard kernels, the device search and the evaluator front end: H*(W+1) <= 64.  kc_games_* and the
+                                net paths take every size up to KC_MAX_LEN (beyond 7x7: a general kernel on 128-bit bitboards) */
 
 typedef struct kc_ctx kc_ctx;
 typedef struct kc_model kc_model;

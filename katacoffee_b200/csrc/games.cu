@@ -27,6 +27,7 @@
 #include "net.h"
 
 #include "games_device.cuh"
+#include "games_big.cuh"
 
 namespace kc {
 
@@ -564,6 +565,13 @@ void launchGamesD(kc_games* G, int feat, int useMoves, const StepOut& so, const 
 }
 template <bool DO_STEP>
 void launchGames(kc_games* G, int feat, int useMoves, const StepOut& so, FeatOut fo) {
+  if(G->big) {   // boards beyond 7x7: the general 128-bit kernel (no planes / fp32 NCHW / fp32 NHWC; callers never ask it for trunk tiles)
+    const int blocks = (G->geom.numGames + TB_BIG - 1) / TB_BIG;
+    games_big_kernel<DO_STEP><<<blocks, TB_BIG, 0, G->stream>>>(G->geom, G->st, static_cast<const BigGeom*>(G->d_bigGeom), G->d_moves, useMoves, G->d_zob, so,
+                                                               fo.planes, fo.global, fo.symmetry, fo.permuteDirs, feat > 2 ? 0 : feat);
+    G->launches++;
+    return;
+  }
   int gpb = feat == 3 ? G->geom.NB * 8 : feat == 4 ? G->geom.NB * 2 : TB_PLAIN;   // FEAT 3 / 4: whole trunk tiles per CTA
   fo.gamesPerBlock = gpb;
   int blocks = (G->geom.numGames + gpb - 1) / gpb;
@@ -599,9 +607,10 @@ extern "C" {
 int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen, kc_games** out) {
   KC_CHECK(ctx && out, "kc_games_create: null argument");
   KC_CHECK(numGames > 0, "kc_games_create: numGames must be positive");
-  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN,
-           "kc_games_create: board size must be within 2..7 (bitboard kernels need H*(W+1) <= 64)");
-  KC_CHECK(winLen >= 2 && winLen <= 7, "kc_games_create: winLen must be within 2..7");
+  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_LEN && ySize <= KC_MAX_LEN, "kc_games_create: board size must be within 2..10 (board.h:120)");
+  KC_CHECK(winLen >= 2 && winLen <= KC_MAX_LEN, "kc_games_create: winLen must be within 2..10");
+  // up to 7x7 a padded bitboard (bit = y*(W+1) + x) fits 64 bits: the fast kernels; beyond that the general 128-bit kernel
+  const bool big = xSize > KC_MAX_DEVICE_LEN || ySize > KC_MAX_DEVICE_LEN;
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_games* G = new kc_games();
   G->ctx = ctx;
@@ -611,7 +620,20 @@ int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen,
   g.LW = (4 * g.HW + 31) / 32;
   g.numGames = numGames;
   g.rowMask = (1ULL << g.W) - 1;
-  for(int y = 0; y < g.H; y++)
+  G->big = big;
+  if(big) {
+    BigGeom bg;
+    memset(&bg, 0, sizeof bg);
+    for(int y = 0; y < g.H; y++)
+      for(int x = 0; x < g.W; x++) {
+        const B128 bit = B128::bit(y * g.stride + x);
+        bg.all |= bit;
+        bg.lines[0][x] |= bit; bg.lines[1][y] |= bit; bg.lines[2][x - y + g.H - 1] |= bit; bg.lines[3][x + y] |= bit;
+      }
+    KC_CUDA(cudaMalloc(&G->d_bigGeom, sizeof bg));
+    KC_CUDA(cudaMemcpy(G->d_bigGeom, &bg, sizeof bg, cudaMemcpyHostToDevice));
+  }
+  for(int y = 0; y < g.H && !big; y++)
     for(int x = 0; x < g.W; x++) {
       uint64_t bit = 1ULL << (y * g.stride + x);
       g.all |= bit;
@@ -641,6 +663,7 @@ int kc_games_create(kc_ctx* ctx, int numGames, int xSize, int ySize, int winLen,
   KC_CUDA(cudaMalloc(&G->st.black, n * 8)); KC_CUDA(cudaMalloc(&G->st.white, n * 8));
   KC_CUDA(cudaMalloc(&G->st.hash0, n * 8)); KC_CUDA(cudaMalloc(&G->st.hash1, n * 8));
   KC_CUDA(cudaMalloc(&G->st.gameId, n * 8)); KC_CUDA(cudaMalloc(&G->st.misc, n * 8));
+  if(big) { KC_CUDA(cudaMalloc(&G->st.blackHi, n * 8)); KC_CUDA(cudaMalloc(&G->st.whiteHi, n * 8)); }
   KC_CUDA(cudaMalloc(&G->d_moves, n * 2));
   KC_CUDA(cudaMalloc(&G->d_legal, 4 * n * g.LW * 4)); KC_CUDA(cudaMalloc(&G->d_status, 4 * n * 4));   // 4 slots: the per-ply ring of the multi-ply launches, slot 0 = the current position
   KC_CUDA(cudaMalloc(&G->d_sitHash, 4 * n * 16)); KC_CUDA(cudaMalloc(&G->d_played, 4 * n * 2));
@@ -661,7 +684,7 @@ int kc_games_destroy(kc_games* G) {
   cudaFree(G->d_zob); cudaFree(G->st.black); cudaFree(G->st.white); cudaFree(G->st.hash0); cudaFree(G->st.hash1);
   cudaFree(G->st.gameId); cudaFree(G->st.misc); cudaFree(G->d_moves); cudaFree(G->d_legal); cudaFree(G->d_status);
   cudaFree(G->d_sitHash); cudaFree(G->d_played); cudaFree(G->d_stats); cudaFree(G->d_planes); cudaFree(G->d_global);
-  cudaFree(G->d_sym); cudaFree(G->d_flush);
+  cudaFree(G->d_sym); cudaFree(G->d_flush); cudaFree(G->st.blackHi); cudaFree(G->st.whiteHi); cudaFree(G->d_bigGeom);
   cudaFree(G->d_ppPolicy); cudaFree(G->d_ppWinLoss); cudaFree(G->d_ppMisc); cudaFree(G->d_ppHash);
   for(float* p : G->d_planesRing) cudaFree(p);
   for(cudaEvent_t e : G->evPool) cudaEventDestroy(e);
@@ -678,7 +701,11 @@ int kc_games_reset(kc_games* G, uint64_t seed, uint64_t firstGameId, int autoRef
   g.seed = seed;
   g.autoRefill = autoRefill ? 1 : 0;
   size_t n = (size_t)g.numGames;
-  std::vector<uint64_t> zero(n, 0), h0(n, g.sizeHash[0]), h1(n, g.sizeHash[1]), ids(n), misc(n, (4ULL << 40) | ((uint64_t)(1 << 3) << 56));
+  std::vector<uint64_t> zero(n, 0), h0(n, g.sizeHash[0]), h1(n, g.sizeHash[1]), ids(n), misc(n, G->big ? BIG_MISC_START : (4ULL << 40) | ((uint64_t)(1 << 3) << 56));
+  if(G->big) {
+    KC_CUDA(cudaMemcpyAsync(G->st.blackHi, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+    KC_CUDA(cudaMemcpyAsync(G->st.whiteHi, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
+  }
   for(size_t i = 0; i < n; i++) ids[i] = firstGameId + i;
   KC_CUDA(cudaMemcpyAsync(G->st.black, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
   KC_CUDA(cudaMemcpyAsync(G->st.white, zero.data(), n * 8, cudaMemcpyHostToDevice, G->stream));
@@ -699,6 +726,45 @@ int kc_games_load(kc_games* G, int g0, int n, const int8_t* stones, const int8_t
   KC_CUDA(cudaSetDevice(G->ctx->device));
   const ZobristTables& z = zobrist();
   std::vector<uint64_t> b(n), w(n), h0(n), h1(n), misc(n);
+  if(G->big) {   // 128-bit boards, 9-bit history entries (games_big.cuh)
+    std::vector<uint64_t> bh(n), wh(n);
+    for(int i = 0; i < n; i++) {
+      B128 bb{}, ww{};
+      uint64_t a0 = g.sizeHash[0], a1 = g.sizeHash[1];
+      for(int y = 0; y < g.H; y++)
+        for(int x = 0; x < g.W; x++) {
+          const int c = stones[(size_t)i * g.HW + y * g.W + x];
+          KC_CHECK(c >= 0 && c <= 2, "kc_games_load: stone colour must be 0, 1 or 2");
+          if(c == 0) continue;
+          if(c == 1) bb |= B128::bit(y * g.stride + x); else ww |= B128::bit(y * g.stride + x);
+          const int spot = (x + 1) + (y + 1) * (g.W + 1);
+          a0 ^= z.board[spot][c][0]; a1 ^= z.board[spot][c][1];
+        }
+      KC_CHECK(nextPla[i] == 1 || nextPla[i] == 2, "kc_games_load: nextPla must be 1 or 2");
+      uint64_t m = 0;
+      int lastDir = 4;
+      if(moves)
+        for(int k = 0; k < 5; k++) {
+          const int pos = moves[((size_t)i * 5 + (4 - k)) * 2 + 0], pla = moves[((size_t)i * 5 + (4 - k)) * 2 + 1];
+          if(pos < 0) continue;
+          KC_CHECK(pos < 4 * g.HW && (pla == 1 || pla == 2), "kc_games_load: bad history entry");
+          m |= (uint64_t)((pos % g.HW) | (pla << 7)) << (9 * k);
+          if(k == 0) lastDir = pos / g.HW;
+        }
+      const int nt = numTurns ? numTurns[i] : 0;
+      KC_CHECK(nt >= 0 && nt <= 255, "kc_games_load: numTurns out of range");
+      m |= ((uint64_t)lastDir << 45) | ((uint64_t)nt << 48) | ((uint64_t)(nextPla[i] << 3) << 56);
+      b[i] = bb.lo; bh[i] = bb.hi; w[i] = ww.lo; wh[i] = ww.hi; h0[i] = a0; h1[i] = a1; misc[i] = m;
+    }
+    KC_CUDA(cudaMemcpy(G->st.black + g0, b.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.blackHi + g0, bh.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.white + g0, w.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.whiteHi + g0, wh.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.hash0 + g0, h0.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.hash1 + g0, h1.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    KC_CUDA(cudaMemcpy(G->st.misc + g0, misc.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    return 0;
+  }
   for(int i = 0; i < n; i++) {
     uint64_t bb = 0, ww = 0, a0 = g.sizeHash[0], a1 = g.sizeHash[1];
     for(int y = 0; y < g.H; y++)
@@ -795,7 +861,15 @@ int gamesEval(kc_games* G, kc_handle* h, const int8_t* symmetry, const int* nDev
   fo.permuteDirs = (haveSym && kc::handlePermutesDirs(h)) ? 1 : 0;
   StepOut so = stepOutOf(G, true);   // also refreshes legal masks / status / sit-hashes of the evaluated positions
   so.played = nullptr; so.stats = nullptr;
-  if(kc::handleIsBf16(h)) {
+  if(kc::handleIsBf16(h) && G->big) {
+    // boards beyond 7x7: plain fp32 NCHW planes into the handle's raw input rows, then the conversion kc_forward uses (it applies
+    // the symmetry and builds the tiles)
+    KC_CHECK(rowOffset == 0 && !nDev, "kc_games_eval: boards beyond 7x7 are evaluated as one plain batch");
+    fo.planes = kc::handleRawInput(h); fo.global = kc::handleRawGlobal(h); fo.symmetry = nullptr; fo.permuteDirs = 0;
+    launchGames<false>(G, 1, 0, so, fo);
+    KC_CUDA(cudaGetLastError());
+    if(kc::handleConvertRaw(h, g.numGames, haveSym ? G->d_sym : nullptr, G->stream)) return 1;
+  } else if(kc::handleIsBf16(h)) {
     fo.tiles = (uint4*)kc::handleInputTiles(h) + (size_t)(rowOffset / g.NB) * 2 * TILE_ROWS;
     kc::handleTileConstants(h, (float)g.K, &fo.tileOne, &fo.tileK);
     launchGames<false>(G, smallCtas ? 4 : 3, 0, so, fo);
@@ -836,7 +910,19 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
     for(int i = 0; i < RING - 1; i++)
       if(!G->d_planesRing[i]) KC_CUDA(cudaMalloc(&G->d_planesRing[i], (size_t)g.numGames * 15 * g.HW * 4));
   int nGroups = 0;
-  if(!h) {
+  if(!h && G->big) {
+    // boards beyond 7x7: the general kernel, one launch (rules + fp32 NCHW planes) and one event pair per ply
+    for(int p = 0; p < plies; p++) {
+      if(flushL2Bytes) KC_CUDA(cudaMemsetAsync(G->d_flush, p & 0xff, flushL2Bytes, G->stream));
+      KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups], G->stream));
+      FeatOut fo{};
+      fo.planes = G->d_planes; fo.global = G->d_global;
+      launchGames<true>(G, 1, 0, stepOutOf(G, true), fo);
+      KC_CUDA(cudaEventRecord(G->evPool[2 * nGroups + 1], G->stream));
+      nGroups++;
+    }
+    G->lastRunPlanes = G->d_planes; G->lastRunPlies = 1; G->lastRunRing = false;
+  } else if(!h) {
     // rules + features only: one multi-ply launch per group of RING plies, one event pair per launch
     PlaneRing ring;
     for(int i = 0; i < RING; i++) ring.slot[i] = (flushL2Bytes && i > 0) ? G->d_planesRing[i - 1] : G->d_planes;
@@ -890,6 +976,11 @@ int kc_games_run_timed(kc_games* G, kc_handle* h, int plies, size_t flushL2Bytes
       const int slot = flushL2Bytes ? p % RING : 0;
       fo.planes = slot == 0 ? G->d_planes : G->d_planesRing[slot - 1]; fo.global = G->d_global;
       launchGames<true>(G, 1, 0, so, fo);
+    } else if(kc::handleIsBf16(h) && G->big) {   // boards beyond 7x7: raw fp32 rows + the conversion kc_forward uses (see gamesEval)
+      fo.planes = kc::handleRawInput(h); fo.global = kc::handleRawGlobal(h);
+      launchGames<true>(G, 1, 0, so, fo);
+      if(kc::handleConvertRaw(h, g.numGames, nullptr, G->stream)) return 1;
+      if(kc::handleRunOnStream(h, g.numGames, G->stream, nullptr)) return 1;
     } else if(kc::handleIsBf16(h)) {
       fo.tiles = (uint4*)kc::handleInputTiles(h);
       kc::handleTileConstants(h, (float)g.K, &fo.tileOne, &fo.tileK);

@@ -9,6 +9,8 @@ struct kc_games {
   kc_ctx* ctx = nullptr;
   kc::Geom geom;
   kc::State st;
+  bool big = false;                   // a board beyond 7x7: 128-bit bitboards, games_big.cuh
+  void* d_bigGeom = nullptr;          // kc::BigGeom (line masks) for those boards
   uint64_t* d_zob = nullptr;          // [HW][2 colours][2]
   int16_t* d_moves = nullptr;
   uint32_t* d_legal = nullptr; uint32_t* d_status = nullptr; uint64_t* d_sitHash = nullptr; int16_t* d_played = nullptr;   // 4 slots of G entries each (slot 0 = current position; 1..3 = the multi-ply launches' per-ply ring)

@@ -24,6 +24,7 @@ struct Geom {
 
 struct State {   // SoA device arrays, one entry per game lane
   uint64_t* black; uint64_t* white; uint64_t* hash0; uint64_t* hash1; uint64_t* gameId; uint64_t* misc;
+  uint64_t* blackHi; uint64_t* whiteHi;   // boards beyond 7x7 only (games_big.cuh): bits 64.. of the padded bitboards, else null
 };
 // misc: bytes 0..4 = last five moves, most recent first: bits 0-5 dense cell, bits 6-7 player (0 = none)
 //       byte 5 = direction of the most recent move (4 = none), byte 6 = numTurns,

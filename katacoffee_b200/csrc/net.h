@@ -22,6 +22,9 @@ void* handleInputTiles(kc_handle* h);      // tensor path: [tiles][2][128] 16-by
 // bit patterns of 1.0 and of `k` (the win length, a small integer) in the handle's operand format: what a tile producer writes.
 // (tcgen05 kind::f16 wants A and B in ONE format: an MMA with bf16 tiles against fp16 weights is an illegal instruction on B200.)
 void handleTileConstants(const kc_handle* h, float k, uint32_t* one, uint32_t* kBits);
+float* handleRawInput(kc_handle* h);       // both paths: kc_forward's device copy of the raw rows [n][15*H*W] fp32
+float* handleRawGlobal(kc_handle* h);      // [n]
+int handleConvertRaw(kc_handle* h, int n, const int8_t* sym_dev, cudaStream_t stream);   // tensor path: raw NCHW rows -> symmetrised input tiles
 float* handleInputNHWC(kc_handle* h);      // fp32 path: [n][H*W][15]
 float* handleInputGlobal(kc_handle* h);    // fp32 path: [n][1]
 // Runs the net on the handle's (already symmetrised) input buffer on `stream`; symmetry_dev (device

@@ -370,6 +370,9 @@ int handleCheckGeometry(kc_handle* h, int W, int H, int n) {
 bool handleIsBf16(const kc_handle* h) { return h->bf16; }
 bool handlePermutesDirs(const kc_handle* h) { return (h->flags & KC_FLAG_SYM_PERMUTE_DIRS) != 0; }
 void* handleInputTiles(kc_handle* h) { return h->d_tiles; }
+float* handleRawInput(kc_handle* h) { return h->d_raw; }
+float* handleRawGlobal(kc_handle* h) { return h->d_rawGlobal; }
+int handleConvertRaw(kc_handle* h, int n, const int8_t* sym_dev, cudaStream_t stream) { return convertInputToTiles(h, n, /*rawNHWC=*/0, sym_dev, stream, 0); }
 float* handleInputNHWC(kc_handle* h) { return h->f32.in; }
 float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
 int handleCheckAbort(kc_handle* h) { return checkTrunkAbort(h); }

@@ -1773,6 +1773,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(!p->useUncertainty || (p->uncertaintyCoeff > 0.0 && p->uncertaintyExponent >= 0.0 && p->uncertaintyMaxWeight >= 1.0),
            "kc_search_create: useUncertainty needs uncertaintyCoeff > 0, uncertaintyExponent >= 0 and uncertaintyMaxWeight >= 1");
   KC_CHECK(!p->useNoisePruning || (p->noisePruneUtilityScale > 0.0 && p->noisePruningCap >= 0.0), "kc_search_create: useNoisePruning needs noisePruneUtilityScale > 0 and noisePruningCap >= 0");
+  KC_CHECK(xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN,
+           "kc_search_create: the device search runs on boards up to 7x7 (its rules and node layout are the 64-bit ones); kc_games_* take up to 10x10");
   KC_CUDA(cudaSetDevice(ctx->device));
   kc_search* S = new kc_search();
   S->ctx = ctx; S->handle = handleOrNull;

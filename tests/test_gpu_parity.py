@@ -93,7 +93,8 @@ def oracle_trajectories(oracle, W, H, K, seed, G, planes=True, nhwc=False):
     return recs, pl, gl, starts, ends
 
 
-@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 4096, 1), (6, 6, 4, 1500, 20261018), (5, 5, 4, 333, 7), (7, 7, 5, 200, 3), (4, 5, 3, 257, 9)])
+@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 4096, 1), (6, 6, 4, 1500, 20261018), (5, 5, 4, 333, 7), (7, 7, 5, 200, 3), (4, 5, 3, 257, 9),
+                                          (9, 9, 5, 300, 4), (10, 10, 5, 257, 5), (8, 8, 4, 200, 6), (10, 7, 5, 130, 8), (3, 10, 3, 100, 2)])   # beyond 7x7: 128-bit boards
 def test_games_step_bit_exact(ctx, oracle, W, H, K, G, seed):
     """Random-legal playouts to terminal: legal masks, status words (ply/finished/winner/next
     player), sit-hashes and the played move of every step equal the oracle's, bit for bit."""
@@ -122,7 +123,7 @@ def test_games_step_bit_exact(ctx, oracle, W, H, K, G, seed):
     games.close()
 
 
-@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 2048, 1), (6, 6, 4, 700, 5)])
+@pytest.mark.parametrize("W,H,K,G,seed", [(5, 5, 4, 2048, 1), (6, 6, 4, 700, 5), (10, 10, 5, 150, 2), (9, 8, 4, 130, 3)])
 def test_features_bit_exact(ctx, oracle, W, H, K, G, seed):
     """NNInputs::fillRowV1 planes (NCHW and NHWC) + global feature at every ply, incl. terminal positions."""
     from katacoffee_b200 import backend
@@ -144,10 +145,10 @@ def test_features_bit_exact(ctx, oracle, W, H, K, G, seed):
     games.close()
 
 
-def test_features_with_symmetry_bit_exact(ctx, oracle):
+@pytest.mark.parametrize("G,W,H", [(1024, 5, 5), (256, 10, 10), (200, 9, 7)])
+def test_features_with_symmetry_bit_exact(ctx, oracle, G, W, H):
     """copyInputsWithSymmetry fused into the feature kernel equals the oracle's copy of the plain planes."""
     from katacoffee_b200 import backend
-    G, W, H = 1024, 5, 5
     games = backend.Games(ctx, G, W, H, 4)
     games.reset(seed=11)
     for _ in range(6):
@@ -160,17 +161,17 @@ def test_features_with_symmetry_bit_exact(ctx, oracle):
             sel = np.flatnonzero(sym == s)
             src = base[sel]
             if nhwc:
-                src = src.reshape(-1, 15, 25).transpose(0, 2, 1).reshape(len(sel), -1)
+                src = src.reshape(-1, 15, W * H).transpose(0, 2, 1).reshape(len(sel), -1)
             exp = oracle.copy_inputs_with_symmetry(src, len(sel), H, W, 15, nhwc, s)
             assert (got[sel] == exp).all(), (nhwc, s)
     games.close()
 
 
-def test_forced_moves_illegal_and_load(ctx, oracle):
+@pytest.mark.parametrize("G,W,H,K", [(512, 5, 5, 4), (300, 10, 9, 5)])
+def test_forced_moves_illegal_and_load(ctx, oracle, G, W, H, K):
     """kc_games_step with explicit moves (legal, illegal, skip) and kc_games_load of arbitrary positions."""
     from katacoffee_b200 import backend
     rng = np.random.default_rng(4)
-    G, W, H, K = 512, 5, 5, 4
     HW = W * H
     stones = np.zeros((G, HW), np.int8)
     nextPla = np.zeros(G, np.int8)
@@ -179,7 +180,7 @@ def test_forced_moves_illegal_and_load(ctx, oracle):
     ogames = []
     for g in range(G):
         og = oracle.Game(W, H, K)
-        nst = int(rng.integers(0, 18))
+        nst = int(rng.integers(0, int(0.7 * HW)))
         cells = rng.permutation(HW)[:nst]
         hist = []
         for i, c in enumerate(cells):
@@ -369,10 +370,10 @@ def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "f16"])
-def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
+@pytest.mark.parametrize("G,W,H", [(777, 5, 5), (150, 10, 10), (140, 9, 8)])   # beyond 7x7: the 128-bit rules kernel feeds the net paths too
+def test_device_resident_eval_matches_oracle(ctx, oracle, mode, G, W, H):
     """kc_games_eval: planes generated on the device straight into the net input (no PCIe), with symmetry."""
     from katacoffee_b200 import backend, modeldesc
-    G, W, H = 777, 5, 5
     model = modeldesc.Model("b6c96", seed=2)
     om = oracle.Model(model)
     lm = backend.LoadedModel(ctx, model)
@@ -382,7 +383,7 @@ def test_device_resident_eval_matches_oracle(ctx, oracle, mode):
     for _ in range(9):
         games.step()
     planes, glob = games.features()
-    sym = ((np.arange(G) * 5) % 8).astype(np.int8)
+    sym = ((np.arange(G) * 5) % 8).astype(np.int8) if W == H else ((np.arange(G) * 5) % 4).astype(np.int8)
     games.eval(h, sym)
     got = h.readOutputs(G)
     if mode == "fp32":
@@ -464,7 +465,7 @@ def test_run_counters_and_checksum(ctx, oracle):
 
 
 @pytest.mark.parametrize("W,H,K,G,plies,flush", [(5, 5, 4, 3000, 1, 0), (5, 5, 4, 3000, 6, 0), (5, 5, 4, 2500, 11, 1 << 20), (5, 5, 4, 70, 19, 1 << 20),
-                                                 (6, 6, 4, 900, 7, 1 << 20), (4, 5, 3, 333, 10, 0)])
+                                                 (6, 6, 4, 900, 7, 1 << 20), (4, 5, 3, 333, 10, 0), (10, 10, 5, 130, 9, 0)])
 def test_fused_multi_ply_kernel_outputs_bit_exact(ctx, oracle, W, H, K, G, plies, flush):
     """The kernel the rules+features bench times (games_multi_kernel: up to 8 plies per launch, state in registers, planes to a
     ring of buffers): what its last ply leaves in the device buffers -- planes, masks, status words, hashes, moves -- equals the
@@ -477,7 +478,7 @@ def test_fused_multi_ply_kernel_outputs_bit_exact(ctx, oracle, W, H, K, G, plies
     out = games.readRunOutputs()
     # every ply of a launch writes its own slot of a 4-slot ring: the last min(4, plies of the last launch) plies are all delivered
     # (masks, status words, hashes, moves always; planes when the run used the plane ring)
-    back = min(4, (plies - 1) % 8 + 1)
+    back = min(4, (plies - 1) % 8 + 1) if max(W, H) <= 7 else 1    # boards beyond 7x7 step one ply per launch
     earlier = {b: games.readRunPly(b, planes=flush > 0) for b in range(back)}
     with pytest.raises(Exception):
         games.readRunPly(back if back < 4 else 4)

@@ -29,7 +29,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-SHAPES = [(5, 5, 4), (6, 6, 4), (4, 5, 3), (7, 7, 5), (3, 3, 3)]
+SHAPES = [(5, 5, 4), (6, 6, 4), (4, 5, 3), (7, 7, 5), (3, 3, 3), (10, 10, 5), (9, 8, 4)]   # incl. the reference maximum (board.h:120)
 
 
 @pytest.fixture(scope="module")
