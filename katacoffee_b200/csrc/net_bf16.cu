@@ -198,6 +198,7 @@ struct EpiCtx {
   float* scr; float* poolA; float* poolB; float* biasBuf; float* v2buf;
   const float* par;  // staged folded BN of the layer being finished: scale[MAXC] | bias[MAXC]
   const float* maskRow;   // masked boards: [128] 1.0 / 0.0 per row of this tile (shared), else null
+  const uint8_t* cellRow; // [H*W] tile row (y * tileRowW + x) of a board's cell, without the board offset (shared)
   const float* boardK;    // masked boards: [MAX_NB][4] = 1 / cells, (sqrt(cells) - 14) * 0.1, (sqrt(cells) - 14)^2 * 0.01 - 0.1 per board of this tile
   long long* dbg;    // non-null for the one thread / layer whose timeline is recorded
 };
@@ -242,36 +243,55 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
 
 // Two threads per (board, channel): even lane = upper rows, odd lane = lower rows, combined by one shuffle; the even lane
 // (c.e even, c.e >> 1 = board*16 + channel < NB*16) returns the board's sum and max.
-__device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float& sum, float& mx) {
+__device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float& sum, float& mx, long long* pd = nullptr) {
+  if(pd) pd[0] = clock64();
   named_bar_sync(1 + c.t, 128);   // the previous use of the scratch has been read
+  if(pd) pd[1] = clock64();
 #pragma unroll
   for(int j = 0; j < 16; j++) c.scr[c.r * SCR_STRIDE + j] = g[j];
   named_bar_sync(1 + c.t, 128);
+  if(pd) pd[2] = clock64();
   const int o = c.e >> 1, part = c.e & 1;
   const int b = o >> 4, j = o & 15;
   float s = 0.f, m = -1.0f;   // eigenbackend.cpp:145: max starts at -1
   if(b < P.NB) {
-    const int yMid = (P.H + 1) >> 1;
-    const int y0 = part ? yMid : 0, y1 = part ? P.H : yMid;
-    for(int y = y0; y < y1; y++) {
-      const float* rowp = c.scr + (y * P.tileRowW + b * P.stride) * SCR_STRIDE + j;
-      if(c.maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
-        const float* mk = c.maskRow + y * P.tileRowW + b * P.stride;
-        for(int x = 0; x < P.W; x++) {
-          float v = rowp[x * SCR_STRIDE];
-          s += v;
-          m = fmaxf(m, v + (mk[x] - 1.0f));
-        }
-      } else
-      for(int x = 0; x < P.W; x++) {
-        float v = rowp[x * SCR_STRIDE];
+    // even lane: cells 0, 2, 4, ...; odd lane: cells 1, 3, 5, ...  The tile row of a cell comes from a table (c.cellRow), four cells per
+    // iteration on two accumulators, so the shared-memory loads are independent of one another and of the running sums
+    const uint8_t* cr = c.cellRow;
+    const float* base = c.scr + b * P.stride * SCR_STRIDE + j;
+    float sB = 0.f, mB = -1.0f;
+    int i = part;
+    if(c.maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
+      const float* mk = c.maskRow + b * P.stride;   // same summation order as below: a board that fills its slot gives the same bits
+      for(; i + 6 < P.HW; i += 8) {
+        const int r0 = cr[i], r1 = cr[i + 2], r2 = cr[i + 4], r3 = cr[i + 6];
+        const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
+        s += v0; sB += v1; s += v2; sB += v3;
+        m = fmaxf(m, fmaxf(v0 + (mk[r0] - 1.0f), v2 + (mk[r2] - 1.0f))); mB = fmaxf(mB, fmaxf(v1 + (mk[r1] - 1.0f), v3 + (mk[r3] - 1.0f)));
+      }
+      for(; i < P.HW; i += 2) {
+        const int r = cr[i];
+        const float v = base[r * SCR_STRIDE];
+        s += v;
+        m = fmaxf(m, v + (mk[r] - 1.0f));
+      }
+    } else {
+      for(; i + 6 < P.HW; i += 8) {
+        const int r0 = cr[i], r1 = cr[i + 2], r2 = cr[i + 4], r3 = cr[i + 6];
+        const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
+        s += v0; sB += v1; s += v2; sB += v3;
+        m = fmaxf(m, fmaxf(v0, v2)); mB = fmaxf(mB, fmaxf(v1, v3));
+      }
+      for(; i < P.HW; i += 2) {
+        const float v = base[cr[i] * SCR_STRIDE];
         s += v;
         m = fmaxf(m, v);
       }
     }
+    s += sB; m = fmaxf(m, mB);
   }
   const float s2 = __shfl_xor_sync(0xffffffffu, s, 1), m2 = __shfl_xor_sync(0xffffffffu, m, 1);
-  sum = s + s2;       // even lane: upper rows + lower rows
+  sum = s + s2;       // even lane: even cells + odd cells
   mx = fmaxf(m, m2);
 }
 
@@ -378,8 +398,9 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
   }
 }
 
-__shared__ float sW3[2][4][MAX_V2 + 1];   // value / misc output matrices of the head, [tile][output][k], [V2] = bias
-__shared__ float sHeadPar[2][11 * HEADC + MAX_V2];   // small head parameters per tile (layout in epilogueHead), staged once per kernel
+__shared__ __align__(16) float sW3[2][4][MAX_V2 + 1];   // value / misc output matrices of the head, [tile][output][k], [V2] = bias
+__shared__ __align__(16) float sHeadPar[2][11 * HEADC + MAX_V2];   // read with 128-bit loads (W2)
+__shared__ uint8_t sCellRow[112];            // tile row of cell i of a board (pooling), up to 10x10   // small head parameters per tile (layout in epilogueHead), staged once per kernel
 
 __device__ __forceinline__ void stageHeadParams(const TrunkParams& P, const LayerDesc& L, int e, int t, float* par) {
   const int V2 = P.v2C;
@@ -435,12 +456,14 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   for(int half = 0; half < 2; half++) {
     float v[16], g[16], sum, mx;
     tmem_ld16(src + HEADC + half * 16, v);
+    if(hp) P.dbg[30 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), P.g1Act);
       g[j] = c.valid ? a : 0.f;
     }
-    poolBoards16(P, c, g, sum, mx);
+    poolBoards16(P, c, g, sum, mx, hp && half == 0 ? P.dbg + 40 : nullptr);
+    if(hp) P.dbg[31 + 4 * half] = clock64();
     const float kInv = c.boardK ? c.boardK[pb * 4] : P.invHW, kS1 = c.boardK ? c.boardK[pb * 4 + 1] : P.poolScale1,
                 kS2 = c.boardK ? c.boardK[pb * 4 + 2] : P.poolScale2;
     if(poolOut) {
@@ -450,6 +473,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       pooledG[pb * 96 + 64 + half * 16 + pj] = mx;
     }
     tmem_ld16(src + 2 * HEADC + half * 16, v);
+    if(hp) P.dbg[32 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), P.v1Act);
@@ -457,6 +481,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       v1a[half * 16 + j] = g[j];
     }
     poolBoards16(P, c, g, sum, mx);
+    if(hp) P.dbg[33 + 4 * half] = clock64();
     if(poolOut) {
       float mean = sum * kInv;
       pooledV[pb * 96 + half * 16 + pj] = mean;
@@ -730,6 +755,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
   // ---- one-time setup ----
   for(int i = threadIdx.x; i < NT * K::ACT_BYTES / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
   for(int i = threadIdx.x; i < 8 * P.HW; i += K::THREADS) sSym[i] = P.dstOfSrcRev[i];
+  for(int i = threadIdx.x; i < P.HW; i += K::THREADS) sCellRow[i] = (uint8_t)((i / P.W) * P.tileRowW + i % P.W);
   if(threadIdx.x == 0) {
     *reinterpret_cast<volatile int*>(smem + K::OFF_PROG) = 0;
     for(int i = 0; i < K::NSTAGES; i++) {
@@ -837,6 +863,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     c.slotB = c.b; c.slotCell = slotValid ? c.cell : -1;
     float* maskRowW = reinterpret_cast<float*>(smem + K::OFF_MASK) + c.t * 128;
     float* boardKW = reinterpret_cast<float*>(smem + K::OFF_MASK) + NT * 128 + c.t * MAX_NB * 4;
+    c.cellRow = sCellRow;
     c.maskRow = P.masked ? maskRowW : nullptr;
     c.boardK = P.masked ? boardKW : nullptr;
     uint32_t itemCount = 0;

@@ -25,3 +25,5 @@ for rep in range(3):
           "item 0 total (layer 5 ref -> head conv issue)", int(t1 - t0))
     print("   head phases rel. to head conv issue:", {k: int(out[i] - t1) for k, i in (("start", 24), ("pooling done", 25), ("TMEM released, synced", 26),
           ("pooled matmuls done", 27), ("synced", 28), ("v3 done", 29), ("end", 19))})
+    print("   head pooling detail rel. to head conv issue:", [int(out[i] - t1) for i in range(30, 38)])
+    print("   first pool call: entry, after barrier A, after stores + barrier B:", [int(out[i] - t1) for i in range(40, 43)])
