@@ -218,6 +218,7 @@ struct DeviceServer {
   kc_handle* handle = nullptr;
   kc_games* games = nullptr;        // maxBatch lanes; a batch of n rows runs with geom.numGames = n
   uint64_t* dH = nullptr;           // the device's own NNInputs::getHash of the rows (k_postprocess always writes it)
+  int* dBad = nullptr;              // set by k_postprocess when a row's policy sum or win / loss probabilities are not finite
   int P = 0, HW = 0;
 
   int create(kc_ctx* c, const kc_model* model, const kc_evaluator_config& cfg) {
@@ -225,6 +226,7 @@ struct DeviceServer {
     if(kc_handle_create(c, model, cfg.maxBatch, cfg.nnXLen, cfg.nnYLen, cfg.handleFlags & ~KC_FLAG_INPUTS_NHWC, &handle)) return 1;
     if(kc_games_create(c, cfg.maxBatch, cfg.nnXLen, cfg.nnYLen, cfg.winLen, &games)) return 1;
     KC_CUDA(cudaMalloc(&dH, (size_t)cfg.maxBatch * 16));
+    KC_CUDA(cudaMalloc(&dBad, 4));
     return 0;
   }
   void destroy() {
@@ -232,8 +234,8 @@ struct DeviceServer {
     if(games) kc_games_destroy(games);
     if(handle) kc_handle_destroy(handle);
     games = nullptr; handle = nullptr;
-    cudaFree(dH);
-    dH = nullptr;
+    cudaFree(dH); cudaFree(dBad);
+    dH = nullptr; dBad = nullptr;
   }
   int run(const kc_eval_batch* b) {
     KC_CUDA(cudaSetDevice(ctx->device));
@@ -253,12 +255,19 @@ struct DeviceServer {
     G->st = saved;
     G->geom.numGames = savedN;
     if(rc) return 1;
+    KC_CUDA(cudaMemsetAsync(dBad, 0, 4, st));
     kc::launchPostprocess(handle, b->n, G->geom.LW, G->d_legal, G->d_status, G->d_sitHash, b->policyTemperature, b->policyProbs, b->whiteWinLoss,
-                          b->miscOut, dH, st);
+                          b->miscOut, dH, st, 0, dBad);
     KC_CUDA(cudaGetLastError());
     if(b->wantOwnership) KC_CUDA(cudaMemcpyAsync(b->ownership, handle->d_own, n * HW * 4, cudaMemcpyDeviceToHost, st));
+    int bad = 0;
+    KC_CUDA(cudaMemcpyAsync(&bad, dBad, 4, cudaMemcpyDeviceToHost, st));
     KC_CUDA(cudaStreamSynchronize(st));
-    return kc::handleCheckAbort(handle);
+    if(kc::handleCheckAbort(handle)) return 1;
+    // the reference throws here ("Got nonfinite for policy sum" / "Got nonfinite for nneval value", nneval.cpp:745-750, 789-793): the
+    // batch fails -- its requests get the error, nothing of it enters the cache
+    KC_CHECK(!bad, "kc_evaluator: got nonfinite for policy sum or nneval value (NaN / infinite weights or inputs?)");
+    return 0;
   }
 };
 #else

@@ -38,6 +38,7 @@ void handleLeaveRegisters(kc_handle* h, bool on);   // bf16 pair-mode trunk: use
 // NNEvaluator::evaluate post-processing (nneval.cpp:702-815) of the handle's last outputs, on `stream`
 void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, const uint32_t* status_dev, const uint64_t* sitHash_dev,
                        float policyTemperature, float* policy_dev, float* winLoss_dev, float* misc_dev, uint64_t* nnHash_dev, cudaStream_t stream,
-                       int rowOffset = 0);   // rowOffset: first row of the handle's outputs to read
+                       int rowOffset = 0, int* nonfinite_dev = nullptr);   // rowOffset: first row of the handle's outputs to read;
+                       // nonfinite_dev: set to 1 if a row's policy sum or win / loss probabilities are not finite (nneval.cpp:745-750, 789-793)
 
 }  // namespace kc

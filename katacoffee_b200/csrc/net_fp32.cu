@@ -169,7 +169,7 @@ __global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__
 __global__ void k_postprocess(const float* __restrict__ policyLogits, const float* __restrict__ valueLogits, const float* __restrict__ miscLogits,
                               const uint32_t* __restrict__ legal, const uint32_t* __restrict__ status, const uint64_t* __restrict__ sitHash,
                               int n, int policySize, int LW, float invTemp, float* __restrict__ policy, float* __restrict__ winLoss,
-                              float* __restrict__ misc, uint64_t* __restrict__ nnHash) {
+                              float* __restrict__ misc, uint64_t* __restrict__ nnHash, int* __restrict__ nonfinite) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(row >= n) return;
   const float* p = policyLogits + (size_t)row * policySize;
@@ -202,6 +202,8 @@ __global__ void k_postprocess(const float* __restrict__ policyLogits, const floa
     double w = valueLogits[2 * (size_t)row], l = valueLogits[2 * (size_t)row + 1];
     double m = fmax(w, l), ew = exp(w - m), el = exp(l - m), ps = ew + el;
     double winProb = ew / ps, lossProb = el / ps;
+    // NNEvaluator::evaluate throws "Got nonfinite for policy sum" / "... nneval value" (nneval.cpp:745-750, 789-793): flag the batch
+    if(nonfinite && (!isfinite(sum) || !isfinite(winProb) || !isfinite(lossProb))) atomicOr(nonfinite, 1);
     auto softPlus = [](double x) { return x > 40.0 ? x : log(1.0 + exp(x)); };
     double vtl = softPlus((double)miscLogits[2 * (size_t)row]) * 40.0;
     double s = softPlus((double)miscLogits[2 * (size_t)row + 1] * 0.5);
@@ -378,10 +380,10 @@ float* handleInputGlobal(kc_handle* h) { return h->f32.global; }
 int handleCheckAbort(kc_handle* h) { return checkTrunkAbort(h); }
 void launchPostprocess(kc_handle* h, int n, int LW, const uint32_t* legal_dev, const uint32_t* status_dev, const uint64_t* sitHash_dev,
                        float policyTemperature, float* policy_dev, float* winLoss_dev, float* misc_dev, uint64_t* nnHash_dev, cudaStream_t stream,
-                       int rowOffset) {
+                       int rowOffset, int* nonfinite_dev) {
   const size_t ro = (size_t)rowOffset;
   k_postprocess<<<blocksFor((long long)n * 32), 256, 0, stream>>>(h->d_policy + ro * 4 * h->W * h->H, h->d_value + ro * 2, h->d_misc + ro * 2, legal_dev, status_dev, sitHash_dev, n,
-                                                                 4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev);
+                                                                 4 * h->W * h->H, LW, 1.0f / policyTemperature, policy_dev, winLoss_dev, misc_dev, nnHash_dev, nonfinite_dev);
 }
 void handleLeaveRegisters(kc_handle* h, bool on) { h->leaveRegisters = on; }
 int handleRunOnStream(kc_handle* h, int n, cudaStream_t stream, const int8_t* sym_dev, const int* nDev, int rowOffset, bool symIsLocal) {

@@ -138,3 +138,22 @@ def test_cpp_nnevaluator_class_on_the_device(ctx, tmp_path):
     r = subprocess.run([exe, path, "gpu"], capture_output=True, text=True, timeout=200)
     assert r.returncode == 0 and "test_b200nneval gpu: ok" in r.stdout, r.stdout + r.stderr
     print(r.stdout.strip())
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_nonfinite_outputs_fail_the_batch(ctx, oracle):
+    """NNEvaluator::evaluate throws 'Got nonfinite for policy sum / nneval value' (nneval.cpp:745-750, 789-793): a net whose value
+    head produces NaN makes the evaluation fail with an error instead of handing out (and caching) NaN probabilities."""
+    from katacoffee_b200 import backend, modeldesc
+    model = modeldesc.Model("b2c32", seed=4)
+    model._w(model.desc.v3Mul)[:] = np.nan          # the win / loss logits of every row become NaN
+    lm = backend.LoadedModel(ctx, model)
+    ev = backend.NNEvaluator(ctx, lm, nnXLen=W, nnYLen=H, winLen=K, maxBatchSize=16, maxConcurrentEvals=64, numThreads=1, nnCacheSizePowerOfTwo=10)
+    p = make_positions(oracle, 3, seed=5)[0]
+    with pytest.raises(RuntimeError, match="nonfinite"):
+        ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+    with pytest.raises(RuntimeError, match="nonfinite"):   # and nothing was cached
+        ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
+    assert ev.stats()["cacheHits"] == 0
+    ev.close(); lm.close()
