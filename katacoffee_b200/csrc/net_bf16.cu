@@ -95,6 +95,8 @@ using Cfg128 = TrunkCfg<128, 2, 7>;
 using Cfg128P = TrunkCfg<128, 2, 5, true, false, 9>;
 using Cfg128PR = TrunkCfg<128, 2, 5, true, true, 9>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
+using Cfg256 = TrunkCfg<256, 1, 4>;                    // trunks up to 256 channels (b20c256 / b40c256 shapes): one tile, T 256 + S 256 = all 512 TMEM columns,
+                                                        // single CTA (a pair's 9-tap stages of 256 output channels do not fit beside the 94 KB activation tile)
 using Cfg192P = TrunkCfg<192, 1, 4, true, false, 9>;   // b15c192 as CTA pairs: each CTA stages half of the 192 output channels (27 KB stages)
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
@@ -126,7 +128,7 @@ struct TrunkProgram {
   LayerDesc* d_layers = nullptr;
   size_t wBytes = 0;
   int v2C = 0;
-  int cfg = 0;     // 0: TrunkCfg<128, 2, 7>, 1: TrunkCfg<192, 1, 6>
+  int cfg = 0;     // 0: TrunkCfg<128, 2, 7>, 1: TrunkCfg<192, 1, 6>, 2: TrunkCfg<256, 1, 4>
   double flopsPerEval = 0;
 };
 
@@ -1118,10 +1120,10 @@ std::vector<float> cat(std::initializer_list<const std::vector<float>*> parts) {
 int buildTrunkProgram(kc_model* m) {
   auto unsupported = [&](const std::string& why) { m->trunk = nullptr; m->trunkUnsupportedWhy = why; return 0; };
   const int C = m->trunkC;
-  if(C % 16 != 0 || C > Cfg192::MAXC) return unsupported("trunk channels must be a multiple of 16 and <= 192 for the tcgen05 kernel");
-  // <= 128 channels: two activation tiles per CTA; up to 192 (b15c192): one tile per CTA (TMEM budget)
-  const int cfg = C <= Cfg128::MAXC ? 0 : 1;
-  const int maxC = cfg == 0 ? Cfg128::MAXC : Cfg192::MAXC, maxG = cfg == 0 ? Cfg128::MAXG : Cfg192::MAXG;
+  if(C % 16 != 0 || C > Cfg256::MAXC) return unsupported("trunk channels must be a multiple of 16 and <= 256 for the tcgen05 kernel");
+  // <= 128 channels: two activation tiles per CTA; up to 192 (b15c192) and up to 256 (b20c256): one tile per CTA (TMEM budget)
+  const int cfg = C <= Cfg128::MAXC ? 0 : C <= Cfg192::MAXC ? 1 : 2;
+  const int maxC = cfg == 0 ? Cfg128::MAXC : cfg == 1 ? Cfg192::MAXC : Cfg256::MAXC, maxG = cfg == 0 ? Cfg128::MAXG : cfg == 1 ? Cfg192::MAXG : Cfg256::MAXG;
   if(m->initialConv.ky != 3 || m->initialConv.kx != 3) return unsupported("initial conv must be 3x3");
   if(m->p1Conv.oc != HEADC || m->g1Conv.oc != HEADC || m->v1Conv.oc != HEADC) return unsupported("head convs must have 32 channels");
   if(m->p1Conv.ky != 1 || m->g1Conv.ky != 1 || m->v1Conv.ky != 1 || m->p2Conv.ky != 1 || m->vOwnershipConv.ky != 1)
@@ -1131,7 +1133,7 @@ int buildTrunkProgram(kc_model* m) {
     if(b.regularConv.ky != 3 || b.regularConv.kx != 3 || b.finalConv.ky != 3 || b.finalConv.kx != 3) return unsupported("block convs must be 3x3");
     if(b.kind == 0 && (b.regularConv.oc % 16 != 0 || b.regularConv.oc > maxC)) return unsupported("mid channels must be a multiple of 16 and within the trunk width class");
     if(b.kind == 2) {
-      if(b.gpoolConv.ky != 3 || b.gpoolConv.oc % 16 != 0 || b.gpoolConv.oc > maxG) return unsupported("gpool conv must be 3x3 with a multiple of 16 channels, <= 32 (trunk <= 128) or <= 64 (trunk <= 192)");
+      if(b.gpoolConv.ky != 3 || b.gpoolConv.oc % 16 != 0 || b.gpoolConv.oc > maxG) return unsupported("gpool conv must be 3x3 with a multiple of 16 channels, <= 32 (trunk <= 128), <= 64 (trunk <= 192) or <= 80 (trunk <= 256)");
       if(b.regularConv.oc % 16 != 0 || b.regularConv.oc + b.gpoolConv.oc > maxC) return unsupported("gpool block: regular + gpool channels must fit the trunk width class");
     }
   }
@@ -1269,6 +1271,7 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192P::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg256::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PR::SMEM));
   return 0;
@@ -1306,7 +1309,7 @@ void handleTileConstants(const kc_handle* h, float k, uint32_t* one, uint32_t* k
   *one = a; *kBits = b;
 }
 
-int handleTilesPerItem(const kc_handle* h) { return h->model->trunk && h->model->trunk->cfg != 0 ? Cfg192::NT : Cfg128::NT; }
+int handleTilesPerItem(const kc_handle* h) { return h->model->trunk && h->model->trunk->cfg != 0 ? Cfg192::NT : Cfg128::NT; }   // (Cfg256::NT == Cfg192::NT)
 
 static bool trunkUsesPairs() { static const bool usePair = [] { const char* e = getenv("KC_TRUNK_PAIR"); return !e || atoi(e) != 0; }(); return usePair; }
 // true if this handle's trunk kernel has a variant that leaves registers to co-resident kernels (pair mode, trunks up to 128 channels)
@@ -1349,7 +1352,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   bool timed = (int)h->evPool.size() >= h->evUsed + 2;
   if(timed) cudaEventRecord(h->evPool[h->evUsed], st);
   // CTA pairs (cta_group::2) are the default for trunks up to 128 channels; KC_TRUNK_PAIR=0 selects the single-CTA kernel
-  const bool usePair = trunkUsesPairs();
+  const bool usePair = trunkUsesPairs() && T->cfg != 2;   // the 256-channel configuration has no pair form
   // tile skew (see TrunkParams::skew): 5 of the 14 ring stages in pair mode, measured +1.5 % burst / +1 % under the power cap
   // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
   static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();
@@ -1372,7 +1375,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
     else KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
   }
   else if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
-  else trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);
+  else if(T->cfg == 1) trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);
+  else trunk_kernel<Cfg256><<<grid, Cfg256::THREADS, Cfg256::SMEM, st>>>(P);
   if(timed) { cudaEventRecord(h->evPool[h->evUsed + 1], st); h->evUsed += 2; }
   h->launches++;
   KC_CUDA(cudaGetLastError());

@@ -27,7 +27,10 @@ CONFIGS = {
     "b10c128": (128, 128, 96, 32, 10, (4, 7), 80),
     "b15c192": (192, 192, 128, 64, 15, (6, 11), 96),
     "b1c192g": (192, 192, 128, 64, 1, (0,), 96),   # shallow 192-wide net: pointwise check of the one-tile-per-CTA kernel
-    "b2c256": (256, 256, 192, 64, 2, (1,), 96),    # wider than the tensor-core kernel supports: must be rejected, not emulated
+    "b2c256": (256, 256, 192, 64, 2, (1,), 96),    # the 256-wide single-tile kernel (modelconfigs.py b20c256 / b40c256 shapes), shallow for pointwise checks
+    "b6c256": (256, 256, 192, 64, 6, (2, 4), 96),
+    "b20c256": (256, 256, 192, 64, 20, (6, 11, 16), 112),   # modelconfigs.py:249-288 b20c256 trunk (gpool blocks 7, 12, 17; v2 112) with this repo's 32-channel heads
+    "b1c320": (320, 320, 256, 64, 1, (), 96),      # wider than the tensor-core kernel supports: must be rejected, not emulated
 }
 HEAD_C = 32
 

@@ -323,7 +323,8 @@ def check_tensor_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, s
 
 @pytest.mark.parametrize("net,W,H,n,calibrate", [("b2c32", 5, 5, 37, "rms"), ("b6c96", 5, 5, 200, "rms"), ("b10c128", 5, 5, 300, "rms"),
                                                  ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none"),
-                                                 ("b15c192", 6, 6, 61, "rms"), ("b15c192", 5, 5, 45, "rms")])
+                                                 ("b15c192", 6, 6, 61, "rms"), ("b15c192", 5, 5, 45, "rms"),
+                                                 ("b2c256", 5, 5, 40, "rms"), ("b6c256", 6, 6, 37, "rms")])   # the 256-channel single-tile kernel
 @pytest.mark.parametrize("mode", ["fp32", "f16", "bf16"])
 def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
     """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward: the fp32 check path, the
@@ -658,7 +659,7 @@ def test_b15c192_6x6_device_resident_and_unsupported_width_rejected(ctx, oracle)
     ref = om.forward(planes, glob, W, H, mode=0, threads=8)
     assert max(np.abs(a - b).max() for a, b in zip(got, ref)) < TOL_TC   # the north-star bar on every raw output (fp16 operands)
     games.close(); h.close(); lm.close()
-    wide = modeldesc.Model("b2c256", seed=2)
+    wide = modeldesc.Model("b1c320", seed=2)
     lm2 = backend.LoadedModel(ctx, wide)
     with pytest.raises(capi.KCError, match="trunk channels"):
         backend.createComputeHandle(ctx, lm2, 8, 5, 5)
