@@ -219,12 +219,12 @@ def config_6x6_arm(steps, warmup):
     self-play / CPU / evaluator arms.  Returns the child's value / e2e / roofline / clocks.  Never fatal."""
     try:
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "6x6", "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline",
-                            "--no-selfplay", "--no-evaluator", "--no-extra-configs"], capture_output=True, text=True, timeout=600)
+                            "--no-selfplay-plain", "--selfplay-moves", "2", "--no-evaluator", "--no-extra-configs"], capture_output=True, text=True, timeout=900)
         if p.returncode != 0:
             return {"error": (p.stderr or p.stdout)[-300:]}
         d = json.loads(p.stdout.strip().splitlines()[-1])
         return {k: d[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "e2e", "getoutput_cpp", "clocks", "roofline",
-                                  "roofline_rules_features", "gpu_launches") if k in d}
+                                  "roofline_rules_features", "selfplay_graph", "gpu_launches") if k in d}
     except Exception as e:   # noqa: BLE001
         return {"error": repr(e)[:300]}
 
@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--games", type=int, default=0, help="games per GPU (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-selfplay-plain", action="store_true", help="only the selfplay1.cfg self-play arm, not the SearchParams() defaults one")
     ap.add_argument("--no-evaluator", action="store_true", help="skip the evaluator front-end arm (native client threads in a child process)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the batch1024 (BASELINE configs[2]) and config_6x6 (configs[4]) objects")
     ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
@@ -437,8 +438,9 @@ def main():
                                       rootDesiredPerChildVisitsCoeff=2.0, valueWeightExponent=0.5,
                                       chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, nnRandomize=1,
                                       rootNumSymmetriesToSample=4, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1)
-        selfplay = selfplay_arm("lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
-                                reuseTree=True)
+        if not args.no_selfplay_plain:
+            selfplay = selfplay_arm("lock-step PUCT per game (SearchParams() defaults, valueWeightExponent 0), tree re-use, visit-proportional move choice",
+                                    reuseTree=True)
 
     if rank == 0:
         flops = modeldesc.flops_per_eval(NET, hw)
