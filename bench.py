@@ -286,6 +286,8 @@ def main():
     ap.add_argument("--no-evaluator", action="store_true", help="skip the evaluator front-end arm (native client threads in a child process)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the batch1024 (BASELINE configs[2]) and config_6x6 (configs[4]) objects")
     ap.add_argument("--visits", type=int, default=800, help="visits per move of the self-play arm (BASELINE config 4)")
+    ap.add_argument("--nn-cache", type=int, default=24, help="nnCacheSizePowerOfTwo of the self-play arms (selfplay1.cfg:121 has 21 for its 128 games; "
+                                                              "here 18,944 games share one cache; 0 = no NN cache)")
     ap.add_argument("--selfplay-moves", type=int, default=8, help="consecutive moves per game lane timed in the self-play arm")
     args = ap.parse_args()
     select_config(args.config)
@@ -401,7 +403,8 @@ def main():
             barrier()
             tot, rep = backend.selfplayRun(model, [local], G, W, H, WINLEN, moves=args.selfplay_moves, movesPerChunk=chunk, warmupMoves=1,
                                            staggerPlies=SELFPLAY_STAGGER, maxRowsPerChunk=G * 3 * chunk, outputDir=out_dir, seed=SEED,
-                                           firstGameId=shard.first_game_id(rank), maxVisits=args.visits, autoRefill=1, temperaturePlies=30, **search_kw)
+                                           firstGameId=shard.first_game_id(rank), maxVisits=args.visits, autoRefill=1, temperaturePlies=30,
+                                           nnCacheSizePowerOfTwo=args.nn_cache, **search_kw)
             barrier()
             files = len(os.listdir(out_dir))
         finally:
@@ -409,7 +412,7 @@ def main():
         sec = shard.max_over_ranks(rep.wallSeconds, "cuda")
         dev_ms = shard.max_over_ranks(rep.deviceMsMax, "cuda")
         sp = shard.reduce_stats([tot.movesPlayed, tot.visits, tot.netEvals, tot.terminalVisits, tot.gamesFinished, tot.batchRows, tot.transpositionHits,
-                                 tot.catchUpVisits, rep.rowsWritten, rep.rowsDropped, rep.bytesWritten, rep.kernelLaunches, files], "cuda")
+                                 tot.catchUpVisits, rep.rowsWritten, rep.rowsDropped, rep.bytesWritten, rep.kernelLaunches, files, tot.nnCacheHits], "cuda")
         return {"metric": "selfplay_moves_per_s", "value": sp[0] / sec, "unit": "moves/s", "visits_per_move": args.visits,
                 "games_per_gpu": G, "moves_timed_per_game": args.selfplay_moves,
                 "timed_region": "host clock around kc_selfplay_run's move loop: search, move choice, refill of finished games, k_emit_rows, row read-back "
@@ -419,6 +422,8 @@ def main():
                 "batch_rows_per_s": sp[5] / sec, "net_eval_fraction_of_visits": sp[2] / max(sp[1], 1),
                 "transposition_fraction_of_visits": (sp[6] + sp[7]) / max(sp[1], 1),
                 "ms_per_move_batch": sec * 1e3 / args.selfplay_moves, "games_finished": int(sp[4]),
+                "nn_cache": f"2^{args.nn_cache} entries shared by the games of the GPU (nnCacheSizePowerOfTwo, selfplay1.cfg:121: 21 for 128 games); a hit is bit-identical to the evaluation" if args.nn_cache else "off",
+                "nn_cache_hits_per_s": sp[13] / sec,
                 "training_rows_written": int(sp[8]), "training_rows_dropped": int(sp[9]), "npz_files": int(sp[12]), "npz_bytes": int(sp[10]),
                 "search": label, "kernel_launches": int(sp[11])}
 

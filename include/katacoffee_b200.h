@@ -357,6 +357,10 @@ typedef struct {
   int32_t pad4_;
   double uncertaintyCoeff, uncertaintyExponent, uncertaintyMaxWeight;   /* 0.25 / 1.0 / 8.0 in the GTP defaults (setup.cpp:545-560) */
   double noisePruneUtilityScale, noisePruningCap;                        /* 0.15 / 1e50 (searchparams.cpp:27-28) */
+  int32_t nnCacheSizePowerOfTwo;   /* NNCacheTable for the device search (nneval.cpp:874-932; selfplay1.cfg:121 uses 21): 2^n direct-mapped entries of
+                                      post-processed outputs shared by all games of the search, keyed by the whole identity of the net's inputs, so
+                                      a hit returns bit for bit what the evaluation would have returned -- fewer rows, same search.  0 = off. */
+  int32_t pad5_;
 } kc_search_params;
 /* With any of chosenMoveTemperature[Early] or useLcbForSelection set in graph mode the move is chosen from the full
  * Search::getPlaySelectionValues (child weights; children other than the most stably explored one cut down to the weight its final
@@ -367,6 +371,7 @@ typedef struct {
   uint64_t batchRows;           /* rows sent through the evaluator */
   uint64_t transpositionHits;   /* graph search: new edges that found their position already in the graph (no evaluation) */
   uint64_t catchUpVisits;       /* graph search: visits absorbed by an edge lagging behind its node (maybeCatchUpEdgeVisits) */
+  uint64_t nnCacheHits;         /* leaves whose evaluation came from the search's NN cache (nnCacheSizePowerOfTwo > 0); not counted in netEvals */
 } kc_search_stats;
 /* handle == NULL selects the deterministic integer-hash evaluator (exact fp32 policy/value derived from the sit-hash),
  * which exists so that the search logic can be compared bit for bit with the CPU oracle; with a handle the leaves go

@@ -70,12 +70,13 @@ class SearchParams(C.Structure):
                 ("useLcbForSelection", C.c_int32), ("useNonBuggyLcb", C.c_int32), ("lcbStdevs", C.c_double), ("minVisitPropForLCB", C.c_double),
                 ("rootNumSymmetriesToSample", C.c_int32), ("useNoisePruning", C.c_int32), ("useUncertainty", C.c_int32), ("pad4_", C.c_int32),
                 ("uncertaintyCoeff", C.c_double), ("uncertaintyExponent", C.c_double), ("uncertaintyMaxWeight", C.c_double),
-                ("noisePruneUtilityScale", C.c_double), ("noisePruningCap", C.c_double)]
+                ("noisePruneUtilityScale", C.c_double), ("noisePruningCap", C.c_double),
+                ("nnCacheSizePowerOfTwo", C.c_int32), ("pad5_", C.c_int32)]
 
 
 class SearchStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("visits", "netEvals", "terminalVisits", "movesPlayed", "gamesFinished", "blackWins",
-                                          "whiteWins", "draws", "batchRows", "transpositionHits", "catchUpVisits")]
+                                          "whiteWins", "draws", "batchRows", "transpositionHits", "catchUpVisits", "nnCacheHits")]
 
 
 class SelfplayConfig(C.Structure):

@@ -68,6 +68,7 @@ struct SearchCfg {
   // the rest of selfplay1.cfg / the GTP defaults: LCB move selection, root symmetry averaging, uncertainty weighting
   int useLcb, nonBuggyLcb, rootSyms, noisePruning, useUncertainty;
   double lcbStdevs, minVisitPropLcb, uncCoeff, uncExp, uncMaxWeight, noisePruneScale, noisePruneCap;
+  int iterStamp;           // NN cache: number of the current iteration (entries hit in it are pinned against replacement until it is over)
   int fullPlaySelection;   // the move choice runs Search::getPlaySelectionValues (child weights, reduced weights, LCB) instead of plain edge visits
   uint64_t seed;
 };
@@ -99,6 +100,17 @@ struct TreeMem {
   // graph mode with tree re-use: re-rooting rebuilds the tables into a second set, then the two swap (like nodes / nodesAlt)
   uint64_t* tblKeysAlt; int* tblValsAlt; uint64_t* biasKeysAlt; double* biasValsAlt;
   int* remap;             // [G][maxNodes] old node index -> new index (-1: dropped)
+  // NN cache shared by all games of the search (NNCacheTable, cpp/neuralnet/nneval.cpp:874-932; selfplay1.cfg:121 nnCacheSizePowerOfTwo = 21):
+  // direct-mapped on the low bits of the key, entries hold the post-processed outputs.  The key is the whole identity of the net's inputs
+  // (sit-hash of the player to move, the last five moves with their players, the last direction, min(numTurns, 5)), so a hit returns
+  // bit for bit what the evaluation would have returned and the search result does not depend on the cache.
+  uint64_t* cacheKeys;    // [N][2] (0, 0 = empty)
+  int* cacheState;        // [N][2]: lock (1 while an entry is being written), iteration stamp of the last hit
+  float* cachePolicy;     // [N][P]
+  float* cacheScalars;    // [N][4] whiteWin, whiteLoss, varTimeLeft, shorttermWinlossError
+  unsigned cacheMask;     // N - 1; 0 = no cache
+  int* leafCache;         // [G] entry the leaf's evaluation comes from (hit), -1: evaluated in the batch (then inserted)
+  uint64_t* leafCKey;     // [G][2] cache key of a leaf that missed
   const double* tcdf;     // [2000] Student-t (3 degrees of freedom) cdf on [-50, 50] for valueWeightExponent
   const double* stdevTab; // [1025] sqrt(1e-8 + 1 / (1.5 sqrt(w))) for integer child weights w (the common case): same bits as computing it
 };
@@ -173,6 +185,49 @@ __device__ __forceinline__ void applyMoveLight(const D& dm, GameRegs<typename D:
 __device__ __forceinline__ double warpSumD(double v) {   // butterfly: every lane ends with the same, order-defined sum
   for(int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// NN cache key of a position: everything the planes and the legal mask read (see TreeMem::cacheKeys)
+__device__ __forceinline__ void nnCacheKey(const Geom& g, uint64_t h0, uint64_t h1, uint64_t misc, uint64_t& k0, uint64_t& k1) {
+  const int np = (flagsOf(misc) >> 3) & 3;
+  const uint64_t hist = (misc & 0xffffffffffffULL) | ((uint64_t)min(numTurnsOf(misc), 5) << 48);   // five moves, last direction, capped turn count
+  const uint64_t m0 = splitmix64(hist ^ 0x6b4c1e2d9a5f3c71ULL), m1 = splitmix64(m0 ^ hist);
+  k0 = h0 ^ g.playerHash[np][0] ^ m0; k1 = h1 ^ g.playerHash[np][1] ^ m1;
+  if((k0 | k1) == 0) k0 = 1;   // (0, 0) marks an empty entry
+}
+// lane 0 of the selecting warp: true (and *entry) if the leaf's evaluation is in the cache; the entry is pinned for this iteration
+__device__ __forceinline__ bool nnCacheLookup(const SearchCfg& c, const TreeMem& t, int gi, uint64_t k0, uint64_t k1) {
+  const unsigned idx = (unsigned)k0 & t.cacheMask;
+  if(t.cacheKeys[2 * (size_t)idx] == k0 && t.cacheKeys[2 * (size_t)idx + 1] == k1) {
+    t.cacheState[2 * (size_t)idx + 1] = c.iterStamp;   // racing writers store the same value
+    t.leafCache[gi] = (int)idx;
+    return true;
+  }
+  t.leafCache[gi] = -1;
+  t.leafCKey[2 * (size_t)gi] = k0; t.leafCKey[2 * (size_t)gi + 1] = k1;
+  return false;
+}
+// whole warp, after an evaluation that missed: store it unless the slot was hit in this iteration or another warp is writing it
+__device__ __forceinline__ void nnCacheInsert(const SearchCfg& c, const TreeMem& t, int gi, int lane, const float* __restrict__ pol, const float* __restrict__ wl,
+                                              const float* __restrict__ misc) {
+  const uint64_t k0 = t.leafCKey[2 * (size_t)gi], k1 = t.leafCKey[2 * (size_t)gi + 1];
+  const unsigned idx = (unsigned)k0 & t.cacheMask;
+  int ok = 0;
+  if(lane == 0) ok = t.cacheState[2 * (size_t)idx + 1] != c.iterStamp && atomicCAS(&t.cacheState[2 * (size_t)idx], 0, 1) == 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if(!ok) return;
+  if(lane == 0) { t.cacheKeys[2 * (size_t)idx] = 0; t.cacheKeys[2 * (size_t)idx + 1] = 0; }   // no reader runs beside this kernel; kept tidy anyway
+  for(int pos = lane; pos < c.P; pos += 32) t.cachePolicy[(size_t)idx * c.P + pos] = pol[pos];
+  if(lane == 0) {
+    float* sc = t.cacheScalars + (size_t)idx * 4;
+    sc[0] = wl[0]; sc[1] = wl[1]; sc[2] = misc ? misc[0] : 0.f; sc[3] = misc ? misc[1] : 0.f;
+  }
+  __syncwarp();
+  if(lane == 0) {
+    t.cacheKeys[2 * (size_t)idx] = k0; t.cacheKeys[2 * (size_t)idx + 1] = k1;
+    __threadfence();
+    atomicExch(&t.cacheState[2 * (size_t)idx], 0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,7 +320,15 @@ __global__ void __launch_bounds__(128, 10) k_select(const Geom g, const SearchCf
     if(kind != 0) t.active[c.half] = 1;
     t.leafKind[gi] = kind; t.pathLen[gi] = depth; t.leafValue[gi] = leafVal;
     t.leafNextPla[gi] = (flagsOf(s.misc) >> 3) & 3;
-    const bool needsNet = kind == 1 || kind == 4;
+    bool needsNet = kind == 1 || kind == 4;
+    if(t.cacheMask) {
+      t.leafCache[gi] = -2;
+      if(needsNet) {
+        uint64_t ck0, ck1;
+        nnCacheKey(g, s.h0, s.h1, s.misc, ck0, ck1);
+        if(nnCacheLookup(c, t, gi, ck0, ck1) && c.compact) needsNet = false;   // the evaluation is already there: no row
+      }
+    }
     // the position handed to the evaluator.  Compact mode: only leaves that need the net take a row, in arrival order
     // (an evaluation does not depend on its row); otherwise row = game and idle rows are evaluated and ignored.
     if(needsNet || !c.compact) {
@@ -400,19 +463,25 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
   const int gi = c.gOff + li;
   const int kind = t.leafKind[gi];
   if(kind == 0) return;
+  bool cached = false;
   uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
   const int depth = t.pathLen[gi];
   double v = t.leafValue[gi];
   int newIdx = -1;
   if(kind == 1 || kind == 4) {
     const size_t row = (size_t)t.leafSlot[gi];
-    v = __dsub_rn((double)winLoss[2 * row], (double)winLoss[2 * row + 1]);   // white-positive utility of the evaluation
+    const int ce = t.cacheMask ? t.leafCache[gi] : -2;                     // >= 0: the evaluation comes from the NN cache
+    const float* polSrc = ce >= 0 ? t.cachePolicy + (size_t)ce * c.P : policy + row * c.P;
+    const float* wlSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 : winLoss + 2 * row;
+    cached = ce >= 0;
+    v = __dsub_rn((double)wlSrc[0], (double)wlSrc[1]);   // white-positive utility of the evaluation
     newIdx = t.nodeCount[gi];
     if(newIdx >= c.maxNodes) return;   // cannot happen: one new node per visit, maxNodes == maxVisits
     NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P, c.polOff};
     for(int pos = lane; pos < c.P; pos += 32) {
-      nd.edgeW()[pos] = 0.0; nd.policy()[pos] = policy[row * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
+      nd.edgeW()[pos] = 0.0; nd.policy()[pos] = polSrc[pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
     }
+    if(ce == -1) nnCacheInsert(c, t, gi, lane, polSrc, wlSrc, nullptr);
     if(lane == 0) { nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi]; nd.W() = v; t.nodeCount[gi] = newIdx + 1; }
   }
   if(lane != 0) return;
@@ -430,7 +499,7 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
     nd.edgeW()[pos] = __dadd_rn(nd.edgeW()[pos], v);
   }
   atomicAdd(&t.stats[0], 1ULL);
-  if(kind == 1 || kind == 4) atomicAdd(&t.stats[1], 1ULL); else atomicAdd(&t.stats[2], 1ULL);
+  if(kind == 1 || kind == 4) atomicAdd(&t.stats[cached ? 10 : 1], 1ULL); else atomicAdd(&t.stats[2], 1ULL);
 }
 
 // =============================================================================================
@@ -688,7 +757,15 @@ __global__ void __launch_bounds__(128, 8) k_select_graph(const Geom g, const Sea
     t.leafKey[2 * (size_t)gi] = key0; t.leafKey[2 * (size_t)gi + 1] = key1;
     t.leafBiasKey[2 * (size_t)gi] = bk0; t.leafBiasKey[2 * (size_t)gi + 1] = bk1;
     t.leafTarget[gi] = target;
-    const bool needsNet = kind == 1 || kind == 4;
+    bool needsNet = kind == 1 || kind == 4;
+    if(t.cacheMask) {
+      t.leafCache[gi] = -2;
+      if(needsNet) {
+        uint64_t ck0, ck1;
+        nnCacheKey(g, s.h0, s.h1, s.misc, ck0, ck1);
+        if(nnCacheLookup(c, t, gi, ck0, ck1) && c.compact) needsNet = false;   // the evaluation is already there: no row
+      }
+    }
     if(needsNet || !c.compact) {
       const int slot = c.compact ? atomicAdd(t.evalCount + c.half, 1) : li;
       t.leafSlot[gi] = slot;
@@ -907,19 +984,28 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
   const int gi = c.gOff + li;
   const int kind = t.leafKind[gi];
   if(kind == 0) return;
+  bool cached = false;
+  float shortErr = 0.0f;
   uint8_t* treeBase = t.nodes + (size_t)gi * c.maxNodes * c.nodeStride;
   const int depth = t.pathLen[gi];
   double v = t.leafValue[gi];
   int newIdx = -1;
   if(kind == 1 || kind == 4) {
     const size_t row = (size_t)t.leafSlot[gi];
-    v = __dsub_rn((double)winLoss[2 * row], (double)winLoss[2 * row + 1]);
+    const int ce = t.cacheMask ? t.leafCache[gi] : -2;                     // >= 0: the evaluation comes from the NN cache
+    const float* polSrc = ce >= 0 ? t.cachePolicy + (size_t)ce * c.P : policy + row * c.P;
+    const float* wlSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 : winLoss + 2 * row;
+    const float* miscSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 + 2 : (misc ? misc + 2 * row : nullptr);
+    cached = ce >= 0;
+    shortErr = miscSrc ? miscSrc[1] : 0.0f;
+    v = __dsub_rn((double)wlSrc[0], (double)wlSrc[1]);
     newIdx = t.nodeCount[gi];
     if(newIdx >= c.maxNodes) return;   // cannot happen: at most one new node per visit
     NodeRef nd{treeBase + (size_t)newIdx * c.nodeStride, c.P, c.polOff};
     for(int pos = lane; pos < c.P; pos += 32) {
-      nd.policy()[pos] = policy[row * c.P + pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
+      nd.policy()[pos] = polSrc[pos]; nd.child()[pos] = -1; nd.edgeN()[pos] = 0; nd.order()[pos] = 0;
     }
+    if(ce == -1) nnCacheInsert(c, t, gi, lane, polSrc, wlSrc, miscSrc);
     if(lane == 0) {
       int be = -1;
       double utility = v;
@@ -936,7 +1022,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
         const double* E = t.biasVals + ((size_t)gi * c.tableCap + be) * 2;
         if(E[1] > 0.001) utility = __dadd_rn(utility, __ddiv_rn(__dmul_rn(c.biasFactor, E[0]), E[1]));   // addLeafValue :27-37
       }
-      const double w0 = nnWeightOf(c, misc ? misc[2 * row + 1] : 0.0f);
+      const double w0 = nnWeightOf(c, shortErr);
       nd.N() = 1; nd.numChildren() = 0; nd.nextPla() = t.leafNextPla[gi] & 0xff; nd.biasEntry() = be;
       nd.weightSum() = w0; nd.utilityAvg() = utility; nd.nnUtility() = v; nd.lastDelta() = 0.0; nd.lastWeight() = 0.0;
       nd.utilitySqAvg() = __dmul_rn(utility, utility); nd.weightSqSum() = __dmul_rn(w0, w0); nd.nnWeight() = w0;
@@ -971,7 +1057,7 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
   }
   if(lane != 0) return;
   atomicAdd(&t.stats[0], 1ULL);
-  if(kind == 1 || kind == 4) atomicAdd(&t.stats[1], 1ULL);
+  if(kind == 1 || kind == 4) atomicAdd(&t.stats[cached ? 10 : 1], 1ULL);
   else if(kind == 2 || kind == 3) atomicAdd(&t.stats[2], 1ULL);
   else if(kind == 6) atomicAdd(&t.stats[8], 1ULL);
   else atomicAdd(&t.stats[9], 1ULL);
@@ -1618,6 +1704,7 @@ struct kc_search {
   kc::SearchCfg cfg;
   kc::TreeMem tree;
   float* d_policy = nullptr; float* d_winLoss = nullptr; float* d_misc = nullptr; uint64_t* d_nnHash = nullptr;
+  int iterCounter = 0;            // NN cache: stamps of the iterations run so far
   int16_t* d_chosen = nullptr;
   double* d_psv = nullptr;                                   // [G][P] play-selection values of the last move choice
   float* d_rootAccPolicy = nullptr; float* d_rootAccScalars = nullptr;   // rootNumSymmetriesToSample: [G][P] and [G][4] running sums
@@ -1709,7 +1796,9 @@ int runVisits(kc_search* S) {
       if(!active[0] && !active[1]) break;
       for(int h = 0; h < nh; h++) KC_CUDA(cudaMemsetAsync(S->tree.active + h, 0, 4, H[h].st));
     }
+    S->iterCounter++;
     for(int h = 0; h < nh; h++) {
+      H[h].c.iterStamp = S->iterCounter;
       const SearchCfg& ch = H[h].c;
       kc_games* Lf = H[h].leaf;
       cudaStream_t hs = H[h].st;
@@ -1772,6 +1861,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   KC_CHECK(p->rootNumSymmetriesToSample >= 0 && p->rootNumSymmetriesToSample <= 8, "kc_search_create: rootNumSymmetriesToSample must be within 0..8");
   KC_CHECK(!p->useUncertainty || (p->uncertaintyCoeff > 0.0 && p->uncertaintyExponent >= 0.0 && p->uncertaintyMaxWeight >= 1.0),
            "kc_search_create: useUncertainty needs uncertaintyCoeff > 0, uncertaintyExponent >= 0 and uncertaintyMaxWeight >= 1");
+  KC_CHECK(p->nnCacheSizePowerOfTwo >= 0 && p->nnCacheSizePowerOfTwo <= 26, "kc_search_create: nnCacheSizePowerOfTwo must be within 0..26");
   KC_CHECK(!p->useNoisePruning || (p->noisePruneUtilityScale > 0.0 && p->noisePruningCap >= 0.0), "kc_search_create: useNoisePruning needs noisePruneUtilityScale > 0 and noisePruningCap >= 0");
   KC_CHECK(xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN,
            "kc_search_create: the device search runs on boards up to 7x7 (its rules and node layout are the 64-bit ones); kc_games_* take up to 10x10");
@@ -1865,6 +1955,15 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
   }
   KC_CUDA(cudaMalloc(&S->d_policy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_winLoss, n * 8));
   KC_CUDA(cudaMalloc(&S->d_misc, n * 8)); KC_CUDA(cudaMalloc(&S->d_nnHash, n * 16));
+  if(p->nnCacheSizePowerOfTwo > 0) {
+    const size_t N = (size_t)1 << p->nnCacheSizePowerOfTwo;
+    c.iterStamp = 0;
+    S->tree.cacheMask = (unsigned)(N - 1);
+    KC_CUDA(cudaMalloc(&S->tree.cacheKeys, N * 16)); KC_CUDA(cudaMemset(S->tree.cacheKeys, 0, N * 16));
+    KC_CUDA(cudaMalloc(&S->tree.cacheState, N * 8)); KC_CUDA(cudaMemset(S->tree.cacheState, 0, N * 8));
+    KC_CUDA(cudaMalloc(&S->tree.cachePolicy, N * c.P * 4)); KC_CUDA(cudaMalloc(&S->tree.cacheScalars, N * 16));
+    KC_CUDA(cudaMalloc(&S->tree.leafCache, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafCKey, n * 16));
+  }
   KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
   KC_CUDA(cudaMalloc(&S->d_psv, n * c.P * 8)); KC_CUDA(cudaMemset(S->d_psv, 0, n * c.P * 8));
   if(c.rootSyms > 1) { KC_CUDA(cudaMalloc(&S->d_rootAccPolicy, n * c.P * 4)); KC_CUDA(cudaMalloc(&S->d_rootAccScalars, n * 16)); }
@@ -1879,7 +1978,7 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     static const bool allow = [] { const char* e = getenv("KC_SEARCH_PIPELINE"); return e && atoi(e) != 0; }();
     const int item = 2 * kc::boardsPerTile(xSize, ySize);                 // boards per CTA work item
     const int half = ((numGames + 1) / 2 + item - 1) / item * item;
-    if((p->noPipeline == 2 || (allow && p->noPipeline == 0)) && c.compact && kc::handleCanLeaveRegisters(handleOrNull) && half >= item * ctx->smCount && numGames - half > 0) {
+    if((p->noPipeline == 2 || (allow && p->noPipeline == 0)) && p->nnCacheSizePowerOfTwo <= 0 && c.compact && kc::handleCanLeaveRegisters(handleOrNull) && half >= item * ctx->smCount && numGames - half > 0) {
       S->pipelined = true;
       kc::handleLeaveRegisters(handleOrNull, true);
       S->halfOff[0] = 0; S->halfCnt[0] = half; S->halfOff[1] = half; S->halfCnt[1] = numGames - half;
@@ -1908,6 +2007,7 @@ int kc_search_destroy(kc_search* S) {
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
   cudaFree(S->d_psv); cudaFree(S->d_rootAccPolicy); cudaFree(S->d_rootAccScalars);
+  cudaFree(S->tree.cacheKeys); cudaFree(S->tree.cacheState); cudaFree(S->tree.cachePolicy); cudaFree(S->tree.cacheScalars); cudaFree(S->tree.leafCache); cudaFree(S->tree.leafCKey);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
   for(int h = 0; h < 2; h++) { if(S->leafHalf[h]) { cudaStreamSynchronize(S->leafHalf[h]->stream); kc_games_destroy(S->leafHalf[h]); } if(S->evJoin[h]) cudaEventDestroy(S->evJoin[h]); }
   if(S->evFork) cudaEventDestroy(S->evFork);
@@ -1926,6 +2026,10 @@ int kc_search_reset(kc_search* S, uint64_t seed, uint64_t firstGameId) {
   KC_CUDA(cudaMemset(S->tree.nodeCount, 0, (size_t)S->cfg.numGames * 4));
   KC_CUDA(cudaMemset(S->tree.stats, 0, NUM_STATS * 8));
   if(clearTables(S, S->leaf->stream)) return 1;
+  if(S->tree.cacheMask) {   // evaluations depend on the seed through nnRandomize's symmetry: a new run starts with an empty NN cache
+    KC_CUDA(cudaMemsetAsync(S->tree.cacheKeys, 0, ((size_t)S->tree.cacheMask + 1) * 16, S->leaf->stream));
+    KC_CUDA(cudaMemsetAsync(S->tree.cacheState, 0, ((size_t)S->tree.cacheMask + 1) * 8, S->leaf->stream));
+  }
   KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
   return 0;
 }
@@ -2030,7 +2134,7 @@ int kc_search_play(kc_search* S, int moves, int16_t* chosenLast, kc_search_stats
     acc->visits += hs[0]; acc->netEvals += hs[1]; acc->terminalVisits += hs[2]; acc->movesPlayed += hs[3];
     acc->gamesFinished += hs[4]; acc->blackWins += hs[5]; acc->whiteWins += hs[6]; acc->draws += hs[7];
     acc->batchRows += c.compact ? hs[1] : (uint64_t)c.numGames * c.maxVisits * moves;
-    acc->transpositionHits += hs[8]; acc->catchUpVisits += hs[9];
+    acc->transpositionHits += hs[8]; acc->catchUpVisits += hs[9]; acc->nnCacheHits += hs[10];
   }
   return 0;
 }

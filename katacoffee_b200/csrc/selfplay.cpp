@@ -25,7 +25,7 @@
 namespace {
 
 constexpr uint64_t GAME_ID_STRIDE = 1ULL << 40;   // ids of pool i live in [first + i * 2^40, ...): never collide, refills included
-constexpr int NUM_COUNTERS = 11;                  // kc_search_stats as uint64[11]
+constexpr int NUM_COUNTERS = 12;                  // kc_search_stats as uint64[12]
 
 struct RowBuffers {
   std::vector<uint8_t> bin; std::vector<float> glob; std::vector<int16_t> policy; std::vector<float> targets; std::vector<int8_t> value;

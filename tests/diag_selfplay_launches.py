@@ -12,11 +12,13 @@ kw = dict(useGraphSearch=1, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightE
           chosenMoveTemperatureHalflife=19.0, fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=2.0, rootDesiredPerChildVisitsCoeff=2.0,
           valueWeightExponent=0.5, chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, nnRandomize=1,
           rootNumSymmetriesToSample=4, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1)
+if os.environ.get("KC_DIAG_NNCACHE"):
+    kw["nnCacheSizePowerOfTwo"] = int(os.environ["KC_DIAG_NNCACHE"])
 if os.environ.get("KC_DIAG_PLAIN"):
     kw = dict(reuseTree=1)
 t0 = time.time()
 tot, rep = backend.selfplayRun(model, [0], G, 5, 5, 4, moves=moves, movesPerChunk=moves, warmupMoves=int(os.environ.get("KC_DIAG_WARMUP", 0)), staggerPlies=20,
                                maxRowsPerChunk=0, seed=1, maxVisits=visits, autoRefill=1, temperaturePlies=30, **kw)
 print(json.dumps({"moves": tot.movesPlayed, "visits": tot.visits, "netEvals": tot.netEvals, "batchRows": tot.batchRows, "wall_s": rep.wallSeconds,
-                  "device_s": rep.deviceMsMax * 1e-3, "launches": rep.kernelLaunches, "rows_per_s": tot.batchRows / rep.wallSeconds,
+                  "device_s": rep.deviceMsMax * 1e-3, "launches": rep.kernelLaunches, "nnCacheHits": tot.nnCacheHits, "rows_per_s": tot.batchRows / rep.wallSeconds,
                   "moves_per_s": tot.movesPlayed / rep.wallSeconds, "total_s": time.time() - t0}))

@@ -15,7 +15,8 @@ kw = dict(useGraphSearch=1, subtreeValueBiasFactor=0.30, subtreeValueBiasWeightE
           rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83, rootDirichletNoiseWeight=0.25, rootPolicyTemperature=1.1, rootPolicyTemperatureEarly=1.25,
           chosenMoveTemperatureHalflife=19.0, fpuParentWeightByVisitedPolicy=1, fpuParentWeightByVisitedPolicyPow=2.0, rootDesiredPerChildVisitsCoeff=2.0,
           valueWeightExponent=0.5, chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, nnRandomize=1,
-          rootNumSymmetriesToSample=4, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1)
+          rootNumSymmetriesToSample=4, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15, useNonBuggyLcb=1,
+          nnCacheSizePowerOfTwo=int(os.environ.get("KC_DIAG_NNCACHE", 21)))
 for devs in ([0], list(range(n.value))):
     out = tempfile.mkdtemp(prefix="kc_sp_")
     try:

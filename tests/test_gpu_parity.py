@@ -1461,3 +1461,59 @@ def test_masked_boards_on_the_tensor_path(ctx, oracle, net, nnX, nnY, boards):
         assert np.abs(exact[0][full] - got[0][full]).max() < 1e-6 and np.abs(exact[1][full] - got[1][full]).max() < 1e-6
     for o in (h, hc, he, lm):
         o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("net", [None, "fp32", "f16"])
+def test_search_nn_cache_changes_nothing_but_the_row_count(ctx, net):
+    """nnCacheSizePowerOfTwo (NNCacheTable for the device search; selfplay1.cfg:121): the cache is keyed by the whole identity of the
+    net's inputs and an evaluation does not depend on its batch row, so a hit returns the bits the evaluation would have returned:
+    moves, root statistics, graphs and visit counters are identical with and without it -- only fewer rows go through the net
+    (evaluations + cache hits = the evaluations of the run without a cache).  Games that start from the same position share heavily."""
+    from katacoffee_b200 import backend, modeldesc, capi
+    W = H = 5
+    G, V = 192, 48
+    h = lm = None
+    if net is not None:
+        lm = backend.LoadedModel(ctx, modeldesc.Model("b2c32", seed=12))
+        h = backend.createComputeHandle(ctx, lm, G, W, H, useFP32Check=(net == "fp32"))
+    kw = dict(useGraphSearch=True, subtreeValueBiasFactor=0.3, subtreeValueBiasWeightExponent=0.8, rootNoiseEnabled=1, rootDirichletNoiseTotalConcentration=10.83,
+              rootDirichletNoiseWeight=0.25, valueWeightExponent=0.5, nnRandomize=1 if net else 0, rootNumSymmetriesToSample=2,
+              chosenMoveTemperatureEarly=0.75, chosenMoveTemperature=0.15, chosenMovePrune=1.0, useLcbForSelection=1, lcbStdevs=5.0, minVisitPropForLCB=0.15,
+              useNonBuggyLcb=1)
+    res = []
+    for cache in (0, 12, 3):      # off, roomy, tiny (8 entries: constant replacement)
+        for graph in (True, False):
+            opts = kw if graph else {}
+            s = backend.Search(ctx, h, G, W, H, 4, maxVisits=V, temperaturePlies=8, reuseTree=True, nnCacheSizePowerOfTwo=cache, **opts)
+            s.reset(seed=31)
+            lane = np.arange(G)
+            for t in range(4):
+                s.games.step(np.where(lane % 4 > t, -2, -1).astype(np.int16))     # a quarter of the games each at plies 0..3
+            st = capi.SearchStats()
+            moves = []
+            for _ in range(3):
+                _, chosen, _ = s.play(1, st)
+                moves.append(chosen.copy())
+            s.runVisits()
+            root = s.readRoot()
+            dig = s.treeDigest() if graph else None
+            res.append((cache, graph, np.stack(moves), root, dig, st))
+            s.close()
+    base = {g: r for (cch, g, *r) in res if cch == 0}
+    for cch, graph, moves, root, dig, st in res:
+        if cch == 0:
+            continue
+        bm, br, bd, bs = base[graph]
+        assert (moves == bm).all(), (cch, graph)
+        for k in ("rootVisits", "rootUtilitySum", "edgeVisits", "edgeUtilitySum", "policy", "order"):
+            assert (root[k] == br[k]).all(), (cch, graph, k)
+        if graph:
+            assert (dig == bd).all()
+        assert (st.visits, st.terminalVisits, st.transpositionHits, st.catchUpVisits, st.gamesFinished) == \
+               (bs.visits, bs.terminalVisits, bs.transpositionHits, bs.catchUpVisits, bs.gamesFinished)
+        assert st.netEvals + st.nnCacheHits == bs.netEvals and bs.nnCacheHits == 0
+        if cch == 12:
+            assert st.nnCacheHits > 0.02 * bs.netEvals, (st.nnCacheHits, bs.netEvals)    # games from equal positions share evaluations (in lock step most duplicates arrive together)
+    if h is not None:
+        h.close(); lm.close()
