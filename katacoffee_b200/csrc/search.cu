@@ -109,7 +109,11 @@ struct TreeMem {
   float* cachePolicy;     // [N][P]
   float* cacheScalars;    // [N][4] whiteWin, whiteLoss, varTimeLeft, shorttermWinlossError
   unsigned cacheMask;     // N - 1; 0 = no cache
-  int* leafCache;         // [G] entry the leaf's evaluation comes from (hit), -1: evaluated in the batch (then inserted)
+  int* leafCache;         // [G] entry the leaf's evaluation comes from (hit); -1: evaluated in the batch (then inserted); -3: another game evaluates the
+                          //     same position in this very batch (leafOwner) -- in lock step the duplicates of an iteration arrive together
+  unsigned long long* claimWord;   // [N] (iteration stamp << 32) | (owner game + 1), 0xffffffff in the low half while the key is being written
+  uint64_t* claimKey;     // [N][2] key the slot is claimed for in that iteration
+  int* leafOwner;         // [G] the game whose batch row a -3 leaf reads
   uint64_t* leafCKey;     // [G][2] cache key of a leaf that missed
   const double* tcdf;     // [2000] Student-t (3 degrees of freedom) cdf on [-50, 50] for valueWeightExponent
   const double* stdevTab; // [1025] sqrt(1e-8 + 1 / (1.5 sqrt(w))) for integer child weights w (the common case): same bits as computing it
@@ -203,8 +207,29 @@ __device__ __forceinline__ bool nnCacheLookup(const SearchCfg& c, const TreeMem&
     t.leafCache[gi] = (int)idx;
     return true;
   }
-  t.leafCache[gi] = -1;
   t.leafCKey[2 * (size_t)gi] = k0; t.leafCKey[2 * (size_t)gi + 1] = k1;
+  // a miss: claim the slot for this key and this iteration, or follow the game that has
+  const unsigned long long stampHi = (unsigned long long)(unsigned)c.iterStamp << 32;
+  unsigned long long w = t.claimWord[idx];
+  if((w >> 32) != (unsigned)c.iterStamp) {
+    if(atomicCAS(&t.claimWord[idx], w, stampHi | 0xffffffffULL) == w) {   // ours: key first, then the owner becomes visible
+      t.claimKey[2 * (size_t)idx] = k0; t.claimKey[2 * (size_t)idx + 1] = k1;
+      __threadfence();
+      atomicExch(&t.claimWord[idx], stampHi | (unsigned long long)(gi + 1));
+      t.leafCache[gi] = -1;
+      return false;
+    }
+    w = t.claimWord[idx];
+  }
+  if((w >> 32) == (unsigned)c.iterStamp && (unsigned)w != 0xffffffffu && (unsigned)w != 0u) {
+    __threadfence();
+    if(t.claimKey[2 * (size_t)idx] == k0 && t.claimKey[2 * (size_t)idx + 1] == k1) {
+      t.leafCache[gi] = -3;
+      t.leafOwner[gi] = (int)(unsigned)w - 1;
+      return true;
+    }
+  }
+  t.leafCache[gi] = -2;   // evaluated in the batch, not inserted (the slot belongs to another key this iteration)
   return false;
 }
 // whole warp, after an evaluation that missed: store it unless the slot was hit in this iteration or another warp is writing it
@@ -469,11 +494,11 @@ __global__ void __launch_bounds__(128) k_expand_backup(const SearchCfg c, TreeMe
   double v = t.leafValue[gi];
   int newIdx = -1;
   if(kind == 1 || kind == 4) {
-    const size_t row = (size_t)t.leafSlot[gi];
     const int ce = t.cacheMask ? t.leafCache[gi] : -2;                     // >= 0: the evaluation comes from the NN cache
+    const size_t row = (size_t)t.leafSlot[ce == -3 ? t.leafOwner[gi] : gi];   // -3: the row of the game that evaluates the same position
     const float* polSrc = ce >= 0 ? t.cachePolicy + (size_t)ce * c.P : policy + row * c.P;
     const float* wlSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 : winLoss + 2 * row;
-    cached = ce >= 0;
+    cached = ce >= 0 || ce == -3;
     v = __dsub_rn((double)wlSrc[0], (double)wlSrc[1]);   // white-positive utility of the evaluation
     newIdx = t.nodeCount[gi];
     if(newIdx >= c.maxNodes) return;   // cannot happen: one new node per visit, maxNodes == maxVisits
@@ -991,12 +1016,12 @@ __global__ void __launch_bounds__(128, 8) k_expand_backup_graph(const SearchCfg 
   double v = t.leafValue[gi];
   int newIdx = -1;
   if(kind == 1 || kind == 4) {
-    const size_t row = (size_t)t.leafSlot[gi];
     const int ce = t.cacheMask ? t.leafCache[gi] : -2;                     // >= 0: the evaluation comes from the NN cache
+    const size_t row = (size_t)t.leafSlot[ce == -3 ? t.leafOwner[gi] : gi];   // -3: the row of the game that evaluates the same position
     const float* polSrc = ce >= 0 ? t.cachePolicy + (size_t)ce * c.P : policy + row * c.P;
     const float* wlSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 : winLoss + 2 * row;
     const float* miscSrc = ce >= 0 ? t.cacheScalars + (size_t)ce * 4 + 2 : (misc ? misc + 2 * row : nullptr);
-    cached = ce >= 0;
+    cached = ce >= 0 || ce == -3;
     shortErr = miscSrc ? miscSrc[1] : 0.0f;
     v = __dsub_rn((double)wlSrc[0], (double)wlSrc[1]);
     newIdx = t.nodeCount[gi];
@@ -1963,6 +1988,8 @@ int kc_search_create(kc_ctx* ctx, kc_handle* handleOrNull, int numGames, int xSi
     KC_CUDA(cudaMalloc(&S->tree.cacheState, N * 8)); KC_CUDA(cudaMemset(S->tree.cacheState, 0, N * 8));
     KC_CUDA(cudaMalloc(&S->tree.cachePolicy, N * c.P * 4)); KC_CUDA(cudaMalloc(&S->tree.cacheScalars, N * 16));
     KC_CUDA(cudaMalloc(&S->tree.leafCache, n * 4)); KC_CUDA(cudaMalloc(&S->tree.leafCKey, n * 16));
+    KC_CUDA(cudaMalloc(&S->tree.claimWord, N * 8)); KC_CUDA(cudaMemset(S->tree.claimWord, 0, N * 8));
+    KC_CUDA(cudaMalloc(&S->tree.claimKey, N * 16)); KC_CUDA(cudaMalloc(&S->tree.leafOwner, n * 4));
   }
   KC_CUDA(cudaMalloc(&S->d_chosen, n * 2));
   KC_CUDA(cudaMalloc(&S->d_psv, n * c.P * 8)); KC_CUDA(cudaMemset(S->d_psv, 0, n * c.P * 8));
@@ -2007,7 +2034,7 @@ int kc_search_destroy(kc_search* S) {
     cudaFree(t.recGameId); cudaFree(t.rowCount); cudaFree(t.outBin); cudaFree(t.outGlobalIn); cudaFree(t.outPolicy); cudaFree(t.outGlobalT); cudaFree(t.outValue); }
   cudaFree(S->d_policy); cudaFree(S->d_winLoss); cudaFree(S->d_misc); cudaFree(S->d_nnHash); cudaFree(S->d_chosen);
   cudaFree(S->d_psv); cudaFree(S->d_rootAccPolicy); cudaFree(S->d_rootAccScalars);
-  cudaFree(S->tree.cacheKeys); cudaFree(S->tree.cacheState); cudaFree(S->tree.cachePolicy); cudaFree(S->tree.cacheScalars); cudaFree(S->tree.leafCache); cudaFree(S->tree.leafCKey);
+  cudaFree(S->tree.cacheKeys); cudaFree(S->tree.cacheState); cudaFree(S->tree.cachePolicy); cudaFree(S->tree.cacheScalars); cudaFree(S->tree.leafCache); cudaFree(S->tree.leafCKey); cudaFree(S->tree.claimWord); cudaFree(S->tree.claimKey); cudaFree(S->tree.leafOwner);
   cudaEventDestroy(S->ev0); cudaEventDestroy(S->ev1);
   for(int h = 0; h < 2; h++) { if(S->leafHalf[h]) { cudaStreamSynchronize(S->leafHalf[h]->stream); kc_games_destroy(S->leafHalf[h]); } if(S->evJoin[h]) cudaEventDestroy(S->evJoin[h]); }
   if(S->evFork) cudaEventDestroy(S->evFork);
@@ -2029,6 +2056,7 @@ int kc_search_reset(kc_search* S, uint64_t seed, uint64_t firstGameId) {
   if(S->tree.cacheMask) {   // evaluations depend on the seed through nnRandomize's symmetry: a new run starts with an empty NN cache
     KC_CUDA(cudaMemsetAsync(S->tree.cacheKeys, 0, ((size_t)S->tree.cacheMask + 1) * 16, S->leaf->stream));
     KC_CUDA(cudaMemsetAsync(S->tree.cacheState, 0, ((size_t)S->tree.cacheMask + 1) * 8, S->leaf->stream));
+    KC_CUDA(cudaMemsetAsync(S->tree.claimWord, 0, ((size_t)S->tree.cacheMask + 1) * 8, S->leaf->stream));
   }
   KC_CUDA(cudaStreamSynchronize(S->leaf->stream));
   return 0;
