@@ -42,7 +42,8 @@ using namespace ptx;
 constexpr int CHUNK_BYTES = ACT_ROWS * 16;             // one 8-channel chunk of an activation tile
 constexpr int SCR_STRIDE = 17;
 constexpr int MAX_NB = 4;
-constexpr int HEADC = 32;   // p1 = g1 = v1 = 32 channels
+constexpr int HEADC = 32;   // p1 = g1 = v1 channels of the BASELINE nets; TrunkCfg::HC is what a kernel instantiation runs
+constexpr int MAX_HEADC = 64;
 constexpr int MAX_V2 = 128;
 
 // Compile-time shape of one trunk-kernel instantiation.  <128, 2, 7>: trunks up to 128 channels, two activation tiles
@@ -55,9 +56,11 @@ constexpr int MAX_V2 = 128;
 // KSTEPS: K-steps (16 input channels x 1 tap each) per weight stage.  3 = one kernel row of a 16-channel chunk; 9 = the whole chunk
 // (pair mode): one barrier round and one commit per 9 MMAs, because the single issuing thread -- not the tensor pipe -- is what
 // runs out first with small stages (an MMA of a CTA pair is 64 clk of pipe time; three waits + a commit per 192 clk did not fit).
-template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false, int KSTEPS_ = 3>
+template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false, int KSTEPS_ = 3, int HEADC_ = 32>
 struct TrunkCfg {
   static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_, KSTEPS = KSTEPS_;
+  static constexpr int HC = HEADC_;   // p1 = g1 = v1 channels: 32 (b6c96 .. b15c192), 48 (b20c256), 64 (b40c256) -- python/modelconfigs.py
+  static_assert(HC % 16 == 0 && HC >= 32 && HC <= MAX_HEADC && 3 * HC <= MAXC, "the head convolution's 3 x HC columns live in TMEM region S");
   static_assert(KSTEPS == 3 || KSTEPS == 9, "a stage is one kernel row or one whole 16-channel chunk of a 3x3 layer");
   static constexpr bool PAIR = PAIR_;
   static constexpr bool REALLOC = REALLOC_;   // launch with 128 registers per thread and re-allocate between the warpgroups (setmaxnreg)
@@ -89,13 +92,15 @@ struct TrunkCfg {
   static constexpr int SMEM = OFF_TMEM + 16;
   static_assert(NT * 2 * MAXC <= 512, "TMEM: every tile needs a trunk region and a block-internal region");
   static_assert(SMEM <= 232448, "shared memory budget");
-  static_assert(POOLW >= 96, "the heads pool 32 channels three ways");
+  static_assert(POOLW >= 3 * HC, "the heads pool HC channels three ways");
 };
 using Cfg128 = TrunkCfg<128, 2, 7>;
 using Cfg128P = TrunkCfg<128, 2, 5, true, false, 9>;
 using Cfg128PR = TrunkCfg<128, 2, 5, true, true, 9>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
-using Cfg256 = TrunkCfg<256, 1, 4>;                    // trunks up to 256 channels (b20c256 / b40c256 shapes): one tile, T 256 + S 256 = all 512 TMEM columns,
+using Cfg256 = TrunkCfg<256, 1, 4>;
+using Cfg256H48 = TrunkCfg<256, 1, 4, false, false, 3, 48>;   // b20c256's 48-channel heads (modelconfigs.py:284-286)
+using Cfg256H64 = TrunkCfg<256, 1, 4, false, false, 3, 64>;   // b40c256's 64-channel heads                    // trunks up to 256 channels (b20c256 / b40c256 shapes): one tile, T 256 + S 256 = all 512 TMEM columns,
                                                         // single CTA (a pair's 9-tap stages of 256 output channels do not fit beside the 94 KB activation tile)
 using Cfg192P = TrunkCfg<192, 1, 4, true, false, 9>;   // b15c192 as CTA pairs: each CTA stages half of the 192 output channels (27 KB stages)
 
@@ -129,6 +134,7 @@ struct TrunkProgram {
   size_t wBytes = 0;
   int v2C = 0;
   int cfg = 0;     // 0: TrunkCfg<128, 2, 7>, 1: TrunkCfg<192, 1, 6>, 2: TrunkCfg<256, 1, 4>
+  int headC = 32;  // p1 = g1 = v1 channels (cfg 2 also runs 48 and 64)
   double flopsPerEval = 0;
 };
 
@@ -401,21 +407,23 @@ __device__ void epilogueGPool(const TrunkParams& P, const LayerDesc& L, const Ep
 }
 
 __shared__ __align__(16) float sW3[2][4][MAX_V2 + 1];   // value / misc output matrices of the head, [tile][output][k], [V2] = bias
-__shared__ __align__(16) float sHeadPar[2][11 * HEADC + MAX_V2];   // read with 128-bit loads (W2)
+__shared__ __align__(16) float sHeadPar[2][11 * MAX_HEADC + MAX_V2];   // read with 128-bit loads (W2)
 __shared__ uint8_t sCellRow[112];            // tile row of cell i of a board (pooling), up to 10x10   // small head parameters per tile (layout in epilogueHead), staged once per kernel
 
+template <int HC>
 __device__ __forceinline__ void stageHeadParams(const TrunkParams& P, const LayerDesc& L, int e, int t, float* par) {
+  constexpr int HEADC = HC;   // shadows the global: every offset below is in units of this instantiation's head width
   const int V2 = P.v2C;
   const float* base = P.params + L.pOff;
-  const float* p1s = base + 2 * HEADC + 96 * HEADC;              // p1BN s, b | W2 | v1BN s, b: 256 contiguous floats
+  const float* p1s = base + 2 * HEADC + 3 * HEADC * HEADC;              // p1BN s, b | W2 | v1BN s, b: 256 contiguous floats
   const float* Wv2 = p1s + 8 * HEADC;
-  const float* b2 = Wv2 + 96 * V2;
+  const float* b2 = Wv2 + 3 * HEADC * V2;
   const float* Wv3 = b2 + V2;
   const float* b3 = Wv3 + V2 * 2;
   const float* Wsv3 = b3 + 2;
   const float* bsv3 = Wsv3 + V2 * 2;
   const float* Wown = bsv3 + 2;
-  if(e < 2 * HEADC) par[e] = __ldg(base + e);
+  for(int i = e; i < 2 * HEADC; i += 128) par[i] = __ldg(base + i);
   for(int i = e; i < 8 * HEADC; i += 128) par[2 * HEADC + i] = __ldg(p1s + i);
   if(e < HEADC) par[10 * HEADC + e] = __ldg(Wown + e);
   for(int i = e; i < V2; i += 128) par[11 * HEADC + i] = __ldg(b2 + i);
@@ -426,100 +434,107 @@ __device__ __forceinline__ void stageHeadParams(const TrunkParams& P, const Laye
   if(e < 4) sW3[t][e][V2] = __ldg(((e < 2) ? b3 : bsv3) + (e & 1));
 }
 
-// params: g1BN s[32] b[32] | Wpb [96][32] | p1BN s[32] b[32] | W2 [32][4] | v1BN s[32] b[32] |
-//         Wv2 [96][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [32]
+// params (HC = K::HC head channels, PW = 3 HC): g1BN s[HC] b[HC] | Wpb [PW][HC] | p1BN s[HC] b[HC] | W2 [HC][4] | v1BN s[HC] b[HC] |
+//         Wv2 [PW][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [HC]
 template <class K>
 __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
                              const uint8_t* sSym, const int nRows) {
+  constexpr int HC = K::HC, PW = 3 * HC;
+  // 32-channel heads keep p1 in registers and release TMEM region S before the pooled matmuls (the next item's first layer can be issued
+  // under the rest of this epilogue); wider heads read p1 from TMEM 16 columns at a time when the policy is formed, and release then
+  constexpr bool EARLY = HC <= 32;
   const int V2 = P.v2C;
   // small parameters were staged in shared memory before the accumulator wait (stageHeadParams): layout of c.par
-  //   [0,32) g1BN s | [32,64) g1BN b | [64,96) p1BN s | [96,128) p1BN b | [128,256) W2 [32][4] | [256,288) v1BN s | [288,320) v1BN b |
-  //   [320,352) Wown | [352,352+V2) b2 ;  sW3[tile][o][k] = value / misc output matrices, [o][V2] = their biases
+  //   [0,HC) g1BN s | [HC,2HC) g1BN b | [2HC,3HC) p1BN s | [3HC,4HC) p1BN b | [4HC,8HC) W2 [HC][4] | [8HC,9HC) v1BN s | [9HC,10HC) v1BN b |
+  //   [10HC,11HC) Wown | [11HC,11HC+V2) b2 ;  sW3[tile][o][k] = value / misc output matrices, [o][V2] = their biases
   const float* g1s = c.par;
-  const float* g1b = c.par + 32;
-  const float* p1s = c.par + 64;
-  const float* p1b = c.par + 96;
-  const float* W2 = c.par + 128;
-  const float* v1s = c.par + 256;
-  const float* v1b = c.par + 288;
-  const float* Wown = c.par + 320;
-  const float* b2 = c.par + 352;
-  const float* Wpb = P.params + L.pOff + 2 * HEADC;
-  const float* Wv2 = Wpb + 96 * HEADC + 2 * HEADC + 4 * HEADC + 2 * HEADC;
+  const float* g1b = c.par + HC;
+  const float* p1s = c.par + 2 * HC;
+  const float* p1b = c.par + 3 * HC;
+  const float* W2 = c.par + 4 * HC;
+  const float* v1s = c.par + 8 * HC;
+  const float* v1b = c.par + 9 * HC;
+  const float* Wown = c.par + 10 * HC;
+  const float* b2 = c.par + 11 * HC;
+  const float* Wpb = P.params + L.pOff + 2 * HC;
+  const float* Wv2 = Wpb + PW * HC + 2 * HC + 4 * HC + 2 * HC;
   uint32_t src = c.tmemLane + K::MAXC;
-  float* pooledG = c.poolA;   // [NB][96]
-  float* pooledV = c.poolB;   // [NB][96]
-  float v1a[HEADC];
+  float* pooledG = c.poolA;   // [NB][PW]
+  float* pooledV = c.poolB;   // [NB][PW]
+  float own = 0.f;            // ownership = v1 (after BN / activation / mask) . Wown, formed while v1 passes through the pooling
   const bool hp = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
   if(hp) P.dbg[24] = clock64();
   const bool poolOut = !(c.e & 1) && (c.e >> 1) < P.NB * 16;
   const int pb = c.e >> 5, pj = (c.e >> 1) & 15;
   // g1 -> BN -> ReLU -> gpool (eigenbackend.cpp:1290-1291) ; v1 -> BN -> ReLU -> value pool (:1364-1366)
-  for(int half = 0; half < 2; half++) {
+  for(int half = 0; half < HC / 16; half++) {
     float v[16], g[16], sum, mx;
-    tmem_ld16(src + HEADC + half * 16, v);
-    if(hp) P.dbg[30 + 4 * half] = clock64();
+    tmem_ld16(src + HC + half * 16, v);
+    if(hp && half < 2) P.dbg[30 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), P.g1Act);
       g[j] = c.valid ? a : 0.f;
     }
     poolBoards16(P, c, g, sum, mx, hp && half == 0 ? P.dbg + 40 : nullptr);
-    if(hp) P.dbg[31 + 4 * half] = clock64();
+    if(hp && half < 2) P.dbg[31 + 4 * half] = clock64();
     const float kInv = c.boardK ? c.boardK[pb * 4] : P.invHW, kS1 = c.boardK ? c.boardK[pb * 4 + 1] : P.poolScale1,
                 kS2 = c.boardK ? c.boardK[pb * 4 + 2] : P.poolScale2;
     if(poolOut) {
       float mean = sum * kInv;
-      pooledG[pb * 96 + half * 16 + pj] = mean;
-      pooledG[pb * 96 + 32 + half * 16 + pj] = mean * kS1;
-      pooledG[pb * 96 + 64 + half * 16 + pj] = mx;
+      pooledG[pb * PW + half * 16 + pj] = mean;
+      pooledG[pb * PW + HC + half * 16 + pj] = mean * kS1;
+      pooledG[pb * PW + 2 * HC + half * 16 + pj] = mx;
     }
-    tmem_ld16(src + 2 * HEADC + half * 16, v);
-    if(hp) P.dbg[32 + 4 * half] = clock64();
+    tmem_ld16(src + 2 * HC + half * 16, v);
+    if(hp && half < 2) P.dbg[32 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), P.v1Act);
       g[j] = c.valid ? a : 0.f;
-      v1a[half * 16 + j] = g[j];
+      own = fmaf(g[j], Wown[half * 16 + j], own);
     }
     poolBoards16(P, c, g, sum, mx);
-    if(hp) P.dbg[33 + 4 * half] = clock64();
+    if(hp && half < 2) P.dbg[33 + 4 * half] = clock64();
     if(poolOut) {
       float mean = sum * kInv;
-      pooledV[pb * 96 + half * 16 + pj] = mean;
-      pooledV[pb * 96 + 32 + half * 16 + pj] = mean * kS1;
-      pooledV[pb * 96 + 64 + half * 16 + pj] = mean * kS2;
+      pooledV[pb * PW + half * 16 + pj] = mean;
+      pooledV[pb * PW + HC + half * 16 + pj] = mean * kS1;
+      pooledV[pb * PW + 2 * HC + half * 16 + pj] = mean * kS2;
     }
   }
   if(hp) P.dbg[25] = clock64();
-  float p1[HEADC];
-  {
+  float p1[EARLY ? HC : 1];
+  auto releaseTmem = [&]() {
+    // all TMEM reads of this tile are done: the MMA warp may overwrite region S for the next item
+    tc_fence_before();
+    __syncwarp();
+    if((c.r & 31) == 0) { if(c.remote) mbar_arrive_cluster(barHead); else mbar_arrive(barHead); }
+    if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0) P.dbg[18] = clock64();
+  };
+  if constexpr(EARLY) {
     float v[16];
-    tmem_ld16(src, v);
 #pragma unroll
-    for(int j = 0; j < 16; j++) p1[j] = v[j];
-    tmem_ld16(src + 16, v);
+    for(int q = 0; q < HC / 16; q++) {
+      tmem_ld16(src + q * 16, v);
 #pragma unroll
-    for(int j = 0; j < 16; j++) p1[16 + j] = v[j];
+      for(int j = 0; j < 16; j++) p1[q * 16 + j] = v[j];
+    }
+    releaseTmem();
   }
-  // all TMEM reads of this tile are done: the MMA warp may overwrite region S for the next item
-  tc_fence_before();
-  __syncwarp();
-  if((c.r & 31) == 0) { if(c.remote) mbar_arrive_cluster(barHead); else mbar_arrive(barHead); }
-  if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0) P.dbg[18] = clock64();
   named_bar_sync(1 + c.t, 128);
-  // pooled matmuls: policy bias (NB*32 outputs) and v2 (NB*V2 outputs)
+  // pooled matmuls: policy bias (NB*HC outputs) and v2 (NB*V2 outputs)
   if(hp) P.dbg[26] = clock64();
-  // threads 0..31: policy bias column oc; threads 32..127: v2 columns -- both matmuls in flight at once
-  if(c.e < HEADC) {
+  // threads 0..HC-1: policy bias column oc; the others: v2 columns -- both matmuls in flight at once
+  if(c.e < HC) {
     float acc[MAX_NB];
-    pooledMatmul(pooledG, 96, Wpb, 96, HEADC, c.e, P.NB, acc);
+    pooledMatmul(pooledG, PW, Wpb, PW, HC, c.e, P.NB, acc);
 #pragma unroll
-    for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[b * 96 + c.e] = acc[b];
+    for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[b * PW + c.e] = acc[b];
   } else {
-    for(int oc = c.e - HEADC; oc < V2; oc += 128 - HEADC) {
+    for(int oc = c.e - HC; oc < V2; oc += 128 - HC) {
       float acc[MAX_NB];
-      pooledMatmul(pooledV, 96, Wv2, 96, V2, oc, P.NB, acc);
+      pooledMatmul(pooledV, PW, Wv2, PW, V2, oc, P.NB, acc);
       const float bias2 = b2[oc];
 #pragma unroll
       for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = actf(acc[b] + bias2, P.v2Act);
@@ -558,16 +573,32 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     pol[dst] = 0.f; pol[P.HW + dst] = 0.f; pol[2 * P.HW + dst] = 0.f; pol[3 * P.HW + dst] = 0.f;
     P.own[(size_t)g2 * P.HW + dst] = 0.f;
   }
-  if(c.valid && game < nRows) {
-    const float* add = c.biasBuf + c.b * 96;
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, own = 0.f;
+  // the policy: p1 + pooled bias -> BN -> activation -> the 1x1 p2 convolution (eigenbackend.cpp:1292-1298).  Every thread runs the loop
+  // (the late form reads TMEM warp-wide); only the threads of board cells store.
+  const float* add = c.biasBuf + c.b * PW;
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  if constexpr(EARLY) {
 #pragma unroll
-    for(int k = 0; k < HEADC; k++) {
+    for(int k = 0; k < HC; k++) {
       float a = actf(fmaf(p1[k] + add[k], p1s[k], p1b[k]), P.p1Act);
       float4 w = *(reinterpret_cast<const float4*>(W2) + k);
       o0 = fmaf(a, w.x, o0); o1 = fmaf(a, w.y, o1); o2 = fmaf(a, w.z, o2); o3 = fmaf(a, w.w, o3);
-      own = fmaf(v1a[k], Wown[k], own);
     }
+  } else {
+    for(int q = 0; q < HC / 16; q++) {
+      float v[16];
+      tmem_ld16(src + q * 16, v);
+#pragma unroll
+      for(int j = 0; j < 16; j++) {
+        const int k = q * 16 + j;
+        float a = actf(fmaf(v[j] + add[k], p1s[k], p1b[k]), P.p1Act);
+        float4 w = *(reinterpret_cast<const float4*>(W2) + k);
+        o0 = fmaf(a, w.x, o0); o1 = fmaf(a, w.y, o1); o2 = fmaf(a, w.z, o2); o3 = fmaf(a, w.w, o3);
+      }
+    }
+    releaseTmem();
+  }
+  if(c.valid && game < nRows) {
     int s = P.sym ? P.sym[game] : 0;
     int dst = sSym[s * P.HW + c.cell];
     float* pol = P.policy + (size_t)game * 4 * P.HW;
@@ -883,7 +914,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     c.v2buf = c.scr + MAX_NB * K::MAXC;
     uint32_t layerCount = 0;
     bool alive = true;
-    stageHeadParams(P, P.layers[P.numLayers - 1], c.e, c.t, sHeadPar[c.t]);   // read after the first layer's named barrier at the earliest
+    stageHeadParams<K::HC>(P, P.layers[P.numLayers - 1], c.e, c.t, sHeadPar[c.t]);   // read after the first layer's named barrier at the earliest
     for(int unit = unit0; unit < numUnits && alive; unit += unitStep) {
       const int item = itemOf(unit);
       for(int l = 0; l < P.numLayers && alive; l++, layerCount++) {
@@ -1125,7 +1156,11 @@ int buildTrunkProgram(kc_model* m) {
   const int cfg = C <= Cfg128::MAXC ? 0 : C <= Cfg192::MAXC ? 1 : 2;
   const int maxC = cfg == 0 ? Cfg128::MAXC : cfg == 1 ? Cfg192::MAXC : Cfg256::MAXC, maxG = cfg == 0 ? Cfg128::MAXG : cfg == 1 ? Cfg192::MAXG : Cfg256::MAXG;
   if(m->initialConv.ky != 3 || m->initialConv.kx != 3) return unsupported("initial conv must be 3x3");
-  if(m->p1Conv.oc != HEADC || m->g1Conv.oc != HEADC || m->v1Conv.oc != HEADC) return unsupported("head convs must have 32 channels");
+  const int HC = m->p1Conv.oc;   // shadows nothing: the packing below is in units of the model's head width
+  if(m->g1Conv.oc != HC || m->v1Conv.oc != HC) return unsupported("the three head convolutions must have the same number of channels");
+  if(HC != 32 && !(cfg == 2 && (HC == 48 || HC == 64)))
+    return unsupported("head convolutions must have 32 channels (48 or 64 with a trunk of 193..256 channels: the b20c256 / b40c256 shapes)");
+  if(m->gpoolToBiasMul.oc != HC || m->p2Conv.ic != HC || m->vOwnershipConv.ic != HC) return unsupported("head shapes do not fit together");
   if(m->p1Conv.ky != 1 || m->g1Conv.ky != 1 || m->v1Conv.ky != 1 || m->p2Conv.ky != 1 || m->vOwnershipConv.ky != 1)
     return unsupported("head convs must be 1x1");
   if(m->v2Mul.oc > MAX_V2 || m->v2Mul.oc % 16 != 0) return unsupported("v2 size must be a multiple of 16, <= 128");
@@ -1140,6 +1175,7 @@ int buildTrunkProgram(kc_model* m) {
   if(2 * m->blocks.size() + 2 > (size_t)MAX_LAYERS) return unsupported("too many blocks for the tcgen05 kernel's layer table");
   TrunkProgram* T = new TrunkProgram();
   T->cfg = cfg;
+  T->headC = HC;
   double macs = 0;
   // the layer table and the fp32 parameters do not depend on the operand format; the weight stream is packed once per format
   auto packAll = [&](Packer& pk) {
@@ -1185,22 +1221,22 @@ int buildTrunkProgram(kc_model* m) {
   }
   {
     LayerDesc L{};
-    L.nk = C / 16; L.ntaps = 1; L.N = 3 * HEADC; L.outSel = 1; L.accumulate = 0; L.epi = EPI_HEAD; L.epiC = 0;
-    L.wOffset = pk.addConv(3 * HEADC, C, 1, [&](int n, int ic, int) {
-      if(n < HEADC) return convW(m->p1Conv, n, ic, 0);
-      if(n < 2 * HEADC) return convW(m->g1Conv, n - HEADC, ic, 0);
-      return convW(m->v1Conv, n - 2 * HEADC, ic, 0);
+    L.nk = C / 16; L.ntaps = 1; L.N = 3 * HC; L.outSel = 1; L.accumulate = 0; L.epi = EPI_HEAD; L.epiC = 0;
+    L.wOffset = pk.addConv(3 * HC, C, 1, [&](int n, int ic, int) {
+      if(n < HC) return convW(m->p1Conv, n, ic, 0);
+      if(n < 2 * HC) return convW(m->g1Conv, n - HC, ic, 0);
+      return convW(m->v1Conv, n - 2 * HC, ic, 0);
     });
     // p2Conv oc,ic,1,1 -> [ic][4]
-    std::vector<float> w2((size_t)HEADC * 4), wown(HEADC);
-    for(int k = 0; k < HEADC; k++) {
-      for(int d = 0; d < 4; d++) w2[(size_t)k * 4 + d] = m->p2Conv.h[(size_t)d * HEADC + k];
+    std::vector<float> w2((size_t)HC * 4), wown(HC);
+    for(int k = 0; k < HC; k++) {
+      for(int d = 0; d < 4; d++) w2[(size_t)k * 4 + d] = m->p2Conv.h[(size_t)d * HC + k];
       wown[k] = m->vOwnershipConv.h[k];
     }
     L.pOff = pk.addParams(cat({&m->g1BN.scale, &m->g1BN.bias, &m->gpoolToBiasMul.h, &m->p1BN.scale, &m->p1BN.bias, &w2, &m->v1BN.scale,
                                &m->v1BN.bias, &m->v2Mul.h, &m->v2Bias.h, &m->v3Mul.h, &m->v3Bias.h, &m->sv3Mul.h, &m->sv3Bias.h, &wown}));
     T->layers.push_back(L);
-    macs += 3.0 * HEADC * C;
+    macs += 3.0 * HC * C;
   }
   };
   Packer pk, pkB;
@@ -1208,7 +1244,7 @@ int buildTrunkProgram(kc_model* m) {
   packAll(pkB);
   packAll(pk);
   // Note: cat() above relies on each sub-block keeping the exact sizes the kernel indexes with
-  // (HEADC, 96*HEADC, ...); alignment padding is only appended after the whole block.
+  // (HC, 3*HC*HC, ...); alignment padding is only appended after the whole block.
   T->v2C = m->v2Mul.oc;
   T->wBytes = pk.w.size();
   T->flopsPerEval = 2.0 * macs;   // per board cell; multiplied by H*W by the caller
@@ -1272,6 +1308,8 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg256::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg256H48>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg256H48::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg256H64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg256H64::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PR::SMEM));
   return 0;
@@ -1376,6 +1414,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   }
   else if(T->cfg == 0) trunk_kernel<Cfg128><<<grid, Cfg128::THREADS, Cfg128::SMEM, st>>>(P);
   else if(T->cfg == 1) trunk_kernel<Cfg192><<<grid, Cfg192::THREADS, Cfg192::SMEM, st>>>(P);
+  else if(T->headC == 48) trunk_kernel<Cfg256H48><<<grid, Cfg256H48::THREADS, Cfg256H48::SMEM, st>>>(P);
+  else if(T->headC == 64) trunk_kernel<Cfg256H64><<<grid, Cfg256H64::THREADS, Cfg256H64::SMEM, st>>>(P);
   else trunk_kernel<Cfg256><<<grid, Cfg256::THREADS, Cfg256::SMEM, st>>>(P);
   if(timed) { cudaEventRecord(h->evPool[h->evUsed + 1], st); h->evUsed += 2; }
   h->launches++;

@@ -18,7 +18,7 @@ import numpy as np
 from . import capi
 
 CONFIGS = {
-    # name: (trunk, mid, regular, gpool, numBlocks, gpool block indices, v2 size)
+    # name: (trunk, mid, regular, gpool, numBlocks, gpool block indices, v2 size[, head channels = 32])
     "b0c32": (32, 32, 16, 16, 0, (), 32),        # shallow nets: bf16 rounding has not decorrelated yet, so the
     "b1c32": (32, 32, 16, 16, 1, (), 32),        #   tensor-core path can be compared POINTWISE with the bf16-emulating oracle
     "b1c32g": (32, 32, 16, 16, 1, (0,), 32),
@@ -29,7 +29,10 @@ CONFIGS = {
     "b1c192g": (192, 192, 128, 64, 1, (0,), 96),   # shallow 192-wide net: pointwise check of the one-tile-per-CTA kernel
     "b2c256": (256, 256, 192, 64, 2, (1,), 96),    # the 256-wide single-tile kernel (modelconfigs.py b20c256 / b40c256 shapes), shallow for pointwise checks
     "b6c256": (256, 256, 192, 64, 6, (2, 4), 96),
-    "b20c256": (256, 256, 192, 64, 20, (6, 11, 16), 112),   # modelconfigs.py:249-288 b20c256 trunk (gpool blocks 7, 12, 17; v2 112) with this repo's 32-channel heads
+    "b20c256": (256, 256, 192, 64, 20, (6, 11, 16), 112, 48),   # modelconfigs.py:249-288 b20c256: gpool blocks 7, 12, 17, 48-channel heads, v2 112
+    "b2c256h48": (256, 256, 192, 64, 2, (1,), 112, 48),         # shallow forms of the b20c256 / b40c256 head widths
+    "b2c256h64": (256, 256, 192, 64, 2, (0,), 128, 64),
+    "b2c128h48": (128, 128, 96, 32, 2, (1,), 80, 48),           # wide heads on a narrow trunk: not a tensor-path shape, must be rejected
     "b1c320": (320, 320, 256, 64, 1, (), 96),      # wider than the tensor-core kernel supports: must be rejected, not emulated
 }
 HEAD_C = 32
@@ -45,7 +48,8 @@ class Model:
             raise ValueError("activation must be 'relu' or 'mish' (cpp/neuralnet/activations.h:4-6)")
         self.name = name
         self.act = act = 1 if activation == "relu" else 2
-        C_, mid, reg, gp, nb, gpool_blocks, v2 = CONFIGS[name]
+        C_, mid, reg, gp, nb, gpool_blocks, v2 = CONFIGS[name][:7]
+        HEAD_C = self.head_c = CONFIGS[name][7] if len(CONFIGS[name]) > 7 else 32
         self.trunk, self.num_blocks, self.v2 = C_, nb, v2
         rng = np.random.default_rng(seed)
         self._keep = []
@@ -198,7 +202,8 @@ class Model:
 
 def flops_per_eval(name, hw):
     """Algorithmic FLOPs of one forward = 2 x direct-conv/matmul MACs."""
-    C_, mid, reg, gp, nb, gpool_blocks, v2 = CONFIGS[name]
+    C_, mid, reg, gp, nb, gpool_blocks, v2 = CONFIGS[name][:7]
+    HEAD_C = CONFIGS[name][7] if len(CONFIGS[name]) > 7 else 32
     macs = hw * 9 * 15 * C_ + C_                       # initial conv + global matmul
     for i in range(nb):
         if i in gpool_blocks:

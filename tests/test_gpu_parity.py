@@ -324,7 +324,8 @@ def check_tensor_against_oracle(oracle, om, got, planes, glob, recs_sel, W, H, s
 @pytest.mark.parametrize("net,W,H,n,calibrate", [("b2c32", 5, 5, 37, "rms"), ("b6c96", 5, 5, 200, "rms"), ("b10c128", 5, 5, 300, "rms"),
                                                  ("b6c96", 6, 6, 50, "rms"), ("b10c128", 5, 5, 300, "full"), ("b6c96", 5, 5, 100, "none"),
                                                  ("b15c192", 6, 6, 61, "rms"), ("b15c192", 5, 5, 45, "rms"),
-                                                 ("b2c256", 5, 5, 40, "rms"), ("b6c256", 6, 6, 37, "rms")])   # the 256-channel single-tile kernel
+                                                 ("b2c256", 5, 5, 40, "rms"), ("b6c256", 6, 6, 37, "rms"),    # the 256-channel single-tile kernel
+                                                 ("b2c256h48", 5, 5, 40, "rms"), ("b2c256h64", 6, 6, 37, "rms")])   # ... with the b20c256 / b40c256 head widths
 @pytest.mark.parametrize("mode", ["fp32", "f16", "bf16"])
 def test_forward_matches_oracle(ctx, oracle, net, W, H, n, calibrate, mode):
     """NeuralNet::getOutput (kc_forward, host rows incl. per-row symmetry) vs the oracle's forward: the fp32 check path, the
@@ -669,6 +670,10 @@ def test_b15c192_6x6_device_resident_and_unsupported_width_rejected(ctx, oracle)
     ref2 = oracle.Model(wide).forward(planes5, glob5, 5, 5, mode=0, threads=8)
     assert max(np.abs(a - b).max() for a, b in zip(got2, ref2)) < TOL_FP32
     h2.close(); lm2.close()
+    lm3 = backend.LoadedModel(ctx, modeldesc.Model("b2c128h48", seed=2))    # 48-channel heads need the 256-wide kernel's TMEM region
+    with pytest.raises(capi.KCError, match="head convolutions"):
+        backend.createComputeHandle(ctx, lm3, 8, 5, 5)
+    lm3.close()
 
 
 # ------------------------------------------------------------------------------------------------

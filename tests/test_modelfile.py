@@ -59,7 +59,7 @@ def test_modelfile_round_trip(tmp_path, suffix, net, activation):
     # the file is what the reference's parser expects: the text form starts name / version / 15 / 1 / trunk header
     text = gzip.decompress(raw) if suffix.endswith(".gz") else raw
     head = text.split(b"\n", 6)
-    C_, mid, reg, gp, nb, _, _ = modeldesc.CONFIGS[net]
+    C_, mid, reg, gp, nb, _, _ = modeldesc.CONFIGS[net][:7]
     assert head[:5] == [b"kc-test-" + net.encode(), b"1", b"15", b"1", b"trunk"]
     assert head[5].split() == [str(x).encode() for x in (nb, C_, mid, reg, reg, gp)]
     assert (b"@BIN@" in text) == (".bin" in suffix)
