@@ -144,6 +144,7 @@ struct TrunkParams {
   int numLayers, numItems, n;
   const int* nDev;   // if non-null: the number of rows is read from device memory (a batch compacted on the device)
   int NB, W, H, HW, stride, tileRowW;
+  int wMagic;        // 65536 / W + 1: cell / W = cell * wMagic >> 16 for cell < 128, W <= 10
   const int8_t* sym; const uint8_t* dstOfSrcRev;
   float *policy, *value, *misc, *own;
   int permuteDirs;   // KC_FLAG_SYM_PERMUTE_DIRS
@@ -220,7 +221,7 @@ __device__ __forceinline__ void publish16T(const EpiCtx& c, int cc, const float 
     float4 s = *(reinterpret_cast<const float4*>(scale + cc * 16) + q);     // shared memory (c.par), staged before the accumulator wait
     float4 bb = *(reinterpret_cast<const float4*>(bias + cc * 16) + q);
     float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
-    if(add) { x0 += add[cc * 16 + 4 * q]; x1 += add[cc * 16 + 4 * q + 1]; x2 += add[cc * 16 + 4 * q + 2]; x3 += add[cc * 16 + 4 * q + 3]; }
+    if(add) { const float4 ad = *(reinterpret_cast<const float4*>(add + cc * 16) + q); x0 += ad.x; x1 += ad.y; x2 += ad.z; x3 += ad.w; }
     float a0, a1, a2, a3;
     if(RELU) {
       a0 = fmaxf(fmaf(x0, s.x, bb.x), 0.f); a1 = fmaxf(fmaf(x1, s.y, bb.y), 0.f);
@@ -265,33 +266,34 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
   if(b < P.NB) {
     // even lane: cells 0, 2, 4, ...; odd lane: cells 1, 3, 5, ...  The tile row of a cell comes from a table (c.cellRow), four cells per
     // iteration on two accumulators, so the shared-memory loads are independent of one another and of the running sums
-    const uint8_t* cr = c.cellRow;
+    const int dRow = P.tileRowW - P.W;   // tile row of cell i = i + (i / W) * (tileRowW - W); i / W = i * wMagic >> 16
+    auto crf = [&](int i) { return i + (int)(((unsigned)i * (unsigned)P.wMagic) >> 16) * dRow; };
     const float* base = c.scr + b * P.stride * SCR_STRIDE + j;
     float sB = 0.f, mB = -1.0f;
     int i = part;
     if(c.maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
       const float* mk = c.maskRow + b * P.stride;   // same summation order as below: a board that fills its slot gives the same bits
       for(; i + 6 < P.HW; i += 8) {
-        const int r0 = cr[i], r1 = cr[i + 2], r2 = cr[i + 4], r3 = cr[i + 6];
+        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
         const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
         s += v0; sB += v1; s += v2; sB += v3;
         m = fmaxf(m, fmaxf(v0 + (mk[r0] - 1.0f), v2 + (mk[r2] - 1.0f))); mB = fmaxf(mB, fmaxf(v1 + (mk[r1] - 1.0f), v3 + (mk[r3] - 1.0f)));
       }
       for(; i < P.HW; i += 2) {
-        const int r = cr[i];
+        const int r = crf(i);
         const float v = base[r * SCR_STRIDE];
         s += v;
         m = fmaxf(m, v + (mk[r] - 1.0f));
       }
     } else {
       for(; i + 6 < P.HW; i += 8) {
-        const int r0 = cr[i], r1 = cr[i + 2], r2 = cr[i + 4], r3 = cr[i + 6];
+        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
         const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
         s += v0; sB += v1; s += v2; sB += v3;
         m = fmaxf(m, fmaxf(v0, v2)); mB = fmaxf(mB, fmaxf(v1, v3));
       }
       for(; i < P.HW; i += 2) {
-        const float v = base[cr[i] * SCR_STRIDE];
+        const float v = base[crf(i) * SCR_STRIDE];
         s += v;
         m = fmaxf(m, v);
       }
@@ -304,7 +306,20 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
 }
 
 // acc[b] = sum_k in[b*inStride + k] * W[k*OC + oc] for the NB boards of a tile, k ascending (same summation order as a plain
-// loop), with the weight loads issued 16 at a time: these tiny matmuls are pure L2 latency, not bandwidth.  Kdim % 16 == 0.
+// loop), with the weight loads issued 32 at a time: these tiny matmuls are pure L2 latency, not bandwidth.  Kdim % 16 == 0; `in` rows
+// are 16-byte aligned and read four values per shared-memory access (broadcast: one wavefront per instruction whatever its width).
+template <int NW>
+__device__ __forceinline__ void pooledFma(const float* in, int inStride, int k0, const float (&w)[NW], int NB, float acc[MAX_NB]) {
+#pragma unroll
+  for(int j = 0; j < NW; j += 4)
+#pragma unroll
+    for(int b = 0; b < MAX_NB; b++)
+      if(b < NB) {
+        const float4 x = *reinterpret_cast<const float4*>(in + b * inStride + k0 + j);
+        acc[b] = fmaf(x.x, w[j], acc[b]); acc[b] = fmaf(x.y, w[j + 1], acc[b]);
+        acc[b] = fmaf(x.z, w[j + 2], acc[b]); acc[b] = fmaf(x.w, w[j + 3], acc[b]);
+      }
+}
 __device__ __forceinline__ void pooledMatmul(const float* in, int inStride, const float* __restrict__ W, int Kdim, int OC, int oc, int NB,
                                              float acc[MAX_NB]) {
 #pragma unroll
@@ -314,21 +329,13 @@ __device__ __forceinline__ void pooledMatmul(const float* in, int inStride, cons
     float w[32];
 #pragma unroll
     for(int j = 0; j < 32; j++) w[j] = __ldg(W + (size_t)(k0 + j) * OC + oc);
-#pragma unroll
-    for(int j = 0; j < 32; j++)
-#pragma unroll
-      for(int b = 0; b < MAX_NB; b++)
-        if(b < NB) acc[b] = fmaf(in[b * inStride + k0 + j], w[j], acc[b]);
+    pooledFma<32>(in, inStride, k0, w, NB, acc);
   }
   for(; k0 < Kdim; k0 += 16) {
     float w[16];
 #pragma unroll
     for(int j = 0; j < 16; j++) w[j] = __ldg(W + (size_t)(k0 + j) * OC + oc);
-#pragma unroll
-    for(int j = 0; j < 16; j++)
-#pragma unroll
-      for(int b = 0; b < MAX_NB; b++)
-        if(b < NB) acc[b] = fmaf(in[b * inStride + k0 + j], w[j], acc[b]);
+    pooledFma<16>(in, inStride, k0, w, NB, acc);
   }
 }
 
@@ -462,6 +469,9 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   float* pooledG = c.poolA;   // [NB][PW]
   float* pooledV = c.poolB;   // [NB][PW]
   float own = 0.f;            // ownership = v1 (after BN / activation / mask) . Wown, formed while v1 passes through the pooling
+  // this row's output symmetry, fetched now: a global load takes 1,500+ clk here (L2 is streaming the next item's weights), and the
+  // policy stores at the end of this epilogue depend on it
+  const int symEarly = (P.sym && tileIndex * P.NB + c.b < nRows) ? P.sym[tileIndex * P.NB + c.b] : 0;
   const bool hp = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
   if(hp) P.dbg[24] = clock64();
   const bool poolOut = !(c.e & 1) && (c.e >> 1) < P.NB * 16;
@@ -599,7 +609,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     releaseTmem();
   }
   if(c.valid && game < nRows) {
-    int s = P.sym ? P.sym[game] : 0;
+    int s = symEarly;
     int dst = sSym[s * P.HW + c.cell];
     float* pol = P.policy + (size_t)game * 4 * P.HW;
     if(P.permuteDirs) {   // play mode: the net's direction channel d is direction symDir(d, s) of the original position
@@ -669,7 +679,7 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
   for(int item = K::PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x; item < numItems; item += itemStep, itemCount++) {   // pair mode: item = item pair
     if(!mbar_wait(bars + (K::BAR_IN + t) * 8, itemCount & 1, abortFlag, 21)) return;
     if(K::PAIR && !waitc(bars + (K::BAR_INP + t) * 8, itemCount & 1, 26)) return;
-    if(itemCount > 0 && !waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
+    bool needHead = itemCount > 0;   // region S still belongs to the previous item's head epilogue; region T (layer 0) does not
     tc_fence_after();
     if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) P.dbg[20] = clock64();
     for(int l = 0; l < P.numLayers; l++) {
@@ -678,6 +688,11 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
       //   k = 0 issuer reaches the layer, 1 first chunk available, 2 layer issued and committed, 3 epilogue sees the accumulator, 4 epilogue done
       long long* tl = (P.dbg && blockIdx.x == 0 && itemCount == 1 && leader) ? P.dbg + 64 + (t * MAX_LAYERS + l) * 8 : nullptr;
       if(tl) tl[0] = clock64();
+      if(needHead && P.layers[l].outSel) {
+        if(!waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
+        tc_fence_after();
+        needHead = false;
+      }
       const uint32_t idesc = idesc_f16kind_f32(128 * K::NCTA, N, (uint32_t)P.opFmt, (uint32_t)P.opFmt);   // A and B must share the format
       const uint32_t d = tmemBase + t * (2 * K::MAXC) + (P.layers[l].outSel ? K::MAXC : 0);
       const uint32_t bStep = 2 * N / K::NCTA;                    // one K-step of weights = N*32 bytes (per CTA: its half of the rows)
@@ -1361,7 +1376,7 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   P.wstream = T->d_w[P.opFmt]; P.params = T->d_params;
   P.numLayers = (int)T->layers.size();
   for(int i = 0; i < P.numLayers; i++) P.layers[i] = T->layers[i];
-  P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride;
+  P.NB = boardsPerTile(h->W, h->H); P.W = h->W; P.H = h->H; P.HW = h->W * h->H; P.stride = h->W + 1; P.tileRowW = P.NB * P.stride; P.wMagic = 65536 / h->W + 1;
   int numTiles = (n + P.NB - 1) / P.NB;
   const int NT = T->cfg == 0 ? Cfg128::NT : Cfg192::NT;
   P.numItems = (numTiles + NT - 1) / NT;
