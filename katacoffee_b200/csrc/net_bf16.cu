@@ -168,13 +168,23 @@ struct TrunkParams {
 // ------------------------------------------------------------------------------------------------
 // Activations (cpp/neuralnet/activations.h:4-6): 0 identity, 1 ReLU, 2 Mish = x*tanh(softplus(x)) (eigenbackend.cpp:729, linear
 // above 20).  With n = e^x, tanh(log(1+n)) = n(n+2) / (n(n+2) + 2): one exponential and one division.  `act` is warp-uniform.
+// Loads through shared-window addresses: a pointer handed to an out-of-line function is generic, and a generic load is slower than LDS
+__device__ __forceinline__ float lds32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// The kernel's code is far larger than the 32 KB instruction cache and its once-per-item epilogues (global pooling, heads) run cold --
+// a cold pass over them was measured at 2x a warm one -- so whatever is not on the per-layer path is kept out of line and shared.
+__device__ __noinline__ float mishf(float x) {
+  const float n = __expf(fminf(x, 20.f));
+  const float t = n * (n + 2.f);
+  return x > 20.f ? x : x * __fdividef(t, t + 2.f);
+}
 __device__ __forceinline__ float actf(float x, int act) {
   if(act == 1) return fmaxf(x, 0.f);
-  if(act == 2) {
-    const float n = __expf(fminf(x, 20.f));
-    const float t = n * (n + 2.f);
-    return x > 20.f ? x : x * __fdividef(t, t + 2.f);
-  }
+  if(act == 2) return mishf(x);
   return x;
 }
 
@@ -250,8 +260,54 @@ __device__ __forceinline__ void publish16(const EpiCtx& c, int cc, const float v
   else publish16T<false>(c, cc, v, scale, bias, add, act);
 }
 
-// Two threads per (board, channel): even lane = upper rows, odd lane = lower rows, combined by one shuffle; the even lane
-// (c.e even, c.e >> 1 = board*16 + channel < NB*16) returns the board's sum and max.
+// Global pooling of 16 channels held one row per thread.  Two threads per (board, channel): even lane = even cells, odd lane = odd
+// cells, combined by one shuffle; the even lane (e even, e >> 1 = board*16 + channel < NB*16) returns the board's sum (.x) and max (.y).
+// The reduction is one out-of-line copy for every caller (two gpool layers, four passes in the heads): it stays in the instruction cache.
+// The tile row of a cell is computed (cell / W = cell * wMagic >> 16), not looked up: shared-memory loads are slow while the tensor
+// core streams its operands from the same memory.
+__device__ __noinline__ float2 poolReduce(uint32_t scr, uint32_t maskRow, int e, int NB, int stride, int HW, int wMagic, int dRow) {
+  const int o = e >> 1, part = e & 1;
+  const int b = o >> 4, j = o & 15;
+  float s = 0.f, m = -1.0f;   // eigenbackend.cpp:145: max starts at -1
+  if(b < NB) {
+    const uint32_t base = scr + (uint32_t)(b * stride * SCR_STRIDE + j) * 4u;
+    auto crf = [&](int i) { return i + (int)(((unsigned)i * (unsigned)wMagic) >> 16) * dRow; };
+    auto val = [&](int r) { return lds32(base + (uint32_t)(r * SCR_STRIDE) * 4u); };
+    float sB = 0.f, mB = -1.0f;
+    int i = part;
+    if(maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
+      const uint32_t mk = maskRow + (uint32_t)(b * stride) * 4u;   // same summation order as below: a board that fills its slot gives the same bits
+      for(; i + 6 < HW; i += 8) {
+        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
+        const float v0 = val(r0), v1 = val(r1), v2 = val(r2), v3 = val(r3);
+        const float k0 = lds32(mk + r0 * 4u) - 1.0f, k1 = lds32(mk + r1 * 4u) - 1.0f, k2 = lds32(mk + r2 * 4u) - 1.0f, k3 = lds32(mk + r3 * 4u) - 1.0f;
+        s += v0; sB += v1; s += v2; sB += v3;
+        m = fmaxf(m, fmaxf(v0 + k0, v2 + k2)); mB = fmaxf(mB, fmaxf(v1 + k1, v3 + k3));
+      }
+      for(; i < HW; i += 2) {
+        const int r = crf(i);
+        const float v = val(r);
+        s += v;
+        m = fmaxf(m, v + (lds32(mk + r * 4u) - 1.0f));
+      }
+    } else {
+      for(; i + 6 < HW; i += 8) {
+        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
+        const float v0 = val(r0), v1 = val(r1), v2 = val(r2), v3 = val(r3);
+        s += v0; sB += v1; s += v2; sB += v3;
+        m = fmaxf(m, fmaxf(v0, v2)); mB = fmaxf(mB, fmaxf(v1, v3));
+      }
+      for(; i < HW; i += 2) {
+        const float v = val(crf(i));
+        s += v;
+        m = fmaxf(m, v);
+      }
+    }
+    s += sB; m = fmaxf(m, mB);
+  }
+  const float s2 = __shfl_xor_sync(0xffffffffu, s, 1), m2 = __shfl_xor_sync(0xffffffffu, m, 1);
+  return make_float2(s + s2, fmaxf(m, m2));   // even lane: even cells + odd cells
+}
 __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx& c, const float g[16], float& sum, float& mx, long long* pd = nullptr) {
   if(pd) pd[0] = clock64();
   named_bar_sync(1 + c.t, 128);   // the previous use of the scratch has been read
@@ -260,68 +316,28 @@ __device__ __forceinline__ void poolBoards16(const TrunkParams& P, const EpiCtx&
   for(int j = 0; j < 16; j++) c.scr[c.r * SCR_STRIDE + j] = g[j];
   named_bar_sync(1 + c.t, 128);
   if(pd) pd[2] = clock64();
-  const int o = c.e >> 1, part = c.e & 1;
-  const int b = o >> 4, j = o & 15;
-  float s = 0.f, m = -1.0f;   // eigenbackend.cpp:145: max starts at -1
-  if(b < P.NB) {
-    // even lane: cells 0, 2, 4, ...; odd lane: cells 1, 3, 5, ...  The tile row of a cell comes from a table (c.cellRow), four cells per
-    // iteration on two accumulators, so the shared-memory loads are independent of one another and of the running sums
-    const int dRow = P.tileRowW - P.W;   // tile row of cell i = i + (i / W) * (tileRowW - W); i / W = i * wMagic >> 16
-    auto crf = [&](int i) { return i + (int)(((unsigned)i * (unsigned)P.wMagic) >> 16) * dRow; };
-    const float* base = c.scr + b * P.stride * SCR_STRIDE + j;
-    float sB = 0.f, mB = -1.0f;
-    int i = part;
-    if(c.maskRow) {   // off-board cells count as -1 in the maximum (eigenbackend.cpp:150-155); they are 0 in the sum already
-      const float* mk = c.maskRow + b * P.stride;   // same summation order as below: a board that fills its slot gives the same bits
-      for(; i + 6 < P.HW; i += 8) {
-        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
-        const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
-        s += v0; sB += v1; s += v2; sB += v3;
-        m = fmaxf(m, fmaxf(v0 + (mk[r0] - 1.0f), v2 + (mk[r2] - 1.0f))); mB = fmaxf(mB, fmaxf(v1 + (mk[r1] - 1.0f), v3 + (mk[r3] - 1.0f)));
-      }
-      for(; i < P.HW; i += 2) {
-        const int r = crf(i);
-        const float v = base[r * SCR_STRIDE];
-        s += v;
-        m = fmaxf(m, v + (mk[r] - 1.0f));
-      }
-    } else {
-      for(; i + 6 < P.HW; i += 8) {
-        const int r0 = crf(i), r1 = crf(i + 2), r2 = crf(i + 4), r3 = crf(i + 6);
-        const float v0 = base[r0 * SCR_STRIDE], v1 = base[r1 * SCR_STRIDE], v2 = base[r2 * SCR_STRIDE], v3 = base[r3 * SCR_STRIDE];
-        s += v0; sB += v1; s += v2; sB += v3;
-        m = fmaxf(m, fmaxf(v0, v2)); mB = fmaxf(mB, fmaxf(v1, v3));
-      }
-      for(; i < P.HW; i += 2) {
-        const float v = base[crf(i) * SCR_STRIDE];
-        s += v;
-        m = fmaxf(m, v);
-      }
-    }
-    s += sB; m = fmaxf(m, mB);
-  }
-  const float s2 = __shfl_xor_sync(0xffffffffu, s, 1), m2 = __shfl_xor_sync(0xffffffffu, m, 1);
-  sum = s + s2;       // even lane: even cells + odd cells
-  mx = fmaxf(m, m2);
+  const float2 r = poolReduce(smem_u32(c.scr), c.maskRow ? smem_u32(c.maskRow) : 0u, c.e, P.NB, P.stride, P.HW, P.wMagic, P.tileRowW - P.W);
+  sum = r.x; mx = r.y;
 }
 
 // acc[b] = sum_k in[b*inStride + k] * W[k*OC + oc] for the NB boards of a tile, k ascending (same summation order as a plain
 // loop), with the weight loads issued 32 at a time: these tiny matmuls are pure L2 latency, not bandwidth.  Kdim % 16 == 0; `in` rows
 // are 16-byte aligned and read four values per shared-memory access (broadcast: one wavefront per instruction whatever its width).
 template <int NW>
-__device__ __forceinline__ void pooledFma(const float* in, int inStride, int k0, const float (&w)[NW], int NB, float acc[MAX_NB]) {
+__device__ __forceinline__ void pooledFma(uint32_t in, int inStride, int k0, const float (&w)[NW], int NB, float acc[MAX_NB]) {
 #pragma unroll
   for(int j = 0; j < NW; j += 4)
 #pragma unroll
     for(int b = 0; b < MAX_NB; b++)
       if(b < NB) {
-        const float4 x = *reinterpret_cast<const float4*>(in + b * inStride + k0 + j);
+        const float4 x = lds128(in + (uint32_t)(b * inStride + k0 + j) * 4u);
         acc[b] = fmaf(x.x, w[j], acc[b]); acc[b] = fmaf(x.y, w[j + 1], acc[b]);
         acc[b] = fmaf(x.z, w[j + 2], acc[b]); acc[b] = fmaf(x.w, w[j + 3], acc[b]);
       }
 }
-__device__ __forceinline__ void pooledMatmul(const float* in, int inStride, const float* __restrict__ W, int Kdim, int OC, int oc, int NB,
-                                             float acc[MAX_NB]) {
+static_assert(MAX_NB == 4, "pooledMatmul returns one accumulator per board in a float4");
+__device__ __noinline__ float4 pooledMatmul4(uint32_t in, int inStride, const float* __restrict__ W, int Kdim, int OC, int oc, int NB) {
+  float acc[MAX_NB];
 #pragma unroll
   for(int b = 0; b < MAX_NB; b++) acc[b] = 0.f;
   int k0 = 0;
@@ -337,6 +353,12 @@ __device__ __forceinline__ void pooledMatmul(const float* in, int inStride, cons
     for(int j = 0; j < 16; j++) w[j] = __ldg(W + (size_t)(k0 + j) * OC + oc);
     pooledFma<16>(in, inStride, k0, w, NB, acc);
   }
+  return make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+__device__ __forceinline__ void pooledMatmul(const float* in, int inStride, const float* __restrict__ W, int Kdim, int OC, int oc, int NB,
+                                             float acc[MAX_NB]) {
+  const float4 r = pooledMatmul4(smem_u32(in), inStride, W, Kdim, OC, oc, NB);
+  acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
 }
 
 template <class K>
