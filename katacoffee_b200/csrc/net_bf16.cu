@@ -56,8 +56,10 @@ constexpr int MAX_V2 = 128;
 // KSTEPS: K-steps (16 input channels x 1 tap each) per weight stage.  3 = one kernel row of a 16-channel chunk; 9 = the whole chunk
 // (pair mode): one barrier round and one commit per 9 MMAs, because the single issuing thread -- not the tensor pipe -- is what
 // runs out first with small stages (an MMA of a CTA pair is 64 clk of pipe time; three waits + a commit per 192 clk did not fit).
-template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false, int KSTEPS_ = 3, int HEADC_ = 32>
+template <int MAXC_, int NT_, int NSTAGES_, bool PAIR_ = false, bool REALLOC_ = false, int KSTEPS_ = 3, int HEADC_ = 32, bool PROBE_ = false>
 struct TrunkCfg {
+  static constexpr bool PROBE = PROBE_;   // the in-kernel clock probes (kc_handle_trunk_probe) are compiled into their own instantiations: they
+                                          // are ~3 KB of a per-layer path that has to share a 32 KB instruction cache
   static constexpr int MAXC = MAXC_, NT = NT_, NSTAGES = NSTAGES_, KSTEPS = KSTEPS_;
   static constexpr int HC = HEADC_;   // p1 = g1 = v1 channels: 32 (b6c96 .. b15c192), 48 (b20c256), 64 (b40c256) -- python/modelconfigs.py
   static_assert(HC % 16 == 0 && HC >= 32 && HC <= MAX_HEADC && 3 * HC <= MAXC, "the head convolution's 3 x HC columns live in TMEM region S");
@@ -96,12 +98,14 @@ struct TrunkCfg {
 };
 using Cfg128 = TrunkCfg<128, 2, 7>;
 using Cfg128P = TrunkCfg<128, 2, 5, true, false, 9>;
+using Cfg128PProbe = TrunkCfg<128, 2, 5, true, false, 9, 32, true>;
 using Cfg128PR = TrunkCfg<128, 2, 5, true, true, 9>;   // the variant that leaves 16 k registers per SM to co-resident kernels (search half batches)
 using Cfg192 = TrunkCfg<192, 1, 6>;
 using Cfg256 = TrunkCfg<256, 1, 4>;
 using Cfg256H48 = TrunkCfg<256, 1, 4, false, false, 3, 48>;   // b20c256's 48-channel heads (modelconfigs.py:284-286)
 using Cfg256H64 = TrunkCfg<256, 1, 4, false, false, 3, 64>;   // b40c256's 64-channel heads                    // trunks up to 256 channels (b20c256 / b40c256 shapes): one tile, T 256 + S 256 = all 512 TMEM columns,
                                                         // single CTA (a pair's 9-tap stages of 256 output channels do not fit beside the 94 KB activation tile)
+using Cfg192PProbe = TrunkCfg<192, 1, 4, true, false, 9, 32, true>;
 using Cfg192P = TrunkCfg<192, 1, 4, true, false, 9>;   // b15c192 as CTA pairs: each CTA stages half of the 192 output channels (27 KB stages)
 
 enum { EPI_BN = 0, EPI_GPOOL = 1, EPI_HEAD = 2 };
@@ -361,6 +365,7 @@ __device__ __forceinline__ void pooledMatmul(const float* in, int inStride, cons
   acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
 }
 
+#define KC_DBG (K::PROBE ? P.dbg : static_cast<long long*>(nullptr))
 template <class K>
 __device__ void epilogueBN(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c) {
   const float* scale = c.par;
@@ -494,22 +499,22 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   // this row's output symmetry, fetched now: a global load takes 1,500+ clk here (L2 is streaming the next item's weights), and the
   // policy stores at the end of this epilogue depend on it
   const int symEarly = (P.sym && tileIndex * P.NB + c.b < nRows) ? P.sym[tileIndex * P.NB + c.b] : 0;
-  const bool hp = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
-  if(hp) P.dbg[24] = clock64();
+  const bool hp = KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
+  if(hp) KC_DBG[24] = clock64();
   const bool poolOut = !(c.e & 1) && (c.e >> 1) < P.NB * 16;
   const int pb = c.e >> 5, pj = (c.e >> 1) & 15;
   // g1 -> BN -> ReLU -> gpool (eigenbackend.cpp:1290-1291) ; v1 -> BN -> ReLU -> value pool (:1364-1366)
   for(int half = 0; half < HC / 16; half++) {
     float v[16], g[16], sum, mx;
     tmem_ld16(src + HC + half * 16, v);
-    if(hp && half < 2) P.dbg[30 + 4 * half] = clock64();
+    if(hp && half < 2) KC_DBG[30 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], g1s[half * 16 + j], g1b[half * 16 + j]), P.g1Act);
       g[j] = c.valid ? a : 0.f;
     }
-    poolBoards16(P, c, g, sum, mx, hp && half == 0 ? P.dbg + 40 : nullptr);
-    if(hp && half < 2) P.dbg[31 + 4 * half] = clock64();
+    poolBoards16(P, c, g, sum, mx, hp && half == 0 ? KC_DBG + 40 : nullptr);
+    if(hp && half < 2) KC_DBG[31 + 4 * half] = clock64();
     const float kInv = c.boardK ? c.boardK[pb * 4] : P.invHW, kS1 = c.boardK ? c.boardK[pb * 4 + 1] : P.poolScale1,
                 kS2 = c.boardK ? c.boardK[pb * 4 + 2] : P.poolScale2;
     if(poolOut) {
@@ -519,7 +524,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       pooledG[pb * PW + 2 * HC + half * 16 + pj] = mx;
     }
     tmem_ld16(src + 2 * HC + half * 16, v);
-    if(hp && half < 2) P.dbg[32 + 4 * half] = clock64();
+    if(hp && half < 2) KC_DBG[32 + 4 * half] = clock64();
 #pragma unroll
     for(int j = 0; j < 16; j++) {
       float a = actf(fmaf(v[j], v1s[half * 16 + j], v1b[half * 16 + j]), P.v1Act);
@@ -527,7 +532,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       own = fmaf(g[j], Wown[half * 16 + j], own);
     }
     poolBoards16(P, c, g, sum, mx);
-    if(hp && half < 2) P.dbg[33 + 4 * half] = clock64();
+    if(hp && half < 2) KC_DBG[33 + 4 * half] = clock64();
     if(poolOut) {
       float mean = sum * kInv;
       pooledV[pb * PW + half * 16 + pj] = mean;
@@ -535,14 +540,14 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       pooledV[pb * PW + 2 * HC + half * 16 + pj] = mean * kS2;
     }
   }
-  if(hp) P.dbg[25] = clock64();
+  if(hp) KC_DBG[25] = clock64();
   float p1[EARLY ? HC : 1];
   auto releaseTmem = [&]() {
     // all TMEM reads of this tile are done: the MMA warp may overwrite region S for the next item
     tc_fence_before();
     __syncwarp();
     if((c.r & 31) == 0) { if(c.remote) mbar_arrive_cluster(barHead); else mbar_arrive(barHead); }
-    if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0) P.dbg[18] = clock64();
+    if(KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0) KC_DBG[18] = clock64();
   };
   if constexpr(EARLY) {
     float v[16];
@@ -556,7 +561,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
   named_bar_sync(1 + c.t, 128);
   // pooled matmuls: policy bias (NB*HC outputs) and v2 (NB*V2 outputs)
-  if(hp) P.dbg[26] = clock64();
+  if(hp) KC_DBG[26] = clock64();
   // threads 0..HC-1: policy bias column oc; the others: v2 columns -- both matmuls in flight at once
   if(c.e < HC) {
     float acc[MAX_NB];
@@ -572,9 +577,9 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = actf(acc[b] + bias2, P.v2Act);
     }
   }
-  if(hp) P.dbg[27] = clock64();
+  if(hp) KC_DBG[27] = clock64();
   named_bar_sync(1 + c.t, 128);
-  if(hp) P.dbg[28] = clock64();
+  if(hp) KC_DBG[28] = clock64();
   const int gameBase = tileIndex * P.NB;
   {
     // value / misc outputs: 8 lanes per (board, output), each a slice of k, combined by an xor butterfly
@@ -594,7 +599,7 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
       if(o < 2) P.value[(size_t)game * 2 + (o & 1)] = acc; else P.misc[(size_t)game * 2 + (o & 1)] = acc;
     }
   }
-  if(hp) P.dbg[29] = clock64();
+  if(hp) KC_DBG[29] = clock64();
   int game = gameBase + c.b;
   if(c.maskRow && !c.valid && c.slotCell >= 0 && gameBase + c.slotB < nRows) {
     // a cell of the nnXLen x nnYLen slot that is off this board: masked p1 / v1 through the bias-free 1x1 output convolutions = 0
@@ -703,12 +708,12 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
     if(K::PAIR && !waitc(bars + (K::BAR_INP + t) * 8, itemCount & 1, 26)) return;
     bool needHead = itemCount > 0;   // region S still belongs to the previous item's head epilogue; region T (layer 0) does not
     tc_fence_after();
-    if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) P.dbg[20] = clock64();
+    if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 1 && leader) KC_DBG[20] = clock64();
     for(int l = 0; l < P.numLayers; l++) {
       const int nk = P.layers[l].nk, ntaps = P.layers[l].ntaps, N = P.layers[l].N;
       // whole-item timeline (KC_TRUNK_PROBE): CTA 0, second item (steady state): [64 + ((t * MAX_LAYERS + l) * 8 + k)]
       //   k = 0 issuer reaches the layer, 1 first chunk available, 2 layer issued and committed, 3 epilogue sees the accumulator, 4 epilogue done
-      long long* tl = (P.dbg && blockIdx.x == 0 && itemCount == 1 && leader) ? P.dbg + 64 + (t * MAX_LAYERS + l) * 8 : nullptr;
+      long long* tl = (KC_DBG && blockIdx.x == 0 && itemCount == 1 && leader) ? KC_DBG + 64 + (t * MAX_LAYERS + l) * 8 : nullptr;
       if(tl) tl[0] = clock64();
       if(needHead && P.layers[l].outSel) {
         if(!waitc(bars + (K::BAR_HEAD + t) * 8, (itemCount - 1) & 1, 22)) return;
@@ -725,16 +730,16 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
         constexpr int ROWS_PER_STAGE = K::KSTEPS / 3;          // kernel rows (dy) per weight stage: 1 or 3
         if(!waitForLeadTile(nchunks * (3 / ROWS_PER_STAGE))) return;
         for(int cc = 0; cc < nchunks; cc++) {
-          const bool probe = P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && cc == 0 && leader;
-          if(probe) P.dbg[6] = clock64();
+          const bool probe = KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && cc == 0 && leader;
+          if(probe) KC_DBG[6] = clock64();
           if(l > 0) {
             const uint32_t bit = 1u << cc;
             if(!waitc(barChunk + cc * 8, (chunkPhase & bit) ? 1 : 0, 24)) return;
             chunkPhase ^= bit;
           }
-          if(probe) P.dbg[4] = clock64();
+          if(probe) KC_DBG[4] = clock64();
           if(tl && cc == 0) tl[1] = clock64();
-          if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 1 && cc == 0 && leader) P.dbg[23] = clock64();
+          if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 1 && cc == 0 && leader) KC_DBG[23] = clock64();
           const uint32_t aLoC = aLo0 + cc * (2 * CHUNK_BYTES >> 4);
 #pragma unroll
           for(int dy0 = 0; dy0 < 3; dy0 += ROWS_PER_STAGE) {
@@ -753,8 +758,8 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
                 accum = 1u;
               }
               commit(barEmpty + slot * 8);
-              if(probe && dy0 == 0) P.dbg[5] = clock64();
-              if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && dy0 + ROWS_PER_STAGE == 3 && cc < 7) P.dbg[8 + cc] = clock64();
+              if(probe && dy0 == 0) KC_DBG[5] = clock64();
+              if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6 && dy0 + ROWS_PER_STAGE == 3 && cc < 7) KC_DBG[8 + cc] = clock64();
             }
             __syncwarp();
             accum = 1u;
@@ -793,10 +798,10 @@ __device__ __forceinline__ void mmaIssuer(const TrunkParams& P, const int t, con
         commit(bars + (K::BAR_ACC + t) * 8);
         if(tl) tl[2] = clock64();
         if(l == P.numLayers - 1) commit(bars + (K::BAR_ACTFREE + t) * 8);
-        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 5) P.dbg[0] = clock64();
-        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6) P.dbg[15] = clock64();
-        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == P.numLayers - 1) P.dbg[16] = clock64();
-        if(P.dbg && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 0) P.dbg[21] = clock64();
+        if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 5) KC_DBG[0] = clock64();
+        if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == 6) KC_DBG[15] = clock64();
+        if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 0 && l == P.numLayers - 1) KC_DBG[16] = clock64();
+        if(KC_DBG && blockIdx.x == 0 && t == 0 && itemCount == 1 && l == 0) KC_DBG[21] = clock64();
       }
       __syncwarp();
     }
@@ -997,19 +1002,19 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
           }
           named_bar_sync(1 + c.t, 128);
         }
-        long long* tl = (P.dbg && blockIdx.x == 0 && c.e == 0 && (int)layerCount >= P.numLayers && (int)layerCount < 2 * P.numLayers)
-                          ? P.dbg + 64 + (c.t * MAX_LAYERS + l) * 8 : nullptr;
+        long long* tl = (KC_DBG && blockIdx.x == 0 && c.e == 0 && (int)layerCount >= P.numLayers && (int)layerCount < 2 * P.numLayers)
+                          ? KC_DBG + 64 + (c.t * MAX_LAYERS + l) * 8 : nullptr;
         if(tl) tl[3] = clock64();
-        c.dbg = (P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && layerCount == 5) ? P.dbg : nullptr;
+        c.dbg = (KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && layerCount == 5) ? KC_DBG : nullptr;
         if(c.dbg) c.dbg[1] = clock64();
-        const bool probeHead = P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers - 1;
-        if(probeHead) P.dbg[17] = clock64();
-        if(P.dbg && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers) P.dbg[22] = clock64();
+        const bool probeHead = KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers - 1;
+        if(probeHead) KC_DBG[17] = clock64();
+        if(KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers) KC_DBG[22] = clock64();
         tc_fence_after();
         if(L.epi == EPI_BN) epilogueBN<K>(P, L, c);
         else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
         else epilogueHead<K>(P, L, c, item * NT + c.t, barHead, sSym, nRows);
-        if(probeHead) P.dbg[19] = clock64();
+        if(probeHead) KC_DBG[19] = clock64();
         if(tl) tl[4] = clock64();
       }
       itemCount++;
@@ -1024,6 +1029,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
   }
 }
 
+#undef KC_DBG
 // kc_forward input conversion: raw fp32 rows (NCHW/NHWC) + global -> symmetrised bf16 tiles
 __global__ void k_convert_tiles(const float* __restrict__ raw, const float* __restrict__ rawGlobal, const int8_t* __restrict__ sym,
                                 const uint8_t* __restrict__ dstOfSrc, uint4* __restrict__ tiles, int n, int numTiles,
@@ -1349,6 +1355,8 @@ int allocTrunkBuffers(kc_handle* h) {
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg256H64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg256H64::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128P::SMEM));
   KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PR::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg128PProbe>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg128PProbe::SMEM));
+  KC_CUDA(cudaFuncSetAttribute(trunk_kernel<Cfg192PProbe>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg192PProbe::SMEM));
   return 0;
 }
 void freeTrunkBuffers(kc_handle* h) {
@@ -1445,7 +1453,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
     cfg.attrs = attr; cfg.numAttrs = 1;
     // the re-allocating variant only where something wants to run beside the trunk (the search's half batches); KC_TRUNK_REALLOC forces
     static const int reallocEnv = [] { const char* e = getenv("KC_TRUNK_REALLOC"); return e ? atoi(e) : -1; }();
-    if(T->cfg != 0) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg192P>, P));
+    if(T->cfg != 0) KC_CUDA(cudaLaunchKernelEx(&cfg, P.dbg ? trunk_kernel<Cfg192PProbe> : trunk_kernel<Cfg192P>, P));
+    else if(P.dbg) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128PProbe>, P));
     else if(reallocEnv >= 0 ? reallocEnv != 0 : h->leaveRegisters) KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128PR>, P));
     else KC_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<Cfg128P>, P));
   }
