@@ -59,7 +59,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -69,6 +69,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout_s=3.0):
+        """nvidia-smi takes a few hundred ms to print its first row: the timed region (tens of ms) starts only once it is streaming."""
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout_s:
+            time.sleep(0.01)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -76,7 +82,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.03] or [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -320,11 +326,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm (`value`) ----------------
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi must be streaming when the timed region begins
+    if sampler:
+        sampler.wait_first()
+    barrier()
     games.runTimed(handle, args.warmup, L2_FLUSH_BYTES)
     handle.trunkTime()
     l0 = games.launchCount() + handle.launchCount()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
     stats, ms_total = games.runTimed(handle, args.steps, L2_FLUSH_BYTES)
     t1 = time.time()
