@@ -33,8 +33,8 @@ extern "C" {
 #define KC_MAX_ARR_SIZE ((KC_MAX_LEN + 1) * (KC_MAX_LEN + 2) + 1) /* board.h:120-124 */
 #define KC_NUM_SPATIAL_V1 15                                 /* SURVEY.md 8.1-F      */
 #define KC_NUM_GLOBAL_V1 1
-#define KC_MAX_DEVICE_LEN 7  /* fast bitboard kernels, the device search and the evaluator front end: H*(W+1) <= 64.  kc_games_* and the
-                                net paths take every size up to KC_MAX_LEN (beyond 7x7: a general kernel on 128-bit bitboards) */
+#define KC_MAX_DEVICE_LEN 7  /* the 64-bit bitboard kernels and the device search: H*(W+1) <= 64.  kc_games_*, the net paths and the evaluator
+                                front end take every size up to KC_MAX_LEN (beyond 7x7: general kernels on 128-bit bitboards) */
 
 typedef struct kc_ctx kc_ctx;
 typedef struct kc_model kc_model;
@@ -526,6 +526,9 @@ typedef struct {
   const uint64_t *black, *white, *hash0, *hash1, *misc;
   const int8_t* symmetry;
   float *policyProbs, *whiteWinLoss, *miscOut, *ownership;
+  /* boards beyond 7x7 (up to the reference's 10x10, board.h:120): bits 64.. of the 128-bit bitboards, and misc in the wide format of
+   * csrc/games_big.cuh (9-bit history entries, last direction at bit 45) -- kc_eval_unpack_position_wide; null otherwise */
+  const uint64_t *blackHi, *whiteHi;
 } kc_eval_batch;
 typedef int (*kc_eval_backend_fn)(void* user, int serverThread, const kc_eval_batch* batch);
 
@@ -554,6 +557,9 @@ int kc_evaluator_clear_stats(kc_evaluator* ev);  /* NNEvaluator::clearStats */
 int kc_eval_position_hash(int xSize, int ySize, const kc_eval_position* pos, float policyTemperature, uint64_t nnHash[2], uint64_t cacheKey[2]);
 int kc_eval_unpack_position(int xSize, int ySize, uint64_t black, uint64_t white, uint64_t misc, int8_t* stones, int8_t* nextPla,
                             int16_t* movesCellPla, int32_t* numTurns, int32_t* lastDir);
+/* the same for a row of a board beyond 7x7 (kc_eval_batch::blackHi / whiteHi non-null) */
+int kc_eval_unpack_position_wide(int xSize, int ySize, uint64_t blackLo, uint64_t blackHi, uint64_t whiteLo, uint64_t whiteHi, uint64_t misc,
+                                 int8_t* stones, int8_t* nextPla, int16_t* movesCellPla, int32_t* numTurns, int32_t* lastDir);
 
 #ifdef __cplusplus
 }

@@ -557,6 +557,16 @@ def evalUnpackPosition(xSize, ySize, black, white, misc):
     return stones, int(pla.value), moves, int(nt.value), int(ld.value)
 
 
+def evalUnpackPositionWide(xSize, ySize, blackLo, blackHi, whiteLo, whiteHi, misc):
+    """The same for a row of a board beyond 7x7 (EvalBatch.blackHi / whiteHi non-null)."""
+    stones = np.zeros(xSize * ySize, np.int8)
+    moves = np.zeros((5, 2), np.int16)
+    pla, nt, ld = C.c_int8(), C.c_int32(), C.c_int32()
+    check(lib().kc_eval_unpack_position_wide(xSize, ySize, int(blackLo), int(blackHi), int(whiteLo), int(whiteHi), int(misc), ptr(stones),
+                                             C.byref(pla), ptr(moves), C.byref(nt), C.byref(ld)))
+    return stones, int(pla.value), moves, int(nt.value), int(ld.value)
+
+
 def writeTrainingNpz(path, xSize, ySize, rows):
     """kc_training_write_npz: the reference's training-data file (trainingwrite.cpp:566-587) from a dict of the five row arrays."""
     n = len(rows["globalInputNC"])

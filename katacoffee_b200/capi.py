@@ -117,7 +117,8 @@ class EvalBatch(C.Structure):
     _fields_ = [("n", C.c_int32), ("wantOwnership", C.c_int32), ("policyTemperature", C.c_float),
                 ("black", C.POINTER(C.c_uint64)), ("white", C.POINTER(C.c_uint64)), ("hash0", C.POINTER(C.c_uint64)),
                 ("hash1", C.POINTER(C.c_uint64)), ("misc", C.POINTER(C.c_uint64)), ("symmetry", C.POINTER(C.c_int8)),
-                ("policyProbs", c_float_p), ("whiteWinLoss", c_float_p), ("miscOut", c_float_p), ("ownership", c_float_p)]
+                ("policyProbs", c_float_p), ("whiteWinLoss", c_float_p), ("miscOut", c_float_p), ("ownership", c_float_p),
+                ("blackHi", C.POINTER(C.c_uint64)), ("whiteHi", C.POINTER(C.c_uint64))]
 
 
 EVAL_BACKEND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(EvalBatch))
@@ -203,6 +204,8 @@ PROTOTYPES = {
     "kc_eval_position_hash": (C.c_int, [C.c_int, C.c_int, C.POINTER(EvalPosition), C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "kc_eval_unpack_position": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.POINTER(C.c_int8), vp,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "kc_eval_unpack_position_wide": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.POINTER(C.c_int8), vp,
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -52,7 +52,10 @@ constexpr uint64_t ZOBRIST_NN_POLICY_TEMP0 = 0xebcbdfeec6f4334bULL, ZOBRIST_NN_P
 
 struct PackedRow {
   uint64_t black, white, hash0, hash1, misc;
+  uint64_t blackHi = 0, whiteHi = 0;   // boards beyond 7x7: bits 64.. of the 128-bit bitboards (games_big.cuh)
 };
+// the criterion of kc_games_create: such boards run the 128-bit rules kernels, with their wider misc format
+inline bool bigBoard(int W, int H) { return W > KC_MAX_DEVICE_LEN || H > KC_MAX_DEVICE_LEN; }
 
 // The packing of kc_games_load (games.cu) for one position; also the literal nnHash and the cache key.
 int packPosition(int W, int H, const kc_eval_position* p, float policyTemperature, PackedRow& r, uint64_t nnHash[2], uint64_t key[2]) {
@@ -61,35 +64,39 @@ int packPosition(int W, int H, const kc_eval_position* p, float policyTemperatur
   KC_CHECK(p->numTurns >= 0 && p->numTurns <= 255, "kc_evaluator: numTurns out of range");
   const ZobristTables& z = kc::zobrist();
   const int HW = W * H, stride = W + 1;
-  uint64_t bb = 0, ww = 0, a0 = z.sizeX[W][0] ^ z.sizeY[H][0], a1 = z.sizeX[W][1] ^ z.sizeY[H][1];
+  const bool big = bigBoard(W, H);   // 128-bit boards, 9-bit history entries, last direction at bit 45 (kc_games_load's wide branch)
+  uint64_t bb = 0, ww = 0, bbHi = 0, wwHi = 0, a0 = z.sizeX[W][0] ^ z.sizeY[H][0], a1 = z.sizeX[W][1] ^ z.sizeY[H][1];
   for(int y = 0; y < H; y++)
     for(int x = 0; x < W; x++) {
       const int c = p->stones[y * W + x];
       KC_CHECK(c >= 0 && c <= 2, "kc_evaluator: stone colour must be 0, 1 or 2");
       if(c == 0) continue;
-      const uint64_t bit = 1ULL << (y * stride + x);
-      if(c == 1) bb |= bit; else ww |= bit;
+      const int idx = y * stride + x;
+      const uint64_t bit = 1ULL << (idx & 63);
+      if(idx < 64) { if(c == 1) bb |= bit; else ww |= bit; }
+      else { if(c == 1) bbHi |= bit; else wwHi |= bit; }
       const int spot = (x + 1) + (y + 1) * (W + 1);   // board.h:74-75
       a0 ^= z.board[spot][c][0]; a1 ^= z.board[spot][c][1];
     }
   uint64_t m = 0;
   int lastDir = 4;
   if(p->moves) {
-    for(int k = 0; k < 5; k++) {   // given oldest first; byte 0 of misc is the most recent
+    for(int k = 0; k < 5; k++) {   // given oldest first; entry 0 of misc is the most recent
       const int pos = p->moves[(4 - k) * 2 + 0], pla = p->moves[(4 - k) * 2 + 1];
       if(pos < 0) continue;
       KC_CHECK(pos < 4 * HW && (pla == 1 || pla == 2), "kc_evaluator: bad history entry");
-      m |= (uint64_t)((pos % HW) | (pla << 6)) << (8 * k);
+      if(big) m |= (uint64_t)((pos % HW) | (pla << 7)) << (9 * k);
+      else m |= (uint64_t)((pos % HW) | (pla << 6)) << (8 * k);
       if(k == 0) lastDir = pos / HW;
     }
   }
-  m |= ((uint64_t)lastDir << 40);
+  m |= ((uint64_t)lastDir << (big ? 45 : 40));
   // last five (cell, player) + last direction + min(numTurns, 5): with the stones, everything the planes and legality read -- the history
   // planes 7..10 are gated on numTurns >= 2..5 (games_device.cuh v1Planes, as nninputs.cpp:575-620), so two requests with equal moves
   // and different numTurns have different inputs and must not share a cache entry
   const uint64_t historyBits = m | ((uint64_t)std::min(p->numTurns, 5) << 44);
   m |= ((uint64_t)p->numTurns << 48) | ((uint64_t)(p->nextPla << 3) << 56);
-  r.black = bb; r.white = ww; r.hash0 = a0; r.hash1 = a1; r.misc = m;
+  r.black = bb; r.white = ww; r.blackHi = bbHi; r.whiteHi = wwHi; r.hash0 = a0; r.hash1 = a1; r.misc = m;
   // NNInputs::getHash: getSitHash(nextPla) = pos_hash ^ ZOBRIST_PLAYER_HASH[pla] (board.cpp:288-292); never finished here
   uint64_t h0 = a0 ^ z.player[p->nextPla][0], h1 = a1 ^ z.player[p->nextPla][1];
   if(policyTemperature != 1.0f) {   // nninputs.cpp:485-492
@@ -166,6 +173,7 @@ struct Cache {
 struct Staging {
   // inputs: the packed rows as five arrays (the layout of kc::State); mapped page-locked memory when the device backend is used
   uint64_t *black = nullptr, *white = nullptr, *hash0 = nullptr, *hash1 = nullptr, *misc = nullptr;
+  uint64_t *blackHi = nullptr, *whiteHi = nullptr;   // boards beyond 7x7 only
   int8_t* symmetry = nullptr;
   uint8_t* wantOwner = nullptr;
   // outputs
@@ -250,6 +258,10 @@ struct DeviceServer {
     G->st.black = const_cast<uint64_t*>(b->black); G->st.white = const_cast<uint64_t*>(b->white);
     G->st.hash0 = const_cast<uint64_t*>(b->hash0); G->st.hash1 = const_cast<uint64_t*>(b->hash1);
     G->st.misc = const_cast<uint64_t*>(b->misc);   // (gameId stays the device array: the kernel loads it, nothing here depends on it)
+    if(G->big) {
+      KC_CHECK(b->blackHi && b->whiteHi, "kc_evaluator: a batch for a board beyond 7x7 without the upper bitboard words");
+      G->st.blackHi = const_cast<uint64_t*>(b->blackHi); G->st.whiteHi = const_cast<uint64_t*>(b->whiteHi);
+    }
     G->geom.numGames = b->n;
     const int rc = kc::gamesEval(G, handle, nullptr, nullptr, 0, false, /*symOnDevice=*/true);   // read-only on the state (no step)
     G->st = saved;
@@ -331,6 +343,7 @@ void serveLoop(kc_evaluator* ev, int serverIdx) {
     eb.n = n;
     eb.policyTemperature = ev->cfg.policyTemperature;
     eb.black = b.black; eb.white = b.white; eb.hash0 = b.hash0; eb.hash1 = b.hash1; eb.misc = b.misc;
+    eb.blackHi = b.blackHi; eb.whiteHi = b.whiteHi;
     eb.symmetry = b.symmetry;
     eb.policyProbs = b.policy; eb.whiteWinLoss = b.winLoss; eb.miscOut = b.miscOut; eb.ownership = b.ownership;
     for(int i = 0; i < n; i++) if(b.wantOwner[i]) { eb.wantOwnership = 1; break; }
@@ -374,6 +387,7 @@ void publishRow(kc_evaluator* ev, uint64_t t, const PackedRow& r, int symmetry, 
     b.cv.wait(lock, [&] { return bufferReady(b, q); });
   }
   b.black[s] = r.black; b.white[s] = r.white; b.hash0[s] = r.hash0; b.hash1[s] = r.hash1; b.misc[s] = r.misc;
+  if(b.blackHi) { b.blackHi[s] = r.blackHi; b.whiteHi[s] = r.whiteHi; }
   b.symmetry[s] = (int8_t)symmetry;
   b.wantOwner[s] = wantOwner ? 1 : 0;
   b.ready.fetch_add(1, std::memory_order_release);
@@ -474,8 +488,8 @@ extern "C" {
 
 static int evaluatorCreateCommon(const kc_evaluator_config* cfg, bool pinned, kc_evaluator** out) {
   KC_CHECK(cfg && out, "kc_evaluator_create: null argument");
-  KC_CHECK(cfg->nnXLen >= 2 && cfg->nnYLen >= 2 && cfg->nnXLen <= KC_MAX_DEVICE_LEN && cfg->nnYLen <= KC_MAX_DEVICE_LEN &&
-             cfg->nnYLen * (cfg->nnXLen + 1) <= 64, "kc_evaluator_create: board size must be within 2..7 with H*(W+1) <= 64");
+  KC_CHECK(cfg->nnXLen >= 2 && cfg->nnYLen >= 2 && cfg->nnXLen <= KC_MAX_LEN && cfg->nnYLen <= KC_MAX_LEN,
+           "kc_evaluator_create: board size must be within 2..10 (board.h:120)");
   KC_CHECK(cfg->winLen >= 2 && cfg->winLen <= 7, "kc_evaluator_create: winLen must be within 2..7");
   KC_CHECK(cfg->maxBatch > 0, "kc_evaluator_create: maxBatchSize is not positive");                // nneval.cpp:121-122
   KC_CHECK(cfg->maxConcurrentEvals > 0, "kc_evaluator_create: maxConcurrentEvals is not positive");  // nneval.cpp:119-120
@@ -500,6 +514,10 @@ static int evaluatorCreateCommon(const kc_evaluator_config* cfg, bool pinned, kc
     b.black = (uint64_t*)stagingAlloc(pinned, mb * 8); b.white = (uint64_t*)stagingAlloc(pinned, mb * 8);
     b.hash0 = (uint64_t*)stagingAlloc(pinned, mb * 8); b.hash1 = (uint64_t*)stagingAlloc(pinned, mb * 8);
     b.misc = (uint64_t*)stagingAlloc(pinned, mb * 8);
+    if(bigBoard(ev->W, ev->H)) {
+      b.blackHi = (uint64_t*)stagingAlloc(pinned, mb * 8); b.whiteHi = (uint64_t*)stagingAlloc(pinned, mb * 8);
+      if(!(b.blackHi && b.whiteHi)) { kc_evaluator_destroy(ev.release()); return kc::fail("kc_evaluator_create: staging allocation failed"); }
+    }
     b.symmetry = (int8_t*)stagingAlloc(pinned, mb);
     b.wantOwner = (uint8_t*)stagingAlloc(false, mb);
     b.policy = (float*)stagingAlloc(pinned, mb * ev->P * 4);
@@ -584,6 +602,7 @@ int kc_evaluator_destroy(kc_evaluator* ev) {
     for(int i = 0; i < ev->ring; i++) {
       Staging& b = ev->bufs[i];
       const bool p = ev->pinned;
+      stagingFree(p, b.blackHi); stagingFree(p, b.whiteHi);
       stagingFree(p, b.black); stagingFree(p, b.white); stagingFree(p, b.hash0); stagingFree(p, b.hash1); stagingFree(p, b.misc);
       stagingFree(p, b.symmetry); stagingFree(false, b.wantOwner);
       stagingFree(p, b.policy); stagingFree(p, b.winLoss); stagingFree(p, b.miscOut); stagingFree(p, b.ownership);
@@ -659,8 +678,7 @@ int kc_evaluator_clear_stats(kc_evaluator* ev) {
 }
 
 int kc_eval_position_hash(int xSize, int ySize, const kc_eval_position* pos, float policyTemperature, uint64_t nnHash[2], uint64_t cacheKey[2]) {
-  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN && ySize * (xSize + 1) <= 64,
-           "kc_eval_position_hash: board size out of range");
+  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_LEN && ySize <= KC_MAX_LEN, "kc_eval_position_hash: board size out of range");
   KC_CHECK(nnHash && cacheKey, "kc_eval_position_hash: null argument");
   PackedRow r;
   return packPosition(xSize, ySize, pos, policyTemperature, r, nnHash, cacheKey);
@@ -668,7 +686,8 @@ int kc_eval_position_hash(int xSize, int ySize, const kc_eval_position* pos, flo
 
 int kc_eval_unpack_position(int xSize, int ySize, uint64_t black, uint64_t white, uint64_t misc, int8_t* stones, int8_t* nextPla,
                             int16_t* movesCellPla, int32_t* numTurns, int32_t* lastDir) {
-  KC_CHECK(xSize >= 2 && ySize >= 2 && ySize * (xSize + 1) <= 64, "kc_eval_unpack_position: board size out of range");
+  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_DEVICE_LEN && ySize <= KC_MAX_DEVICE_LEN,
+           "kc_eval_unpack_position: board size out of range (beyond 7x7: kc_eval_unpack_position_wide)");
   KC_CHECK(stones, "kc_eval_unpack_position: null argument");
   const int stride = xSize + 1;
   for(int y = 0; y < ySize; y++)
@@ -683,6 +702,31 @@ int kc_eval_unpack_position(int xSize, int ySize, uint64_t black, uint64_t white
     for(int k = 0; k < 5; k++) {   // oldest first, like kc_eval_position::moves; (cell, player), cell = -1 for none
       const int byte = (int)((misc >> (8 * k)) & 0xff), pla = byte >> 6;
       movesCellPla[(4 - k) * 2 + 0] = pla ? (int16_t)(byte & 63) : (int16_t)-1;
+      movesCellPla[(4 - k) * 2 + 1] = (int16_t)pla;
+    }
+  return 0;
+}
+
+int kc_eval_unpack_position_wide(int xSize, int ySize, uint64_t blackLo, uint64_t blackHi, uint64_t whiteLo, uint64_t whiteHi, uint64_t misc,
+                                 int8_t* stones, int8_t* nextPla, int16_t* movesCellPla, int32_t* numTurns, int32_t* lastDir) {
+  KC_CHECK(xSize >= 2 && ySize >= 2 && xSize <= KC_MAX_LEN && ySize <= KC_MAX_LEN && bigBoard(xSize, ySize),
+           "kc_eval_unpack_position_wide: for boards beyond 7x7, up to 10x10");
+  KC_CHECK(stones, "kc_eval_unpack_position_wide: null argument");
+  const int stride = xSize + 1;
+  for(int y = 0; y < ySize; y++)
+    for(int x = 0; x < xSize; x++) {
+      const int idx = y * stride + x;
+      const uint64_t bit = 1ULL << (idx & 63);
+      const bool b = ((idx < 64 ? blackLo : blackHi) & bit) != 0, w = ((idx < 64 ? whiteLo : whiteHi) & bit) != 0;
+      stones[y * xSize + x] = b ? 1 : w ? 2 : 0;
+    }
+  if(nextPla) *nextPla = (int8_t)((misc >> 59) & 3);
+  if(numTurns) *numTurns = (int32_t)((misc >> 48) & 0xff);
+  if(lastDir) *lastDir = (int32_t)((misc >> 45) & 7);
+  if(movesCellPla)
+    for(int k = 0; k < 5; k++) {   // oldest first, like kc_eval_position::moves; (cell, player), cell = -1 for none
+      const int e = (int)((misc >> (9 * k)) & 0x1ff), pla = e >> 7;
+      movesCellPla[(4 - k) * 2 + 0] = pla ? (int16_t)(e & 127) : (int16_t)-1;
       movesCellPla[(4 - k) * 2 + 1] = (int16_t)pla;
     }
   return 0;

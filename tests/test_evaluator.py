@@ -328,7 +328,7 @@ def test_backend_failure_and_argument_errors(oracle, built_lib, omodel):
     with pytest.raises(capi.KCError, match="stone colour"):
         ev.evaluate(bad, p["nextPla"], p["moves"], p["numTurns"])
     ev.close()
-    for kw, msg in (({"maxBatchSize": 0}, "maxBatchSize"), ({"numThreads": 0}, "numServerThreads"), ({"nnXLen": 9}, "board size"),
+    for kw, msg in (({"maxBatchSize": 0}, "maxBatchSize"), ({"numThreads": 0}, "numServerThreads"), ({"nnXLen": 11}, "board size"),
                     ({"defaultSymmetry": 8}, "defaultSymmetry"), ({"nnPolicyTemperature": 0.0}, "policyTemperature"),
                     ({"nnCacheSizePowerOfTwo": 40}, "cacheSizePowerOfTwo")):
         with pytest.raises(capi.KCError, match=msg):
@@ -434,7 +434,7 @@ def test_other_board_sizes(oracle, built_lib, omodel, dims):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("dims", [(2, 2, 2), (3, 7, 3), (5, 5, 4), (7, 7, 4), (7, 4, 4)])
+@pytest.mark.parametrize("dims", [(2, 2, 2), (3, 7, 3), (5, 5, 4), (7, 7, 4), (7, 4, 4), (8, 8, 4), (10, 10, 5), (9, 3, 3), (2, 10, 2)])
 def test_packing_round_trip_on_arbitrary_positions(oracle, built_lib, dims):
     """Random stone placements and histories (not only reachable ones), every supported shape: what the front end stages unpacks to what
     was submitted, its pos_hash / NNInputs::getHash are the oracle's, and the cache key separates any two different (stones, player,
@@ -456,7 +456,12 @@ def test_packing_round_trip_on_arbitrary_positions(oracle, built_lib, dims):
 
     def record(server, b):
         for i in range(b.n):
-            st, pla, mv, nt, ld = backend.evalUnpackPosition(Wd, Hd, b.black[i], b.white[i], b.misc[i])
+            if Wd > 7 or Hd > 7:   # 128-bit boards, the wide misc format (games_big.cuh)
+                assert b.blackHi and b.whiteHi
+                st, pla, mv, nt, ld = backend.evalUnpackPositionWide(Wd, Hd, b.black[i], b.blackHi[i], b.white[i], b.whiteHi[i], b.misc[i])
+            else:
+                assert not b.blackHi and not b.whiteHi
+                st, pla, mv, nt, ld = backend.evalUnpackPosition(Wd, Hd, b.black[i], b.white[i], b.misc[i])
             staged[(st.tobytes(), pla, mv.tobytes(), nt, ld)] = (int(b.hash0[i]), int(b.hash1[i]))
             np.ctypeslib.as_array(b.policyProbs, shape=(b.n, 4 * HWd))[i] = 0.0
         return 0

@@ -157,3 +157,51 @@ def test_nonfinite_outputs_fail_the_batch(ctx, oracle):
         ev.evaluate(p["stones"], p["nextPla"], p["moves"], p["numTurns"])
     assert ev.stats()["cacheHits"] == 0
     ev.close(); lm.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("dims", [(9, 9, 5), (10, 10, 5), (8, 7, 4)])
+def test_device_evaluator_on_boards_beyond_7x7(ctx, oracle, dims):
+    """Boards up to the reference's 10x10 (board.h:120) through the evaluator front end: the rows are staged as 128-bit bitboards with the
+    wide misc format and must come out as kc_games_load + kc_games_eval + kc_games_postprocess give them (that path is held to the oracle
+    by test_gpu_parity), with the oracle's NNInputs::getHash."""
+    from katacoffee_b200 import backend, modeldesc
+    Wd, Hd, Kd = dims
+    seen, ps = set(), []
+    for p in make_positions(oracle, 90, seed=7, max_plies=30, dims=dims):
+        key = backend.evalPositionHash(Wd, Hd, p["stones"], p["nextPla"], p["moves"], p["numTurns"])[1]
+        if key not in seen:
+            seen.add(key)
+            ps.append(p)
+    N = len(ps)
+    assert N >= 60
+    stones, nextPla, moves, numTurns = _arrays(ps)
+    model = modeldesc.Model("b2c32", seed=9)
+    lm = backend.LoadedModel(ctx, model)
+    sym = (np.arange(N) % 8).astype(np.int8) if Wd == Hd else (np.arange(N) % 4).astype(np.int8)   # transposing symmetries need a square board
+    h = backend.createComputeHandle(ctx, lm, N, Wd, Hd)
+    games = backend.Games(ctx, N, Wd, Hd, Kd)
+    games.load(0, stones, nextPla, moves, numTurns)
+    games.eval(h, sym)
+    dpol, dwl, dmisc, dhash = games.postprocess(h, 1.0)
+    down = h.readOutputs(N)[3]
+    ev = backend.NNEvaluator(ctx, lm, nnXLen=Wd, nnYLen=Hd, winLen=Kd, maxBatchSize=32, maxConcurrentEvals=128, numThreads=2, nnCacheSizePowerOfTwo=12)
+    res = ev.evaluateMany(stones, nextPla, moves, numTurns, symmetry=sym, includeOwnerMap=True)
+    for i, r in enumerate(res):
+        og = oracle.Game(Wd, Hd, Kd)
+        for c in range(Wd * Hd):
+            if stones[i, c]:
+                og.set_stone(c % Wd, c // Wd, int(stones[i, c]))
+        og.set_history([(int(m[0]), int(m[1])) for m in moves[i] if m[0] >= 0], int(numTurns[i]), int(nextPla[i]))
+        assert r["nnHash"] == tuple(int(x) for x in og.nn_hash()) == (int(dhash[i][0]), int(dhash[i][1]))
+        assert ((r["policyProbs"] == -1) == (dpol[i] == -1)).all(), "legal mask"
+        assert np.abs(r["policyProbs"] - dpol[i]).max() <= 2e-6, i
+        assert abs(r["whiteWinProb"] - dwl[i][0]) <= 2e-6 and abs(r["whiteLossProb"] - dwl[i][1]) <= 2e-6
+        assert np.allclose([r["varTimeLeft"], r["shorttermWinlossError"]], dmisc[i], rtol=1e-6, atol=1e-6)
+        sign = 1.0 if nextPla[i] == 2 else -1.0
+        assert np.abs(r["whiteOwnerMap"] - sign * np.tanh(down[i])).max() <= 1e-5
+        assert r["symmetry"] == sym[i] and not r["cacheHit"]
+    again = ev.evaluate(stones[0], nextPla[0], moves[0], numTurns[0], includeOwnerMap=True)
+    assert again["cacheHit"] and (again["policyProbs"] == res[0]["policyProbs"]).all()
+    for x in (ev, games, h, lm):
+        x.close()
