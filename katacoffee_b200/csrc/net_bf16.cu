@@ -81,6 +81,8 @@ struct TrunkCfg {
   // the per-board bias buffer [MAX_NB][MAXC] and the v2 buffer [MAX_NB][MAX_V2] of the gpool / head epilogues live in the pooling
   // scratch: they are written after the last pooling pass has been read (named barrier in between) and read before the next one
   static_assert((MAX_NB * MAXC + MAX_NB * MAX_V2) * 4 <= 128 * SCR_STRIDE * 4, "bias + v2 buffers alias the pooling scratch");
+  static constexpr int HEAD_ADD_OFF = MAX_NB * MAXC + MAX_NB * MAX_V2;   // floats into a tile's pooling scratch: the 32-channel head's folded policy bias [MAX_NB][32]
+  static_assert(HEAD_ADD_OFF + MAX_NB * 32 <= 128 * SCR_STRIDE && 4 * MAX_NB * 32 <= MAX_NB * MAXC, "folded policy bias and its K-quarter parts");
   static constexpr int OFF_SYM = OFF_POOLB + NT * MAX_NB * POOLW * 4;
   static constexpr int OFF_MASK = OFF_SYM + 800;                  // (OFF_SYM: the inverse symmetry maps, 8 x H*W bytes, up to 10x10)                  // masked boards: [NT][128] row mask + [NT][MAX_NB][4] per-board pooling constants (fp32)
   static constexpr int OFF_PAR = OFF_MASK + NT * (128 + MAX_NB * 4) * 4;                   // [tile][2 buffers][scale MAXC | bias MAXC] fp32: the next layer's
@@ -163,6 +165,7 @@ struct TrunkParams {
   long long* dbg;    // diagnostic: SM clock at the hand-over points of one layer boundary (CTA 0, first item, tile 0), or null
   float poolScale1, poolScale2, invHW;
   int v2C;
+  int deferHead;     // 32-channel heads: run an item's value head after the next item's first-layer epilogue (KC_TRUNK_DEFER_HEAD=0: off)
   int masked;        // KC_FLAG_MASKED_BOARDS: boards may be smaller than nnXLen x nnYLen; input channel 0 (the on-board plane) is the mask
                      // (eigenbackend.cpp:1438) and the pooling divides by each board's own cell count (:141-166)
 };
@@ -470,9 +473,13 @@ __device__ __forceinline__ void stageHeadParams(const TrunkParams& P, const Laye
 
 // params (HC = K::HC head channels, PW = 3 HC): g1BN s[HC] b[HC] | Wpb [PW][HC] | p1BN s[HC] b[HC] | W2 [HC][4] | v1BN s[HC] b[HC] |
 //         Wv2 [PW][V2] | b2 [V2] | Wv3 [V2][2] | b3[2] | Wsv3 [V2][2] | bsv3[2] | Wown [HC]
-template <class K>
-__device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
-                             const uint8_t* sSym, const int nRows) {
+template <class K, bool PART_A, bool PART_B>
+__device__ __forceinline__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const EpiCtx& c, int tileIndex, uint32_t barHead,
+                                             const uint8_t* sSym, const int nRows, const float* par) {
+  // Two parts.  A: everything that reads TMEM or sits between this item and the next one's layers -- pooling, ownership, policy.  B: the
+  // value head (v2 matmul = three round trips to L2, value / misc outputs), which reads shared memory only and, for 32-channel heads,
+  // runs after the next item's first-layer epilogue, i.e. under that item's second layer (TrunkParams::deferHead).
+  static_assert(PART_A || PART_B, "");
   constexpr int HC = K::HC, PW = 3 * HC;
   // 32-channel heads keep p1 in registers and release TMEM region S before the pooled matmuls (the next item's first layer can be issued
   // under the rest of this epilogue); wider heads read p1 from TMEM 16 columns at a time when the policy is formed, and release then
@@ -481,25 +488,36 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   // small parameters were staged in shared memory before the accumulator wait (stageHeadParams): layout of c.par
   //   [0,HC) g1BN s | [HC,2HC) g1BN b | [2HC,3HC) p1BN s | [3HC,4HC) p1BN b | [4HC,8HC) W2 [HC][4] | [8HC,9HC) v1BN s | [9HC,10HC) v1BN b |
   //   [10HC,11HC) Wown | [11HC,11HC+V2) b2 ;  sW3[tile][o][k] = value / misc output matrices, [o][V2] = their biases
-  const float* g1s = c.par;
-  const float* g1b = c.par + HC;
-  const float* p1s = c.par + 2 * HC;
-  const float* p1b = c.par + 3 * HC;
-  const float* W2 = c.par + 4 * HC;
-  const float* v1s = c.par + 8 * HC;
-  const float* v1b = c.par + 9 * HC;
-  const float* Wown = c.par + 10 * HC;
-  const float* b2 = c.par + 11 * HC;
+  const float* g1s = par;
+  const float* g1b = par + HC;
+  const float* p1s = par + 2 * HC;
+  const float* p1b = par + 3 * HC;
+  const float* W2 = par + 4 * HC;
+  const float* v1s = par + 8 * HC;
+  const float* v1b = par + 9 * HC;
+  const float* Wown = par + 10 * HC;
+  const float* b2 = par + 11 * HC;
   const float* Wpb = P.params + L.pOff + 2 * HC;
   const float* Wv2 = Wpb + PW * HC + 2 * HC + 4 * HC + 2 * HC;
   uint32_t src = c.tmemLane + K::MAXC;
   float* pooledG = c.poolA;   // [NB][PW]
   float* pooledV = c.poolB;   // [NB][PW]
+  const bool hp = KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
+  const int gameBase = tileIndex * P.NB;
+  if constexpr(PART_A) {
   float own = 0.f;            // ownership = v1 (after BN / activation / mask) . Wown, formed while v1 passes through the pooling
+  // 32-channel heads: the pooled policy bias is formed by all 128 threads, each one K quarter (24 pooled features) of one output
+  // channel; its weights are requested now and arrive under the pooling
+  constexpr int KQ = PW / 4;
+  const int pbOc = c.e % HC, pbK = c.e / HC;
+  float wpb[EARLY ? KQ : 1];
+  if constexpr(EARLY) {
+#pragma unroll
+    for(int j = 0; j < KQ; j++) wpb[j] = __ldg(Wpb + (size_t)(pbK * KQ + j) * HC + pbOc);
+  }
   // this row's output symmetry, fetched now: a global load takes 1,500+ clk here (L2 is streaming the next item's weights), and the
   // policy stores at the end of this epilogue depend on it
   const int symEarly = (P.sym && tileIndex * P.NB + c.b < nRows) ? P.sym[tileIndex * P.NB + c.b] : 0;
-  const bool hp = KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && tileIndex == 0;
   if(hp) KC_DBG[24] = clock64();
   const bool poolOut = !(c.e & 1) && (c.e >> 1) < P.NB * 16;
   const int pb = c.e >> 5, pj = (c.e >> 1) & 15;
@@ -559,47 +577,29 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     }
     releaseTmem();
   }
-  named_bar_sync(1 + c.t, 128);
-  // pooled matmuls: policy bias (NB*HC outputs) and v2 (NB*V2 outputs)
+  named_bar_sync(1 + c.t, 128);   // pooledG / pooledV complete, the pooling scratch has been read
   if(hp) KC_DBG[26] = clock64();
-  // threads 0..HC-1: policy bias column oc; the others: v2 columns -- both matmuls in flight at once
-  if(c.e < HC) {
+  if constexpr(EARLY) {
+    float part[MAX_NB] = {0.f, 0.f, 0.f, 0.f};
+    pooledFma<KQ>(smem_u32(pooledG), PW, pbK * KQ, wpb, P.NB, part);
+#pragma unroll
+    for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[(pbK * MAX_NB + b) * HC + pbOc] = part[b];   // 4 * MAX_NB * HC <= MAX_NB * MAXC floats
+    named_bar_sync(1 + c.t, 128);
+    // thread (board, channel): the four K quarters summed and folded into p1's normalisation: (p1 + bias) * s + b = p1 * s + (bias * s + b)
+    if(c.e < P.NB * HC) {
+      const float* q4 = c.biasBuf + c.e;   // c.e = board * HC + channel
+      const float bias = (q4[0] + q4[MAX_NB * HC]) + (q4[2 * MAX_NB * HC] + q4[3 * MAX_NB * HC]);
+      c.scr[K::HEAD_ADD_OFF + c.e] = fmaf(bias, p1s[c.e % HC], p1b[c.e % HC]);
+    }
+  } else if(c.e < HC) {
     float acc[MAX_NB];
     pooledMatmul(pooledG, PW, Wpb, PW, HC, c.e, P.NB, acc);
 #pragma unroll
     for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.biasBuf[b * PW + c.e] = acc[b];
-  } else {
-    for(int oc = c.e - HC; oc < V2; oc += 128 - HC) {
-      float acc[MAX_NB];
-      pooledMatmul(pooledV, PW, Wv2, PW, V2, oc, P.NB, acc);
-      const float bias2 = b2[oc];
-#pragma unroll
-      for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = actf(acc[b] + bias2, P.v2Act);
-    }
   }
   if(hp) KC_DBG[27] = clock64();
   named_bar_sync(1 + c.t, 128);
   if(hp) KC_DBG[28] = clock64();
-  const int gameBase = tileIndex * P.NB;
-  {
-    // value / misc outputs: 8 lanes per (board, output), each a slice of k, combined by an xor butterfly
-    const int q = c.e >> 3, seg = c.e & 7;
-    const int b = q >> 2, o = q & 3;
-    float acc = 0.f;
-    if(b < P.NB) {
-      const int kn = V2 >> 3;
-      for(int k = seg * kn; k < (seg + 1) * kn; k++) acc = fmaf(c.v2buf[b * MAX_V2 + k], sW3[c.t][o][k], acc);
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    const int game = gameBase + b;
-    if(seg == 0 && b < P.NB && game < nRows) {
-      acc += sW3[c.t][o][V2];
-      if(o < 2) P.value[(size_t)game * 2 + (o & 1)] = acc; else P.misc[(size_t)game * 2 + (o & 1)] = acc;
-    }
-  }
-  if(hp) KC_DBG[29] = clock64();
   int game = gameBase + c.b;
   if(c.maskRow && !c.valid && c.slotCell >= 0 && gameBase + c.slotB < nRows) {
     // a cell of the nnXLen x nnYLen slot that is off this board: masked p1 / v1 through the bias-free 1x1 output convolutions = 0
@@ -612,12 +612,12 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
   }
   // the policy: p1 + pooled bias -> BN -> activation -> the 1x1 p2 convolution (eigenbackend.cpp:1292-1298).  Every thread runs the loop
   // (the late form reads TMEM warp-wide); only the threads of board cells store.
-  const float* add = c.biasBuf + c.b * PW;
+  const float* add = EARLY ? c.scr + K::HEAD_ADD_OFF + c.b * HC : c.biasBuf + c.b * PW;
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   if constexpr(EARLY) {
 #pragma unroll
     for(int k = 0; k < HC; k++) {
-      float a = actf(fmaf(p1[k] + add[k], p1s[k], p1b[k]), P.p1Act);
+      float a = actf(fmaf(p1[k], p1s[k], add[k]), P.p1Act);   // add = pooled bias * s + b
       float4 w = *(reinterpret_cast<const float4*>(W2) + k);
       o0 = fmaf(a, w.x, o0); o1 = fmaf(a, w.y, o1); o2 = fmaf(a, w.z, o2); o3 = fmaf(a, w.w, o3);
     }
@@ -647,6 +647,34 @@ __device__ void epilogueHead(const TrunkParams& P, const LayerDesc& L, const Epi
     }
     P.own[(size_t)game * P.HW + dst] = own;
   }
+  }   // PART_A
+  if constexpr(PART_B) {
+    for(int oc = c.e; oc < V2; oc += 128) {
+      float acc[MAX_NB];
+      pooledMatmul(pooledV, PW, Wv2, PW, V2, oc, P.NB, acc);
+      const float bias2 = b2[oc];
+#pragma unroll
+      for(int b = 0; b < MAX_NB; b++) if(b < P.NB) c.v2buf[b * MAX_V2 + oc] = actf(acc[b] + bias2, P.v2Act);
+    }
+    named_bar_sync(1 + c.t, 128);
+    // value / misc outputs: 8 lanes per (board, output), each a slice of k, combined by an xor butterfly
+    const int q = c.e >> 3, seg = c.e & 7;
+    const int b = q >> 2, o = q & 3;
+    float acc = 0.f;
+    if(b < P.NB) {
+      const int kn = V2 >> 3;
+      for(int k = seg * kn; k < (seg + 1) * kn; k++) acc = fmaf(c.v2buf[b * MAX_V2 + k], sW3[c.t][o][k], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    const int game = gameBase + b;
+    if(seg == 0 && b < P.NB && game < nRows) {
+      acc += sW3[c.t][o][V2];
+      if(o < 2) P.value[(size_t)game * 2 + (o & 1)] = acc; else P.misc[(size_t)game * 2 + (o & 1)] = acc;
+    }
+    if(hp) KC_DBG[29] = clock64();
+  }   // PART_B
 }
 
 // The MMA issuer of one tile: a whole warp runs the (warp-uniform) control flow and waits on the
@@ -956,6 +984,7 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
     c.v2buf = c.scr + MAX_NB * K::MAXC;
     uint32_t layerCount = 0;
     bool alive = true;
+    int pendingTile = -1;   // tile index of the item whose value head (part B of the head epilogue) is still to run
     stageHeadParams<K::HC>(P, P.layers[P.numLayers - 1], c.e, c.t, sHeadPar[c.t]);   // read after the first layer's named barrier at the earliest
     for(int unit = unit0; unit < numUnits && alive; unit += unitStep) {
       const int item = itemOf(unit);
@@ -1011,9 +1040,23 @@ __global__ void __launch_bounds__(K::REALLOC ? 512 : K::THREADS, 1) trunk_kernel
         if(probeHead) KC_DBG[17] = clock64();
         if(KC_DBG && blockIdx.x == 0 && c.t == 0 && c.e == 0 && (int)layerCount == P.numLayers) KC_DBG[22] = clock64();
         tc_fence_after();
-        if(L.epi == EPI_BN) epilogueBN<K>(P, L, c);
-        else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
-        else epilogueHead<K>(P, L, c, item * NT + c.t, barHead, sSym, nRows);
+        // the head epilogue is two calls: part A here, part B (the value head: shared memory only) either right away or -- 32-channel
+        // heads with another item to come -- after that item's first-layer epilogue, under its second layer.  One call site each: the
+        // code is inlined, and the kernel has to share a 32 KB instruction cache.
+        bool valueHeadNow = false;
+        if(L.epi == EPI_BN) {
+          epilogueBN<K>(P, L, c);
+          valueHeadNow = pendingTile >= 0;
+        } else if(L.epi == EPI_GPOOL) epilogueGPool<K>(P, L, c);
+        else {
+          epilogueHead<K, true, false>(P, L, c, item * NT + c.t, barHead, sSym, nRows, sHeadPar[c.t]);
+          pendingTile = item * NT + c.t;
+          valueHeadNow = !(K::HC <= 32 && P.deferHead && unit + unitStep < numUnits);
+        }
+        if(valueHeadNow) {
+          epilogueHead<K, false, true>(P, P.layers[P.numLayers - 1], c, pendingTile, barHead, sSym, nRows, sHeadPar[c.t]);
+          pendingTile = -1;
+        }
         if(probeHead) KC_DBG[19] = clock64();
         if(tl) tl[4] = clock64();
       }
@@ -1439,6 +1482,8 @@ int runTrunkBf16(kc_handle* h, int n, cudaStream_t st, const int8_t* sym_dev, in
   // tile skew (see TrunkParams::skew): 5 of the 14 ring stages in pair mode, measured +1.5 % burst / +1 % under the power cap
   // (0: 7.165, 2: 7.195, 4: 7.22, 5-8: 7.27-7.285, 10: 7.26 M evals/s); 2 of 7 in the single-CTA kernel; KC_TRUNK_SKEW overrides
   static const int skewEnv = [] { const char* e = getenv("KC_TRUNK_SKEW"); return e ? atoi(e) : -1; }();
+  static const int deferEnv = [] { const char* e = getenv("KC_TRUNK_DEFER_HEAD"); return e ? atoi(e) : 1; }();
+  P.deferHead = deferEnv;
   P.skew = T->cfg != 0 ? 0 : skewEnv >= 0 ? std::min(skewEnv, usePair ? Cfg128P::NSTAGES - 2 : Cfg128::NSTAGES - 2) : usePair ? 2 : 2;
   if(usePair) {
     // clusters of two CTAs (one TPC), cta_group::2 MMAs; a cluster takes two items per round
