@@ -1,9 +1,11 @@
-// The bf16 production path: the whole residual net as ONE persistent tcgen05/TMEM kernel.
+// The tensor-core production path: the whole residual net as ONE persistent tcgen05/TMEM kernel.
 //
 // What it computes is the reference's Model::apply (cpp/neuralnet/eigenbackend.cpp:1420-1472:
-// trunk :1202-1226, blocks :912-930 / :968-1005, policy head :1265-1298, value head :1341-1376) for
-// boards that exactly fill nnXLen x nnYLen (mask == 1, ledger 8.1-M), with bf16 operands and fp32
-// accumulation.  How it computes it is B200-native:
+// trunk :1202-1226, blocks :912-930 / :968-1005, policy head :1265-1298, value head :1341-1376), for
+// boards that fill nnXLen x nnYLen or -- KC_FLAG_MASKED_BOARDS -- smaller ones in that slot, with fp16
+// (default) or bf16 operands and fp32 accumulation.  The bullets describe the basic two-tile form
+// (TrunkCfg<128, 2, 7>); the CTA-pair, 192- and 256-channel forms, the deferred value head and what
+// the epilogues were measured to cost are in DESIGN.md 4.2.  How it computes it is B200-native:
 //
 //  * A CTA owns two 128-row activation tiles (NB boards each, laid side by side with one zero pad
 //    column per board, see net.h) for the whole depth of the net.  Activations never leave the SM:
@@ -24,6 +26,10 @@
 //    published chunk c, so the tensor pipe only idles for the first chunk of every layer.
 //  * Global pooling, the pooled matmuls, both heads, the inverse output symmetry and the final
 //    stores are done by the epilogue warps in fp32 on CUDA cores (they are < 0.5 % of the FLOPs).
+//  * The kernel is far larger than the 32 KB instruction cache, so the per-layer path is kept lean:
+//    once-per-item code is out of line and shared (poolReduce, pooledMatmul4, mishf), each part of
+//    the head epilogue has one call site, and the clock probes of kc_handle_trunk_probe are compiled
+//    into separate instantiations (TrunkCfg::PROBE) that only KC_TRUNK_PROBE=1 launches.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
